@@ -1,0 +1,150 @@
+/* pylogeny_b200 -- C-ABI of the B200-native tree-scoring engine.
+ *
+ * This is the drop-in boundary for Pylogeny's two native extension modules:
+ *   `fitch`          (/root/reference/pylogeny/fitch.cpp, CPython-2 binding :274-346)
+ *   `libpllWrapper`  (/root/reference/pylogeny/libpllWrapper.c, method table :323-339)
+ * Plain pointers and sizes only; no exceptions cross the ABI; every function
+ * returns a status (PLG_OK == 0) and plg_last_error() holds the message of the
+ * last failure on the calling thread.  Handles are opaque and explicitly
+ * destroyed.  Device memory is owned by the handles; `stream` arguments are
+ * cudaStream_t passed as void* (0 = default stream).  There is NO CPU fallback:
+ * without a CUDA device every compute entry point returns PLG_ERR_CUDA.
+ *
+ * The ctypes shim modules pylogeny_b200/fitch.py and pylogeny_b200/libpllWrapper.py
+ * bind exactly these symbols; INTEGRATION.md shows the reference-side stub.
+ */
+#ifndef PYLOGENY_B200_H
+#define PYLOGENY_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLG_OK 0
+#define PLG_ERR_ARG 1         /* bad argument, length mismatch (fitch.cpp:285 returns NULL) */
+#define PLG_ERR_PARSE 2       /* Newick string could not be parsed */
+#define PLG_ERR_LABEL 3       /* leaf label missing from the taxa map (fitch.cpp:255 aborts) */
+#define PLG_ERR_CUDA 4        /* CUDA error or no device */
+#define PLG_ERR_STATES 5      /* more distinct states in one column than the kernels support */
+#define PLG_ERR_UNSUPPORTED 6 /* e.g. non-binary tree handed to a binary-only entry point */
+#define PLG_ERR_IO 7          /* file could not be read (libpllWrapper.c:141-146 IOError) */
+
+#define PLG_MOVE_NNI 2 /* rearrangement.py:27 TYPE_SPR, TYPE_NNI, TYPE_TBR = 1, 2, 3 */
+#define PLG_MOVE_SPR 1
+#define PLG_MOVE_TBR 3
+
+#define PLG_DATA_DNA 4  /* 4 states, tip codes are 4-bit ambiguity masks (A=1,C=2,G=4,T=8) */
+#define PLG_DATA_AA 20  /* 20 states, tip codes 0..19, 20=B, 21=Z, 22=X/-/? */
+
+const char *plg_last_error(void);
+int plg_version(void);
+int plg_device_count(int *count);
+int plg_set_device(int device);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t plg_launch_count(void);
+
+/* ------------------------------------------------------------------ */
+/* Parsimony (replaces fitch.cpp)                                      */
+/* ------------------------------------------------------------------ */
+typedef struct plg_fitch_aln plg_fitch_aln;
+
+/* Device-resident, bit-plane packed pattern set.  `profiles[i]` is the i-th
+ * profile string exactly as scoring.py:134 builds it (one char per alignment
+ * row; fitch.cpp:256 reads profile[taxInd]); weights as parsimony.py:28-46.
+ * Replaces the per-call copy loop fitch.cpp:293-309. */
+int plg_fitch_aln_create(int64_t n_prof, const char *const *profiles,
+                         const int64_t *weights, plg_fitch_aln **out);
+/* Same from a dense row-major [n_prof][n_cols] byte matrix of state symbols. */
+int plg_fitch_aln_create_dense(int64_t n_prof, int n_cols, const uint8_t *states,
+                               const int64_t *weights, plg_fitch_aln **out);
+void plg_fitch_aln_destroy(plg_fitch_aln *aln);
+int plg_fitch_aln_info(const plg_fitch_aln *aln, int64_t *n_prof, int *n_cols, int *n_planes);
+
+/* fitch.calculateCost(newick, profiles, weights, taxa) -> int  (fitch.cpp:274-334).
+ * One-shot: packs + uploads the profiles, scores one tree, frees. k-ary nodes
+ * follow fitch.cpp:215-226/262-264 exactly; result wraps as 32-bit int (:247,268). */
+int plg_fitch_cost(const char *newick, int64_t n_prof, const char *const *profiles,
+                   const int64_t *weights, int n_taxa, const char *const *taxa_names,
+                   const int32_t *taxa_idx, int32_t *out_cost);
+/* Same, against a resident alignment, for many Newick strings at once. */
+int plg_fitch_score_newicks(plg_fitch_aln *aln, int64_t n_trees,
+                            const char *const *newicks, int n_taxa,
+                            const char *const *taxa_names, const int32_t *taxa_idx,
+                            int32_t *out_costs, void *stream);
+/* Batched post-order descriptor (the hot path): n_trees rooted binary trees over
+ * the same n_tips leaves.  desc[t][i][0..1] = children of internal node i of tree
+ * t, nodes in post-order; child id < n_tips is leaf (alignment row tip_rows[id]),
+ * child id >= n_tips is internal node (id - n_tips) of the same tree; the root is
+ * internal node n_tips-2.  Scores to host memory. */
+int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_tips,
+                          const int32_t *desc, const int32_t *tip_rows,
+                          int32_t *out_costs, void *stream);
+
+/* Whole rearrangement neighbourhood of one rooted binary base tree (descriptor as
+ * above, n_tips-1 internal nodes).  Enumerates every distinct neighbour topology
+ * (NNI: 2(n-3); SPR: 2(n-3)(2n-7)) and scores each by edge-insertion Fitch
+ * (exact for binary trees: Fitch length is root-invariant).  Moves are returned
+ * as (prune_node, regraft_node) pairs naming the child end of the pruned /
+ * target branch in the base tree's node ids.  Call with out_* == NULL to get
+ * the count.  Replaces the per-neighbour loop landscape.py:724-756. */
+int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, int n_tips,
+                                  const int32_t *desc, const int32_t *tip_rows,
+                                  int64_t shard_index, int64_t shard_count,
+                                  int64_t *n_moves, int32_t *out_moves,
+                                  int32_t *out_costs, void *stream);
+
+/* ------------------------------------------------------------------ */
+/* Likelihood (replaces libpllWrapper.c + the libpll calls it makes)   */
+/* ------------------------------------------------------------------ */
+typedef struct plg_lik_aln plg_lik_aln;
+typedef struct plg_model plg_model;
+
+/* Tip codes, row-major [n_rows][n_patterns] (1 byte per cell), pattern weights. */
+int plg_lik_aln_create(int datatype, int n_rows, int64_t n_patterns, const uint8_t *codes,
+                       const double *weights, plg_lik_aln **out);
+void plg_lik_aln_destroy(plg_lik_aln *aln);
+
+/* Reversible model + discrete Gamma (Yang 1994 mean categories).  exch: K(K-1)/2
+ * exchangeabilities (upper triangle, row-major), freqs: K.  What pllInitModel
+ * sets up at libpllWrapper.c:159. */
+int plg_model_create(int n_states, const double *exch, const double *freqs, double alpha,
+                     int n_cat, plg_model **out);
+void plg_model_destroy(plg_model *m);
+int plg_model_gamma_rates(const plg_model *m, double *rates /*[n_cat]*/);
+/* P(t) on the host from the model's eigensystem, row-major K*K (for tests). */
+int plg_model_pmatrix(const plg_model *m, double t, double *out);
+
+/* Batched fixed-branch-length log-likelihood: descriptor as for
+ * plg_fitch_score_trees plus brlen[t][i][0..1] = lengths of the two child
+ * branches of internal node i.  out_lnl[t] on the host. */
+int plg_lik_score_trees(plg_lik_aln *aln, plg_model *m, int64_t n_trees, int n_tips,
+                        const int32_t *desc, const double *brlen, const int32_t *tip_rows,
+                        double *out_lnl, void *stream);
+
+/* lnL of every distinct SPR/NNI neighbour of one base tree at fixed branch lengths.
+ * Neighbour branch lengths follow rearrangement.py:466-486 (target branch split in
+ * half, the two branches left at the pruned node merged by summing). */
+int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int move_type, int n_tips,
+                                const int32_t *desc, const double *brlen,
+                                const int32_t *tip_rows, int64_t shard_index,
+                                int64_t shard_count, int64_t *n_moves, int32_t *out_moves,
+                                double *out_lnl, void *stream);
+
+/* ---- libpllWrapper compat (libpllWrapper.c:97-239): opaque problem handle ---- */
+typedef struct plg_pll plg_pll;
+/* new(alignment_file, newick, partition_file) -- PHYLIP file, unrooted Newick,
+ * partition file "DNA, p1 = 1-N" | "WAG, p1 = 1-N" (pll.py:112-115). */
+int plg_pll_new(const char *phylip_path, const char *newick, const char *partition_path,
+                plg_pll **out);
+int plg_pll_destroy(plg_pll *p);
+/* getLogLikelihood(handle): branch-length smoothing (3 passes) then lnL (:195-215). */
+int plg_pll_loglik(plg_pll *p, double *out);
+/* getNewickString(handle) (:217-239); returns needed size in *len when buf too small. */
+int plg_pll_newick(plg_pll *p, char *buf, size_t *len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

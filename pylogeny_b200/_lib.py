@@ -1,0 +1,56 @@
+"""ctypes binding of include/pylogeny_b200.h.  Fails loudly: there is no CPU fallback."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpylogeny_b200.so")
+
+OK, ERR_ARG, ERR_PARSE, ERR_LABEL, ERR_CUDA, ERR_STATES, ERR_UNSUPPORTED, ERR_IO = range(8)
+MOVE_SPR, MOVE_NNI, MOVE_TBR = 1, 2, 3
+DATA_DNA, DATA_AA = 4, 20
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "pylogeny_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built (python -m pylogeny_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: run `python -m pylogeny_b200.build` (needs nvcc); "
+                              "pylogeny_b200 has no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise EngineError(rc, lib().plg_last_error().decode(errors="replace"))
+
+
+def _declare(L):
+    i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    strs = C.POINTER(C.c_char_p)
+    vp = C.c_void_p
+    L.plg_last_error.restype = C.c_char_p
+    L.plg_last_error.argtypes = []
+    L.plg_version.restype = C.c_int
+    L.plg_launch_count.restype = C.c_int64
+    L.plg_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.plg_set_device.argtypes = [C.c_int]
+    L.plg_fitch_aln_create.argtypes = [C.c_int64, strs, i64p, C.POINTER(vp)]
+    L.plg_fitch_aln_create_dense.argtypes = [C.c_int64, C.c_int, vp, vp, C.POINTER(vp)]
+    L.plg_fitch_aln_destroy.argtypes = [vp]
+    L.plg_fitch_aln_destroy.restype = None
+    L.plg_fitch_aln_info.argtypes = [vp, i64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.plg_fitch_cost.argtypes = [C.c_char_p, C.c_int64, strs, i64p, C.c_int, strs, i32p, i32p]
+    L.plg_fitch_score_newicks.argtypes = [vp, C.c_int64, strs, C.c_int, strs, i32p, vp, vp]
+    L.plg_fitch_score_trees.argtypes = [vp, C.c_int64, C.c_int, vp, vp, vp, vp]

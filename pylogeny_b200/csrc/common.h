@@ -1,0 +1,101 @@
+// Shared host-side plumbing for the C-ABI library: error reporting, CUDA checks.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pylogeny_b200.h"
+
+namespace plg {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+// Thrown inside the library, always caught at the extern "C" boundary.
+struct Error {
+  int code;
+};
+
+#define PLG_CUDA(call)                                                               \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      plg::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                     __LINE__);                                                      \
+      throw plg::Error{PLG_ERR_CUDA};                                                \
+    }                                                                                \
+  } while (0)
+
+#define PLG_FAIL(code, ...)        \
+  do {                             \
+    plg::set_error(__VA_ARGS__);   \
+    throw plg::Error{code};        \
+  } while (0)
+
+#define PLG_API_BEGIN try {
+#define PLG_API_END                                    \
+  }                                                    \
+  catch (const plg::Error &e) { return e.code; }       \
+  catch (const std::bad_alloc &) {                     \
+    plg::set_error("out of host memory");              \
+    return PLG_ERR_ARG;                                \
+  }                                                    \
+  catch (...) {                                        \
+    plg::set_error("unexpected C++ exception");        \
+    return PLG_ERR_ARG;                                \
+  }                                                    \
+  return PLG_OK;
+
+inline void count_launch(int64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Owning device buffer.
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    release();
+    if (count == 0) return;
+    PLG_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    n = count;
+  }
+};
+
+// Owning pinned host buffer (async H2D/D2H staging).
+template <typename T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  PinBuf() = default;
+  PinBuf(const PinBuf &) = delete;
+  PinBuf &operator=(const PinBuf &) = delete;
+  ~PinBuf() {
+    if (p) cudaFreeHost(p);
+  }
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    if (count == 0) return;
+    PLG_CUDA(cudaMallocHost((void **)&p, count * sizeof(T)));
+    n = count;
+  }
+};
+
+}  // namespace plg

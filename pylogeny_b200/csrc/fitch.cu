@@ -1,0 +1,522 @@
+// Fitch small parsimony on sm_100a: bit-plane state sets, level-synchronous op programs.
+//
+// Replaces cost() and the string-set helpers of the reference
+// (/root/reference/pylogeny/fitch.cpp:197-272).  Data layout in HBM:
+//
+//   state-set vector of one node = K bit-planes over the P patterns,
+//   [plane][W4] uint4, W4 = ceil(P/128) (every plane is a whole number of 128-bit
+//   words so all accesses are 16-byte vectorised and coalesced).  Bit i of plane s
+//   is set iff state s is in the node's set at pattern i.  Tips (one vector per
+//   alignment row) are read-only; internal vectors live in a scratch pool.
+//
+//   Patterns are re-ordered by weight (descending).  Weights are bit-sliced:
+//   wbits[b][W4] holds bit b of every pattern weight, so a weighted miss count is
+//   sum_b popc(miss & wbits[b]) << b -- integer, order-independent, hence
+//   bit-exact with fitch.cpp:268 including its 32-bit wrap-around.  128-pattern
+//   chunks whose weights are all 1 (the long tail after sorting) skip the loads.
+//
+// One "op" = one internal node: fold over its children with the reference's
+// restarting intersection (fitch.cpp:215-226), union on empty (:262-264), cost
+// (k-1) per missed pattern.  Ops of the same level are independent and run in one
+// launch; a thread owns one 128/64/32-pattern column of all K planes.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "fitch.h"
+
+namespace plg {
+
+// ----------------------------------------------------------------------------
+// device
+// ----------------------------------------------------------------------------
+template <int VW>
+struct VecT;
+template <>
+struct VecT<4> { using type = uint4; };
+template <>
+struct VecT<2> { using type = uint2; };
+template <>
+struct VecT<1> { using type = unsigned int; };
+
+template <int VW>
+__device__ __forceinline__ void load_vec(const unsigned int *p, unsigned int (&v)[VW]) {
+  if constexpr (VW == 4) {
+    uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (VW == 2) {
+    uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+
+template <int VW>
+__device__ __forceinline__ void store_vec(unsigned int *p, const unsigned int (&v)[VW]) {
+  if constexpr (VW == 4) *reinterpret_cast<uint4 *>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+  else if constexpr (VW == 2) *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1]);
+  else p[0] = v[0];
+}
+
+// words32: 32-bit words per plane (= 4*W4).  cols_per_op = words32 / VW.
+template <int K, int VW>
+__global__ void __launch_bounds__(256)
+fitch_level_kernel(const unsigned int *__restrict__ tips, unsigned int *__restrict__ scratch,
+                   int n_tip_slots, const FitchOp *__restrict__ ops,
+                   const int *__restrict__ children, int64_t words32, int blocks_per_op,
+                   const unsigned int *__restrict__ wbits, const unsigned char *__restrict__ chunk_nb,
+                   unsigned int *__restrict__ cost) {
+  const int op_idx = blockIdx.x / blocks_per_op;
+  const int cb = blockIdx.x - op_idx * blocks_per_op;
+  const FitchOp op = ops[op_idx];
+  const int64_t col = (int64_t)cb * blockDim.x + threadIdx.x;  // VW-word column
+  const int64_t w0 = col * VW;                                   // first 32-bit word
+  const int64_t vec_words = (int64_t)K * words32;
+  unsigned int partial = 0;
+  if (w0 < words32) {
+    unsigned int acc[K][VW], orr[K][VW];
+    {
+      const int c0 = children[op.child_off];
+      const unsigned int *src = (c0 < n_tip_slots ? tips + (int64_t)c0 * vec_words
+                                                  : scratch + (int64_t)(c0 - n_tip_slots) * vec_words) + w0;
+#pragma unroll
+      for (int s = 0; s < K; s++) {
+        load_vec<VW>(src + s * words32, acc[s]);
+#pragma unroll
+        for (int v = 0; v < VW; v++) orr[s][v] = acc[s][v];
+      }
+    }
+    for (int j = 1; j < op.nchild; j++) {
+      const int cj = children[op.child_off + j];
+      const unsigned int *src = (cj < n_tip_slots ? tips + (int64_t)cj * vec_words
+                                                  : scratch + (int64_t)(cj - n_tip_slots) * vec_words) + w0;
+      unsigned int x[K][VW];
+#pragma unroll
+      for (int s = 0; s < K; s++) load_vec<VW>(src + s * words32, x[s]);
+      unsigned int empty[VW];
+#pragma unroll
+      for (int v = 0; v < VW; v++) {
+        unsigned int any = 0;
+#pragma unroll
+        for (int s = 0; s < K; s++) any |= acc[s][v];
+        empty[v] = ~any;
+      }
+#pragma unroll
+      for (int s = 0; s < K; s++)
+#pragma unroll
+        for (int v = 0; v < VW; v++) {
+          // running intersection that restarts from the child when empty (fitch.cpp:221-222)
+          acc[s][v] = (acc[s][v] | empty[v]) & x[s][v];
+          orr[s][v] |= x[s][v];
+        }
+    }
+    unsigned int miss[VW];
+#pragma unroll
+    for (int v = 0; v < VW; v++) {
+      unsigned int any = 0;
+#pragma unroll
+      for (int s = 0; s < K; s++) any |= acc[s][v];
+      miss[v] = ~any;
+    }
+    if (op.dst >= 0) {
+      unsigned int *dst = scratch + (int64_t)(op.dst - n_tip_slots) * vec_words + w0;
+#pragma unroll
+      for (int s = 0; s < K; s++) {
+        unsigned int o[VW];
+#pragma unroll
+        for (int v = 0; v < VW; v++) o[v] = acc[s][v] | (miss[v] & orr[s][v]);  // union on empty (:262-263)
+        store_vec<VW>(dst + s * words32, o);
+      }
+    }
+    // weighted miss count
+    const unsigned int nb = chunk_nb[w0 >> 2];
+    if (nb == 0xFFu) {
+#pragma unroll
+      for (int v = 0; v < VW; v++) partial += __popc(miss[v]);
+    } else {
+      for (unsigned int b = 0; b < nb; b++) {
+        unsigned int wv[VW];
+        load_vec<VW>(wbits + (int64_t)b * words32 + w0, wv);
+        unsigned int c = 0;
+#pragma unroll
+        for (int v = 0; v < VW; v++) c += __popc(miss[v] & wv[v]);
+        partial += c << b;
+      }
+    }
+    partial *= (unsigned int)(op.nchild - 1);  // numChildren-1 per missed pattern (:264)
+  }
+  // block reduction -> one integer atomic per block (order-independent => deterministic)
+  partial = __reduce_add_sync(0xffffffffu, partial);
+  __shared__ unsigned int warp_sums[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_sums[warp] = partial;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned int v = lane < (blockDim.x + 31) / 32 ? warp_sums[lane] : 0;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (lane == 0 && v) atomicAdd(cost + op.tree, v);
+  }
+}
+
+// Packs a dense [P][n_cols] symbol matrix (already permuted by weight on the host
+// through `order`) into bit-planes on the device: thread = (row, 32-pattern word).
+__global__ void fitch_pack_kernel(const unsigned char *__restrict__ states, const int *__restrict__ order,
+                                  int64_t P, int n_cols, int K, int64_t words32,
+                                  unsigned int *__restrict__ tips) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (w >= words32) return;
+  unsigned int planes[FITCH_MAX_PLANES];
+  for (int s = 0; s < K; s++) planes[s] = 0;
+  for (int b = 0; b < 32; b++) {
+    const int64_t p = w * 32 + b;
+    int st = 0;  // padding patterns: every row in state 0 -> never a miss
+    if (p < P) {
+      // canonical relabel within the pattern: rank of first appearance among rows
+      const unsigned char *colp = states + (int64_t)order[p] * n_cols;
+      const unsigned char me = colp[row];
+      int rank = 0;
+      for (int r = 0; r < row; r++) {
+        const unsigned char c = colp[r];
+        if (c == me) break;
+        bool first = true;
+        for (int q = 0; q < r; q++) if (colp[q] == c) { first = false; break; }
+        rank += first;
+      }
+      // rows before the first occurrence of `me` contributed `rank` distinct symbols
+      st = rank;
+    }
+    planes[st] |= 1u << b;
+  }
+  for (int s = 0; s < K; s++) tips[((int64_t)row * K + s) * words32 + w] = planes[s];
+}
+
+// ----------------------------------------------------------------------------
+// host: alignment
+// ----------------------------------------------------------------------------
+static int pick_template_planes(int K) {
+  static const int opts[] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 20};
+  for (int o : opts)
+    if (K <= o) return o;
+  return -1;
+}
+
+FitchAln::FitchAln(int64_t n_prof, int n_cols_, const uint8_t *states, const int64_t *weights) {
+  P = n_prof;
+  n_cols = n_cols_;
+  if (P < 0 || n_cols <= 0) PLG_FAIL(PLG_ERR_ARG, "alignment needs n_prof >= 0 and n_cols > 0");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+    PLG_FAIL(PLG_ERR_CUDA, "no CUDA device: pylogeny_b200 has no CPU fallback");
+  // distinct symbols per pattern -> number of planes
+  int kmax = 1;
+  for (int64_t p = 0; p < P; p++) {
+    bool seen[256] = {false};
+    int k = 0;
+    const uint8_t *colp = states + p * n_cols;
+    for (int r = 0; r < n_cols; r++)
+      if (!seen[colp[r]]) { seen[colp[r]] = true; k++; }
+    kmax = std::max(kmax, k);
+  }
+  K_real = kmax;
+  K = pick_template_planes(kmax);
+  if (K < 0)
+    PLG_FAIL(PLG_ERR_STATES, "a pattern has %d distinct states; at most %d are supported", kmax,
+             FITCH_MAX_PLANES);
+  W4 = std::max<int64_t>(1, (P + 127) / 128);
+  words32 = W4 * 4;
+  // weight order (descending by low 32 bits: the cost is taken mod 2^32, fitch.cpp:247,268)
+  std::vector<int> order(P);
+  std::iota(order.begin(), order.end(), 0);
+  std::vector<uint32_t> w32(P);
+  for (int64_t p = 0; p < P; p++) w32[p] = (uint32_t)(uint64_t)weights[p];
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return w32[a] > w32[b]; });
+  // bit-sliced weights + per-128-chunk plane count
+  std::vector<uint8_t> nb(W4, 0xFF);
+  int B = 0;
+  for (int64_t c = 0; c < W4; c++) {
+    uint32_t mx = 0;
+    bool unit = true;
+    for (int64_t p = c * 128; p < std::min<int64_t>(P, c * 128 + 128); p++) {
+      uint32_t w = w32[order[p]];
+      mx = std::max(mx, w);
+      unit = unit && w == 1;
+    }
+    if (!unit) {
+      int bits = 0;
+      while (bits < 32 && (mx >> bits)) bits++;
+      nb[c] = (uint8_t)bits;
+      B = std::max(B, bits);
+    }
+  }
+  n_wbits = B;
+  std::vector<uint32_t> wb((size_t)std::max(B, 1) * words32, 0);
+  for (int64_t p = 0; p < P; p++) {
+    uint32_t w = w32[order[p]];
+    for (int b = 0; b < B; b++)
+      if (w >> b & 1) wb[(size_t)b * words32 + (p >> 5)] |= 1u << (p & 31);
+  }
+  tips.alloc((size_t)n_cols * K * words32);
+  wbits.alloc(wb.size());
+  chunk_nb.alloc(W4);
+  PLG_CUDA(cudaMemcpy(wbits.p, wb.data(), wb.size() * 4, cudaMemcpyHostToDevice));
+  PLG_CUDA(cudaMemcpy(chunk_nb.p, nb.data(), W4, cudaMemcpyHostToDevice));
+  // pack on the device
+  DevBuf<unsigned char> d_states;
+  DevBuf<int> d_order;
+  d_states.alloc(std::max<size_t>(1, (size_t)P * n_cols));
+  d_order.alloc(std::max<size_t>(1, P));
+  if (P) {
+    PLG_CUDA(cudaMemcpy(d_states.p, states, (size_t)P * n_cols, cudaMemcpyHostToDevice));
+    PLG_CUDA(cudaMemcpy(d_order.p, order.data(), (size_t)P * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  dim3 grid((unsigned)((words32 + 127) / 128), (unsigned)n_cols);
+  fitch_pack_kernel<<<grid, 128>>>(d_states.p, d_order.p, P, n_cols, K, words32, tips.p);
+  count_launch();
+  PLG_CUDA(cudaGetLastError());
+  PLG_CUDA(cudaDeviceSynchronize());
+}
+
+// ----------------------------------------------------------------------------
+// host: program construction and execution
+// ----------------------------------------------------------------------------
+void FitchProgram::clear() {
+  ops.clear();
+  children.clear();
+  level_off.clear();
+  n_scratch_slots = 0;
+  n_costs = 0;
+}
+
+// Full re-traversal of trees [t0, t1) of a batch: every internal node is one op.
+void build_full_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_tip_slots, FitchProgram &prog) {
+  prog.clear();
+  const int64_t n0 = b.node_off[t0], n1 = b.node_off[t1];
+  const int64_t n_ops = n1 - n0;
+  std::vector<int> level(n_ops);
+  int max_level = 0;
+  for (int64_t t = t0; t < t1; t++) {
+    const int64_t base = b.node_off[t];
+    for (int64_t x = base; x < b.node_off[t + 1]; x++) {
+      int lv = 0;
+      for (int64_t c = b.child_off[x]; c < b.child_off[x + 1]; c++) {
+        int32_t ch = b.child[c];
+        if (ch < 0) lv = std::max(lv, level[base + (-ch - 1) - n0] + 1);
+      }
+      level[x - n0] = lv;
+      max_level = std::max(max_level, lv);
+    }
+  }
+  prog.level_off.assign(max_level + 2, 0);
+  for (int64_t i = 0; i < n_ops; i++) prog.level_off[level[i] + 1]++;
+  for (int l = 0; l <= max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+  std::vector<int64_t> cursor(prog.level_off.begin(), prog.level_off.end() - 1);
+  prog.ops.resize(n_ops);
+  prog.children.resize(b.child_off[n1] - b.child_off[n0]);
+  const int64_t c_base = b.child_off[n0];
+  for (int64_t t = t0; t < t1; t++) {
+    const int64_t base = b.node_off[t], end = b.node_off[t + 1];
+    for (int64_t x = base; x < end; x++) {
+      FitchOp op;
+      op.tree = (int)(t - t0);
+      op.nchild = (int)(b.child_off[x + 1] - b.child_off[x]);
+      op.child_off = (int)(b.child_off[x] - c_base);
+      op.dst = (x == end - 1) ? -1 : (int)(n_tip_slots + (x - n0));  // roots are not stored
+      for (int64_t c = b.child_off[x]; c < b.child_off[x + 1]; c++) {
+        int32_t ch = b.child[c];
+        // (rows beyond the alignment only occur with zero patterns; clamp keeps the address valid)
+        prog.children[c - c_base] =
+            ch >= 0 ? std::min(ch, n_tip_slots - 1) : (int)(n_tip_slots + (base - n0) + (-ch - 1));
+      }
+      prog.ops[cursor[level[x - n0]]++] = op;
+    }
+  }
+  prog.n_scratch_slots = n_ops;
+  prog.n_costs = t1 - t0;
+}
+
+template <int K, int VW>
+static void launch_level(const FitchAln &a, FitchWorkspace &ws, int64_t op0, int64_t n_ops, cudaStream_t st) {
+  const int64_t cols = a.words32 / VW;
+  // block size: multiple of 32 in [64,256] wasting the fewest lanes
+  int best_t = 256;
+  int64_t best_waste = INT64_MAX;
+  for (int t = 256; t >= 64; t -= 32) {
+    int64_t blocks = (cols + t - 1) / t;
+    int64_t waste = blocks * t - cols;
+    if (waste < best_waste) { best_waste = waste; best_t = t; }
+  }
+  const int64_t bpo = (cols + best_t - 1) / best_t;
+  const int64_t max_ops_per_launch = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
+  for (int64_t o = 0; o < n_ops; o += max_ops_per_launch) {
+    const int64_t cnt = std::min(max_ops_per_launch, n_ops - o);
+    fitch_level_kernel<K, VW><<<(unsigned)(cnt * bpo), best_t, 0, st>>>(
+        a.tips.p, ws.scratch.p, a.n_cols, ws.ops.p + op0 + o, ws.children.p, a.words32, (int)bpo,
+        a.wbits.p, a.chunk_nb.p, ws.cost.p);
+    count_launch();
+  }
+}
+
+void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram &prog, int32_t *out_costs,
+                       cudaStream_t st) {
+  const size_t vec_words = (size_t)a.K * a.words32;
+  ws.scratch.alloc(std::max<size_t>(1, (size_t)prog.n_scratch_slots * vec_words));
+  ws.ops.alloc(std::max<size_t>(1, prog.ops.size()));
+  ws.children.alloc(std::max<size_t>(1, prog.children.size()));
+  ws.cost.alloc(std::max<size_t>(1, (size_t)prog.n_costs));
+  if (!prog.ops.empty()) {
+    PLG_CUDA(cudaMemcpyAsync(ws.ops.p, prog.ops.data(), prog.ops.size() * sizeof(FitchOp), cudaMemcpyHostToDevice, st));
+    PLG_CUDA(cudaMemcpyAsync(ws.children.p, prog.children.data(), prog.children.size() * sizeof(int),
+                             cudaMemcpyHostToDevice, st));
+  }
+  PLG_CUDA(cudaMemsetAsync(ws.cost.p, 0, std::max<size_t>(1, (size_t)prog.n_costs) * sizeof(unsigned int), st));
+  for (size_t l = 0; l + 1 < prog.level_off.size(); l++) {
+    const int64_t o0 = prog.level_off[l], cnt = prog.level_off[l + 1] - o0;
+    if (!cnt) continue;
+    switch (a.K) {
+      case 2: launch_level<2, 4>(a, ws, o0, cnt, st); break;
+      case 3: launch_level<3, 4>(a, ws, o0, cnt, st); break;
+      case 4: launch_level<4, 4>(a, ws, o0, cnt, st); break;
+      case 5: launch_level<5, 4>(a, ws, o0, cnt, st); break;
+      case 6: launch_level<6, 4>(a, ws, o0, cnt, st); break;
+      case 8: launch_level<8, 2>(a, ws, o0, cnt, st); break;
+      case 10: launch_level<10, 2>(a, ws, o0, cnt, st); break;
+      case 12: launch_level<12, 1>(a, ws, o0, cnt, st); break;
+      case 16: launch_level<16, 1>(a, ws, o0, cnt, st); break;
+      case 20: launch_level<20, 1>(a, ws, o0, cnt, st); break;
+      default: PLG_FAIL(PLG_ERR_STATES, "no kernel for %d planes", a.K);
+    }
+  }
+  PLG_CUDA(cudaGetLastError());
+  if (out_costs && prog.n_costs) {
+    PLG_CUDA(cudaMemcpyAsync(out_costs, ws.cost.p, (size_t)prog.n_costs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PLG_CUDA(cudaStreamSynchronize(st));
+  }
+}
+
+// Scores every tree of a batch by full re-traversal, splitting it so the scratch
+// pool stays inside the memory budget.
+void score_batch_full(FitchAln &a, const TreeBatch &b, int32_t *out_costs, cudaStream_t st) {
+  const int64_t n_trees = b.n_trees();
+  if (n_trees == 0) return;
+  size_t free_b = 0, total_b = 0;
+  PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t vec_bytes = (size_t)a.K * a.words32 * 4;
+  // scratch budget: half of what is free (counting the pool we already hold), capped at 48 GiB
+  const size_t budget = std::min<size_t>((free_b + a.ws.scratch.n * 4) / 2, (size_t)48 << 30);
+  const int64_t max_slots = std::max<int64_t>(1, (int64_t)(budget / vec_bytes));
+  FitchProgram prog;
+  int64_t t0 = 0;
+  while (t0 < n_trees) {
+    int64_t t1 = t0 + 1;  // a single over-budget tree is still attempted; cudaMalloc reports failure
+    while (t1 < n_trees && b.node_off[t1 + 1] - b.node_off[t0] <= max_slots) t1++;
+    build_full_program(b, t0, t1, a.n_cols, prog);
+    run_fitch_program(a, a.ws, prog, out_costs + t0, st);
+    t0 = t1;
+  }
+}
+
+}  // namespace plg
+
+// ----------------------------------------------------------------------------
+// C-ABI
+// ----------------------------------------------------------------------------
+using namespace plg;
+
+struct plg_fitch_aln {
+  FitchAln impl;
+  plg_fitch_aln(int64_t P, int n_cols, const uint8_t *s, const int64_t *w) : impl(P, n_cols, s, w) {}
+};
+
+static std::vector<uint8_t> gather_profiles(int64_t n_prof, const char *const *profiles, int *n_cols) {
+  size_t mn = SIZE_MAX;
+  for (int64_t i = 0; i < n_prof; i++) {
+    if (!profiles[i]) PLG_FAIL(PLG_ERR_ARG, "profile %lld is NULL", (long long)i);
+    mn = std::min(mn, strlen(profiles[i]));
+  }
+  if (n_prof == 0) mn = 1;  // no patterns: every tree costs 0 (fitch.cpp:249 loop is empty)
+  if (mn == 0) PLG_FAIL(PLG_ERR_ARG, "empty profile string");
+  *n_cols = (int)mn;
+  std::vector<uint8_t> dense((size_t)n_prof * mn);
+  for (int64_t i = 0; i < n_prof; i++) memcpy(dense.data() + (size_t)i * mn, profiles[i], mn);
+  return dense;
+}
+
+extern "C" int plg_fitch_aln_create_dense(int64_t n_prof, int n_cols, const uint8_t *states,
+                                          const int64_t *weights, plg_fitch_aln **out) {
+  PLG_API_BEGIN
+  if (!out || (n_prof > 0 && (!states || !weights))) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  *out = new plg_fitch_aln(n_prof, n_cols, states, weights);
+  PLG_API_END
+}
+
+extern "C" int plg_fitch_aln_create(int64_t n_prof, const char *const *profiles, const int64_t *weights,
+                                    plg_fitch_aln **out) {
+  PLG_API_BEGIN
+  if (!out || (n_prof > 0 && (!profiles || !weights))) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  int n_cols = 0;
+  std::vector<uint8_t> dense = gather_profiles(n_prof, profiles, &n_cols);
+  *out = new plg_fitch_aln(n_prof, n_cols, dense.data(), weights);
+  PLG_API_END
+}
+
+extern "C" void plg_fitch_aln_destroy(plg_fitch_aln *aln) { delete aln; }
+
+extern "C" int plg_fitch_aln_info(const plg_fitch_aln *aln, int64_t *n_prof, int *n_cols, int *n_planes) {
+  PLG_API_BEGIN
+  if (!aln) PLG_FAIL(PLG_ERR_ARG, "null alignment handle");
+  if (n_prof) *n_prof = aln->impl.P;
+  if (n_cols) *n_cols = aln->impl.n_cols;
+  if (n_planes) *n_planes = aln->impl.K;
+  PLG_API_END
+}
+
+static void check_rows(const FitchAln &a, const TreeBatch &b) {
+  if (a.P == 0) return;  // no patterns: rows are never read (fitch.cpp:249 loop body never runs)
+  for (int32_t c : b.child)
+    if (c >= a.n_cols)
+      PLG_FAIL(PLG_ERR_ARG, "taxon index %d is outside the profile length %d (fitch.cpp:256 substr would throw)",
+               c, a.n_cols);
+}
+
+extern "C" int plg_fitch_score_newicks(plg_fitch_aln *aln, int64_t n_trees, const char *const *newicks,
+                                       int n_taxa, const char *const *taxa_names, const int32_t *taxa_idx,
+                                       int32_t *out_costs, void *stream) {
+  PLG_API_BEGIN
+  if (!aln || !out_costs || (n_trees > 0 && !newicks) || (n_taxa > 0 && (!taxa_names || !taxa_idx)))
+    PLG_FAIL(PLG_ERR_ARG, "null argument");
+  TaxaMap taxa(n_taxa, taxa_names, taxa_idx);
+  TreeBatch b;
+  for (int64_t t = 0; t < n_trees; t++) append_tree(b, parse_newick(newicks[t]), taxa, false);
+  check_rows(aln->impl, b);
+  score_batch_full(aln->impl, b, out_costs, (cudaStream_t)stream);
+  PLG_API_END
+}
+
+extern "C" int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_tips, const int32_t *desc,
+                                     const int32_t *tip_rows, int32_t *out_costs, void *stream) {
+  PLG_API_BEGIN
+  if (!aln || !out_costs || (n_trees > 0 && !desc)) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  TreeBatch b = batch_from_desc(n_trees, n_tips, desc, nullptr, tip_rows);
+  check_rows(aln->impl, b);
+  score_batch_full(aln->impl, b, out_costs, (cudaStream_t)stream);
+  PLG_API_END
+}
+
+extern "C" int plg_fitch_cost(const char *newick, int64_t n_prof, const char *const *profiles,
+                              const int64_t *weights, int n_taxa, const char *const *taxa_names,
+                              const int32_t *taxa_idx, int32_t *out_cost) {
+  PLG_API_BEGIN
+  if (!newick || !out_cost) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  // parse + resolve labels first: a bad tree must fail before any device work
+  TaxaMap taxa(n_taxa, taxa_names, taxa_idx);
+  TreeBatch b;
+  append_tree(b, parse_newick(newick), taxa, false);
+  int n_cols = 0;
+  std::vector<uint8_t> dense = gather_profiles(n_prof, profiles, &n_cols);
+  FitchAln a(n_prof, n_cols, dense.data(), weights);
+  check_rows(a, b);
+  score_batch_full(a, b, out_cost, 0);
+  PLG_API_END
+}

@@ -1,0 +1,52 @@
+// Fitch parsimony engine: device-resident alignment, op programs, executor.
+#pragma once
+#include "common.h"
+#include "tree.h"
+
+namespace plg {
+
+constexpr int FITCH_MAX_PLANES = 20;
+
+// One internal node = one op (16 bytes, read once per block).
+struct FitchOp {
+  int dst;        // slot to store the node's state set, -1 = do not store (roots, pure cost ops)
+  int nchild;     // children folded in list order (fitch.cpp:215-226)
+  int child_off;  // into the children[] slot array
+  int tree;       // index of the cost accumulator this op adds to
+};
+
+struct FitchWorkspace {
+  DevBuf<unsigned int> scratch;  // internal-node vectors, slot-major
+  DevBuf<FitchOp> ops;
+  DevBuf<int> children;
+  DevBuf<unsigned int> cost;
+};
+
+struct FitchAln {
+  int64_t P = 0;        // patterns
+  int n_cols = 0;       // alignment rows = tip slots
+  int K = 0, K_real = 0;  // planes allocated (template instance) / distinct states seen
+  int64_t W4 = 0, words32 = 0;
+  int n_wbits = 0;
+  DevBuf<unsigned int> tips;      // [n_cols][K][words32]
+  DevBuf<unsigned int> wbits;     // [n_wbits][words32]
+  DevBuf<unsigned char> chunk_nb; // [W4] weight bit-planes per 128-pattern chunk, 0xFF = all weights 1
+  FitchWorkspace ws;
+  FitchAln(int64_t n_prof, int n_cols, const uint8_t *states, const int64_t *weights);
+};
+
+struct FitchProgram {
+  std::vector<FitchOp> ops;        // sorted by level
+  std::vector<int> children;       // slot ids: < n_cols tip row, else n_cols + scratch slot
+  std::vector<int64_t> level_off;  // [n_levels+1] into ops
+  int64_t n_scratch_slots = 0;
+  int64_t n_costs = 0;
+  void clear();
+};
+
+void build_full_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_tip_slots, FitchProgram &prog);
+void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram &prog, int32_t *out_costs,
+                       cudaStream_t st);
+void score_batch_full(FitchAln &a, const TreeBatch &b, int32_t *out_costs, cudaStream_t st);
+
+}  // namespace plg

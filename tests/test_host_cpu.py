@@ -1,0 +1,117 @@
+"""CPU-side checks: host logic (profile_set, alignment reader), the C-ABI boundary (library loads,
+every declared symbol exported) and product/oracle separation.  No GPU compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def _alignment():
+    from pylogeny_b200 import alignment
+    al = load_golden("al_alignment.json")
+    return alignment.alignment(names=al["taxa"], seqs=al["seqs"])
+
+
+def test_profile_set_matches_reference_golden(al_profiles):
+    """Same profiles, first-occurrence order, weights and taxa dict as reference parsimony.profile_set."""
+    from pylogeny_b200 import parsimony
+    ps = parsimony.profile_set(_alignment())
+    assert [str(p) for p in ps.profiles] == al_profiles["profiles"]
+    assert ps.weights == al_profiles["weights"]
+    assert ps.taxa == al_profiles["taxa"]
+    assert ps.numSites == al_profiles["n_sites"] == len(ps.sites) == sum(ps.weights)
+    assert len(ps) == 142
+    assert [(str(p), w) for p, w in zip(ps.profiles[:5], ps.weights[:5])] == [
+        ('00010100', 38), ('00010120', 2), ('00012122', 3), ('00012102', 1), ('00010000', 35)]
+
+
+def test_profile_set_generic_path_equals_vectorised(al_profiles):
+    """An alignment object without as_matrix() (only the reference's p4-style surface) gives the same set."""
+    from pylogeny_b200 import parsimony
+    al = _alignment()
+
+    class Plain(object):
+        data = al.data
+        getSize = staticmethod(al.getSize)
+        getTaxa = staticmethod(al.getTaxa)
+
+    ps = parsimony.profile_set(Plain())
+    assert [str(p) for p in ps.profiles] == al_profiles["profiles"] and ps.weights == al_profiles["weights"]
+    assert ps.getForTaxa(1, al.getTaxa()[7]) == '0'
+    assert ps.get(2) == ps.profiles[2] and ps.weight(2) == 3
+
+
+def test_profile_set_many_symbols():
+    """>= 10 distinct symbols in a column: str(idx) turns multi-char exactly as parsimony.py:144 does."""
+    from pylogeny_b200 import alignment, parsimony
+    seqs = [c for c in "ABCDEFGHIJKLM"]
+    al = alignment.alignment(names=["t%d" % i for i in range(13)], seqs=seqs)
+    ps = parsimony.profile_set(al)
+    assert str(ps.profiles[0]) == "0123456789101112"
+
+
+def test_phylip_friendly_alignment(tmp_path):
+    from pylogeny_b200 import alignment
+    g = load_golden("al_alignment.json")
+    fa = tmp_path / "a.fasta"
+    fa.write_text("".join(">%s\n%s\n" % (n, s) for n, s in zip(g["taxa"], g["seqs"])))
+    al = alignment.phylipFriendlyAlignment(str(fa))
+    assert al.getTaxa() == ["T%d" % i for i in range(8)]
+    assert al.getProperName("T3") == g["taxa"][3]
+    assert al.getSize() == 1431 and al.getNumSeqs() == 8 and al.getDataType() == 'dna'
+    ph = al.getPhylip()
+    back = alignment.alignment(ph)
+    assert back.getTaxa() == al.getTaxa() and back.toStrList() == al.toStrList()
+    al.close()
+    assert not os.path.exists(ph)
+
+
+def test_library_exports_every_declared_symbol():
+    from pylogeny_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "pylogeny_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(plg_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 10
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert _lib.lib().plg_version() >= 100
+
+
+def test_no_gpu_fails_loudly():
+    """Without a CUDA device the compute entry points report PLG_ERR_CUDA instead of falling back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pylogeny_b200 import _lib, fitch
+    with pytest.raises(_lib.EngineError) as e:
+        fitch.calculateCost("(A,B);", ["01"], [1], {"A": 0, "B": 1})
+    assert e.value.code == _lib.ERR_CUDA
+
+
+def test_product_never_touches_the_oracle():
+    """Only tests/, bench.py's CPU legs and __graft_entry__.smoke() may use oracle/."""
+    bad = []
+    for dp, _, fns in os.walk(os.path.join(ROOT, "pylogeny_b200")):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cpp", ".h")):
+                src = open(os.path.join(dp, fn), errors="replace").read()
+                if re.search(r"\boracle\b", src):
+                    bad.append(fn)
+    assert not bad, bad
+
+
+def test_newick_errors_are_reported_not_thrown():
+    from pylogeny_b200 import _lib
+    import ctypes as C
+    out = C.c_int32()
+    rc = _lib.lib().plg_fitch_cost(b"((A,B);", 0, None, None, 0, None, None, C.byref(out))
+    assert rc == _lib.ERR_PARSE and b"Newick" in _lib.lib().plg_last_error()
+    names = (C.c_char_p * 1)(b"A")
+    idx = (C.c_int32 * 1)(0)
+    rc = _lib.lib().plg_fitch_cost(b"(A,B);", 0, None, None, 1, names, idx, C.byref(out))
+    assert rc == _lib.ERR_LABEL
