@@ -54,3 +54,13 @@ def _declare(L):
     L.plg_fitch_cost.argtypes = [C.c_char_p, C.c_int64, strs, i64p, C.c_int, strs, i32p, i32p]
     L.plg_fitch_score_newicks.argtypes = [vp, C.c_int64, strs, C.c_int, strs, i32p, vp, vp]
     L.plg_fitch_score_trees.argtypes = [vp, C.c_int64, C.c_int, vp, vp, vp, vp]
+    dp = C.POINTER(C.c_double)
+    L.plg_lik_aln_create.argtypes = [C.c_int, C.c_int, C.c_int64, vp, vp, C.POINTER(vp)]
+    L.plg_lik_aln_destroy.argtypes = [vp]
+    L.plg_lik_aln_destroy.restype = None
+    L.plg_model_create.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, C.POINTER(vp)]
+    L.plg_model_destroy.argtypes = [vp]
+    L.plg_model_destroy.restype = None
+    L.plg_model_gamma_rates.argtypes = [vp, dp]
+    L.plg_model_pmatrix.argtypes = [vp, C.c_double, dp]
+    L.plg_lik_score_trees.argtypes = [vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp, vp]

@@ -1,0 +1,502 @@
+// Felsenstein-pruning log-likelihood on sm_100a (FP64 CUDA cores), level-synchronous op programs.
+//
+// Replaces the libpll 1.0.2 kernels reached from libpllWrapper.c (pllInitModel :159,
+// newview/evaluate behind pllOptimizeBranchLengths :205 and pllEvaluateLikelihood :77):
+//   pmatrix_kernel   P(t * r_c) = U exp(L t r_c) U^-1 per unique branch length and Gamma
+//                    category, plus the tip lookup table sum_{j in code} P[.][j]
+//   clv_update_kernel  x3 = (P_L x1) .* (P_R x2) per pattern and category, with per-pattern
+//                    2^-256 rescaling counters (PLL_MINLIKELIHOOD semantics)
+//   root_eval_kernel site likelihood at a branch, log, pattern weights, scaler correction
+//   reduce_partials_kernel  fixed-order (deterministic) sum of the per-block partials
+//
+// Data layout in HBM: a conditional likelihood vector is pattern-minor SoA,
+// clv[slot][r*K + k][Ppad] doubles (+ int32 scaler[slot][Ppad]), so that the 32 lanes of a
+// warp -- 8 consecutive patterns x 4 rate categories -- read 64-byte contiguous runs of four
+// planes: every 32-byte sector fetched is fully used.  Tips are 1 byte per pattern.
+// 4x4 / 20x20 per-site products are not a dense contraction worth tensor cores
+// (BASELINE.json north_star); the roofline that bounds the DNA kernels is HBM.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "lik.h"
+
+namespace plg {
+
+constexpr double TWO256 = 1.15792089237316195423570985008687907853269984665640564039457584007913129639936e77;
+constexpr double MINLH = 1.0 / TWO256;
+constexpr int LIK_THREADS = 256;
+
+template <int K>
+struct NCodes { static constexpr int value = K == 4 ? 16 : 23; };
+
+// ----------------------------------------------------------------------------
+// device
+// ----------------------------------------------------------------------------
+template <int K, int R>
+__global__ void pmatrix_kernel(const ModelDev *__restrict__ model, const double *__restrict__ brlen,
+                               const unsigned int *__restrict__ masks, double *__restrict__ pmat,
+                               double *__restrict__ tiptab) {
+  constexpr int KK = K * K, KKP = KK + 1, NC = NCodes<K>::value;
+  __shared__ double ex[R * K];
+  __shared__ double Pm[R * KKP];
+  const int pm = blockIdx.x;
+  const double t = brlen[pm];
+  for (int e = threadIdx.x; e < R * K; e += blockDim.x)
+    ex[e] = exp(model->eval[e % K] * t * model->rates[e / K]);
+  __syncthreads();
+  for (int e = threadIdx.x; e < R * KK; e += blockDim.x) {
+    const int r = e / KK, i = (e / K) % K, j = e % K;
+    double s = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < K; k++) s += model->U[i * K + k] * ex[r * K + k] * model->Uinv[k * K + j];
+    Pm[r * KKP + i * K + j] = s;
+    pmat[(int64_t)pm * R * KKP + r * KKP + i * K + j] = s;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NC * R * K; e += blockDim.x) {
+    const int code = e / (R * K), r = (e / K) % R, k = e % K;
+    const unsigned int m = masks[code];
+    double s = 0.0;
+    for (int j = 0; j < K; j++)
+      if (m >> j & 1) s += Pm[r * KKP + k * K + j];
+    tiptab[(int64_t)pm * NC * R * K + e] = s;
+  }
+}
+
+// Shared-memory staging of one operand's matrix: tip -> lookup table, inner -> P-matrix.
+template <int K, int R>
+__device__ __forceinline__ void stage_operand(double *sm, bool is_tip, int pm, const double *__restrict__ pmat,
+                                              const double *__restrict__ tiptab) {
+  constexpr int KKP = K * K + 1, NC = NCodes<K>::value;
+  if (is_tip) {
+    const double *src = tiptab + (int64_t)pm * NC * R * K;
+    for (int e = threadIdx.x; e < NC * R * K; e += blockDim.x) sm[e] = src[e];
+  } else {
+    const double *src = pmat + (int64_t)pm * R * KKP;
+    for (int e = threadIdx.x; e < R * KKP; e += blockDim.x) sm[e] = src[e];
+  }
+}
+
+// (P x)[0..K) for this thread's pattern p and category r.
+template <int K, int R>
+__device__ __forceinline__ void apply_operand(const double *sm, bool is_tip, int id, int n_rows, int64_t p, int r,
+                                              int64_t Ppad, const unsigned char *__restrict__ codes,
+                                              const double *__restrict__ clv, double (&v)[K]) {
+  constexpr int KKP = K * K + 1;
+  if (is_tip) {
+    const int code = codes[(int64_t)id * Ppad + p];
+    const double *row = sm + (code * R + r) * K;
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = row[k];
+  } else {
+    const double *src = clv + ((int64_t)(id - n_rows) * R * K + r * K) * Ppad + p;
+    double x[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) x[j] = __ldg(src + (int64_t)j * Ppad);
+    const double *Pm = sm + r * KKP;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < K; j++) s = fma(Pm[k * K + j], x[j], s);
+      v[k] = s;
+    }
+  }
+}
+
+template <int K, int R>
+__global__ void __launch_bounds__(LIK_THREADS)
+clv_update_kernel(const LikOp *__restrict__ ops, int blocks_per_op, int n_rows, int64_t Ppad,
+                  const unsigned char *__restrict__ codes, const double *__restrict__ pmat,
+                  const double *__restrict__ tiptab, double *__restrict__ clv, int *__restrict__ scl) {
+  constexpr int KKP = K * K + 1, NC = NCodes<K>::value;
+  constexpr int SM = (NC * R * K > R * KKP) ? NC * R * K : R * KKP;
+  __shared__ double smA[SM];
+  __shared__ double smB[SM];
+  const int op_idx = blockIdx.x / blocks_per_op;
+  const int pb = blockIdx.x - op_idx * blocks_per_op;
+  const LikOp op = ops[op_idx];
+  const bool tipA = op.a < n_rows, tipB = op.b >= 0 && op.b < n_rows;
+  stage_operand<K, R>(smA, tipA, op.pa, pmat, tiptab);
+  if (op.b >= 0) stage_operand<K, R>(smB, tipB, op.pb, pmat, tiptab);
+  __syncthreads();
+  const int r = threadIdx.x % R;
+  const int64_t p = (int64_t)pb * (LIK_THREADS / R) + threadIdx.x / R;
+  // Ppad is a multiple of LIK_THREADS/R, so every thread owns a (possibly padding) pattern
+  double va[K], vb[K];
+  apply_operand<K, R>(smA, tipA, op.a, n_rows, p, r, Ppad, codes, clv, va);
+  int sc = tipA ? 0 : scl[(int64_t)(op.a - n_rows) * Ppad + p];
+  if (op.b >= 0) {
+    apply_operand<K, R>(smB, tipB, op.b, n_rows, p, r, Ppad, codes, clv, vb);
+    if (!tipB) sc += scl[(int64_t)(op.b - n_rows) * Ppad + p];
+#pragma unroll
+    for (int k = 0; k < K; k++) va[k] *= vb[k];
+  }
+  double mx = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; k++) mx = fmax(mx, fabs(va[k]));
+#pragma unroll
+  for (int d = 1; d < R; d <<= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  const bool rescale = mx < MINLH;  // all R*K entries below 2^-256
+  double *dst = clv + ((int64_t)(op.dst - n_rows) * R * K + r * K) * Ppad + p;
+#pragma unroll
+  for (int k = 0; k < K; k++) dst[(int64_t)k * Ppad] = rescale ? va[k] * TWO256 : va[k];
+  if (r == 0) scl[(int64_t)(op.dst - n_rows) * Ppad + p] = sc + (rescale ? 1 : 0);
+}
+
+template <int K, int R>
+__global__ void __launch_bounds__(LIK_THREADS)
+root_eval_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_rows, int64_t Ppad,
+                 const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
+                 const double *__restrict__ weights, const ModelDev *__restrict__ model,
+                 const double *__restrict__ pmat, const double *__restrict__ tiptab,
+                 const double *__restrict__ clv, const int *__restrict__ scl, double *__restrict__ partial) {
+  constexpr int KKP = K * K + 1, NC = NCodes<K>::value;
+  constexpr int SM = (NC * R * K > R * KKP) ? NC * R * K : R * KKP;
+  __shared__ double smB[SM];
+  __shared__ double warp_sums[LIK_THREADS / 32];
+  const int ev_idx = blockIdx.x / blocks_per_eval;
+  const int pb = blockIdx.x - ev_idx * blocks_per_eval;
+  const LikEval ev = evals[ev_idx];
+  const bool tipA = ev.a < n_rows, tipB = ev.b < n_rows;
+  stage_operand<K, R>(smB, tipB, ev.pm, pmat, tiptab);
+  __syncthreads();
+  const int r = threadIdx.x % R;
+  const int64_t p = (int64_t)pb * (LIK_THREADS / R) + threadIdx.x / R;
+  double vb[K];
+  apply_operand<K, R>(smB, tipB, ev.b, n_rows, p, r, Ppad, codes, clv, vb);
+  double term = 0.0;
+  int sc = tipB ? 0 : scl[(int64_t)(ev.b - n_rows) * Ppad + p];
+  if (tipA) {
+    const unsigned int m = masks[codes[(int64_t)ev.a * Ppad + p]];
+#pragma unroll
+    for (int k = 0; k < K; k++)
+      if (m >> k & 1) term = fma(model->freqs[k], vb[k], term);
+  } else {
+    const double *src = clv + ((int64_t)(ev.a - n_rows) * R * K + r * K) * Ppad + p;
+#pragma unroll
+    for (int k = 0; k < K; k++) term = fma(model->freqs[k] * __ldg(src + (int64_t)k * Ppad), vb[k], term);
+    sc += scl[(int64_t)(ev.a - n_rows) * Ppad + p];
+  }
+#pragma unroll
+  for (int d = 1; d < R; d <<= 1) term += __shfl_xor_sync(0xffffffffu, term, d);
+  double val = 0.0;
+  if (r == 0) {
+    const double w = weights[p];
+    if (w != 0.0) val = w * (log(term * (1.0 / R)) + sc * log(MINLH));
+  }
+  // fixed-shape block reduction (deterministic order)
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = val;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < LIK_THREADS / 32; w++) s += warp_sums[w];
+    partial[(int64_t)ev_idx * blocks_per_eval + pb] = s;
+  }
+}
+
+// One warp per evaluation: strided partial sums, then a fixed shuffle tree; accumulates per tree
+// through the eval's tree index (each tree owns exactly one eval in every program we build).
+__global__ void reduce_partials_kernel(const LikEval *__restrict__ evals, int n_evals, int blocks_per_eval,
+                                       const double *__restrict__ partial, double *__restrict__ lnl) {
+  const int ev = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (ev >= n_evals) return;
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int b = lane; b < blocks_per_eval; b += 32) s += partial[(int64_t)ev * blocks_per_eval + b];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+  if (lane == 0) lnl[evals[ev].tree] = s;
+}
+
+// ----------------------------------------------------------------------------
+// host: alignment
+// ----------------------------------------------------------------------------
+LikAln::LikAln(int datatype, int n_rows_, int64_t P_, const uint8_t *h_codes, const double *h_w) {
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+    PLG_FAIL(PLG_ERR_CUDA, "no CUDA device: pylogeny_b200 has no CPU fallback");
+  if (datatype != PLG_DATA_DNA && datatype != PLG_DATA_AA) PLG_FAIL(PLG_ERR_ARG, "datatype must be 4 (DNA) or 20 (AA)");
+  if (n_rows_ <= 0 || P_ < 0) PLG_FAIL(PLG_ERR_ARG, "alignment needs n_rows > 0 and n_patterns >= 0");
+  K = datatype;
+  n_rows = n_rows_;
+  P = P_;
+  if (K == 4) {
+    n_codes = 16;
+    for (unsigned int c = 0; c < 16; c++) h_masks.push_back(c ? c : 15u);  // code 0 (no state) reads as unknown
+  } else {
+    n_codes = 23;
+    for (int c = 0; c < 20; c++) h_masks.push_back(1u << c);
+    h_masks.push_back((1u << 2) | (1u << 3));  // B = N|D   (order ARNDCQEGHILKMFPSTWYV)
+    h_masks.push_back((1u << 5) | (1u << 6));  // Z = Q|E
+    h_masks.push_back((1u << 20) - 1);          // X, -, ?
+  }
+  const int64_t tile = LIK_THREADS;  // multiple of LIK_THREADS / R for every supported R
+  Ppad = std::max<int64_t>(tile, (P + tile - 1) / tile * tile);
+  const uint8_t any = (uint8_t)(K == 4 ? 15 : 22);
+  std::vector<uint8_t> padded((size_t)n_rows * Ppad, any);
+  for (int r = 0; r < n_rows; r++)
+    for (int64_t p = 0; p < P; p++) {
+      uint8_t c = h_codes[(size_t)r * P + p];
+      if (c >= n_codes) PLG_FAIL(PLG_ERR_ARG, "tip code %d at row %d pattern %lld is out of range", c, r, (long long)p);
+      padded[(size_t)r * Ppad + p] = c;
+    }
+  std::vector<double> w(Ppad, 0.0);
+  for (int64_t p = 0; p < P; p++) w[p] = h_w[p];
+  codes.alloc(padded.size());
+  weights.alloc(w.size());
+  masks.alloc(h_masks.size());
+  PLG_CUDA(cudaMemcpy(codes.p, padded.data(), padded.size(), cudaMemcpyHostToDevice));
+  PLG_CUDA(cudaMemcpy(weights.p, w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+  PLG_CUDA(cudaMemcpy(masks.p, h_masks.data(), h_masks.size() * 4, cudaMemcpyHostToDevice));
+}
+
+// ----------------------------------------------------------------------------
+// host: programs
+// ----------------------------------------------------------------------------
+void LikProgram::clear() {
+  ops.clear();
+  level_off.clear();
+  evals.clear();
+  brlens.clear();
+  pm_index.clear();
+  n_slots = n_trees = 0;
+}
+
+int LikProgram::pm(double t) {
+  if (!(t >= 0.0)) t = 0.0;  // negative / NaN lengths are read as zero
+  uint64_t bits;
+  memcpy(&bits, &t, 8);
+  auto it = pm_index.find(bits);
+  if (it != pm_index.end()) return it->second;
+  int id = (int)brlens.size();
+  brlens.push_back(t);
+  pm_index.emplace(bits, id);
+  return id;
+}
+
+// Full re-traversal: every non-root internal node is one CLV update (k-ary nodes become a chain
+// of binary updates joined by zero-length branches), the root is one branch evaluation.
+void build_full_lik_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_rows, LikProgram &prog) {
+  prog.clear();
+  if (b.child_len.size() != b.child.size()) PLG_FAIL(PLG_ERR_ARG, "likelihood programs need branch lengths");
+  struct Tmp { LikOp op; int level; };
+  std::vector<Tmp> tmp;
+  std::vector<int> node_id, node_level;
+  int64_t slot = 0;
+  int max_level = 0;
+  for (int64_t t = t0; t < t1; t++) {
+    const int64_t base = b.node_off[t], end = b.node_off[t + 1];
+    node_id.assign(end - base, -1);
+    node_level.assign(end - base, 0);
+    for (int64_t x = base; x < end; x++) {
+      const int64_t c0 = b.child_off[x], k = b.child_off[x + 1] - c0;
+      const bool is_root = (x == end - 1);
+      auto operand = [&](int64_t c, int &id, int &lvl) {
+        int32_t ch = b.child[c];
+        if (ch >= 0) { id = ch; lvl = 0; }
+        else { id = node_id[-ch - 1]; lvl = node_level[-ch - 1]; }
+      };
+      if (k < 1) PLG_FAIL(PLG_ERR_ARG, "internal node without children");
+      if (is_root && k == 1) PLG_FAIL(PLG_ERR_UNSUPPORTED, "likelihood of a tree whose root has a single child");
+      int acc_id, acc_lvl;
+      double acc_len = b.child_len[c0];
+      operand(c0, acc_id, acc_lvl);
+      auto emit = [&](int cid, int clvl, double clen) {
+        Tmp e;
+        e.op.dst = n_rows + (int)slot++;
+        e.op.a = acc_id; e.op.pa = prog.pm(acc_len);
+        e.op.b = cid; e.op.pb = cid >= 0 ? prog.pm(clen) : 0;
+        e.level = std::max(acc_lvl, clvl) + 1;
+        tmp.push_back(e);
+        acc_id = e.op.dst; acc_lvl = e.level; acc_len = 0.0;  // the chain continues AT this node
+        max_level = std::max(max_level, e.level);
+      };
+      if (k == 1) emit(-1, 0, 0.0);  // unary node: CLV = P(t) x
+      for (int64_t j = 1; j < k; j++) {
+        int cid, clvl;
+        operand(c0 + j, cid, clvl);
+        const double clen = b.child_len[c0 + j];
+        if (is_root && j == k - 1) {
+          // site likelihood across the last branch; sum_k pi_k A_k (P B)_k is symmetric in A,B
+          // (reversibility), and for a bifurcating root P(ta)A . P(tb)B collapses to P(ta+tb)
+          LikEval ev;
+          ev.a = acc_id; ev.b = cid; ev.pm = prog.pm(acc_len + clen);
+          if (ev.b < n_rows && ev.a >= n_rows) std::swap(ev.a, ev.b);  // tip on the indicator side
+          ev.tree = (int)(t - t0);
+          prog.evals.push_back(ev);
+          max_level = std::max(max_level, std::max(acc_lvl, clvl));
+        } else {
+          emit(cid, clvl, clen);
+        }
+      }
+      node_id[x - base] = acc_id;
+      node_level[x - base] = acc_lvl;
+    }
+  }
+  prog.level_off.assign(max_level + 2, 0);
+  for (auto &e : tmp) prog.level_off[e.level + 1]++;
+  for (int l = 0; l <= max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+  std::vector<int64_t> cur(prog.level_off.begin(), prog.level_off.end() - 1);
+  prog.ops.resize(tmp.size());
+  for (auto &e : tmp) prog.ops[cur[e.level]++] = e.op;
+  prog.n_slots = slot;
+  prog.n_trees = t1 - t0;
+}
+
+template <int K, int R>
+static void run_typed(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, cudaStream_t st) {
+  constexpr int KKP = K * K + 1, NC = NCodes<K>::value;
+  const int n_pm = (int)prog.brlens.size();
+  ws.pmat.alloc(std::max<size_t>(1, (size_t)n_pm * R * KKP));
+  ws.tiptab.alloc(std::max<size_t>(1, (size_t)n_pm * NC * R * K));
+  ws.brlen.alloc(std::max<size_t>(1, n_pm));
+  if (n_pm) {
+    PLG_CUDA(cudaMemcpyAsync(ws.brlen.p, prog.brlens.data(), (size_t)n_pm * 8, cudaMemcpyHostToDevice, st));
+    pmatrix_kernel<K, R><<<n_pm, 128, 0, st>>>(m.d.p, ws.brlen.p, a.masks.p, ws.pmat.p, ws.tiptab.p);
+    count_launch();
+  }
+  const int per_block = LIK_THREADS / R;
+  const int64_t bpo = a.Ppad / per_block;
+  for (size_t l = 0; l + 1 < prog.level_off.size(); l++) {
+    const int64_t o0 = prog.level_off[l], cnt = prog.level_off[l + 1] - o0;
+    const int64_t max_ops = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
+    for (int64_t o = 0; o < cnt; o += max_ops) {
+      const int64_t c = std::min(max_ops, cnt - o);
+      clv_update_kernel<K, R><<<(unsigned)(c * bpo), LIK_THREADS, 0, st>>>(
+          ws.ops.p + o0 + o, (int)bpo, a.n_rows, a.Ppad, a.codes.p, ws.pmat.p, ws.tiptab.p, ws.clv.p, ws.scl.p);
+      count_launch();
+    }
+  }
+  const int64_t n_ev = (int64_t)prog.evals.size();
+  if (n_ev) {
+    const int64_t max_ev = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
+    for (int64_t e = 0; e < n_ev; e += max_ev) {
+      const int64_t c = std::min(max_ev, n_ev - e);
+      root_eval_kernel<K, R><<<(unsigned)(c * bpo), LIK_THREADS, 0, st>>>(
+          ws.evals.p + e, (int)bpo, a.n_rows, a.Ppad, a.codes.p, a.masks.p, a.weights.p, m.d.p, ws.pmat.p,
+          ws.tiptab.p, ws.clv.p, ws.scl.p, ws.partial.p + e * bpo);
+      count_launch();
+    }
+    reduce_partials_kernel<<<(unsigned)((n_ev + 7) / 8), 256, 0, st>>>(ws.evals.p, (int)n_ev, (int)bpo, ws.partial.p,
+                                                                       ws.lnl.p);
+    count_launch();
+  }
+}
+
+void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, double *out_lnl,
+                     cudaStream_t st) {
+  if (m.K != a.K) PLG_FAIL(PLG_ERR_ARG, "model has %d states but the alignment has %d", m.K, a.K);
+  const size_t RK = (size_t)m.R * a.K;
+  ws.clv.alloc(std::max<size_t>(1, (size_t)prog.n_slots * RK * a.Ppad));
+  ws.scl.alloc(std::max<size_t>(1, (size_t)prog.n_slots * a.Ppad));
+  ws.ops.alloc(std::max<size_t>(1, prog.ops.size()));
+  ws.evals.alloc(std::max<size_t>(1, prog.evals.size()));
+  const int64_t bpo = a.Ppad / (LIK_THREADS / m.R);
+  ws.partial.alloc(std::max<size_t>(1, prog.evals.size() * (size_t)bpo));
+  ws.lnl.alloc(std::max<size_t>(1, (size_t)prog.n_trees));
+  if (!prog.ops.empty())
+    PLG_CUDA(cudaMemcpyAsync(ws.ops.p, prog.ops.data(), prog.ops.size() * sizeof(LikOp), cudaMemcpyHostToDevice, st));
+  if (!prog.evals.empty())
+    PLG_CUDA(cudaMemcpyAsync(ws.evals.p, prog.evals.data(), prog.evals.size() * sizeof(LikEval),
+                             cudaMemcpyHostToDevice, st));
+  PLG_CUDA(cudaMemsetAsync(ws.lnl.p, 0, std::max<size_t>(1, (size_t)prog.n_trees) * 8, st));
+  if (a.K == 4 && m.R == 4) run_typed<4, 4>(a, m, ws, prog, st);
+  else if (a.K == 4 && m.R == 1) run_typed<4, 1>(a, m, ws, prog, st);
+  else if (a.K == 20 && m.R == 4) run_typed<20, 4>(a, m, ws, prog, st);
+  else if (a.K == 20 && m.R == 1) run_typed<20, 1>(a, m, ws, prog, st);
+  else PLG_FAIL(PLG_ERR_UNSUPPORTED, "kernels exist for 4 or 20 states with 1 or 4 rate categories");
+  PLG_CUDA(cudaGetLastError());
+  if (out_lnl && prog.n_trees) {
+    PLG_CUDA(cudaMemcpyAsync(out_lnl, ws.lnl.p, (size_t)prog.n_trees * 8, cudaMemcpyDeviceToHost, st));
+    PLG_CUDA(cudaStreamSynchronize(st));
+  }
+}
+
+void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double *out_lnl, cudaStream_t st) {
+  const int64_t n_trees = b.n_trees();
+  if (n_trees == 0) return;
+  size_t free_b = 0, total_b = 0;
+  PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t slot_bytes = ((size_t)m.R * a.K * 8 + 4) * a.Ppad;
+  const size_t held = a.ws.clv.n * 8 + a.ws.scl.n * 4;
+  const size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)64 << 30);
+  const int64_t max_slots = std::max<int64_t>(1, (int64_t)(budget / slot_bytes));
+  LikProgram prog;
+  int64_t t0 = 0;
+  while (t0 < n_trees) {
+    // slots needed by a tree <= its child count (binary: one per non-root internal node)
+    int64_t t1 = t0 + 1;
+    auto need = [&](int64_t lo, int64_t hi) { return b.child_off[b.node_off[hi]] - b.child_off[b.node_off[lo]]; };
+    while (t1 < n_trees && need(t0, t1 + 1) / 2 <= max_slots) t1++;
+    build_full_lik_program(b, t0, t1, a.n_rows, prog);
+    run_lik_program(a, m, a.ws, prog, out_lnl + t0, st);
+    t0 = t1;
+  }
+}
+
+}  // namespace plg
+
+// ----------------------------------------------------------------------------
+// C-ABI
+// ----------------------------------------------------------------------------
+using namespace plg;
+
+struct plg_lik_aln {
+  LikAln impl;
+  plg_lik_aln(int dt, int n, int64_t P, const uint8_t *c, const double *w) : impl(dt, n, P, c, w) {}
+};
+struct plg_model {
+  Model impl;
+  plg_model(int K, const double *e, const double *f, double a, int n) : impl(K, e, f, a, n) {}
+};
+
+extern "C" int plg_lik_aln_create(int datatype, int n_rows, int64_t n_patterns, const uint8_t *codes,
+                                  const double *weights, plg_lik_aln **out) {
+  PLG_API_BEGIN
+  if (!out || (n_patterns > 0 && (!codes || !weights))) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  *out = new plg_lik_aln(datatype, n_rows, n_patterns, codes, weights);
+  PLG_API_END
+}
+extern "C" void plg_lik_aln_destroy(plg_lik_aln *aln) { delete aln; }
+
+extern "C" int plg_model_create(int n_states, const double *exch, const double *freqs, double alpha, int n_cat,
+                                plg_model **out) {
+  PLG_API_BEGIN
+  if (!out || !exch || !freqs) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+    PLG_FAIL(PLG_ERR_CUDA, "no CUDA device: pylogeny_b200 has no CPU fallback");
+  *out = new plg_model(n_states, exch, freqs, alpha, n_cat);
+  PLG_API_END
+}
+extern "C" void plg_model_destroy(plg_model *m) { delete m; }
+
+extern "C" int plg_model_gamma_rates(const plg_model *m, double *rates) {
+  PLG_API_BEGIN
+  if (!m || !rates) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  for (int i = 0; i < m->impl.R; i++) rates[i] = m->impl.h.rates[i];
+  PLG_API_END
+}
+
+extern "C" int plg_model_pmatrix(const plg_model *m, double t, double *out) {
+  PLG_API_BEGIN
+  if (!m || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  m->impl.pmatrix(t, out);
+  PLG_API_END
+}
+
+extern "C" int plg_lik_score_trees(plg_lik_aln *aln, plg_model *m, int64_t n_trees, int n_tips, const int32_t *desc,
+                                   const double *brlen, const int32_t *tip_rows, double *out_lnl, void *stream) {
+  PLG_API_BEGIN
+  if (!aln || !m || !out_lnl || (n_trees > 0 && (!desc || !brlen))) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  TreeBatch b = batch_from_desc(n_trees, n_tips, desc, brlen, tip_rows);
+  for (int32_t c : b.child)
+    if (c >= aln->impl.n_rows) PLG_FAIL(PLG_ERR_ARG, "tip row %d is outside the alignment (%d rows)", c, aln->impl.n_rows);
+  score_lik_batch_full(aln->impl, m->impl, b, out_lnl, (cudaStream_t)stream);
+  PLG_API_END
+}

@@ -1,0 +1,59 @@
+// Felsenstein-pruning likelihood engine: device-resident tips, CLV op programs, executor.
+#pragma once
+#include <unordered_map>
+
+#include "common.h"
+#include "model.h"
+#include "tree.h"
+
+namespace plg {
+
+// dst = CLV( P[pa] * a ) .* ( P[pb] * b ); operand ids: < n_rows tip row, else n_rows + slot
+struct LikOp {
+  int dst, a, b, pa, pb;
+};
+// lnL[tree] += sum_p w_p log( (1/R) sum_r sum_k pi_k A_r[k] (P[pm]_r B_r)[k] ) + scalers
+struct LikEval {
+  int a, b, pm, tree;
+};
+
+struct LikWorkspace {
+  DevBuf<double> clv;      // [slot][R*K][Ppad]
+  DevBuf<int> scl;         // [slot][Ppad] per-pattern 2^-256 scaling counters
+  DevBuf<double> pmat;     // [pm][R][K*K+1]  (padded stride: conflict-free shared-memory staging)
+  DevBuf<double> tiptab;   // [pm][ncodes][R*K]  sum over the code's states of P columns
+  DevBuf<double> brlen;    // [pm]
+  DevBuf<LikOp> ops;
+  DevBuf<LikEval> evals;
+  DevBuf<double> partial;  // [eval][blocks]
+  DevBuf<double> lnl;      // [tree]
+};
+
+struct LikAln {
+  int K = 0, n_codes = 0, n_rows = 0;
+  int64_t P = 0, Ppad = 0;
+  DevBuf<unsigned char> codes;  // [n_rows][Ppad]; padding = the any-state code
+  DevBuf<double> weights;       // [Ppad]; padding = 0
+  DevBuf<unsigned int> masks;   // [n_codes] bit k = state k compatible
+  std::vector<unsigned int> h_masks;
+  LikWorkspace ws;
+  LikAln(int datatype, int n_rows, int64_t P, const uint8_t *codes, const double *weights);
+};
+
+struct LikProgram {
+  std::vector<LikOp> ops;          // sorted by level
+  std::vector<int64_t> level_off;  // [n_levels+1]
+  std::vector<LikEval> evals;
+  std::vector<double> brlens;      // unique branch lengths -> P-matrix index
+  std::unordered_map<uint64_t, int> pm_index;
+  int64_t n_slots = 0, n_trees = 0;
+  void clear();
+  int pm(double t);
+};
+
+void build_full_lik_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_rows, LikProgram &prog);
+void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, double *out_lnl,
+                     cudaStream_t st);
+void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double *out_lnl, cudaStream_t st);
+
+}  // namespace plg
