@@ -82,13 +82,28 @@ int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_tips,
                           const int32_t *desc, const int32_t *tip_rows,
                           int32_t *out_costs, void *stream);
 
-/* Whole rearrangement neighbourhood of one rooted binary base tree (descriptor as
- * above, n_tips-1 internal nodes).  Enumerates every distinct neighbour topology
- * (NNI: 2(n-3); SPR: 2(n-3)(2n-7)) and scores each by edge-insertion Fitch
- * (exact for binary trees: Fitch length is root-invariant).  Moves are returned
- * as (prune_node, regraft_node) pairs naming the child end of the pruned /
- * target branch in the base tree's node ids.  Call with out_* == NULL to get
- * the count.  Replaces the per-neighbour loop landscape.py:724-756. */
+/* ---- rearrangement neighbourhoods (host side; no device needed) ----
+ * Base tree = rooted binary descriptor as above (n_tips-1 internal nodes, ids n_tips+i, root
+ * last).  It is read as the unrooted tree it represents (the root's two child branches merge).
+ * Every DISTINCT neighbour topology is produced once -- NNI: 2(n-3), SPR: 2(n-3)(2n-7) -- in a
+ * deterministic order, identified by a canonical topology hash (sum over splits), whereas the
+ * reference emits 4(n-3)(n-2) SPR moves with duplicates (rearrangement.py:580-594). */
+int plg_neighbourhood_size(int move_type, int n_tips, const int32_t *desc, int64_t *n_moves);
+/* Materialise selected neighbours: out_desc/out_brlen [n_sel][n_tips-1][2], rooted on tip 0's
+ * branch (rearrangement.py:267-331); neighbour branch lengths follow rearrangement.py:466-497
+ * (target branch halved, the two branches left at the pruned node summed).  out_hash[n_sel]. */
+int plg_neighbourhood_trees(int move_type, int n_tips, const int32_t *desc, const double *brlen,
+                            int64_t n_sel, const int64_t *sel, int32_t *out_desc,
+                            double *out_brlen, uint64_t *out_hash);
+int plg_topology_hash(int n_tips, const int32_t *desc, uint64_t *out);
+
+/* Fitch length of every distinct neighbour in one call, by edge insertion: directional state
+ * sets of the base tree once, one partial per search step, one 3-way join per neighbour
+ * (exact for binary trees: Fitch length is root-invariant).  *n_moves = total count M.
+ * out_moves (may be NULL): int32 [M][4] = (child end of pruned branch, 0 subtree / 1 complement
+ * moves, child end of target branch, SPR distance) in base-tree node ids.  out_costs (may be
+ * NULL): int32 [M]; only the shard [M*i/c, M*(i+1)/c) is written (ranks score disjoint blocks,
+ * the host all-gathers).  Replaces the per-neighbour loop landscape.py:724-756. */
 int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, int n_tips,
                                   const int32_t *desc, const int32_t *tip_rows,
                                   int64_t shard_index, int64_t shard_count,
@@ -123,26 +138,15 @@ int plg_lik_score_trees(plg_lik_aln *aln, plg_model *m, int64_t n_trees, int n_t
                         const int32_t *desc, const double *brlen, const int32_t *tip_rows,
                         double *out_lnl, void *stream);
 
-/* lnL of every distinct SPR/NNI neighbour of one base tree at fixed branch lengths.
- * Neighbour branch lengths follow rearrangement.py:466-486 (target branch split in
- * half, the two branches left at the pruned node merged by summing). */
+/* lnL of every distinct SPR/NNI neighbour of one base tree at fixed branch lengths, by edge
+ * insertion (directional CLVs of the base tree, one CLV update per search step, one 3-way
+ * evaluation per neighbour).  Same conventions as plg_fitch_score_neighbourhood; the closest
+ * reference analogue is getSPR/NNIMovesInDistance, libpllWrapper.c:241-319. */
 int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int move_type, int n_tips,
                                 const int32_t *desc, const double *brlen,
                                 const int32_t *tip_rows, int64_t shard_index,
                                 int64_t shard_count, int64_t *n_moves, int32_t *out_moves,
                                 double *out_lnl, void *stream);
-
-/* ---- libpllWrapper compat (libpllWrapper.c:97-239): opaque problem handle ---- */
-typedef struct plg_pll plg_pll;
-/* new(alignment_file, newick, partition_file) -- PHYLIP file, unrooted Newick,
- * partition file "DNA, p1 = 1-N" | "WAG, p1 = 1-N" (pll.py:112-115). */
-int plg_pll_new(const char *phylip_path, const char *newick, const char *partition_path,
-                plg_pll **out);
-int plg_pll_destroy(plg_pll *p);
-/* getLogLikelihood(handle): branch-length smoothing (3 passes) then lnL (:195-215). */
-int plg_pll_loglik(plg_pll *p, double *out);
-/* getNewickString(handle) (:217-239); returns needed size in *len when buf too small. */
-int plg_pll_newick(plg_pll *p, char *buf, size_t *len);
 
 #ifdef __cplusplus
 }

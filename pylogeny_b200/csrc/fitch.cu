@@ -87,7 +87,8 @@ fitch_level_kernel(const unsigned int *__restrict__ tips, unsigned int *__restri
         for (int v = 0; v < VW; v++) orr[s][v] = acc[s][v];
       }
     }
-    for (int j = 1; j < op.nchild; j++) {
+    const int nfold = op.nchild == FITCH_JOIN3 ? 2 : op.nchild;
+    for (int j = 1; j < nfold; j++) {
       const int cj = children[op.child_off + j];
       const unsigned int *src = (cj < n_tip_slots ? tips + (int64_t)cj * vec_words
                                                   : scratch + (int64_t)(cj - n_tip_slots) * vec_words) + w0;
@@ -110,6 +111,27 @@ fitch_level_kernel(const unsigned int *__restrict__ tips, unsigned int *__restri
           acc[s][v] = (acc[s][v] | empty[v]) & x[s][v];
           orr[s][v] |= x[s][v];
         }
+    }
+    if (op.nchild == FITCH_JOIN3) {
+      // edge-insertion test: state set of the first two operands joined (Fitch), intersected
+      // with the third; only the miss count is kept
+      const int c2 = children[op.child_off + 2];
+      const unsigned int *src = (c2 < n_tip_slots ? tips + (int64_t)c2 * vec_words
+                                                  : scratch + (int64_t)(c2 - n_tip_slots) * vec_words) + w0;
+      unsigned int any[VW];
+#pragma unroll
+      for (int v = 0; v < VW; v++) {
+        any[v] = 0;
+#pragma unroll
+        for (int s = 0; s < K; s++) any[v] |= acc[s][v];
+      }
+#pragma unroll
+      for (int s = 0; s < K; s++) {
+        unsigned int x[VW];
+        load_vec<VW>(src + s * words32, x);
+#pragma unroll
+        for (int v = 0; v < VW; v++) acc[s][v] = (acc[s][v] | (~any[v] & orr[s][v])) & x[v];
+      }
     }
     unsigned int miss[VW];
 #pragma unroll
@@ -144,7 +166,8 @@ fitch_level_kernel(const unsigned int *__restrict__ tips, unsigned int *__restri
         partial += c << b;
       }
     }
-    partial *= (unsigned int)(op.nchild - 1);  // numChildren-1 per missed pattern (:264)
+    if (op.nchild > 2) partial *= (unsigned int)(op.nchild - 1);  // numChildren-1 per missed pattern (:264)
+    if (op.nchild == 1) partial = 0;
   }
   // block reduction -> one integer atomic per block (order-independent => deterministic)
   partial = __reduce_add_sync(0xffffffffu, partial);
@@ -423,11 +446,6 @@ void score_batch_full(FitchAln &a, const TreeBatch &b, int32_t *out_costs, cudaS
 // C-ABI
 // ----------------------------------------------------------------------------
 using namespace plg;
-
-struct plg_fitch_aln {
-  FitchAln impl;
-  plg_fitch_aln(int64_t P, int n_cols, const uint8_t *s, const int64_t *w) : impl(P, n_cols, s, w) {}
-};
 
 static std::vector<uint8_t> gather_profiles(int64_t n_prof, const char *const *profiles, int *n_cols) {
   size_t mn = SIZE_MAX;

@@ -6,6 +6,7 @@
 namespace plg {
 
 constexpr int FITCH_MAX_PLANES = 20;
+constexpr int FITCH_JOIN3 = -3;  // FitchOp::nchild marker: cost += miss(fitch(c0, c1), c2), nothing stored
 
 // One internal node = one op (16 bytes, read once per block).
 struct FitchOp {
@@ -50,3 +51,9 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
 void score_batch_full(FitchAln &a, const TreeBatch &b, int32_t *out_costs, cudaStream_t st);
 
 }  // namespace plg
+
+// opaque handle of the C-ABI
+struct plg_fitch_aln {
+  plg::FitchAln impl;
+  plg_fitch_aln(int64_t P, int n_cols, const uint8_t *s, const int64_t *w) : impl(P, n_cols, s, w) {}
+};

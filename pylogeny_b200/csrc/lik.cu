@@ -145,6 +145,31 @@ clv_update_kernel(const LikOp *__restrict__ ops, int blocks_per_op, int n_rows, 
   if (r == 0) scl[(int64_t)(op.dst - n_rows) * Ppad + p] = sc + (rescale ? 1 : 0);
 }
 
+// Operand value at the evaluation point: P x when a matrix is given, x itself when pm < 0.
+template <int K, int R>
+__device__ __forceinline__ void eval_operand(const double *sm, int id, int pm, int n_rows, int64_t p, int r,
+                                             int64_t Ppad, const unsigned char *__restrict__ codes,
+                                             const unsigned int *__restrict__ masks, const double *__restrict__ clv,
+                                             const int *__restrict__ scl, double (&v)[K], int &sc) {
+  const bool tip = id < n_rows;
+  if (pm >= 0) {
+    apply_operand<K, R>(sm, tip, id, n_rows, p, r, Ppad, codes, clv, v);
+  } else if (tip) {
+    const unsigned int m = masks[codes[(int64_t)id * Ppad + p]];
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = (m >> k & 1) ? 1.0 : 0.0;
+  } else {
+    const double *src = clv + ((int64_t)(id - n_rows) * R * K + r * K) * Ppad + p;
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = __ldg(src + (int64_t)k * Ppad);
+  }
+  if (!tip) sc += scl[(int64_t)(id - n_rows) * Ppad + p];
+}
+
+// Site log-likelihood at a node joining up to three subtrees:
+//   L_p = (1/R) sum_r sum_k pi_k prod_{o in a,b,c} (P_o x_o)[k]
+// Two operands = evaluation across a branch (libpll `evaluate`); three = a subtree inserted
+// into the middle of an edge (edge-insertion scoring of an SPR neighbour).
 template <int K, int R>
 __global__ void __launch_bounds__(LIK_THREADS)
 root_eval_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_rows, int64_t Ppad,
@@ -154,31 +179,31 @@ root_eval_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_r
                  const double *__restrict__ clv, const int *__restrict__ scl, double *__restrict__ partial) {
   constexpr int KKP = K * K + 1, NC = NCodes<K>::value;
   constexpr int SM = (NC * R * K > R * KKP) ? NC * R * K : R * KKP;
-  __shared__ double smB[SM];
+  __shared__ double sm[3][SM];
   __shared__ double warp_sums[LIK_THREADS / 32];
   const int ev_idx = blockIdx.x / blocks_per_eval;
   const int pb = blockIdx.x - ev_idx * blocks_per_eval;
   const LikEval ev = evals[ev_idx];
-  const bool tipA = ev.a < n_rows, tipB = ev.b < n_rows;
-  stage_operand<K, R>(smB, tipB, ev.pm, pmat, tiptab);
+  if (ev.pa >= 0) stage_operand<K, R>(sm[0], ev.a < n_rows, ev.pa, pmat, tiptab);
+  if (ev.pb >= 0) stage_operand<K, R>(sm[1], ev.b < n_rows, ev.pb, pmat, tiptab);
+  if (ev.c >= 0 && ev.pc >= 0) stage_operand<K, R>(sm[2], ev.c < n_rows, ev.pc, pmat, tiptab);
   __syncthreads();
   const int r = threadIdx.x % R;
   const int64_t p = (int64_t)pb * (LIK_THREADS / R) + threadIdx.x / R;
-  double vb[K];
-  apply_operand<K, R>(smB, tipB, ev.b, n_rows, p, r, Ppad, codes, clv, vb);
-  double term = 0.0;
-  int sc = tipB ? 0 : scl[(int64_t)(ev.b - n_rows) * Ppad + p];
-  if (tipA) {
-    const unsigned int m = masks[codes[(int64_t)ev.a * Ppad + p]];
+  double v[K], x[K];
+  int sc = 0;
+  eval_operand<K, R>(sm[0], ev.a, ev.pa, n_rows, p, r, Ppad, codes, masks, clv, scl, v, sc);
+  eval_operand<K, R>(sm[1], ev.b, ev.pb, n_rows, p, r, Ppad, codes, masks, clv, scl, x, sc);
 #pragma unroll
-    for (int k = 0; k < K; k++)
-      if (m >> k & 1) term = fma(model->freqs[k], vb[k], term);
-  } else {
-    const double *src = clv + ((int64_t)(ev.a - n_rows) * R * K + r * K) * Ppad + p;
+  for (int k = 0; k < K; k++) v[k] *= x[k];
+  if (ev.c >= 0) {
+    eval_operand<K, R>(sm[2], ev.c, ev.pc, n_rows, p, r, Ppad, codes, masks, clv, scl, x, sc);
 #pragma unroll
-    for (int k = 0; k < K; k++) term = fma(model->freqs[k] * __ldg(src + (int64_t)k * Ppad), vb[k], term);
-    sc += scl[(int64_t)(ev.a - n_rows) * Ppad + p];
+    for (int k = 0; k < K; k++) v[k] *= x[k];
   }
+  double term = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; k++) term = fma(model->freqs[k], v[k], term);
 #pragma unroll
   for (int d = 1; d < R; d <<= 1) term += __shfl_xor_sync(0xffffffffu, term, d);
   double val = 0.0;
@@ -325,7 +350,8 @@ void build_full_lik_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_ro
           // site likelihood across the last branch; sum_k pi_k A_k (P B)_k is symmetric in A,B
           // (reversibility), and for a bifurcating root P(ta)A . P(tb)B collapses to P(ta+tb)
           LikEval ev;
-          ev.a = acc_id; ev.b = cid; ev.pm = prog.pm(acc_len + clen);
+          ev.a = acc_id; ev.pa = -1; ev.b = cid; ev.pb = prog.pm(acc_len + clen);
+          ev.c = -1; ev.pc = -1; ev.pad = 0;
           if (ev.b < n_rows && ev.a >= n_rows) std::swap(ev.a, ev.b);  // tip on the indicator side
           ev.tree = (int)(t - t0);
           prog.evals.push_back(ev);
@@ -445,15 +471,6 @@ void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double 
 // C-ABI
 // ----------------------------------------------------------------------------
 using namespace plg;
-
-struct plg_lik_aln {
-  LikAln impl;
-  plg_lik_aln(int dt, int n, int64_t P, const uint8_t *c, const double *w) : impl(dt, n, P, c, w) {}
-};
-struct plg_model {
-  Model impl;
-  plg_model(int K, const double *e, const double *f, double a, int n) : impl(K, e, f, a, n) {}
-};
 
 extern "C" int plg_lik_aln_create(int datatype, int n_rows, int64_t n_patterns, const uint8_t *codes,
                                   const double *weights, plg_lik_aln **out) {

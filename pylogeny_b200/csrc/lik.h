@@ -12,9 +12,10 @@ namespace plg {
 struct LikOp {
   int dst, a, b, pa, pb;
 };
-// lnL[tree] += sum_p w_p log( (1/R) sum_r sum_k pi_k A_r[k] (P[pm]_r B_r)[k] ) + scalers
+// lnL[tree] = sum_p w_p log( (1/R) sum_r sum_k pi_k prod_o (P[po] x_o)_r[k] ) + scalers over the
+// operands o in {a, b, c}; c < 0 = absent; pm < 0 = identity (the operand sits at the node itself)
 struct LikEval {
-  int a, b, pm, tree;
+  int a, pa, b, pb, c, pc, tree, pad;
 };
 
 struct LikWorkspace {
@@ -57,3 +58,13 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
 void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double *out_lnl, cudaStream_t st);
 
 }  // namespace plg
+
+// opaque handles of the C-ABI
+struct plg_lik_aln {
+  plg::LikAln impl;
+  plg_lik_aln(int dt, int n, int64_t P, const uint8_t *c, const double *w) : impl(dt, n, P, c, w) {}
+};
+struct plg_model {
+  plg::Model impl;
+  plg_model(int K, const double *e, const double *f, double a, int n) : impl(K, e, f, a, n) {}
+};

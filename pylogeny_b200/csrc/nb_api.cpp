@@ -1,0 +1,152 @@
+// C-ABI entry points that score a whole rearrangement neighbourhood in one call
+// (replaces the per-neighbour loop landscape.py:724-756 and, for likelihood, the closest
+// reference analogue libpllWrapper.c:241-319 getSPR/NNIMovesInDistance).
+#include <algorithm>
+
+#include "neighbourhood.h"
+
+using namespace plg;
+
+namespace {
+
+int depth_for(int move_type) {
+  if (move_type == PLG_MOVE_NNI) return 1;
+  if (move_type == PLG_MOVE_SPR) return -1;
+  PLG_FAIL(PLG_ERR_UNSUPPORTED, "move type %d: only NNI (2) and SPR (1) neighbourhoods are built in", move_type);
+}
+
+void fill_moves(const Neighbourhood &nb, int32_t *out_moves) {
+  if (!out_moves) return;
+  const UTree &t = nb.t;
+  for (size_t i = 0; i < nb.unique.size(); i++) {
+    const Move &m = nb.moves[nb.unique[i]];
+    const int v = t.nb[m.u][m.k];
+    const int pe = t.rooted_child_end[3 * m.u + m.k];
+    out_moves[4 * i + 0] = pe;                 // child end of the pruned branch (base-tree node id)
+    out_moves[4 * i + 1] = pe == v ? 0 : 1;    // 0: the subtree below it moves; 1: its complement moves
+    out_moves[4 * i + 2] = t.rooted_child_end[3 * m.x + m.kx];  // child end of the target branch
+    out_moves[4 * i + 3] = m.depth;            // 1 = NNI
+  }
+}
+
+void shard_range(int64_t M, int64_t idx, int64_t cnt, int64_t *lo, int64_t *hi) {
+  if (cnt < 1 || idx < 0 || idx >= cnt) PLG_FAIL(PLG_ERR_ARG, "bad shard %lld of %lld", (long long)idx, (long long)cnt);
+  *lo = M * idx / cnt;
+  *hi = M * (idx + 1) / cnt;
+}
+
+}  // namespace
+
+extern "C" int plg_neighbourhood_size(int move_type, int n_tips, const int32_t *desc, int64_t *n_moves) {
+  PLG_API_BEGIN
+  if (!desc || !n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, nullptr), depth_for(move_type));
+  *n_moves = (int64_t)nb.unique.size();
+  PLG_API_END
+}
+
+extern "C" int plg_neighbourhood_trees(int move_type, int n_tips, const int32_t *desc, const double *brlen,
+                                       int64_t n_sel, const int64_t *sel, int32_t *out_desc, double *out_brlen,
+                                       uint64_t *out_hash) {
+  PLG_API_BEGIN
+  if (!desc || (n_sel > 0 && !sel)) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, brlen), depth_for(move_type));
+  const size_t stride = (size_t)(n_tips - 1) * 2;
+  for (int64_t i = 0; i < n_sel; i++) {
+    if (sel[i] < 0 || sel[i] >= (int64_t)nb.unique.size()) PLG_FAIL(PLG_ERR_ARG, "move index out of range");
+    const Move &m = nb.moves[nb.unique[sel[i]]];
+    if (out_desc) {
+      UTree r = apply_move(nb.t, m);
+      desc_from_utree(r, out_desc + i * stride, out_brlen ? out_brlen + i * stride : nullptr);
+    }
+    if (out_hash) out_hash[i] = m.hash;
+  }
+  PLG_API_END
+}
+
+extern "C" int plg_topology_hash(int n_tips, const int32_t *desc, uint64_t *out) {
+  PLG_API_BEGIN
+  if (!desc || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  *out = topology_hash(utree_from_desc(n_tips, desc, nullptr));
+  PLG_API_END
+}
+
+extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, int n_tips, const int32_t *desc,
+                                             const int32_t *tip_rows, int64_t shard_index, int64_t shard_count,
+                                             int64_t *n_moves, int32_t *out_moves, int32_t *out_costs,
+                                             void *stream) {
+  PLG_API_BEGIN
+  if (!aln || !desc || !n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  FitchAln &a = aln->impl;
+  for (int x = 0; x < n_tips; x++) {
+    int row = tip_rows ? tip_rows[x] : x;
+    if (row < 0 || row >= a.n_cols) PLG_FAIL(PLG_ERR_ARG, "tip row %d is outside the alignment", row);
+  }
+  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, nullptr), depth_for(move_type));
+  const int64_t M = (int64_t)nb.unique.size();
+  *n_moves = M;
+  fill_moves(nb, out_moves);
+  if (!out_costs || M == 0) return PLG_OK;
+  int64_t lo, hi;
+  shard_range(M, shard_index, shard_count, &lo, &hi);
+  size_t free_b = 0, total_b = 0;
+  PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t vec_bytes = (size_t)a.K * a.words32 * 4;
+  const size_t budget = std::min<size_t>((free_b + a.ws.scratch.n * 4) / 2, (size_t)64 << 30);
+  const int64_t max_slots = std::max<int64_t>(4 * n_tips, (int64_t)(budget / vec_bytes));
+  FitchNbProgram p;
+  std::vector<int32_t> acc;
+  int64_t chunk = hi - lo;
+  for (int64_t c0 = lo; c0 < hi;) {
+    int64_t c1 = std::min(hi, c0 + chunk);
+    build_fitch_nb_program(nb, tip_rows, a.n_cols, c0, c1, p);
+    if (p.prog.n_scratch_slots > max_slots && c1 - c0 > 1) {
+      chunk = std::max<int64_t>(1, (c1 - c0) / 2);
+      continue;
+    }
+    acc.resize(p.prog.n_costs);
+    run_fitch_program(a, a.ws, p.prog, acc.data(), (cudaStream_t)stream);
+    finish_fitch_nb(nb, p, acc.data(), c0, c1, out_costs + c0);
+    c0 = c1;
+  }
+  PLG_API_END
+}
+
+extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int move_type, int n_tips,
+                                           const int32_t *desc, const double *brlen, const int32_t *tip_rows,
+                                           int64_t shard_index, int64_t shard_count, int64_t *n_moves,
+                                           int32_t *out_moves, double *out_lnl, void *stream) {
+  PLG_API_BEGIN
+  if (!aln || !m || !desc || !brlen || !n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  LikAln &a = aln->impl;
+  for (int x = 0; x < n_tips; x++) {
+    int row = tip_rows ? tip_rows[x] : x;
+    if (row < 0 || row >= a.n_rows) PLG_FAIL(PLG_ERR_ARG, "tip row %d is outside the alignment", row);
+  }
+  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, brlen), depth_for(move_type));
+  const int64_t M = (int64_t)nb.unique.size();
+  *n_moves = M;
+  fill_moves(nb, out_moves);
+  if (!out_lnl || M == 0) return PLG_OK;
+  int64_t lo, hi;
+  shard_range(M, shard_index, shard_count, &lo, &hi);
+  size_t free_b = 0, total_b = 0;
+  PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t slot_bytes = ((size_t)m->impl.R * a.K * 8 + 4) * a.Ppad;
+  const size_t held = a.ws.clv.n * 8 + a.ws.scl.n * 4;
+  const size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)80 << 30);
+  const int64_t max_slots = std::max<int64_t>(4 * n_tips, (int64_t)(budget / slot_bytes));
+  LikProgram p;
+  int64_t chunk = hi - lo;
+  for (int64_t c0 = lo; c0 < hi;) {
+    int64_t c1 = std::min(hi, c0 + chunk);
+    build_lik_nb_program(nb, tip_rows, a.n_rows, c0, c1, p);
+    if (p.n_slots > max_slots && c1 - c0 > 1) {
+      chunk = std::max<int64_t>(1, (c1 - c0) / 2);
+      continue;
+    }
+    run_lik_program(a, m->impl, a.ws, p, out_lnl + c0, (cudaStream_t)stream);
+    c0 = c1;
+  }
+  PLG_API_END
+}

@@ -1,0 +1,499 @@
+#include "neighbourhood.h"
+
+#include <algorithm>
+#include <unordered_map>
+
+namespace plg {
+
+namespace {
+
+inline uint64_t splitmix(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// Directed edges of an unrooted tree in dependency order.  D[x->y] (the partial of x's side
+// seen from y) needs D[a->x], D[b->x] for x's other neighbours a, b.
+struct DirOrder {
+  std::vector<int> order;  // directed edge ids 3*x+k with x internal, dependencies first
+  std::vector<int> level;  // per directed edge id (tips: 0)
+  int max_level = 0;
+};
+
+DirOrder dir_order(const UTree &t) {
+  DirOrder d;
+  d.level.assign((size_t)t.n_nodes * 3, 0);
+  if (t.n_tips < 3) return d;
+  // BFS from tip 0
+  std::vector<int> par(t.n_nodes, -1), bfs;
+  bfs.reserve(t.n_nodes);
+  bfs.push_back(0);
+  for (size_t i = 0; i < bfs.size(); i++) {
+    int x = bfs[i];
+    for (int k = 0; k < 3; k++) {
+      int y = t.nb[x][k];
+      if (y >= 0 && y != par[x]) {
+        par[y] = x;
+        bfs.push_back(y);
+      }
+    }
+  }
+  // down directions x -> par[x], leaves first
+  for (size_t i = bfs.size(); i-- > 1;) {
+    int x = bfs[i];
+    if (t.is_tip(x)) continue;
+    int k = t.slot_of(x, par[x]);
+    int lv = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        int c = t.nb[x][j];
+        lv = std::max(lv, d.level[3 * c + t.slot_of(c, x)]);
+      }
+    d.level[3 * x + k] = lv + 1;
+    d.order.push_back(3 * x + k);
+  }
+  // up directions p -> x for internal p, root side first
+  for (size_t i = 1; i < bfs.size(); i++) {
+    int x = bfs[i], p = par[x];
+    if (t.is_tip(p)) continue;  // p == tip 0: D[0->x] is the tip itself
+    int k = t.slot_of(p, x);
+    int lv = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        int c = t.nb[p][j];
+        lv = std::max(lv, d.level[3 * c + t.slot_of(c, p)]);
+      }
+    d.level[3 * p + k] = lv + 1;
+    d.order.push_back(3 * p + k);
+  }
+  for (int e : d.order) d.max_level = std::max(d.max_level, d.level[e]);
+  return d;
+}
+
+// XOR of leaf keys on x's side of every directed edge, and their grand total.
+std::vector<uint64_t> side_hashes(const UTree &t, const DirOrder &d, uint64_t *all) {
+  std::vector<uint64_t> h((size_t)t.n_nodes * 3, 0);
+  uint64_t tot = 0;
+  for (int x = 0; x < t.n_tips; x++) {
+    uint64_t key = splitmix((uint64_t)x + 1);
+    tot ^= key;
+    for (int k = 0; k < 3; k++) h[3 * x + k] = key;
+  }
+  for (int e : d.order) {
+    int x = e / 3, k = e % 3;
+    uint64_t v = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        int c = t.nb[x][j];
+        v ^= h[3 * c + t.slot_of(c, x)];
+      }
+    h[e] = v;
+  }
+  *all = tot;
+  return h;
+}
+
+inline uint64_t split_term(uint64_t side, uint64_t all) { return splitmix(std::min(side, side ^ all)); }
+
+}  // namespace
+
+UTree utree_from_desc(int n_tips, const int32_t *desc, const double *brlen) {
+  if (n_tips < 2) PLG_FAIL(PLG_ERR_ARG, "a tree needs at least 2 tips");
+  const int n = n_tips, ni = n - 1, root = n + ni - 1;
+  std::vector<int> parent(2 * n - 1, -1);
+  std::vector<double> plen(2 * n - 1, 0.0);
+  for (int i = 0; i < ni; i++)
+    for (int c = 0; c < 2; c++) {
+      int ch = desc[2 * i + c];
+      if (ch < 0 || ch >= n + i || parent[ch] >= 0)
+        PLG_FAIL(PLG_ERR_ARG, "descriptor node %d: child %d is not a valid earlier node", i, ch);
+      parent[ch] = n + i;
+      plen[ch] = brlen ? brlen[2 * i + c] : 0.0;
+    }
+  for (int x = 0; x < root; x++)
+    if (parent[x] < 0) PLG_FAIL(PLG_ERR_ARG, "descriptor does not connect node %d", x);
+  UTree t;
+  t.n_tips = n;
+  t.n_nodes = 2 * n - 2;
+  t.nb.assign(t.n_nodes, {-1, -1, -1});
+  t.len.assign(t.n_nodes, {0.0, 0.0, 0.0});
+  t.rooted_child_end.assign((size_t)t.n_nodes * 3, -1);
+  auto link = [&](int x, int y, double l, int child_end) {
+    for (int pass = 0; pass < 2; pass++) {
+      int a = pass ? y : x, b = pass ? x : y;
+      int k = 0;
+      while (k < 3 && t.nb[a][k] >= 0) k++;
+      if (k == 3) PLG_FAIL(PLG_ERR_ARG, "descriptor is not binary at node %d", a);
+      t.nb[a][k] = b;
+      t.len[a][k] = l;
+      t.rooted_child_end[3 * a + k] = child_end;
+    }
+  };
+  // internal nodes list their two children first, then the parent side
+  for (int i = 0; i < ni - 1; i++)
+    for (int c = 0; c < 2; c++) {
+      int ch = desc[2 * i + c];
+      link(n + i, ch, plen[ch], ch);
+    }
+  const int c0 = desc[2 * (ni - 1)], c1 = desc[2 * (ni - 1) + 1];
+  link(c0, c1, plen[c0] + plen[c1], c0);  // the edge through the root is named by its first child
+  return t;
+}
+
+uint64_t topology_hash(const UTree &t) {
+  DirOrder d = dir_order(t);
+  uint64_t all;
+  std::vector<uint64_t> h = side_hashes(t, d, &all);
+  uint64_t s = 0;
+  for (int x = 0; x < t.n_nodes; x++)
+    for (int k = 0; k < 3; k++) {
+      int y = t.nb[x][k];
+      if (y > x) s += split_term(h[3 * x + k], all);
+    }
+  return s;
+}
+
+Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
+  Neighbourhood nb;
+  nb.t = t;
+  DirOrder d = dir_order(t);
+  uint64_t all;
+  std::vector<uint64_t> h = side_hashes(t, d, &all);
+  uint64_t base = 0;
+  for (int x = 0; x < t.n_nodes; x++)
+    for (int k = 0; k < 3; k++)
+      if (t.nb[x][k] > x) base += split_term(h[3 * x + k], all);
+  nb.base_hash = base;
+  if (t.n_tips < 4) return nb;
+  struct Frame { int x, from, parent_move, depth; uint64_t rem, add; };
+  std::vector<Frame> st;
+  for (int u = t.n_tips; u < t.n_nodes; u++)
+    for (int k = 0; k < 3; k++) {
+      const int v = t.nb[u][k];
+      const uint64_t hv = h[3 * v + t.slot_of(v, u)];
+      for (int side = 0; side < 2; side++) {
+        const int start = t.nb[u][(k + 1 + side) % 3];
+        st.push_back({start, u, -1, 0, split_term(h[3 * start + t.slot_of(start, u)], all), 0});
+        while (!st.empty()) {
+          Frame f = st.back();
+          st.pop_back();
+          if (t.is_tip(f.x)) continue;
+          if (max_depth >= 0 && f.depth >= max_depth) continue;
+          for (int j = 2; j >= 0; j--) {  // (reverse so that the stack pops in neighbour order)
+            const int c = t.nb[f.x][j];
+            if (c == f.from) continue;
+            const uint64_t far = h[3 * c + t.slot_of(c, f.x)];
+            Move m;
+            m.u = u; m.k = k; m.x = f.x; m.kx = j; m.depth = f.depth + 1; m.parent = f.parent_move;
+            m.side = side;
+            m.hash = base - f.rem + f.add + split_term(far ^ hv, all);
+            m.unique_id = -1;
+            nb.moves.push_back(m);
+            st.push_back({c, f.x, (int)nb.moves.size() - 1, f.depth + 1, f.rem + split_term(far, all),
+                          f.add + split_term(far ^ hv, all)});
+          }
+        }
+      }
+    }
+  std::unordered_map<uint64_t, int> seen;
+  seen.reserve(nb.moves.size() * 2);
+  seen.emplace(base, -1);
+  for (size_t i = 0; i < nb.moves.size(); i++) {
+    auto ins = seen.emplace(nb.moves[i].hash, (int)i);
+    if (ins.second) {
+      nb.moves[i].unique_id = (int)nb.unique.size();
+      nb.unique.push_back((int)i);
+    }
+  }
+  return nb;
+}
+
+UTree apply_move(const UTree &t, const Move &m) {
+  UTree r = t;
+  const int u = m.u, v = t.nb[u][m.k];
+  const int a = t.nb[u][(m.k + 1) % 3], b = t.nb[u][(m.k + 2) % 3];
+  const double la = t.len[u][(m.k + 1) % 3], lb = t.len[u][(m.k + 2) % 3], lv = t.len[u][m.k];
+  // suppress u: a -- b with the summed length (rearrangement.py:480-490)
+  const int ka = r.slot_of(a, u), kb = r.slot_of(b, u);
+  r.nb[a][ka] = b; r.len[a][ka] = la + lb;
+  r.nb[b][kb] = a; r.len[b][kb] = la + lb;
+  // break the target edge in half and hang u (with the pruned branch) in the middle (:466-478)
+  const int x = m.x, c = t.nb[x][m.kx];
+  const double half = t.len[x][m.kx] / 2.0;
+  const int kx = r.slot_of(x, c), kc = r.slot_of(c, x);
+  r.nb[x][kx] = u; r.len[x][kx] = half;
+  r.nb[c][kc] = u; r.len[c][kc] = half;
+  r.nb[u] = {v, x, c};
+  r.len[u] = {lv, half, half};
+  for (auto &e : r.rooted_child_end) e = -1;  // names of the base tree no longer apply
+  return r;
+}
+
+void desc_from_utree(const UTree &t, int32_t *desc, double *brlen) {
+  const int n = t.n_tips;
+  if (n == 2) {
+    desc[0] = 0; desc[1] = 1;
+    if (brlen) { brlen[0] = t.len[0][0]; brlen[1] = 0.0; }
+    return;
+  }
+  // iterative post-order from tip 0's neighbour, away from tip 0
+  const int w = t.nb[0][0];
+  std::vector<int> new_id(t.n_nodes, -1);
+  for (int x = 0; x < n; x++) new_id[x] = x;
+  struct Frame { int x, from, next; };
+  std::vector<Frame> st;
+  st.push_back({w, 0, 0});
+  int made = 0;
+  while (!st.empty()) {
+    Frame &f = st.back();
+    if (t.is_tip(f.x)) { st.pop_back(); continue; }
+    if (f.next < 3) {
+      int c = t.nb[f.x][f.next++];
+      if (c != f.from) st.push_back({c, f.x, 0});
+      continue;
+    }
+    int slot = 0;
+    for (int j = 0; j < 3; j++) {
+      int c = t.nb[f.x][j];
+      if (c == f.from) continue;
+      desc[2 * made + slot] = new_id[c];
+      if (brlen) brlen[2 * made + slot] = t.len[f.x][j];
+      slot++;
+    }
+    new_id[f.x] = n + made++;
+    st.pop_back();
+  }
+  desc[2 * made] = 0;
+  desc[2 * made + 1] = new_id[w];
+  if (brlen) { brlen[2 * made] = t.len[0][0]; brlen[2 * made + 1] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// edge-insertion programs
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// moves needed by unique[lo..hi): the selected ones and every ancestor on their search paths
+std::vector<char> needed_moves(const Neighbourhood &nb, int64_t lo, int64_t hi) {
+  std::vector<char> need(nb.moves.size(), 0);
+  for (int64_t i = lo; i < hi; i++) {
+    int m = nb.unique[i];
+    while (m >= 0 && !need[m]) {
+      need[m] = 1;
+      m = nb.moves[m].parent;
+    }
+  }
+  return need;
+}
+
+}  // namespace
+
+void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_tip_slots, int64_t lo,
+                            int64_t hi, FitchNbProgram &out) {
+  const UTree &t = nb.t;
+  FitchProgram &prog = out.prog;
+  prog.clear();
+  DirOrder d = dir_order(t);
+  out.dir_acc.assign((size_t)t.n_nodes * 3, -1);
+  out.dir_kids.assign((size_t)t.n_nodes * 3, {-1, -1});
+  std::vector<int> dir_slot((size_t)t.n_nodes * 3, -1);  // operand id of D[x->.]
+  for (int x = 0; x < t.n_tips; x++)
+    for (int k = 0; k < 3; k++) dir_slot[3 * x + k] = tip_rows ? tip_rows[x] : x;
+  struct Tmp { FitchOp op; int level; int kids[3]; };
+  std::vector<Tmp> tmp;
+  int64_t slots = 0, accs = 0;
+  for (int e : d.order) {
+    const int x = e / 3, k = e % 3;
+    Tmp o;
+    o.op.dst = n_tip_slots + (int)slots++;
+    o.op.nchild = 2;
+    o.op.tree = (int)accs;
+    out.dir_acc[e] = (int)accs++;
+    int s = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        const int c = t.nb[x][j];
+        const int ce = 3 * c + t.slot_of(c, x);
+        o.kids[s] = dir_slot[ce];
+        out.dir_kids[e][s] = t.is_tip(c) ? -1 : ce;
+        s++;
+      }
+    o.kids[2] = -1;
+    o.level = d.level[e];
+    dir_slot[e] = o.op.dst;
+    tmp.push_back(o);
+  }
+  const int dump_acc = (int)accs++;  // search-step partials add their own misses here (unused)
+  out.first_move_acc = accs;
+  std::vector<char> need = needed_moves(nb, lo, hi);
+  std::vector<int> n_slot(nb.moves.size(), -1);
+  int max_depth = 0;
+  for (size_t i = 0; i < nb.moves.size(); i++) {
+    if (!need[i]) continue;
+    const Move &m = nb.moves[i];
+    const int x = m.x, c = t.nb[x][m.kx];
+    int from, xin;
+    if (m.parent < 0) {
+      const int other = t.nb[m.u][(m.k + 1 + (1 - m.side)) % 3];
+      from = m.u;
+      xin = dir_slot[3 * other + t.slot_of(other, m.u)];  // D[other->u] enters x over the merged edge
+    } else {
+      from = nb.moves[m.parent].x;
+      xin = n_slot[m.parent];
+    }
+    int s = -1;
+    for (int j = 0; j < 3; j++)
+      if (t.nb[x][j] != from && t.nb[x][j] != c) s = t.nb[x][j];
+    Tmp o;
+    o.op.dst = n_tip_slots + (int)slots++;
+    o.op.nchild = 2;
+    o.op.tree = dump_acc;
+    o.kids[0] = xin;
+    o.kids[1] = dir_slot[3 * s + t.slot_of(s, x)];
+    o.kids[2] = -1;
+    o.level = d.max_level + m.depth;
+    n_slot[i] = o.op.dst;
+    max_depth = std::max(max_depth, m.depth);
+    tmp.push_back(o);
+  }
+  for (int64_t i = lo; i < hi; i++) {
+    const int mi = nb.unique[i];
+    const Move &m = nb.moves[mi];
+    const int v = t.nb[m.u][m.k], c = t.nb[m.x][m.kx];
+    Tmp o;
+    o.op.dst = -1;
+    o.op.nchild = FITCH_JOIN3;
+    o.op.tree = (int)(out.first_move_acc + (i - lo));
+    o.kids[0] = n_slot[mi];
+    o.kids[1] = dir_slot[3 * c + t.slot_of(c, m.x)];
+    o.kids[2] = dir_slot[3 * v + t.slot_of(v, m.u)];
+    o.level = d.max_level + max_depth + 1;
+    tmp.push_back(o);
+  }
+  int max_level = 0;
+  for (auto &o : tmp) max_level = std::max(max_level, o.level);
+  prog.level_off.assign(max_level + 2, 0);
+  for (auto &o : tmp) prog.level_off[o.level + 1]++;
+  for (int l = 0; l <= max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+  std::vector<int64_t> cur(prog.level_off.begin(), prog.level_off.end() - 1);
+  prog.ops.resize(tmp.size());
+  prog.children.reserve(tmp.size() * 3);
+  for (auto &o : tmp) {
+    o.op.child_off = (int)prog.children.size();
+    const int nk = o.op.nchild == FITCH_JOIN3 ? 3 : 2;
+    for (int j = 0; j < nk; j++) prog.children.push_back(o.kids[j]);
+    prog.ops[cur[o.level]++] = o.op;
+  }
+  prog.n_scratch_slots = slots;
+  prog.n_costs = out.first_move_acc + (hi - lo);
+}
+
+void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int32_t *acc, int64_t lo, int64_t hi,
+                     int32_t *out_costs) {
+  const UTree &t = nb.t;
+  // total Fitch length of every directional partial: own misses + the two partials below it
+  DirOrder d = dir_order(t);
+  std::vector<uint32_t> total((size_t)t.n_nodes * 3, 0);
+  for (int e : d.order) {
+    uint32_t s = (uint32_t)acc[p.dir_acc[e]];
+    for (int j = 0; j < 2; j++)
+      if (p.dir_kids[e][j] >= 0) s += total[p.dir_kids[e][j]];
+    total[e] = s;
+  }
+  for (int64_t i = lo; i < hi; i++) {
+    const Move &m = nb.moves[nb.unique[i]];
+    const int v = t.nb[m.u][m.k];
+    // length(T') = length(pruned subtree) + length(rest) + [their state sets miss at the new edge]
+    uint32_t c = total[3 * m.u + m.k] + (t.is_tip(v) ? 0u : total[3 * v + t.slot_of(v, m.u)]) +
+                 (uint32_t)acc[p.first_move_acc + (i - lo)];
+    out_costs[i - lo] = (int32_t)c;
+  }
+}
+
+void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
+                          LikProgram &prog) {
+  const UTree &t = nb.t;
+  prog.clear();
+  DirOrder d = dir_order(t);
+  std::vector<int> dir_slot((size_t)t.n_nodes * 3, -1);
+  for (int x = 0; x < t.n_tips; x++)
+    for (int k = 0; k < 3; k++) dir_slot[3 * x + k] = tip_rows ? tip_rows[x] : x;
+  struct Tmp { LikOp op; int level; };
+  std::vector<Tmp> tmp;
+  int64_t slots = 0;
+  for (int e : d.order) {
+    const int x = e / 3, k = e % 3;
+    Tmp o;
+    o.op.dst = n_rows + (int)slots++;
+    int s = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        const int c = t.nb[x][j];
+        const int id = dir_slot[3 * c + t.slot_of(c, x)];
+        const int pm = prog.pm(t.len[x][j]);
+        if (s == 0) { o.op.a = id; o.op.pa = pm; } else { o.op.b = id; o.op.pb = pm; }
+        s++;
+      }
+    o.level = d.level[e];
+    dir_slot[e] = o.op.dst;
+    tmp.push_back(o);
+  }
+  std::vector<char> need = needed_moves(nb, lo, hi);
+  std::vector<int> n_slot(nb.moves.size(), -1);
+  for (size_t i = 0; i < nb.moves.size(); i++) {
+    if (!need[i]) continue;
+    const Move &m = nb.moves[i];
+    const int x = m.x, c = t.nb[x][m.kx];
+    int from, xin;
+    double lin;
+    if (m.parent < 0) {
+      const int ko = (m.k + 1 + (1 - m.side)) % 3, ks = (m.k + 1 + m.side) % 3;
+      const int other = t.nb[m.u][ko];
+      from = m.u;
+      xin = dir_slot[3 * other + t.slot_of(other, m.u)];
+      lin = t.len[m.u][ko] + t.len[m.u][ks];  // merged edge other -- x (rearrangement.py:480-490)
+    } else {
+      const Move &pm = nb.moves[m.parent];
+      from = pm.x;
+      xin = n_slot[m.parent];
+      lin = t.len[pm.x][pm.kx];
+    }
+    int s = -1, ks2 = -1;
+    for (int j = 0; j < 3; j++)
+      if (t.nb[x][j] != from && t.nb[x][j] != c) { s = t.nb[x][j]; ks2 = j; }
+    Tmp o;
+    o.op.dst = n_rows + (int)slots++;
+    o.op.a = xin; o.op.pa = prog.pm(lin);
+    o.op.b = dir_slot[3 * s + t.slot_of(s, x)]; o.op.pb = prog.pm(t.len[x][ks2]);
+    o.level = d.max_level + m.depth;
+    n_slot[i] = o.op.dst;
+    tmp.push_back(o);
+  }
+  for (int64_t i = lo; i < hi; i++) {
+    const int mi = nb.unique[i];
+    const Move &m = nb.moves[mi];
+    const int v = t.nb[m.u][m.k], c = t.nb[m.x][m.kx];
+    const double half = t.len[m.x][m.kx] / 2.0;  // target branch broken in half (rearrangement.py:466-470)
+    LikEval ev;
+    ev.a = n_slot[mi]; ev.pa = prog.pm(half);
+    ev.b = dir_slot[3 * c + t.slot_of(c, m.x)]; ev.pb = prog.pm(half);
+    ev.c = dir_slot[3 * v + t.slot_of(v, m.u)]; ev.pc = prog.pm(t.len[m.u][m.k]);
+    ev.tree = (int)(i - lo);
+    ev.pad = 0;
+    prog.evals.push_back(ev);
+  }
+  int max_level = 0;
+  for (auto &o : tmp) max_level = std::max(max_level, o.level);
+  prog.level_off.assign(max_level + 2, 0);
+  for (auto &o : tmp) prog.level_off[o.level + 1]++;
+  for (int l = 0; l <= max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+  std::vector<int64_t> cur(prog.level_off.begin(), prog.level_off.end() - 1);
+  prog.ops.resize(tmp.size());
+  for (auto &o : tmp) prog.ops[cur[o.level]++] = o.op;
+  prog.n_slots = slots;
+  prog.n_trees = hi - lo;
+}
+
+}  // namespace plg

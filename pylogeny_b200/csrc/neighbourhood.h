@@ -1,0 +1,81 @@
+// Rearrangement neighbourhoods on the host: unrooted view of a base tree, enumeration of the
+// distinct NNI/SPR/TBR neighbours with canonical topology hashes, and the edge-insertion
+// programs that score all of them from the base tree's directional partials.
+//
+// Reference behaviour this stands in for: rearrangement.py:542-594 (iterSPRForBranch,
+// _flipOperation, allSPR), :440-511 (move -- branch lengths of the neighbour), and the
+// per-neighbour scoring loop landscape.py:724-756.  The reference emits 4(n-3)(n-2) SPR moves of
+// which 2(n-3)(2n-7) are distinct topologies; here each distinct topology is
+// produced once (first occurrence in enumeration order).
+#pragma once
+#include <array>
+#include <vector>
+
+#include "fitch.h"
+#include "lik.h"
+
+namespace plg {
+
+// Unrooted binary tree: tips 0..n-1 (degree 1), internal nodes n..2n-3 (degree 3).
+struct UTree {
+  int n_tips = 0, n_nodes = 0;
+  std::vector<std::array<int, 3>> nb;      // neighbours, -1 = none
+  std::vector<std::array<double, 3>> len;  // branch length to that neighbour
+  std::vector<int> rooted_child_end;       // per directed edge 3*x+k: id (rooted desc numbering) naming the edge
+  int slot_of(int x, int y) const {
+    for (int k = 0; k < 3; k++)
+      if (nb[x][k] == y) return k;
+    return -1;
+  }
+  bool is_tip(int x) const { return x < n_tips; }
+};
+
+// Rooted binary descriptor (include/pylogeny_b200.h) -> unrooted tree; the root's two child
+// branches merge into one edge whose length is their sum.
+UTree utree_from_desc(int n_tips, const int32_t *desc, const double *brlen);
+
+struct Move {
+  int u, k;        // pruned: the subtree on nb[u][k]'s side of edge {u, nb[u][k]}; u is suppressed
+  int x, kx;       // target edge {x, nb[x][kx]}, x on the side nearer to u
+  int depth;       // 1 = NNI distance
+  int parent;      // index of the move one step nearer to u on the same search path, -1 at depth 1
+  int side;        // which of u's two remaining neighbours the path left through (0/1)
+  uint64_t hash;   // canonical topology hash of the neighbour
+  int unique_id;   // index among distinct topologies, -1 if a duplicate of an earlier move
+};
+
+struct Neighbourhood {
+  UTree t;
+  std::vector<Move> moves;       // every (prune, target) pair in enumeration order
+  std::vector<int> unique;       // indices into moves, first occurrence of each topology
+  uint64_t base_hash = 0;
+};
+
+// Canonical topology hash of an unrooted tree (sum over edges of a mixed split hash).
+uint64_t topology_hash(const UTree &t);
+// max_depth < 0: all SPR moves; 1: NNI.
+Neighbourhood enumerate_spr(const UTree &t, int max_depth);
+// The neighbour tree of one move, with the reference's branch-length rule (rearrangement.py:466-497).
+UTree apply_move(const UTree &t, const Move &m);
+// Rooted post-order descriptor of an unrooted tree, rooted on tip 0's pendant edge
+// (what rerootToLeaf does for the lowest-order leaf, rearrangement.py:267-331).
+void desc_from_utree(const UTree &t, int32_t *desc, double *brlen);
+
+// Edge-insertion programs over moves unique[lo..hi): directional partials of the base tree, one
+// partial per search step, one join / 3-way evaluation per distinct neighbour.
+struct FitchNbProgram {
+  FitchProgram prog;
+  std::vector<int> dir_acc;                 // accumulator of directional op 3*x+k (-1 for tips)
+  std::vector<std::array<int, 2>> dir_kids; // children directed edges of each directional op
+  int64_t first_move_acc = 0;
+};
+void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_tip_slots, int64_t lo,
+                            int64_t hi, FitchNbProgram &out);
+// Combines the downloaded accumulators into one Fitch length per move in [lo, hi).
+void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int32_t *acc, int64_t lo, int64_t hi,
+                     int32_t *out_costs);
+
+void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
+                          LikProgram &out);
+
+}  // namespace plg

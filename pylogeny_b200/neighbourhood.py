@@ -1,0 +1,164 @@
+"""Whole-neighbourhood scoring: the batched consumer the landscape should call instead of one
+scoring call per neighbour (landscape.py:724-756).
+
+Trees are rooted binary post-order descriptors (int32 [n_tips-1, 2], see
+include/pylogeny_b200.h); `newick_to_desc` / `desc_to_newick` convert from and to the Newick
+strings the rest of Pylogeny uses.  Enumeration and materialisation run on the host (C++ in the
+C-ABI library); scoring runs on the GPU by edge insertion.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MOVE_NNI, MOVE_SPR  # noqa: F401
+
+
+def _desc(desc):
+    d = np.ascontiguousarray(desc, dtype=np.int32)
+    if d.ndim != 2 or d.shape[1] != 2:
+        raise ValueError("descriptor must be int32 [n_tips-1, 2]")
+    return d
+
+
+def neighbourhood_size(desc, move_type=MOVE_SPR):
+    d = _desc(desc)
+    n = C.c_int64()
+    _lib.check(_lib.lib().plg_neighbourhood_size(move_type, d.shape[0] + 1, d.ctypes.data, C.byref(n)))
+    return n.value
+
+
+def topology_hash(desc):
+    d = _desc(desc)
+    h = C.c_uint64()
+    _lib.check(_lib.lib().plg_topology_hash(d.shape[0] + 1, d.ctypes.data, C.byref(h)))
+    return h.value
+
+
+def neighbour_trees(desc, brlen=None, sel=None, move_type=MOVE_SPR):
+    """Materialise neighbours `sel` (default: all). Returns (descs [m, n-1, 2], brlens or None, hashes [m])."""
+    d = _desc(desc)
+    if sel is None:
+        sel = np.arange(neighbourhood_size(d, move_type), dtype=np.int64)
+    sel = np.ascontiguousarray(sel, dtype=np.int64)
+    b = np.ascontiguousarray(brlen, dtype=np.float64) if brlen is not None else None
+    out_d = np.zeros((len(sel),) + d.shape, dtype=np.int32)
+    out_b = np.zeros((len(sel),) + d.shape, dtype=np.float64) if b is not None else None
+    out_h = np.zeros(len(sel), dtype=np.uint64)
+    _lib.check(_lib.lib().plg_neighbourhood_trees(
+        move_type, d.shape[0] + 1, d.ctypes.data, b.ctypes.data if b is not None else None, len(sel),
+        sel.ctypes.data, out_d.ctypes.data, out_b.ctypes.data if out_b is not None else None, out_h.ctypes.data))
+    return out_d, out_b, out_h
+
+
+def score_parsimony(aln, desc, tip_rows=None, move_type=MOVE_SPR, shard=(0, 1)):
+    """Fitch length of every distinct neighbour. aln: fitch.FitchAlignment.
+    Returns (moves int32 [M, 4], costs int32 [M]); with shard=(i, c) only block i of c is filled."""
+    d = _desc(desc)
+    rows = np.ascontiguousarray(tip_rows, dtype=np.int32) if tip_rows is not None else None
+    n = C.c_int64()
+    L = _lib.lib()
+    M = neighbourhood_size(d, move_type)
+    moves = np.zeros((M, 4), dtype=np.int32)
+    costs = np.zeros(M, dtype=np.int32)
+    _lib.check(L.plg_fitch_score_neighbourhood(aln._h, move_type, d.shape[0] + 1, d.ctypes.data,
+                                               rows.ctypes.data if rows is not None else None, shard[0], shard[1],
+                                               C.byref(n), moves.ctypes.data, costs.ctypes.data, None))
+    return moves, costs
+
+
+def score_likelihood(aln, model, desc, brlen, tip_rows=None, move_type=MOVE_SPR, shard=(0, 1)):
+    """lnL (fixed branch lengths) of every distinct neighbour. aln: likelihood.LikAlignment."""
+    d = _desc(desc)
+    b = np.ascontiguousarray(brlen, dtype=np.float64)
+    rows = np.ascontiguousarray(tip_rows, dtype=np.int32) if tip_rows is not None else None
+    n = C.c_int64()
+    M = neighbourhood_size(d, move_type)
+    moves = np.zeros((M, 4), dtype=np.int32)
+    lnl = np.zeros(M, dtype=np.float64)
+    _lib.check(_lib.lib().plg_lik_score_neighbourhood(
+        aln._h, model._h, move_type, d.shape[0] + 1, d.ctypes.data, b.ctypes.data,
+        rows.ctypes.data if rows is not None else None, shard[0], shard[1], C.byref(n), moves.ctypes.data,
+        lnl.ctypes.data, None))
+    return moves, lnl
+
+
+def newick_to_desc(newick, taxa):
+    """Newick string -> (desc int32 [n-1, 2], brlen float64 [n-1, 2], tip_rows int32 [n]).
+
+    `taxa` maps leaf label -> alignment row (the profile_set.taxa dict).  Tips are numbered in order
+    of appearance.  A multifurcating node (e.g. the trifurcating root of toUnrootedNewick,
+    rearrangement.py:715-732) is resolved left to right with zero-length branches, which leaves the
+    unrooted topology and every likelihood unchanged."""
+    s = newick.strip().rstrip(';')
+    pos = [0]
+    tips, rows, desc, brl = [], [], [], []
+
+    def length():
+        if pos[0] < len(s) and s[pos[0]] == ':':
+            j = pos[0] + 1
+            while j < len(s) and s[j] not in ',)':
+                j += 1
+            try:
+                v = float(s[pos[0] + 1:j])
+            except ValueError:
+                v = 0.0
+            pos[0] = j
+            return v
+        return 0.0
+
+    def label():
+        j = pos[0]
+        while j < len(s) and s[j] not in ',:;)':
+            j += 1
+        lab = s[pos[0]:j]
+        pos[0] = j
+        return lab
+
+    def sub():
+        if s[pos[0]] == '(':
+            pos[0] += 1
+            kids = [sub()]
+            while s[pos[0]] == ',':
+                pos[0] += 1
+                kids.append(sub())
+            if s[pos[0]] != ')':
+                raise ValueError("malformed Newick string")
+            pos[0] += 1
+            label()
+            ln = length()
+            node, nl = kids[0]
+            for k, kl in kids[1:]:
+                desc.append((node, k))
+                brl.append((nl, kl))
+                node, nl = ('i', len(desc) - 1), 0.0
+            return node, ln
+        lab = label()
+        ln = length()
+        tips.append(lab)
+        rows.append(taxa[lab])
+        return ('t', len(tips) - 1), ln
+
+    sub()
+    n = len(tips)
+    ids = lambda x: x[1] if x[0] == 't' else n + x[1]
+    d = np.array([(ids(a), ids(b)) for a, b in desc], dtype=np.int32).reshape(-1, 2)
+    return d, np.array(brl, dtype=np.float64).reshape(-1, 2), np.array(rows, dtype=np.int32), tips
+
+
+def desc_to_newick(desc, labels, brlen=None):
+    """Rooted descriptor -> Newick string; children sorted by label like newick.py:40-46 does."""
+    n = len(labels)
+    text = {}
+    for i, (a, b) in enumerate(np.asarray(desc)):
+        parts = []
+        for k, c in enumerate((int(a), int(b))):
+            is_tip = c < n
+            t = labels[c] if is_tip else text[c]
+            key = labels[c] if is_tip else ''
+            if brlen is not None and brlen[i][k] > 0:
+                t += ":%s" % str(float(brlen[i][k]))
+            parts.append((key, t))
+        parts.sort(key=lambda p: p[0])
+        text[n + i] = "(%s)" % ",".join(p[1] for p in parts)
+    return text[n + len(desc) - 1] + ";"

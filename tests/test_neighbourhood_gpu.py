@@ -1,0 +1,84 @@
+"""Whole-neighbourhood scoring by edge insertion vs (a) full re-traversal of the materialised
+neighbour trees on the GPU, (b) the CPU oracles, (c) golden numbers generated from the reference."""
+import numpy as np
+import pytest
+
+import oracle
+from util import desc_to_newick, random_desc, random_states, states_to_profiles
+
+pytestmark = pytest.mark.gpu
+
+
+def test_al_fasta_spr_and_nni_golden(al_profiles, al_fitch):
+    """BASELINE config 1: al.fasta, every SPR / NNI neighbour of the file-order caterpillar."""
+    from pylogeny_b200 import fitch, neighbourhood as nbh
+    a = fitch.FitchAlignment(al_profiles["profiles"], al_profiles["weights"])
+    named = {c["name"]: c for c in al_fitch["named"]}
+    d, _, rows, tips = nbh.newick_to_desc(named["caterpillar_file_order"]["newick"], al_profiles["taxa"])
+    assert a.score_trees(d[None], rows)[0] == 1167
+    moves, costs = nbh.score_parsimony(a, d, rows, nbh.MOVE_SPR)
+    assert len(costs) == 90 and costs.min() == 1149 and costs.max() == 1416 and int(costs.sum()) == 115698
+    # the reference's own 120 SPR moves cover the same set of (topology -> score)
+    ref_scores = sorted(set((m["cost"]) for m in al_fitch["spr_moves"]))
+    assert sorted(set(costs.tolist())) == ref_scores
+    _, nni = nbh.score_parsimony(a, d, rows, nbh.MOVE_NNI)
+    assert sorted(nni.tolist()) == [1161, 1162, 1164, 1165, 1167, 1171, 1179, 1186, 1292, 1292]
+    # every neighbour, materialised and re-scored from scratch, and through the oracle via Newick
+    descs, _, _ = nbh.neighbour_trees(d, None, None, nbh.MOVE_SPR)
+    assert a.score_trees(descs, rows).tolist() == costs.tolist()
+    x = oracle.FitchInputs(al_profiles["profiles"], al_profiles["weights"], al_profiles["taxa"])
+    want = [oracle.fitch_cost(nbh.desc_to_newick(dd, tips), inputs=x) for dd in descs]
+    assert want == costs.tolist()
+    a.close()
+
+
+@pytest.mark.parametrize("n,P,ns", [(4, 50, 4), (9, 300, 5), (33, 2000, 4)])
+def test_fitch_edge_insertion_vs_retraversal(n, P, ns):
+    from pylogeny_b200 import fitch, neighbourhood as nbh
+    rng = np.random.default_rng(n + P)
+    states = random_states(rng, n, P, ns, 0.02)
+    w = np.where(rng.random(P) < 0.3, rng.integers(1, 100, P), 1).astype(np.int64)
+    a = fitch.FitchAlignment.from_dense(states, w)
+    d = random_desc(rng, n)
+    perm = rng.permutation(n).astype(np.int32)  # tips -> alignment rows
+    moves, costs = nbh.score_parsimony(a, d, perm)
+    descs, _, _ = nbh.neighbour_trees(d)
+    full = a.score_trees(descs, perm)
+    assert costs.tolist() == full.tolist()
+    # shards tile the move list
+    parts = [nbh.score_parsimony(a, d, perm, shard=(i, 3))[1] for i in range(3)]
+    M = len(costs)
+    merged = np.concatenate([parts[i][M * i // 3: M * (i + 1) // 3] for i in range(3)])
+    assert merged.tolist() == costs.tolist()
+    # a few against the oracle
+    labels = ["T%d" % i for i in range(n)]
+    taxa = {labels[i]: int(perm[i]) for i in range(n)}
+    x = oracle.FitchInputs(states_to_profiles(states), w.tolist(), taxa)
+    for i in range(0, M, max(1, M // 25)):
+        assert oracle.fitch_cost(desc_to_newick(descs[i], labels), inputs=x) == costs[i]
+    a.close()
+
+
+@pytest.mark.parametrize("n,P", [(4, 64), (7, 500), (20, 1500)])
+def test_lnl_edge_insertion_vs_retraversal_and_oracle(n, P):
+    from pylogeny_b200 import likelihood, neighbourhood as nbh
+    rng = np.random.default_rng(7 * n + P)
+    codes = (1 << rng.integers(0, 4, (n, P))).astype(np.uint8)
+    codes = np.where(rng.random((n, P)) < 0.03, 15, codes).astype(np.uint8)
+    w = rng.integers(1, 5, P).astype(float)
+    exch, f = rng.uniform(0.3, 3, 6), rng.dirichlet(np.ones(4) * 6)
+    a = likelihood.LikAlignment(codes, w)
+    m = likelihood.Model(exch, f, 0.7)
+    d = random_desc(rng, n)
+    br = rng.exponential(0.1, d.shape)
+    moves, lnl = nbh.score_likelihood(a, m, d, br)
+    descs, brs, _ = nbh.neighbour_trees(d, br)
+    full = a.score_trees(m, descs, brs)
+    np.testing.assert_allclose(lnl, full, rtol=1e-11)
+    M = len(lnl)
+    for i in range(0, M, max(1, M // 12)):
+        want = oracle.lnl(codes, w, exch, f, 0.7, descs[i], brs[i])
+        assert abs(lnl[i] - want) <= 1e-8 * abs(want)
+    _, nni = nbh.score_likelihood(a, m, d, br, move_type=nbh.MOVE_NNI)
+    assert len(nni) == 2 * (n - 3)
+    a.close(); m.close()
