@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the tree-scoring hot path (BASELINE.json metric: trees x sites scored / second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload at every N: BASELINE.json configs[1] -- synthetic DNA, 64 taxa x 10,000 sites (i.i.d.
+uniform ACGT, seed 1001, so patterns = sites), GTR+Gamma4 log-likelihood at fixed branch
+lengths of every distinct SPR neighbour (14,762) of a random tree.  One "step" = one pass of
+the hot path over that batch: plan (host) + score (device) + read back the per-tree scores.
+At N > 1 the job is N such neighbourhoods (base trees seeded 1001+b); every neighbourhood is
+sharded N ways across the ranks (contiguous blocks of its move list, full alignment on every
+GPU), and the per-tree scores come back through one NCCL all-gather -- weak scaling.
+
+One JSON line on stdout (rank 0).  Extra objects: "roofline" (dominant kernel, CUDA-event timed
+inside the timed region), "cpu_baseline" (CPU oracle on a bounded sample of the same workload),
+"e2e" (same metric through the public API with host buffers, H2D of the alignment and D2H of
+the scores inside the timed region), "parsimony" (BASELINE config 3 shape, 256 taxa x 100k
+sites, Fitch scoring of all 255,530 SPR neighbours; N=1 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_TAXA, N_SITES, SEED = 64, 10_000, 1001
+EXCH = np.array([1.2, 3.4, 0.8, 1.1, 4.1, 1.0])
+FREQS = np.array([0.28, 0.22, 0.24, 0.26])
+ALPHA = 0.7
+METRIC = "trees x sites scored / sec (GTR+G4 logL, all SPR neighbours, 64 taxa x 10k sites)"
+UNIT = "tree-sites/s"
+
+
+def random_desc(rng, n_tips):
+    nodes = list(range(n_tips))
+    desc, nxt = [], n_tips
+    while len(nodes) > 1:
+        a = nodes.pop(int(rng.integers(len(nodes))))
+        b = nodes.pop(int(rng.integers(len(nodes))))
+        desc.append((a, b))
+        nodes.append(nxt)
+        nxt += 1
+    return np.array(desc, dtype=np.int32)
+
+
+def make_alignment(seed=SEED, n=N_TAXA, s=N_SITES):
+    rng = np.random.default_rng(seed)
+    codes = (1 << rng.integers(0, 4, (n, s))).astype(np.uint8)
+    return codes, np.ones(s)
+
+
+def make_tree(seed, n=N_TAXA):
+    rng = np.random.default_rng(seed + 7919)
+    d = random_desc(rng, n)
+    return d, rng.exponential(0.1, d.shape)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py touches oracle/)
+# ----------------------------------------------------------------------------------------------
+def cpu_lnl_sample(seconds=12.0):
+    """FP64 CPU restatement (oracle/lik_oracle.c; libpll itself is not available) on a bounded
+    sample of the workload's neighbour trees, all host cores (one tree per thread at a time)."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from pylogeny_b200 import neighbourhood as nbh
+    codes, w = make_alignment()
+    d, br = make_tree(SEED)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    descs, brs, _ = nbh.neighbour_trees(d, br, np.arange(1))
+    oracle.lnl(codes, w, EXCH, FREQS, ALPHA, descs[0], brs[0])
+    t1 = time.perf_counter() - t0
+    n_sample = int(max(cores, min(4096, seconds * cores / max(t1, 1e-3))))
+    n_sample -= n_sample % cores
+    sel = np.linspace(0, nbh.neighbourhood_size(d) - 1, n_sample).astype(np.int64)
+    descs, brs, _ = nbh.neighbour_trees(d, br, sel)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:  # ctypes releases the GIL inside the C call
+        out = list(ex.map(lambda i: oracle.lnl(codes, w, EXCH, FREQS, ALPHA, descs[i], brs[i]), range(n_sample)))
+    dt = time.perf_counter() - t0
+    return {"value": n_sample * N_SITES / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of the 14762 neighbour trees x all 10000 sites, FP64 scalar pruning oracle "
+                      "(libpll 1.0.2 SSE3 is not available offline), %.1f s" % (n_sample, dt)}, dt, out
+
+
+def cpu_fitch_sample(states, desc, seconds=10.0):
+    """The reference's own compiled fitch.cpp core (oracle/_ref) when present, else the C port."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from pylogeny_b200 import neighbourhood as nbh
+    cores = os.cpu_count() or 1
+    n, S = states.shape[1], states.shape[0]
+    sub = 5000
+    profs = [bytes(r).decode("ascii") for r in states[:sub]]
+    labels = ["T%d" % i for i in range(n)]
+    x = oracle.FitchInputs(profs, [1] * sub, {l: i for i, l in enumerate(labels)})
+    use_ref = oracle.ref_available()
+    fn = oracle.ref_fitch_cost if use_ref else oracle.fitch_cost
+    descs, _, _ = nbh.neighbour_trees(desc, None, np.linspace(0, nbh.neighbourhood_size(desc) - 1, cores).astype(np.int64))
+    nws = [nbh.desc_to_newick(dd, labels) for dd in descs]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(lambda s: fn(s, inputs=x), nws))
+    dt = time.perf_counter() - t0
+    return {"value": cores * sub / dt, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": "%d neighbour trees x %d of the %d sites, %s, %.1f s" % (
+                cores, sub, S, "reference fitch.cpp:6-272 compiled (oracle/_ref)" if use_ref else "C port", dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference-side CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        cpu_lnl_sample(seconds=1.0)
+    vals, times = [], []
+    for _ in range(args.steps):
+        cb, dt, _ = cpu_lnl_sample(seconds=max(2.0, 40.0 / args.steps))
+        vals.append(cb["value"])
+        times.append(dt)
+    v = float(np.mean(vals))
+    cb["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(1), "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[1]: synthetic DNA 64 taxa x 10k sites, GTR+G4 lnL (fixed branch lengths) "
+                        "of all 14762 distinct SPR neighbours of a random tree",
+            "planner": "edge insertion (directional CLVs + 1 CLV update + 1 three-way evaluation per neighbour)",
+            "neighbourhoods_per_step": n_gpus, "sharding": "each neighbourhood split %d ways, scores all-gathered" % n_gpus,
+            "l2": "per-step working set (~19 GB of CLVs) >> 126 MB L2; L2 additionally flushed between steps",
+            "seed": SEED}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pylogeny_b200 import _lib, fitch, likelihood, neighbourhood as nbh
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (pylogeny_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    _lib.check(_lib.lib().plg_set_device(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _lib.lib()
+    dev = torch.device("cuda", local)
+    codes, w = make_alignment()
+    trees = [make_tree(SEED + b) for b in range(world)]
+    model = likelihood.Model(EXCH, FREQS, ALPHA)
+    aln = likelihood.LikAlignment(codes, w)
+    M = nbh.neighbourhood_size(trees[0][0])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * world * (M // world + 1), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        outs = []
+        for d, br in trees:
+            _, lnl = nbh.score_likelihood(aln, model, d, br, shard=(rank, world))
+            outs.append(lnl[M * rank // world: M * (rank + 1) // world])
+        if world > 1:  # tiny all-gather of the per-tree scores over NCCL
+            mine = torch.zeros(world * (M // world + 1), dtype=torch.float64)
+            cat = np.concatenate(outs)
+            mine[:len(cat)] = torch.from_numpy(cat)
+            dist.all_gather_into_tensor(gathered, mine.to(dev, non_blocking=True))
+            return gathered
+        return outs[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.plg_profile_enable(1)
+    for k in range(4):
+        L.plg_profile_read(k, None, None, None, None)
+    launches0 = L.plg_launch_count()
+    total_ms = 0.0
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()  # L2 flush, outside the per-step events
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        res = step()
+        e1.record()
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e1)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = L.plg_launch_count() - launches0
+    L.plg_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * M * N_SITES / (ms_per_step * 1e-3)
+
+    # per-kernel roofline (events recorded by the library around every launch of the timed steps)
+    import ctypes as C
+    prof = {}
+    for k, name in enumerate(("fitch_level_kernel", "clv_update_kernel", "root_eval_kernel", "pmatrix_kernel")):
+        ms, by, un, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        L.plg_profile_read(k, C.byref(ms), C.byref(by), C.byref(un), C.byref(n))
+        prof[name] = {"ms": ms.value, "bytes": by.value, "units": un.value, "launches": n.value}
+    peak, peak_src = measured_peaks()
+    dom = max(("clv_update_kernel", "root_eval_kernel"), key=lambda k: prof[k]["ms"])
+
+    def roof(name):
+        p = prof[name]
+        if not p["launches"] or p["ms"] <= 0:
+            return None
+        ach = p["bytes"] / (p["ms"] * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": ncu_traffic(name), "peak_source": peak_src, "launches": p["launches"],
+                "avg_launch_ms": p["ms"] / p["launches"], "algorithmic_bytes_per_launch": p["bytes"] / p["launches"],
+                "share_of_step": p["ms"] / total_ms}
+
+    roofline = roof(dom)
+    roofline["other_kernels"] = [r for r in (roof(k) for k in prof if k != dom) if r]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0 only from here: e2e, CPU baseline, parsimony leg --------------------------------
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+           "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
+           "wall_s_timed_region": wall, "trees_per_step": world * M}
+
+    # e2e: same metric through the public API with HOST buffers; the alignment goes up and the
+    # scores come down inside the timed region, every step
+    pinned_codes = torch.from_numpy(codes).pin_memory()
+    pinned_w = torch.from_numpy(w).pin_memory()
+    d0, br0 = trees[0]
+    e2e_ms = []
+    for i in range(2 + min(args.steps, 5)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a2 = likelihood.LikAlignment(pinned_codes.numpy(), pinned_w.numpy())
+        moves, lnl = nbh.score_likelihood(a2, model, d0, br0)
+        a2.close()
+        torch.cuda.synchronize()
+        if i >= 2:
+            e2e_ms.append(1e3 * (time.perf_counter() - t0))
+    h2d = codes.nbytes + w.nbytes + d0.nbytes + br0.nbytes
+    out["e2e"] = {"value": M * N_SITES / (np.mean(e2e_ms) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                  "d2h_bytes_per_step": int(lnl.nbytes), "ms_per_step": float(np.mean(e2e_ms)),
+                  "note": "1 GPU, plg_lik_aln_create + plg_lik_score_neighbourhood + destroy per step"}
+    if world == 1:
+        if not args.no_cpu:
+            out["cpu_baseline"] = cpu_lnl_sample()[0]
+        out["parsimony"] = parsimony_leg(fitch, nbh, L, peak, peak_src, not args.no_cpu)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
+    """BASELINE config 3 shape: 256 taxa x 100k sites, Fitch length of all 255,530 SPR neighbours."""
+    import ctypes as C
+    import torch
+    n, S = 256, 100_000
+    rng = np.random.default_rng(1002)
+    states = (rng.integers(0, 4, (S, n)) + 48).astype(np.uint8)
+    a = fitch.FitchAlignment.from_dense(states, np.ones(S, dtype=np.int64))
+    d = random_desc(np.random.default_rng(1002 + 7919), n)
+    for _ in range(2):
+        moves, costs = nbh.score_parsimony(a, d)
+    L.plg_profile_enable(1)
+    L.plg_profile_read(0, None, None, None, None)
+    ms = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        moves, costs = nbh.score_parsimony(a, d)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    L.plg_profile_enable(0)
+    kms, by, un, nl = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+    L.plg_profile_read(0, C.byref(kms), C.byref(by), C.byref(un), C.byref(nl))
+    M = len(costs)
+    ach = by.value / (kms.value * 1e-3) / 1e9
+    res = {"workload": "BASELINE configs[2] shape: synthetic DNA 256 taxa x 100k sites, Fitch length of all %d "
+                       "distinct SPR neighbours of a random tree (edge insertion)" % M,
+           "value": M * S / (np.mean(ms) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms)), "dtype": "u32 bitsets",
+           "roofline": {"kernel": "fitch_level_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": ncu_traffic("fitch_level_kernel"), "peak_source": peak_src,
+                        "launches": nl.value, "avg_launch_ms": kms.value / max(nl.value, 1),
+                        "share_of_step": kms.value / sum(ms)},
+           "checksum": int(costs.astype(np.int64).sum()), "min_cost": int(costs.min())}
+    if cpu:
+        res["cpu_baseline"] = cpu_fitch_sample(states, d)
+    a.close()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,12 @@ int plg_device_count(int *count);
 int plg_set_device(int device);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t plg_launch_count(void);
+/* Per-kernel timing for the roofline report: CUDA events recorded on the launching stream
+ * around every launch while enabled.  kind: 0 Fitch node-ops, 1 CLV update, 2 root/3-way
+ * evaluation, 3 P-matrices.  plg_profile_read sums and clears one kind: device ms,
+ * algorithmic bytes (SURVEY.md 8d accounting), node-op x pattern units, launches. */
+int plg_profile_enable(int on);
+int plg_profile_read(int kind, double *ms, double *bytes, double *units, int64_t *launches);
 
 /* ------------------------------------------------------------------ */
 /* Parsimony (replaces fitch.cpp)                                      */

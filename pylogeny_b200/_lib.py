@@ -71,3 +71,5 @@ def _declare(L):
     L.plg_fitch_score_neighbourhood.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int64, C.c_int64, i64p, vp, vp, vp]
     L.plg_lik_score_neighbourhood.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, i64p, vp,
                                               vp, vp]
+    L.plg_profile_enable.argtypes = [C.c_int]
+    L.plg_profile_read.argtypes = [C.c_int, dp, dp, dp, i64p]

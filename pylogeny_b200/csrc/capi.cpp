@@ -33,3 +33,61 @@ extern "C" int plg_set_device(int device) {
   PLG_CUDA(cudaSetDevice(device));
   PLG_API_END
 }
+
+// ---- per-kernel profiling -------------------------------------------------------------------
+namespace plg {
+namespace {
+struct ProfRec { int kind; cudaEvent_t a, b; double bytes, units; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t g_prof_open[PROF_KINDS];
+cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof_on) return;
+  g_prof_open[kind] = prof_event();
+  cudaEventRecord(g_prof_open[kind], st);
+}
+void prof_end(int kind, cudaStream_t st, double bytes, double units) {
+  if (!g_prof_on) return;
+  cudaEvent_t b = prof_event();
+  cudaEventRecord(b, st);
+  g_prof_recs.push_back({kind, g_prof_open[kind], b, bytes, units});
+}
+}  // namespace plg
+
+extern "C" int plg_profile_enable(int on) {
+  plg::g_prof_on = on != 0;
+  return PLG_OK;
+}
+
+// Sums (and clears) what was recorded for one kernel kind: device milliseconds between the
+// events around each launch, algorithmic bytes, node-op x pattern units, launches.
+extern "C" int plg_profile_read(int kind, double *ms, double *bytes, double *units, int64_t *launches) {
+  PLG_API_BEGIN
+  if (kind < 0 || kind >= plg::PROF_KINDS) PLG_FAIL(PLG_ERR_ARG, "bad kernel kind");
+  PLG_CUDA(cudaDeviceSynchronize());
+  double t = 0, by = 0, un = 0;
+  int64_t n = 0;
+  std::vector<plg::ProfRec> keep;
+  for (auto &r : plg::g_prof_recs) {
+    if (r.kind != kind) { keep.push_back(r); continue; }
+    float e = 0;
+    PLG_CUDA(cudaEventElapsedTime(&e, r.a, r.b));
+    t += e; by += r.bytes; un += r.units; n++;
+    plg::g_prof_pool.push_back(r.a);
+    plg::g_prof_pool.push_back(r.b);
+  }
+  plg::g_prof_recs.swap(keep);
+  if (ms) *ms = t;
+  if (bytes) *bytes = by;
+  if (units) *units = un;
+  if (launches) *launches = n;
+  PLG_API_END
+}

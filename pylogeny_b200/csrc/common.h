@@ -53,6 +53,11 @@ struct Error {
 
 inline void count_launch(int64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+enum ProfKind { PROF_FITCH_OPS = 0, PROF_CLV_UPDATE = 1, PROF_ROOT_EVAL = 2, PROF_PMATRIX = 3, PROF_KINDS = 4 };
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st, double algorithmic_bytes, double units);
+
 // Owning device buffer.
 template <typename T>
 struct DevBuf {

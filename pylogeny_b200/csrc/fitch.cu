@@ -360,7 +360,8 @@ void build_full_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_tip_sl
 }
 
 template <int K, int VW>
-static void launch_level(const FitchAln &a, FitchWorkspace &ws, int64_t op0, int64_t n_ops, cudaStream_t st) {
+static void launch_level(const FitchAln &a, FitchWorkspace &ws, int64_t op0, int64_t n_ops, double level_bytes,
+                         cudaStream_t st) {
   const int64_t cols = a.words32 / VW;
   // block size: multiple of 32 in [64,256] wasting the fewest lanes
   int best_t = 256;
@@ -374,10 +375,12 @@ static void launch_level(const FitchAln &a, FitchWorkspace &ws, int64_t op0, int
   const int64_t max_ops_per_launch = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
   for (int64_t o = 0; o < n_ops; o += max_ops_per_launch) {
     const int64_t cnt = std::min(max_ops_per_launch, n_ops - o);
+    prof_begin(PROF_FITCH_OPS, st);
     fitch_level_kernel<K, VW><<<(unsigned)(cnt * bpo), best_t, 0, st>>>(
         a.tips.p, ws.scratch.p, a.n_cols, ws.ops.p + op0 + o, ws.children.p, a.words32, (int)bpo,
         a.wbits.p, a.chunk_nb.p, ws.cost.p);
     count_launch();
+    prof_end(PROF_FITCH_OPS, st, level_bytes * (double)cnt / (double)n_ops, (double)cnt * (double)a.P);
   }
 }
 
@@ -397,17 +400,23 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
   for (size_t l = 0; l + 1 < prog.level_off.size(); l++) {
     const int64_t o0 = prog.level_off[l], cnt = prog.level_off[l + 1] - o0;
     if (!cnt) continue;
+    // algorithmic bytes of this launch: every operand vector read once, every stored vector
+    // written once, K_real planes of P bits each (3*K_p/8 B per binary node-op)
+    double vecs = 0;
+    for (int64_t o = o0; o < o0 + cnt; o++)
+      vecs += (prog.ops[o].nchild == FITCH_JOIN3 ? 3 : prog.ops[o].nchild) + (prog.ops[o].dst >= 0 ? 1 : 0);
+    const double lb = vecs * a.K_real * (double)a.P / 8.0;
     switch (a.K) {
-      case 2: launch_level<2, 4>(a, ws, o0, cnt, st); break;
-      case 3: launch_level<3, 4>(a, ws, o0, cnt, st); break;
-      case 4: launch_level<4, 4>(a, ws, o0, cnt, st); break;
-      case 5: launch_level<5, 4>(a, ws, o0, cnt, st); break;
-      case 6: launch_level<6, 4>(a, ws, o0, cnt, st); break;
-      case 8: launch_level<8, 2>(a, ws, o0, cnt, st); break;
-      case 10: launch_level<10, 2>(a, ws, o0, cnt, st); break;
-      case 12: launch_level<12, 1>(a, ws, o0, cnt, st); break;
-      case 16: launch_level<16, 1>(a, ws, o0, cnt, st); break;
-      case 20: launch_level<20, 1>(a, ws, o0, cnt, st); break;
+      case 2: launch_level<2, 4>(a, ws, o0, cnt, lb, st); break;
+      case 3: launch_level<3, 4>(a, ws, o0, cnt, lb, st); break;
+      case 4: launch_level<4, 4>(a, ws, o0, cnt, lb, st); break;
+      case 5: launch_level<5, 4>(a, ws, o0, cnt, lb, st); break;
+      case 6: launch_level<6, 4>(a, ws, o0, cnt, lb, st); break;
+      case 8: launch_level<8, 2>(a, ws, o0, cnt, lb, st); break;
+      case 10: launch_level<10, 2>(a, ws, o0, cnt, lb, st); break;
+      case 12: launch_level<12, 1>(a, ws, o0, cnt, lb, st); break;
+      case 16: launch_level<16, 1>(a, ws, o0, cnt, lb, st); break;
+      case 20: launch_level<20, 1>(a, ws, o0, cnt, lb, st); break;
       default: PLG_FAIL(PLG_ERR_STATES, "no kernel for %d planes", a.K);
     }
   }

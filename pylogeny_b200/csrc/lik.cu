@@ -220,23 +220,26 @@ root_eval_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_r
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < LIK_THREADS / 32; w++) s += warp_sums[w];
-    partial[(int64_t)ev_idx * blocks_per_eval + pb] = s;
+    partial[(int64_t)ev.tree * blocks_per_eval + pb] = s;
   }
 }
 
-// One warp per evaluation: strided partial sums, then a fixed shuffle tree; accumulates per tree
-// through the eval's tree index (each tree owns exactly one eval in every program we build).
-__global__ void reduce_partials_kernel(const LikEval *__restrict__ evals, int n_evals, int blocks_per_eval,
-                                       const double *__restrict__ partial, double *__restrict__ lnl) {
-  const int ev = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-  if (ev >= n_evals) return;
+// One warp per tree: strided partial sums, then a fixed shuffle tree (deterministic order).
+__global__ void reduce_partials_kernel(int n_trees, int blocks_per_eval, const double *__restrict__ partial,
+                                       double *__restrict__ lnl) {
+  const int t = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (t >= n_trees) return;
   const int lane = threadIdx.x & 31;
   double s = 0.0;
-  for (int b = lane; b < blocks_per_eval; b += 32) s += partial[(int64_t)ev * blocks_per_eval + b];
+  for (int b = lane; b < blocks_per_eval; b += 32) s += partial[(int64_t)t * blocks_per_eval + b];
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
-  if (lane == 0) lnl[evals[ev].tree] = s;
+  if (lane == 0) lnl[t] = s;
 }
+
+}  // namespace plg
+#include "lik_dna.cuh"
+namespace plg {
 
 // ----------------------------------------------------------------------------
 // host: alignment
@@ -383,8 +386,10 @@ static void run_typed(const LikAln &a, const Model &m, LikWorkspace &ws, const L
   ws.brlen.alloc(std::max<size_t>(1, n_pm));
   if (n_pm) {
     PLG_CUDA(cudaMemcpyAsync(ws.brlen.p, prog.brlens.data(), (size_t)n_pm * 8, cudaMemcpyHostToDevice, st));
+    prof_begin(PROF_PMATRIX, st);
     pmatrix_kernel<K, R><<<n_pm, 128, 0, st>>>(m.d.p, ws.brlen.p, a.masks.p, ws.pmat.p, ws.tiptab.p);
     count_launch();
+    prof_end(PROF_PMATRIX, st, (double)n_pm * (R * KKP + NC * R * K) * 8.0, n_pm);
   }
   const int per_block = LIK_THREADS / R;
   const int64_t bpo = a.Ppad / per_block;
@@ -393,9 +398,18 @@ static void run_typed(const LikAln &a, const Model &m, LikWorkspace &ws, const L
     const int64_t max_ops = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
     for (int64_t o = 0; o < cnt; o += max_ops) {
       const int64_t c = std::min(max_ops, cnt - o);
+      // algorithmic bytes: C + 4 per inner CLV moved (scaler included), 1 per tip code
+      double bytes = 0;
+      const double Cb = (double)R * K * 8.0 + 4.0;
+      for (int64_t q = o0 + o; q < o0 + o + c; q++) {
+        const LikOp &op = prog.ops[q];
+        bytes += Cb + (op.a < a.n_rows ? 1.0 : Cb) + (op.b < 0 ? 0.0 : (op.b < a.n_rows ? 1.0 : Cb));
+      }
+      prof_begin(PROF_CLV_UPDATE, st);
       clv_update_kernel<K, R><<<(unsigned)(c * bpo), LIK_THREADS, 0, st>>>(
           ws.ops.p + o0 + o, (int)bpo, a.n_rows, a.Ppad, a.codes.p, ws.pmat.p, ws.tiptab.p, ws.clv.p, ws.scl.p);
       count_launch();
+      prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, (double)c * (double)a.P);
     }
   }
   const int64_t n_ev = (int64_t)prog.evals.size();
@@ -403,13 +417,113 @@ static void run_typed(const LikAln &a, const Model &m, LikWorkspace &ws, const L
     const int64_t max_ev = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
     for (int64_t e = 0; e < n_ev; e += max_ev) {
       const int64_t c = std::min(max_ev, n_ev - e);
+      double bytes = 0;
+      const double Cb = (double)R * K * 8.0 + 4.0;
+      for (int64_t q = e; q < e + c; q++) {
+        const LikEval &ev = prog.evals[q];
+        bytes += 8.0 + (ev.a < a.n_rows ? 1.0 : Cb) + (ev.b < a.n_rows ? 1.0 : Cb) +
+                 (ev.c < 0 ? 0.0 : (ev.c < a.n_rows ? 1.0 : Cb));
+      }
+      prof_begin(PROF_ROOT_EVAL, st);
       root_eval_kernel<K, R><<<(unsigned)(c * bpo), LIK_THREADS, 0, st>>>(
           ws.evals.p + e, (int)bpo, a.n_rows, a.Ppad, a.codes.p, a.masks.p, a.weights.p, m.d.p, ws.pmat.p,
-          ws.tiptab.p, ws.clv.p, ws.scl.p, ws.partial.p + e * bpo);
+          ws.tiptab.p, ws.clv.p, ws.scl.p, ws.partial.p);
       count_launch();
+      prof_end(PROF_ROOT_EVAL, st, bytes * (double)a.P, (double)c * (double)a.P);
     }
-    reduce_partials_kernel<<<(unsigned)((n_ev + 7) / 8), 256, 0, st>>>(ws.evals.p, (int)n_ev, (int)bpo, ws.partial.p,
-                                                                       ws.lnl.p);
+    reduce_partials_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, (int)bpo,
+                                                                               ws.partial.p, ws.lnl.p);
+    count_launch();
+  }
+}
+
+// DNA x Gamma-4 path: thread-per-pattern kernels, evaluations fused into the CLV update that
+// produces their first operand whenever the other operands are ready by then.
+static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, cudaStream_t st) {
+  constexpr int K = 4, R = 4, KKP = 17, NC = 16;
+  const int n_pm = (int)prog.brlens.size();
+  ws.pmat.alloc(std::max<size_t>(1, (size_t)n_pm * R * KKP));
+  ws.tiptab.alloc(std::max<size_t>(1, (size_t)n_pm * NC * R * K));
+  ws.brlen.alloc(std::max<size_t>(1, n_pm));
+  if (n_pm) {
+    PLG_CUDA(cudaMemcpyAsync(ws.brlen.p, prog.brlens.data(), (size_t)n_pm * 8, cudaMemcpyHostToDevice, st));
+    prof_begin(PROF_PMATRIX, st);
+    pmatrix_kernel<K, R><<<n_pm, 128, 0, st>>>(m.d.p, ws.brlen.p, a.masks.p, ws.pmat.p, ws.tiptab.p);
+    count_launch();
+    prof_end(PROF_PMATRIX, st, (double)n_pm * (R * KKP + NC * R * K) * 8.0, n_pm);
+  }
+  // ---- fusion pass (host) ----
+  const int64_t n_ops = (int64_t)prog.ops.size();
+  std::vector<LikOpF> fops(n_ops);
+  std::vector<int> producer(prog.n_slots, -1), op_level(n_ops, 0);
+  for (size_t l = 0; l + 1 < prog.level_off.size(); l++)
+    for (int64_t o = prog.level_off[l]; o < prog.level_off[l + 1]; o++) op_level[o] = (int)l;
+  for (int64_t o = 0; o < n_ops; o++) {
+    const LikOp &op = prog.ops[o];
+    LikOpF f;
+    f.dst = op.dst; f.a = op.a; f.b = op.b; f.pa = op.pa; f.pb = op.pb;
+    f.tree = -1; f.e_pa = f.e_b = f.e_pb = f.e_c = f.e_pc = -1; f.pad = 0;
+    fops[o] = f;
+    producer[op.dst - a.n_rows] = (int)o;
+  }
+  auto level_of = [&](int id) { return id < a.n_rows ? -1 : op_level[producer[id - a.n_rows]]; };
+  std::vector<LikEval> rest;
+  for (const LikEval &ev : prog.evals) {
+    bool fused = false;
+    if (ev.a >= a.n_rows && ev.pa >= 0 && ev.c >= 0 && ev.pb >= 0 && ev.pc >= 0) {
+      const int o = producer[ev.a - a.n_rows];
+      if (fops[o].tree < 0 && level_of(ev.b) < op_level[o] && level_of(ev.c) < op_level[o]) {
+        fops[o].tree = ev.tree; fops[o].e_pa = ev.pa;
+        fops[o].e_b = ev.b; fops[o].e_pb = ev.pb; fops[o].e_c = ev.c; fops[o].e_pc = ev.pc;
+        fused = true;
+      }
+    }
+    if (!fused) rest.push_back(ev);
+  }
+  ws.fops.alloc(std::max<size_t>(1, (size_t)n_ops * sizeof(LikOpF)));
+  if (n_ops)
+    PLG_CUDA(cudaMemcpyAsync(ws.fops.p, fops.data(), (size_t)n_ops * sizeof(LikOpF), cudaMemcpyHostToDevice, st));
+  if (!rest.empty())
+    PLG_CUDA(cudaMemcpyAsync(ws.evals.p, rest.data(), rest.size() * sizeof(LikEval), cudaMemcpyHostToDevice, st));
+  const int64_t bpo = a.Ppad / D4_THREADS;
+  const double Cb = (double)R * K * 8.0 + 4.0;
+  auto opnd = [&](int id) { return id < 0 ? 0.0 : (id < a.n_rows ? 1.0 : Cb); };
+  const LikOpF *d_ops = reinterpret_cast<const LikOpF *>(ws.fops.p);
+  for (size_t l = 0; l + 1 < prog.level_off.size(); l++) {
+    const int64_t o0 = prog.level_off[l], cnt = prog.level_off[l + 1] - o0;
+    const int64_t max_ops = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
+    for (int64_t o = 0; o < cnt; o += max_ops) {
+      const int64_t c = std::min(max_ops, cnt - o);
+      double bytes = 0;  // algorithmic bytes: C+4 per inner CLV moved, 1 per tip code, 8 per weight
+      for (int64_t q = o0 + o; q < o0 + o + c; q++) {
+        const LikOpF &f = fops[q];
+        bytes += Cb + opnd(f.a) + opnd(f.b);
+        if (f.tree >= 0) bytes += opnd(f.e_b) + opnd(f.e_c) + 8.0;
+      }
+      prof_begin(PROF_CLV_UPDATE, st);
+      clv4_kernel<<<(unsigned)(c * bpo), D4_THREADS, 0, st>>>(d_ops + o0 + o, (int)bpo, a.n_rows, a.Ppad, a.codes.p,
+                                                             a.masks.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
+                                                             ws.clv.p, ws.scl.p, ws.partial.p);
+      count_launch();
+      prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, (double)c * (double)a.P);
+    }
+  }
+  const int64_t n_ev = (int64_t)rest.size();
+  const int64_t max_ev = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
+  for (int64_t e = 0; e < n_ev; e += max_ev) {
+    const int64_t c = std::min(max_ev, n_ev - e);
+    double bytes = 0;
+    for (int64_t q = e; q < e + c; q++) bytes += 8.0 + opnd(rest[q].a) + opnd(rest[q].b) + opnd(rest[q].c);
+    prof_begin(PROF_ROOT_EVAL, st);
+    eval4_kernel<<<(unsigned)(c * bpo), D4_THREADS, 0, st>>>(ws.evals.p + e, (int)bpo, a.n_rows, a.Ppad, a.codes.p,
+                                                            a.masks.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
+                                                            ws.clv.p, ws.scl.p, ws.partial.p);
+    count_launch();
+    prof_end(PROF_ROOT_EVAL, st, bytes * (double)a.P, (double)c * (double)a.P);
+  }
+  if (prog.n_trees) {
+    reduce_partials_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, (int)bpo,
+                                                                               ws.partial.p, ws.lnl.p);
     count_launch();
   }
 }
@@ -422,16 +536,17 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   ws.scl.alloc(std::max<size_t>(1, (size_t)prog.n_slots * a.Ppad));
   ws.ops.alloc(std::max<size_t>(1, prog.ops.size()));
   ws.evals.alloc(std::max<size_t>(1, prog.evals.size()));
-  const int64_t bpo = a.Ppad / (LIK_THREADS / m.R);
-  ws.partial.alloc(std::max<size_t>(1, prog.evals.size() * (size_t)bpo));
+  const bool dna4 = (a.K == 4 && m.R == 4);
+  const int64_t bpo = dna4 ? a.Ppad / D4_THREADS : a.Ppad / (LIK_THREADS / m.R);
+  ws.partial.alloc(std::max<size_t>(1, (size_t)prog.n_trees * (size_t)bpo));
   ws.lnl.alloc(std::max<size_t>(1, (size_t)prog.n_trees));
-  if (!prog.ops.empty())
+  if (!dna4 && !prog.ops.empty())
     PLG_CUDA(cudaMemcpyAsync(ws.ops.p, prog.ops.data(), prog.ops.size() * sizeof(LikOp), cudaMemcpyHostToDevice, st));
-  if (!prog.evals.empty())
+  if (!dna4 && !prog.evals.empty())
     PLG_CUDA(cudaMemcpyAsync(ws.evals.p, prog.evals.data(), prog.evals.size() * sizeof(LikEval),
                              cudaMemcpyHostToDevice, st));
   PLG_CUDA(cudaMemsetAsync(ws.lnl.p, 0, std::max<size_t>(1, (size_t)prog.n_trees) * 8, st));
-  if (a.K == 4 && m.R == 4) run_typed<4, 4>(a, m, ws, prog, st);
+  if (dna4) run_dna4(a, m, ws, prog, st);
   else if (a.K == 4 && m.R == 1) run_typed<4, 1>(a, m, ws, prog, st);
   else if (a.K == 20 && m.R == 4) run_typed<20, 4>(a, m, ws, prog, st);
   else if (a.K == 20 && m.R == 1) run_typed<20, 1>(a, m, ws, prog, st);

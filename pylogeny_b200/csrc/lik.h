@@ -25,6 +25,7 @@ struct LikWorkspace {
   DevBuf<double> tiptab;   // [pm][ncodes][R*K]  sum over the code's states of P columns
   DevBuf<double> brlen;    // [pm]
   DevBuf<LikOp> ops;
+  DevBuf<char> fops;       // LikOpF[] (DNA x Gamma-4 path: updates with fused evaluations)
   DevBuf<LikEval> evals;
   DevBuf<double> partial;  // [eval][blocks]
   DevBuf<double> lnl;      // [tree]

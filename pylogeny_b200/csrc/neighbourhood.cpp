@@ -1,6 +1,7 @@
 #include "neighbourhood.h"
 
 #include <algorithm>
+#include <thread>
 #include <unordered_map>
 
 namespace plg {
@@ -167,45 +168,79 @@ Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
       if (t.nb[x][k] > x) base += split_term(h[3 * x + k], all);
   nb.base_hash = base;
   if (t.n_tips < 4) return nb;
-  struct Frame { int x, from, parent_move, depth; uint64_t rem, add; };
-  std::vector<Frame> st;
-  for (int u = t.n_tips; u < t.n_nodes; u++)
+  // far[3*x+k] = hash of the side beyond edge x -> nb[x][k]; term[] = its split term
+  std::vector<uint64_t> far((size_t)t.n_nodes * 3, 0), term((size_t)t.n_nodes * 3, 0);
+  for (int x = 0; x < t.n_nodes; x++)
     for (int k = 0; k < 3; k++) {
-      const int v = t.nb[u][k];
-      const uint64_t hv = h[3 * v + t.slot_of(v, u)];
-      for (int side = 0; side < 2; side++) {
-        const int start = t.nb[u][(k + 1 + side) % 3];
-        st.push_back({start, u, -1, 0, split_term(h[3 * start + t.slot_of(start, u)], all), 0});
-        while (!st.empty()) {
-          Frame f = st.back();
-          st.pop_back();
-          if (t.is_tip(f.x)) continue;
-          if (max_depth >= 0 && f.depth >= max_depth) continue;
-          for (int j = 2; j >= 0; j--) {  // (reverse so that the stack pops in neighbour order)
-            const int c = t.nb[f.x][j];
-            if (c == f.from) continue;
-            const uint64_t far = h[3 * c + t.slot_of(c, f.x)];
-            Move m;
-            m.u = u; m.k = k; m.x = f.x; m.kx = j; m.depth = f.depth + 1; m.parent = f.parent_move;
-            m.side = side;
-            m.hash = base - f.rem + f.add + split_term(far ^ hv, all);
-            m.unique_id = -1;
-            nb.moves.push_back(m);
-            st.push_back({c, f.x, (int)nb.moves.size() - 1, f.depth + 1, f.rem + split_term(far, all),
-                          f.add + split_term(far ^ hv, all)});
+      const int y = t.nb[x][k];
+      if (y < 0) continue;
+      far[3 * x + k] = h[3 * y + t.slot_of(y, x)];
+      term[3 * x + k] = split_term(far[3 * x + k], all);
+    }
+  struct Frame { int x, from, parent_move, depth; uint64_t rem, add; };
+  // independent searches per pruned subtree, spread over the host cores
+  const int n_int = t.n_nodes - t.n_tips;
+  const int n_thr = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, n_int / 8)));
+  std::vector<std::vector<Move>> part(n_thr);
+  auto work = [&](int ti) {
+    std::vector<Move> &out = part[ti];
+    std::vector<Frame> st;
+    const int u0 = t.n_tips + (int)((int64_t)n_int * ti / n_thr), u1 = t.n_tips + (int)((int64_t)n_int * (ti + 1) / n_thr);
+    out.reserve((size_t)(u1 - u0) * 6 * t.n_tips);
+    for (int u = u0; u < u1; u++)
+      for (int k = 0; k < 3; k++) {
+        const uint64_t hv = far[3 * u + k];
+        for (int side = 0; side < 2; side++) {
+          const int ks = (k + 1 + side) % 3;
+          st.push_back({t.nb[u][ks], u, -1, 0, term[3 * u + ks], 0});
+          while (!st.empty()) {
+            const Frame f = st.back();
+            st.pop_back();
+            if (t.is_tip(f.x)) continue;
+            if (max_depth >= 0 && f.depth >= max_depth) continue;
+            for (int j = 2; j >= 0; j--) {  // (reverse so that the stack pops in neighbour order)
+              const int c = t.nb[f.x][j];
+              if (c == f.from) continue;
+              const uint64_t joined = split_term(far[3 * f.x + j] ^ hv, all);
+              Move m;
+              m.u = u; m.k = k; m.x = f.x; m.kx = j; m.depth = f.depth + 1; m.parent = f.parent_move;
+              m.side = side;
+              m.hash = base - f.rem + f.add + joined;
+              m.unique_id = -1;
+              out.push_back(m);
+              st.push_back({c, f.x, (int)out.size() - 1, f.depth + 1, f.rem + term[3 * f.x + j], f.add + joined});
+            }
           }
         }
       }
+  };
+  if (n_thr == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_thr; i++) th.emplace_back(work, i);
+    for (auto &x : th) x.join();
+  }
+  size_t total = 0;
+  for (auto &p : part) total += p.size();
+  nb.moves.reserve(total);
+  for (auto &p : part) {
+    const int off = (int)nb.moves.size();
+    for (Move m : p) {
+      if (m.parent >= 0) m.parent += off;
+      nb.moves.push_back(m);
     }
+    std::vector<Move>().swap(p);
+  }
+  // Distinct topologies.  Only moves at distance 1 (NNI) repeat: each NNI neighbour arises from
+  // 4 of the 8(n-3) distance-1 (prune, target) pairs, which accounts for all of
+  // 4(n-3)(n-2) - 2(n-3)(2n-7) = 6(n-3) duplicates; tests check distinctness of every hash.
   std::unordered_map<uint64_t, int> seen;
-  seen.reserve(nb.moves.size() * 2);
-  seen.emplace(base, -1);
+  seen.reserve(32 * (size_t)t.n_tips);
+  nb.unique.reserve(nb.moves.size());
   for (size_t i = 0; i < nb.moves.size(); i++) {
-    auto ins = seen.emplace(nb.moves[i].hash, (int)i);
-    if (ins.second) {
-      nb.moves[i].unique_id = (int)nb.unique.size();
-      nb.unique.push_back((int)i);
-    }
+    if (nb.moves[i].depth == 1 && !seen.emplace(nb.moves[i].hash, (int)i).second) continue;
+    nb.moves[i].unique_id = (int)nb.unique.size();
+    nb.unique.push_back((int)i);
   }
   return nb;
 }
