@@ -114,10 +114,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, units_per_launch):
+    """DRAM bytes (ncu dram__bytes_read+write) of one captured launch, scaled per node-op x pattern
+    unit to this run's average launch -- 'per launch like achieved'.  None if never captured."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
-        return json.load(open(p)).get(kernel)
+        t = json.load(open(p)).get(kernel)
+        if t and t.get("units"):
+            return t["dram_bytes"] / t["units"] * units_per_launch
     return None
 
 
@@ -157,21 +161,22 @@ def cpu_fitch_sample(states, desc, seconds=10.0):
     from pylogeny_b200 import neighbourhood as nbh
     cores = os.cpu_count() or 1
     n, S = states.shape[1], states.shape[0]
-    sub = 5000
+    sub, per_core = 25000, 4
     profs = [bytes(r).decode("ascii") for r in states[:sub]]
     labels = ["T%d" % i for i in range(n)]
     x = oracle.FitchInputs(profs, [1] * sub, {l: i for i, l in enumerate(labels)})
     use_ref = oracle.ref_available()
     fn = oracle.ref_fitch_cost if use_ref else oracle.fitch_cost
-    descs, _, _ = nbh.neighbour_trees(desc, None, np.linspace(0, nbh.neighbourhood_size(desc) - 1, cores).astype(np.int64))
+    descs, _, _ = nbh.neighbour_trees(desc, None, np.linspace(0, nbh.neighbourhood_size(desc) - 1, cores * per_core).astype(np.int64))
     nws = [nbh.desc_to_newick(dd, labels) for dd in descs]
     t0 = time.perf_counter()
     with ThreadPoolExecutor(cores) as ex:
         list(ex.map(lambda s: fn(s, inputs=x), nws))
     dt = time.perf_counter() - t0
-    return {"value": cores * sub / dt, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+    return {"value": cores * per_core * sub / dt, "unit": UNIT, "cores": cores,
+            "kind": "reference" if use_ref else "port",
             "sample": "%d neighbour trees x %d of the %d sites, %s, %.1f s" % (
-                cores, sub, S, "reference fitch.cpp:6-272 compiled (oracle/_ref)" if use_ref else "C port", dt)}
+                cores * per_core, sub, S, "reference fitch.cpp:6-272 compiled (oracle/_ref)" if use_ref else "C port", dt)}
 
 
 def run_reference(args):
@@ -299,7 +304,8 @@ def run_ours(args):
             return None
         ach = p["bytes"] / (p["ms"] * 1e-3) / 1e9
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": ncu_traffic(name), "peak_source": peak_src, "launches": p["launches"],
+                "traffic": ncu_traffic(name, p["units"] / p["launches"]), "peak_source": peak_src,
+                "launches": p["launches"],
                 "avg_launch_ms": p["ms"] / p["launches"], "algorithmic_bytes_per_launch": p["bytes"] / p["launches"],
                 "share_of_step": p["ms"] / total_ms}
 
@@ -376,7 +382,8 @@ def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
                        "distinct SPR neighbours of a random tree (edge insertion)" % M,
            "value": M * S / (np.mean(ms) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms)), "dtype": "u32 bitsets",
            "roofline": {"kernel": "fitch_level_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": ncu_traffic("fitch_level_kernel"), "peak_source": peak_src,
+                        "frac": ach / peak, "traffic": ncu_traffic("fitch_level_kernel", un.value / max(nl.value, 1)),
+                        "algorithmic_bytes_per_launch": by.value / max(nl.value, 1), "peak_source": peak_src,
                         "launches": nl.value, "avg_launch_ms": kms.value / max(nl.value, 1),
                         "share_of_step": kms.value / sum(ms)},
            "checksum": int(costs.astype(np.int64).sum()), "min_cost": int(costs.min())}

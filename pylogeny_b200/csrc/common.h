@@ -6,6 +6,8 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -101,6 +103,40 @@ struct PinBuf {
     PLG_CUDA(cudaMallocHost((void **)&p, count * sizeof(T)));
     n = count;
   }
+};
+
+// Growable host array in pinned memory (async H2D of op programs at full PCIe rate); plain
+// malloc when no device is present.  Contents are NOT preserved across resize().
+template <typename T>
+struct HostArr {
+  T *p = nullptr;
+  size_t n = 0, cap = 0;
+  bool pinned = false;
+  HostArr() = default;
+  HostArr(const HostArr &) = delete;
+  HostArr &operator=(const HostArr &) = delete;
+  ~HostArr() { release(); }
+  void release() {
+    if (p) { if (pinned) cudaFreeHost(p); else free(p); }
+    p = nullptr; n = cap = 0;
+  }
+  void resize(size_t count) {
+    if (count > cap) {
+      release();
+      size_t want = count + count / 4 + 16;
+      if (cudaMallocHost((void **)&p, want * sizeof(T)) == cudaSuccess) pinned = true;
+      else { cudaGetLastError(); p = (T *)malloc(want * sizeof(T)); pinned = false; if (!p) throw std::bad_alloc(); }
+      cap = want;
+    }
+    n = count;
+  }
+  void clear() { n = 0; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T *data() { return p; }
+  const T *data() const { return p; }
+  T &operator[](size_t i) { return p[i]; }
+  const T &operator[](size_t i) const { return p[i]; }
 };
 
 }  // namespace plg

@@ -87,7 +87,7 @@ fitch_level_kernel(const unsigned int *__restrict__ tips, unsigned int *__restri
         for (int v = 0; v < VW; v++) orr[s][v] = acc[s][v];
       }
     }
-    const int nfold = op.nchild == FITCH_JOIN3 ? 2 : op.nchild;
+    const int nfold = op.nchild < 0 ? 2 : op.nchild;
     for (int j = 1; j < nfold; j++) {
       const int cj = children[op.child_off + j];
       const unsigned int *src = (cj < n_tip_slots ? tips + (int64_t)cj * vec_words
@@ -145,11 +145,50 @@ fitch_level_kernel(const unsigned int *__restrict__ tips, unsigned int *__restri
       unsigned int *dst = scratch + (int64_t)(op.dst - n_tip_slots) * vec_words + w0;
 #pragma unroll
       for (int s = 0; s < K; s++) {
-        unsigned int o[VW];
 #pragma unroll
-        for (int v = 0; v < VW; v++) o[v] = acc[s][v] | (miss[v] & orr[s][v]);  // union on empty (:262-263)
-        store_vec<VW>(dst + s * words32, o);
+        for (int v = 0; v < VW; v++) acc[s][v] |= miss[v] & orr[s][v];  // union on empty (:262-263)
+        store_vec<VW>(dst + s * words32, acc[s]);
       }
+    } else if (op.nchild == FITCH_FUSED) {
+#pragma unroll
+      for (int s = 0; s < K; s++)
+#pragma unroll
+        for (int v = 0; v < VW; v++) acc[s][v] |= miss[v] & orr[s][v];
+    }
+    if (op.nchild == FITCH_FUSED) {
+      // edge insertion in one pass: acc now holds N; join it with the far side of the target
+      // edge (Fitch), intersect with the pruned subtree's set, keep only that miss count
+      const int c2 = children[op.child_off + 2], c3 = children[op.child_off + 3];
+      const unsigned int *f = (c2 < n_tip_slots ? tips + (int64_t)c2 * vec_words
+                                                : scratch + (int64_t)(c2 - n_tip_slots) * vec_words) + w0;
+      const unsigned int *tv = (c3 < n_tip_slots ? tips + (int64_t)c3 * vec_words
+                                                 : scratch + (int64_t)(c3 - n_tip_slots) * vec_words) + w0;
+      unsigned int any[VW];
+#pragma unroll
+      for (int v = 0; v < VW; v++) any[v] = 0;
+#pragma unroll
+      for (int s = 0; s < K; s++) {
+        unsigned int x[VW];
+        load_vec<VW>(f + s * words32, x);
+#pragma unroll
+        for (int v = 0; v < VW; v++) {
+          orr[s][v] = acc[s][v] | x[v];
+          acc[s][v] &= x[v];
+          any[v] |= acc[s][v];
+        }
+      }
+      unsigned int hit[VW];
+#pragma unroll
+      for (int v = 0; v < VW; v++) hit[v] = 0;
+#pragma unroll
+      for (int s = 0; s < K; s++) {
+        unsigned int x[VW];
+        load_vec<VW>(tv + s * words32, x);
+#pragma unroll
+        for (int v = 0; v < VW; v++) hit[v] |= (acc[s][v] | (~any[v] & orr[s][v])) & x[v];
+      }
+#pragma unroll
+      for (int v = 0; v < VW; v++) miss[v] = ~hit[v];
     }
     // weighted miss count
     const unsigned int nb = chunk_nb[w0 >> 2];
@@ -304,6 +343,14 @@ FitchAln::FitchAln(int64_t n_prof, int n_cols_, const uint8_t *states, const int
 // ----------------------------------------------------------------------------
 // host: program construction and execution
 // ----------------------------------------------------------------------------
+FitchWorkspace &fitch_workspace() {
+  static FitchWorkspace *ws[64] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!ws[dev & 63]) ws[dev & 63] = new FitchWorkspace();  // intentionally never freed (process lifetime)
+  return *ws[dev & 63];
+}
+
 void FitchProgram::clear() {
   ops.clear();
   children.clear();
@@ -404,7 +451,8 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
     // written once, K_real planes of P bits each (3*K_p/8 B per binary node-op)
     double vecs = 0;
     for (int64_t o = o0; o < o0 + cnt; o++)
-      vecs += (prog.ops[o].nchild == FITCH_JOIN3 ? 3 : prog.ops[o].nchild) + (prog.ops[o].dst >= 0 ? 1 : 0);
+      vecs += (prog.ops[o].nchild == FITCH_JOIN3 ? 3 : prog.ops[o].nchild == FITCH_FUSED ? 4 : prog.ops[o].nchild) +
+              (prog.ops[o].dst >= 0 ? 1 : 0);
     const double lb = vecs * a.K_real * (double)a.P / 8.0;
     switch (a.K) {
       case 2: launch_level<2, 4>(a, ws, o0, cnt, lb, st); break;
@@ -436,7 +484,7 @@ void score_batch_full(FitchAln &a, const TreeBatch &b, int32_t *out_costs, cudaS
   PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t vec_bytes = (size_t)a.K * a.words32 * 4;
   // scratch budget: half of what is free (counting the pool we already hold), capped at 48 GiB
-  const size_t budget = std::min<size_t>((free_b + a.ws.scratch.n * 4) / 2, (size_t)48 << 30);
+  const size_t budget = std::min<size_t>((free_b + fitch_workspace().scratch.n * 4) / 2, (size_t)48 << 30);
   const int64_t max_slots = std::max<int64_t>(1, (int64_t)(budget / vec_bytes));
   FitchProgram prog;
   int64_t t0 = 0;
@@ -444,7 +492,7 @@ void score_batch_full(FitchAln &a, const TreeBatch &b, int32_t *out_costs, cudaS
     int64_t t1 = t0 + 1;  // a single over-budget tree is still attempted; cudaMalloc reports failure
     while (t1 < n_trees && b.node_off[t1 + 1] - b.node_off[t0] <= max_slots) t1++;
     build_full_program(b, t0, t1, a.n_cols, prog);
-    run_fitch_program(a, a.ws, prog, out_costs + t0, st);
+    run_fitch_program(a, fitch_workspace(), prog, out_costs + t0, st);
     t0 = t1;
   }
 }

@@ -7,6 +7,7 @@ namespace plg {
 
 constexpr int FITCH_MAX_PLANES = 20;
 constexpr int FITCH_JOIN3 = -3;  // FitchOp::nchild marker: cost += miss(fitch(c0, c1), c2), nothing stored
+constexpr int FITCH_FUSED = -4;  // N = fitch(c0, c1) stored to dst; cost += miss(fitch(N, c2), c3)
 
 // One internal node = one op (16 bytes, read once per block).
 struct FitchOp {
@@ -16,12 +17,18 @@ struct FitchOp {
   int tree;       // index of the cost accumulator this op adds to
 };
 
+struct FitchProgram;
+struct FitchNbProgram;
 struct FitchWorkspace {
   DevBuf<unsigned int> scratch;  // internal-node vectors, slot-major
   DevBuf<FitchOp> ops;
   DevBuf<int> children;
   DevBuf<unsigned int> cost;
 };
+
+// Scratch pool shared by every alignment handle on the current device (grow-only; dropping a
+// handle must not free tens of GB that the next call would re-allocate).
+FitchWorkspace &fitch_workspace();
 
 struct FitchAln {
   int64_t P = 0;        // patterns
@@ -32,16 +39,18 @@ struct FitchAln {
   DevBuf<unsigned int> tips;      // [n_cols][K][words32]
   DevBuf<unsigned int> wbits;     // [n_wbits][words32]
   DevBuf<unsigned char> chunk_nb; // [W4] weight bit-planes per 128-pattern chunk, 0xFF = all weights 1
-  FitchWorkspace ws;
   FitchAln(int64_t n_prof, int n_cols, const uint8_t *states, const int64_t *weights);
 };
 
 struct FitchProgram {
-  std::vector<FitchOp> ops;        // sorted by level
-  std::vector<int> children;       // slot ids: < n_cols tip row, else n_cols + scratch slot
+  HostArr<FitchOp> ops;            // sorted by level (pinned: uploaded asynchronously)
+  HostArr<int> children;           // slot ids: < n_cols tip row, else n_cols + scratch slot
   std::vector<int64_t> level_off;  // [n_levels+1] into ops
   int64_t n_scratch_slots = 0;
   int64_t n_costs = 0;
+  FitchProgram() = default;
+  FitchProgram(const FitchProgram &) = delete;
+  FitchProgram &operator=(const FitchProgram &) = delete;
   void clear();
 };
 

@@ -286,6 +286,14 @@ LikAln::LikAln(int datatype, int n_rows_, int64_t P_, const uint8_t *h_codes, co
 // ----------------------------------------------------------------------------
 // host: programs
 // ----------------------------------------------------------------------------
+LikWorkspace &lik_workspace() {
+  static LikWorkspace *ws[64] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!ws[dev & 63]) ws[dev & 63] = new LikWorkspace();  // intentionally never freed (process lifetime)
+  return *ws[dev & 63];
+}
+
 void LikProgram::clear() {
   ops.clear();
   level_off.clear();
@@ -564,7 +572,7 @@ void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double 
   size_t free_b = 0, total_b = 0;
   PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t slot_bytes = ((size_t)m.R * a.K * 8 + 4) * a.Ppad;
-  const size_t held = a.ws.clv.n * 8 + a.ws.scl.n * 4;
+  const size_t held = lik_workspace().clv.n * 8 + lik_workspace().scl.n * 4;
   const size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)64 << 30);
   const int64_t max_slots = std::max<int64_t>(1, (int64_t)(budget / slot_bytes));
   LikProgram prog;
@@ -575,7 +583,7 @@ void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double 
     auto need = [&](int64_t lo, int64_t hi) { return b.child_off[b.node_off[hi]] - b.child_off[b.node_off[lo]]; };
     while (t1 < n_trees && need(t0, t1 + 1) / 2 <= max_slots) t1++;
     build_full_lik_program(b, t0, t1, a.n_rows, prog);
-    run_lik_program(a, m, a.ws, prog, out_lnl + t0, st);
+    run_lik_program(a, m, lik_workspace(), prog, out_lnl + t0, st);
     t0 = t1;
   }
 }

@@ -31,6 +31,8 @@ struct LikWorkspace {
   DevBuf<double> lnl;      // [tree]
 };
 
+LikWorkspace &lik_workspace();  // shared per device, grow-only (see fitch_workspace)
+
 struct LikAln {
   int K = 0, n_codes = 0, n_rows = 0;
   int64_t P = 0, Ppad = 0;
@@ -38,7 +40,6 @@ struct LikAln {
   DevBuf<double> weights;       // [Ppad]; padding = 0
   DevBuf<unsigned int> masks;   // [n_codes] bit k = state k compatible
   std::vector<unsigned int> h_masks;
-  LikWorkspace ws;
   LikAln(int datatype, int n_rows, int64_t P, const uint8_t *codes, const double *weights);
 };
 

@@ -5,9 +5,23 @@
 
 #include "neighbourhood.h"
 
+#include <chrono>
+#include <cstdlib>
+
 using namespace plg;
 
 namespace {
+
+struct StageTimer {  // PLG_TIMING=1: host-side stage times on stderr
+  bool on = getenv("PLG_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[plg] %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 int depth_for(int move_type) {
   if (move_type == PLG_MOVE_NNI) return 1;
@@ -40,8 +54,11 @@ void shard_range(int64_t M, int64_t idx, int64_t cnt, int64_t *lo, int64_t *hi) 
 extern "C" int plg_neighbourhood_size(int move_type, int n_tips, const int32_t *desc, int64_t *n_moves) {
   PLG_API_BEGIN
   if (!desc || !n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
-  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, nullptr), depth_for(move_type));
-  *n_moves = (int64_t)nb.unique.size();
+  const int depth = depth_for(move_type);
+  utree_from_desc(n_tips, desc, nullptr);  // validates the descriptor
+  // closed forms for an unrooted binary tree (checked against the enumeration in the tests)
+  const int64_t n = n_tips;
+  *n_moves = n < 4 ? 0 : (depth == 1 ? 2 * (n - 3) : 2 * (n - 3) * (2 * n - 7));
   PLG_API_END
 }
 
@@ -82,19 +99,22 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
     int row = tip_rows ? tip_rows[x] : x;
     if (row < 0 || row >= a.n_cols) PLG_FAIL(PLG_ERR_ARG, "tip row %d is outside the alignment", row);
   }
+  StageTimer tm;
   Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, nullptr), depth_for(move_type));
+  tm.lap("enumerate");
   const int64_t M = (int64_t)nb.unique.size();
   *n_moves = M;
   fill_moves(nb, out_moves);
+  tm.lap("fill_moves");
   if (!out_costs || M == 0) return PLG_OK;
   int64_t lo, hi;
   shard_range(M, shard_index, shard_count, &lo, &hi);
   size_t free_b = 0, total_b = 0;
   PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t vec_bytes = (size_t)a.K * a.words32 * 4;
-  const size_t budget = std::min<size_t>((free_b + a.ws.scratch.n * 4) / 2, (size_t)64 << 30);
+  const size_t budget = std::min<size_t>((free_b + fitch_workspace().scratch.n * 4) / 2, (size_t)64 << 30);
   const int64_t max_slots = std::max<int64_t>(4 * n_tips, (int64_t)(budget / vec_bytes));
-  FitchNbProgram p;
+  static thread_local FitchNbProgram p;  // keeps its pinned staging across calls
   std::vector<int32_t> acc;
   int64_t chunk = hi - lo;
   for (int64_t c0 = lo; c0 < hi;) {
@@ -104,9 +124,12 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
       chunk = std::max<int64_t>(1, (c1 - c0) / 2);
       continue;
     }
+    tm.lap("build");
     acc.resize(p.prog.n_costs);
-    run_fitch_program(a, a.ws, p.prog, acc.data(), (cudaStream_t)stream);
+    run_fitch_program(a, fitch_workspace(), p.prog, acc.data(), (cudaStream_t)stream);
+    tm.lap("run");
     finish_fitch_nb(nb, p, acc.data(), c0, c1, out_costs + c0);
+    tm.lap("finish");
     c0 = c1;
   }
   PLG_API_END
@@ -123,7 +146,9 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
     int row = tip_rows ? tip_rows[x] : x;
     if (row < 0 || row >= a.n_rows) PLG_FAIL(PLG_ERR_ARG, "tip row %d is outside the alignment", row);
   }
+  StageTimer tm;
   Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, brlen), depth_for(move_type));
+  tm.lap("enumerate");
   const int64_t M = (int64_t)nb.unique.size();
   *n_moves = M;
   fill_moves(nb, out_moves);
@@ -133,7 +158,7 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
   size_t free_b = 0, total_b = 0;
   PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t slot_bytes = ((size_t)m->impl.R * a.K * 8 + 4) * a.Ppad;
-  const size_t held = a.ws.clv.n * 8 + a.ws.scl.n * 4;
+  const size_t held = lik_workspace().clv.n * 8 + lik_workspace().scl.n * 4;
   const size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)80 << 30);
   const int64_t max_slots = std::max<int64_t>(4 * n_tips, (int64_t)(budget / slot_bytes));
   LikProgram p;
@@ -145,7 +170,9 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
       chunk = std::max<int64_t>(1, (c1 - c0) / 2);
       continue;
     }
-    run_lik_program(a, m->impl, a.ws, p, out_lnl + c0, (cudaStream_t)stream);
+    tm.lap("build");
+    run_lik_program(a, m->impl, lik_workspace(), p, out_lnl + c0, (cudaStream_t)stream);
+    tm.lap("run");
     c0 = c1;
   }
   PLG_API_END

@@ -325,6 +325,15 @@ std::vector<char> needed_moves(const Neighbourhood &nb, int64_t lo, int64_t hi) 
 
 }  // namespace
 
+// Runs fn(t, n_threads) on the host cores.
+template <typename F>
+static void parallel_for_threads(int n_thr, F fn) {
+  if (n_thr <= 1) { fn(0, 1); return; }
+  std::vector<std::thread> th;
+  for (int i = 0; i < n_thr; i++) th.emplace_back(fn, i, n_thr);
+  for (auto &x : th) x.join();
+}
+
 void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_tip_slots, int64_t lo,
                             int64_t hi, FitchNbProgram &out) {
   const UTree &t = nb.t;
@@ -336,92 +345,129 @@ void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, in
   std::vector<int> dir_slot((size_t)t.n_nodes * 3, -1);  // operand id of D[x->.]
   for (int x = 0; x < t.n_tips; x++)
     for (int k = 0; k < 3; k++) dir_slot[3 * x + k] = tip_rows ? tip_rows[x] : x;
-  struct Tmp { FitchOp op; int level; int kids[3]; };
-  std::vector<Tmp> tmp;
-  int64_t slots = 0, accs = 0;
-  for (int e : d.order) {
-    const int x = e / 3, k = e % 3;
-    Tmp o;
-    o.op.dst = n_tip_slots + (int)slots++;
-    o.op.nchild = 2;
-    o.op.tree = (int)accs;
-    out.dir_acc[e] = (int)accs++;
-    int s = 0;
-    for (int j = 0; j < 3; j++)
-      if (j != k) {
-        const int c = t.nb[x][j];
-        const int ce = 3 * c + t.slot_of(c, x);
-        o.kids[s] = dir_slot[ce];
-        out.dir_kids[e][s] = t.is_tip(c) ? -1 : ce;
-        s++;
-      }
-    o.kids[2] = -1;
-    o.level = d.level[e];
-    dir_slot[e] = o.op.dst;
-    tmp.push_back(o);
+  const int64_t n_dir = (int64_t)d.order.size();
+  const int64_t n_moves = (int64_t)nb.moves.size();
+  // which search steps are needed, and their scratch slots (enumeration order)
+  const bool all = (lo == 0 && hi == (int64_t)nb.unique.size());
+  std::vector<char> need;
+  std::vector<int> n_slot_rank;
+  int64_t n_need = n_moves;
+  if (!all) {
+    need = needed_moves(nb, lo, hi);
+    n_slot_rank.resize(n_moves);
+    n_need = 0;
+    for (int64_t i = 0; i < n_moves; i++) { n_slot_rank[i] = (int)n_need; n_need += need[i]; }
   }
-  const int dump_acc = (int)accs++;  // search-step partials add their own misses here (unused)
-  out.first_move_acc = accs;
-  std::vector<char> need = needed_moves(nb, lo, hi);
-  std::vector<int> n_slot(nb.moves.size(), -1);
+  auto slot_of_move = [&](int64_t i) { return n_tip_slots + (int)(n_dir + (all ? i : n_slot_rank[i])); };
+  // level layout: directional ops keep their dependency level, search steps sit at Ld + depth
   int max_depth = 0;
-  for (size_t i = 0; i < nb.moves.size(); i++) {
-    if (!need[i]) continue;
-    const Move &m = nb.moves[i];
-    const int x = m.x, c = t.nb[x][m.kx];
-    int from, xin;
-    if (m.parent < 0) {
-      const int other = t.nb[m.u][(m.k + 1 + (1 - m.side)) % 3];
-      from = m.u;
-      xin = dir_slot[3 * other + t.slot_of(other, m.u)];  // D[other->u] enters x over the merged edge
-    } else {
-      from = nb.moves[m.parent].x;
-      xin = n_slot[m.parent];
+  const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(std::thread::hardware_concurrency(), n_moves / 4096));
+  std::vector<std::vector<int64_t>> cnt(n_thr);
+  parallel_for_threads(n_thr, [&](int ti, int nt) {
+    std::vector<int64_t> &c = cnt[ti];
+    c.assign(64, 0);
+    for (int64_t i = n_moves * ti / nt; i < n_moves * (ti + 1) / nt; i++) {
+      if (!all && !need[i]) continue;
+      const int dep = nb.moves[i].depth;
+      if ((size_t)dep >= c.size()) c.resize(dep + 64, 0);
+      c[dep]++;
     }
-    int s = -1;
-    for (int j = 0; j < 3; j++)
-      if (t.nb[x][j] != from && t.nb[x][j] != c) s = t.nb[x][j];
-    Tmp o;
-    o.op.dst = n_tip_slots + (int)slots++;
-    o.op.nchild = 2;
-    o.op.tree = dump_acc;
-    o.kids[0] = xin;
-    o.kids[1] = dir_slot[3 * s + t.slot_of(s, x)];
-    o.kids[2] = -1;
-    o.level = d.max_level + m.depth;
-    n_slot[i] = o.op.dst;
-    max_depth = std::max(max_depth, m.depth);
-    tmp.push_back(o);
+  });
+  for (auto &c : cnt) {
+    int top = (int)c.size() - 1;
+    while (top > 0 && c[top] == 0) top--;
+    max_depth = std::max(max_depth, top);
   }
-  for (int64_t i = lo; i < hi; i++) {
-    const int mi = nb.unique[i];
-    const Move &m = nb.moves[mi];
-    const int v = t.nb[m.u][m.k], c = t.nb[m.x][m.kx];
-    Tmp o;
-    o.op.dst = -1;
-    o.op.nchild = FITCH_JOIN3;
-    o.op.tree = (int)(out.first_move_acc + (i - lo));
-    o.kids[0] = n_slot[mi];
-    o.kids[1] = dir_slot[3 * c + t.slot_of(c, m.x)];
-    o.kids[2] = dir_slot[3 * v + t.slot_of(v, m.u)];
-    o.level = d.max_level + max_depth + 1;
-    tmp.push_back(o);
+  const int n_levels = d.max_level + max_depth + 1;
+  prog.level_off.assign(n_levels + 1, 0);
+  for (int e : d.order) prog.level_off[d.level[e] + 1]++;
+  for (auto &c : cnt)
+    for (int dep = 1; dep <= max_depth && dep < (int)c.size(); dep++) prog.level_off[d.max_level + dep + 1] += c[dep];
+  for (int l = 0; l < n_levels; l++) prog.level_off[l + 1] += prog.level_off[l];
+  // per-thread write cursors per depth
+  std::vector<std::vector<int64_t>> cur(n_thr, std::vector<int64_t>(max_depth + 1, 0));
+  for (int dep = 1; dep <= max_depth; dep++) {
+    int64_t at = prog.level_off[d.max_level + dep];
+    for (int ti = 0; ti < n_thr; ti++) {
+      cur[ti][dep] = at;
+      at += dep < (int)cnt[ti].size() ? cnt[ti][dep] : 0;
+    }
   }
-  int max_level = 0;
-  for (auto &o : tmp) max_level = std::max(max_level, o.level);
-  prog.level_off.assign(max_level + 2, 0);
-  for (auto &o : tmp) prog.level_off[o.level + 1]++;
-  for (int l = 0; l <= max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
-  std::vector<int64_t> cur(prog.level_off.begin(), prog.level_off.end() - 1);
-  prog.ops.resize(tmp.size());
-  prog.children.reserve(tmp.size() * 3);
-  for (auto &o : tmp) {
-    o.op.child_off = (int)prog.children.size();
-    const int nk = o.op.nchild == FITCH_JOIN3 ? 3 : 2;
-    for (int j = 0; j < nk; j++) prog.children.push_back(o.kids[j]);
-    prog.ops[cur[o.level]++] = o.op;
+  const int64_t n_ops = n_dir + n_need;
+  prog.ops.resize(n_ops);
+  prog.children.resize(2 * n_dir + 4 * n_need);
+  FitchOp *ops = prog.ops.data();
+  int *kids = prog.children.data();
+  // directional ops (serial: 3(n-2) of them)
+  {
+    std::vector<int64_t> dcur(prog.level_off.begin(), prog.level_off.begin() + d.max_level + 1);
+    int64_t slots = 0, accs = 0;
+    for (int e : d.order) {
+      const int x = e / 3, k = e % 3;
+      const int64_t at = dcur[d.level[e]]++;
+      FitchOp o;
+      o.dst = n_tip_slots + (int)slots++;
+      o.nchild = 2;
+      o.tree = (int)accs;
+      o.child_off = (int)(2 * at);
+      out.dir_acc[e] = (int)accs++;
+      int s = 0;
+      for (int j = 0; j < 3; j++)
+        if (j != k) {
+          const int c = t.nb[x][j];
+          const int ce = 3 * c + t.slot_of(c, x);
+          kids[2 * at + s] = dir_slot[ce];
+          out.dir_kids[e][s] = t.is_tip(c) ? -1 : ce;
+          s++;
+        }
+      dir_slot[e] = o.dst;
+      ops[at] = o;
+    }
   }
-  prog.n_scratch_slots = slots;
+  const int dump_acc = (int)n_dir;  // own misses of search-step partials (never read)
+  out.first_move_acc = n_dir + 1;
+  // search steps, fused with the join of the neighbour they realise when that one is selected
+  parallel_for_threads(n_thr, [&](int ti, int nt) {
+    std::vector<int64_t> &c = cur[ti];
+    for (int64_t i = n_moves * ti / nt; i < n_moves * (ti + 1) / nt; i++) {
+      if (!all && !need[i]) continue;
+      const Move &m = nb.moves[i];
+      const int x = m.x, cnode = t.nb[x][m.kx];
+      int from, xin;
+      if (m.parent < 0) {
+        const int other = t.nb[m.u][(m.k + 1 + (1 - m.side)) % 3];
+        from = m.u;
+        xin = dir_slot[3 * other + t.slot_of(other, m.u)];  // D[other->u] enters x over the merged edge
+      } else {
+        from = nb.moves[m.parent].x;
+        xin = slot_of_move(m.parent);
+      }
+      int s = -1;
+      for (int j = 0; j < 3; j++)
+        if (t.nb[x][j] != from && t.nb[x][j] != cnode) s = t.nb[x][j];
+      const int64_t at = c[m.depth]++;
+      const int64_t koff = 2 * n_dir + 4 * (at - n_dir);
+      FitchOp o;
+      o.dst = slot_of_move(i);
+      o.child_off = (int)koff;
+      kids[koff] = xin;
+      kids[koff + 1] = dir_slot[3 * s + t.slot_of(s, x)];
+      const int uid = m.unique_id;
+      if (uid >= lo && uid < hi) {
+        const int v = t.nb[m.u][m.k];
+        o.nchild = FITCH_FUSED;
+        o.tree = (int)(out.first_move_acc + (uid - lo));
+        kids[koff + 2] = dir_slot[3 * cnode + t.slot_of(cnode, x)];
+        kids[koff + 3] = dir_slot[3 * v + t.slot_of(v, m.u)];
+      } else {
+        o.nchild = 2;
+        o.tree = dump_acc;
+        kids[koff + 2] = kids[koff + 3] = 0;
+      }
+      ops[at] = o;
+    }
+  });
+  prog.n_scratch_slots = n_dir + n_need;
   prog.n_costs = out.first_move_acc + (hi - lo);
 }
 
