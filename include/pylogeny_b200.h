@@ -154,6 +154,26 @@ int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int move_type, i
                                 int64_t shard_count, int64_t *n_moves, int32_t *out_moves,
                                 double *out_lnl, void *stream);
 
+/* ---- libpllWrapper compat (libpllWrapper.c:97-239): opaque problem handle ---- */
+typedef struct plg_pll plg_pll;
+/* new(alignment_file, newick, partition_file): PHYLIP file, unrooted Newick, partition file
+ * "DNA, p1 = 1-N" | "WAG, p1 = 1-N" (pll.py:112-115).  Input branch lengths are discarded
+ * (useDefaultz, :152): every branch starts at z = 0.9.  DNA = GTR with all rates 1 and
+ * empirical base frequencies, alpha = 1, 4 Gamma categories; WAG table provenance: see
+ * csrc/protein_models.cpp. */
+int plg_pll_new(const char *phylip_path, const char *newick, const char *partition_path,
+                plg_pll **out);
+int plg_pll_destroy(plg_pll *p);
+/* getLogLikelihood(handle): 3 branch-length smoothing passes, then lnL (:195-215).  MUTATES the
+ * handle's branch lengths like the reference does. */
+int plg_pll_loglik(plg_pll *p, double *out);
+/* lnL at the current branch lengths without optimisation (pllEvaluateLikelihood, :77-78). */
+int plg_pll_evaluate(plg_pll *p, double *out);
+/* getNewickString(handle) (:217-239): unrooted Newick with the current branch lengths.  *len in:
+ * buffer size, out: bytes needed incl. NUL; call with buf == NULL to size the buffer. */
+int plg_pll_newick(plg_pll *p, char *buf, size_t *len);
+int plg_pll_info(plg_pll *p, int *n_states, int64_t *n_patterns, double *freqs, double *rates);
+
 #ifdef __cplusplus
 }
 #endif

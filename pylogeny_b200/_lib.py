@@ -73,3 +73,9 @@ def _declare(L):
                                               vp, vp]
     L.plg_profile_enable.argtypes = [C.c_int]
     L.plg_profile_read.argtypes = [C.c_int, dp, dp, dp, i64p]
+    L.plg_pll_new.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(vp)]
+    L.plg_pll_destroy.argtypes = [vp]
+    L.plg_pll_loglik.argtypes = [vp, dp]
+    L.plg_pll_evaluate.argtypes = [vp, dp]
+    L.plg_pll_newick.argtypes = [vp, C.c_char_p, C.POINTER(C.c_size_t)]
+    L.plg_pll_info.argtypes = [vp, C.POINTER(C.c_int), i64p, dp, dp]

@@ -1,0 +1,550 @@
+// libpllWrapper compat: the opaque "problem" handle of libpllWrapper.c (:12-19, :97-239) on the
+// B200 engine -- new / destroy / getLogLikelihood / getNewickString.
+//
+// getLogLikelihood in the reference is pllOptimizeBranchLengths(inst, partitions, 3) followed by
+// instance->likelihood (libpllWrapper.c:205-209) on a tree loaded with DEFAULT branch lengths
+// (pllTreeInitTopologyNewick(..., PLL_TRUE), :152) under pllInitModel defaults (:159).  libpll's
+// source is not available offline, so what follows restates the published procedure it implements
+// (marked "from memory" there): branch-by-branch Newton-Raphson on log z
+// (z = exp(-t)), start z = 0.9, one Newton step per branch per smoothing pass, at most 3 passes,
+// z clamped to [1e-15, 1-1e-6], depth-first from the first taxon with on-demand re-orientation of
+// the conditional likelihood vectors.  Parity with libpll's number is UNPINNED;
+// parity with the CPU oracle at the resulting branch lengths is tested.
+//
+// Device work: sumtable_kernel (per-pattern eigen-space products of the two CLVs facing a
+// branch), deriv_kernel (lnL, d/dlz, d2/dlz2 per pattern, block-reduced), plus the CLV update
+// kernels of lik.cu for the re-orientations.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <unordered_map>
+
+#include "lik.h"
+#include "neighbourhood.h"
+
+namespace plg {
+
+constexpr double PLL_ZMIN = 1.0e-15, PLL_ZMAX = 1.0 - 1.0e-6, PLL_DEFAULTZ = 0.9, PLL_DELTAZ = 1.0e-5;
+constexpr double SM_MINLH = 8.636168555094445e-78;  // 2^-256
+constexpr int SM_THREADS = 256;
+
+extern const double *const WAG_EXCH_PTR;  // protein_models.cpp
+extern const double WAG_FREQS[20];
+
+// S[r*K+k][p] = (sum_i pi_i A_r[i] U[i][k]) * (sum_j Uinv[k][j] B_r[j]);  L_p(t) = (1/R) sum S exp(eval_k rate_r t)
+template <int K, int R>
+__global__ void __launch_bounds__(SM_THREADS)
+sumtable_kernel(int a_id, int b_id, int n_rows, int64_t Ppad, const unsigned char *__restrict__ codes,
+                const unsigned int *__restrict__ masks, const ModelDev *__restrict__ model,
+                const double *__restrict__ clv, const int *__restrict__ scl, double *__restrict__ S,
+                int *__restrict__ sc_out) {
+  const int r = threadIdx.x % R;
+  const int64_t p = (int64_t)blockIdx.x * (SM_THREADS / R) + threadIdx.x / R;
+  double A[K], B[K];
+  int sc = 0;
+  auto fetch = [&](int id, double(&x)[K]) {
+    if (id < n_rows) {
+      const unsigned int m = masks[codes[(int64_t)id * Ppad + p]];
+#pragma unroll
+      for (int k = 0; k < K; k++) x[k] = (m >> k & 1) ? 1.0 : 0.0;
+    } else {
+      const double *src = clv + ((int64_t)(id - n_rows) * R * K + r * K) * Ppad + p;
+#pragma unroll
+      for (int k = 0; k < K; k++) x[k] = src[(int64_t)k * Ppad];
+      sc += scl[(int64_t)(id - n_rows) * Ppad + p];
+    }
+  };
+  fetch(a_id, A);
+  fetch(b_id, B);
+#pragma unroll
+  for (int i = 0; i < K; i++) A[i] *= model->freqs[i];
+  for (int k = 0; k < K; k++) {
+    double l = 0.0, rr = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      l = fma(A[i], model->U[i * K + k], l);
+      rr = fma(model->Uinv[k * K + i], B[i], rr);
+    }
+    S[((int64_t)r * K + k) * Ppad + p] = l * rr;
+  }
+  if (r == 0) sc_out[p] = sc;
+}
+
+struct ExpTable {  // e0 = exp(eval*rate*t), e1 = (eval*rate) e0 * dt/dlz, e2 likewise squared
+  double e0[LIK_MAX_CATS * LIK_MAX_STATES], e1[LIK_MAX_CATS * LIK_MAX_STATES], e2[LIK_MAX_CATS * LIK_MAX_STATES];
+};
+
+template <int K, int R>
+__global__ void __launch_bounds__(SM_THREADS)
+deriv_kernel(const double *__restrict__ S, const int *__restrict__ sc, const double *__restrict__ weights,
+             const ExpTable *__restrict__ tab, int64_t Ppad, double *__restrict__ partial, int n_blocks) {
+  __shared__ double ws[3][SM_THREADS / 32];
+  const int r = threadIdx.x % R;
+  const int64_t p = (int64_t)blockIdx.x * (SM_THREADS / R) + threadIdx.x / R;
+  double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const double s = S[((int64_t)r * K + k) * Ppad + p];
+    l0 = fma(s, tab->e0[r * K + k], l0);
+    l1 = fma(s, tab->e1[r * K + k], l1);
+    l2 = fma(s, tab->e2[r * K + k], l2);
+  }
+#pragma unroll
+  for (int d = 1; d < R; d <<= 1) {
+    l0 += __shfl_xor_sync(0xffffffffu, l0, d);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, d);
+    l2 += __shfl_xor_sync(0xffffffffu, l2, d);
+  }
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  const double w = weights[p];
+  if (r == 0 && w != 0.0) {
+    const double inv = 1.0 / l0, d1 = l1 * inv;
+    v0 = w * (log(l0 * (1.0 / R)) + sc[p] * log(SM_MINLH));
+    v1 = w * d1;
+    v2 = w * (l2 * inv - d1 * d1);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v0 += __shfl_down_sync(0xffffffffu, v0, d);
+    v1 += __shfl_down_sync(0xffffffffu, v1, d);
+    v2 += __shfl_down_sync(0xffffffffu, v2, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    ws[0][threadIdx.x >> 5] = v0; ws[1][threadIdx.x >> 5] = v1; ws[2][threadIdx.x >> 5] = v2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int i = 0; i < SM_THREADS / 32; i++) s += ws[threadIdx.x][i];
+    partial[(int64_t)threadIdx.x * n_blocks + blockIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct PllProblem {
+  std::unique_ptr<LikAln> aln;
+  std::unique_ptr<Model> model;
+  UTree tree;
+  std::vector<std::string> tip_names;  // tip id -> label
+  std::vector<int32_t> tip_rows;       // tip id -> alignment row
+  bool smoothed = false;
+  double lnl = 0.0;
+
+  // scratch (device) for smoothing
+  DevBuf<double> S;
+  DevBuf<int> Ssc;
+  DevBuf<double> partial;
+  DevBuf<ExpTable> tab;
+  std::vector<double> h_partial;
+
+  int dir_id(int x, int k) const { return x < tree.n_tips ? tip_rows[x] : aln->n_rows + 3 * x + k; }
+  int dir_to(int x, int y) const { return dir_id(x, tree.slot_of(x, y)); }
+  int64_t n_slots() const { return 3 * (int64_t)tree.n_nodes; }
+
+  void clv_update(int x, int k) {  // D[x -> nb[x][k]] from the two other neighbours' partials
+    LikProgram prog;
+    LikOp op;
+    op.dst = dir_id(x, k);
+    int s = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        const int c = tree.nb[x][j];
+        const int id = dir_to(c, x), pm = prog.pm(tree.len[x][j]);
+        if (s == 0) { op.a = id; op.pa = pm; } else { op.b = id; op.pb = pm; }
+        s++;
+      }
+    prog.ops.push_back(op);
+    prog.level_off = {0, 1};
+    prog.n_slots = n_slots();
+    prog.n_trees = 0;
+    run_lik_program(*aln, *model, lik_workspace(), prog, nullptr, 0);
+  }
+
+  template <int K, int R>
+  void derivs_typed(int a_id, int b_id, bool build_table, double lz, double out[3]) {
+    LikWorkspace &ws = lik_workspace();
+    const int per_block = SM_THREADS / R;
+    const int n_blocks = (int)(aln->Ppad / per_block);
+    if (build_table) {
+      sumtable_kernel<K, R><<<n_blocks, SM_THREADS>>>(a_id, b_id, aln->n_rows, aln->Ppad, aln->codes.p, aln->masks.p,
+                                                      model->d.p, ws.clv.p, ws.scl.p, S.p, Ssc.p);
+      count_launch();
+    }
+    ExpTable h;
+    for (int r = 0; r < R; r++)
+      for (int k = 0; k < K; k++) {
+        const double g = -model->h.eval[k] * model->h.rates[r];  // t = -lz: d/dlz exp(eval*rate*t) = g * exp(.)
+        const double e = std::exp(g * lz);
+        h.e0[r * K + k] = e; h.e1[r * K + k] = g * e; h.e2[r * K + k] = g * g * e;
+      }
+    PLG_CUDA(cudaMemcpyAsync(tab.p, &h, sizeof h, cudaMemcpyHostToDevice, 0));
+    deriv_kernel<K, R><<<n_blocks, SM_THREADS>>>(S.p, Ssc.p, aln->weights.p, tab.p, aln->Ppad, partial.p, n_blocks);
+    count_launch();
+    PLG_CUDA(cudaMemcpy(h_partial.data(), partial.p, (size_t)3 * n_blocks * 8, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 3; q++) {
+      double s = 0.0;
+      for (int b = 0; b < n_blocks; b++) s += h_partial[(size_t)q * n_blocks + b];  // fixed order
+      out[q] = s;
+    }
+  }
+
+  void derivs(int a_id, int b_id, bool build_table, double lz, double out[3]) {
+    const int K = aln->K, R = model->R;
+    if (K == 4 && R == 4) derivs_typed<4, 4>(a_id, b_id, build_table, lz, out);
+    else if (K == 4 && R == 1) derivs_typed<4, 1>(a_id, b_id, build_table, lz, out);
+    else if (K == 20 && R == 4) derivs_typed<20, 4>(a_id, b_id, build_table, lz, out);
+    else if (K == 20 && R == 1) derivs_typed<20, 1>(a_id, b_id, build_table, lz, out);
+    else PLG_FAIL(PLG_ERR_UNSUPPORTED, "kernels exist for 4 or 20 states with 1 or 4 rate categories");
+  }
+
+  // One makenewz-style update of branch {x, y}: `maxiter` Newton steps on lz = log z.  Returns the new z.
+  double optimise_branch(int x, int y, int maxiter, double *lnl_out) {
+    const int kx = tree.slot_of(x, y), ky = tree.slot_of(y, x);
+    double z = std::exp(-tree.len[x][kx]);
+    z = std::min(std::max(z, PLL_ZMIN), PLL_ZMAX);
+    const int a_id = dir_to(x, y), b_id = dir_to(y, x);
+    bool first = true;
+    double d[3] = {0, 0, 0};
+    while (maxiter-- > 0) {
+      double zprev = z;
+      const double zstep = (1.0 - PLL_ZMAX) * z + PLL_ZMIN;
+      for (int guard = 0; guard < 64; guard++) {  // "bad curvature: shorten the branch" loop
+        derivs(a_id, b_id, first, std::log(std::max(z, PLL_ZMIN)), d);
+        first = false;
+        if (d[2] >= 0.0 && z < PLL_ZMAX) zprev = z = 0.37 * z + 0.63;
+        else break;
+      }
+      if (d[2] < 0.0) {
+        const double tantmp = -d[1] / d[2];
+        if (tantmp < 100.0) {
+          z *= std::exp(tantmp);
+          if (z < PLL_ZMIN) z = PLL_ZMIN;
+          if (z > 0.25 * zprev + 0.75) z = 0.25 * zprev + 0.75;
+        } else {
+          z = 0.25 * zprev + 0.75;
+        }
+      }
+      if (z > PLL_ZMAX) z = PLL_ZMAX;
+      if (std::fabs(z - zprev) <= zstep) break;
+    }
+    const double t = -std::log(z);
+    tree.len[x][kx] = tree.len[y][ky] = t;
+    if (lnl_out) *lnl_out = d[0];
+    return z;
+  }
+
+  // smooth(): optimise the branch above x, then its subtree, then restore x's down view
+  void smooth(int x, int from, bool *all_smoothed) {
+    const int kf = tree.slot_of(x, from);
+    const double z0 = std::exp(-tree.len[x][kf]);
+    const double z = optimise_branch(x, from, 1, nullptr);
+    if (std::fabs(z - z0) > PLL_DELTAZ) *all_smoothed = false;
+    if (tree.is_tip(x)) return;
+    for (int j = 0; j < 3; j++) {
+      if (j == kf) continue;
+      clv_update(x, j);  // view from x toward this child: needs the (just re-optimised) branch above x
+      smooth(tree.nb[x][j], x, all_smoothed);
+    }
+    clv_update(x, kf);  // children's branches changed: refresh x's down view
+  }
+
+  double evaluate() {  // lnL across the branch at tip 0 with all down views fresh
+    const int w = tree.nb[0][0];
+    LikProgram prog;
+    LikEval ev;
+    ev.a = tip_rows[0]; ev.pa = -1;
+    ev.b = dir_to(w, 0); ev.pb = prog.pm(tree.len[0][0]);
+    ev.c = -1; ev.pc = -1; ev.tree = 0; ev.pad = 0;
+    prog.evals.push_back(ev);
+    prog.level_off = {0, 0};
+    prog.n_slots = n_slots();
+    prog.n_trees = 1;
+    double out = 0.0;
+    run_lik_program(*aln, *model, lik_workspace(), prog, &out, 0);
+    return out;
+  }
+
+  void down_pass() {  // every D[x -> parent] with tip 0 as the root, leaves first
+    std::vector<int> par(tree.n_nodes, -1), bfs{0};
+    for (size_t i = 0; i < bfs.size(); i++)
+      for (int k = 0; k < 3; k++) {
+        const int y = tree.nb[bfs[i]][k];
+        if (y >= 0 && y != par[bfs[i]]) { par[y] = bfs[i]; bfs.push_back(y); }
+      }
+    for (size_t i = bfs.size(); i-- > 1;)
+      if (!tree.is_tip(bfs[i])) clv_update(bfs[i], tree.slot_of(bfs[i], par[bfs[i]]));
+  }
+
+  double loglik(int max_passes) {
+    if (tree.n_tips < 3) PLG_FAIL(PLG_ERR_UNSUPPORTED, "need at least 3 taxa");
+    const int per_block = SM_THREADS / model->R;
+    const int n_blocks = (int)(aln->Ppad / per_block);
+    S.alloc((size_t)model->R * aln->K * aln->Ppad);
+    Ssc.alloc(aln->Ppad);
+    partial.alloc((size_t)3 * n_blocks);
+    tab.alloc(1);
+    h_partial.resize((size_t)3 * n_blocks);
+    down_pass();
+    for (int pass = 0; pass < max_passes; pass++) {  // smoothTree(maxtimes)
+      bool all_smoothed = true;
+      smooth(tree.nb[0][0], 0, &all_smoothed);
+      if (all_smoothed) break;
+    }
+    lnl = evaluate();
+    smoothed = true;
+    return lnl;
+  }
+
+  void newick_rec(int x, int from, std::ostringstream &os) const {
+    if (tree.is_tip(x)) { os << tip_names[x]; return; }
+    os << "(";
+    bool first = true;
+    for (int j = 0; j < 3; j++) {
+      const int c = tree.nb[x][j];
+      if (c == from) continue;
+      if (!first) os << ",";
+      first = false;
+      newick_rec(c, x, os);
+      os << ":" << tree.len[x][j];
+    }
+    os << ")";
+  }
+
+  std::string newick() const {  // unrooted, from the inner node next to the first taxon (:227-229)
+    std::ostringstream os;
+    os.precision(17);
+    const int w = tree.nb[0][0];
+    os << "(" << tip_names[0] << ":" << tree.len[0][0];
+    for (int j = 0; j < 3; j++) {
+      const int c = tree.nb[w][j];
+      if (c == 0) continue;
+      os << ",";
+      newick_rec(c, w, os);
+      os << ":" << tree.len[w][j];
+    }
+    os << ");";
+    return os.str();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+static void read_phylip(const char *path, std::vector<std::string> &names, std::vector<std::string> &seqs) {
+  std::ifstream in(path);
+  if (!in) PLG_FAIL(PLG_ERR_IO, "Alignment file could not be parsed.");
+  size_t n = 0, m = 0;
+  in >> n >> m;
+  if (!in || n == 0 || m == 0) PLG_FAIL(PLG_ERR_IO, "Alignment file could not be parsed.");
+  std::string line;
+  std::getline(in, line);
+  names.assign(n, "");
+  seqs.assign(n, "");
+  size_t row = 0;
+  bool header_done = false;
+  while (std::getline(in, line)) {
+    std::istringstream ls(line);
+    std::string tok;
+    std::vector<std::string> toks;
+    while (ls >> tok) toks.push_back(tok);
+    if (toks.empty()) continue;
+    size_t from = 0;
+    if (!header_done) { names[row] = toks[0]; from = 1; }
+    for (size_t i = from; i < toks.size(); i++) seqs[row] += toks[i];
+    if (++row == n) { row = 0; header_done = true; }
+    bool full = header_done;
+    for (auto &s : seqs) full = full && s.size() >= m;
+    if (full) break;
+  }
+  for (auto &s : seqs)
+    if (s.size() != m) PLG_FAIL(PLG_ERR_IO, "Alignment file could not be parsed.");
+}
+
+static std::string read_partition_model(const char *path) {
+  std::ifstream in(path);
+  if (!in) PLG_FAIL(PLG_ERR_IO, "Partition file could not be read.");
+  std::string line;
+  std::getline(in, line);  // "DNA, p1 = 1-N" | "WAG, p1 = 1-N"  (pll.py:112-115)
+  std::string model = line.substr(0, line.find(','));
+  model.erase(std::remove_if(model.begin(), model.end(), [](char c) { return c == ' ' || c == '\t' || c == '\r'; }),
+              model.end());
+  if (model.empty()) PLG_FAIL(PLG_ERR_IO, "Partition file could not be parsed.");
+  return model;
+}
+
+static uint8_t dna_code(char c) {
+  switch (c >= 'a' && c <= 'z' ? c - 32 : c) {
+    case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': case 'U': return 8;
+    case 'M': return 3; case 'R': return 5; case 'W': return 9; case 'S': return 6; case 'Y': return 10;
+    case 'K': return 12; case 'V': return 7; case 'H': return 11; case 'D': return 13; case 'B': return 14;
+    default: return 15;
+  }
+}
+static uint8_t aa_code(char c) {
+  static const char *order = "ARNDCQEGHILKMFPSTWYV";
+  const char u = c >= 'a' && c <= 'z' ? c - 32 : c;
+  const char *at = strchr(order, u);
+  if (at && u) return (uint8_t)(at - order);
+  if (u == 'B') return 20;
+  if (u == 'Z') return 21;
+  return 22;
+}
+
+// HostTree (bifurcating or trifurcating root, binary elsewhere) -> UTree with tips in Newick order
+static UTree utree_from_newick(const HostTree &ht, std::vector<std::string> &tip_names) {
+  std::vector<int> po = ht.post_order();
+  std::vector<int> id(ht.nodes.size(), -1);
+  int n_tips = 0;
+  for (int x : po)
+    if (ht.nodes[x].children.empty()) { id[x] = n_tips++; tip_names.push_back(ht.nodes[x].label); }
+  if (n_tips < 3) PLG_FAIL(PLG_ERR_UNSUPPORTED, "need at least 3 taxa");
+  // binarise: resolve every k-ary node left to right with zero-length branches, as a rooted descriptor
+  std::vector<int32_t> desc;
+  std::vector<double> br;
+  for (int x : po) {
+    const HostNode &nd = ht.nodes[x];
+    if (nd.children.empty()) continue;
+    if (nd.children.size() == 1) PLG_FAIL(PLG_ERR_UNSUPPORTED, "unary nodes are not supported in likelihood trees");
+    int acc = id[nd.children[0]];
+    double acc_len = ht.nodes[nd.children[0]].brlen;
+    for (size_t j = 1; j < nd.children.size(); j++) {
+      desc.push_back(acc);
+      desc.push_back(id[nd.children[j]]);
+      br.push_back(acc_len);
+      br.push_back(ht.nodes[nd.children[j]].brlen);
+      acc = n_tips + (int)desc.size() / 2 - 1;
+      acc_len = 0.0;
+    }
+    id[x] = acc;
+  }
+  if ((int)desc.size() / 2 != n_tips - 1) PLG_FAIL(PLG_ERR_PARSE, "Tree was not able to be parsed.");
+  return utree_from_desc(n_tips, desc.data(), br.data());
+}
+
+}  // namespace plg
+
+using namespace plg;
+
+struct plg_pll {
+  PllProblem p;
+};
+
+extern "C" int plg_pll_new(const char *phylip_path, const char *newick, const char *partition_path, plg_pll **out) {
+  PLG_API_BEGIN
+  if (!phylip_path || !newick || !partition_path || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+    PLG_FAIL(PLG_ERR_CUDA, "no CUDA device: pylogeny_b200 has no CPU fallback");
+  std::vector<std::string> names, seqs;
+  read_phylip(phylip_path, names, seqs);
+  const std::string model_name = read_partition_model(partition_path);
+  const bool dna = (model_name == "DNA");
+  if (!dna && model_name != "WAG")
+    PLG_FAIL(PLG_ERR_UNSUPPORTED, "protein model '%s': only WAG ships with the engine (pll.py:102 default); "
+             "use plg_model_create for other matrices", model_name.c_str());
+  std::unique_ptr<plg_pll> h(new plg_pll());
+  PllProblem &pr = h->p;
+  HostTree ht = parse_newick(newick);
+  pr.tree = utree_from_newick(ht, pr.tip_names);
+  std::unordered_map<std::string, int> row_of;
+  for (size_t i = 0; i < names.size(); i++) row_of.emplace(names[i], (int)i);
+  if ((size_t)pr.tree.n_tips != names.size())
+    PLG_FAIL(PLG_ERR_IO, "Could not find correct correspondances.");  // libpllWrapper.c:153-156
+  for (auto &nm : pr.tip_names) {
+    auto it = row_of.find(nm);
+    if (it == row_of.end()) PLG_FAIL(PLG_ERR_IO, "Could not find correct correspondances.");
+    pr.tip_rows.push_back(it->second);
+  }
+  // default branch lengths (useDefaultz = PLL_TRUE, libpllWrapper.c:152): every z = 0.9
+  for (auto &l : pr.tree.len) for (auto &x : l) x = -std::log(PLL_DEFAULTZ);
+  // encode + compress identical columns (weights = multiplicities; lnL is unchanged)
+  const size_t n = names.size(), m = seqs[0].size();
+  std::vector<uint8_t> codes(n * m);
+  for (size_t r = 0; r < n; r++)
+    for (size_t s = 0; s < m; s++) codes[r * m + s] = dna ? dna_code(seqs[r][s]) : aa_code(seqs[r][s]);
+  std::unordered_map<std::string, int> seen;
+  std::vector<size_t> first;
+  std::vector<double> w;
+  std::string col(n, '\0');
+  for (size_t s = 0; s < m; s++) {
+    for (size_t r = 0; r < n; r++) col[r] = (char)codes[r * m + s];
+    auto ins = seen.emplace(col, (int)first.size());
+    if (ins.second) { first.push_back(s); w.push_back(1.0); }
+    else w[ins.first->second] += 1.0;
+  }
+  const size_t P = first.size();
+  std::vector<uint8_t> packed(n * P);
+  for (size_t r = 0; r < n; r++)
+    for (size_t q = 0; q < P; q++) packed[r * P + q] = codes[r * m + first[q]];
+  pr.aln.reset(new LikAln(dna ? PLG_DATA_DNA : PLG_DATA_AA, (int)n, (int64_t)P, packed.data(), w.data()));
+  if (dna) {
+    // GTR with all six rates 1.0 and empirical base frequencies; ambiguity codes share their
+    // count among compatible bases in proportion to the current estimate (8 rounds)
+    double f[4] = {0.25, 0.25, 0.25, 0.25};
+    for (int round = 0; round < 8; round++) {
+      double cnt[4] = {0, 0, 0, 0};
+      for (size_t q = 0; q < P; q++)
+        for (size_t r = 0; r < n; r++) {
+          const unsigned mask = packed[r * P + q];
+          if (mask == 15 || mask == 0) continue;
+          double tot = 0;
+          for (int k = 0; k < 4; k++) if (mask >> k & 1) tot += f[k];
+          for (int k = 0; k < 4; k++) if (mask >> k & 1) cnt[k] += w[q] * f[k] / tot;
+        }
+      double s = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+      if (s <= 0) break;
+      for (int k = 0; k < 4; k++) f[k] = std::max(cnt[k] / s, 1e-6);
+    }
+    const double ones[6] = {1, 1, 1, 1, 1, 1};
+    pr.model.reset(new Model(4, ones, f, 1.0, 4));
+  } else {
+    pr.model.reset(new Model(20, WAG_EXCH_PTR, WAG_FREQS, 1.0, 4));
+  }
+  *out = h.release();
+  PLG_API_END
+}
+
+extern "C" int plg_pll_destroy(plg_pll *p) {
+  delete p;
+  return PLG_OK;
+}
+
+extern "C" int plg_pll_loglik(plg_pll *p, double *out) {
+  PLG_API_BEGIN
+  if (!p || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  *out = p->p.loglik(3);  // pllOptimizeBranchLengths(instance, partitions, 3), libpllWrapper.c:205
+  PLG_API_END
+}
+
+// lnL at the CURRENT branch lengths, no optimisation (pllEvaluateLikelihood, libpllWrapper.c:77-78)
+extern "C" int plg_pll_evaluate(plg_pll *p, double *out) {
+  PLG_API_BEGIN
+  if (!p || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  p->p.down_pass();
+  *out = p->p.evaluate();
+  PLG_API_END
+}
+
+extern "C" int plg_pll_newick(plg_pll *p, char *buf, size_t *len) {
+  PLG_API_BEGIN
+  if (!p || !len) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  const std::string s = p->p.newick();
+  const size_t need = s.size() + 1;
+  if (buf && *len >= need) memcpy(buf, s.c_str(), need);
+  const bool ok = buf && *len >= need;
+  *len = need;
+  if (!ok && buf) PLG_FAIL(PLG_ERR_ARG, "buffer too small: need %zu bytes", need);
+  PLG_API_END
+}
+
+// Model and pattern set of a problem, for tests: exch[K(K-1)/2], freqs[K], rates[R], and counts.
+extern "C" int plg_pll_info(plg_pll *p, int *n_states, int64_t *n_patterns, double *freqs, double *rates) {
+  PLG_API_BEGIN
+  if (!p) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  if (n_states) *n_states = p->p.aln->K;
+  if (n_patterns) *n_patterns = p->p.aln->P;
+  if (freqs) for (int k = 0; k < p->p.aln->K; k++) freqs[k] = p->p.model->h.freqs[k];
+  if (rates) for (int r = 0; r < p->p.model->R; r++) rates[r] = p->p.model->h.rates[r];
+  PLG_API_END
+}

@@ -1,0 +1,87 @@
+"""Drop-in for the reference's `libpllWrapper` extension module (libpllWrapper.c:323-339).
+
+    new(alignment_file, newick, partition_file) -> handle      (:97-171)
+    destroy(handle) -> None                                    (:173-193)
+    getLogLikelihood(handle) -> float   (mutates branch lengths, :195-215)
+    getNewickString(handle) -> str                             (:217-239)
+
+over the C-ABI `plg_pll_*` (include/pylogeny_b200.h).  Error behaviour follows the reference:
+IOError for unparsable inputs (:141-146, :153-156, :211), ReferenceError for a bad handle (:178).
+The libpll-internal move enumerators getSPR/NNI/AllMovesInDistance (:241-319) have no Python caller
+in the reference; their role -- lnL of a whole neighbourhood -- is
+pylogeny_b200.neighbourhood.score_likelihood.
+"""
+import ctypes as C
+
+from . import _lib
+
+__all__ = ["new", "destroy", "getLogLikelihood", "getNewickString", "evaluate"]
+
+
+class _Handle(object):
+    __slots__ = ("ptr",)
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+
+def _ptr(handle):
+    if not isinstance(handle, _Handle) or not handle.ptr:
+        raise ReferenceError("Could not parse pointer.")
+    return handle.ptr
+
+
+def _raise(rc):
+    msg = _lib.lib().plg_last_error().decode(errors="replace")
+    if rc in (_lib.ERR_IO, _lib.ERR_PARSE, _lib.ERR_LABEL):
+        raise IOError(msg)
+    raise _lib.EngineError(rc, msg)
+
+
+def new(alignf, newick, partf):
+    """Initialize a problem with an alignment, Newick tree, and partition model."""
+    if not all(isinstance(x, str) for x in (alignf, newick, partf)):
+        raise IOError("Need alignment file, newick string, partition file as strings.")
+    h = C.c_void_p()
+    rc = _lib.lib().plg_pll_new(alignf.encode(), newick.encode(), partf.encode(), C.byref(h))
+    if rc:
+        _raise(rc)
+    return _Handle(h)
+
+
+def destroy(handle):
+    """Destroy an input problem and deallocate all resources."""
+    p = _ptr(handle)
+    _lib.lib().plg_pll_destroy(p)
+    handle.ptr = None
+
+
+def getLogLikelihood(handle):
+    """Score a tree and acquire its log-likelihood for a given input problem."""
+    out = C.c_double()
+    rc = _lib.lib().plg_pll_loglik(_ptr(handle), C.byref(out))
+    if rc:
+        _raise(rc)
+    if not out.value:
+        raise IOError("Unable to evaluate tree for likelihood.")
+    return out.value
+
+
+def evaluate(handle):
+    """lnL at the current branch lengths, no optimisation (extension; pllEvaluateLikelihood)."""
+    out = C.c_double()
+    rc = _lib.lib().plg_pll_evaluate(_ptr(handle), C.byref(out))
+    if rc:
+        _raise(rc)
+    return out.value
+
+
+def getNewickString(handle):
+    """Get the Newick string for the current initialized problem."""
+    n = C.c_size_t(0)
+    _lib.lib().plg_pll_newick(_ptr(handle), None, C.byref(n))
+    buf = C.create_string_buffer(n.value)
+    rc = _lib.lib().plg_pll_newick(_ptr(handle), buf, C.byref(n))
+    if rc:
+        raise IOError("Unable to acquire Newick string for tree.")
+    return buf.value.decode()

@@ -1,0 +1,118 @@
+"""libpllWrapper / pll.py / scoring.getLogLikelihood compat path on the GPU: evaluation at the
+default branch lengths and after 3 smoothing passes, both checked against the FP64 oracle at the
+branch lengths the handle reports (1e-8 relative)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from util import desc_to_newick, random_desc, simulate_dna
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_at(newick, taxa, codes, w, exch, freqs, alpha):
+    from pylogeny_b200 import neighbourhood as nbh
+    d, br, rows, _ = nbh.newick_to_desc(newick, taxa)
+    return oracle.lnl(codes[rows], w, exch, freqs, alpha, d, br)
+
+
+def _case(n=12, S=1500, seed=3):
+    from pylogeny_b200 import alignment
+    rng = np.random.default_rng(seed)
+    d = random_desc(rng, n)
+    br = rng.exponential(0.08, d.shape) + 0.01
+    exch = np.array([1.0, 3.0, 0.7, 1.3, 4.0, 1.0])
+    f = np.array([0.3, 0.2, 0.2, 0.3])
+    seqs = simulate_dna(rng, d, br, S, exch, f)
+    seqs[1] = seqs[1][:20] + "N-RY" + seqs[1][24:]      # ambiguity codes and gaps
+    ali = alignment.phylipFriendlyAlignment(names=["tax%d" % i for i in range(n)], seqs=seqs)
+    return ali, d
+
+
+def test_new_evaluate_smooth_newick():
+    from pylogeny_b200 import _lib, libpllWrapper as W, likelihood, pll
+    ali, d = _case()
+    n = ali.getNumSeqs()
+    labels = ali.getTaxa()
+    # unrooted Newick with a trifurcating top node, as toUnrootedNewick() hands over (rearrangement.py:715-732)
+    rooted = desc_to_newick(d, labels)
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    h = W.new(ali.getPhylip(), rooted, pm.getFileName())
+    K, P = C.c_int(), C.c_int64()
+    freqs, rates = np.zeros(4), np.zeros(4)
+    dp = C.POINTER(C.c_double)
+    _lib.check(_lib.lib().plg_pll_info(h.ptr, C.byref(K), C.byref(P), freqs.ctypes.data_as(dp), rates.ctypes.data_as(dp)))
+    assert K.value == 4 and P.value <= ali.getSize()
+    np.testing.assert_allclose(rates, oracle.gamma_rates(1.0, 4), rtol=1e-12)
+    codes = likelihood.encode_sequences(ali.toStrList(), _lib.DATA_DNA)
+    counts = np.array([(codes == m).sum() for m in (1, 2, 4, 8)], float)
+    assert np.allclose(freqs, counts / counts.sum(), atol=2e-3)        # empirical (ambiguities shared out)
+    taxa = {l: i for i, l in enumerate(labels)}
+    w = np.ones(ali.getSize())
+    l0 = W.evaluate(h)
+    nw0 = W.getNewickString(h)
+    assert abs(l0 - _oracle_at(nw0, taxa, codes, w, np.ones(6), freqs, 1.0)) <= 1e-8 * abs(l0)
+    from pylogeny_b200 import neighbourhood as nbh
+    _, br0, _, _ = nbh.newick_to_desc(nw0, taxa)
+    assert np.allclose(br0[br0 > 0], -np.log(0.9))                      # default z = 0.9 on every branch
+    l1 = W.getLogLikelihood(h)
+    nw1 = W.getNewickString(h)
+    assert l1 > l0 + 1.0
+    assert abs(l1 - _oracle_at(nw1, taxa, codes, w, np.ones(6), freqs, 1.0)) <= 1e-8 * abs(l1)
+    l2 = W.getLogLikelihood(h)                                          # three more passes: nearly converged
+    assert l2 >= l1 - 1e-6 and (l2 - l1) < 1e-3 * abs(l1)
+    W.destroy(h)
+    with pytest.raises(ReferenceError):
+        W.getLogLikelihood(h)
+    with pytest.raises(IOError):
+        W.new("/nonexistent.phy", rooted, pm.getFileName())
+    pm.close()
+    ali.close()
+
+
+def test_scoring_getLogLikelihood_dropin():
+    """scoring.getLogLikelihood(tree, alignment) with the reference's call pattern (scoring.py:41-75)."""
+    from pylogeny_b200 import scoring
+    ali, d = _case(n=8, S=600, seed=9)
+    labels = ali.getTaxa()
+
+    class Topo(object):
+        def toUnrootedNewick(self):
+            return desc_to_newick(d, labels)
+
+    class Tree(object):
+        newick = None
+
+        def toTopology(self):
+            return Topo()
+
+        def updateNewick(self, nw, reroot=True):
+            self.newick = nw
+
+    t = Tree()
+    sc = scoring.getLogLikelihood(t, ali)
+    assert isinstance(sc, float) and sc < 0
+    assert t.newick.endswith(";") and t.newick.count(":") == 2 * 8 - 3
+    assert scoring.getLogLikelihood(t, "not an alignment") is None       # any failure -> None (scoring.py:59-60)
+    ali.close()
+
+
+def test_wag_model_is_usable():
+    """The shipped WAG table builds a valid reversible model (provenance flagged unverified)."""
+    from pylogeny_b200 import _lib, alignment, libpllWrapper as W, pll
+    rng = np.random.default_rng(4)
+    aa = "ARNDCQEGHILKMFPSTWYV"
+    seqs = ["".join(aa[i] for i in rng.integers(0, 20, 120)) for _ in range(6)]
+    ali = alignment.phylipFriendlyAlignment(names=list("abcdef"), seqs=seqs)
+    assert ali.getDataType() == 'protein'
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    h = W.new(ali.getPhylip(), "(T0,T1,(T2,(T3,(T4,T5))));", pm.getFileName())
+    l0 = W.evaluate(h)
+    l1 = W.getLogLikelihood(h)
+    assert np.isfinite(l0) and l1 >= l0
+    W.destroy(h)
+    pm.close(); ali.close()

@@ -56,3 +56,20 @@ def random_states(rng, n_rows, P, n_states=4, gap_frac=0.0):
 
 def states_to_profiles(states):
     return [bytes(row).decode("ascii") for row in states]
+
+
+def simulate_dna(rng, desc, brlen, n_sites, exch, freqs):
+    """Evolve ACGT sequences down a rooted descriptor tree with one rate category (test data with signal)."""
+    import oracle
+    n = desc.shape[0] + 1
+    root = n + len(desc) - 1
+    states = {root: rng.choice(4, n_sites, p=freqs)}
+    for i in range(len(desc) - 1, -1, -1):
+        for k, c in enumerate(desc[i]):
+            P = oracle.pmatrix(exch, freqs, float(brlen[i][k]))
+            P = np.clip(P, 0, None)
+            P /= P.sum(1, keepdims=True)
+            cum = P.cumsum(1)
+            u = rng.random(n_sites)
+            states[int(c)] = (u[:, None] > cum[states[n + i]]).sum(1).clip(0, 3)
+    return ["".join("ACGT"[s] for s in states[t]) for t in range(n)]
