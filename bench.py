@@ -7,9 +7,12 @@ Workload at every N: BASELINE.json configs[1] -- synthetic DNA, 64 taxa x 10,000
 uniform ACGT, seed 1001, so patterns = sites), GTR+Gamma4 log-likelihood at fixed branch
 lengths of every distinct SPR neighbour (14,762) of a random tree.  One "step" = one pass of
 the hot path over that batch: plan (host) + score (device) + read back the per-tree scores.
-At N > 1 the job is N such neighbourhoods (base trees seeded 1001+b); every neighbourhood is
-sharded N ways across the ranks (contiguous blocks of its move list, full alignment on every
-GPU), and the per-tree scores come back through one NCCL all-gather -- weak scaling.
+At N > 1 the job is the pooled neighbour-tree list of N such neighbourhoods (base trees seeded
+1001+b): N x 14,762 trees, sharded across the ranks in contiguous blocks (rank r scores block r
+= the neighbours of base tree r; full alignment on every GPU, no data-path collective) and the
+per-tree scores come back through one NCCL all-gather -- weak scaling.  (Splitting ONE
+neighbourhood across ranks is also supported -- shard=(rank, world) in the C-ABI, tested in
+tests/test_neighbourhood_gpu.py -- and is what a single hill-climb would use.)
 
 One JSON line on stdout (rank 0).  Extra objects: "roofline" (dominant kernel, CUDA-event timed
 inside the timed region), "cpu_baseline" (CPU oracle on a bounded sample of the same workload),
@@ -205,7 +208,9 @@ def workload_config(n_gpus):
     return {"workload": "BASELINE configs[1]: synthetic DNA 64 taxa x 10k sites, GTR+G4 lnL (fixed branch lengths) "
                         "of all 14762 distinct SPR neighbours of a random tree",
             "planner": "edge insertion (directional CLVs + 1 CLV update + 1 three-way evaluation per neighbour)",
-            "neighbourhoods_per_step": n_gpus, "sharding": "each neighbourhood split %d ways, scores all-gathered" % n_gpus,
+            "neighbourhoods_per_step": n_gpus,
+            "sharding": "pooled list of %d x 14762 neighbour trees in %d contiguous blocks, scores all-gathered (NCCL)" % (
+                n_gpus, n_gpus),
             "l2": "per-step working set (~19 GB of CLVs) >> 126 MB L2; L2 additionally flushed between steps",
             "seed": SEED}
 
@@ -234,20 +239,16 @@ def run_ours(args):
     aln = likelihood.LikAlignment(codes, w)
     M = nbh.neighbourhood_size(trees[0][0])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(world * world * (M // world + 1), dtype=torch.float64, device=dev) if world > 1 else None
+    gathered = torch.empty(world * M, dtype=torch.float64, device=dev) if world > 1 else None
+
+    my_d, my_br = trees[rank]
 
     def step():
-        outs = []
-        for d, br in trees:
-            _, lnl = nbh.score_likelihood(aln, model, d, br, shard=(rank, world))
-            outs.append(lnl[M * rank // world: M * (rank + 1) // world])
+        _, lnl = nbh.score_likelihood(aln, model, my_d, my_br)
         if world > 1:  # tiny all-gather of the per-tree scores over NCCL
-            mine = torch.zeros(world * (M // world + 1), dtype=torch.float64)
-            cat = np.concatenate(outs)
-            mine[:len(cat)] = torch.from_numpy(cat)
-            dist.all_gather_into_tensor(gathered, mine.to(dev, non_blocking=True))
+            dist.all_gather_into_tensor(gathered, torch.from_numpy(lnl).to(dev, non_blocking=True))
             return gathered
-        return outs[0]
+        return lnl
 
     def barrier():
         if world > 1:

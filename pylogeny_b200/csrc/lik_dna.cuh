@@ -14,7 +14,15 @@
 
 namespace plg {
 
-constexpr int D4_THREADS = 128;
+// Block size / residency chosen by the sweep in profiles/tune_d4.sh (B200, 64 taxa x 10k sites):
+// 128 x {5,6,7} blocks per SM plateau at ~5.1 TB/s algorithmic; 4 blocks (128 registers) gives 4.6.
+#ifndef PLG_D4_THREADS
+#define PLG_D4_THREADS 128
+#endif
+#ifndef PLG_D4_MINB
+#define PLG_D4_MINB 6
+#endif
+constexpr int D4_THREADS = PLG_D4_THREADS;
 
 struct LikOpF {                      // 48 bytes
   int dst, a, b, pa, pb;             // as LikOp
@@ -121,7 +129,7 @@ __device__ __forceinline__ void d4_site_sum(const double (&v)[16], int sc, int64
   }
 }
 
-__global__ void __launch_bounds__(D4_THREADS, 4)
+__global__ void __launch_bounds__(D4_THREADS, PLG_D4_MINB)
 clv4_kernel(const LikOpF *__restrict__ ops, int blocks_per_op, int n_rows, int64_t Ppad,
             const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
             const double *__restrict__ weights, const ModelDev *__restrict__ model,
@@ -168,7 +176,7 @@ clv4_kernel(const LikOpF *__restrict__ ops, int blocks_per_op, int n_rows, int64
   }
 }
 
-__global__ void __launch_bounds__(D4_THREADS, 4)
+__global__ void __launch_bounds__(D4_THREADS, PLG_D4_MINB)
 eval4_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_rows, int64_t Ppad,
              const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
              const double *__restrict__ weights, const ModelDev *__restrict__ model,
