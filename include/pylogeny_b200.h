@@ -97,11 +97,14 @@ int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_tips,
 int plg_neighbourhood_size(int move_type, int n_tips, const int32_t *desc, int64_t *n_moves);
 /* Materialise selected neighbours: out_desc/out_brlen [n_sel][n_tips-1][2], rooted on tip 0's
  * branch (rearrangement.py:267-331); neighbour branch lengths follow rearrangement.py:466-497
- * (target branch halved, the two branches left at the pruned node summed).  out_hash[n_sel]. */
+ * (target branch halved, the two branches left at the pruned node summed).  out_hash[n_sel] =
+ * canonical topology hashes (tips identified by tip_rows, NULL: by id). */
 int plg_neighbourhood_trees(int move_type, int n_tips, const int32_t *desc, const double *brlen,
-                            int64_t n_sel, const int64_t *sel, int32_t *out_desc,
-                            double *out_brlen, uint64_t *out_hash);
-int plg_topology_hash(int n_tips, const int32_t *desc, uint64_t *out);
+                            const int32_t *tip_rows, int64_t n_sel, const int64_t *sel,
+                            int32_t *out_desc, double *out_brlen, uint64_t *out_hash);
+/* Canonical hash of the unrooted topology; tips are identified by tip_rows[id] (NULL: by id), so
+ * the same tree written with its leaves in another order hashes the same. */
+int plg_topology_hash(int n_tips, const int32_t *desc, const int32_t *tip_rows, uint64_t *out);
 
 /* Fitch length of every distinct neighbour in one call, by edge insertion: directional state
  * sets of the base tree once, one partial per search step, one 3-way join per neighbour

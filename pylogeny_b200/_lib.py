@@ -66,8 +66,8 @@ def _declare(L):
     L.plg_lik_score_trees.argtypes = [vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp, vp]
     u64p = C.POINTER(C.c_uint64)
     L.plg_neighbourhood_size.argtypes = [C.c_int, C.c_int, vp, i64p]
-    L.plg_neighbourhood_trees.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int64, vp, vp, vp, vp]
-    L.plg_topology_hash.argtypes = [C.c_int, vp, u64p]
+    L.plg_neighbourhood_trees.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, vp]
+    L.plg_topology_hash.argtypes = [C.c_int, vp, vp, u64p]
     L.plg_fitch_score_neighbourhood.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int64, C.c_int64, i64p, vp, vp, vp]
     L.plg_lik_score_neighbourhood.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, i64p, vp,
                                               vp, vp]

@@ -63,11 +63,11 @@ extern "C" int plg_neighbourhood_size(int move_type, int n_tips, const int32_t *
 }
 
 extern "C" int plg_neighbourhood_trees(int move_type, int n_tips, const int32_t *desc, const double *brlen,
-                                       int64_t n_sel, const int64_t *sel, int32_t *out_desc, double *out_brlen,
-                                       uint64_t *out_hash) {
+                                       const int32_t *tip_rows, int64_t n_sel, const int64_t *sel,
+                                       int32_t *out_desc, double *out_brlen, uint64_t *out_hash) {
   PLG_API_BEGIN
   if (!desc || (n_sel > 0 && !sel)) PLG_FAIL(PLG_ERR_ARG, "null argument");
-  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, brlen), depth_for(move_type));
+  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, brlen, tip_rows), depth_for(move_type));
   const size_t stride = (size_t)(n_tips - 1) * 2;
   for (int64_t i = 0; i < n_sel; i++) {
     if (sel[i] < 0 || sel[i] >= (int64_t)nb.unique.size()) PLG_FAIL(PLG_ERR_ARG, "move index out of range");
@@ -81,10 +81,10 @@ extern "C" int plg_neighbourhood_trees(int move_type, int n_tips, const int32_t 
   PLG_API_END
 }
 
-extern "C" int plg_topology_hash(int n_tips, const int32_t *desc, uint64_t *out) {
+extern "C" int plg_topology_hash(int n_tips, const int32_t *desc, const int32_t *tip_rows, uint64_t *out) {
   PLG_API_BEGIN
   if (!desc || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
-  *out = topology_hash(utree_from_desc(n_tips, desc, nullptr));
+  *out = topology_hash(utree_from_desc(n_tips, desc, nullptr, tip_rows));
   PLG_API_END
 }
 

@@ -78,7 +78,7 @@ std::vector<uint64_t> side_hashes(const UTree &t, const DirOrder &d, uint64_t *a
   std::vector<uint64_t> h((size_t)t.n_nodes * 3, 0);
   uint64_t tot = 0;
   for (int x = 0; x < t.n_tips; x++) {
-    uint64_t key = splitmix((uint64_t)x + 1);
+    uint64_t key = splitmix((uint64_t)(t.tip_label.empty() ? x : t.tip_label[x]) + 1);
     tot ^= key;
     for (int k = 0; k < 3; k++) h[3 * x + k] = key;
   }
@@ -100,7 +100,7 @@ inline uint64_t split_term(uint64_t side, uint64_t all) { return splitmix(std::m
 
 }  // namespace
 
-UTree utree_from_desc(int n_tips, const int32_t *desc, const double *brlen) {
+UTree utree_from_desc(int n_tips, const int32_t *desc, const double *brlen, const int32_t *tip_labels) {
   if (n_tips < 2) PLG_FAIL(PLG_ERR_ARG, "a tree needs at least 2 tips");
   const int n = n_tips, ni = n - 1, root = n + ni - 1;
   std::vector<int> parent(2 * n - 1, -1);
@@ -121,6 +121,8 @@ UTree utree_from_desc(int n_tips, const int32_t *desc, const double *brlen) {
   t.nb.assign(t.n_nodes, {-1, -1, -1});
   t.len.assign(t.n_nodes, {0.0, 0.0, 0.0});
   t.rooted_child_end.assign((size_t)t.n_nodes * 3, -1);
+  t.tip_label.resize(n);
+  for (int x = 0; x < n; x++) t.tip_label[x] = tip_labels ? tip_labels[x] : x;
   auto link = [&](int x, int y, double l, int child_end) {
     for (int pass = 0; pass < 2; pass++) {
       int a = pass ? y : x, b = pass ? x : y;

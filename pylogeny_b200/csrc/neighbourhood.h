@@ -22,6 +22,7 @@ struct UTree {
   std::vector<std::array<int, 3>> nb;      // neighbours, -1 = none
   std::vector<std::array<double, 3>> len;  // branch length to that neighbour
   std::vector<int> rooted_child_end;       // per directed edge 3*x+k: id (rooted desc numbering) naming the edge
+  std::vector<int> tip_label;              // taxon identity of each tip for topology hashing (default: tip id)
   int slot_of(int x, int y) const {
     for (int k = 0; k < 3; k++)
       if (nb[x][k] == y) return k;
@@ -32,7 +33,7 @@ struct UTree {
 
 // Rooted binary descriptor (include/pylogeny_b200.h) -> unrooted tree; the root's two child
 // branches merge into one edge whose length is their sum.
-UTree utree_from_desc(int n_tips, const int32_t *desc, const double *brlen);
+UTree utree_from_desc(int n_tips, const int32_t *desc, const double *brlen, const int32_t *tip_labels = nullptr);
 
 struct Move {
   int u, k;        // pruned: the subtree on nb[u][k]'s side of edge {u, nb[u][k]}; u is suppressed

@@ -28,16 +28,24 @@ def neighbourhood_size(desc, move_type=MOVE_SPR):
     return n.value
 
 
-def topology_hash(desc):
+def _rows(tip_rows):
+    return np.ascontiguousarray(tip_rows, dtype=np.int32) if tip_rows is not None else None
+
+
+def topology_hash(desc, tip_rows=None):
+    """Canonical (rooting- and leaf-order-independent) hash; tips identified by tip_rows[id]."""
     d = _desc(desc)
+    rows = _rows(tip_rows)
     h = C.c_uint64()
-    _lib.check(_lib.lib().plg_topology_hash(d.shape[0] + 1, d.ctypes.data, C.byref(h)))
+    _lib.check(_lib.lib().plg_topology_hash(d.shape[0] + 1, d.ctypes.data,
+                                            rows.ctypes.data if rows is not None else None, C.byref(h)))
     return h.value
 
 
-def neighbour_trees(desc, brlen=None, sel=None, move_type=MOVE_SPR):
+def neighbour_trees(desc, brlen=None, sel=None, move_type=MOVE_SPR, tip_rows=None):
     """Materialise neighbours `sel` (default: all). Returns (descs [m, n-1, 2], brlens or None, hashes [m])."""
     d = _desc(desc)
+    rows = _rows(tip_rows)
     if sel is None:
         sel = np.arange(neighbourhood_size(d, move_type), dtype=np.int64)
     sel = np.ascontiguousarray(sel, dtype=np.int64)
@@ -46,8 +54,8 @@ def neighbour_trees(desc, brlen=None, sel=None, move_type=MOVE_SPR):
     out_b = np.zeros((len(sel),) + d.shape, dtype=np.float64) if b is not None else None
     out_h = np.zeros(len(sel), dtype=np.uint64)
     _lib.check(_lib.lib().plg_neighbourhood_trees(
-        move_type, d.shape[0] + 1, d.ctypes.data, b.ctypes.data if b is not None else None, len(sel),
-        sel.ctypes.data, out_d.ctypes.data, out_b.ctypes.data if out_b is not None else None, out_h.ctypes.data))
+        move_type, d.shape[0] + 1, d.ctypes.data, b.ctypes.data if b is not None else None,
+        rows.ctypes.data if rows is not None else None, len(sel), sel.ctypes.data, out_d.ctypes.data, out_b.ctypes.data if out_b is not None else None, out_h.ctypes.data))
     return out_d, out_b, out_h
 
 

@@ -38,3 +38,12 @@ def test_hash_is_rooting_invariant():
     b = np.array([[2, 3], [1, 4], [0, 5]])
     c = np.array([[0, 2], [1, 3], [4, 5]])
     assert nbh.topology_hash(a) == nbh.topology_hash(b) != nbh.topology_hash(c)
+
+
+def test_hash_identifies_tips_by_row_not_by_position():
+    from pylogeny_b200 import neighbourhood as nbh
+    taxa = {"a": 0, "b": 1, "c": 2, "d": 3, "e": 4}
+    d1, _, r1, _ = nbh.newick_to_desc("((a,b),(c,(d,e)));", taxa)
+    d2, _, r2, _ = nbh.newick_to_desc("(((e,d),c),(b,a));", taxa)
+    d3, _, r3, _ = nbh.newick_to_desc("((a,c),(b,(d,e)));", taxa)
+    assert nbh.topology_hash(d1, r1) == nbh.topology_hash(d2, r2) != nbh.topology_hash(d3, r3)
