@@ -170,3 +170,24 @@ def desc_to_newick(desc, labels, brlen=None):
         parts.sort(key=lambda p: p[0])
         text[n + i] = "(%s)" % ",".join(p[1] for p in parts)
     return text[n + len(desc) - 1] + ";"
+
+
+def parsimony_greedy(aln, desc, tip_rows=None, move_type=MOVE_SPR, max_steps=10000):
+    """Greedy hill-climb by parsimony over the rearrangement landscape, one engine call per step
+    (what heuristic.parsimonyGreedy.explore does through landscape.exploreTree, heuristic.py:65-105:
+    move to the best neighbour while it is strictly better).  Ties: first minimum in the engine's
+    enumeration order.  Returns (path of costs, final descriptor)."""
+    d = _desc(desc)
+    cur = int(aln.score_trees(d[None], tip_rows)[0])
+    path = [cur]
+    for _ in range(max_steps):
+        _, costs = score_parsimony(aln, d, tip_rows, move_type)
+        if len(costs) == 0:
+            break
+        best = int(np.argmin(costs))
+        if int(costs[best]) >= cur:
+            break
+        descs, _, _ = neighbour_trees(d, None, [best], move_type)
+        d, cur = descs[0], int(costs[best])
+        path.append(cur)
+    return path, d

@@ -1,0 +1,85 @@
+"""The BASELINE.json configs as parity cases (sizes from SURVEY.md 8: C1..C5)."""
+import numpy as np
+import pytest
+
+import oracle
+from util import desc_to_newick, random_desc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c1_greedy_climb_al_fasta(al_profiles, al_fitch, al_greedy):
+    """C1 / C3 logic at C1 size: the batched greedy climb reproduces the reference's golden
+    parsimonyGreedy path 1167 -> 1149 -> 1138 -> 1135."""
+    from pylogeny_b200 import fitch, neighbourhood as nbh
+    a = fitch.FitchAlignment(al_profiles["profiles"], al_profiles["weights"])
+    named = {c["name"]: c for c in al_fitch["named"]}
+    d, _, rows, _ = nbh.newick_to_desc(named["caterpillar_file_order"]["newick"], al_profiles["taxa"])
+    path, final = nbh.parsimony_greedy(a, d, rows)
+    assert path == al_greedy["path_scores"] == [1167, 1149, 1138, 1135]
+    assert a.score_trees(final[None], rows)[0] == 1135
+    a.close()
+
+
+def test_c3_greedy_climb_full_size():
+    """C3: 256 taxa x 100k sites, parsimonyGreedy over the SPR landscape.  Size-independent
+    properties: the path is strictly decreasing, every accepted score equals a from-scratch
+    re-traversal of the accepted tree, the end point is a local optimum of its neighbourhood."""
+    from pylogeny_b200 import fitch, neighbourhood as nbh
+    rng = np.random.default_rng(1003)
+    n, S = 256, 100_000
+    # sites evolved on a hidden tree so that the climb has somewhere to go
+    hidden = random_desc(rng, n)
+    states = np.zeros((2 * n - 1, S), dtype=np.uint8)
+    states[2 * n - 2] = rng.integers(0, 4, S)
+    for i in range(n - 2, -1, -1):
+        for c in hidden[i]:
+            mut = rng.random(S) < 0.04
+            states[c] = np.where(mut, rng.integers(0, 4, S), states[n + i])
+    dense = np.ascontiguousarray(states[:n].T + 48).astype(np.uint8)
+    a = fitch.FitchAlignment.from_dense(dense, np.ones(S, dtype=np.int64))
+    start = random_desc(rng, n)
+    path, final = nbh.parsimony_greedy(a, start, max_steps=6)
+    assert len(path) >= 3 and all(x > y for x, y in zip(path, path[1:]))
+    assert int(a.score_trees(final[None])[0]) == path[-1]
+    _, costs = nbh.score_parsimony(a, final)
+    assert len(costs) == 2 * (n - 3) * (2 * n - 7) == 255530
+    # spot-check the engine's neighbour scores at full width against the oracle on a pattern subset
+    sub = 2000
+    a2 = fitch.FitchAlignment.from_dense(dense[:sub], np.ones(sub, dtype=np.int64))
+    _, c2 = nbh.score_parsimony(a2, final)
+    labels = ["T%d" % i for i in range(n)]
+    x = oracle.FitchInputs([bytes(r).decode() for r in dense[:sub]], [1] * sub, {l: i for i, l in enumerate(labels)})
+    sel = np.linspace(0, len(c2) - 1, 12).astype(np.int64)
+    descs, _, _ = nbh.neighbour_trees(final, None, sel)
+    assert [oracle.fitch_cost(desc_to_newick(d, labels), inputs=x) for d in descs] == c2[sel].tolist()
+    a.close(); a2.close()
+
+
+def test_c4_shape_two_trees_full_width():
+    """C4 shape: 128 taxa x 1M sites, GTR+G4 (two random trees instead of 100k).  Properties:
+    additivity over a split of the sites, pulley principle; oracle on a 20k-site slice."""
+    from pylogeny_b200 import likelihood
+    rng = np.random.default_rng(1004)
+    n, S = 128, 1_000_000
+    codes = (1 << rng.integers(0, 4, (n, S))).astype(np.uint8)
+    exch, f = np.array([1.0, 2.0, 0.5, 1.5, 3.0, 1.0]), np.array([0.25, 0.3, 0.2, 0.25])
+    m = likelihood.Model(exch, f, 0.8)
+    descs = np.stack([random_desc(rng, n) for _ in range(2)])
+    brs = rng.exponential(0.1, descs.shape)
+    brs2 = brs.copy()
+    tot = brs[:, -1].sum(1)
+    brs2[:, -1, 0], brs2[:, -1, 1] = 0.9 * tot, 0.1 * tot
+    a = likelihood.LikAlignment(codes, np.ones(S))
+    full = a.score_trees(m, descs, brs)
+    moved = a.score_trees(m, descs, brs2)
+    np.testing.assert_allclose(full, moved, rtol=1e-12)
+    a.close()
+    cut = 20_000
+    lo = likelihood.LikAlignment(codes[:, :cut], np.ones(cut))
+    hi = likelihood.LikAlignment(codes[:, cut:], np.ones(S - cut))
+    part_lo, part_hi = lo.score_trees(m, descs, brs), hi.score_trees(m, descs, brs)
+    np.testing.assert_allclose(part_lo + part_hi, full, rtol=1e-12)
+    want = oracle.lnl(codes[:, :cut], np.ones(cut), exch, f, 0.8, descs[0], brs[0])
+    assert abs(part_lo[0] - want) <= 1e-8 * abs(want)
+    lo.close(); hi.close(); m.close()
