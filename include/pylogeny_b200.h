@@ -91,7 +91,9 @@ int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_tips,
 /* ---- rearrangement neighbourhoods (host side; no device needed) ----
  * Base tree = rooted binary descriptor as above (n_tips-1 internal nodes, ids n_tips+i, root
  * last).  It is read as the unrooted tree it represents (the root's two child branches merge).
- * Every DISTINCT neighbour topology is produced once -- NNI: 2(n-3), SPR: 2(n-3)(2n-7) -- in a
+ * Every DISTINCT neighbour topology is produced once -- NNI: 2(n-3), SPR: 2(n-3)(2n-7), TBR: by
+ * enumeration (textbook bisection/reconnection; the reference only names TBR,
+ * rearrangement.py:27,88-90,661-664) -- in a
  * deterministic order, identified by a canonical topology hash (sum over splits), whereas the
  * reference emits 4(n-3)(n-2) SPR moves with duplicates (rearrangement.py:580-594). */
 int plg_neighbourhood_size(int move_type, int n_tips, const int32_t *desc, int64_t *n_moves);
@@ -110,7 +112,9 @@ int plg_topology_hash(int n_tips, const int32_t *desc, const int32_t *tip_rows, 
  * sets of the base tree once, one partial per search step, one 3-way join per neighbour
  * (exact for binary trees: Fitch length is root-invariant).  *n_moves = total count M.
  * out_moves (may be NULL): int32 [M][4] = (child end of pruned branch, 0 subtree / 1 complement
- * moves, child end of target branch, SPR distance) in base-tree node ids.  out_costs (may be
+ * moves, child end of target branch, SPR distance) in base-tree node ids; for TBR = (bisected
+ * branch, reconnection edge in part 1 or -1 = original attachment, same for part 2, distance).
+ * out_costs (may be
  * NULL): int32 [M]; only the shard [M*i/c, M*(i+1)/c) is written (ranks score disjoint blocks,
  * the host all-gathers).  Replaces the per-neighbour loop landscape.py:724-756. */
 int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, int n_tips,

@@ -26,7 +26,7 @@ struct StageTimer {  // PLG_TIMING=1: host-side stage times on stderr
 int depth_for(int move_type) {
   if (move_type == PLG_MOVE_NNI) return 1;
   if (move_type == PLG_MOVE_SPR) return -1;
-  PLG_FAIL(PLG_ERR_UNSUPPORTED, "move type %d: only NNI (2) and SPR (1) neighbourhoods are built in", move_type);
+  PLG_FAIL(PLG_ERR_UNSUPPORTED, "move type %d: NNI (2), SPR (1) and TBR (3) neighbourhoods are built in", move_type);
 }
 
 void fill_moves(const Neighbourhood &nb, int32_t *out_moves) {
@@ -49,11 +49,98 @@ void shard_range(int64_t M, int64_t idx, int64_t cnt, int64_t *lo, int64_t *hi) 
   *hi = M * (idx + 1) / cnt;
 }
 
+
+void fill_tbr_moves(const TbrNeighbourhood &tb, int32_t *out_moves) {
+  if (!out_moves) return;
+  const UTree &t = tb.t;
+  for (size_t i = 0; i < tb.pairs.size(); i++) {
+    const TbrCand &c1 = tb.cands[tb.pairs[i].c1], &c2 = tb.cands[tb.pairs[i].c2];
+    out_moves[4 * i + 0] = t.rooted_child_end[3 * c1.u + c1.k];                       // bisected branch
+    out_moves[4 * i + 1] = c1.x < 0 ? -1 : t.rooted_child_end[3 * c1.x + c1.kx];      // reconnection edge, part 1
+    out_moves[4 * i + 2] = c2.x < 0 ? -1 : t.rooted_child_end[3 * c2.x + c2.kx];      // reconnection edge, part 2
+    out_moves[4 * i + 3] = c1.depth + c2.depth;
+  }
+}
+
+// edges [e0, e1) whose pairs intersect [lo, hi), cut into chunks that fit `max_slots`
+template <typename Run>
+void for_tbr_chunks(const TbrNeighbourhood &tb, int64_t lo, int64_t hi, int64_t max_slots, Run run) {
+  const int n_edges = (int)tb.edges.size();
+  int e = 0;
+  while (e < n_edges && tb.edge_pair_off[e + 1] <= lo) e++;
+  while (e < n_edges && tb.edge_pair_off[e] < hi) {
+    int e1 = e + 1;
+    while (e1 < n_edges && tb.edge_pair_off[e1] < hi && tbr_slots_needed(tb, e, e1 + 1) <= max_slots) e1++;
+    run(e, e1);
+    e = e1;
+  }
+}
+
+int score_tbr_fitch(FitchAln &a, int n_tips, const int32_t *desc, const int32_t *tip_rows, int64_t shard_index,
+                    int64_t shard_count, int64_t *n_moves, int32_t *out_moves, int32_t *out_costs, cudaStream_t st) {
+  TbrNeighbourhood tb = enumerate_tbr(utree_from_desc(n_tips, desc, nullptr));
+  const int64_t M = (int64_t)tb.pairs.size();
+  *n_moves = M;
+  fill_tbr_moves(tb, out_moves);
+  if (!out_costs || M == 0) return PLG_OK;
+  int64_t lo, hi;
+  shard_range(M, shard_index, shard_count, &lo, &hi);
+  size_t free_b = 0, total_b = 0;
+  PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t vec_bytes = (size_t)a.K * a.words32 * 4;
+  const size_t budget = std::min<size_t>((free_b + fitch_workspace().scratch.n * 4) / 2, (size_t)64 << 30);
+  const int64_t max_slots = std::max<int64_t>(8 * n_tips, (int64_t)(budget / vec_bytes));
+  FitchTbrProgram p;
+  std::vector<int32_t> acc, costs;
+  for_tbr_chunks(tb, lo, hi, max_slots, [&](int e0, int e1) {
+    build_fitch_tbr_program(tb, tip_rows, a.n_cols, e0, e1, p);
+    acc.resize(p.prog.n_costs);
+    run_fitch_program(a, fitch_workspace(), p.prog, acc.data(), st);
+    const int64_t p0 = tb.edge_pair_off[e0], p1 = tb.edge_pair_off[e1];
+    costs.resize(p1 - p0);
+    finish_fitch_tbr(tb, p, acc.data(), e0, e1, costs.data());
+    for (int64_t i = std::max(p0, lo); i < std::min(p1, hi); i++) out_costs[i] = costs[i - p0];
+  });
+  return PLG_OK;
+}
+
+int score_tbr_lik(LikAln &a, const Model &m, int n_tips, const int32_t *desc, const double *brlen,
+                  const int32_t *tip_rows, int64_t shard_index, int64_t shard_count, int64_t *n_moves,
+                  int32_t *out_moves, double *out_lnl, cudaStream_t st) {
+  TbrNeighbourhood tb = enumerate_tbr(utree_from_desc(n_tips, desc, brlen));
+  const int64_t M = (int64_t)tb.pairs.size();
+  *n_moves = M;
+  fill_tbr_moves(tb, out_moves);
+  if (!out_lnl || M == 0) return PLG_OK;
+  int64_t lo, hi;
+  shard_range(M, shard_index, shard_count, &lo, &hi);
+  size_t free_b = 0, total_b = 0;
+  PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t slot_bytes = ((size_t)m.R * a.K * 8 + 4) * a.Ppad;
+  const size_t held = lik_workspace().clv.n * 8 + lik_workspace().scl.n * 4;
+  const size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)80 << 30);
+  const int64_t max_slots = std::max<int64_t>(8 * n_tips, (int64_t)(budget / slot_bytes));
+  LikProgram p;
+  std::vector<double> lnl;
+  for_tbr_chunks(tb, lo, hi, max_slots, [&](int e0, int e1) {
+    build_lik_tbr_program(tb, tip_rows, a.n_rows, e0, e1, p);
+    const int64_t p0 = tb.edge_pair_off[e0], p1 = tb.edge_pair_off[e1];
+    lnl.resize(p1 - p0);
+    run_lik_program(a, m, lik_workspace(), p, lnl.data(), st);
+    for (int64_t i = std::max(p0, lo); i < std::min(p1, hi); i++) out_lnl[i] = lnl[i - p0];
+  });
+  return PLG_OK;
+}
+
 }  // namespace
 
 extern "C" int plg_neighbourhood_size(int move_type, int n_tips, const int32_t *desc, int64_t *n_moves) {
   PLG_API_BEGIN
   if (!desc || !n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  if (move_type == PLG_MOVE_TBR) {  // no closed form: enumerate
+    *n_moves = (int64_t)enumerate_tbr(utree_from_desc(n_tips, desc, nullptr)).pairs.size();
+    return PLG_OK;
+  }
   const int depth = depth_for(move_type);
   utree_from_desc(n_tips, desc, nullptr);  // validates the descriptor
   // closed forms for an unrooted binary tree (checked against the enumeration in the tests)
@@ -67,8 +154,20 @@ extern "C" int plg_neighbourhood_trees(int move_type, int n_tips, const int32_t 
                                        int32_t *out_desc, double *out_brlen, uint64_t *out_hash) {
   PLG_API_BEGIN
   if (!desc || (n_sel > 0 && !sel)) PLG_FAIL(PLG_ERR_ARG, "null argument");
-  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, brlen, tip_rows), depth_for(move_type));
   const size_t stride = (size_t)(n_tips - 1) * 2;
+  if (move_type == PLG_MOVE_TBR) {
+    TbrNeighbourhood tb = enumerate_tbr(utree_from_desc(n_tips, desc, brlen, tip_rows));
+    for (int64_t i = 0; i < n_sel; i++) {
+      if (sel[i] < 0 || sel[i] >= (int64_t)tb.pairs.size()) PLG_FAIL(PLG_ERR_ARG, "move index out of range");
+      if (out_desc) {
+        UTree r = apply_tbr(tb, tb.pairs[sel[i]]);
+        desc_from_utree(r, out_desc + i * stride, out_brlen ? out_brlen + i * stride : nullptr);
+      }
+      if (out_hash) out_hash[i] = tb.pairs[sel[i]].hash;
+    }
+    return PLG_OK;
+  }
+  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, brlen, tip_rows), depth_for(move_type));
   for (int64_t i = 0; i < n_sel; i++) {
     if (sel[i] < 0 || sel[i] >= (int64_t)nb.unique.size()) PLG_FAIL(PLG_ERR_ARG, "move index out of range");
     const Move &m = nb.moves[nb.unique[sel[i]]];
@@ -100,6 +199,9 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
     if (row < 0 || row >= a.n_cols) PLG_FAIL(PLG_ERR_ARG, "tip row %d is outside the alignment", row);
   }
   StageTimer tm;
+  if (move_type == PLG_MOVE_TBR)
+    return score_tbr_fitch(a, n_tips, desc, tip_rows, shard_index, shard_count, n_moves, out_moves, out_costs,
+                           (cudaStream_t)stream);
   Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, nullptr), depth_for(move_type));
   tm.lap("enumerate");
   const int64_t M = (int64_t)nb.unique.size();
@@ -147,6 +249,9 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
     if (row < 0 || row >= a.n_rows) PLG_FAIL(PLG_ERR_ARG, "tip row %d is outside the alignment", row);
   }
   StageTimer tm;
+  if (move_type == PLG_MOVE_TBR)
+    return score_tbr_lik(a, m->impl, n_tips, desc, brlen, tip_rows, shard_index, shard_count, n_moves, out_moves,
+                         out_lnl, (cudaStream_t)stream);
   Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, brlen), depth_for(move_type));
   tm.lap("enumerate");
   const int64_t M = (int64_t)nb.unique.size();

@@ -580,3 +580,346 @@ void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int 
 }
 
 }  // namespace plg
+
+// =============================================================================================
+// TBR
+// =============================================================================================
+namespace plg {
+
+TbrNeighbourhood enumerate_tbr(const UTree &t) {
+  TbrNeighbourhood nb;
+  nb.t = t;
+  DirOrder d = dir_order(t);
+  uint64_t all;
+  std::vector<uint64_t> h = side_hashes(t, d, &all);
+  uint64_t base = 0;
+  for (int x = 0; x < t.n_nodes; x++)
+    for (int k = 0; k < 3; k++)
+      if (t.nb[x][k] > x) base += split_term(h[3 * x + k], all);
+  nb.base_hash = base;
+  nb.edge_cand_off.push_back(0);
+  nb.edge_pair_off.push_back(0);
+  if (t.n_tips < 4) return nb;
+  std::vector<uint64_t> far((size_t)t.n_nodes * 3, 0), term((size_t)t.n_nodes * 3, 0);
+  for (int x = 0; x < t.n_nodes; x++)
+    for (int k = 0; k < 3; k++) {
+      const int y = t.nb[x][k];
+      if (y < 0) continue;
+      far[3 * x + k] = h[3 * y + t.slot_of(y, x)];
+      term[3 * x + k] = split_term(far[3 * x + k], all);
+    }
+  struct Frame { int x, from, parent, depth; uint64_t rem, add; };
+  std::vector<Frame> st;
+  // candidates of the part containing u when edge {u, nb[u][k]} is cut
+  auto side_cands = [&](int u, int k) {
+    TbrCand orig{u, k, -1, -1, 0, -1, 0, 0};
+    nb.cands.push_back(orig);
+    if (t.is_tip(u)) return;
+    const uint64_t hv = far[3 * u + k];  // the other part moves relative to this one
+    for (int side = 0; side < 2; side++) {
+      const int ks = (k + 1 + side) % 3;
+      st.push_back({t.nb[u][ks], u, -1, 0, term[3 * u + ks], 0});
+      while (!st.empty()) {
+        const Frame f = st.back();
+        st.pop_back();
+        if (t.is_tip(f.x)) continue;
+        for (int j = 2; j >= 0; j--) {
+          const int c = t.nb[f.x][j];
+          if (c == f.from) continue;
+          const uint64_t joined = split_term(far[3 * f.x + j] ^ hv, all);
+          TbrCand m{u, k, f.x, j, f.depth + 1, f.parent, side, joined + f.add - f.rem};
+          nb.cands.push_back(m);
+          st.push_back({c, f.x, (int)nb.cands.size() - 1, f.depth + 1, f.rem + term[3 * f.x + j], f.add + joined});
+        }
+      }
+    }
+  };
+  std::unordered_map<uint64_t, int> seen;
+  seen.emplace(base, -1);
+  for (int u = 0; u < t.n_nodes; u++)
+    for (int k = 0; k < 3; k++) {
+      const int v = t.nb[u][k];
+      if (v < u) continue;  // (also skips -1) each undirected edge once, from its smaller end
+      nb.edges.push_back({u, k});
+      side_cands(u, k);
+      nb.edge_cand_off.push_back((int64_t)nb.cands.size());
+      side_cands(v, t.slot_of(v, u));
+      nb.edge_cand_off.push_back((int64_t)nb.cands.size());
+      const size_t ne = nb.edges.size() - 1;
+      for (int64_t c1 = nb.edge_cand_off[2 * ne]; c1 < nb.edge_cand_off[2 * ne + 1]; c1++)
+        for (int64_t c2 = nb.edge_cand_off[2 * ne + 1]; c2 < nb.edge_cand_off[2 * ne + 2]; c2++) {
+          const uint64_t hh = base + nb.cands[c1].delta + nb.cands[c2].delta;
+          if (!seen.emplace(hh, 0).second) continue;
+          nb.pairs.push_back({(int)c1, (int)c2, hh});
+        }
+      nb.edge_pair_off.push_back((int64_t)nb.pairs.size());
+    }
+  return nb;
+}
+
+UTree apply_tbr(const TbrNeighbourhood &nb, const TbrPair &p) {
+  const UTree &t = nb.t;
+  UTree r = t;
+  auto move_side = [&](const TbrCand &c) {
+    if (c.x < 0) return;  // original attachment
+    const int u = c.u, v = t.nb[u][c.k];
+    const int a = t.nb[u][(c.k + 1) % 3], b = t.nb[u][(c.k + 2) % 3];
+    const double la = t.len[u][(c.k + 1) % 3], lb = t.len[u][(c.k + 2) % 3], lv = t.len[u][c.k];
+    const int ka = r.slot_of(a, u), kb = r.slot_of(b, u);
+    r.nb[a][ka] = b; r.len[a][ka] = la + lb;
+    r.nb[b][kb] = a; r.len[b][kb] = la + lb;
+    const int x = c.x, y = t.nb[x][c.kx];
+    const double half = t.len[x][c.kx] / 2.0;
+    const int kx = r.slot_of(x, y), ky = r.slot_of(y, x);
+    r.nb[x][kx] = u; r.len[x][kx] = half;
+    r.nb[y][ky] = u; r.len[y][ky] = half;
+    r.nb[u] = {v, x, y};
+    r.len[u] = {lv, half, half};
+  };
+  move_side(nb.cands[p.c1]);
+  move_side(nb.cands[p.c2]);
+  for (auto &e : r.rooted_child_end) e = -1;
+  return r;
+}
+
+int64_t tbr_slots_needed(const TbrNeighbourhood &nb, int e0, int e1) {
+  return 3 * (int64_t)nb.t.n_nodes + 2 * (nb.edge_cand_off[2 * e1] - nb.edge_cand_off[2 * e0]);
+}
+
+namespace {
+
+// Shared skeleton: walks directional ops, then the candidates of edges [e0,e1) (search-step
+// partial N and rooted vector R per candidate), then the pairs.  The callbacks emit typed ops.
+struct TbrLayout {
+  DirOrder d;
+  std::vector<int> dir_slot;   // operand id of D[x -> .]
+  std::vector<int> n_slot, r_slot;  // per candidate (global index), operand ids
+};
+
+}  // namespace
+
+void build_fitch_tbr_program(const TbrNeighbourhood &nb, const int32_t *tip_rows, int n_tip_slots, int e0, int e1,
+                             FitchTbrProgram &out) {
+  const UTree &t = nb.t;
+  FitchProgram &prog = out.prog;
+  prog.clear();
+  DirOrder d = dir_order(t);
+  out.dir_acc.assign((size_t)t.n_nodes * 3, -1);
+  out.dir_kids.assign((size_t)t.n_nodes * 3, {-1, -1});
+  std::vector<int> dir_slot((size_t)t.n_nodes * 3, -1);
+  for (int x = 0; x < t.n_tips; x++)
+    for (int k = 0; k < 3; k++) dir_slot[3 * x + k] = tip_rows ? tip_rows[x] : x;
+  struct Tmp { FitchOp op; int level; int kids[2]; };
+  std::vector<Tmp> tmp;
+  int64_t slots = 0, accs = 0;
+  for (int e : d.order) {
+    const int x = e / 3, k = e % 3;
+    Tmp o;
+    o.op.dst = n_tip_slots + (int)slots++;
+    o.op.nchild = 2;
+    o.op.tree = (int)accs;
+    out.dir_acc[e] = (int)accs++;
+    int s = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        const int c = t.nb[x][j];
+        const int ce = 3 * c + t.slot_of(c, x);
+        o.kids[s] = dir_slot[ce];
+        out.dir_kids[e][s] = t.is_tip(c) ? -1 : ce;
+        s++;
+      }
+    o.level = d.level[e];
+    dir_slot[e] = o.op.dst;
+    tmp.push_back(o);
+  }
+  const int dump_acc = (int)accs++;
+  out.first_pair_acc = accs;
+  const int64_t c_lo = nb.edge_cand_off[2 * e0], c_hi = nb.edge_cand_off[2 * e1];
+  std::vector<int> n_slot(c_hi - c_lo, -1), r_slot(c_hi - c_lo, -1);
+  int max_depth = 0;
+  for (int64_t ci = c_lo; ci < c_hi; ci++) {
+    const TbrCand &c = nb.cands[ci];
+    if (c.x < 0) {  // rooted on its original attachment: the directional set at u (or the tip itself)
+      r_slot[ci - c_lo] = dir_slot[3 * c.u + c.k];
+      continue;
+    }
+    const int x = c.x, y = t.nb[x][c.kx];
+    int from, xin;
+    if (c.parent < 0) {
+      const int other = t.nb[c.u][(c.k + 1 + (1 - c.side)) % 3];
+      from = c.u;
+      xin = dir_slot[3 * other + t.slot_of(other, c.u)];
+    } else {
+      from = nb.cands[c.parent].x;
+      xin = n_slot[c.parent - c_lo];
+    }
+    int s = -1;
+    for (int j = 0; j < 3; j++)
+      if (t.nb[x][j] != from && t.nb[x][j] != y) s = t.nb[x][j];
+    Tmp o;
+    o.op.dst = n_tip_slots + (int)slots++;
+    o.op.nchild = 2;
+    o.op.tree = dump_acc;
+    o.kids[0] = xin;
+    o.kids[1] = dir_slot[3 * s + t.slot_of(s, x)];
+    o.level = d.max_level + 2 * c.depth - 1;
+    n_slot[ci - c_lo] = o.op.dst;
+    tmp.push_back(o);
+    Tmp q;  // this part rooted in the middle of {x, y}
+    q.op.dst = n_tip_slots + (int)slots++;
+    q.op.nchild = 2;
+    q.op.tree = dump_acc;
+    q.kids[0] = o.op.dst;
+    q.kids[1] = dir_slot[3 * y + t.slot_of(y, x)];
+    q.level = o.level + 1;
+    r_slot[ci - c_lo] = q.op.dst;
+    tmp.push_back(q);
+    max_depth = std::max(max_depth, c.depth);
+  }
+  const int pair_level = d.max_level + 2 * max_depth + 1;
+  const int64_t p_lo = nb.edge_pair_off[e0], p_hi = nb.edge_pair_off[e1];
+  for (int64_t pi = p_lo; pi < p_hi; pi++) {
+    const TbrPair &p = nb.pairs[pi];
+    Tmp o;
+    o.op.dst = -1;
+    o.op.nchild = 2;
+    o.op.tree = (int)(out.first_pair_acc + (pi - p_lo));
+    o.kids[0] = r_slot[p.c1 - c_lo];
+    o.kids[1] = r_slot[p.c2 - c_lo];
+    o.level = pair_level;
+    tmp.push_back(o);
+  }
+  int max_level = 0;
+  for (auto &o : tmp) max_level = std::max(max_level, o.level);
+  prog.level_off.assign(max_level + 2, 0);
+  for (auto &o : tmp) prog.level_off[o.level + 1]++;
+  for (int l = 0; l <= max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+  std::vector<int64_t> cur(prog.level_off.begin(), prog.level_off.end() - 1);
+  prog.ops.resize(tmp.size());
+  prog.children.resize(tmp.size() * 2);
+  for (auto &o : tmp) {
+    const int64_t at = cur[o.level]++;
+    o.op.child_off = (int)(2 * at);
+    prog.children[2 * at] = o.kids[0];
+    prog.children[2 * at + 1] = o.kids[1];
+    prog.ops[at] = o.op;
+  }
+  prog.n_scratch_slots = slots;
+  prog.n_costs = out.first_pair_acc + (p_hi - p_lo);
+}
+
+void finish_fitch_tbr(const TbrNeighbourhood &nb, const FitchTbrProgram &p, const int32_t *acc, int e0, int e1,
+                      int32_t *out_costs) {
+  const UTree &t = nb.t;
+  DirOrder d = dir_order(t);
+  std::vector<uint32_t> total((size_t)t.n_nodes * 3, 0);
+  for (int e : d.order) {
+    uint32_t s = (uint32_t)acc[p.dir_acc[e]];
+    for (int j = 0; j < 2; j++)
+      if (p.dir_kids[e][j] >= 0) s += total[p.dir_kids[e][j]];
+    total[e] = s;
+  }
+  const int64_t p_lo = nb.edge_pair_off[e0];
+  for (int e = e0; e < e1; e++) {
+    const int u = nb.edges[e][0], k = nb.edges[e][1], v = t.nb[u][k];
+    // both parts keep their own Fitch length wherever they are re-rooted (root invariance)
+    const uint32_t parts = (t.is_tip(u) ? 0u : total[3 * u + k]) + (t.is_tip(v) ? 0u : total[3 * v + t.slot_of(v, u)]);
+    for (int64_t pi = nb.edge_pair_off[e]; pi < nb.edge_pair_off[e + 1]; pi++)
+      out_costs[pi - p_lo] = (int32_t)(parts + (uint32_t)acc[p.first_pair_acc + (pi - p_lo)]);
+  }
+}
+
+void build_lik_tbr_program(const TbrNeighbourhood &nb, const int32_t *tip_rows, int n_rows, int e0, int e1,
+                           LikProgram &prog) {
+  const UTree &t = nb.t;
+  prog.clear();
+  DirOrder d = dir_order(t);
+  std::vector<int> dir_slot((size_t)t.n_nodes * 3, -1);
+  for (int x = 0; x < t.n_tips; x++)
+    for (int k = 0; k < 3; k++) dir_slot[3 * x + k] = tip_rows ? tip_rows[x] : x;
+  struct Tmp { LikOp op; int level; };
+  std::vector<Tmp> tmp;
+  int64_t slots = 0;
+  for (int e : d.order) {
+    const int x = e / 3, k = e % 3;
+    Tmp o;
+    o.op.dst = n_rows + (int)slots++;
+    int s = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        const int c = t.nb[x][j];
+        const int id = dir_slot[3 * c + t.slot_of(c, x)];
+        const int pm = prog.pm(t.len[x][j]);
+        if (s == 0) { o.op.a = id; o.op.pa = pm; } else { o.op.b = id; o.op.pb = pm; }
+        s++;
+      }
+    o.level = d.level[e];
+    dir_slot[e] = o.op.dst;
+    tmp.push_back(o);
+  }
+  const int64_t c_lo = nb.edge_cand_off[2 * e0], c_hi = nb.edge_cand_off[2 * e1];
+  std::vector<int> n_slot(c_hi - c_lo, -1), r_slot(c_hi - c_lo, -1);
+  for (int64_t ci = c_lo; ci < c_hi; ci++) {
+    const TbrCand &c = nb.cands[ci];
+    if (c.x < 0) { r_slot[ci - c_lo] = dir_slot[3 * c.u + c.k]; continue; }
+    const int x = c.x, y = t.nb[x][c.kx];
+    int from, xin;
+    double lin;
+    if (c.parent < 0) {
+      const int ko = (c.k + 1 + (1 - c.side)) % 3, ks = (c.k + 1 + c.side) % 3;
+      const int other = t.nb[c.u][ko];
+      from = c.u;
+      xin = dir_slot[3 * other + t.slot_of(other, c.u)];
+      lin = t.len[c.u][ko] + t.len[c.u][ks];
+    } else {
+      const TbrCand &pc = nb.cands[c.parent];
+      from = pc.x;
+      xin = n_slot[c.parent - c_lo];
+      lin = t.len[pc.x][pc.kx];
+    }
+    int s = -1, ks2 = -1;
+    for (int j = 0; j < 3; j++)
+      if (t.nb[x][j] != from && t.nb[x][j] != y) { s = t.nb[x][j]; ks2 = j; }
+    Tmp o;
+    o.op.dst = n_rows + (int)slots++;
+    o.op.a = xin; o.op.pa = prog.pm(lin);
+    o.op.b = dir_slot[3 * s + t.slot_of(s, x)]; o.op.pb = prog.pm(t.len[x][ks2]);
+    o.level = d.max_level + 2 * c.depth - 1;
+    n_slot[ci - c_lo] = o.op.dst;
+    tmp.push_back(o);
+    const double half = t.len[x][c.kx] / 2.0;
+    Tmp q;
+    q.op.dst = n_rows + (int)slots++;
+    q.op.a = o.op.dst; q.op.pa = prog.pm(half);
+    q.op.b = dir_slot[3 * y + t.slot_of(y, x)]; q.op.pb = prog.pm(half);
+    q.level = o.level + 1;
+    r_slot[ci - c_lo] = q.op.dst;
+    tmp.push_back(q);
+  }
+  const int64_t p_lo = nb.edge_pair_off[e0];
+  for (int e = e0; e < e1; e++) {
+    const int u = nb.edges[e][0], k = nb.edges[e][1];
+    const int pmv = prog.pm(t.len[u][k]);  // the reconnecting branch keeps the removed branch's length
+    for (int64_t pi = nb.edge_pair_off[e]; pi < nb.edge_pair_off[e + 1]; pi++) {
+      const TbrPair &p = nb.pairs[pi];
+      LikEval ev;
+      ev.a = r_slot[p.c1 - c_lo]; ev.pa = -1;
+      ev.b = r_slot[p.c2 - c_lo]; ev.pb = pmv;
+      ev.c = -1; ev.pc = -1; ev.pad = 0;
+      ev.tree = (int)(pi - p_lo);
+      prog.evals.push_back(ev);
+    }
+  }
+  int max_level = 0;
+  for (auto &o : tmp) max_level = std::max(max_level, o.level);
+  prog.level_off.assign(max_level + 2, 0);
+  for (auto &o : tmp) prog.level_off[o.level + 1]++;
+  for (int l = 0; l <= max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+  std::vector<int64_t> cur(prog.level_off.begin(), prog.level_off.end() - 1);
+  prog.ops.resize(tmp.size());
+  for (auto &o : tmp) prog.ops[cur[o.level]++] = o.op;
+  prog.n_slots = slots;
+  prog.n_trees = nb.edge_pair_off[e1] - p_lo;
+}
+
+}  // namespace plg

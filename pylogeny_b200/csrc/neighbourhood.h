@@ -80,3 +80,55 @@ void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int 
                           LikProgram &out);
 
 }  // namespace plg
+
+// ---------------------------------------------------------------------------------------------
+// TBR (tree bisection and reconnection).  The reference only names the operator
+// (rearrangement.py:27 TYPE_TBR, :88-90 isTBR; allType raises for it, :661-664), so this is the
+// textbook definition: remove an edge {u,v}, suppress u and v, reconnect any edge of one part
+// with any edge of the other by a new branch (which keeps the removed branch's length; broken
+// edges are halved and suppressed ones summed, the reference's SPR rule, rearrangement.py:466-497).
+// SPR neighbours are the pairs in which one side keeps its original attachment.
+namespace plg {
+
+struct TbrCand {
+  int u, k;       // this side is the part containing u after cutting edge {u, nb[u][k]}
+  int x, kx;      // reconnect in the middle of edge {x, nb[x][kx]}; x < 0: the original attachment
+  int depth, parent, side;
+  uint64_t delta;  // topology hash change caused by this side alone
+};
+
+struct TbrPair {
+  int c1, c2;      // indices into cands (c1 on the smaller-id end's side)
+  uint64_t hash;
+};
+
+struct TbrNeighbourhood {
+  UTree t;
+  std::vector<TbrCand> cands;
+  std::vector<int64_t> edge_cand_off;  // per undirected edge e: cands of side u in [off[2e], off[2e+1]), side v in [off[2e+1], off[2e+2])
+  std::vector<std::array<int, 2>> edges;  // (u, k)
+  std::vector<TbrPair> pairs;             // distinct neighbours, grouped by edge
+  std::vector<int64_t> edge_pair_off;     // [n_edges + 1]
+  uint64_t base_hash = 0;
+};
+
+TbrNeighbourhood enumerate_tbr(const UTree &t);
+UTree apply_tbr(const TbrNeighbourhood &nb, const TbrPair &p);
+
+struct FitchTbrProgram {
+  FitchProgram prog;
+  std::vector<int> dir_acc;
+  std::vector<std::array<int, 2>> dir_kids;
+  int64_t first_pair_acc = 0;
+};
+// Programs over the pairs of edges [e0, e1).
+void build_fitch_tbr_program(const TbrNeighbourhood &nb, const int32_t *tip_rows, int n_tip_slots, int e0, int e1,
+                             FitchTbrProgram &out);
+void finish_fitch_tbr(const TbrNeighbourhood &nb, const FitchTbrProgram &p, const int32_t *acc, int e0, int e1,
+                      int32_t *out_costs);
+void build_lik_tbr_program(const TbrNeighbourhood &nb, const int32_t *tip_rows, int n_rows, int e0, int e1,
+                           LikProgram &out);
+// scratch slots a chunk of edges needs (for memory budgeting)
+int64_t tbr_slots_needed(const TbrNeighbourhood &nb, int e0, int e1);
+
+}  // namespace plg

@@ -47,3 +47,96 @@ def test_hash_identifies_tips_by_row_not_by_position():
     d2, _, r2, _ = nbh.newick_to_desc("(((e,d),c),(b,a));", taxa)
     d3, _, r3, _ = nbh.newick_to_desc("((a,c),(b,(d,e)));", taxa)
     assert nbh.topology_hash(d1, r1) == nbh.topology_hash(d2, r2) != nbh.topology_hash(d3, r3)
+
+
+def _splits(desc, n):
+    """Set of non-trivial splits (frozenset of the side without tip 0) of a rooted descriptor's unrooted tree."""
+    below = {i: frozenset([i]) for i in range(n)}
+    for i, (a, b) in enumerate(desc):
+        below[n + i] = below[int(a)] | below[int(b)]
+    full = frozenset(range(n))
+    out = set()
+    for k, s in below.items():
+        s = s if 0 not in s else full - s
+        if 1 < len(s) < n - 1:
+            out.add(s)
+    return frozenset(out)
+
+
+def _brute_tbr(desc, n):
+    """All TBR neighbours by brute force on split sets: cut every edge, re-root both parts on every
+    edge, join.  Trees as nested tuples over tip ids."""
+    import itertools
+    nodes = {i: i for i in range(n)}
+    adj = {}
+    def link(x, y):
+        adj.setdefault(x, []).append(y); adj.setdefault(y, []).append(x)
+    root = n + len(desc) - 1
+    for i, (a, b) in enumerate(desc[:-1]):
+        link(n + i, int(a)); link(n + i, int(b))
+    link(int(desc[-1][0]), int(desc[-1][1]))
+    edges = [(x, y) for x in adj for y in adj[x] if x < y]
+
+    def component(start, banned):
+        seen, st = {start}, [start]
+        while st:
+            x = st.pop()
+            for y in adj[x]:
+                if (x, y) != banned and (y, x) != banned and y not in seen:
+                    seen.add(y); st.append(y)
+        return seen
+
+    def rooted(x, frm, comp, banned):
+        kids = [y for y in adj[x] if y != frm and y in comp and (x, y) != banned and (y, x) != banned]
+        if not kids:
+            return x
+        subs = [rooted(y, x, comp, banned) for y in kids]
+        return subs[0] if len(subs) == 1 else tuple(subs)
+
+    def rootings(comp, banned):
+        es = [(x, y) for (x, y) in edges if x in comp and y in comp and (x, y) != banned]
+        if not es:
+            return [next(iter(comp))] if len(comp) == 1 else []
+        return [(rooted(x, y, comp, banned), rooted(y, x, comp, banned)) for x, y in es]
+
+    def leafset(t):
+        return frozenset([t]) if not isinstance(t, tuple) else frozenset().union(*[leafset(c) for c in t])
+
+    def splits_of(t, acc):
+        if isinstance(t, tuple):
+            for c in t:
+                splits_of(c, acc)
+            acc.add(leafset(t))
+
+    full = frozenset(range(n))
+    out = set()
+    for e in edges:
+        c1, c2 = component(e[0], e), component(e[1], e)
+        for r1 in rootings(c1, e):
+            for r2 in rootings(c2, e):
+                acc = set()
+                splits_of((r1, r2), acc)
+                canon = frozenset(s if 0 not in s else full - s for s in acc)
+                out.add(frozenset(s for s in canon if 1 < len(s) < n - 1))
+    return out
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 7, 9])
+def test_tbr_enumeration_vs_bruteforce(n):
+    from pylogeny_b200 import neighbourhood as nbh
+    rng = np.random.default_rng(100 + n)
+    d = random_desc(rng, n)
+    brute = _brute_tbr(d, n)
+    brute.discard(_splits(d, n))
+    M = nbh.neighbourhood_size(d, nbh.MOVE_TBR)
+    br = rng.exponential(0.1, d.shape)
+    descs, brs, hashes = nbh.neighbour_trees(d, br, None, nbh.MOVE_TBR)
+    got = {_splits(x, n) for x in descs}
+    assert len(got) == M == len(set(hashes.tolist()))
+    assert got == brute
+    for i in range(M):
+        assert nbh.topology_hash(descs[i]) == int(hashes[i])
+        assert abs(brs[i].sum() - br.sum()) < 1e-12
+    # SPR neighbours are a subset of TBR neighbours
+    sd, _, sh = nbh.neighbour_trees(d, None, None, nbh.MOVE_SPR)
+    assert set(sh.tolist()) <= set(hashes.tolist())

@@ -82,3 +82,28 @@ def test_lnl_edge_insertion_vs_retraversal_and_oracle(n, P):
     _, nni = nbh.score_likelihood(a, m, d, br, move_type=nbh.MOVE_NNI)
     assert len(nni) == 2 * (n - 3)
     a.close(); m.close()
+
+
+@pytest.mark.parametrize("n,P", [(5, 100), (9, 400), (14, 900)])
+def test_tbr_edge_insertion_vs_retraversal(n, P):
+    """TBR: part roots joined pairwise == full re-traversal of the materialised neighbour (Fitch exact, lnL 1e-11)."""
+    from pylogeny_b200 import fitch, likelihood, neighbourhood as nbh
+    rng = np.random.default_rng(31 * n + P)
+    states = random_states(rng, n, P, 4, 0.03)
+    w = np.where(rng.random(P) < 0.3, rng.integers(1, 50, P), 1).astype(np.int64)
+    fa = fitch.FitchAlignment.from_dense(states, w)
+    d = random_desc(rng, n)
+    br = rng.exponential(0.1, d.shape)
+    moves, costs = nbh.score_parsimony(fa, d, None, nbh.MOVE_TBR)
+    descs, brs, _ = nbh.neighbour_trees(d, br, None, nbh.MOVE_TBR)
+    assert len(costs) == len(descs) > 0
+    assert fa.score_trees(descs).tolist() == costs.tolist()
+    codes = (1 << rng.integers(0, 4, (n, P))).astype(np.uint8)
+    la = likelihood.LikAlignment(codes, w.astype(float))
+    m = likelihood.Model(rng.uniform(0.5, 2, 6), rng.dirichlet(np.ones(4) * 5), 0.8)
+    _, lnl = nbh.score_likelihood(la, m, d, br, move_type=nbh.MOVE_TBR)
+    np.testing.assert_allclose(lnl, la.score_trees(m, descs, brs), rtol=1e-11)
+    parts = [nbh.score_likelihood(la, m, d, br, move_type=nbh.MOVE_TBR, shard=(i, 2))[1] for i in range(2)]
+    M = len(lnl)
+    np.testing.assert_array_equal(np.concatenate([parts[0][:M // 2], parts[1][M // 2:]]), lnl)
+    fa.close(); la.close(); m.close()
