@@ -488,6 +488,16 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     }
     if (!fused) rest.push_back(ev);
   }
+  // dead-store elimination: a CLV nobody reads (its only consumer was the evaluation fused into
+  // the op that produces it) stays in registers
+  {
+    std::vector<int> readers(prog.n_slots, 0);
+    auto rd = [&](int id) { if (id >= a.n_rows) readers[id - a.n_rows]++; };
+    for (const LikOpF &f : fops) { rd(f.a); if (f.b >= 0) rd(f.b); if (f.tree >= 0) { rd(f.e_b); rd(f.e_c); } }
+    for (const LikEval &ev : rest) { rd(ev.a); rd(ev.b); if (ev.c >= 0) rd(ev.c); }
+    for (LikOpF &f : fops)
+      if (f.tree >= 0 && readers[f.dst - a.n_rows] == 0) f.pad = 1;
+  }
   ws.fops.alloc(std::max<size_t>(1, (size_t)n_ops * sizeof(LikOpF)));
   if (n_ops)
     PLG_CUDA(cudaMemcpyAsync(ws.fops.p, fops.data(), (size_t)n_ops * sizeof(LikOpF), cudaMemcpyHostToDevice, st));
@@ -505,7 +515,7 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       double bytes = 0;  // algorithmic bytes: C+4 per inner CLV moved, 1 per tip code, 8 per weight
       for (int64_t q = o0 + o; q < o0 + o + c; q++) {
         const LikOpF &f = fops[q];
-        bytes += Cb + opnd(f.a) + opnd(f.b);
+        bytes += (f.pad ? 0.0 : Cb) + opnd(f.a) + opnd(f.b);
         if (f.tree >= 0) bytes += opnd(f.e_b) + opnd(f.e_c) + 8.0;
       }
       prof_begin(PROF_CLV_UPDATE, st);

@@ -28,7 +28,7 @@ struct LikOpF {                      // 48 bytes
   int dst, a, b, pa, pb;             // as LikOp
   int tree;                          // >= 0: fused evaluation writes partial[tree]
   int e_pa, e_b, e_pb, e_c, e_pc;    // evaluation operands: (P[e_pa] N) (P[e_pb] b) (P[e_pc] c)
-  int pad;
+  int pad;                           // 1: do not store dst (no reader)
 };
 
 __device__ __forceinline__ void d4_load16(const double *__restrict__ base, int64_t Ppad, double (&x)[16]) {
@@ -163,10 +163,12 @@ clv4_kernel(const LikOpF *__restrict__ ops, int blocks_per_op, int n_rows, int64
     for (int i = 0; i < 16; i++) v[i] *= TWO256;
     sc += 1;
   }
-  double *dst = clv + (int64_t)(op.dst - n_rows) * 16 * Ppad + p;
+  if (!op.pad) {  // pad = 1: nobody reads this CLV (dead-store elimination on the host)
+    double *dst = clv + (int64_t)(op.dst - n_rows) * 16 * Ppad + p;
 #pragma unroll
-  for (int i = 0; i < 16; i++) dst[(int64_t)i * Ppad] = v[i];
-  scl[(int64_t)(op.dst - n_rows) * Ppad + p] = sc;
+    for (int i = 0; i < 16; i++) dst[(int64_t)i * Ppad] = v[i];
+    scl[(int64_t)(op.dst - n_rows) * Ppad + p] = sc;
+  }
   if (op.tree >= 0) {
     double e[16];
     d4_apply<false>(smE, v, e);

@@ -450,7 +450,9 @@ void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, in
       const int64_t at = c[m.depth]++;
       const int64_t koff = 2 * n_dir + 4 * (at - n_dir);
       FitchOp o;
-      o.dst = slot_of_move(i);
+      // a step onto a pendant edge has no further steps below it: its partial is only consumed
+      // by its own fused join, so it is never stored
+      o.dst = t.is_tip(cnode) ? -1 : slot_of_move(i);
       o.child_off = (int)koff;
       kids[koff] = xin;
       kids[koff + 1] = dir_slot[3 * s + t.slot_of(s, x)];
@@ -465,6 +467,7 @@ void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, in
         o.nchild = 2;
         o.tree = dump_acc;
         kids[koff + 2] = kids[koff + 3] = 0;
+        if (o.dst < 0) o.nchild = 1;  // duplicate topology on a pendant edge: nothing to do (unary, no store)
       }
       ops[at] = o;
     }
