@@ -180,20 +180,41 @@ Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
       term[3 * x + k] = split_term(far[3 * x + k], all);
     }
   struct Frame { int x, from, parent_move, depth; uint64_t rem, add; };
-  // independent searches per pruned subtree, spread over the host cores
+  if (max_depth > 1) PLG_FAIL(PLG_ERR_UNSUPPORTED, "search depth limits other than 1 are not supported");
+  // Number of search steps of every (pruned subtree, side): all edges beyond `start` seen from u,
+  // i.e. 2*leaves-2 of that side (depth-limited: 2 if start is internal).  Prefix sums give every
+  // search its slice of the move array, so the host cores fill it in place.
+  std::vector<int> leaves((size_t)t.n_nodes * 3, 0);  // leaves on x's side of edge x -> nb[x][k]
+  for (int x = 0; x < t.n_tips; x++) leaves[3 * x] = leaves[3 * x + 1] = leaves[3 * x + 2] = 1;
+  for (int e : d.order) {
+    const int x = e / 3, k = e % 3;
+    int c = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) c += leaves[3 * t.nb[x][j] + t.slot_of(t.nb[x][j], x)];
+    leaves[e] = c;
+  }
   const int n_int = t.n_nodes - t.n_tips;
+  std::vector<int64_t> off((size_t)n_int * 6 + 1, 0);
+  for (int u = t.n_tips; u < t.n_nodes; u++)
+    for (int k = 0; k < 3; k++)
+      for (int side = 0; side < 2; side++) {
+        const int ks = (k + 1 + side) % 3, start = t.nb[u][ks];
+        int64_t cnt = 0;
+        if (!t.is_tip(start)) cnt = (max_depth == 1) ? 2 : 2 * (int64_t)leaves[3 * start + t.slot_of(start, u)] - 2;
+        off[(size_t)(u - t.n_tips) * 6 + k * 2 + side + 1] = cnt;
+      }
+  for (size_t i = 0; i + 1 < off.size(); i++) off[i + 1] += off[i];
+  nb.moves.resize(off.back());
   const int n_thr = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, n_int / 8)));
-  std::vector<std::vector<Move>> part(n_thr);
   auto work = [&](int ti) {
-    std::vector<Move> &out = part[ti];
     std::vector<Frame> st;
     const int u0 = t.n_tips + (int)((int64_t)n_int * ti / n_thr), u1 = t.n_tips + (int)((int64_t)n_int * (ti + 1) / n_thr);
-    out.reserve((size_t)(u1 - u0) * 6 * t.n_tips);
     for (int u = u0; u < u1; u++)
       for (int k = 0; k < 3; k++) {
         const uint64_t hv = far[3 * u + k];
         for (int side = 0; side < 2; side++) {
           const int ks = (k + 1 + side) % 3;
+          int64_t at = off[(size_t)(u - t.n_tips) * 6 + k * 2 + side];
           st.push_back({t.nb[u][ks], u, -1, 0, term[3 * u + ks], 0});
           while (!st.empty()) {
             const Frame f = st.back();
@@ -209,8 +230,9 @@ Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
               m.side = side;
               m.hash = base - f.rem + f.add + joined;
               m.unique_id = -1;
-              out.push_back(m);
-              st.push_back({c, f.x, (int)out.size() - 1, f.depth + 1, f.rem + term[3 * f.x + j], f.add + joined});
+              nb.moves[at] = m;
+              st.push_back({c, f.x, (int)at, f.depth + 1, f.rem + term[3 * f.x + j], f.add + joined});
+              at++;
             }
           }
         }
@@ -221,17 +243,6 @@ Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
     std::vector<std::thread> th;
     for (int i = 0; i < n_thr; i++) th.emplace_back(work, i);
     for (auto &x : th) x.join();
-  }
-  size_t total = 0;
-  for (auto &p : part) total += p.size();
-  nb.moves.reserve(total);
-  for (auto &p : part) {
-    const int off = (int)nb.moves.size();
-    for (Move m : p) {
-      if (m.parent >= 0) m.parent += off;
-      nb.moves.push_back(m);
-    }
-    std::vector<Move>().swap(p);
   }
   // Distinct topologies.  Only moves at distance 1 (NNI) repeat: each NNI neighbour arises from
   // 4 of the 8(n-3) distance-1 (prune, target) pairs, which accounts for all of
@@ -488,14 +499,21 @@ void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int
       if (p.dir_kids[e][j] >= 0) s += total[p.dir_kids[e][j]];
     total[e] = s;
   }
-  for (int64_t i = lo; i < hi; i++) {
-    const Move &m = nb.moves[nb.unique[i]];
-    const int v = t.nb[m.u][m.k];
-    // length(T') = length(pruned subtree) + length(rest) + [their state sets miss at the new edge]
-    uint32_t c = total[3 * m.u + m.k] + (t.is_tip(v) ? 0u : total[3 * v + t.slot_of(v, m.u)]) +
-                 (uint32_t)acc[p.first_move_acc + (i - lo)];
-    out_costs[i - lo] = (int32_t)c;
-  }
+  // length(T') = length(pruned subtree) + length(rest) + [their state sets miss at the new edge];
+  // the first two only depend on the pruned branch
+  std::vector<uint32_t> parts((size_t)t.n_nodes * 3, 0);
+  for (int u = t.n_tips; u < t.n_nodes; u++)
+    for (int k = 0; k < 3; k++) {
+      const int v = t.nb[u][k];
+      parts[3 * u + k] = total[3 * u + k] + (t.is_tip(v) ? 0u : total[3 * v + t.slot_of(v, u)]);
+    }
+  const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(std::thread::hardware_concurrency(), (hi - lo) / 16384));
+  parallel_for_threads(n_thr, [&](int ti, int nt) {
+    for (int64_t i = lo + (hi - lo) * ti / nt; i < lo + (hi - lo) * (ti + 1) / nt; i++) {
+      const Move &m = nb.moves[nb.unique[i]];
+      out_costs[i - lo] = (int32_t)(parts[3 * m.u + m.k] + (uint32_t)acc[p.first_move_acc + (i - lo)]);
+    }
+  });
 }
 
 void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
