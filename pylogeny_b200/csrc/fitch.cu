@@ -60,8 +60,11 @@ __device__ __forceinline__ void store_vec(unsigned int *p, const unsigned int (&
 }
 
 // words32: 32-bit words per plane (= 4*W4).  cols_per_op = words32 / VW.
+#ifndef PLG_FITCH_MINB
+#define PLG_FITCH_MINB 4  // residency sweep in profiles/tune_fitch.sh: 4 is best (6.8 ms vs 8.0 for C3)
+#endif
 template <int K, int VW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PLG_FITCH_MINB)
 fitch_level_kernel(const unsigned int *__restrict__ tips, unsigned int *__restrict__ scratch,
                    int n_tip_slots, const FitchOp *__restrict__ ops,
                    const int *__restrict__ children, int64_t words32, int blocks_per_op,
