@@ -1,0 +1,29 @@
+"""Small end-to-end pass over every kernel family for compute-sanitizer (memcheck)."""
+import sys
+import numpy as np
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+from util import random_desc, random_states
+from pylogeny_b200 import _lib, fitch, likelihood, neighbourhood as nbh
+rng = np.random.default_rng(0)
+n, P = 9, 333
+st = random_states(rng, n, P, 5, 0.05)
+w = rng.integers(1, 9, P).astype(np.int64)
+fa = fitch.FitchAlignment.from_dense(st, w)
+d = random_desc(rng, n); br = rng.exponential(0.1, d.shape)
+print("fitch trees", fa.score_trees(np.stack([d, d])))
+for mt in (nbh.MOVE_NNI, nbh.MOVE_SPR, nbh.MOVE_TBR):
+    print("fitch nb", mt, nbh.score_parsimony(fa, d, None, mt)[1].sum())
+print("kary", fa.score_newicks(["((T0,T1,T2),(T3,T4),T5,(T6,(T7,T8)));"], {"T%d" % i: i for i in range(n)}))
+codes = rng.integers(1, 16, (n, P)).astype(np.uint8)
+la = likelihood.LikAlignment(codes, w.astype(float))
+m = likelihood.Model(rng.uniform(0.5, 2, 6), rng.dirichlet(np.ones(4) * 5), 0.8)
+print("lnl trees", la.score_trees(m, d, br))
+for mt in (nbh.MOVE_NNI, nbh.MOVE_SPR, nbh.MOVE_TBR):
+    print("lnl nb", mt, nbh.score_likelihood(la, m, d, br, move_type=mt)[1].sum())
+aa = rng.integers(0, 23, (n, P)).astype(np.uint8)
+pa = likelihood.LikAlignment(aa, w.astype(float), _lib.DATA_AA)
+pm = likelihood.Model(rng.uniform(0.1, 3, 190), rng.dirichlet(np.ones(20) * 5), 1.1)
+print("aa trees", pa.score_trees(pm, d, br), "aa spr", nbh.score_likelihood(pa, pm, d, br)[1].sum())
+m1 = likelihood.Model(rng.uniform(0.5, 2, 6), rng.dirichlet(np.ones(4) * 5), 1.0, 1)
+print("r1", la.score_trees(m1, d, br))
+print("sanitize pass done")

@@ -239,6 +239,7 @@ __global__ void reduce_partials_kernel(int n_trees, int blocks_per_eval, const d
 
 }  // namespace plg
 #include "lik_dna.cuh"
+#include "lik_aa.cuh"
 namespace plg {
 
 // ----------------------------------------------------------------------------
@@ -546,6 +547,60 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   }
 }
 
+// 20 states x Gamma-4 path: DMMA kernels (lik_aa.cuh).  Tips enter the tensor-core product as
+// indicator columns, so only the P-matrices are needed (the tip tables are still produced by
+// pmatrix_kernel for the generic path).
+static void run_aa20(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, cudaStream_t st) {
+  constexpr int K = 20, R = 4, KKP = 401, NC = 23;
+  const int n_pm = (int)prog.brlens.size();
+  ws.pmat.alloc(std::max<size_t>(1, (size_t)n_pm * R * KKP));
+  ws.tiptab.alloc(std::max<size_t>(1, (size_t)n_pm * NC * R * K));
+  ws.brlen.alloc(std::max<size_t>(1, n_pm));
+  if (n_pm) {
+    PLG_CUDA(cudaMemcpyAsync(ws.brlen.p, prog.brlens.data(), (size_t)n_pm * 8, cudaMemcpyHostToDevice, st));
+    prof_begin(PROF_PMATRIX, st);
+    pmatrix_kernel<K, R><<<n_pm, 128, 0, st>>>(m.d.p, ws.brlen.p, a.masks.p, ws.pmat.p, ws.tiptab.p);
+    count_launch();
+    prof_end(PROF_PMATRIX, st, (double)n_pm * (R * KKP + NC * R * K) * 8.0, n_pm);
+  }
+  const int64_t bpo = a.Ppad / A20_TILE;
+  const double Cb = (double)R * K * 8.0 + 4.0;
+  auto opnd = [&](int id) { return id < 0 ? 0.0 : (id < a.n_rows ? 1.0 : Cb); };
+  for (size_t l = 0; l + 1 < prog.level_off.size(); l++) {
+    const int64_t o0 = prog.level_off[l], cnt = prog.level_off[l + 1] - o0;
+    const int64_t max_ops = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
+    for (int64_t o = 0; o < cnt; o += max_ops) {
+      const int64_t c = std::min(max_ops, cnt - o);
+      double bytes = 0;
+      for (int64_t q = o0 + o; q < o0 + o + c; q++) bytes += Cb + opnd(prog.ops[q].a) + opnd(prog.ops[q].b);
+      prof_begin(PROF_CLV_UPDATE, st);
+      clv20_kernel<<<(unsigned)(c * bpo), A20_THREADS, 0, st>>>(ws.ops.p + o0 + o, (int)bpo, a.n_rows, a.Ppad,
+                                                               a.codes.p, a.masks.p, ws.pmat.p, ws.clv.p, ws.scl.p);
+      count_launch();
+      prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, (double)c * (double)a.P);
+    }
+  }
+  const int64_t n_ev = (int64_t)prog.evals.size();
+  const int64_t max_ev = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
+  for (int64_t e = 0; e < n_ev; e += max_ev) {
+    const int64_t c = std::min(max_ev, n_ev - e);
+    double bytes = 0;
+    for (int64_t q = e; q < e + c; q++)
+      bytes += 8.0 + opnd(prog.evals[q].a) + opnd(prog.evals[q].b) + opnd(prog.evals[q].c);
+    prof_begin(PROF_ROOT_EVAL, st);
+    eval20_kernel<<<(unsigned)(c * bpo), A20_THREADS, 0, st>>>(ws.evals.p + e, (int)bpo, a.n_rows, a.Ppad, a.codes.p,
+                                                              a.masks.p, a.weights.p, m.d.p, ws.pmat.p, ws.clv.p,
+                                                              ws.scl.p, ws.partial.p);
+    count_launch();
+    prof_end(PROF_ROOT_EVAL, st, bytes * (double)a.P, (double)c * (double)a.P);
+  }
+  if (prog.n_trees) {
+    reduce_partials_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, (int)bpo,
+                                                                               ws.partial.p, ws.lnl.p);
+    count_launch();
+  }
+}
+
 void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, double *out_lnl,
                      cudaStream_t st) {
   if (m.K != a.K) PLG_FAIL(PLG_ERR_ARG, "model has %d states but the alignment has %d", m.K, a.K);
@@ -566,7 +621,7 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   PLG_CUDA(cudaMemsetAsync(ws.lnl.p, 0, std::max<size_t>(1, (size_t)prog.n_trees) * 8, st));
   if (dna4) run_dna4(a, m, ws, prog, st);
   else if (a.K == 4 && m.R == 1) run_typed<4, 1>(a, m, ws, prog, st);
-  else if (a.K == 20 && m.R == 4) run_typed<20, 4>(a, m, ws, prog, st);
+  else if (a.K == 20 && m.R == 4) run_aa20(a, m, ws, prog, st);
   else if (a.K == 20 && m.R == 1) run_typed<20, 1>(a, m, ws, prog, st);
   else PLG_FAIL(PLG_ERR_UNSUPPORTED, "kernels exist for 4 or 20 states with 1 or 4 rate categories");
   PLG_CUDA(cudaGetLastError());

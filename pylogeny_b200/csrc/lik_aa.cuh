@@ -1,0 +1,240 @@
+// 20-state x Gamma-4 specialisation of the likelihood kernels on the FP64 tensor cores.
+//
+// For amino-acid data the per-category product V_r = P_r (20x20) * X_r (20 x patterns) IS a dense
+// contraction with the same P_r for every pattern, so it maps onto mma.sync.m8n8k4.f64 (DMMA):
+// the P_r fragments live in registers for the whole tile, X_r streams through as the B operand.
+// (tcgen05 has no FP64 kind; DMMA is the FP64 tensor path on sm_100a.)  The generic
+// (pattern, category)-per-thread kernels of lik.cu need one shared-memory load per FMA and
+// measured 1.7 TB/s algorithmic / ~7 TFLOP/s (profiles/r1_aa_before.txt); these replace them for
+// K = 20, R = 4.
+//
+// Block = 4 warps = the 4 rate categories of a 64-pattern tile.  Fragment layouts (PTX ISA,
+// m8n8k4 .f64): A a0 = A[lane>>2][lane&3]; B b0 = B[lane&3][lane>>2]; C c0,c1 = C[lane>>2][2*(lane&3)+{0,1}].
+// States are padded 20 -> 24 rows (three m-tiles); K = 20 = five k-steps.
+#pragma once
+
+namespace plg {
+
+constexpr int A20_TILE = 64;     // patterns per block
+constexpr int A20_THREADS = 128;  // 4 warps = 4 rate categories
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// A fragments of P[pm][r] (global layout [r][401], row-major 20x20 inside)
+__device__ __forceinline__ void a20_load_p(const double *__restrict__ pmat, int pm, int r, int lane, double (&a)[3][5]) {
+  const double *P = pmat + ((int64_t)pm * 4 + r) * 401;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 3; mt++) {
+    const int row = mt * 8 + g;
+#pragma unroll
+    for (int ks = 0; ks < 5; ks++) a[mt][ks] = row < 20 ? __ldg(P + row * 20 + ks * 4 + t) : 0.0;
+  }
+}
+
+// c[mt] (+)= P_r * X_r for the 8 patterns starting at p0; tips enter as 0/1 indicator columns
+__device__ __forceinline__ void a20_apply(const double (&a)[3][5], int id, int n_rows, int r, int64_t p0, int lane,
+                                          int64_t Ppad, const unsigned char *__restrict__ codes,
+                                          const unsigned int *__restrict__ masks, const double *__restrict__ clv,
+                                          double (&c)[3][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 3; mt++) c[mt][0] = c[mt][1] = 0.0;
+  if (id < n_rows) {
+    const unsigned int m = masks[codes[(int64_t)id * Ppad + p0 + g]];
+#pragma unroll
+    for (int ks = 0; ks < 5; ks++) {
+      const double b = (m >> (ks * 4 + t) & 1) ? 1.0 : 0.0;
+#pragma unroll
+      for (int mt = 0; mt < 3; mt++) dmma884(c[mt], a[mt][ks], b);
+    }
+  } else {
+    const double *src = clv + ((int64_t)(id - n_rows) * 80 + r * 20 + t) * Ppad + p0 + g;
+    double b[5];
+#pragma unroll
+    for (int ks = 0; ks < 5; ks++) b[ks] = __ldg(src + (int64_t)ks * 4 * Ppad);
+#pragma unroll
+    for (int ks = 0; ks < 5; ks++)
+#pragma unroll
+      for (int mt = 0; mt < 3; mt++) dmma884(c[mt], a[mt][ks], b[ks]);
+  }
+}
+
+// an operand that sits at the node itself (no P): its values directly in C-fragment layout
+__device__ __forceinline__ void a20_raw(int id, int n_rows, int r, int64_t p0, int lane, int64_t Ppad,
+                                        const unsigned char *__restrict__ codes,
+                                        const unsigned int *__restrict__ masks, const double *__restrict__ clv,
+                                        double (&c)[3][2]) {
+  const int g = lane >> 2, t = lane & 3;
+  if (id < n_rows) {
+    const unsigned int m0 = masks[codes[(int64_t)id * Ppad + p0 + 2 * t]];
+    const unsigned int m1 = masks[codes[(int64_t)id * Ppad + p0 + 2 * t + 1]];
+#pragma unroll
+    for (int mt = 0; mt < 3; mt++) {
+      const int row = mt * 8 + g;
+      c[mt][0] = (row < 20 && (m0 >> row & 1)) ? 1.0 : 0.0;
+      c[mt][1] = (row < 20 && (m1 >> row & 1)) ? 1.0 : 0.0;
+    }
+  } else {
+#pragma unroll
+    for (int mt = 0; mt < 3; mt++) {
+      const int row = mt * 8 + g;
+      if (row < 20) {
+        const double2 v = *reinterpret_cast<const double2 *>(clv + ((int64_t)(id - n_rows) * 80 + r * 20 + row) * Ppad + p0 + 2 * t);
+        c[mt][0] = v.x; c[mt][1] = v.y;
+      } else {
+        c[mt][0] = c[mt][1] = 0.0;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(A20_THREADS)
+clv20_kernel(const LikOp *__restrict__ ops, int blocks_per_op, int n_rows, int64_t Ppad,
+             const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
+             const double *__restrict__ pmat, double *__restrict__ clv, int *__restrict__ scl) {
+  __shared__ double smax[4][A20_TILE];
+  __shared__ int srescale[A20_TILE];
+  const int op_idx = blockIdx.x / blocks_per_op;
+  const int pb = blockIdx.x - op_idx * blocks_per_op;
+  const LikOp op = ops[op_idx];
+  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int64_t pbase = (int64_t)pb * A20_TILE;
+  double pa[3][5], pbm[3][5];
+  a20_load_p(pmat, op.pa, r, lane, pa);
+  if (op.b >= 0) a20_load_p(pmat, op.pb, r, lane, pbm);
+  double *dst = clv + ((int64_t)(op.dst - n_rows) * 80 + r * 20) * Ppad;
+#pragma unroll 1
+  for (int nt = 0; nt < A20_TILE / 8; nt++) {
+    const int64_t p0 = pbase + nt * 8;
+    double ca[3][2], cb[3][2];
+    a20_apply(pa, op.a, n_rows, r, p0, lane, Ppad, codes, masks, clv, ca);
+    if (op.b >= 0) {
+      a20_apply(pbm, op.b, n_rows, r, p0, lane, Ppad, codes, masks, clv, cb);
+#pragma unroll
+      for (int mt = 0; mt < 3; mt++) { ca[mt][0] *= cb[mt][0]; ca[mt][1] *= cb[mt][1]; }
+    }
+    double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+    for (int mt = 0; mt < 3; mt++) {
+      const int row = mt * 8 + g;
+      if (row < 20) {
+        *reinterpret_cast<double2 *>(dst + (int64_t)row * Ppad + p0 + 2 * t) = make_double2(ca[mt][0], ca[mt][1]);
+        m0 = fmax(m0, fabs(ca[mt][0]));
+        m1 = fmax(m1, fabs(ca[mt][1]));
+      }
+    }
+#pragma unroll
+    for (int d = 4; d < 32; d <<= 1) {
+      m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, d));
+      m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, d));
+    }
+    if (g == 0) { smax[r][nt * 8 + 2 * t] = m0; smax[r][nt * 8 + 2 * t + 1] = m1; }
+  }
+  __syncthreads();
+  int any = 0;
+  if (threadIdx.x < A20_TILE) {
+    const int q = threadIdx.x;
+    const double mx = fmax(fmax(smax[0][q], smax[1][q]), fmax(smax[2][q], smax[3][q]));
+    const int res = mx < MINLH ? 1 : 0;  // every one of the 80 entries below 2^-256
+    srescale[q] = res;
+    any = res;
+    int sc = res;
+    if (op.a >= n_rows) sc += scl[(int64_t)(op.a - n_rows) * Ppad + pbase + q];
+    if (op.b >= n_rows) sc += scl[(int64_t)(op.b - n_rows) * Ppad + pbase + q];
+    scl[(int64_t)(op.dst - n_rows) * Ppad + pbase + q] = sc;
+  }
+  if (__syncthreads_or(any)) {  // rare: multiply the columns just written by 2^256 (each thread its own stores)
+    for (int nt = 0; nt < A20_TILE / 8; nt++) {
+      const int q = nt * 8 + 2 * t;
+      if (!srescale[q] && !srescale[q + 1]) continue;
+#pragma unroll
+      for (int mt = 0; mt < 3; mt++) {
+        const int row = mt * 8 + g;
+        if (row < 20) {
+          double2 *ptr = reinterpret_cast<double2 *>(dst + (int64_t)row * Ppad + pbase + q);
+          double2 v = *ptr;
+          if (srescale[q]) v.x *= TWO256;
+          if (srescale[q + 1]) v.y *= TWO256;
+          *ptr = v;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(A20_THREADS)
+eval20_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_rows, int64_t Ppad,
+              const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
+              const double *__restrict__ weights, const ModelDev *__restrict__ model,
+              const double *__restrict__ pmat, const double *__restrict__ clv, const int *__restrict__ scl,
+              double *__restrict__ partial) {
+  __shared__ double sterm[4][A20_TILE];
+  __shared__ double wsum[2];
+  const int ev_idx = blockIdx.x / blocks_per_eval;
+  const int pb = blockIdx.x - ev_idx * blocks_per_eval;
+  const LikEval ev = evals[ev_idx];
+  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int64_t pbase = (int64_t)pb * A20_TILE;
+  double pa[3][5], pbm[3][5], pc[3][5];
+  if (ev.pa >= 0) a20_load_p(pmat, ev.pa, r, lane, pa);
+  if (ev.pb >= 0) a20_load_p(pmat, ev.pb, r, lane, pbm);
+  if (ev.c >= 0 && ev.pc >= 0) a20_load_p(pmat, ev.pc, r, lane, pc);
+  double fr[3];
+#pragma unroll
+  for (int mt = 0; mt < 3; mt++) fr[mt] = (mt * 8 + g) < 20 ? model->freqs[mt * 8 + g] : 0.0;
+#pragma unroll 1
+  for (int nt = 0; nt < A20_TILE / 8; nt++) {
+    const int64_t p0 = pbase + nt * 8;
+    double v[3][2], x[3][2];
+    if (ev.pa >= 0) a20_apply(pa, ev.a, n_rows, r, p0, lane, Ppad, codes, masks, clv, v);
+    else a20_raw(ev.a, n_rows, r, p0, lane, Ppad, codes, masks, clv, v);
+    if (ev.pb >= 0) a20_apply(pbm, ev.b, n_rows, r, p0, lane, Ppad, codes, masks, clv, x);
+    else a20_raw(ev.b, n_rows, r, p0, lane, Ppad, codes, masks, clv, x);
+#pragma unroll
+    for (int mt = 0; mt < 3; mt++) { v[mt][0] *= x[mt][0]; v[mt][1] *= x[mt][1]; }
+    if (ev.c >= 0) {
+      if (ev.pc >= 0) a20_apply(pc, ev.c, n_rows, r, p0, lane, Ppad, codes, masks, clv, x);
+      else a20_raw(ev.c, n_rows, r, p0, lane, Ppad, codes, masks, clv, x);
+#pragma unroll
+      for (int mt = 0; mt < 3; mt++) { v[mt][0] *= x[mt][0]; v[mt][1] *= x[mt][1]; }
+    }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int mt = 0; mt < 3; mt++) { s0 = fma(fr[mt], v[mt][0], s0); s1 = fma(fr[mt], v[mt][1], s1); }
+#pragma unroll
+    for (int d = 4; d < 32; d <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    }
+    if (g == 0) { sterm[r][nt * 8 + 2 * t] = s0; sterm[r][nt * 8 + 2 * t + 1] = s1; }
+  }
+  __syncthreads();
+  double val = 0.0;
+  if (threadIdx.x < A20_TILE) {
+    const int q = threadIdx.x;
+    const int64_t p = pbase + q;
+    const double w = weights[p];
+    if (w != 0.0) {
+      const double term = (sterm[0][q] + sterm[1][q]) + (sterm[2][q] + sterm[3][q]);
+      int sc = 0;
+      if (ev.a >= n_rows) sc += scl[(int64_t)(ev.a - n_rows) * Ppad + p];
+      if (ev.b >= n_rows) sc += scl[(int64_t)(ev.b - n_rows) * Ppad + p];
+      if (ev.c >= n_rows) sc += scl[(int64_t)(ev.c - n_rows) * Ppad + p];
+      val = w * (log(term * 0.25) + sc * log(MINLH));
+    }
+  }
+  if (threadIdx.x < A20_TILE) {  // warps 0 and 1 hold the 64 site values: fixed-order reduction
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
+    if (lane == 0) wsum[r] = val;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) partial[(int64_t)ev.tree * blocks_per_eval + pb] = wsum[0] + wsum[1];
+}
+
+}  // namespace plg
