@@ -15,6 +15,10 @@
 
 namespace plg {
 
+#ifndef PLG_A20_UNROLL
+#define PLG_A20_UNROLL 1
+#endif
+constexpr int A20_UNROLL = PLG_A20_UNROLL;
 constexpr int A20_TILE = 64;     // patterns per block
 constexpr int A20_THREADS = 128;  // 4 warps = 4 rate categories
 
@@ -108,7 +112,7 @@ clv20_kernel(const LikOp *__restrict__ ops, int blocks_per_op, int n_rows, int64
   a20_load_p(pmat, op.pa, r, lane, pa);
   if (op.b >= 0) a20_load_p(pmat, op.pb, r, lane, pbm);
   double *dst = clv + ((int64_t)(op.dst - n_rows) * 80 + r * 20) * Ppad;
-#pragma unroll 1
+#pragma unroll(A20_UNROLL)
   for (int nt = 0; nt < A20_TILE / 8; nt++) {
     const int64_t p0 = pbase + nt * 8;
     double ca[3][2], cb[3][2];
@@ -187,7 +191,7 @@ eval20_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_rows
   double fr[3];
 #pragma unroll
   for (int mt = 0; mt < 3; mt++) fr[mt] = (mt * 8 + g) < 20 ? model->freqs[mt * 8 + g] : 0.0;
-#pragma unroll 1
+#pragma unroll(A20_UNROLL)
   for (int nt = 0; nt < A20_TILE / 8; nt++) {
     const int64_t p0 = pbase + nt * 8;
     double v[3][2], x[3][2];
