@@ -239,7 +239,17 @@ __global__ void reduce_partials_kernel(int n_trees, int blocks_per_eval, const d
 
 }  // namespace plg
 #include "lik_dna.cuh"
+#ifndef PLG_DNA4_WARP_PER_RATE
+#define PLG_DNA4_WARP_PER_RATE 0
+#endif
+#ifndef PLG_DNA4_VISITS
+#define PLG_DNA4_VISITS 0
+#endif
+namespace plg {
+constexpr int DNA4_PATTERNS_PER_BLOCK = PLG_DNA4_WARP_PER_RATE ? R4_PATTERNS : D4_THREADS;
+}
 #include "lik_aa.cuh"
+#include "lik_visit.cuh"
 namespace plg {
 
 // ----------------------------------------------------------------------------
@@ -296,6 +306,8 @@ LikWorkspace &lik_workspace() {
 }
 
 void LikProgram::clear() {
+  visits.clear();
+  visit_level_off.clear();
   ops.clear();
   level_off.clear();
   evals.clear();
@@ -448,6 +460,8 @@ static void run_typed(const LikAln &a, const Model &m, LikWorkspace &ws, const L
 
 // DNA x Gamma-4 path: thread-per-pattern kernels, evaluations fused into the CLV update that
 // produces their first operand whenever the other operands are ready by then.
+static int64_t dna4_partial_stride(const LikAln &a) { return a.Ppad / (PLG_DNA4_WARP_PER_RATE ? R4_PATTERNS : D4_THREADS); }
+
 static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, cudaStream_t st) {
   constexpr int K = 4, R = 4, KKP = 17, NC = 16;
   const int n_pm = (int)prog.brlens.size();
@@ -504,7 +518,9 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     PLG_CUDA(cudaMemcpyAsync(ws.fops.p, fops.data(), (size_t)n_ops * sizeof(LikOpF), cudaMemcpyHostToDevice, st));
   if (!rest.empty())
     PLG_CUDA(cudaMemcpyAsync(ws.evals.p, rest.data(), rest.size() * sizeof(LikEval), cudaMemcpyHostToDevice, st));
-  const int64_t bpo = a.Ppad / D4_THREADS;
+  const int64_t bpo = a.Ppad / DNA4_PATTERNS_PER_BLOCK;
+  const int64_t pstride = dna4_partial_stride(a);  // finest block tiling among the kernels below
+  if (prog.n_trees) PLG_CUDA(cudaMemsetAsync(ws.partial.p, 0, (size_t)prog.n_trees * pstride * 8, st));
   const double Cb = (double)R * K * 8.0 + 4.0;
   auto opnd = [&](int id) { return id < 0 ? 0.0 : (id < a.n_rows ? 1.0 : Cb); };
   const LikOpF *d_ops = reinterpret_cast<const LikOpF *>(ws.fops.p);
@@ -520,9 +536,15 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
         if (f.tree >= 0) bytes += opnd(f.e_b) + opnd(f.e_c) + 8.0;
       }
       prof_begin(PROF_CLV_UPDATE, st);
+#if PLG_DNA4_WARP_PER_RATE
+      clv4r_kernel<<<(unsigned)(c * bpo), R4_THREADS, 0, st>>>(d_ops + o0 + o, (int)bpo, a.n_rows, a.Ppad, a.codes.p,
+                                                              a.masks.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
+                                                              ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
+#else
       clv4_kernel<<<(unsigned)(c * bpo), D4_THREADS, 0, st>>>(d_ops + o0 + o, (int)bpo, a.n_rows, a.Ppad, a.codes.p,
                                                              a.masks.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
-                                                             ws.clv.p, ws.scl.p, ws.partial.p);
+                                                             ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
+#endif
       count_launch();
       prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, (double)c * (double)a.P);
     }
@@ -534,14 +556,43 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     double bytes = 0;
     for (int64_t q = e; q < e + c; q++) bytes += 8.0 + opnd(rest[q].a) + opnd(rest[q].b) + opnd(rest[q].c);
     prof_begin(PROF_ROOT_EVAL, st);
-    eval4_kernel<<<(unsigned)(c * bpo), D4_THREADS, 0, st>>>(ws.evals.p + e, (int)bpo, a.n_rows, a.Ppad, a.codes.p,
-                                                            a.masks.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
-                                                            ws.clv.p, ws.scl.p, ws.partial.p);
+    const int64_t ebpo = a.Ppad / D4_THREADS;
+    eval4_kernel<<<(unsigned)(c * ebpo), D4_THREADS, 0, st>>>(ws.evals.p + e, (int)ebpo, a.n_rows, a.Ppad, a.codes.p,
+                                                             a.masks.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
+                                                             ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
     count_launch();
     prof_end(PROF_ROOT_EVAL, st, bytes * (double)a.P, (double)c * (double)a.P);
   }
+  // search-step visits (two neighbours per step, operands staged once by the TMA)
+  if (!prog.visits.empty()) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      PLG_CUDA(cudaFuncSetAttribute(visit4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V4_SMEM_BYTES));
+      attr_set = true;
+    }
+    ws.visits.alloc(prog.visits.size());
+    PLG_CUDA(cudaMemcpyAsync(ws.visits.p, prog.visits.data(), prog.visits.size() * sizeof(LikVisit),
+                             cudaMemcpyHostToDevice, st));
+    const int64_t vbpo = a.Ppad / V4_THREADS;
+    for (size_t l = 0; l + 1 < prog.visit_level_off.size(); l++) {
+      const int64_t v0 = prog.visit_level_off[l], cnt = prog.visit_level_off[l + 1] - v0;
+      if (!cnt) continue;
+      double bytes = 0;
+      for (int64_t q = v0; q < v0 + cnt; q++) {
+        const LikVisit &v = prog.visits[q];
+        bytes += opnd(v.x_in) + opnd(v.tv) + opnd(v.d1) + opnd(v.d2) + (v.n1 >= 0 ? Cb : 0.0) + (v.n2 >= 0 ? Cb : 0.0) +
+                 (v.tree1 >= 0 ? 8.0 : 0.0) + (v.tree2 >= 0 ? 8.0 : 0.0);
+      }
+      prof_begin(PROF_CLV_UPDATE, st);
+      visit4_kernel<<<(unsigned)(cnt * vbpo), V4_THREADS, V4_SMEM_BYTES, st>>>(
+          ws.visits.p + v0, (int)vbpo, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
+          ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
+      count_launch();
+      prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, 2.0 * (double)cnt * (double)a.P);
+    }
+  }
   if (prog.n_trees) {
-    reduce_partials_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, (int)bpo,
+    reduce_partials_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, (int)pstride,
                                                                                ws.partial.p, ws.lnl.p);
     count_launch();
   }
@@ -610,7 +661,7 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   ws.ops.alloc(std::max<size_t>(1, prog.ops.size()));
   ws.evals.alloc(std::max<size_t>(1, prog.evals.size()));
   const bool dna4 = (a.K == 4 && m.R == 4);
-  const int64_t bpo = dna4 ? a.Ppad / D4_THREADS : a.Ppad / (LIK_THREADS / m.R);
+  const int64_t bpo = dna4 ? dna4_partial_stride(a) : a.Ppad / (LIK_THREADS / m.R);
   ws.partial.alloc(std::max<size_t>(1, (size_t)prog.n_trees * (size_t)bpo));
   ws.lnl.alloc(std::max<size_t>(1, (size_t)prog.n_trees));
   if (!dna4 && !prog.ops.empty())

@@ -18,6 +18,12 @@ struct LikEval {
   int a, pa, b, pb, c, pc, tree, pad;
 };
 
+// One search step of the SPR edge-insertion walk scoring both neighbours at the node it reaches
+// (DNA x Gamma-4 path, csrc/lik_visit.cuh).  Operand ids as in LikOp; 64 bytes.
+struct LikVisit {
+  int x_in, p_in, tv, p_v, d1, p_t1, p_h1, d2, p_t2, p_h2, n1, n2, tree1, tree2, pad0, pad1;
+};
+
 struct LikWorkspace {
   DevBuf<double> clv;      // [slot][R*K][Ppad]
   DevBuf<int> scl;         // [slot][Ppad] per-pattern 2^-256 scaling counters
@@ -26,6 +32,7 @@ struct LikWorkspace {
   DevBuf<double> brlen;    // [pm]
   DevBuf<LikOp> ops;
   DevBuf<char> fops;       // LikOpF[] (DNA x Gamma-4 path: updates with fused evaluations)
+  DevBuf<LikVisit> visits;
   DevBuf<LikEval> evals;
   DevBuf<double> partial;  // [eval][blocks]
   DevBuf<double> lnl;      // [tree]
@@ -47,6 +54,8 @@ struct LikProgram {
   std::vector<LikOp> ops;          // sorted by level
   std::vector<int64_t> level_off;  // [n_levels+1]
   std::vector<LikEval> evals;
+  std::vector<LikVisit> visits;           // sorted by level; run after every op level
+  std::vector<int64_t> visit_level_off;   // [n_visit_levels+1]
   std::vector<double> brlens;      // unique branch lengths -> P-matrix index
   std::unordered_map<uint64_t, int> pm_index;
   int64_t n_slots = 0, n_trees = 0;

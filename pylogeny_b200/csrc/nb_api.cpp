@@ -5,6 +5,10 @@
 
 #include "neighbourhood.h"
 
+#ifndef PLG_USE_VISITS
+#define PLG_USE_VISITS 0  // pair-fused TMA visit kernel (lik_visit.cuh): correct but slower than clv4r on B200
+#endif
+
 #include <chrono>
 #include <cstdlib>
 
@@ -270,7 +274,7 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
   int64_t chunk = hi - lo;
   for (int64_t c0 = lo; c0 < hi;) {
     int64_t c1 = std::min(hi, c0 + chunk);
-    build_lik_nb_program(nb, tip_rows, a.n_rows, c0, c1, p);
+    build_lik_nb_program(nb, tip_rows, a.n_rows, c0, c1, p, PLG_USE_VISITS && a.K == 4 && m->impl.R == 4);
     if (p.n_slots > max_slots && c1 - c0 > 1) {
       chunk = std::max<int64_t>(1, (c1 - c0) / 2);
       continue;

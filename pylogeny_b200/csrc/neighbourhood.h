@@ -76,8 +76,10 @@ void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, in
 void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int32_t *acc, int64_t lo, int64_t hi,
                      int32_t *out_costs);
 
+// use_visits: emit one LikVisit per search step (both neighbours at the node it reaches; DNA x
+// Gamma-4 kernels) instead of one CLV update + one 3-way evaluation per neighbour.
 void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
-                          LikProgram &out);
+                          LikProgram &out, bool use_visits = false);
 
 }  // namespace plg
 
