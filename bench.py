@@ -347,6 +347,7 @@ def run_ours(args):
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_lnl_sample()[0]
         out["parsimony"] = parsimony_leg(fitch, nbh, L, peak, peak_src, not args.no_cpu)
+        out["streaming"] = streaming_leg(fitch, likelihood, L, peak, peak_src)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -391,6 +392,66 @@ def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
     if cpu:
         res["cpu_baseline"] = cpu_fitch_sample(states, d)
     a.close()
+    return res
+
+
+def streaming_leg(fitch, likelihood, L, peak, peak_src):
+    """Full re-traversal of descriptor batches (plg_*_score_trees), the formulation whose working set
+    is far beyond L2: BASELINE config-4 shape for lnL (128 taxa x 1M sites, 3 random trees, 50 GB of
+    CLVs) and config-3 shape for Fitch (256 taxa x 100k sites, 2048 random trees, 26 GB of state
+    sets).  This is where the kernels meet the HBM roofline proper."""
+    import ctypes as C
+    import torch
+    res = {}
+
+    def read(kind):
+        ms, by, un, nl = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        L.plg_profile_read(kind, C.byref(ms), C.byref(by), C.byref(un), C.byref(nl))
+        return ms.value, by.value, nl.value
+
+    rng = np.random.default_rng(1004)
+    n, S, T = 128, 1_000_000, 3
+    codes = (1 << rng.integers(0, 4, (n, S))).astype(np.uint8)
+    la = likelihood.LikAlignment(codes, np.ones(S))
+    m = likelihood.Model(EXCH, FREQS, ALPHA)
+    descs = np.stack([random_desc(rng, n) for _ in range(T)])
+    brs = rng.exponential(0.1, descs.shape)
+    for _ in range(2):
+        la.score_trees(m, descs, brs)
+    L.plg_profile_enable(1)
+    read(1)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        la.score_trees(m, descs, brs)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 3
+    kms, by, nl = read(1)
+    ach = by / (kms * 1e-3) / 1e9
+    res["lnl_retraversal"] = {"workload": "128 taxa x 1M sites, GTR+G4, %d random trees per call (BASELINE configs[3] shape)" % T,
+                              "value": T * S / dt, "unit": UNIT, "ms_per_call": dt * 1e3,
+                              "roofline": {"kernel": "clv4_kernel (unfused)", "bound": "hbm", "achieved": ach, "peak": peak,
+                                           "unit": "GB/s", "frac": ach / peak, "launches": nl, "peak_source": peak_src}}
+    la.close()
+    n, S, T = 256, 100_000, 2048
+    states = (rng.integers(0, 4, (S, n)) + 48).astype(np.uint8)
+    fa = fitch.FitchAlignment.from_dense(states, np.ones(S, dtype=np.int64))
+    descs = np.stack([random_desc(rng, n) for _ in range(T)])
+    for _ in range(2):
+        fa.score_trees(descs)
+    read(0)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        fa.score_trees(descs)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 3
+    kms, by, nl = read(0)
+    L.plg_profile_enable(0)
+    ach = by / (kms * 1e-3) / 1e9
+    res["fitch_retraversal"] = {"workload": "256 taxa x 100k sites, %d random trees per call (BASELINE configs[2] shape)" % T,
+                                "value": T * S / dt, "unit": UNIT, "ms_per_call": dt * 1e3,
+                                "roofline": {"kernel": "fitch_level_kernel", "bound": "hbm", "achieved": ach, "peak": peak,
+                                             "unit": "GB/s", "frac": ach / peak, "launches": nl, "peak_source": peak_src}}
+    fa.close()
     return res
 
 

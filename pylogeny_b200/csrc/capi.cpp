@@ -6,6 +6,7 @@
 namespace plg {
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::mutex g_api_mutex;
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -33,6 +34,21 @@ extern "C" int plg_set_device(int device) {
   PLG_CUDA(cudaSetDevice(device));
   PLG_API_END
 }
+
+// ---- host stage timer ------------------------------------------------------------------------
+#include <chrono>
+namespace plg {
+double StageTimer::now() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+StageTimer::StageTimer() : on(getenv("PLG_TIMING") != nullptr), t0(now()) {}
+void StageTimer::lap(const char *what) {
+  if (!on) return;
+  const double t1 = now();
+  fprintf(stderr, "[plg] %-14s %8.3f ms\n", what, t1 - t0);
+  t0 = t1;
+}
+}  // namespace plg
 
 // ---- per-kernel profiling -------------------------------------------------------------------
 namespace plg {
@@ -70,7 +86,7 @@ extern "C" int plg_profile_enable(int on) {
 // Sums (and clears) what was recorded for one kernel kind: device milliseconds between the
 // events around each launch, algorithmic bytes, node-op x pattern units, launches.
 extern "C" int plg_profile_read(int kind, double *ms, double *bytes, double *units, int64_t *launches) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (kind < 0 || kind >= plg::PROF_KINDS) PLG_FAIL(PLG_ERR_ARG, "bad kernel kind");
   PLG_CUDA(cudaDeviceSynchronize());
   double t = 0, by = 0, un = 0;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <mutex>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -17,6 +18,7 @@ namespace plg {
 
 void set_error(const char *fmt, ...);
 extern std::atomic<int64_t> g_launches;
+extern std::mutex g_api_mutex;
 
 // Thrown inside the library, always caught at the extern "C" boundary.
 struct Error {
@@ -40,6 +42,8 @@ struct Error {
   } while (0)
 
 #define PLG_API_BEGIN try {
+// compute entry points: the scratch pools are shared per device, so calls are serialised
+#define PLG_API_BEGIN_LOCKED try { std::lock_guard<std::mutex> plg_lock__(plg::g_api_mutex);
 #define PLG_API_END                                    \
   }                                                    \
   catch (const plg::Error &e) { return e.code; }       \
@@ -59,6 +63,15 @@ inline void count_launch(int64_t n = 1) { g_launches.fetch_add(n, std::memory_or
 enum ProfKind { PROF_FITCH_OPS = 0, PROF_CLV_UPDATE = 1, PROF_ROOT_EVAL = 2, PROF_PMATRIX = 3, PROF_KINDS = 4 };
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st, double algorithmic_bytes, double units);
+
+// PLG_TIMING=1: host-side stage times on stderr.
+struct StageTimer {
+  bool on;
+  double t0;
+  static double now();
+  StageTimer();
+  void lap(const char *what);
+};
 
 // Owning device buffer.
 template <typename T>

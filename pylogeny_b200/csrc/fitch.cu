@@ -483,19 +483,23 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
 void score_batch_full(FitchAln &a, const TreeBatch &b, int32_t *out_costs, cudaStream_t st) {
   const int64_t n_trees = b.n_trees();
   if (n_trees == 0) return;
+  StageTimer tm;
   size_t free_b = 0, total_b = 0;
   PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  tm.lap("meminfo");
   const size_t vec_bytes = (size_t)a.K * a.words32 * 4;
   // scratch budget: half of what is free (counting the pool we already hold), capped at 48 GiB
   const size_t budget = std::min<size_t>((free_b + fitch_workspace().scratch.n * 4) / 2, (size_t)48 << 30);
   const int64_t max_slots = std::max<int64_t>(1, (int64_t)(budget / vec_bytes));
-  FitchProgram prog;
+  static thread_local FitchProgram prog;  // keeps its pinned staging across calls
   int64_t t0 = 0;
   while (t0 < n_trees) {
     int64_t t1 = t0 + 1;  // a single over-budget tree is still attempted; cudaMalloc reports failure
     while (t1 < n_trees && b.node_off[t1 + 1] - b.node_off[t0] <= max_slots) t1++;
     build_full_program(b, t0, t1, a.n_cols, prog);
+    tm.lap("build_full");
     run_fitch_program(a, fitch_workspace(), prog, out_costs + t0, st);
+    tm.lap("run");
     t0 = t1;
   }
 }
@@ -523,7 +527,7 @@ static std::vector<uint8_t> gather_profiles(int64_t n_prof, const char *const *p
 
 extern "C" int plg_fitch_aln_create_dense(int64_t n_prof, int n_cols, const uint8_t *states,
                                           const int64_t *weights, plg_fitch_aln **out) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!out || (n_prof > 0 && (!states || !weights))) PLG_FAIL(PLG_ERR_ARG, "null argument");
   *out = new plg_fitch_aln(n_prof, n_cols, states, weights);
   PLG_API_END
@@ -531,7 +535,7 @@ extern "C" int plg_fitch_aln_create_dense(int64_t n_prof, int n_cols, const uint
 
 extern "C" int plg_fitch_aln_create(int64_t n_prof, const char *const *profiles, const int64_t *weights,
                                     plg_fitch_aln **out) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!out || (n_prof > 0 && (!profiles || !weights))) PLG_FAIL(PLG_ERR_ARG, "null argument");
   int n_cols = 0;
   std::vector<uint8_t> dense = gather_profiles(n_prof, profiles, &n_cols);
@@ -561,7 +565,7 @@ static void check_rows(const FitchAln &a, const TreeBatch &b) {
 extern "C" int plg_fitch_score_newicks(plg_fitch_aln *aln, int64_t n_trees, const char *const *newicks,
                                        int n_taxa, const char *const *taxa_names, const int32_t *taxa_idx,
                                        int32_t *out_costs, void *stream) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!aln || !out_costs || (n_trees > 0 && !newicks) || (n_taxa > 0 && (!taxa_names || !taxa_idx)))
     PLG_FAIL(PLG_ERR_ARG, "null argument");
   TaxaMap taxa(n_taxa, taxa_names, taxa_idx);
@@ -574,7 +578,7 @@ extern "C" int plg_fitch_score_newicks(plg_fitch_aln *aln, int64_t n_trees, cons
 
 extern "C" int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_tips, const int32_t *desc,
                                      const int32_t *tip_rows, int32_t *out_costs, void *stream) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!aln || !out_costs || (n_trees > 0 && !desc)) PLG_FAIL(PLG_ERR_ARG, "null argument");
   TreeBatch b = batch_from_desc(n_trees, n_tips, desc, nullptr, tip_rows);
   check_rows(aln->impl, b);
@@ -585,7 +589,7 @@ extern "C" int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_
 extern "C" int plg_fitch_cost(const char *newick, int64_t n_prof, const char *const *profiles,
                               const int64_t *weights, int n_taxa, const char *const *taxa_names,
                               const int32_t *taxa_idx, int32_t *out_cost) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!newick || !out_cost) PLG_FAIL(PLG_ERR_ARG, "null argument");
   // parse + resolve labels first: a bad tree must fail before any device work
   TaxaMap taxa(n_taxa, taxa_names, taxa_idx);

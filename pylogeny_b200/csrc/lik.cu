@@ -685,8 +685,10 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
 void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double *out_lnl, cudaStream_t st) {
   const int64_t n_trees = b.n_trees();
   if (n_trees == 0) return;
+  StageTimer tm;
   size_t free_b = 0, total_b = 0;
   PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  tm.lap("meminfo");
   const size_t slot_bytes = ((size_t)m.R * a.K * 8 + 4) * a.Ppad;
   const size_t held = lik_workspace().clv.n * 8 + lik_workspace().scl.n * 4;
   const size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)64 << 30);
@@ -699,7 +701,9 @@ void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double 
     auto need = [&](int64_t lo, int64_t hi) { return b.child_off[b.node_off[hi]] - b.child_off[b.node_off[lo]]; };
     while (t1 < n_trees && need(t0, t1 + 1) / 2 <= max_slots) t1++;
     build_full_lik_program(b, t0, t1, a.n_rows, prog);
+    tm.lap("build_full");
     run_lik_program(a, m, lik_workspace(), prog, out_lnl + t0, st);
+    tm.lap("run");
     t0 = t1;
   }
 }
@@ -713,7 +717,7 @@ using namespace plg;
 
 extern "C" int plg_lik_aln_create(int datatype, int n_rows, int64_t n_patterns, const uint8_t *codes,
                                   const double *weights, plg_lik_aln **out) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!out || (n_patterns > 0 && (!codes || !weights))) PLG_FAIL(PLG_ERR_ARG, "null argument");
   *out = new plg_lik_aln(datatype, n_rows, n_patterns, codes, weights);
   PLG_API_END
@@ -722,7 +726,7 @@ extern "C" void plg_lik_aln_destroy(plg_lik_aln *aln) { delete aln; }
 
 extern "C" int plg_model_create(int n_states, const double *exch, const double *freqs, double alpha, int n_cat,
                                 plg_model **out) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!out || !exch || !freqs) PLG_FAIL(PLG_ERR_ARG, "null argument");
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
@@ -748,7 +752,7 @@ extern "C" int plg_model_pmatrix(const plg_model *m, double t, double *out) {
 
 extern "C" int plg_lik_score_trees(plg_lik_aln *aln, plg_model *m, int64_t n_trees, int n_tips, const int32_t *desc,
                                    const double *brlen, const int32_t *tip_rows, double *out_lnl, void *stream) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!aln || !m || !out_lnl || (n_trees > 0 && (!desc || !brlen))) PLG_FAIL(PLG_ERR_ARG, "null argument");
   TreeBatch b = batch_from_desc(n_trees, n_tips, desc, brlen, tip_rows);
   for (int32_t c : b.child)

@@ -16,16 +16,6 @@ using namespace plg;
 
 namespace {
 
-struct StageTimer {  // PLG_TIMING=1: host-side stage times on stderr
-  bool on = getenv("PLG_TIMING") != nullptr;
-  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  void lap(const char *what) {
-    if (!on) return;
-    auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[plg] %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
-  }
-};
 
 int depth_for(int move_type) {
   if (move_type == PLG_MOVE_NNI) return 1;
@@ -195,7 +185,7 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
                                              const int32_t *tip_rows, int64_t shard_index, int64_t shard_count,
                                              int64_t *n_moves, int32_t *out_moves, int32_t *out_costs,
                                              void *stream) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!aln || !desc || !n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
   FitchAln &a = aln->impl;
   for (int x = 0; x < n_tips; x++) {
@@ -245,7 +235,7 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
                                            const int32_t *desc, const double *brlen, const int32_t *tip_rows,
                                            int64_t shard_index, int64_t shard_count, int64_t *n_moves,
                                            int32_t *out_moves, double *out_lnl, void *stream) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!aln || !m || !desc || !brlen || !n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
   LikAln &a = aln->impl;
   for (int x = 0; x < n_tips; x++) {

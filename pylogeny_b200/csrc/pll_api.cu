@@ -431,7 +431,7 @@ struct plg_pll {
 };
 
 extern "C" int plg_pll_new(const char *phylip_path, const char *newick, const char *partition_path, plg_pll **out) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!phylip_path || !newick || !partition_path || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
@@ -511,7 +511,7 @@ extern "C" int plg_pll_destroy(plg_pll *p) {
 }
 
 extern "C" int plg_pll_loglik(plg_pll *p, double *out) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!p || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
   *out = p->p.loglik(3);  // pllOptimizeBranchLengths(instance, partitions, 3), libpllWrapper.c:205
   PLG_API_END
@@ -519,7 +519,7 @@ extern "C" int plg_pll_loglik(plg_pll *p, double *out) {
 
 // lnL at the CURRENT branch lengths, no optimisation (pllEvaluateLikelihood, libpllWrapper.c:77-78)
 extern "C" int plg_pll_evaluate(plg_pll *p, double *out) {
-  PLG_API_BEGIN
+  PLG_API_BEGIN_LOCKED
   if (!p || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
   p->p.down_pass();
   *out = p->p.evaluate();
