@@ -263,7 +263,7 @@ def run_ours(args):
         sampler.start()
     L.plg_profile_enable(1)
     for k in range(4):
-        L.plg_profile_read(k, None, None, None, None)
+        L.plg_profile_read(k, None, None, None, None, None)
     launches0 = L.plg_launch_count()
     total_ms = 0.0
     barrier()
@@ -293,9 +293,9 @@ def run_ours(args):
     import ctypes as C
     prof = {}
     for k, name in enumerate(("fitch_level_kernel", "clv_update_kernel", "root_eval_kernel", "pmatrix_kernel")):
-        ms, by, un, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
-        L.plg_profile_read(k, C.byref(ms), C.byref(by), C.byref(un), C.byref(n))
-        prof[name] = {"ms": ms.value, "bytes": by.value, "units": un.value, "launches": n.value}
+        ms, by, un, n, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
+        L.plg_profile_read(k, C.byref(ms), C.byref(by), C.byref(un), C.byref(n), C.byref(rq))
+        prof[name] = {"ms": ms.value, "bytes": by.value, "units": un.value, "launches": n.value, "requested": rq.value}
     peak, peak_src = measured_peaks()
     dom = max(("clv_update_kernel", "root_eval_kernel"), key=lambda k: prof[k]["ms"])
 
@@ -308,6 +308,8 @@ def run_ours(args):
                 "traffic": ncu_traffic(name, p["units"] / p["launches"]), "peak_source": peak_src,
                 "launches": p["launches"],
                 "avg_launch_ms": p["ms"] / p["launches"], "algorithmic_bytes_per_launch": p["bytes"] / p["launches"],
+                "requested_bytes_per_launch": p["requested"] / p["launches"],
+                "requested_gbs": p["requested"] / (p["ms"] * 1e-3) / 1e9,
                 "share_of_step": p["ms"] / total_ms}
 
     roofline = roof(dom)
@@ -365,7 +367,7 @@ def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
     for _ in range(2):
         moves, costs = nbh.score_parsimony(a, d)
     L.plg_profile_enable(1)
-    L.plg_profile_read(0, None, None, None, None)
+    L.plg_profile_read(0, None, None, None, None, None)
     ms = []
     for _ in range(3):
         torch.cuda.synchronize()
@@ -376,8 +378,8 @@ def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     L.plg_profile_enable(0)
-    kms, by, un, nl = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
-    L.plg_profile_read(0, C.byref(kms), C.byref(by), C.byref(un), C.byref(nl))
+    kms, by, un, nl, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
+    L.plg_profile_read(0, C.byref(kms), C.byref(by), C.byref(un), C.byref(nl), C.byref(rq))
     M = len(costs)
     ach = by.value / (kms.value * 1e-3) / 1e9
     res = {"workload": "BASELINE configs[2] shape: synthetic DNA 256 taxa x 100k sites, Fitch length of all %d "
@@ -385,7 +387,8 @@ def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
            "value": M * S / (np.mean(ms) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms)), "dtype": "u32 bitsets",
            "roofline": {"kernel": "fitch_level_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": ach / peak, "traffic": ncu_traffic("fitch_level_kernel", un.value / max(nl.value, 1)),
-                        "algorithmic_bytes_per_launch": by.value / max(nl.value, 1), "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": by.value / max(nl.value, 1),
+                        "requested_gbs": rq.value / (kms.value * 1e-3) / 1e9, "peak_source": peak_src,
                         "launches": nl.value, "avg_launch_ms": kms.value / max(nl.value, 1),
                         "share_of_step": kms.value / sum(ms)},
            "checksum": int(costs.astype(np.int64).sum()), "min_cost": int(costs.min())}
@@ -406,7 +409,7 @@ def streaming_leg(fitch, likelihood, L, peak, peak_src):
 
     def read(kind):
         ms, by, un, nl = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
-        L.plg_profile_read(kind, C.byref(ms), C.byref(by), C.byref(un), C.byref(nl))
+        L.plg_profile_read(kind, C.byref(ms), C.byref(by), C.byref(un), C.byref(nl), None)
         return ms.value, by.value, nl.value
 
     rng = np.random.default_rng(1004)

@@ -8,7 +8,7 @@ L = _lib.lib()
 
 def prof(kind):
     ms, by, un, nl = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
-    L.plg_profile_read(kind, C.byref(ms), C.byref(by), C.byref(un), C.byref(nl))
+    L.plg_profile_read(kind, C.byref(ms), C.byref(by), C.byref(un), C.byref(nl), None)
     return ms.value, by.value, nl.value
 
 rng = np.random.default_rng(4)

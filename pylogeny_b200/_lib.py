@@ -72,7 +72,7 @@ def _declare(L):
     L.plg_lik_score_neighbourhood.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, i64p, vp,
                                               vp, vp]
     L.plg_profile_enable.argtypes = [C.c_int]
-    L.plg_profile_read.argtypes = [C.c_int, dp, dp, dp, i64p]
+    L.plg_profile_read.argtypes = [C.c_int, dp, dp, dp, i64p, dp]
     L.plg_pll_new.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(vp)]
     L.plg_pll_destroy.argtypes = [vp]
     L.plg_pll_loglik.argtypes = [vp, dp]

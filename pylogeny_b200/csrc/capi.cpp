@@ -53,7 +53,7 @@ void StageTimer::lap(const char *what) {
 // ---- per-kernel profiling -------------------------------------------------------------------
 namespace plg {
 namespace {
-struct ProfRec { int kind; cudaEvent_t a, b; double bytes, units; };
+struct ProfRec { int kind; cudaEvent_t a, b; double bytes, units, requested; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof_recs;
 std::vector<cudaEvent_t> g_prof_pool;
@@ -70,11 +70,11 @@ void prof_begin(int kind, cudaStream_t st) {
   g_prof_open[kind] = prof_event();
   cudaEventRecord(g_prof_open[kind], st);
 }
-void prof_end(int kind, cudaStream_t st, double bytes, double units) {
+void prof_end(int kind, cudaStream_t st, double bytes, double units, double requested) {
   if (!g_prof_on) return;
   cudaEvent_t b = prof_event();
   cudaEventRecord(b, st);
-  g_prof_recs.push_back({kind, g_prof_open[kind], b, bytes, units});
+  g_prof_recs.push_back({kind, g_prof_open[kind], b, bytes, units, requested < 0 ? bytes : requested});
 }
 }  // namespace plg
 
@@ -85,18 +85,19 @@ extern "C" int plg_profile_enable(int on) {
 
 // Sums (and clears) what was recorded for one kernel kind: device milliseconds between the
 // events around each launch, algorithmic bytes, node-op x pattern units, launches.
-extern "C" int plg_profile_read(int kind, double *ms, double *bytes, double *units, int64_t *launches) {
+extern "C" int plg_profile_read(int kind, double *ms, double *bytes, double *units, int64_t *launches,
+                                double *requested_bytes) {
   PLG_API_BEGIN_LOCKED
   if (kind < 0 || kind >= plg::PROF_KINDS) PLG_FAIL(PLG_ERR_ARG, "bad kernel kind");
   PLG_CUDA(cudaDeviceSynchronize());
-  double t = 0, by = 0, un = 0;
+  double t = 0, by = 0, un = 0, rq = 0;
   int64_t n = 0;
   std::vector<plg::ProfRec> keep;
   for (auto &r : plg::g_prof_recs) {
     if (r.kind != kind) { keep.push_back(r); continue; }
     float e = 0;
     PLG_CUDA(cudaEventElapsedTime(&e, r.a, r.b));
-    t += e; by += r.bytes; un += r.units; n++;
+    t += e; by += r.bytes; un += r.units; rq += r.requested; n++;
     plg::g_prof_pool.push_back(r.a);
     plg::g_prof_pool.push_back(r.b);
   }
@@ -105,5 +106,6 @@ extern "C" int plg_profile_read(int kind, double *ms, double *bytes, double *uni
   if (bytes) *bytes = by;
   if (units) *units = un;
   if (launches) *launches = n;
+  if (requested_bytes) *requested_bytes = rq;
   PLG_API_END
 }

@@ -411,7 +411,7 @@ void build_full_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_tip_sl
 
 template <int K, int VW>
 static void launch_level(const FitchAln &a, FitchWorkspace &ws, int64_t op0, int64_t n_ops, double level_bytes,
-                         cudaStream_t st) {
+                         double level_req, cudaStream_t st) {
   const int64_t cols = a.words32 / VW;
   // block size: multiple of 32 in [64,256] wasting the fewest lanes
   int best_t = 256;
@@ -430,7 +430,8 @@ static void launch_level(const FitchAln &a, FitchWorkspace &ws, int64_t op0, int
         a.tips.p, ws.scratch.p, a.n_cols, ws.ops.p + op0 + o, ws.children.p, a.words32, (int)bpo,
         a.wbits.p, a.chunk_nb.p, ws.cost.p);
     count_launch();
-    prof_end(PROF_FITCH_OPS, st, level_bytes * (double)cnt / (double)n_ops, (double)cnt * (double)a.P);
+    prof_end(PROF_FITCH_OPS, st, level_bytes * (double)cnt / (double)n_ops, (double)cnt * (double)a.P,
+             level_req * (double)cnt / (double)n_ops);
   }
 }
 
@@ -452,22 +453,27 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
     if (!cnt) continue;
     // algorithmic bytes of this launch: every operand vector read once, every stored vector
     // written once, K_real planes of P bits each (3*K_p/8 B per binary node-op)
-    double vecs = 0;
-    for (int64_t o = o0; o < o0 + cnt; o++)
-      vecs += (prog.ops[o].nchild == FITCH_JOIN3 ? 3 : prog.ops[o].nchild == FITCH_FUSED ? 4 : prog.ops[o].nchild) +
-              (prog.ops[o].dst >= 0 ? 1 : 0);
+    double vecs = 0, req_vecs = 0;
+    for (int64_t o = o0; o < o0 + cnt; o++) {
+      const int nc = prog.ops[o].nchild;
+      const int st_ = prog.ops[o].dst >= 0 ? 1 : 0;
+      if (nc == FITCH_FUSED) { vecs += 6; req_vecs += 4 + st_; }  // fold (2 in, 1 out) + 3-way join (3 in)
+      else if (nc == FITCH_JOIN3) { vecs += 3; req_vecs += 3; }
+      else { vecs += nc + 1; req_vecs += nc + st_; }
+    }
     const double lb = vecs * a.K_real * (double)a.P / 8.0;
+    const double lreq = req_vecs * a.K_real * (double)a.P / 8.0;
     switch (a.K) {
-      case 2: launch_level<2, 4>(a, ws, o0, cnt, lb, st); break;
-      case 3: launch_level<3, 4>(a, ws, o0, cnt, lb, st); break;
-      case 4: launch_level<4, 4>(a, ws, o0, cnt, lb, st); break;
-      case 5: launch_level<5, 4>(a, ws, o0, cnt, lb, st); break;
-      case 6: launch_level<6, 4>(a, ws, o0, cnt, lb, st); break;
-      case 8: launch_level<8, 2>(a, ws, o0, cnt, lb, st); break;
-      case 10: launch_level<10, 2>(a, ws, o0, cnt, lb, st); break;
-      case 12: launch_level<12, 1>(a, ws, o0, cnt, lb, st); break;
-      case 16: launch_level<16, 1>(a, ws, o0, cnt, lb, st); break;
-      case 20: launch_level<20, 1>(a, ws, o0, cnt, lb, st); break;
+      case 2: launch_level<2, 4>(a, ws, o0, cnt, lb, lreq, st); break;
+      case 3: launch_level<3, 4>(a, ws, o0, cnt, lb, lreq, st); break;
+      case 4: launch_level<4, 4>(a, ws, o0, cnt, lb, lreq, st); break;
+      case 5: launch_level<5, 4>(a, ws, o0, cnt, lb, lreq, st); break;
+      case 6: launch_level<6, 4>(a, ws, o0, cnt, lb, lreq, st); break;
+      case 8: launch_level<8, 2>(a, ws, o0, cnt, lb, lreq, st); break;
+      case 10: launch_level<10, 2>(a, ws, o0, cnt, lb, lreq, st); break;
+      case 12: launch_level<12, 1>(a, ws, o0, cnt, lb, lreq, st); break;
+      case 16: launch_level<16, 1>(a, ws, o0, cnt, lb, lreq, st); break;
+      case 20: launch_level<20, 1>(a, ws, o0, cnt, lb, lreq, st); break;
       default: PLG_FAIL(PLG_ERR_STATES, "no kernel for %d planes", a.K);
     }
   }

@@ -242,8 +242,8 @@ __global__ void reduce_partials_kernel(int n_trees, int blocks_per_eval, const d
 #ifndef PLG_DNA4_WARP_PER_RATE
 #define PLG_DNA4_WARP_PER_RATE 0
 #endif
-#ifndef PLG_DNA4_VISITS
-#define PLG_DNA4_VISITS 0
+#ifndef PLG_VISIT_TMA
+#define PLG_VISIT_TMA 0  // 1: visit4_kernel (TMA landing zone); 0: visit4b_kernel (parked shared vectors)
 #endif
 namespace plg {
 constexpr int DNA4_PATTERNS_PER_BLOCK = PLG_DNA4_WARP_PER_RATE ? R4_PATTERNS : D4_THREADS;
@@ -529,11 +529,18 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     const int64_t max_ops = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
     for (int64_t o = 0; o < cnt; o += max_ops) {
       const int64_t c = std::min(max_ops, cnt - o);
-      double bytes = 0;  // algorithmic bytes: C+4 per inner CLV moved, 1 per tip code, 8 per weight
+      // algorithmic bytes (per node-op): CLV update = result + operands, evaluation =
+      // its three operands + weight; C+4 per inner CLV, 1 per tip code.  Requested = what is moved
+      // after fusion (the partial is not re-read) and dead-store elimination.
+      double bytes = 0, req = 0;
       for (int64_t q = o0 + o; q < o0 + o + c; q++) {
         const LikOpF &f = fops[q];
-        bytes += (f.pad ? 0.0 : Cb) + opnd(f.a) + opnd(f.b);
-        if (f.tree >= 0) bytes += opnd(f.e_b) + opnd(f.e_c) + 8.0;
+        bytes += Cb + opnd(f.a) + opnd(f.b);
+        req += (f.pad ? 0.0 : Cb) + opnd(f.a) + opnd(f.b);
+        if (f.tree >= 0) {
+          bytes += Cb + opnd(f.e_b) + opnd(f.e_c) + 8.0;
+          req += opnd(f.e_b) + opnd(f.e_c) + 8.0;
+        }
       }
       prof_begin(PROF_CLV_UPDATE, st);
 #if PLG_DNA4_WARP_PER_RATE
@@ -546,7 +553,7 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
                                                              ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
 #endif
       count_launch();
-      prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, (double)c * (double)a.P);
+      prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, (double)c * (double)a.P, req * (double)a.P);
     }
   }
   const int64_t n_ev = (int64_t)rest.size();
@@ -577,18 +584,27 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     for (size_t l = 0; l + 1 < prog.visit_level_off.size(); l++) {
       const int64_t v0 = prog.visit_level_off[l], cnt = prog.visit_level_off[l + 1] - v0;
       if (!cnt) continue;
-      double bytes = 0;
+      double bytes = 0, req = 0;
       for (int64_t q = v0; q < v0 + cnt; q++) {
         const LikVisit &v = prog.visits[q];
-        bytes += opnd(v.x_in) + opnd(v.tv) + opnd(v.d1) + opnd(v.d2) + (v.n1 >= 0 ? Cb : 0.0) + (v.n2 >= 0 ? Cb : 0.0) +
-                 (v.tree1 >= 0 ? 8.0 : 0.0) + (v.tree2 >= 0 ? 8.0 : 0.0);
+        req += opnd(v.x_in) + opnd(v.tv) + opnd(v.d1) + opnd(v.d2) + (v.n1 >= 0 ? Cb : 0.0) + (v.n2 >= 0 ? Cb : 0.0) +
+               (v.tree1 >= 0 ? 8.0 : 0.0) + (v.tree2 >= 0 ? 8.0 : 0.0);
+        // per neighbour: one CLV update (result + 2 operands) and, if scored, one 3-way evaluation
+        if (v.n1 >= 0 || v.tree1 >= 0) bytes += Cb + opnd(v.x_in) + opnd(v.d2) + (v.tree1 >= 0 ? Cb + opnd(v.d1) + opnd(v.tv) + 8.0 : 0.0);
+        if (v.n2 >= 0 || v.tree2 >= 0) bytes += Cb + opnd(v.x_in) + opnd(v.d1) + (v.tree2 >= 0 ? Cb + opnd(v.d2) + opnd(v.tv) + 8.0 : 0.0);
       }
       prof_begin(PROF_CLV_UPDATE, st);
+#if PLG_VISIT_TMA
       visit4_kernel<<<(unsigned)(cnt * vbpo), V4_THREADS, V4_SMEM_BYTES, st>>>(
           ws.visits.p + v0, (int)vbpo, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
           ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
+#else
+      visit4b_kernel<<<(unsigned)(cnt * vbpo), VB_THREADS, 0, st>>>(
+          ws.visits.p + v0, (int)vbpo, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
+          ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
+#endif
       count_launch();
-      prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, 2.0 * (double)cnt * (double)a.P);
+      prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, 2.0 * (double)cnt * (double)a.P, req * (double)a.P);
     }
   }
   if (prog.n_trees) {

@@ -217,3 +217,127 @@ visit4_kernel(const LikVisit *__restrict__ visits, int blocks_per_op, int n_rows
 }
 
 }  // namespace plg
+
+// ---------------------------------------------------------------------------------------------
+// visit4b_kernel: the same pair-fused search step without the 64 KB landing zone.  Thread = one
+// pattern; the two vectors shared by both neighbours -- a = P_in X and tvv = P_v Tv -- are parked in
+// shared memory by the thread that computed them (conflict-free [entry][thread] layout, no barrier
+// needed), so the register file only ever holds the working set of ONE neighbour and 5-6 blocks stay
+// resident per SM.  D1 / D2 are read from global twice by the same thread (second read hits L1);
+// tip tables are read through the read-only path instead of being staged.
+namespace plg {
+
+constexpr int VB_THREADS = 128;
+#ifndef PLG_VB_MINB
+#define PLG_VB_MINB 5
+#endif
+
+template <bool MUL>
+__device__ __forceinline__ void vb_operand(const double *mat, int id, int pm_tab, int n_rows, int code, int64_t p,
+                                           int64_t Ppad, const double *__restrict__ tiptab,
+                                           const double *__restrict__ clv, double (&v)[16]) {
+  if (id < n_rows) {
+    const double *row = tiptab + (int64_t)pm_tab * 256 + code * 16;
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const double2 t = __ldg(reinterpret_cast<const double2 *>(row + i));
+      if (MUL) { v[i] *= t.x; v[i + 1] *= t.y; } else { v[i] = t.x; v[i + 1] = t.y; }
+    }
+  } else {
+    double x[16];
+    d4_load16(clv + (int64_t)(id - n_rows) * 16 * Ppad + p, Ppad, x);
+    v4_apply_reg<MUL>(mat, x, v);
+  }
+}
+
+__global__ void __launch_bounds__(VB_THREADS, PLG_VB_MINB)
+visit4b_kernel(const LikVisit *__restrict__ visits, int blocks_per_op, int n_rows, int64_t Ppad,
+               const unsigned char *__restrict__ codes, const double *__restrict__ weights,
+               const ModelDev *__restrict__ model, const double *__restrict__ pmat,
+               const double *__restrict__ tiptab, double *__restrict__ clv, int *__restrict__ scl,
+               double *__restrict__ partial, int pstride) {
+  __shared__ __align__(16) double mats[6 * 64];
+  __shared__ double park[2][16][VB_THREADS];  // a, tvv
+  __shared__ double wsum[8];
+  const int v_idx = blockIdx.x / blocks_per_op;
+  const int pb = blockIdx.x - v_idx * blocks_per_op;
+  const LikVisit vi = visits[v_idx];
+  const int64_t p = (int64_t)pb * VB_THREADS + threadIdx.x;
+  v4_stage_mat(mats + 0 * 64, vi.p_in, pmat);
+  v4_stage_mat(mats + 1 * 64, vi.p_v, pmat);
+  v4_stage_mat(mats + 2 * 64, vi.p_t1, pmat);
+  v4_stage_mat(mats + 3 * 64, vi.p_h1, pmat);
+  v4_stage_mat(mats + 4 * 64, vi.p_t2, pmat);
+  v4_stage_mat(mats + 5 * 64, vi.p_h2, pmat);
+  const int cx = vi.x_in < n_rows ? codes[(int64_t)vi.x_in * Ppad + p] : 0;
+  const int ct = vi.tv < n_rows ? codes[(int64_t)vi.tv * Ppad + p] : 0;
+  const int c1 = vi.d1 < n_rows ? codes[(int64_t)vi.d1 * Ppad + p] : 0;
+  const int c2 = vi.d2 < n_rows ? codes[(int64_t)vi.d2 * Ppad + p] : 0;
+  const int sx = vi.x_in < n_rows ? 0 : scl[(int64_t)(vi.x_in - n_rows) * Ppad + p];
+  const int st = vi.tv < n_rows ? 0 : scl[(int64_t)(vi.tv - n_rows) * Ppad + p];
+  const int s1 = vi.d1 < n_rows ? 0 : scl[(int64_t)(vi.d1 - n_rows) * Ppad + p];
+  const int s2 = vi.d2 < n_rows ? 0 : scl[(int64_t)(vi.d2 - n_rows) * Ppad + p];
+  const double w = weights[p];
+  __syncthreads();
+  {
+    double t[16];
+    vb_operand<false>(mats + 0 * 64, vi.x_in, vi.p_in, n_rows, cx, p, Ppad, tiptab, clv, t);
+#pragma unroll
+    for (int i = 0; i < 16; i++) park[0][i][threadIdx.x] = t[i];
+    vb_operand<false>(mats + 1 * 64, vi.tv, vi.p_v, n_rows, ct, p, Ppad, tiptab, clv, t);
+#pragma unroll
+    for (int i = 0; i < 16; i++) park[1][i][threadIdx.x] = t[i];
+  }
+  double v1 = 0.0, v2 = 0.0;
+#pragma unroll
+  for (int mv = 0; mv < 2; mv++) {
+    const int dst = mv == 0 ? vi.n1 : vi.n2, tree = mv == 0 ? vi.tree1 : vi.tree2;
+    if (dst < 0 && tree < 0) continue;
+    // neighbour mv: partial over the OTHER child's full branch, far side = own child over half its branch
+    const int oth_id = mv == 0 ? vi.d2 : vi.d1, own_id = mv == 0 ? vi.d1 : vi.d2;
+    const int oth_pm = mv == 0 ? vi.p_t2 : vi.p_t1, own_pm = mv == 0 ? vi.p_h1 : vi.p_h2;
+    const double *m_oth = mats + (mv == 0 ? 4 : 2) * 64, *m_own = mats + (mv == 0 ? 3 : 5) * 64;
+    const int oth_code = mv == 0 ? c2 : c1, own_code = mv == 0 ? c1 : c2;
+    double n[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) n[i] = park[0][i][threadIdx.x];
+    vb_operand<true>(m_oth, oth_id, oth_pm, n_rows, oth_code, p, Ppad, tiptab, clv, n);
+    int scn = sx + (mv == 0 ? s2 : s1);
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) mx = fmax(mx, fabs(n[i]));
+    if (mx < MINLH) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) n[i] *= TWO256;
+      scn += 1;
+    }
+    if (dst >= 0) {
+      double *out = clv + (int64_t)(dst - n_rows) * 16 * Ppad + p;
+#pragma unroll
+      for (int i = 0; i < 16; i++) out[(int64_t)i * Ppad] = n[i];
+      scl[(int64_t)(dst - n_rows) * Ppad + p] = scn;
+    }
+    if (tree >= 0) {
+      double e[16];
+      v4_apply_reg<false>(m_own, n, e);
+      vb_operand<true>(m_own, own_id, own_pm, n_rows, own_code, p, Ppad, tiptab, clv, e);
+#pragma unroll
+      for (int i = 0; i < 16; i++) e[i] *= park[1][i][threadIdx.x];
+      const double val = v4_site(e, scn + (mv == 0 ? s1 : s2) + st, w, model);
+      if (mv == 0) v1 = val; else v2 = val;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v1 += __shfl_down_sync(0xffffffffu, v1, d);
+    v2 += __shfl_down_sync(0xffffffffu, v2, d);
+  }
+  if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5] = v1; wsum[4 + (threadIdx.x >> 5)] = v2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (vi.tree1 >= 0) partial[(int64_t)vi.tree1 * pstride + pb] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+    if (vi.tree2 >= 0) partial[(int64_t)vi.tree2 * pstride + pb] = (wsum[4] + wsum[5]) + (wsum[6] + wsum[7]);
+  }
+}
+
+}  // namespace plg
