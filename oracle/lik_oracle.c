@@ -148,7 +148,8 @@ void oracle_pmatrix(int K, const double *eval, const double *U, const double *Ui
   for (int i = 0; i < K; i++) for (int j = 0; j < K; j++) {
     double s = 0;
     for (int k = 0; k < K; k++) s += U[i * K + k] * exp(eval[k] * t) * Uinv[k * K + j];
-    P[i * K + j] = s;
+    P[i * K + j] = s > 0.0 ? s : 0.0; /* a probability: round-off can leave -1e-17 at t ~ 0 */
+    if (t == 0.0) P[i * K + j] = (i == j) ? 1.0 : 0.0; /* zero-length branch: identity exactly */
   }
 }
 

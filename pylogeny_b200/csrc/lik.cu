@@ -50,6 +50,8 @@ __global__ void pmatrix_kernel(const ModelDev *__restrict__ model, const double 
     double s = 0.0;
 #pragma unroll 4
     for (int k = 0; k < K; k++) s += model->U[i * K + k] * ex[r * K + k] * model->Uinv[k * K + j];
+    s = fmax(s, 0.0);  // transition probabilities: round-off can leave -1e-17 at t ~ 0
+    if (t == 0.0) s = (i == j) ? 1.0 : 0.0;  // a zero-length branch is the identity exactly
     Pm[r * KKP + i * K + j] = s;
     pmat[(int64_t)pm * R * KKP + r * KKP + i * K + j] = s;
   }

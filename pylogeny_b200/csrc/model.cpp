@@ -151,7 +151,8 @@ void Model::pmatrix(double t, double *out) const {
     for (int j = 0; j < K; j++) {
       double s = 0.0;
       for (int k = 0; k < K; k++) s += h.U[i * K + k] * std::exp(h.eval[k] * t) * h.Uinv[k * K + j];
-      out[i * K + j] = s;
+      out[i * K + j] = s > 0.0 ? s : 0.0;  // probabilities: clamp round-off negatives (as the device kernel does)
+      if (t == 0.0) out[i * K + j] = (i == j) ? 1.0 : 0.0;
     }
 }
 
