@@ -34,6 +34,9 @@ extern "C" {
 #define PLG_MOVE_NNI 2 /* rearrangement.py:27 TYPE_SPR, TYPE_NNI, TYPE_TBR = 1, 2, 3 */
 #define PLG_MOVE_SPR 1
 #define PLG_MOVE_TBR 3
+/* SPR moves whose regraft point is at most r branches from the pruning point (the maxdist of
+ * getSPRMovesInDistance, libpllWrapper.c:241-262); r = 0: unlimited; r = 1 equals NNI. */
+#define PLG_MOVE_SPR_WITHIN(r) (PLG_MOVE_SPR | ((r) << 8))
 
 #define PLG_DATA_DNA 4  /* 4 states, tip codes are 4-bit ambiguity masks (A=1,C=2,G=4,T=8) */
 #define PLG_DATA_AA 20  /* 20 states, tip codes 0..19, 20=B, 21=Z, 22=X/-/? */
@@ -181,6 +184,16 @@ int plg_pll_evaluate(plg_pll *p, double *out);
 /* getNewickString(handle) (:217-239): unrooted Newick with the current branch lengths.  *len in:
  * buffer size, out: bytes needed incl. NUL; call with buf == NULL to size the buffer. */
 int plg_pll_newick(plg_pll *p, char *buf, size_t *len);
+/* getSPRMovesInDistance / getNNIMovesInDistance / getAllMovesInDistance(handle, maxdist)
+ * (:241-319, list built at :36-93): every distinct neighbour of the handle's current tree whose
+ * regraft point is within maxdist branches, with its lnL at the current branch lengths and its
+ * Newick string, best lnL first.  which: PLG_MOVE_SPR, PLG_MOVE_NNI or PLG_MOVES_ALL (distance-1
+ * moves are labelled NNI, the rest SPR).  compute scores the neighbourhood and keeps the list in
+ * the handle; fetch copies it out: kinds[M], lnl[M] (float, like :54), M NUL-terminated strings
+ * back to back in newick_buf. */
+#define PLG_MOVES_ALL 4
+int plg_pll_moves_compute(plg_pll *p, int which, int maxdist, int64_t *n_moves, size_t *newick_bytes);
+int plg_pll_moves_fetch(plg_pll *p, int32_t *kinds, float *lnl, char *newick_buf, size_t newick_bytes);
 int plg_pll_info(plg_pll *p, int *n_states, int64_t *n_patterns, double *freqs, double *rates);
 
 #ifdef __cplusplus

@@ -6,7 +6,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpylogeny_b200.so")
 
 OK, ERR_ARG, ERR_PARSE, ERR_LABEL, ERR_CUDA, ERR_STATES, ERR_UNSUPPORTED, ERR_IO = range(8)
-MOVE_SPR, MOVE_NNI, MOVE_TBR = 1, 2, 3
+MOVE_SPR, MOVE_NNI, MOVE_TBR, MOVES_ALL = 1, 2, 3, 4
+
+
+def MOVE_SPR_WITHIN(radius):
+    """SPR moves regrafting at most `radius` branches away (PLG_MOVE_SPR_WITHIN; 0 = unlimited)."""
+    if radius < 0:
+        raise ValueError("radius must be >= 0")
+    return MOVE_SPR | (int(radius) << 8)
+
+
 DATA_DNA, DATA_AA = 4, 20
 
 _lib = None
@@ -78,4 +87,6 @@ def _declare(L):
     L.plg_pll_loglik.argtypes = [vp, dp]
     L.plg_pll_evaluate.argtypes = [vp, dp]
     L.plg_pll_newick.argtypes = [vp, C.c_char_p, C.POINTER(C.c_size_t)]
+    L.plg_pll_moves_compute.argtypes = [vp, C.c_int, C.c_int, i64p, C.POINTER(C.c_size_t)]
+    L.plg_pll_moves_fetch.argtypes = [vp, vp, vp, vp, C.c_size_t]
     L.plg_pll_info.argtypes = [vp, C.POINTER(C.c_int), i64p, dp, dp]

@@ -17,9 +17,12 @@ using namespace plg;
 namespace {
 
 
+// move_type = kind | radius << 8 (PLG_MOVE_SPR_WITHIN): search depth of the SPR enumeration
 int depth_for(int move_type) {
-  if (move_type == PLG_MOVE_NNI) return 1;
-  if (move_type == PLG_MOVE_SPR) return -1;
+  const int kind = move_type & 0xFF, radius = move_type >> 8;
+  if (radius < 0) PLG_FAIL(PLG_ERR_ARG, "negative search radius");
+  if (kind == PLG_MOVE_NNI) return 1;
+  if (kind == PLG_MOVE_SPR) return radius == 0 ? -1 : radius;
   PLG_FAIL(PLG_ERR_UNSUPPORTED, "move type %d: NNI (2), SPR (1) and TBR (3) neighbourhoods are built in", move_type);
 }
 
@@ -128,6 +131,32 @@ int score_tbr_lik(LikAln &a, const Model &m, int n_tips, const int32_t *desc, co
 
 }  // namespace
 
+namespace plg {
+// lnL of the distinct neighbours [lo, hi) of an enumerated SPR/NNI neighbourhood, in chunks that
+// fit the device (out_lnl is indexed by neighbour, only [lo, hi) is written).
+void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *tip_rows, int64_t lo, int64_t hi,
+                   double *out_lnl, cudaStream_t stream) {
+  size_t free_b = 0, total_b = 0;
+  PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t slot_bytes = ((size_t)m.R * a.K * 8 + 4) * a.Ppad;
+  const size_t held = lik_workspace().clv.n * 8 + lik_workspace().scl.n * 4;
+  const size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)80 << 30);
+  const int64_t max_slots = std::max<int64_t>(4 * nb.t.n_tips, (int64_t)(budget / slot_bytes));
+  LikProgram p;
+  int64_t chunk = hi - lo;
+  for (int64_t c0 = lo; c0 < hi;) {
+    int64_t c1 = std::min(hi, c0 + chunk);
+    build_lik_nb_program(nb, tip_rows, a.n_rows, c0, c1, p, PLG_USE_VISITS && a.K == 4 && m.R == 4);
+    if (p.n_slots > max_slots && c1 - c0 > 1) {
+      chunk = std::max<int64_t>(1, (c1 - c0) / 2);
+      continue;
+    }
+    run_lik_program(a, m, lik_workspace(), p, out_lnl + c0, stream);
+    c0 = c1;
+  }
+}
+}  // namespace plg
+
 extern "C" int plg_neighbourhood_size(int move_type, int n_tips, const int32_t *desc, int64_t *n_moves) {
   PLG_API_BEGIN
   if (!desc || !n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
@@ -136,7 +165,11 @@ extern "C" int plg_neighbourhood_size(int move_type, int n_tips, const int32_t *
     return PLG_OK;
   }
   const int depth = depth_for(move_type);
-  utree_from_desc(n_tips, desc, nullptr);  // validates the descriptor
+  UTree t = utree_from_desc(n_tips, desc, nullptr);  // validates the descriptor
+  if (depth > 1) {  // radius-limited SPR: depends on the tree shape
+    *n_moves = (int64_t)enumerate_spr(t, depth).unique.size();
+    return PLG_OK;
+  }
   // closed forms for an unrooted binary tree (checked against the enumeration in the tests)
   const int64_t n = n_tips;
   *n_moves = n < 4 ? 0 : (depth == 1 ? 2 * (n - 3) : 2 * (n - 3) * (2 * n - 7));
@@ -254,25 +287,7 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
   if (!out_lnl || M == 0) return PLG_OK;
   int64_t lo, hi;
   shard_range(M, shard_index, shard_count, &lo, &hi);
-  size_t free_b = 0, total_b = 0;
-  PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const size_t slot_bytes = ((size_t)m->impl.R * a.K * 8 + 4) * a.Ppad;
-  const size_t held = lik_workspace().clv.n * 8 + lik_workspace().scl.n * 4;
-  const size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)80 << 30);
-  const int64_t max_slots = std::max<int64_t>(4 * n_tips, (int64_t)(budget / slot_bytes));
-  LikProgram p;
-  int64_t chunk = hi - lo;
-  for (int64_t c0 = lo; c0 < hi;) {
-    int64_t c1 = std::min(hi, c0 + chunk);
-    build_lik_nb_program(nb, tip_rows, a.n_rows, c0, c1, p, PLG_USE_VISITS && a.K == 4 && m->impl.R == 4);
-    if (p.n_slots > max_slots && c1 - c0 > 1) {
-      chunk = std::max<int64_t>(1, (c1 - c0) / 2);
-      continue;
-    }
-    tm.lap("build");
-    run_lik_program(a, m->impl, lik_workspace(), p, out_lnl + c0, (cudaStream_t)stream);
-    tm.lap("run");
-    c0 = c1;
-  }
+  score_spr_lik(a, m->impl, nb, tip_rows, lo, hi, out_lnl, (cudaStream_t)stream);
+  tm.lap("score");
   PLG_API_END
 }

@@ -180,7 +180,6 @@ Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
       term[3 * x + k] = split_term(far[3 * x + k], all);
     }
   struct Frame { int x, from, parent_move, depth; uint64_t rem, add; };
-  if (max_depth > 1) PLG_FAIL(PLG_ERR_UNSUPPORTED, "search depth limits other than 1 are not supported");
   // Number of search steps of every (pruned subtree, side): all edges beyond `start` seen from u,
   // i.e. 2*leaves-2 of that side (depth-limited: 2 if start is internal).  Prefix sums give every
   // search its slice of the move array, so the host cores fill it in place.
@@ -200,7 +199,20 @@ Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
       for (int side = 0; side < 2; side++) {
         const int ks = (k + 1 + side) % 3, start = t.nb[u][ks];
         int64_t cnt = 0;
-        if (!t.is_tip(start)) cnt = (max_depth == 1) ? 2 : 2 * (int64_t)leaves[3 * start + t.slot_of(start, u)] - 2;
+        if (!t.is_tip(start)) {
+          if (max_depth < 0) cnt = 2 * (int64_t)leaves[3 * start + t.slot_of(start, u)] - 2;
+          else if (max_depth == 1) cnt = 2;
+          else {  // radius-limited search (getSPRMovesInDistance): count by walking
+            std::vector<std::array<int, 3>> st{{start, u, 0}};
+            while (!st.empty()) {
+              const auto f = st.back();
+              st.pop_back();
+              if (t.is_tip(f[0]) || f[2] >= max_depth) continue;
+              for (int j = 0; j < 3; j++)
+                if (t.nb[f[0]][j] != f[1]) { cnt++; st.push_back({t.nb[f[0]][j], f[0], f[2] + 1}); }
+            }
+          }
+        }
         off[(size_t)(u - t.n_tips) * 6 + k * 2 + side + 1] = cnt;
       }
   for (size_t i = 0; i + 1 < off.size(); i++) off[i + 1] += off[i];

@@ -81,6 +81,10 @@ void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int
 void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
                           LikProgram &out, bool use_visits = false);
 
+// lnL of the distinct neighbours [lo, hi) of an enumerated SPR/NNI neighbourhood (nb_api.cpp).
+void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *tip_rows, int64_t lo, int64_t hi,
+                   double *out_lnl, cudaStream_t stream);
+
 }  // namespace plg
 
 // ---------------------------------------------------------------------------------------------

@@ -133,6 +133,11 @@ struct PllProblem {
   bool smoothed = false;
   double lnl = 0.0;
 
+  // result of the last plg_pll_moves_compute (libpllWrapper.c:36-93 builds the same triples)
+  std::vector<int32_t> mv_kind;
+  std::vector<float> mv_lnl;
+  std::vector<std::string> mv_newick;
+
   // scratch (device) for smoothing
   DevBuf<double> S;
   DevBuf<int> Ssc;
@@ -298,7 +303,7 @@ struct PllProblem {
     return lnl;
   }
 
-  void newick_rec(int x, int from, std::ostringstream &os) const {
+  void newick_rec(const UTree &tree, int x, int from, std::ostringstream &os) const {
     if (tree.is_tip(x)) { os << tip_names[x]; return; }
     os << "(";
     bool first = true;
@@ -307,13 +312,15 @@ struct PllProblem {
       if (c == from) continue;
       if (!first) os << ",";
       first = false;
-      newick_rec(c, x, os);
+      newick_rec(tree, c, x, os);
       os << ":" << tree.len[x][j];
     }
     os << ")";
   }
 
-  std::string newick() const {  // unrooted, from the inner node next to the first taxon (:227-229)
+  std::string newick() const { return newick_of(tree); }
+
+  std::string newick_of(const UTree &tree) const {  // unrooted, from the inner node next to the first taxon (:227-229)
     std::ostringstream os;
     os.precision(17);
     const int w = tree.nb[0][0];
@@ -322,7 +329,7 @@ struct PllProblem {
       const int c = tree.nb[w][j];
       if (c == 0) continue;
       os << ",";
-      newick_rec(c, w, os);
+      newick_rec(tree, c, w, os);
       os << ":" << tree.len[w][j];
     }
     os << ");";
@@ -535,6 +542,59 @@ extern "C" int plg_pll_newick(plg_pll *p, char *buf, size_t *len) {
   const bool ok = buf && *len >= need;
   *len = need;
   if (!ok && buf) PLG_FAIL(PLG_ERR_ARG, "buffer too small: need %zu bytes", need);
+  PLG_API_END
+}
+
+// get{SPR,NNI,All}MovesInDistance (libpllWrapper.c:241-319): every distinct neighbour of the
+// handle's current tree within `maxdist`, its lnL at the current branch lengths (neighbour
+// lengths by the reference's own rule, rearrangement.py:466-497) cast to float like :54, and its
+// Newick string; best first.  Computed once here, copied out by plg_pll_moves_fetch.
+extern "C" int plg_pll_moves_compute(plg_pll *p, int which, int maxdist, int64_t *n_moves, size_t *newick_bytes) {
+  PLG_API_BEGIN_LOCKED
+  if (!p || !n_moves || !newick_bytes) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  if (which != PLG_MOVE_SPR && which != PLG_MOVE_NNI && which != PLG_MOVES_ALL)
+    PLG_FAIL(PLG_ERR_ARG, "moves: SPR (1), NNI (2) or all (4)");
+  PllProblem &pr = p->p;
+  pr.mv_kind.clear(); pr.mv_lnl.clear(); pr.mv_newick.clear();
+  *n_moves = 0; *newick_bytes = 0;
+  if (maxdist < 1) return PLG_OK;  // mintrav = 1 > maxtrav: libpll's search visits nothing
+  Neighbourhood nb = enumerate_spr(pr.tree, which == PLG_MOVE_NNI ? 1 : maxdist);
+  const int64_t M = (int64_t)nb.unique.size();
+  if (M == 0) return PLG_OK;
+  std::vector<double> lnl(M);
+  score_spr_lik(*pr.aln, *pr.model, nb, pr.tip_rows.data(), 0, M, lnl.data(), 0);
+  std::vector<int64_t> order(M);
+  for (int64_t i = 0; i < M; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return lnl[a] > lnl[b]; });
+  size_t bytes = 0;
+  for (int64_t i : order) {
+    const Move &m = nb.moves[nb.unique[i]];
+    const bool nni = which == PLG_MOVE_NNI || (which == PLG_MOVES_ALL && m.depth == 1);
+    pr.mv_kind.push_back(nni ? PLG_MOVE_NNI : PLG_MOVE_SPR);
+    pr.mv_lnl.push_back((float)lnl[i]);
+    pr.mv_newick.push_back(pr.newick_of(apply_move(nb.t, m)));
+    bytes += pr.mv_newick.back().size() + 1;
+  }
+  *n_moves = M;
+  *newick_bytes = bytes;
+  PLG_API_END
+}
+
+extern "C" int plg_pll_moves_fetch(plg_pll *p, int32_t *kinds, float *lnl, char *newick_buf, size_t newick_bytes) {
+  PLG_API_BEGIN
+  if (!p) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  const PllProblem &pr = p->p;
+  size_t at = 0;
+  for (size_t i = 0; i < pr.mv_kind.size(); i++) {
+    if (kinds) kinds[i] = pr.mv_kind[i];
+    if (lnl) lnl[i] = pr.mv_lnl[i];
+    if (newick_buf) {
+      const std::string &s = pr.mv_newick[i];
+      if (at + s.size() + 1 > newick_bytes) PLG_FAIL(PLG_ERR_ARG, "buffer too small for the Newick strings");
+      memcpy(newick_buf + at, s.c_str(), s.size() + 1);  // NUL-separated
+      at += s.size() + 1;
+    }
+  }
   PLG_API_END
 }
 

@@ -7,15 +7,24 @@
 
 over the C-ABI `plg_pll_*` (include/pylogeny_b200.h).  Error behaviour follows the reference:
 IOError for unparsable inputs (:141-146, :153-156, :211), ReferenceError for a bad handle (:178).
-The libpll-internal move enumerators getSPR/NNI/AllMovesInDistance (:241-319) have no Python caller
-in the reference; their role -- lnL of a whole neighbourhood -- is
-pylogeny_b200.neighbourhood.score_likelihood.
+    getSPRMovesInDistance / getNNIMovesInDistance / getAllMovesInDistance(handle, maxdist)
+        -> [("SPR"|"NNI", lnL, newick)]                        (:241-319, list built at :36-93)
+
+The three move enumerators have no Python caller in the reference.  Here they
+return EVERY distinct neighbour of the handle's current tree within `maxdist` branches (libpll
+searches only from nodep[1..n+1], :254, and caps the list at 4(n-3)(n-2)+(n-1), :86-88), scored at
+the handle's current branch lengths with the neighbour's lengths set by the reference's own SPR
+rule (rearrangement.py:466-497), lnL rounded through float like :54, best first.  The bulk form
+without strings is pylogeny_b200.neighbourhood.score_likelihood.
 """
+import numpy as np
+
 import ctypes as C
 
 from . import _lib
 
-__all__ = ["new", "destroy", "getLogLikelihood", "getNewickString", "evaluate"]
+__all__ = ["new", "destroy", "getLogLikelihood", "getNewickString", "evaluate",
+           "getSPRMovesInDistance", "getNNIMovesInDistance", "getAllMovesInDistance"]
 
 
 class _Handle(object):
@@ -85,3 +94,40 @@ def getNewickString(handle):
     if rc:
         raise IOError("Unable to acquire Newick string for tree.")
     return buf.value.decode()
+
+
+def _moves(handle, which, maxdist):
+    if not isinstance(maxdist, int) or isinstance(maxdist, bool):
+        raise ReferenceError("Could not parse pointer, integer.")  # libpllWrapper.c:246-248
+    p = _ptr(handle)
+    L = _lib.lib()
+    n, nbytes = C.c_int64(), C.c_size_t()
+    rc = L.plg_pll_moves_compute(p, which, maxdist, C.byref(n), C.byref(nbytes))
+    if rc:
+        _raise(rc)
+    if n.value == 0:
+        return []
+    kinds = np.zeros(n.value, dtype=np.int32)
+    lnl = np.zeros(n.value, dtype=np.float32)
+    buf = C.create_string_buffer(nbytes.value)
+    rc = L.plg_pll_moves_fetch(p, kinds.ctypes.data, lnl.ctypes.data, buf, nbytes.value)
+    if rc:
+        _raise(rc)
+    strings = buf.raw[:-1].split(b"\0")
+    return [("NNI" if k == _lib.MOVE_NNI else "SPR", float(v), s.decode())
+            for k, v, s in zip(kinds.tolist(), lnl.tolist(), strings)]
+
+
+def getSPRMovesInDistance(handle, maxdist):
+    """Get all SPR moves in a given radius of the current tree."""
+    return _moves(handle, _lib.MOVE_SPR, maxdist)
+
+
+def getNNIMovesInDistance(handle, maxdist):
+    """Get all NNI moves in a given radius of the current tree."""
+    return _moves(handle, _lib.MOVE_NNI, maxdist)
+
+
+def getAllMovesInDistance(handle, maxdist):
+    """Get all NNI and SPR moves in a given radius of the current tree."""
+    return _moves(handle, _lib.MOVES_ALL, maxdist)

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import MOVE_NNI, MOVE_SPR, MOVE_TBR  # noqa: F401
+from ._lib import MOVE_NNI, MOVE_SPR, MOVE_SPR_WITHIN, MOVE_TBR  # noqa: F401
 
 
 def _desc(desc):

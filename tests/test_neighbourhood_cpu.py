@@ -140,3 +140,27 @@ def test_tbr_enumeration_vs_bruteforce(n):
     # SPR neighbours are a subset of TBR neighbours
     sd, _, sh = nbh.neighbour_trees(d, None, None, nbh.MOVE_SPR)
     assert set(sh.tolist()) <= set(hashes.tolist())
+
+
+@pytest.mark.parametrize("n,radius", [(6, 1), (7, 2), (9, 3), (12, 2), (12, 4), (12, 30)])
+def test_radius_limited_spr_vs_split_distance(n, radius):
+    """getSPRMovesInDistance's maxdist (libpllWrapper.c:241-262): the radius-r neighbourhood is exactly
+    the SPR neighbours that differ from the base tree in at most r splits (an SPR across d internal
+    nodes replaces d splits)."""
+    from pylogeny_b200 import neighbourhood as nbh
+    rng = np.random.default_rng(500 + n + radius)
+    d = random_desc(rng, n)
+    base = _splits(d, n)
+    descs, _, hashes = nbh.neighbour_trees(d, None, None, nbh.MOVE_SPR)
+    want = {int(h) for x, h in zip(descs, hashes) if len(_splits(x, n) - base) <= radius}
+    mt = nbh.MOVE_SPR_WITHIN(radius)
+    M = nbh.neighbourhood_size(d, mt)
+    rd, _, rh = nbh.neighbour_trees(d, None, None, mt)
+    assert M == len(rh) == len(set(rh.tolist()))
+    assert set(int(h) for h in rh) == want
+    for x, h in zip(rd, rh):
+        assert nbh.topology_hash(x) == int(h)
+    if radius == 1:
+        assert M == nbh.neighbourhood_size(d, nbh.MOVE_NNI)
+    if radius >= n:
+        assert M == nbh.neighbourhood_size(d, nbh.MOVE_SPR)

@@ -116,3 +116,50 @@ def test_wag_model_is_usable():
     assert np.isfinite(l0) and l1 >= l0
     W.destroy(h)
     pm.close(); ali.close()
+
+
+def test_moves_in_distance_vs_oracle():
+    """get{SPR,NNI,All}MovesInDistance (libpllWrapper.c:241-319): every returned Newick string scores,
+    under the FP64 oracle, the lnL that came with it (float-rounded like :54); counts follow the
+    radius-limited enumeration; best first."""
+    from pylogeny_b200 import _lib, libpllWrapper as W, likelihood, neighbourhood as nbh, pll
+    ali, d = _case(n=9, S=400, seed=11)
+    n = ali.getNumSeqs()
+    labels = ali.getTaxa()
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    h = W.new(ali.getPhylip(), desc_to_newick(d, labels), pm.getFileName())
+    W.getLogLikelihood(h)                         # neighbours are scored at the optimised lengths
+    freqs = np.zeros(4)
+    _lib.check(_lib.lib().plg_pll_info(h.ptr, None, None, freqs.ctypes.data_as(C.POINTER(C.c_double)), None))
+    codes = likelihood.encode_sequences(ali.toStrList(), _lib.DATA_DNA)
+    taxa = {l: i for i, l in enumerate(labels)}
+    w = np.ones(ali.getSize())
+    base_nw = W.getNewickString(h)
+    bd, _, brows, _ = nbh.newick_to_desc(base_nw, taxa)
+    assert W.getSPRMovesInDistance(h, 0) == []
+    nni = W.getNNIMovesInDistance(h, 1)
+    assert len(nni) == 2 * (n - 3) and all(k == "NNI" for k, _, _ in nni)
+    for radius in (1, 2, 50):
+        spr = W.getSPRMovesInDistance(h, radius)
+        assert len(spr) == nbh.neighbourhood_size(bd, nbh.MOVE_SPR_WITHIN(radius))
+        assert all(k == "SPR" for k, _, _ in spr)
+        vals = [v for _, v, _ in spr]
+        assert vals == sorted(vals, reverse=True)
+        hashes = set()
+        for _, v, nw in spr[:: max(1, len(spr) // 25)]:
+            want = _oracle_at(nw, taxa, codes, w, np.ones(6), freqs, 1.0)
+            assert abs(v - want) <= 4e-7 * abs(want)             # float32 rounding of the reference's tuple
+        for _, _, nw in spr:
+            dd, _, rows, _ = nbh.newick_to_desc(nw, taxa)
+            hashes.add(nbh.topology_hash(dd, rows))
+        assert len(hashes) == len(spr) and nbh.topology_hash(bd, brows) not in hashes
+    both = W.getAllMovesInDistance(h, 50)
+    assert len(both) == 2 * (n - 3) * (2 * n - 7)
+    assert sum(k == "NNI" for k, _, _ in both) == 2 * (n - 3)
+    assert {nw for _, _, nw in both if _ == _} >= {nw for _, _, nw in nni}
+    assert W.getNewickString(h) == base_nw                      # the handle's tree is left as it was (rollback, :62)
+    with pytest.raises(ReferenceError):
+        W.getSPRMovesInDistance(h, "2")
+    W.destroy(h)
+    pm.close(); ali.close()
