@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpylogeny_b200.so")
+LIB_PATH = os.environ.get("PLG_LIB_PATH") or os.path.join(_HERE, "libpylogeny_b200.so")  # override: tuning sweeps
 
 OK, ERR_ARG, ERR_PARSE, ERR_LABEL, ERR_CUDA, ERR_STATES, ERR_UNSUPPORTED, ERR_IO = range(8)
 MOVE_SPR, MOVE_NNI, MOVE_TBR, MOVES_ALL = 1, 2, 3, 4

@@ -252,6 +252,7 @@ constexpr int DNA4_PATTERNS_PER_BLOCK = PLG_DNA4_WARP_PER_RATE ? R4_PATTERNS : D
 }
 #include "lik_aa.cuh"
 #include "lik_visit.cuh"
+#include "lik_walk.cuh"
 namespace plg {
 
 // ----------------------------------------------------------------------------
@@ -310,6 +311,9 @@ LikWorkspace &lik_workspace() {
 void LikProgram::clear() {
   visits.clear();
   visit_level_off.clear();
+  walk_visits.clear();
+  walk_groups.clear();
+  walk_levels = 0;
   ops.clear();
   level_off.clear();
   evals.clear();
@@ -521,7 +525,8 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   if (!rest.empty())
     PLG_CUDA(cudaMemcpyAsync(ws.evals.p, rest.data(), rest.size() * sizeof(LikEval), cudaMemcpyHostToDevice, st));
   const int64_t bpo = a.Ppad / DNA4_PATTERNS_PER_BLOCK;
-  const int64_t pstride = dna4_partial_stride(a);  // finest block tiling among the kernels below
+  // finest block tiling among the kernels below (search walks reduce per 32-pattern slice)
+  const int64_t pstride = prog.walk_visits.empty() ? dna4_partial_stride(a) : a.Ppad / 32;
   if (prog.n_trees) PLG_CUDA(cudaMemsetAsync(ws.partial.p, 0, (size_t)prog.n_trees * pstride * 8, st));
   const double Cb = (double)R * K * 8.0 + 4.0;
   auto opnd = [&](int id) { return id < 0 ? 0.0 : (id < a.n_rows ? 1.0 : Cb); };
@@ -609,6 +614,58 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, 2.0 * (double)cnt * (double)a.P, req * (double)a.P);
     }
   }
+  // depth-first search walks: one persistent launch, a warp per (pattern slice, pruned subtree)
+  if (!prog.walk_visits.empty()) {
+    int dev = 0, n_sm = 148;
+    PLG_CUDA(cudaGetDevice(&dev));
+    PLG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const int n_blocks = n_sm * PLG_WK_MINB;
+    const int64_t n_warps = (int64_t)n_blocks * WK_WARPS;
+    const int levels = std::max(1, prog.walk_levels);
+    ws.walk_visits.alloc(prog.walk_visits.size());
+    ws.walk_groups.alloc(prog.walk_groups.size());
+    ws.walk_stack.alloc((size_t)n_warps * levels * 16 * 32);
+    ws.walk_stack_scl.alloc((size_t)n_warps * levels * 32);
+    ws.walk_counter.alloc(1);
+    PLG_CUDA(cudaMemcpyAsync(ws.walk_visits.p, prog.walk_visits.data(), prog.walk_visits.size() * sizeof(LikWalkVisit),
+                             cudaMemcpyHostToDevice, st));
+    PLG_CUDA(cudaMemcpyAsync(ws.walk_groups.p, prog.walk_groups.data(), prog.walk_groups.size() * sizeof(LikWalkGroup),
+                             cudaMemcpyHostToDevice, st));
+    PLG_CUDA(cudaMemsetAsync(ws.walk_counter.p, 0, sizeof(unsigned long long), st));
+    // accounting: algorithmic = per neighbour one CLV update (result + 2 operands) and one 3-way
+    // evaluation (3 operands + weight), as for every other planner; requested = what the walk
+    // really loads and stores (far-side operands, first partial of a side, stack traffic, Tv once
+    // per search)
+    double bytes = 0, req = 0, units = 0;
+    for (const LikWalkGroup &g : prog.walk_groups) {
+      req += opnd(g.tv) + 8.0;
+      for (int q = g.first; q < g.first + g.count; q++) {
+        const LikWalkVisit &v = prog.walk_visits[q];
+        const double xin = v.x_in >= 0 ? opnd(v.x_in) : Cb;
+        const bool n1 = v.tree1 >= 0 || v.keep == 1 || (v.push >= 0 && v.keep == 2);
+        const bool n2 = v.tree2 >= 0 || v.keep == 2 || (v.push >= 0 && v.keep == 1);
+        if (n1) bytes += Cb + xin + opnd(v.d2) + (v.tree1 >= 0 ? Cb + opnd(v.d1) + opnd(g.tv) + 8.0 : 0.0);
+        if (n2) bytes += Cb + xin + opnd(v.d1) + (v.tree2 >= 0 ? Cb + opnd(v.d2) + opnd(g.tv) + 8.0 : 0.0);
+        req += (v.x_in >= 0 ? opnd(v.x_in) : (v.x_in <= -2 ? Cb : 0.0)) + opnd(v.d1) + opnd(v.d2) +
+               (v.push >= 0 ? Cb : 0.0) + (v.tree1 >= 0 ? 0.25 : 0.0) + (v.tree2 >= 0 ? 0.25 : 0.0);
+        units += 2.0;
+      }
+    }
+    const int64_t n_items = (a.Ppad / 32) * (int64_t)prog.walk_groups.size();
+    prof_begin(PROF_CLV_UPDATE, st);
+    static bool walk_attr_set = false;
+    if (!walk_attr_set) {
+      PLG_CUDA(cudaFuncSetAttribute(walk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WK_SMEM_BYTES));
+      walk_attr_set = true;
+    }
+    walk4_kernel<<<n_blocks, WK_THREADS, WK_SMEM_BYTES, st>>>(ws.walk_groups.p, (int)prog.walk_groups.size(), ws.walk_visits.p,
+                                                  n_items, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p, ws.pmat.p,
+                                                  ws.tiptab.p, ws.clv.p, ws.scl.p, ws.walk_stack.p,
+                                                  ws.walk_stack_scl.p, levels, ws.partial.p, (int)pstride,
+                                                  ws.walk_counter.p);
+    count_launch();
+    prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, units * (double)a.P, req * (double)a.P);
+  }
   if (prog.n_trees) {
     reduce_partials_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, (int)pstride,
                                                                                ws.partial.p, ws.lnl.p);
@@ -679,7 +736,8 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   ws.ops.alloc(std::max<size_t>(1, prog.ops.size()));
   ws.evals.alloc(std::max<size_t>(1, prog.evals.size()));
   const bool dna4 = (a.K == 4 && m.R == 4);
-  const int64_t bpo = dna4 ? dna4_partial_stride(a) : a.Ppad / (LIK_THREADS / m.R);
+  const int64_t bpo = !dna4 ? a.Ppad / (LIK_THREADS / m.R)
+                             : (prog.walk_visits.empty() ? dna4_partial_stride(a) : a.Ppad / 32);
   ws.partial.alloc(std::max<size_t>(1, (size_t)prog.n_trees * (size_t)bpo));
   ws.lnl.alloc(std::max<size_t>(1, (size_t)prog.n_trees));
   if (!dna4 && !prog.ops.empty())

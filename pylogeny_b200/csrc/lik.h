@@ -24,6 +24,19 @@ struct LikVisit {
   int x_in, p_in, tv, p_v, d1, p_t1, p_h1, d2, p_t2, p_h2, n1, n2, tree1, tree2, pad0, pad1;
 };
 
+// Depth-first SPR search walks (csrc/lik_walk.cuh).  One group = one pruned subtree (both sides
+// of the pruning point); its visits are listed in the order one warp executes them.
+//   x_in >= 0: the incoming partial is a stored operand (first step of a side); -1: it is the
+//   partial the previous visit kept in registers; <= -2: pop it from stack level (-2 - x_in).
+//   keep: 0 none, 1 / 2: the partial toward d1 / d2 continues in registers into the next visit;
+//   push >= 0: the other partial is parked at that stack level.
+struct LikWalkVisit {
+  int x_in, p_in, d1, p_t1, p_h1, d2, p_t2, p_h2, tree1, tree2, keep, push, pad0, pad1, pad2, pad3;
+};
+struct LikWalkGroup {
+  int tv, p_v, first, count;
+};
+
 struct LikWorkspace {
   DevBuf<double> clv;      // [slot][R*K][Ppad]
   DevBuf<int> scl;         // [slot][Ppad] per-pattern 2^-256 scaling counters
@@ -33,6 +46,11 @@ struct LikWorkspace {
   DevBuf<LikOp> ops;
   DevBuf<char> fops;       // LikOpF[] (DNA x Gamma-4 path: updates with fused evaluations)
   DevBuf<LikVisit> visits;
+  DevBuf<LikWalkVisit> walk_visits;
+  DevBuf<LikWalkGroup> walk_groups;
+  DevBuf<double> walk_stack;   // [warp][level][16][32]
+  DevBuf<int> walk_stack_scl;  // [warp][level][32]
+  DevBuf<unsigned long long> walk_counter;
   DevBuf<LikEval> evals;
   DevBuf<double> partial;  // [eval][blocks]
   DevBuf<double> lnl;      // [tree]
@@ -56,6 +74,9 @@ struct LikProgram {
   std::vector<LikEval> evals;
   std::vector<LikVisit> visits;           // sorted by level; run after every op level
   std::vector<int64_t> visit_level_off;   // [n_visit_levels+1]
+  std::vector<LikWalkVisit> walk_visits;  // depth-first search walks, run after the op levels
+  std::vector<LikWalkGroup> walk_groups;  // longest first
+  int walk_levels = 0;                    // stack levels a walk needs
   std::vector<double> brlens;      // unique branch lengths -> P-matrix index
   std::unordered_map<uint64_t, int> pm_index;
   int64_t n_slots = 0, n_trees = 0;

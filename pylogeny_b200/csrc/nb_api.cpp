@@ -5,12 +5,13 @@
 
 #include "neighbourhood.h"
 
-#ifndef PLG_USE_VISITS
-#define PLG_USE_VISITS 1  // pair-fused search steps (lik_visit.cuh visit4b_kernel): 10.8 vs 12.4 ms per 64x10k step
-#endif
+// DNA x Gamma-4 neighbourhood planner: depth-first walks (lik_walk.cuh walk4_kernel) ship; the
+// level-by-level planners stay selectable for A/B measurements (PLG_LIK_NB_MODE=ops|visits|walk;
+// 64 taxa x 10k sites per step on B200: ops 12.4 ms, visits 10.8 ms).
 
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
 
 using namespace plg;
 
@@ -132,6 +133,12 @@ int score_tbr_lik(LikAln &a, const Model &m, int n_tips, const int32_t *desc, co
 }  // namespace
 
 namespace plg {
+static int lik_nb_mode() {
+  const char *e = std::getenv("PLG_LIK_NB_MODE");
+  if (e && !strcmp(e, "ops")) return LIK_NB_OPS;
+  if (e && !strcmp(e, "visits")) return LIK_NB_VISITS;
+  return LIK_NB_WALK;
+}
 // lnL of the distinct neighbours [lo, hi) of an enumerated SPR/NNI neighbourhood, in chunks that
 // fit the device (out_lnl is indexed by neighbour, only [lo, hi) is written).
 void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *tip_rows, int64_t lo, int64_t hi,
@@ -146,7 +153,7 @@ void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *
   int64_t chunk = hi - lo;
   for (int64_t c0 = lo; c0 < hi;) {
     int64_t c1 = std::min(hi, c0 + chunk);
-    build_lik_nb_program(nb, tip_rows, a.n_rows, c0, c1, p, PLG_USE_VISITS && a.K == 4 && m.R == 4);
+    build_lik_nb_program(nb, tip_rows, a.n_rows, c0, c1, p, a.K == 4 && m.R == 4 ? lik_nb_mode() : LIK_NB_OPS);
     if (p.n_slots > max_slots && c1 - c0 > 1) {
       chunk = std::max<int64_t>(1, (c1 - c0) / 2);
       continue;

@@ -529,7 +529,8 @@ void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int
 }
 
 void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
-                          LikProgram &prog, bool use_visits) {
+                          LikProgram &prog, int mode) {
+  const bool use_visits = mode == LIK_NB_VISITS;
   const UTree &t = nb.t;
   prog.clear();
   DirOrder d = dir_order(t);
@@ -555,6 +556,99 @@ void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int 
     o.level = d.level[e];
     dir_slot[e] = o.op.dst;
     tmp.push_back(o);
+  }
+  if (mode == LIK_NB_WALK) {
+    // Depth-first walks (lik_walk.cuh).  Search steps come in adjacent pairs (2q, 2q+1): the two
+    // insertion edges at the node a step reaches = one visit.  Visits of one pruned subtree are
+    // listed in the order a warp runs them: the partial toward the child with the smaller
+    // remaining search continues in registers, the other one is parked on a stack (depth <= log2 n).
+    std::vector<char> need = needed_moves(nb, lo, hi);
+    const size_t n_moves = nb.moves.size(), n_pairs = n_moves / 2;
+    std::vector<int> child(n_moves, -1);   // move -> the visit that continues below it
+    std::vector<int> sub(n_pairs, 0);      // needed visits in the subtree of a visit
+    for (size_t q = n_pairs; q-- > 0;) {
+      if (!need[2 * q] && !need[2 * q + 1]) continue;
+      sub[q] += 1;
+      const int pm = nb.moves[2 * q].parent;
+      if (pm >= 0) { child[pm] = (int)q; sub[pm / 2] += sub[q]; }
+    }
+    struct Frame { int q, x_in; };
+    std::vector<Frame> st;
+    int cur_u = -1, cur_k = -1, depth = 0;
+    for (size_t q = 0; q < n_pairs; q++) {
+      const Move &r = nb.moves[2 * q];
+      if (r.parent >= 0 || sub[q] == 0) continue;  // roots of needed searches only
+      if (r.u != cur_u || r.k != cur_k) {
+        const int v = t.nb[r.u][r.k];
+        LikWalkGroup g;
+        g.tv = dir_slot[3 * v + t.slot_of(v, r.u)];
+        g.p_v = prog.pm(t.len[r.u][r.k]);
+        g.first = (int)prog.walk_visits.size();
+        g.count = 0;
+        prog.walk_groups.push_back(g);
+        cur_u = r.u; cur_k = r.k;
+      }
+      {
+        const int ko = (r.k + 1 + (1 - r.side)) % 3;
+        const int other = t.nb[r.u][ko];
+        st.push_back({(int)q, dir_slot[3 * other + t.slot_of(other, r.u)]});
+      }
+      while (!st.empty()) {
+        const Frame f = st.back();
+        st.pop_back();
+        if (f.x_in <= -2) depth--;
+        const Move &m1 = nb.moves[2 * f.q], &m2 = nb.moves[2 * f.q + 1];
+        const int x = m1.x, c1 = t.nb[x][m1.kx], c2 = t.nb[x][m2.kx];
+        double lin;
+        if (m1.parent < 0) {
+          const int ko = (m1.k + 1 + (1 - m1.side)) % 3, ks = (m1.k + 1 + m1.side) % 3;
+          lin = t.len[m1.u][ko] + t.len[m1.u][ks];  // merged edge other -- x (rearrangement.py:480-490)
+        } else {
+          const Move &pm = nb.moves[m1.parent];
+          lin = t.len[pm.x][pm.kx];
+        }
+        const double t1 = t.len[x][m1.kx], t2 = t.len[x][m2.kx];
+        LikWalkVisit w;
+        w.x_in = f.x_in; w.p_in = prog.pm(lin);
+        w.d1 = dir_slot[3 * c1 + t.slot_of(c1, x)]; w.p_t1 = prog.pm(t1); w.p_h1 = prog.pm(t1 / 2.0);
+        w.d2 = dir_slot[3 * c2 + t.slot_of(c2, x)]; w.p_t2 = prog.pm(t2); w.p_h2 = prog.pm(t2 / 2.0);
+        w.tree1 = (m1.unique_id >= lo && m1.unique_id < hi) ? (int)(m1.unique_id - lo) : -1;
+        w.tree2 = (m2.unique_id >= lo && m2.unique_id < hi) ? (int)(m2.unique_id - lo) : -1;
+        w.keep = 0; w.push = -1;
+        w.pad0 = w.pad1 = w.pad2 = w.pad3 = 0;
+        const int ch1 = need[2 * f.q] ? child[2 * f.q] : -1, ch2 = need[2 * f.q + 1] ? child[2 * f.q + 1] : -1;
+        if (ch1 >= 0 && ch2 >= 0) {
+          const bool first1 = sub[ch1] <= sub[ch2];
+          w.keep = first1 ? 1 : 2;
+          w.push = depth;
+          st.push_back({first1 ? ch2 : ch1, -2 - depth});
+          st.push_back({first1 ? ch1 : ch2, -1});
+          depth++;
+          prog.walk_levels = std::max(prog.walk_levels, depth);
+        } else if (ch1 >= 0) {
+          w.keep = 1;
+          st.push_back({ch1, -1});
+        } else if (ch2 >= 0) {
+          w.keep = 2;
+          st.push_back({ch2, -1});
+        }
+        prog.walk_visits.push_back(w);
+        prog.walk_groups.back().count++;
+      }
+    }
+    std::stable_sort(prog.walk_groups.begin(), prog.walk_groups.end(),
+                     [](const LikWalkGroup &a, const LikWalkGroup &b) { return a.count > b.count; });
+    int max_level = 0;
+    for (auto &o : tmp) max_level = std::max(max_level, o.level);
+    prog.level_off.assign(max_level + 2, 0);
+    for (auto &o : tmp) prog.level_off[o.level + 1]++;
+    for (int l = 0; l <= max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+    std::vector<int64_t> cur(prog.level_off.begin(), prog.level_off.end() - 1);
+    prog.ops.resize(tmp.size());
+    for (auto &o : tmp) prog.ops[cur[o.level]++] = o.op;
+    prog.n_slots = slots;
+    prog.n_trees = hi - lo;
+    return;
   }
   if (use_visits) {
     // Search steps come in adjacent pairs (2q, 2q+1): the two insertion edges at the node a step

@@ -64,6 +64,8 @@ void desc_from_utree(const UTree &t, int32_t *desc, double *brlen);
 
 // Edge-insertion programs over moves unique[lo..hi): directional partials of the base tree, one
 // partial per search step, one join / 3-way evaluation per distinct neighbour.
+enum { LIK_NB_OPS = 0, LIK_NB_VISITS = 1, LIK_NB_WALK = 2 };
+
 struct FitchNbProgram {
   FitchProgram prog;
   std::vector<int> dir_acc;                 // accumulator of directional op 3*x+k (-1 for tips)
@@ -76,10 +78,12 @@ void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, in
 void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int32_t *acc, int64_t lo, int64_t hi,
                      int32_t *out_costs);
 
-// use_visits: emit one LikVisit per search step (both neighbours at the node it reaches; DNA x
+// mode: LIK_NB_OPS one CLV update + one 3-way evaluation per neighbour (any state count);
+// LIK_NB_WALK depth-first search walks (LikWalkVisit, lik_walk.cuh; DNA x Gamma-4);
+// LIK_NB_VISITS: emit one LikVisit per search step (both neighbours at the node it reaches; DNA x
 // Gamma-4 kernels) instead of one CLV update + one 3-way evaluation per neighbour.
 void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
-                          LikProgram &out, bool use_visits = false);
+                          LikProgram &out, int mode = LIK_NB_OPS);
 
 // lnL of the distinct neighbours [lo, hi) of an enumerated SPR/NNI neighbourhood (nb_api.cpp).
 void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *tip_rows, int64_t lo, int64_t hi,

@@ -107,3 +107,43 @@ def test_tbr_edge_insertion_vs_retraversal(n, P):
     M = len(lnl)
     np.testing.assert_array_equal(np.concatenate([parts[0][:M // 2], parts[1][M // 2:]]), lnl)
     fa.close(); la.close(); m.close()
+
+
+@pytest.mark.parametrize("n,P,scale", [(6, 40, 1.0), (24, 700, 1.0), (70, 300, 1.0), (40, 200, 60.0)])
+def test_lnl_planners_agree(n, P, scale, monkeypatch):
+    """The three DNA x Gamma-4 neighbourhood planners (PLG_LIK_NB_MODE: per-neighbour ops, pair-fused
+    level-by-level visits, depth-first walks -- the default) give the same lnL per neighbour, also
+    in the underflow regime (long branches => 2^-256 rescaling inside the walk), for shards and for
+    radius-limited neighbourhoods; walk == oracle on a sample."""
+    from pylogeny_b200 import likelihood, neighbourhood as nbh
+    rng = np.random.default_rng(11 * n + P)
+    codes = (1 << rng.integers(0, 4, (n, P))).astype(np.uint8)
+    codes = np.where(rng.random((n, P)) < 0.02, 15, codes).astype(np.uint8)
+    w = rng.integers(1, 4, P).astype(float)
+    exch, f = rng.uniform(0.3, 3, 6), rng.dirichlet(np.ones(4) * 6)
+    a = likelihood.LikAlignment(codes, w)
+    m = likelihood.Model(exch, f, 0.6)
+    d = random_desc(rng, n)
+    br = rng.exponential(0.1 * scale, d.shape)
+    res = {}
+    for mode in ("ops", "visits", "walk"):
+        monkeypatch.setenv("PLG_LIK_NB_MODE", mode)
+        res[mode] = nbh.score_likelihood(a, m, d, br)[1]
+    np.testing.assert_allclose(res["walk"], res["ops"], rtol=1e-12)
+    np.testing.assert_allclose(res["walk"], res["visits"], rtol=1e-12)
+    monkeypatch.setenv("PLG_LIK_NB_MODE", "walk")
+    M = len(res["walk"])
+    parts = [nbh.score_likelihood(a, m, d, br, shard=(i, 3))[1] for i in range(3)]
+    merged = np.concatenate([parts[i][M * i // 3: M * (i + 1) // 3] for i in range(3)])
+    np.testing.assert_array_equal(merged, res["walk"])
+    descs, brs, _ = nbh.neighbour_trees(d, br)
+    for i in range(0, M, max(1, M // 10)):
+        want = oracle.lnl(codes, w, exch, f, 0.6, descs[i], brs[i])
+        assert abs(res["walk"][i] - want) <= 1e-8 * abs(want)
+    mt = nbh.MOVE_SPR_WITHIN(3)
+    _, near = nbh.score_likelihood(a, m, d, br, move_type=mt)
+    _, _, near_h = nbh.neighbour_trees(d, br, None, mt)
+    _, _, all_h = nbh.neighbour_trees(d, br)
+    by_hash = dict(zip(all_h.tolist(), res["walk"].tolist()))
+    np.testing.assert_allclose(near, [by_hash[h] for h in near_h.tolist()], rtol=1e-12)
+    a.close(); m.close()
