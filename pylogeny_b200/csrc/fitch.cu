@@ -24,6 +24,7 @@
 #include <numeric>
 
 #include "fitch.h"
+#include "treewalk.h"
 
 namespace plg {
 
@@ -256,6 +257,10 @@ __global__ void fitch_pack_kernel(const unsigned char *__restrict__ states, cons
   }
   for (int s = 0; s < K; s++) tips[((int64_t)row * K + s) * words32 + w] = planes[s];
 }
+
+}  // namespace plg
+#include "fitch_walk.cuh"
+namespace plg {
 
 // ----------------------------------------------------------------------------
 // host: alignment
@@ -510,6 +515,57 @@ void score_batch_full(FitchAln &a, const TreeBatch &b, int32_t *out_costs, cudaS
   }
 }
 
+// Descriptor batches: tree walks planned on the device (treewalk.h).  The host copies the raw
+// descriptors up and the costs down; nothing per node happens on the host.
+bool tree_walk_enabled() {
+  const char *e = getenv("PLG_TREE_MODE");
+  return !(e && !strcmp(e, "levels"));
+}
+
+void score_desc_walk(FitchAln &a, int64_t n_trees, int n_tips, const int32_t *desc, const int32_t *tip_rows,
+                     int32_t *out_costs, cudaStream_t st) {
+  if (n_trees == 0) return;
+  StageTimer tm;
+  validate_desc(n_trees, n_tips, desc, tip_rows, a.n_cols, a.P > 0);
+  tm.lap("validate");
+  FitchWorkspace &ws = fitch_workspace();
+  const int ni = n_tips - 1;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_trees, ((int64_t)512 << 20) / (36 * (int64_t)ni + 8)));
+  ws.walk_desc.alloc((size_t)chunk * ni * 2);
+  ws.walk_ops.alloc((size_t)chunk * ni);
+  ws.walk_scratch.alloc((size_t)chunk * (3 * (size_t)ni + 2));
+  ws.cost.alloc((size_t)chunk);
+  ws.walk_rows.alloc((size_t)n_tips);
+  if (tip_rows)
+    PLG_CUDA(cudaMemcpyAsync(ws.walk_rows.p, tip_rows, (size_t)n_tips * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  for (int64_t t0 = 0; t0 < n_trees; t0 += chunk) {
+    const int64_t cnt = std::min(chunk, n_trees - t0);
+    PLG_CUDA(cudaMemcpyAsync(ws.walk_desc.p, desc + (size_t)t0 * ni * 2, (size_t)cnt * ni * 2 * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, st));
+    PLG_CUDA(cudaMemsetAsync(ws.cost.p, 0, (size_t)cnt * sizeof(unsigned int), st));
+    launch_plan_walk(cnt, n_tips, ws.walk_desc.p, tip_rows ? ws.walk_rows.p : nullptr, a.n_cols,
+                     reinterpret_cast<WalkOp *>(ws.walk_ops.p), ws.walk_scratch.p, st);
+    const WalkOp *ops = reinterpret_cast<const WalkOp *>(ws.walk_ops.p);
+    switch (a.K) {
+      case 2: launch_fitch_walk<2, 4>(a, ops, cnt, ni, ws.cost.p, st); break;
+      case 3: launch_fitch_walk<3, 4>(a, ops, cnt, ni, ws.cost.p, st); break;
+      case 4: launch_fitch_walk<4, 4>(a, ops, cnt, ni, ws.cost.p, st); break;
+      case 5: launch_fitch_walk<5, 4>(a, ops, cnt, ni, ws.cost.p, st); break;
+      case 6: launch_fitch_walk<6, 4>(a, ops, cnt, ni, ws.cost.p, st); break;
+      case 8: launch_fitch_walk<8, 2>(a, ops, cnt, ni, ws.cost.p, st); break;
+      case 10: launch_fitch_walk<10, 2>(a, ops, cnt, ni, ws.cost.p, st); break;
+      case 12: launch_fitch_walk<12, 1>(a, ops, cnt, ni, ws.cost.p, st); break;
+      case 16: launch_fitch_walk<16, 1>(a, ops, cnt, ni, ws.cost.p, st); break;
+      case 20: launch_fitch_walk<20, 1>(a, ops, cnt, ni, ws.cost.p, st); break;
+      default: PLG_FAIL(PLG_ERR_STATES, "no kernel for %d planes", a.K);
+    }
+    PLG_CUDA(cudaGetLastError());
+    PLG_CUDA(cudaMemcpyAsync(out_costs + t0, ws.cost.p, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PLG_CUDA(cudaStreamSynchronize(st));
+    tm.lap("walk chunk");
+  }
+}
+
 }  // namespace plg
 
 // ----------------------------------------------------------------------------
@@ -586,6 +642,10 @@ extern "C" int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_
                                      const int32_t *tip_rows, int32_t *out_costs, void *stream) {
   PLG_API_BEGIN_LOCKED
   if (!aln || !out_costs || (n_trees > 0 && !desc)) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  if (tree_walk_enabled() && n_tips >= 2 && n_tips <= (1 << WALK_MAX_LEVELS)) {
+    score_desc_walk(aln->impl, n_trees, n_tips, desc, tip_rows, out_costs, (cudaStream_t)stream);
+    return PLG_OK;
+  }
   TreeBatch b = batch_from_desc(n_trees, n_tips, desc, nullptr, tip_rows);
   check_rows(aln->impl, b);
   score_batch_full(aln->impl, b, out_costs, (cudaStream_t)stream);

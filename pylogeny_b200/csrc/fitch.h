@@ -24,6 +24,10 @@ struct FitchWorkspace {
   DevBuf<FitchOp> ops;
   DevBuf<int> children;
   DevBuf<unsigned int> cost;
+  DevBuf<int32_t> walk_desc;    // tree walks (treewalk.h): raw descriptors, planned ops, planner scratch
+  DevBuf<int4> walk_ops;
+  DevBuf<int> walk_scratch;
+  DevBuf<int32_t> walk_rows;
 };
 
 // Scratch pool shared by every alignment handle on the current device (grow-only; dropping a
@@ -58,6 +62,10 @@ void build_full_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_tip_sl
 void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram &prog, int32_t *out_costs,
                        cudaStream_t st);
 void score_batch_full(FitchAln &a, const TreeBatch &b, int32_t *out_costs, cudaStream_t st);
+// binary descriptor batches by on-chip tree walks (PLG_TREE_MODE=levels selects the level programs)
+bool tree_walk_enabled();
+void score_desc_walk(FitchAln &a, int64_t n_trees, int n_tips, const int32_t *desc, const int32_t *tip_rows,
+                     int32_t *out_costs, cudaStream_t st);
 
 }  // namespace plg
 

@@ -20,6 +20,7 @@
 #include <cstring>
 
 #include "lik.h"
+#include "treewalk.h"
 
 namespace plg {
 
@@ -253,6 +254,7 @@ constexpr int DNA4_PATTERNS_PER_BLOCK = PLG_DNA4_WARP_PER_RATE ? R4_PATTERNS : D
 #include "lik_aa.cuh"
 #include "lik_visit.cuh"
 #include "lik_walk.cuh"
+#include "lik_twalk.cuh"
 namespace plg {
 
 // ----------------------------------------------------------------------------
@@ -784,6 +786,77 @@ void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double 
   }
 }
 
+// Binary descriptor batches, DNA x Gamma-4: tree walks planned on the device (treewalk.h,
+// lik_twalk.cuh).  Host work per call: validate, copy desc / brlen up, copy lnL down.
+static bool lik_tree_walk_enabled() {
+  const char *e = getenv("PLG_TREE_MODE");
+  return !(e && !strcmp(e, "levels"));
+}
+
+void score_lik_desc_walk(LikAln &a, const Model &m, int64_t n_trees, int n_tips, const int32_t *desc,
+                         const double *brlen, const int32_t *tip_rows, double *out_lnl, cudaStream_t st) {
+  if (n_trees == 0) return;
+  StageTimer tm;
+  validate_desc(n_trees, n_tips, desc, tip_rows, a.n_rows, true);
+  tm.lap("validate");
+  LikWorkspace &ws = lik_workspace();
+  const int ni = n_tips - 1;
+  const int64_t tiles = a.Ppad / TW_THREADS;
+  int64_t chunk = std::min<int64_t>(n_trees, ((int64_t)1 << 30) / ((int64_t)2 * ni * 512));
+  chunk = std::min<int64_t>(chunk, ((int64_t)512 << 20) / (tiles * 8));
+  chunk = std::max<int64_t>(1, chunk);
+  int dev = 0, n_sm = 148;
+  PLG_CUDA(cudaGetDevice(&dev));
+  PLG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  const int n_blocks = n_sm * PLG_TW_MINB;
+  const int levels = walk_levels(n_tips);
+  ws.tw_desc.alloc((size_t)chunk * ni * 2);
+  ws.brlen.alloc((size_t)chunk * ni * 2 + 1);
+  ws.tw_ops.alloc((size_t)chunk * ni);
+  ws.tw_scratch.alloc((size_t)chunk * (3 * (size_t)ni + 2));
+  ws.tw_rows.alloc((size_t)n_tips);
+  ws.pmat.alloc((size_t)chunk * 2 * ni * 64);
+  ws.walk_stack.alloc((size_t)n_blocks * levels * 16 * TW_THREADS);
+  ws.walk_stack_scl.alloc((size_t)n_blocks * levels * TW_THREADS);
+  ws.walk_counter.alloc(1);
+  ws.partial.alloc((size_t)chunk * tiles);
+  ws.lnl.alloc((size_t)chunk);
+  if (tip_rows)
+    PLG_CUDA(cudaMemcpyAsync(ws.tw_rows.p, tip_rows, (size_t)n_tips * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  const double Cb = 132.0;
+  for (int64_t t0 = 0; t0 < n_trees; t0 += chunk) {
+    const int64_t cnt = std::min(chunk, n_trees - t0);
+    const int64_t n_slots = cnt * 2 * ni;
+    PLG_CUDA(cudaMemcpyAsync(ws.tw_desc.p, desc + (size_t)t0 * ni * 2, (size_t)n_slots * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, st));
+    PLG_CUDA(cudaMemcpyAsync(ws.brlen.p, brlen + (size_t)t0 * ni * 2, (size_t)n_slots * sizeof(double),
+                             cudaMemcpyHostToDevice, st));
+    PLG_CUDA(cudaMemsetAsync(ws.walk_counter.p, 0, sizeof(unsigned long long), st));
+    launch_plan_walk(cnt, n_tips, ws.tw_desc.p, tip_rows ? ws.tw_rows.p : nullptr, a.n_rows,
+                     reinterpret_cast<WalkOp *>(ws.tw_ops.p), ws.tw_scratch.p, st);
+    prof_begin(PROF_PMATRIX, st);
+    pmatrix4_slots_kernel<<<(unsigned)((n_slots + 3) / 4), 256, 0, st>>>(m.d.p, ws.brlen.p, n_slots, 2 * ni, ws.pmat.p);
+    count_launch();
+    prof_end(PROF_PMATRIX, st, (double)n_slots * 64 * 8.0, (double)n_slots);
+    prof_begin(PROF_CLV_UPDATE, st);
+    twalk4_kernel<<<n_blocks, TW_THREADS, 0, st>>>(reinterpret_cast<const WalkOp *>(ws.tw_ops.p), ni, (int)cnt,
+                                                  (unsigned long long)(cnt * tiles), a.Ppad, a.codes.p, a.weights.p,
+                                                  m.d.p, ws.pmat.p, ws.walk_stack.p, ws.walk_stack_scl.p, levels,
+                                                  ws.partial.p, (int)tiles, ws.walk_counter.p);
+    count_launch();
+    // algorithmic bytes: every non-root node-op writes its CLV once and it is read
+    // once, tips 1 byte, weight 8 bytes; requested: tips + weight (stack traffic stays in L2)
+    prof_end(PROF_CLV_UPDATE, st, (double)cnt * (double)a.P * (2.0 * (ni - 1) * Cb + n_tips + 8.0),
+             (double)cnt * ni * (double)a.P, (double)cnt * (double)a.P * (n_tips + 8.0));
+    reduce_partials_kernel<<<(unsigned)((cnt + 7) / 8), 256, 0, st>>>((int)cnt, (int)tiles, ws.partial.p, ws.lnl.p);
+    count_launch();
+    PLG_CUDA(cudaGetLastError());
+    PLG_CUDA(cudaMemcpyAsync(out_lnl + t0, ws.lnl.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+    PLG_CUDA(cudaStreamSynchronize(st));
+    tm.lap("walk chunk");
+  }
+}
+
 }  // namespace plg
 
 // ----------------------------------------------------------------------------
@@ -830,6 +903,11 @@ extern "C" int plg_lik_score_trees(plg_lik_aln *aln, plg_model *m, int64_t n_tre
                                    const double *brlen, const int32_t *tip_rows, double *out_lnl, void *stream) {
   PLG_API_BEGIN_LOCKED
   if (!aln || !m || !out_lnl || (n_trees > 0 && (!desc || !brlen))) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  if (aln->impl.K == 4 && m->impl.K == 4 && m->impl.R == 4 && lik_tree_walk_enabled() && n_tips >= 2 &&
+      n_tips <= (1 << WALK_MAX_LEVELS)) {
+    score_lik_desc_walk(aln->impl, m->impl, n_trees, n_tips, desc, brlen, tip_rows, out_lnl, (cudaStream_t)stream);
+    return PLG_OK;
+  }
   TreeBatch b = batch_from_desc(n_trees, n_tips, desc, brlen, tip_rows);
   for (int32_t c : b.child)
     if (c >= aln->impl.n_rows) PLG_FAIL(PLG_ERR_ARG, "tip row %d is outside the alignment (%d rows)", c, aln->impl.n_rows);

@@ -51,6 +51,10 @@ struct LikWorkspace {
   DevBuf<double> walk_stack;   // [warp][level][16][32]
   DevBuf<int> walk_stack_scl;  // [warp][level][32]
   DevBuf<unsigned long long> walk_counter;
+  DevBuf<int32_t> tw_desc;     // tree walks (treewalk.h): raw descriptors, planned ops, planner scratch
+  DevBuf<int4> tw_ops;
+  DevBuf<int> tw_scratch;
+  DevBuf<int32_t> tw_rows;
   DevBuf<LikEval> evals;
   DevBuf<double> partial;  // [eval][blocks]
   DevBuf<double> lnl;      // [tree]
