@@ -262,7 +262,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     L.plg_profile_enable(1)
-    for k in range(4):
+    for k in range(5):
         L.plg_profile_read(k, None, None, None, None, None)
     launches0 = L.plg_launch_count()
     total_ms = 0.0
@@ -292,12 +292,12 @@ def run_ours(args):
     # per-kernel roofline (events recorded by the library around every launch of the timed steps)
     import ctypes as C
     prof = {}
-    for k, name in enumerate(("fitch_level_kernel", "clv_update_kernel", "root_eval_kernel", "pmatrix_kernel")):
+    for k, name in enumerate(("fitch_level_kernel", "clv4_kernel", "eval4_kernel", "pmatrix_kernel", "walk4m_kernel")):
         ms, by, un, n, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
         L.plg_profile_read(k, C.byref(ms), C.byref(by), C.byref(un), C.byref(n), C.byref(rq))
         prof[name] = {"ms": ms.value, "bytes": by.value, "units": un.value, "launches": n.value, "requested": rq.value}
     peak, peak_src = measured_peaks()
-    dom = max(("clv_update_kernel", "root_eval_kernel"), key=lambda k: prof[k]["ms"])
+    dom = max(("walk4m_kernel", "clv4_kernel", "eval4_kernel"), key=lambda k: prof[k]["ms"])
 
     def roof(name):
         p = prof[name]
@@ -399,61 +399,67 @@ def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
 
 
 def streaming_leg(fitch, likelihood, L, peak, peak_src):
-    """Full re-traversal of descriptor batches (plg_*_score_trees), the formulation whose working set
-    is far beyond L2: BASELINE config-4 shape for lnL (128 taxa x 1M sites, 3 random trees, 50 GB of
-    CLVs) and config-3 shape for Fitch (256 taxa x 100k sites, 2048 random trees, 26 GB of state
-    sets).  This is where the kernels meet the HBM roofline proper."""
+    """Descriptor batches (plg_*_score_trees) at BASELINE config-4 shape for lnL (128 taxa x 1M sites)
+    and config-3 shape for Fitch (256 taxa x 100k sites, 2048 random trees).  Two formulations each:
+    `tree_walk` (shipped: whole post-order on chip, HBM only supplies the tips -- FP64 / integer
+    pipe bound, algorithmic-bytes fraction > 1) and `levels` (PLG_TREE_MODE=levels: one launch per
+    tree level, every node vector through HBM -- the plain HBM-roofline evidence for the streaming
+    kernels, working set far beyond L2)."""
     import ctypes as C
     import torch
     res = {}
 
     def read(kind):
-        ms, by, un, nl = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
-        L.plg_profile_read(kind, C.byref(ms), C.byref(by), C.byref(un), C.byref(nl), None)
-        return ms.value, by.value, nl.value
+        ms, by, un, nl, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
+        L.plg_profile_read(kind, C.byref(ms), C.byref(by), C.byref(un), C.byref(nl), C.byref(rq))
+        return ms.value, by.value, nl.value, rq.value
+
+    def leg(call, n_units, kinds, kernel, workload):
+        for _ in range(2):
+            call()
+        L.plg_profile_enable(1)
+        for k in kinds:
+            read(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        kms = by = nl = rq = 0
+        for k in kinds:
+            a, b, c, d = read(k)
+            kms += a; by += b; nl += c; rq += d
+        L.plg_profile_enable(0)
+        ach = by / (kms * 1e-3) / 1e9
+        return {"workload": workload, "value": n_units / dt, "unit": UNIT, "ms_per_call": dt * 1e3,
+                "roofline": {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                             "frac": ach / peak, "requested_gbs": rq / (kms * 1e-3) / 1e9, "launches": nl // 3,
+                             "kernel_ms_per_call": kms / 3, "peak_source": peak_src}}
 
     rng = np.random.default_rng(1004)
-    n, S, T = 128, 1_000_000, 3
+    n, S = 128, 1_000_000
     codes = (1 << rng.integers(0, 4, (n, S))).astype(np.uint8)
     la = likelihood.LikAlignment(codes, np.ones(S))
     m = likelihood.Model(EXCH, FREQS, ALPHA)
-    descs = np.stack([random_desc(rng, n) for _ in range(T)])
+    descs = np.stack([random_desc(rng, n) for _ in range(16)])
     brs = rng.exponential(0.1, descs.shape)
-    for _ in range(2):
-        la.score_trees(m, descs, brs)
-    L.plg_profile_enable(1)
-    read(1)
-    t0 = time.perf_counter()
-    for _ in range(3):
-        la.score_trees(m, descs, brs)
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / 3
-    kms, by, nl = read(1)
-    ach = by / (kms * 1e-3) / 1e9
-    res["lnl_retraversal"] = {"workload": "128 taxa x 1M sites, GTR+G4, %d random trees per call (BASELINE configs[3] shape)" % T,
-                              "value": T * S / dt, "unit": UNIT, "ms_per_call": dt * 1e3,
-                              "roofline": {"kernel": "clv4_kernel (unfused)", "bound": "hbm", "achieved": ach, "peak": peak,
-                                           "unit": "GB/s", "frac": ach / peak, "launches": nl, "peak_source": peak_src}}
+    for mode, T, kinds, kernel in (("walk", 16, (4,), "twalk4_kernel"), ("levels", 3, (1, 2), "clv4_kernel + eval4_kernel")):
+        os.environ["PLG_TREE_MODE"] = mode
+        res["lnl_" + ("tree_walk" if mode == "walk" else "levels")] = leg(
+            lambda: la.score_trees(m, descs[:T], brs[:T]), T * S, kinds, kernel,
+            "128 taxa x 1M sites, GTR+G4, %d random trees per call (BASELINE configs[3] shape)" % T)
     la.close()
     n, S, T = 256, 100_000, 2048
     states = (rng.integers(0, 4, (S, n)) + 48).astype(np.uint8)
     fa = fitch.FitchAlignment.from_dense(states, np.ones(S, dtype=np.int64))
     descs = np.stack([random_desc(rng, n) for _ in range(T)])
-    for _ in range(2):
-        fa.score_trees(descs)
-    read(0)
-    t0 = time.perf_counter()
-    for _ in range(3):
-        fa.score_trees(descs)
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / 3
-    kms, by, nl = read(0)
-    L.plg_profile_enable(0)
-    ach = by / (kms * 1e-3) / 1e9
-    res["fitch_retraversal"] = {"workload": "256 taxa x 100k sites, %d random trees per call (BASELINE configs[2] shape)" % T,
-                                "value": T * S / dt, "unit": UNIT, "ms_per_call": dt * 1e3,
-                                "roofline": {"kernel": "fitch_level_kernel", "bound": "hbm", "achieved": ach, "peak": peak,
-                                             "unit": "GB/s", "frac": ach / peak, "launches": nl, "peak_source": peak_src}}
+    for mode, kernel in (("walk", "fitch_walk_kernel"), ("levels", "fitch_level_kernel")):
+        os.environ["PLG_TREE_MODE"] = mode
+        res["fitch_" + ("tree_walk" if mode == "walk" else "levels")] = leg(
+            lambda: fa.score_trees(descs), T * S, (0,), kernel,
+            "256 taxa x 100k sites, %d random trees per call (BASELINE configs[2] shape)" % T)
+    os.environ.pop("PLG_TREE_MODE", None)
     fa.close()
     return res
 

@@ -49,7 +49,8 @@ int plg_set_device(int device);
 int64_t plg_launch_count(void);
 /* Per-kernel timing for the roofline report: CUDA events recorded on the launching stream
  * around every launch while enabled.  kind: 0 Fitch node-ops, 1 CLV update, 2 root/3-way
- * evaluation, 3 P-matrices.  plg_profile_read sums and clears one kind: device ms,
+ * evaluation, 3 P-matrices, 4 depth-first likelihood walks (SPR search walks, tree walks).
+ * plg_profile_read sums and clears one kind: device ms,
  * algorithmic bytes (SURVEY.md 8d per-node-op figures, unaffected by fusion or operand
  * sharing), node-op x pattern units, launches, and the bytes the kernels actually requested. */
 int plg_profile_enable(int on);

@@ -25,9 +25,9 @@ for mode in modes:
     os.environ["PLG_TREE_MODE"] = mode
     Tm = T if mode == "walk" else min(T, 3)
     la.score_trees(m, descs[:Tm], brs[:Tm])
-    L.plg_profile_enable(1); prof(1); prof(2)
+    L.plg_profile_enable(1); prof(1); prof(2); prof(4)
     t = time.perf_counter(); out = la.score_trees(m, descs[:Tm], brs[:Tm]); dt = time.perf_counter() - t
-    ms, by, nl = prof(1); ems, eby, enl = prof(2)
+    ms, by, nl = prof(1); ems, eby, enl = prof(2); wms, wby, wnl = prof(4); ms += wms; by += wby; nl += wnl
     L.plg_profile_enable(0)
     ref = out if ref is None else ref
     print("lnL 128x1M x%d trees [%s]: call %.1f ms = %.2f ms/tree (%.3g tree-sites/s); kernels %.1f ms, %.0f GB/s algorithmic (%d launches); maxrel %.1e" % (

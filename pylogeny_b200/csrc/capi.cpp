@@ -16,6 +16,21 @@ void set_error(const char *fmt, ...) {
 }
 }  // namespace plg
 
+namespace plg {
+// keep freed blocks in the pool of every device this process touches
+void pool_setup_once() {
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || done[dev & 63]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[dev & 63] = true;
+}
+}  // namespace plg
+
 extern "C" const char *plg_last_error(void) { return plg::g_err; }
 extern "C" int plg_version(void) { return 100; }
 extern "C" int64_t plg_launch_count(void) { return plg::g_launches.load(); }

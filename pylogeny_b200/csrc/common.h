@@ -60,7 +60,7 @@ struct Error {
 inline void count_launch(int64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
-enum ProfKind { PROF_FITCH_OPS = 0, PROF_CLV_UPDATE = 1, PROF_ROOT_EVAL = 2, PROF_PMATRIX = 3, PROF_KINDS = 4 };
+enum ProfKind { PROF_FITCH_OPS = 0, PROF_CLV_UPDATE = 1, PROF_ROOT_EVAL = 2, PROF_PMATRIX = 3, PROF_WALK = 4, PROF_KINDS = 5 };
 void prof_begin(int kind, cudaStream_t st);
 // algorithmic_bytes: SURVEY.md 8d per-node-op figures (independent of fusion / operand sharing);
 // requested_bytes: what this implementation actually loads and stores (< 0: same as algorithmic)
@@ -75,17 +75,23 @@ struct StageTimer {
   void lap(const char *what);
 };
 
-// Owning device buffer.
+// Owning device buffer.  Small buffers (< 64 MB: alignment handles, op programs) come from the
+// device's stream-ordered memory pool, which keeps freed blocks, so creating and destroying a handle
+// does not pay cudaMalloc / cudaFree each time; the multi-GB scratch pools use cudaMalloc so that
+// what they give back is visible to cudaMemGetInfo.  Every use of a buffer is complete when it is
+// released: compute entry points synchronise their stream before returning.
+void pool_setup_once();
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  bool pooled = false;
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) { if (pooled) cudaFreeAsync(p, 0); else cudaFree(p); }
     p = nullptr;
     n = 0;
   }
@@ -93,7 +99,13 @@ struct DevBuf {
     if (count <= n && p) return;
     release();
     if (count == 0) return;
-    PLG_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    pooled = count * sizeof(T) < ((size_t)64 << 20);
+    if (pooled) {
+      pool_setup_once();
+      PLG_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), 0));
+    } else {
+      PLG_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    }
     n = count;
   }
 };

@@ -254,6 +254,7 @@ constexpr int DNA4_PATTERNS_PER_BLOCK = PLG_DNA4_WARP_PER_RATE ? R4_PATTERNS : D
 #include "lik_aa.cuh"
 #include "lik_visit.cuh"
 #include "lik_walk.cuh"
+#include "lik_walkm.cuh"
 #include "lik_twalk.cuh"
 namespace plg {
 
@@ -282,13 +283,19 @@ LikAln::LikAln(int datatype, int n_rows_, int64_t P_, const uint8_t *h_codes, co
   const int64_t tile = LIK_THREADS;  // multiple of LIK_THREADS / R for every supported R
   Ppad = std::max<int64_t>(tile, (P + tile - 1) / tile * tile);
   const uint8_t any = (uint8_t)(K == 4 ? 15 : 22);
-  std::vector<uint8_t> padded((size_t)n_rows * Ppad, any);
-  for (int r = 0; r < n_rows; r++)
-    for (int64_t p = 0; p < P; p++) {
-      uint8_t c = h_codes[(size_t)r * P + p];
-      if (c >= n_codes) PLG_FAIL(PLG_ERR_ARG, "tip code %d at row %d pattern %lld is out of range", c, r, (long long)p);
-      padded[(size_t)r * Ppad + p] = c;
-    }
+  std::vector<uint8_t> padded((size_t)n_rows * Ppad);
+  for (int r = 0; r < n_rows; r++) {
+    const uint8_t *src = h_codes + (size_t)r * P;
+    uint8_t *dst = padded.data() + (size_t)r * Ppad;
+    uint8_t mx = 0;
+    for (int64_t p = 0; p < P; p++) mx = std::max(mx, src[p]);  // vectorised range check
+    if (mx >= n_codes)
+      for (int64_t p = 0; p < P; p++)
+        if (src[p] >= n_codes)
+          PLG_FAIL(PLG_ERR_ARG, "tip code %d at row %d pattern %lld is out of range", src[p], r, (long long)p);
+    memcpy(dst, src, (size_t)P);
+    memset(dst + P, any, (size_t)(Ppad - P));
+  }
   std::vector<double> w(Ppad, 0.0);
   for (int64_t p = 0; p < P; p++) w[p] = h_w[p];
   codes.alloc(padded.size());
@@ -472,6 +479,7 @@ static int64_t dna4_partial_stride(const LikAln &a) { return a.Ppad / (PLG_DNA4_
 
 static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, cudaStream_t st) {
   constexpr int K = 4, R = 4, KKP = 17, NC = 16;
+  StageTimer tm;
   const int n_pm = (int)prog.brlens.size();
   ws.pmat.alloc(std::max<size_t>(1, (size_t)n_pm * R * KKP));
   ws.tiptab.alloc(std::max<size_t>(1, (size_t)n_pm * NC * R * K));
@@ -483,6 +491,7 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     count_launch();
     prof_end(PROF_PMATRIX, st, (double)n_pm * (R * KKP + NC * R * K) * 8.0, n_pm);
   }
+  tm.lap("    pmatrix");
   // ---- fusion pass (host) ----
   const int64_t n_ops = (int64_t)prog.ops.size();
   std::vector<LikOpF> fops(n_ops);
@@ -526,6 +535,7 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     PLG_CUDA(cudaMemcpyAsync(ws.fops.p, fops.data(), (size_t)n_ops * sizeof(LikOpF), cudaMemcpyHostToDevice, st));
   if (!rest.empty())
     PLG_CUDA(cudaMemcpyAsync(ws.evals.p, rest.data(), rest.size() * sizeof(LikEval), cudaMemcpyHostToDevice, st));
+  tm.lap("    fuse+upload");
   const int64_t bpo = a.Ppad / DNA4_PATTERNS_PER_BLOCK;
   // finest block tiling among the kernels below (search walks reduce per 32-pattern slice)
   const int64_t pstride = prog.walk_visits.empty() ? dna4_partial_stride(a) : a.Ppad / 32;
@@ -616,18 +626,22 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, 2.0 * (double)cnt * (double)a.P, req * (double)a.P);
     }
   }
+  tm.lap("    level launches");
   // depth-first search walks: one persistent launch, a warp per (pattern slice, pruned subtree)
   if (!prog.walk_visits.empty()) {
     int dev = 0, n_sm = 148;
     PLG_CUDA(cudaGetDevice(&dev));
     PLG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const int n_blocks = n_sm * PLG_WK_MINB;
+    // PLG_LIK_NB_MODE=walk: scalar FP64 walk (lik_walk.cuh); default: the DMMA walk (lik_walkm.cuh)
+    const char *mode_env = getenv("PLG_LIK_NB_MODE");
+    const bool dmma = !(mode_env && !strcmp(mode_env, "walk"));
+    const int n_blocks = n_sm * (dmma ? PLG_WM_MINB : PLG_WK_MINB);
     const int64_t n_warps = (int64_t)n_blocks * WK_WARPS;
     const int levels = std::max(1, prog.walk_levels);
     ws.walk_visits.alloc(prog.walk_visits.size());
     ws.walk_groups.alloc(prog.walk_groups.size());
     ws.walk_stack.alloc((size_t)n_warps * levels * 16 * 32);
-    ws.walk_stack_scl.alloc((size_t)n_warps * levels * 32);
+    ws.walk_stack_scl.alloc((size_t)n_warps * levels * 4 * 32);
     ws.walk_counter.alloc(1);
     PLG_CUDA(cudaMemcpyAsync(ws.walk_visits.p, prog.walk_visits.data(), prog.walk_visits.size() * sizeof(LikWalkVisit),
                              cudaMemcpyHostToDevice, st));
@@ -654,19 +668,29 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       }
     }
     const int64_t n_items = (a.Ppad / 32) * (int64_t)prog.walk_groups.size();
-    prof_begin(PROF_CLV_UPDATE, st);
-    static bool walk_attr_set = false;
-    if (!walk_attr_set) {
-      PLG_CUDA(cudaFuncSetAttribute(walk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WK_SMEM_BYTES));
-      walk_attr_set = true;
+    prof_begin(PROF_WALK, st);
+    if (dmma) {
+      const int smem = WM_WARPS * WM_SMEM_DOUBLES_PER_WARP * 8;
+      walk4m_kernel<<<n_blocks, WM_THREADS, smem, st>>>(ws.walk_groups.p, (int)prog.walk_groups.size(), ws.walk_visits.p,
+                                                       n_items, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p,
+                                                       ws.pmat.p, ws.clv.p, ws.scl.p, ws.walk_stack.p,
+                                                       ws.walk_stack_scl.p, levels, ws.partial.p, (int)pstride,
+                                                       ws.walk_counter.p);
+    } else {
+      static bool walk_attr_set = false;
+      if (!walk_attr_set) {
+        PLG_CUDA(cudaFuncSetAttribute(walk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WK_SMEM_BYTES));
+        walk_attr_set = true;
+      }
+      walk4_kernel<<<n_blocks, WK_THREADS, WK_SMEM_BYTES, st>>>(ws.walk_groups.p, (int)prog.walk_groups.size(),
+                                                               ws.walk_visits.p, n_items, a.n_rows, a.Ppad, a.codes.p,
+                                                               a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p, ws.clv.p,
+                                                               ws.scl.p, ws.walk_stack.p, ws.walk_stack_scl.p, levels,
+                                                               ws.partial.p, (int)pstride, ws.walk_counter.p);
     }
-    walk4_kernel<<<n_blocks, WK_THREADS, WK_SMEM_BYTES, st>>>(ws.walk_groups.p, (int)prog.walk_groups.size(), ws.walk_visits.p,
-                                                  n_items, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p, ws.pmat.p,
-                                                  ws.tiptab.p, ws.clv.p, ws.scl.p, ws.walk_stack.p,
-                                                  ws.walk_stack_scl.p, levels, ws.partial.p, (int)pstride,
-                                                  ws.walk_counter.p);
     count_launch();
-    prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, units * (double)a.P, req * (double)a.P);
+    prof_end(PROF_WALK, st, bytes * (double)a.P, units * (double)a.P, req * (double)a.P);
+    tm.lap("    walk launch");
   }
   if (prog.n_trees) {
     reduce_partials_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, (int)pstride,
@@ -755,8 +779,10 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   else PLG_FAIL(PLG_ERR_UNSUPPORTED, "kernels exist for 4 or 20 states with 1 or 4 rate categories");
   PLG_CUDA(cudaGetLastError());
   if (out_lnl && prog.n_trees) {
+    StageTimer tm;
     PLG_CUDA(cudaMemcpyAsync(out_lnl, ws.lnl.p, (size_t)prog.n_trees * 8, cudaMemcpyDeviceToHost, st));
     PLG_CUDA(cudaStreamSynchronize(st));
+    tm.lap("    sync+D2H");
   }
 }
 
@@ -838,15 +864,20 @@ void score_lik_desc_walk(LikAln &a, const Model &m, int64_t n_trees, int n_tips,
     pmatrix4_slots_kernel<<<(unsigned)((n_slots + 3) / 4), 256, 0, st>>>(m.d.p, ws.brlen.p, n_slots, 2 * ni, ws.pmat.p);
     count_launch();
     prof_end(PROF_PMATRIX, st, (double)n_slots * 64 * 8.0, (double)n_slots);
-    prof_begin(PROF_CLV_UPDATE, st);
-    twalk4_kernel<<<n_blocks, TW_THREADS, 0, st>>>(reinterpret_cast<const WalkOp *>(ws.tw_ops.p), ni, (int)cnt,
+    prof_begin(PROF_WALK, st);
+    static bool tw_attr_set = false;
+    if (!tw_attr_set) {
+      PLG_CUDA(cudaFuncSetAttribute(twalk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM_BYTES));
+      tw_attr_set = true;
+    }
+    twalk4_kernel<<<n_blocks, TW_THREADS, TW_SMEM_BYTES, st>>>(reinterpret_cast<const WalkOp *>(ws.tw_ops.p), ni, (int)cnt,
                                                   (unsigned long long)(cnt * tiles), a.Ppad, a.codes.p, a.weights.p,
                                                   m.d.p, ws.pmat.p, ws.walk_stack.p, ws.walk_stack_scl.p, levels,
                                                   ws.partial.p, (int)tiles, ws.walk_counter.p);
     count_launch();
     // algorithmic bytes: every non-root node-op writes its CLV once and it is read
     // once, tips 1 byte, weight 8 bytes; requested: tips + weight (stack traffic stays in L2)
-    prof_end(PROF_CLV_UPDATE, st, (double)cnt * (double)a.P * (2.0 * (ni - 1) * Cb + n_tips + 8.0),
+    prof_end(PROF_WALK, st, (double)cnt * (double)a.P * (2.0 * (ni - 1) * Cb + n_tips + 8.0),
              (double)cnt * ni * (double)a.P, (double)cnt * (double)a.P * (n_tips + 8.0));
     reduce_partials_kernel<<<(unsigned)((cnt + 7) / 8), 256, 0, st>>>((int)cnt, (int)tiles, ws.partial.p, ws.lnl.p);
     count_launch();

@@ -39,22 +39,57 @@ __global__ void pmatrix4_slots_kernel(const ModelDev *__restrict__ model, const 
   pmat[slot * 64 + e] = s;
 }
 
-// both matrices of a node-op (child slots `slot`, `slot + 1`): P as [r][k][j] and, for tip
-// operands, its transpose [r][j][k] (a tip's column of P as two 16-byte reads per category)
-__device__ __forceinline__ void tw_stage(double *buf, const double *__restrict__ pm, int slot) {
+// Both matrices of a node-op (child slots `slot`, `slot + 1`): each thread fetches one element
+// early (tw_fetch, while the previous node-op computes) and files it late (tw_file): P as
+// [r][k][j] and, for tip operands, its transpose [r][j][k] (a tip's column of P is then two
+// 16-byte reads per category).
+__device__ __forceinline__ double tw_fetch(const double *__restrict__ pm, int slot) {
+  return __ldg(pm + ((int64_t)slot + (threadIdx.x >> 6)) * 64 + (threadIdx.x & 63));
+}
+__device__ __forceinline__ void tw_file(double *buf, double x) {
   const int m = threadIdx.x >> 6, e = threadIdx.x & 63;
-  const double x = __ldg(pm + ((int64_t)slot + m) * 64 + e);
   buf[m * 128 + e] = x;
   buf[m * 128 + 64 + (e & 48) + ((e & 3) << 2) + ((e >> 2) & 3)] = x;
 }
 
-// v (*)= P x for one operand of a node-op
+constexpr int TW_SMEM_LEVELS = 2;  // stack levels kept in shared memory (the rest: global, L2-resident)
+
+// parked CLV column `l`: shared memory for the lowest levels, the block's global stack above
+struct TwStack {
+  double *sm;   // [TW_SMEM_LEVELS][16][TW_THREADS] + this thread
+  int *sms;     // [TW_SMEM_LEVELS][TW_THREADS] + this thread
+  double *gl;   // global [levels][16][TW_THREADS] + this thread
+  int *gls;
+  __device__ __forceinline__ void load(int l, double (&x)[16], int &sc) const {
+    if (l < TW_SMEM_LEVELS) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) x[i] = sm[(l * 16 + i) * TW_THREADS];
+      sc += sms[l * TW_THREADS];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i++) x[i] = gl[(l * 16 + i) * TW_THREADS];
+      sc += gls[l * TW_THREADS];
+    }
+  }
+  __device__ __forceinline__ void store(int l, const double (&x)[16], int sc) const {
+    if (l < TW_SMEM_LEVELS) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) sm[(l * 16 + i) * TW_THREADS] = x[i];
+      sms[l * TW_THREADS] = sc;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i++) gl[(l * 16 + i) * TW_THREADS] = x[i];
+      gls[l * TW_THREADS] = sc;
+    }
+  }
+};
+
+// v (*)= P x for one operand of a node-op; `code` = the tip's code when id >= 0 (fetched one
+// node-op ahead)
 template <bool MUL>
-__device__ __forceinline__ void tw_operand(int id, const double *M, int64_t p, int64_t Ppad,
-                                           const unsigned char *__restrict__ codes, const double (&top)[16], int sct,
-                                           const double *stk, const int *stks, double (&v)[16], int &sc) {
+__device__ __forceinline__ void tw_operand(int id, int code, const double *M, const double (&top)[16], int sct,
+                                           const TwStack &stk, double (&v)[16], int &sc) {
   if (id >= 0) {
-    const int code = codes[(int64_t)id * Ppad + p];
     const int mask = code ? code : 15;
     if (__all_sync(0xffffffffu, (mask & (mask - 1)) == 0)) {  // unambiguous: one column of P
       const double *col = M + 64 + ((__ffs(mask) - 1) << 2);
@@ -75,14 +110,13 @@ __device__ __forceinline__ void tw_operand(int id, const double *M, int64_t p, i
     v4_apply_reg<MUL>(M, top, v);
     sc += sct;
   } else {
-    const int l = -2 - id;
     double x[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) x[i] = stk[(l * 16 + i) * TW_THREADS];
-    sc += stks[l * TW_THREADS];
+    stk.load(-2 - id, x, sc);
     v4_apply_reg<MUL>(M, x, v);
   }
 }
+
+constexpr int TW_SMEM_BYTES = (2 * 256 + TW_SMEM_LEVELS * 16 * TW_THREADS) * 8 + TW_SMEM_LEVELS * TW_THREADS * 4;
 
 __global__ void __launch_bounds__(TW_THREADS, PLG_TW_MINB)
 twalk4_kernel(const WalkOp *__restrict__ ops, int ni, int n_trees, unsigned long long n_items, int64_t Ppad,
@@ -90,11 +124,15 @@ twalk4_kernel(const WalkOp *__restrict__ ops, int ni, int n_trees, unsigned long
               const ModelDev *__restrict__ model, const double *__restrict__ pmat, double *__restrict__ stack,
               int *__restrict__ stack_scl, int levels, double *__restrict__ partial, int pstride,
               unsigned long long *counter) {
-  __shared__ __align__(16) double mats[2][256];  // [buffer][a: P, P^T | b: P, P^T]
+  extern __shared__ __align__(16) double tw_smem[];
+  double(*mats)[256] = reinterpret_cast<double(*)[256]>(tw_smem);  // [buffer][a: P, P^T | b: P, P^T]
   __shared__ unsigned long long s_item;
   __shared__ double wsum[TW_THREADS / 32];
-  double *stk = stack + (int64_t)blockIdx.x * levels * 16 * TW_THREADS + threadIdx.x;
-  int *stks = stack_scl + (int64_t)blockIdx.x * levels * TW_THREADS + threadIdx.x;
+  TwStack stk;
+  stk.sm = tw_smem + 2 * 256 + threadIdx.x;
+  stk.sms = reinterpret_cast<int *>(tw_smem + 2 * 256 + TW_SMEM_LEVELS * 16 * TW_THREADS) + threadIdx.x;
+  stk.gl = stack + (int64_t)blockIdx.x * levels * 16 * TW_THREADS + threadIdx.x;
+  stk.gls = stack_scl + (int64_t)blockIdx.x * levels * TW_THREADS + threadIdx.x;
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(counter, 1ull);
     __syncthreads();
@@ -102,12 +140,15 @@ twalk4_kernel(const WalkOp *__restrict__ ops, int ni, int n_trees, unsigned long
     if (item >= n_items) break;
     const int64_t tile = (int64_t)(item / (unsigned)n_trees);
     const int tree = (int)(item - (unsigned long long)tile * (unsigned)n_trees);
-    const int64_t p = tile * TW_THREADS + threadIdx.x;
+    const unsigned char *cp = codes + tile * TW_THREADS + threadIdx.x;
     const int4 *op_p = reinterpret_cast<const int4 *>(ops + (int64_t)tree * ni);
     const double *pm = pmat + (int64_t)tree * 2 * ni * 64;
-    int4 nxt = __ldg(op_p);
-    tw_stage(mats[0], pm, nxt.w);
-    const double w = weights[p];
+    // software pipeline: descriptors two node-ops ahead, tip codes and matrix elements one ahead
+    int4 op = __ldg(op_p);
+    int4 nxt = ni > 1 ? __ldg(op_p + 1) : op;
+    tw_file(mats[0], tw_fetch(pm, op.w));
+    int ca = op.x >= 0 ? cp[(int64_t)op.x * Ppad] : 0, cb = op.y >= 0 ? cp[(int64_t)op.y * Ppad] : 0;
+    const double w = weights[tile * TW_THREADS + threadIdx.x];
     __syncthreads();
     double top[16];
     int sct = 0;
@@ -115,33 +156,36 @@ twalk4_kernel(const WalkOp *__restrict__ ops, int ni, int n_trees, unsigned long
     for (int i = 0; i < 16; i++) top[i] = 0.0;
     double val = 0.0;
     for (int i = 0; i < ni; i++) {
-      const int4 op = nxt;
-      if (i + 1 < ni) {
-        nxt = __ldg(op_p + i + 1);
-        tw_stage(mats[(i + 1) & 1], pm, nxt.w);
+      const bool more = i + 1 < ni;
+      int4 nxt2 = nxt;
+      double melt = 0.0;
+      int na = 0, nb = 0;
+      if (more) {
+        if (i + 2 < ni) nxt2 = __ldg(op_p + i + 2);
+        melt = tw_fetch(pm, nxt.w);
+        if (nxt.x >= 0) na = cp[(int64_t)nxt.x * Ppad];
+        if (nxt.y >= 0) nb = cp[(int64_t)nxt.y * Ppad];
       }
       const double *MA = mats[i & 1], *MB = mats[i & 1] + 128;
       double v[16];
       int sc = 0;
-      if (i + 1 < ni) {
-        tw_operand<false>(op.x, MA, p, Ppad, codes, top, sct, stk, stks, v, sc);
-        tw_operand<true>(op.y, MB, p, Ppad, codes, top, sct, stk, stks, v, sc);
+      if (more) {
+        tw_operand<false>(op.x, ca, MA, top, sct, stk, v, sc);
+        tw_operand<true>(op.y, cb, MB, top, sct, stk, v, sc);
         sc += wk_rescale(v);
         if (op.z >= 0) {
-#pragma unroll
-          for (int q = 0; q < 16; q++) stk[(op.z * 16 + q) * TW_THREADS] = v[q];
-          stks[op.z * TW_THREADS] = sc;
+          stk.store(op.z, v, sc);
         } else {
 #pragma unroll
           for (int q = 0; q < 16; q++) top[q] = v[q];
           sct = sc;
         }
+        tw_file(mats[(i + 1) & 1], melt);
       } else {
         // root: site likelihood across the root branch, sum_k pi_k a_k (P(ta+tb) b)_k
-        tw_operand<false>(op.y, MA, p, Ppad, codes, top, sct, stk, stks, v, sc);
+        tw_operand<false>(op.y, cb, MA, top, sct, stk, v, sc);
         if (op.x >= 0) {
-          const int code = codes[(int64_t)op.x * Ppad + p];
-          const int mask = code ? code : 15;
+          const int mask = ca ? ca : 15;
 #pragma unroll
           for (int q = 0; q < 16; q++) v[q] = (mask >> (q & 3) & 1) ? v[q] : 0.0;
         } else if (op.x == -1) {
@@ -149,13 +193,14 @@ twalk4_kernel(const WalkOp *__restrict__ ops, int ni, int n_trees, unsigned long
           for (int q = 0; q < 16; q++) v[q] *= top[q];
           sc += sct;
         } else {
-          const int l = -2 - op.x;
+          double x[16];
+          stk.load(-2 - op.x, x, sc);
 #pragma unroll
-          for (int q = 0; q < 16; q++) v[q] *= stk[(l * 16 + q) * TW_THREADS];
-          sc += stks[l * TW_THREADS];
+          for (int q = 0; q < 16; q++) v[q] *= x[q];
         }
         val = v4_site(v, sc, w, model);
       }
+      op = nxt; nxt = nxt2; ca = na; cb = nb;
       __syncthreads();
     }
 #pragma unroll

@@ -28,7 +28,7 @@ constexpr int WK_THREADS = 32 * WK_WARPS;
 #ifndef PLG_WK_MINB
 #define PLG_WK_MINB 3
 #endif
-constexpr int WK_SMEM_DOUBLES_PER_WARP = 5 * 64 + 3 * 16 * 32;
+constexpr int WK_SMEM_DOUBLES_PER_WARP = 2 * 5 * 64 + 3 * 16 * 32;  // matrices double-buffered + 3 parked vectors
 constexpr int WK_SMEM_BYTES = WK_WARPS * WK_SMEM_DOUBLES_PER_WARP * 8;
 
 // stage one 4 x (4x4) P-matrix (global stride 17 per category) into this warp's shared memory
@@ -36,6 +36,17 @@ __device__ __forceinline__ void wk_stage_mat(double *sm, int pm, const double *_
   const double *src = pmat + (int64_t)pm * 68;
   sm[lane] = __ldg(src + (lane >> 4) * 17 + (lane & 15));
   sm[lane + 32] = __ldg(src + ((lane + 32) >> 4) * 17 + (lane & 15));
+}
+// the same without a register round trip (cp.async, 8 bytes per copy): issued one visit ahead
+__device__ __forceinline__ void wk_stage_mat_async(double *sm, int pm, const double *__restrict__ pmat, int lane) {
+  const double *src = pmat + (int64_t)pm * 68;
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(sm + lane);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src + (lane >> 4) * 17 + (lane & 15)) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d + 256), "l"(src + ((lane + 32) >> 4) * 17 + (lane & 15)) : "memory");
+}
+// One visit descriptor = 12 ints: lane l < 12 keeps int l, fields are broadcast at the point of use
+__device__ __forceinline__ int wk_desc_load(const LikWalkVisit *__restrict__ visits, int vi, int lane) {
+  return lane < 12 ? __ldg(reinterpret_cast<const int *>(visits + vi) + lane) : 0;
 }
 
 // y = P x for an operand that is either a tip row (table lookup, the table already holds P e_code)
@@ -92,6 +103,10 @@ __device__ __forceinline__ int wk_rescale(double (&n)[16]) {
   return 1;
 }
 
+#ifndef PLG_WK_PIPE
+#define PLG_WK_PIPE 1  // 0: visit descriptors, matrices and codes fetched at the top of each visit (first version)
+#endif
+#if PLG_WK_PIPE
 __global__ void __launch_bounds__(WK_THREADS, PLG_WK_MINB)
 walk4_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWalkVisit *__restrict__ visits,
              int64_t n_items, int n_rows, int64_t Ppad, const unsigned char *__restrict__ codes,
@@ -101,8 +116,182 @@ walk4_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWal
              int stack_levels, double *__restrict__ partial, int pstride, unsigned long long *counter) {
   extern __shared__ __align__(16) double wk_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *mats = wk_smem + warp * WK_SMEM_DOUBLES_PER_WARP;                                      // [5][64]
-  double(*park)[16][32] = reinterpret_cast<double(*)[16][32]>(mats + 5 * 64);  // [0] a = P_in X, [1] tvv = P_v Tv, [2] h1 = P_h1 D1
+  double *mats0 = wk_smem + warp * WK_SMEM_DOUBLES_PER_WARP;                                     // [2][5][64]
+  double(*park)[16][32] = reinterpret_cast<double(*)[16][32]>(mats0 + 2 * 5 * 64);  // [0] a = P_in X, [1] tvv = P_v Tv, [2] h1 = P_h1 D1
+  const int64_t gw = (int64_t)blockIdx.x * WK_WARPS + warp;
+  double *stk = stack_clv + gw * stack_levels * 16 * 32 + lane;
+  int *stks = stack_scl + gw * stack_levels * 32 + lane;
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(counter, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if ((int64_t)item >= n_items) break;
+    const int slice = (int)(item / (unsigned)n_groups);
+    const LikWalkGroup g = groups[item - (unsigned long long)slice * n_groups];
+    const int64_t p = (int64_t)slice * 32 + lane;
+    const unsigned char *cp = codes + p;
+    const int *sp = scl + p;
+    const double w = weights[p];
+    int st = 0;
+    // software pipeline over the visits of this search: descriptor two visits ahead, matrices
+    // (cp.async, double-buffered), tip codes and scaling counters one visit ahead
+    const int v_end = g.first + g.count;
+    int dcur = wk_desc_load(visits, g.first, lane);
+    int dnxt = g.count > 1 ? wk_desc_load(visits, g.first + 1, lane) : 0;
+    __syncwarp();
+    {
+      double *m = mats0;  // buffer 0: first visit (slot 0 doubles as the pruned subtree's matrix first)
+      wk_stage_mat_async(m + 1 * 64, __shfl_sync(0xffffffffu, dcur, 3), pmat, lane);
+      wk_stage_mat_async(m + 2 * 64, __shfl_sync(0xffffffffu, dcur, 4), pmat, lane);
+      wk_stage_mat_async(m + 3 * 64, __shfl_sync(0xffffffffu, dcur, 6), pmat, lane);
+      wk_stage_mat_async(m + 4 * 64, __shfl_sync(0xffffffffu, dcur, 7), pmat, lane);
+    }
+    int c1, c2, s1, s2;
+    {
+      const int d1 = __shfl_sync(0xffffffffu, dcur, 2), d2 = __shfl_sync(0xffffffffu, dcur, 5);
+      c1 = d1 < n_rows ? cp[(int64_t)d1 * Ppad] : 0;
+      c2 = d2 < n_rows ? cp[(int64_t)d2 * Ppad] : 0;
+      s1 = d1 < n_rows ? 0 : sp[(int64_t)(d1 - n_rows) * Ppad];
+      s2 = d2 < n_rows ? 0 : sp[(int64_t)(d2 - n_rows) * Ppad];
+    }
+    {  // the pruned subtree seen through its branch, once per search
+      if (g.tv >= n_rows) { wk_stage_mat(mats0, g.p_v, pmat, lane); st = sp[(int64_t)(g.tv - n_rows) * Ppad]; }
+      const int ct = g.tv < n_rows ? cp[(int64_t)g.tv * Ppad] : 0;
+      __syncwarp();
+      double t[16];
+      wk_operand<false>(mats0, g.tv, g.p_v, n_rows, ct, p, Ppad, tiptab, clv, t);
+#pragma unroll
+      for (int i = 0; i < 16; i++) park[1][i][lane] = t[i];
+      __syncwarp();
+      wk_stage_mat_async(mats0, __shfl_sync(0xffffffffu, dcur, 1), pmat, lane);
+    }
+    double nk[16];  // the partial that continues into the next visit
+    int sck = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) nk[i] = 0.0;
+    for (int vi = g.first; vi < v_end; vi++) {
+      double *mats = mats0 + ((vi - g.first) & 1) * 5 * 64;
+      const int x_in = __shfl_sync(0xffffffffu, dcur, 0), p_in = __shfl_sync(0xffffffffu, dcur, 1);
+      const int d1 = __shfl_sync(0xffffffffu, dcur, 2), p_t1 = __shfl_sync(0xffffffffu, dcur, 3);
+      const int p_h1 = __shfl_sync(0xffffffffu, dcur, 4), d2 = __shfl_sync(0xffffffffu, dcur, 5);
+      const int p_t2 = __shfl_sync(0xffffffffu, dcur, 6), p_h2 = __shfl_sync(0xffffffffu, dcur, 7);
+      const int tree1 = __shfl_sync(0xffffffffu, dcur, 8), tree2 = __shfl_sync(0xffffffffu, dcur, 9);
+      const int keep = __shfl_sync(0xffffffffu, dcur, 10), push = __shfl_sync(0xffffffffu, dcur, 11);
+      // this visit's matrices have landed; start the next visit's copies into the other buffer
+      asm volatile("cp.async.wait_all;\n" ::: "memory");
+      __syncwarp();
+      int dnn = 0, nc1 = 0, nc2 = 0, ns1 = 0, ns2 = 0;
+      if (vi + 1 < v_end) {
+        if (vi + 2 < v_end) dnn = wk_desc_load(visits, vi + 2, lane);
+        double *mn = mats0 + ((vi + 1 - g.first) & 1) * 5 * 64;
+        wk_stage_mat_async(mn + 0 * 64, __shfl_sync(0xffffffffu, dnxt, 1), pmat, lane);
+        wk_stage_mat_async(mn + 1 * 64, __shfl_sync(0xffffffffu, dnxt, 3), pmat, lane);
+        wk_stage_mat_async(mn + 2 * 64, __shfl_sync(0xffffffffu, dnxt, 4), pmat, lane);
+        wk_stage_mat_async(mn + 3 * 64, __shfl_sync(0xffffffffu, dnxt, 6), pmat, lane);
+        wk_stage_mat_async(mn + 4 * 64, __shfl_sync(0xffffffffu, dnxt, 7), pmat, lane);
+        const int e1 = __shfl_sync(0xffffffffu, dnxt, 2), e2 = __shfl_sync(0xffffffffu, dnxt, 5);
+        nc1 = e1 < n_rows ? cp[(int64_t)e1 * Ppad] : 0;
+        nc2 = e2 < n_rows ? cp[(int64_t)e2 * Ppad] : 0;
+        ns1 = e1 < n_rows ? 0 : sp[(int64_t)(e1 - n_rows) * Ppad];
+        ns2 = e2 < n_rows ? 0 : sp[(int64_t)(e2 - n_rows) * Ppad];
+      }
+      int sx;
+      {  // a = P_in X: X from global (first step of a side), from the stack, or still in registers
+        double a[16];
+        if (x_in >= 0) {
+          const int cx = x_in < n_rows ? codes[(int64_t)x_in * Ppad + p] : 0;
+          sx = x_in < n_rows ? 0 : scl[(int64_t)(x_in - n_rows) * Ppad + p];
+          wk_operand<false>(mats, x_in, p_in, n_rows, cx, p, Ppad, tiptab, clv, a);
+        } else {
+          if (x_in <= -2) {
+            const int lvl = -2 - x_in;
+#pragma unroll
+            for (int i = 0; i < 16; i++) nk[i] = stk[(lvl * 16 + i) * 32];
+            sck = stks[lvl * 32];
+          }
+          sx = sck;
+          v4_apply_reg<false>(mats, nk, a);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) park[0][i][lane] = a[i];
+      }
+      // D1 once: the partial toward d2 (N2 = a o P_t1 D1) and the far side of edge 1 (h1 = P_h1 D1)
+      double n2[16];
+      {
+        double h1[16];
+        wk_operand2(mats + 1 * 64, mats + 2 * 64, d1, p_t1, p_h1, n_rows, c1, p, Ppad, tiptab, clv, n2, h1);
+#pragma unroll
+        for (int i = 0; i < 16; i++) { n2[i] *= park[0][i][lane]; park[2][i][lane] = h1[i]; }
+      }
+      int sc2 = sx + s1;
+      sc2 += wk_rescale(n2);
+      // D2 once: N1 = a o P_t2 D2 and h2 = P_h2 D2
+      double n1[16], h2[16];
+      wk_operand2(mats + 3 * 64, mats + 4 * 64, d2, p_t2, p_h2, n_rows, c2, p, Ppad, tiptab, clv, n1, h2);
+#pragma unroll
+      for (int i = 0; i < 16; i++) n1[i] *= park[0][i][lane];
+      int sc1 = sx + s2;
+      sc1 += wk_rescale(n1);
+      // neighbour 2 (insertion into edge x--c2): (P_h2 N2) o h2 o tvv
+      if (tree2 >= 0) {
+        double e[16];
+        v4_apply_reg<false>(mats + 4 * 64, n2, e);
+#pragma unroll
+        for (int i = 0; i < 16; i++) e[i] *= h2[i] * park[1][i][lane];
+        double val = v4_site(e, sc2 + s2 + st, w, model);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
+        if (lane == 0) partial[(int64_t)tree2 * pstride + slice] = val;
+      }
+      // neighbour 1 (insertion into edge x--c1): (P_h1 N1) o h1 o tvv
+      if (tree1 >= 0) {
+        double e[16];
+        v4_apply_reg<false>(mats + 2 * 64, n1, e);
+#pragma unroll
+        for (int i = 0; i < 16; i++) e[i] *= park[2][i][lane] * park[1][i][lane];
+        double val = v4_site(e, sc1 + s1 + st, w, model);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
+        if (lane == 0) partial[(int64_t)tree1 * pstride + slice] = val;
+      }
+      if (push >= 0) {  // the partial that does not continue right away waits on the stack
+        if (keep == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) stk[(push * 16 + i) * 32] = n2[i];
+          stks[push * 32] = sc2;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i++) stk[(push * 16 + i) * 32] = n1[i];
+          stks[push * 32] = sc1;
+        }
+      }
+      if (keep == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) nk[i] = n1[i];
+        sck = sc1;
+      } else if (keep == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) nk[i] = n2[i];
+        sck = sc2;
+      }
+      dcur = dnxt; dnxt = dnn;
+      c1 = nc1; c2 = nc2; s1 = ns1; s2 = ns2;
+    }
+  }
+}
+
+#else
+__global__ void __launch_bounds__(WK_THREADS, PLG_WK_MINB)
+walk4_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWalkVisit *__restrict__ visits,
+             int64_t n_items, int n_rows, int64_t Ppad, const unsigned char *__restrict__ codes,
+             const double *__restrict__ weights, const ModelDev *__restrict__ model,
+             const double *__restrict__ pmat, const double *__restrict__ tiptab, const double *__restrict__ clv,
+             const int *__restrict__ scl, double *__restrict__ stack_clv, int *__restrict__ stack_scl,
+             int stack_levels, double *__restrict__ partial, int pstride, unsigned long long *counter) {
+  extern __shared__ __align__(16) double wk_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *mats = wk_smem + warp * WK_SMEM_DOUBLES_PER_WARP;  // [5][64] (+ an unused second buffer)                                      // [5][64]
+  double(*park)[16][32] = reinterpret_cast<double(*)[16][32]>(mats + 2 * 5 * 64);  // [0] a = P_in X, [1] tvv = P_v Tv, [2] h1 = P_h1 D1
   const int64_t gw = (int64_t)blockIdx.x * WK_WARPS + warp;
   double *stk = stack_clv + gw * stack_levels * 16 * 32 + lane;
   int *stks = stack_scl + gw * stack_levels * 32 + lane;
@@ -229,5 +418,7 @@ walk4_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWal
     }
   }
 }
+
+#endif
 
 }  // namespace plg

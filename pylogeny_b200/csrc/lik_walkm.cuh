@@ -1,0 +1,313 @@
+// DNA x Gamma-4 SPR search walk on the FP64 tensor pipe (DMMA m8n8k4).
+//
+// Same walk as walk4_kernel (lik_walk.cuh): one warp carries a 32-pattern slice through a whole
+// SPR search, partials never leave the SM.  What changes is WHERE the 4x4 products run.  ncu on
+// the scalar walk (profiles/r1c_walk4_kernel_ncu.txt) shows the FP64 pipe 27 % busy and the warps
+// waiting on shared-memory broadcasts of P rows (32 LDS.128 per 64 FMAs) -- the matrices are
+// warp-uniform but every lane needs every entry.  mma.sync.m8n8k4.f64 turns that around: the
+// matrix is a FRAGMENT (one double per lane), the vectors are the other fragment, and one
+// instruction does 256 FMAs.  B200 measurement (profiles/r1c_fp64_peak.txt): DMMA 37 TFLOP/s,
+// DFMA 34 TFLOP/s, one shared pipe -- so this buys no flops, it removes 7/8 of the issue slots
+// and all of the P-row traffic.
+//
+// Layout ("V"): lane = 4g + q holds STATE q of pattern g of each of four 8-pattern groups j, for
+// the four categories r: v[r*4+j].  pattern(j, g) = 16 (j >> 1) + 2 g + (j & 1), so a lane reads
+// two adjacent patterns with one 16-byte load.  With A = the vector (8 patterns x 4 states) and
+// B[k][n] = (n odd ? P_h : P_t)[n >> 1][k] -- two matrices of one branch pair interleaved -- the
+// accumulator fragment comes out as d0 = (P_t x)[q], d1 = (P_h x)[q] for pattern g: again layout V,
+// no transposition between chained products.  Every product of a visit is such a pair:
+//     D1 -> (P_t1 D1, P_h1 D1)      N1 = a o P_t2 D2 -> (a' toward c1 = P_t1 N1, P_h1 N1)
+//     D2 -> (P_t2 D2, P_h2 D2)      N2 = a o P_t1 D1 -> (a' toward c2 = P_t2 N2, P_h2 N2)
+// 64 DMMAs per visit, none wasted when the search continues; what a visit hands on (registers or
+// stack) is a' = P_in N, already pushed through the next incoming branch.
+#pragma once
+
+namespace plg {
+
+constexpr int WM_WARPS = 4;
+constexpr int WM_THREADS = 32 * WM_WARPS;
+#ifndef PLG_WM_MINB
+#define PLG_WM_MINB 3
+#endif
+#ifndef PLG_WM_PREFETCH
+#define PLG_WM_PREFETCH 0  // 1: matrix fragments of the next visit fetched during this one (16 more registers: 7.65 vs 7.09 ms)
+#endif
+#ifndef PLG_WM_PARK_H2
+#define PLG_WM_PARK_H2 0   // 1: h2 waits in shared memory instead of registers
+#endif
+constexpr int WM_SMEM_DOUBLES_PER_WARP = (2 + PLG_WM_PARK_H2) * 16 * 32;  // parked: tvv, h1 (, h2)
+
+__device__ __forceinline__ void wm_dmma(double &d0, double &d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
+      : "=d"(d0), "=d"(d1)
+      : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
+// (t, h) = (P_t x, P_h x) for the branch pair whose interleaved fragment is bf[r]
+__device__ __forceinline__ void wm_pair(const double (&x)[16], const double (&bf)[4], double (&t)[16], double (&h)[16]) {
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) wm_dmma(t[r * 4 + j], h[r * 4 + j], x[r * 4 + j], bf[r]);
+}
+
+// fragment of a branch pair: lane (g, q) holds (g odd ? P[pm_h] : P[pm_t])[r][g >> 1][q]
+__device__ __forceinline__ void wm_frag(const double *__restrict__ pmat, int pm_t, int pm_h, int lane, double (&bf)[4]) {
+  const double *src = pmat + (int64_t)((lane >> 2) & 1 ? pm_h : pm_t) * 68 + (lane >> 3) * 4 + (lane & 3);
+#pragma unroll
+  for (int r = 0; r < 4; r++) asm volatile("ld.global.nc.f64 %0, [%1];\n" : "=d"(bf[r]) : "l"(src + r * 17));
+}
+
+// Operand `id` as it sits at its node, in layout V (tips: indicator of the code's states; one code
+// path for both kinds -- a separate tip path doubles the DMMA blocks and costs more in spills than
+// the 32 register moves it saves).
+__device__ __forceinline__ void wm_load_raw(int id, int n_rows, int64_t Ppad, int64_t p0, int lane,
+                                            const unsigned char *__restrict__ codes, const double *__restrict__ clv,
+                                            const int *__restrict__ scl, double (&x)[16], int (&s)[4]) {
+  const int g2 = (lane >> 2) * 2, q = lane & 3;
+  if (id < n_rows) {
+    const unsigned char *c = codes + (int64_t)id * Ppad + p0 + g2;
+    const unsigned int lo = *reinterpret_cast<const unsigned short *>(c);
+    const unsigned int hi = *reinterpret_cast<const unsigned short *>(c + 16);
+    const unsigned int m[4] = {lo & 255u, lo >> 8, hi & 255u, hi >> 8};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned int mask = m[j] ? m[j] : 15u;
+      const double ind = (mask >> q & 1u) ? 1.0 : 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) x[r * 4 + j] = ind;
+      s[j] = 0;
+    }
+  } else {
+    const double *b = clv + (int64_t)(id - n_rows) * 16 * Ppad + p0 + g2;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const double2 u = __ldg(reinterpret_cast<const double2 *>(b + (int64_t)(r * 4 + q) * Ppad));
+      const double2 v = __ldg(reinterpret_cast<const double2 *>(b + (int64_t)(r * 4 + q) * Ppad + 16));
+      x[r * 4] = u.x; x[r * 4 + 1] = u.y; x[r * 4 + 2] = v.x; x[r * 4 + 3] = v.y;
+    }
+    const int *sp = scl + (int64_t)(id - n_rows) * Ppad + p0 + g2;
+    const int2 a = __ldg(reinterpret_cast<const int2 *>(sp)), c = __ldg(reinterpret_cast<const int2 *>(sp + 16));
+    s[0] = a.x; s[1] = a.y; s[2] = c.x; s[3] = c.y;
+  }
+}
+
+// per pattern: all 16 entries below 2^-256 -> multiply by 2^256 and count (libpll's scaling).
+// A pattern's entries sit in the four lanes of a quad: one vote per pattern group.
+__device__ __forceinline__ void wm_rescale(double (&n)[16], int (&sc)[4], int lane) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int hi = max(max(__double2hiint(n[j]), __double2hiint(n[4 + j])), max(__double2hiint(n[8 + j]), __double2hiint(n[12 + j])));
+    const unsigned int big = __ballot_sync(0xffffffffu, hi >= 0x2FF00000);
+    if (((big >> (lane & 28)) & 15u) == 0u) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) n[r * 4 + j] *= TWO256;
+      sc[j] += 1;
+    }
+  }
+}
+
+// sum over the warp's 32 patterns of w (log L + scaling), L = 1/4 sum_r sum_k pi_k e[r][k];
+// the result is valid in lane 0
+__device__ __forceinline__ double wm_site_sum(const double (&e)[16], const int (&sc)[4], double w_out, double pi_q,
+                                              int lane) {
+  double v[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) v[j] = pi_q * ((e[j] + e[4 + j]) + (e[8 + j] + e[12 + j]));
+  // transpose-reduce over the quad: lane q ends with the sum of group j = q
+  const bool hi = lane & 2, odd = lane & 1;
+  double k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
+  k0 += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 2);
+  k1 += __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 2);
+  double L = odd ? k1 : k0;
+  L += __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 1);
+  const int scq = hi ? (odd ? sc[3] : sc[2]) : (odd ? sc[1] : sc[0]);
+  double val = w_out != 0.0 ? w_out * (log(L * 0.25) + scq * log(MINLH)) : 0.0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
+  return val;
+}
+
+__device__ __forceinline__ int wm_desc_load(const LikWalkVisit *__restrict__ visits, int vi, int lane) {
+  int v = 0;
+  if (lane < 12) asm volatile("ld.global.nc.b32 %0, [%1];\n" : "=r"(v) : "l"(reinterpret_cast<const int *>(visits + vi) + lane));
+  return v;
+}
+
+__global__ void __launch_bounds__(WM_THREADS, PLG_WM_MINB)
+walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWalkVisit *__restrict__ visits,
+              int64_t n_items, int n_rows, int64_t Ppad, const unsigned char *__restrict__ codes,
+              const double *__restrict__ weights, const ModelDev *__restrict__ model,
+              const double *__restrict__ pmat, const double *__restrict__ clv, const int *__restrict__ scl,
+              double *__restrict__ stack_clv, int *__restrict__ stack_scl, int stack_levels,
+              double *__restrict__ partial, int pstride, unsigned long long *counter) {
+  extern __shared__ __align__(16) double wm_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 3;
+  double(*park)[16][32] = reinterpret_cast<double(*)[16][32]>(wm_smem + warp * WM_SMEM_DOUBLES_PER_WARP);  // [0] tvv, [1] h1
+  const int64_t gw = (int64_t)blockIdx.x * WM_WARPS + warp;
+  double *stk = stack_clv + gw * stack_levels * 16 * 32 + lane;
+  int *stks = stack_scl + gw * stack_levels * 4 * 32 + lane;
+  const double pi_q = model->freqs[q];
+  const int out_off = 16 * (q >> 1) + 2 * (lane >> 2) + (q & 1);  // the pattern whose site term this lane ends up with
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(counter, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if ((int64_t)item >= n_items) break;
+    const int slice = (int)(item / (unsigned)n_groups);
+    const LikWalkGroup g = groups[item - (unsigned long long)slice * n_groups];
+    const int64_t p0 = (int64_t)slice * 32;
+    const double w_out = weights[p0 + out_off];
+    const int v_end = g.first + g.count;
+    // pipeline: descriptors two visits ahead (one int per lane), matrix fragments one visit ahead
+    int dcur = wm_desc_load(visits, g.first, lane);
+    int dnxt = g.count > 1 ? wm_desc_load(visits, g.first + 1, lane) : 0;
+    double bf1[4], bf2[4];
+    wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 3), __shfl_sync(0xffffffffu, dcur, 4), lane, bf1);
+    wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 6), __shfl_sync(0xffffffffu, dcur, 7), lane, bf2);
+    int st[4];
+    {  // the pruned subtree seen through its branch, once per search
+      double x[16], bv[4], t[16], dump[16];
+      wm_load_raw(g.tv, n_rows, Ppad, p0, lane, codes, clv, scl, x, st);
+      wm_frag(pmat, g.p_v, g.p_v, lane, bv);
+      wm_pair(x, bv, t, dump);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 16; i++) park[0][i][lane] = t[i];
+    }
+    double ak[16];  // a = P_in (incoming partial), handed from visit to visit
+    int sk[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; i++) ak[i] = 0.0;
+    for (int vi = g.first; vi < v_end; vi++) {
+      const int x_in = __shfl_sync(0xffffffffu, dcur, 0), p_in = __shfl_sync(0xffffffffu, dcur, 1);
+      const int d1 = __shfl_sync(0xffffffffu, dcur, 2), d2 = __shfl_sync(0xffffffffu, dcur, 5);
+      const int tree1 = __shfl_sync(0xffffffffu, dcur, 8), tree2 = __shfl_sync(0xffffffffu, dcur, 9);
+      const int keep = __shfl_sync(0xffffffffu, dcur, 10), push = __shfl_sync(0xffffffffu, dcur, 11);
+      int dnn = 0;
+#if PLG_WM_PREFETCH
+      double nf1[4] = {0, 0, 0, 0}, nf2[4] = {0, 0, 0, 0};
+      if (vi + 1 < v_end) {
+        if (vi + 2 < v_end) dnn = wm_desc_load(visits, vi + 2, lane);
+        wm_frag(pmat, __shfl_sync(0xffffffffu, dnxt, 3), __shfl_sync(0xffffffffu, dnxt, 4), lane, nf1);
+        wm_frag(pmat, __shfl_sync(0xffffffffu, dnxt, 6), __shfl_sync(0xffffffffu, dnxt, 7), lane, nf2);
+      }
+#else
+      if (vi + 2 < v_end) dnn = wm_desc_load(visits, vi + 2, lane);
+      if (vi > g.first) {
+        wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 3), __shfl_sync(0xffffffffu, dcur, 4), lane, bf1);
+        wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 6), __shfl_sync(0xffffffffu, dcur, 7), lane, bf2);
+      }
+#endif
+      if (x_in >= 0) {  // first step of a side: a = P_in X from a stored operand
+        double x[16], bi[4], dump[16];
+        wm_load_raw(x_in, n_rows, Ppad, p0, lane, codes, clv, scl, x, sk);
+        wm_frag(pmat, p_in, p_in, lane, bi);
+        wm_pair(x, bi, ak, dump);
+      } else if (x_in <= -2) {
+        const int lvl = -2 - x_in;
+#pragma unroll
+        for (int i = 0; i < 16; i++) ak[i] = stk[(lvl * 16 + i) * 32];
+#pragma unroll
+        for (int j = 0; j < 4; j++) sk[j] = stks[(lvl * 4 + j) * 32];
+      }
+      // D1 once: N2 = a o P_t1 D1 (the partial toward d2) and h1 = P_h1 D1 (far side of edge 1)
+      double n2[16];
+      int s1[4], sc2[4];
+      {
+        double x[16], h1[16];
+        wm_load_raw(d1, n_rows, Ppad, p0, lane, codes, clv, scl, x, s1);
+        wm_pair(x, bf1, n2, h1);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; i++) { n2[i] *= ak[i]; park[1][i][lane] = h1[i]; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) sc2[j] = sk[j] + s1[j];
+      wm_rescale(n2, sc2, lane);
+      // D2 once: N1 = a o P_t2 D2 and h2 = P_h2 D2
+      double n1[16], h2[16];
+      int s2[4], sc1[4];
+      {
+        double x[16];
+        wm_load_raw(d2, n_rows, Ppad, p0, lane, codes, clv, scl, x, s2);
+        wm_pair(x, bf2, n1, h2);
+#pragma unroll
+        for (int i = 0; i < 16; i++) n1[i] *= ak[i];
+#if PLG_WM_PARK_H2
+#pragma unroll
+        for (int i = 0; i < 16; i++) park[2][i][lane] = h2[i];
+#endif
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) sc1[j] = sk[j] + s2[j];
+      wm_rescale(n1, sc1, lane);
+      // pair 2 on N2: the partial handed toward c2 and neighbour 2's own side (insertion into x--c2)
+      const bool cont2 = keep == 2 || (push >= 0 && keep == 1);
+      double a2[16];
+      if (tree2 >= 0 || cont2) {
+        double g2[16];
+        wm_pair(n2, bf2, a2, g2);
+        if (tree2 >= 0) {
+          int sct[4];
+#pragma unroll
+#if PLG_WM_PARK_H2
+          for (int i = 0; i < 16; i++) g2[i] *= park[2][i][lane] * park[0][i][lane];
+#else
+          for (int i = 0; i < 16; i++) g2[i] *= h2[i] * park[0][i][lane];
+#endif
+#pragma unroll
+          for (int j = 0; j < 4; j++) sct[j] = sc2[j] + s2[j] + st[j];
+          const double val = wm_site_sum(g2, sct, w_out, pi_q, lane);
+          if (lane == 0) partial[(int64_t)tree2 * pstride + slice] = val;
+        }
+      }
+      // pair 1 on N1: toward c1 and neighbour 1 (insertion into x--c1)
+      const bool cont1 = keep == 1 || (push >= 0 && keep == 2);
+      if (tree1 >= 0 || cont1) {
+        double a1[16], g1[16];
+        wm_pair(n1, bf1, a1, g1);
+        if (tree1 >= 0) {
+          int sct[4];
+#pragma unroll
+          for (int i = 0; i < 16; i++) g1[i] *= park[1][i][lane] * park[0][i][lane];
+#pragma unroll
+          for (int j = 0; j < 4; j++) sct[j] = sc1[j] + s1[j] + st[j];
+          const double val = wm_site_sum(g1, sct, w_out, pi_q, lane);
+          if (lane == 0) partial[(int64_t)tree1 * pstride + slice] = val;
+        }
+        if (push >= 0 && keep == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) stk[(push * 16 + i) * 32] = a1[i];
+#pragma unroll
+          for (int j = 0; j < 4; j++) stks[(push * 4 + j) * 32] = sc1[j];
+        }
+        if (keep == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) ak[i] = a1[i];
+#pragma unroll
+          for (int j = 0; j < 4; j++) sk[j] = sc1[j];
+        }
+      }
+      if (push >= 0 && keep == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) stk[(push * 16 + i) * 32] = a2[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) stks[(push * 4 + j) * 32] = sc2[j];
+      }
+      if (keep == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) ak[i] = a2[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) sk[j] = sc2[j];
+      }
+      dcur = dnxt; dnxt = dnn;
+#if PLG_WM_PREFETCH
+#pragma unroll
+      for (int r = 0; r < 4; r++) { bf1[r] = nf1[r]; bf2[r] = nf2[r]; }
+#endif
+    }
+  }
+}
+
+}  // namespace plg

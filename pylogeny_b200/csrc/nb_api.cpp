@@ -3,6 +3,7 @@
 // reference analogue libpllWrapper.c:241-319 getSPR/NNIMovesInDistance).
 #include <algorithm>
 
+#include "hostpool.h"
 #include "neighbourhood.h"
 
 // DNA x Gamma-4 neighbourhood planner: depth-first walks (lik_walk.cuh walk4_kernel) ship; the
@@ -30,15 +31,19 @@ int depth_for(int move_type) {
 void fill_moves(const Neighbourhood &nb, int32_t *out_moves) {
   if (!out_moves) return;
   const UTree &t = nb.t;
-  for (size_t i = 0; i < nb.unique.size(); i++) {
-    const Move &m = nb.moves[nb.unique[i]];
-    const int v = t.nb[m.u][m.k];
-    const int pe = t.rooted_child_end[3 * m.u + m.k];
-    out_moves[4 * i + 0] = pe;                 // child end of the pruned branch (base-tree node id)
-    out_moves[4 * i + 1] = pe == v ? 0 : 1;    // 0: the subtree below it moves; 1: its complement moves
-    out_moves[4 * i + 2] = t.rooted_child_end[3 * m.x + m.kx];  // child end of the target branch
-    out_moves[4 * i + 3] = m.depth;            // 1 = NNI
-  }
+  const int64_t M = (int64_t)nb.unique.size();
+  const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(HostPool::get().size(), M / 16384));
+  HostPool::get().run(n_thr, [&](int ti, int nt) {
+    for (int64_t i = M * ti / nt; i < M * (ti + 1) / nt; i++) {
+      const Move &m = nb.moves[nb.unique[i]];
+      const int v = t.nb[m.u][m.k];
+      const int pe = t.rooted_child_end[3 * m.u + m.k];
+      out_moves[4 * i + 0] = pe;                 // child end of the pruned branch (base-tree node id)
+      out_moves[4 * i + 1] = pe == v ? 0 : 1;    // 0: the subtree below it moves; 1: its complement moves
+      out_moves[4 * i + 2] = t.rooted_child_end[3 * m.x + m.kx];  // child end of the target branch
+      out_moves[4 * i + 3] = m.depth;            // 1 = NNI
+    }
+  });
 }
 
 void shard_range(int64_t M, int64_t idx, int64_t cnt, int64_t *lo, int64_t *hi) {
@@ -150,6 +155,7 @@ void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *
   const size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)80 << 30);
   const int64_t max_slots = std::max<int64_t>(4 * nb.t.n_tips, (int64_t)(budget / slot_bytes));
   LikProgram p;
+  StageTimer tm;
   int64_t chunk = hi - lo;
   for (int64_t c0 = lo; c0 < hi;) {
     int64_t c1 = std::min(hi, c0 + chunk);
@@ -158,7 +164,9 @@ void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *
       chunk = std::max<int64_t>(1, (c1 - c0) / 2);
       continue;
     }
+    tm.lap("  build");
     run_lik_program(a, m, lik_workspace(), p, out_lnl + c0, stream);
+    tm.lap("  run");
     c0 = c1;
   }
 }
@@ -236,7 +244,8 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
   if (move_type == PLG_MOVE_TBR)
     return score_tbr_fitch(a, n_tips, desc, tip_rows, shard_index, shard_count, n_moves, out_moves, out_costs,
                            (cudaStream_t)stream);
-  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, nullptr), depth_for(move_type));
+  static thread_local Neighbourhood nb;  // storage reused from call to call (one neighbourhood per climb step)
+  enumerate_spr(utree_from_desc(n_tips, desc, nullptr), depth_for(move_type), nb);
   tm.lap("enumerate");
   const int64_t M = (int64_t)nb.unique.size();
   *n_moves = M;
@@ -286,7 +295,8 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
   if (move_type == PLG_MOVE_TBR)
     return score_tbr_lik(a, m->impl, n_tips, desc, brlen, tip_rows, shard_index, shard_count, n_moves, out_moves,
                          out_lnl, (cudaStream_t)stream);
-  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, brlen), depth_for(move_type));
+  static thread_local Neighbourhood nb;
+  enumerate_spr(utree_from_desc(n_tips, desc, brlen), depth_for(move_type), nb);
   tm.lap("enumerate");
   const int64_t M = (int64_t)nb.unique.size();
   *n_moves = M;

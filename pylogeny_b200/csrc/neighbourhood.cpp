@@ -4,6 +4,8 @@
 #include <thread>
 #include <unordered_map>
 
+#include "hostpool.h"
+
 namespace plg {
 
 namespace {
@@ -160,6 +162,11 @@ uint64_t topology_hash(const UTree &t) {
 
 Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
   Neighbourhood nb;
+  enumerate_spr(t, max_depth, nb);
+  return nb;
+}
+
+void enumerate_spr(const UTree &t, int max_depth, Neighbourhood &nb) {
   nb.t = t;
   DirOrder d = dir_order(t);
   uint64_t all;
@@ -169,7 +176,7 @@ Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
     for (int k = 0; k < 3; k++)
       if (t.nb[x][k] > x) base += split_term(h[3 * x + k], all);
   nb.base_hash = base;
-  if (t.n_tips < 4) return nb;
+  if (t.n_tips < 4) { nb.moves.clear(); nb.unique.clear(); return; }
   // far[3*x+k] = hash of the side beyond edge x -> nb[x][k]; term[] = its split term
   std::vector<uint64_t> far((size_t)t.n_nodes * 3, 0), term((size_t)t.n_nodes * 3, 0);
   for (int x = 0; x < t.n_nodes; x++)
@@ -217,7 +224,7 @@ Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
       }
   for (size_t i = 0; i + 1 < off.size(); i++) off[i + 1] += off[i];
   nb.moves.resize(off.back());
-  const int n_thr = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, n_int / 8)));
+  const int n_thr = std::max(1, std::min(HostPool::get().size(), std::max(1, n_int / 8)));
   auto work = [&](int ti) {
     std::vector<Frame> st;
     const int u0 = t.n_tips + (int)((int64_t)n_int * ti / n_thr), u1 = t.n_tips + (int)((int64_t)n_int * (ti + 1) / n_thr);
@@ -250,24 +257,35 @@ Neighbourhood enumerate_spr(const UTree &t, int max_depth) {
         }
       }
   };
-  if (n_thr == 1) work(0);
-  else {
-    std::vector<std::thread> th;
-    for (int i = 0; i < n_thr; i++) th.emplace_back(work, i);
-    for (auto &x : th) x.join();
-  }
+  HostPool::get().run(n_thr, [&](int ti, int) { work(ti); });
   // Distinct topologies.  Only moves at distance 1 (NNI) repeat: each NNI neighbour arises from
   // 4 of the 8(n-3) distance-1 (prune, target) pairs, which accounts for all of
   // 4(n-3)(n-2) - 2(n-3)(2n-7) = 6(n-3) duplicates; tests check distinctness of every hash.
+  // The distance-1 moves are the first two of every search: dedup those serially in enumeration
+  // order (marking repeats with unique_id -2), then number everything else in parallel.
   std::unordered_map<uint64_t, int> seen;
   seen.reserve(32 * (size_t)t.n_tips);
-  nb.unique.reserve(nb.moves.size());
-  for (size_t i = 0; i < nb.moves.size(); i++) {
-    if (nb.moves[i].depth == 1 && !seen.emplace(nb.moves[i].hash, (int)i).second) continue;
-    nb.moves[i].unique_id = (int)nb.unique.size();
-    nb.unique.push_back((int)i);
-  }
-  return nb;
+  for (size_t s = 0; s + 1 < off.size(); s++)
+    for (int64_t i = off[s]; i < off[s + 1] && nb.moves[i].depth == 1; i++)
+      if (!seen.emplace(nb.moves[i].hash, (int)i).second) nb.moves[i].unique_id = -2;
+  const int64_t n_moves = (int64_t)nb.moves.size();
+  const int n_thr2 = (int)std::max<int64_t>(1, std::min<int64_t>(HostPool::get().size(), n_moves / 8192));
+  std::vector<int64_t> kept(n_thr2 + 1, 0);
+  HostPool::get().run(n_thr2, [&](int ti, int nt) {
+    int64_t c = 0;
+    for (int64_t i = n_moves * ti / nt; i < n_moves * (ti + 1) / nt; i++) c += nb.moves[i].unique_id != -2;
+    kept[ti + 1] = c;
+  });
+  for (int i = 0; i < n_thr2; i++) kept[i + 1] += kept[i];
+  nb.unique.resize(kept[n_thr2]);
+  HostPool::get().run(n_thr2, [&](int ti, int nt) {
+    int64_t at = kept[ti];
+    for (int64_t i = n_moves * ti / nt; i < n_moves * (ti + 1) / nt; i++) {
+      if (nb.moves[i].unique_id == -2) { nb.moves[i].unique_id = -1; continue; }
+      nb.moves[i].unique_id = (int)at;
+      nb.unique[at++] = (int)i;
+    }
+  });
 }
 
 UTree apply_move(const UTree &t, const Move &m) {
@@ -353,10 +371,7 @@ std::vector<char> needed_moves(const Neighbourhood &nb, int64_t lo, int64_t hi) 
 // Runs fn(t, n_threads) on the host cores.
 template <typename F>
 static void parallel_for_threads(int n_thr, F fn) {
-  if (n_thr <= 1) { fn(0, 1); return; }
-  std::vector<std::thread> th;
-  for (int i = 0; i < n_thr; i++) th.emplace_back(fn, i, n_thr);
-  for (auto &x : th) x.join();
+  HostPool::get().run(n_thr, fn);
 }
 
 void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_tip_slots, int64_t lo,
@@ -386,7 +401,7 @@ void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, in
   auto slot_of_move = [&](int64_t i) { return n_tip_slots + (int)(n_dir + (all ? i : n_slot_rank[i])); };
   // level layout: directional ops keep their dependency level, search steps sit at Ld + depth
   int max_depth = 0;
-  const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(std::thread::hardware_concurrency(), n_moves / 4096));
+  const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(HostPool::get().size(), n_moves / 4096));
   std::vector<std::vector<int64_t>> cnt(n_thr);
   parallel_for_threads(n_thr, [&](int ti, int nt) {
     std::vector<int64_t> &c = cnt[ti];
@@ -519,7 +534,7 @@ void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int
       const int v = t.nb[u][k];
       parts[3 * u + k] = total[3 * u + k] + (t.is_tip(v) ? 0u : total[3 * v + t.slot_of(v, u)]);
     }
-  const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(std::thread::hardware_concurrency(), (hi - lo) / 16384));
+  const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(HostPool::get().size(), (hi - lo) / 16384));
   parallel_for_threads(n_thr, [&](int ti, int nt) {
     for (int64_t i = lo + (hi - lo) * ti / nt; i < lo + (hi - lo) * (ti + 1) / nt; i++) {
       const Move &m = nb.moves[nb.unique[i]];

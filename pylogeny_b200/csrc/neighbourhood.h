@@ -56,6 +56,10 @@ struct Neighbourhood {
 uint64_t topology_hash(const UTree &t);
 // max_depth < 0: all SPR moves; 1: NNI.
 Neighbourhood enumerate_spr(const UTree &t, int max_depth);
+// same into a caller-owned neighbourhood whose storage is reused from call to call (a hill climb
+// enumerates one neighbourhood per step; a fresh 12 MB move array costs more in page faults than
+// the enumeration itself)
+void enumerate_spr(const UTree &t, int max_depth, Neighbourhood &out);
 // The neighbour tree of one move, with the reference's branch-length rule (rearrangement.py:466-497).
 UTree apply_move(const UTree &t, const Move &m);
 // Rooted post-order descriptor of an unrooted tree, rooted on tip 0's pendant edge

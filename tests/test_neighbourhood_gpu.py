@@ -111,8 +111,9 @@ def test_tbr_edge_insertion_vs_retraversal(n, P):
 
 @pytest.mark.parametrize("n,P,scale", [(6, 40, 1.0), (24, 700, 1.0), (70, 300, 1.0), (40, 200, 60.0)])
 def test_lnl_planners_agree(n, P, scale, monkeypatch):
-    """The three DNA x Gamma-4 neighbourhood planners (PLG_LIK_NB_MODE: per-neighbour ops, pair-fused
-    level-by-level visits, depth-first walks -- the default) give the same lnL per neighbour, also
+    """The DNA x Gamma-4 neighbourhood planners (PLG_LIK_NB_MODE: per-neighbour ops, pair-fused
+    level-by-level visits, depth-first walks on the FP64 CUDA cores, and -- the default, "walkm" --
+    the same walks on the FP64 tensor pipe) give the same lnL per neighbour, also
     in the underflow regime (long branches => 2^-256 rescaling inside the walk), for shards and for
     radius-limited neighbourhoods; walk == oracle on a sample."""
     from pylogeny_b200 import likelihood, neighbourhood as nbh
@@ -126,12 +127,14 @@ def test_lnl_planners_agree(n, P, scale, monkeypatch):
     d = random_desc(rng, n)
     br = rng.exponential(0.1 * scale, d.shape)
     res = {}
-    for mode in ("ops", "visits", "walk"):
+    for mode in ("ops", "visits", "walk", "walkm"):
         monkeypatch.setenv("PLG_LIK_NB_MODE", mode)
         res[mode] = nbh.score_likelihood(a, m, d, br)[1]
     np.testing.assert_allclose(res["walk"], res["ops"], rtol=1e-12)
     np.testing.assert_allclose(res["walk"], res["visits"], rtol=1e-12)
-    monkeypatch.setenv("PLG_LIK_NB_MODE", "walk")
+    np.testing.assert_allclose(res["walkm"], res["ops"], rtol=1e-12)
+    monkeypatch.setenv("PLG_LIK_NB_MODE", "walkm")
+    res["walk"] = res["walkm"]
     M = len(res["walk"])
     parts = [nbh.score_likelihood(a, m, d, br, shard=(i, 3))[1] for i in range(3)]
     merged = np.concatenate([parts[i][M * i // 3: M * (i + 1) // 3] for i in range(3)])
@@ -140,6 +143,8 @@ def test_lnl_planners_agree(n, P, scale, monkeypatch):
     for i in range(0, M, max(1, M // 10)):
         want = oracle.lnl(codes, w, exch, f, 0.6, descs[i], brs[i])
         assert abs(res["walk"][i] - want) <= 1e-8 * abs(want)
+    monkeypatch.delenv("PLG_LIK_NB_MODE")
+    np.testing.assert_array_equal(nbh.score_likelihood(a, m, d, br)[1], res["walkm"])  # walkm is the default
     mt = nbh.MOVE_SPR_WITHIN(3)
     _, near = nbh.score_likelihood(a, m, d, br, move_type=mt)
     _, _, near_h = nbh.neighbour_trees(d, br, None, mt)
