@@ -363,6 +363,8 @@ void FitchProgram::clear() {
   ops.clear();
   children.clear();
   level_off.clear();
+  walk_visits.clear();
+  walk_groups.clear();
   n_scratch_slots = 0;
   n_costs = 0;
 }
@@ -481,6 +483,47 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
       case 20: launch_level<20, 1>(a, ws, o0, cnt, lb, lreq, st); break;
       default: PLG_FAIL(PLG_ERR_STATES, "no kernel for %d planes", a.K);
     }
+  }
+  if (!prog.walk_groups.empty()) {
+    ws.nbw_visits.alloc(prog.walk_visits.size() * 2);
+    ws.nbw_groups.alloc(prog.walk_groups.size());
+    PLG_CUDA(cudaMemcpyAsync(ws.nbw_visits.p, prog.walk_visits.data(), prog.walk_visits.size() * sizeof(FitchWalkVisit),
+                             cudaMemcpyHostToDevice, st));
+    PLG_CUDA(cudaMemcpyAsync(ws.nbw_groups.p, prog.walk_groups.data(), prog.walk_groups.size() * sizeof(FitchWalkGroup),
+                             cudaMemcpyHostToDevice, st));
+    // algorithmic bytes as for the per-step ops it replaces: a scored neighbour = fold (2 in, 1 out)
+    // + 3-way join (3 in); requested: D1, D2 per visit, a stored X at the first step of a side,
+    // Tv per search (partials stay on chip)
+    double vecs = 0, req_vecs = 0, units = 0;
+    for (size_t g = 0; g < prog.walk_groups.size(); g++) req_vecs += 1;
+    for (size_t v = 0; v < prog.walk_visits.size(); v++) {
+      const FitchWalkVisit &w = prog.walk_visits[v];
+      const bool n1 = w.tree1 >= 0 || w.keep == 1 || (w.push >= 0 && w.keep == 2);
+      const bool n2 = w.tree2 >= 0 || w.keep == 2 || (w.push >= 0 && w.keep == 1);
+      vecs += (n1 ? 3 : 0) + (n2 ? 3 : 0) + (w.tree1 >= 0 ? 3 : 0) + (w.tree2 >= 0 ? 3 : 0);
+      req_vecs += 2 + (w.x_in >= 0 ? 1 : 0);
+      units += 2;
+    }
+    const double vb = a.K_real * (double)a.P / 8.0;
+    const FitchWalkVisit *dv = reinterpret_cast<const FitchWalkVisit *>(ws.nbw_visits.p);
+    const FitchWalkGroup *dg = reinterpret_cast<const FitchWalkGroup *>(ws.nbw_groups.p);
+    const int ng = (int)prog.walk_groups.size();
+    prof_begin(PROF_FITCH_OPS, st);
+    switch (a.K) {
+      case 2: launch_fitch_search_walk<2, 4>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      case 3: launch_fitch_search_walk<3, 4>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      case 4: launch_fitch_search_walk<4, 4>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      case 5: launch_fitch_search_walk<5, 4>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      case 6: launch_fitch_search_walk<6, 4>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      case 8: launch_fitch_search_walk<8, 2>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      case 10: launch_fitch_search_walk<10, 2>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      case 12: launch_fitch_search_walk<12, 1>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      case 16: launch_fitch_search_walk<16, 1>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      case 20: launch_fitch_search_walk<20, 1>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      default: PLG_FAIL(PLG_ERR_STATES, "no kernel for %d planes", a.K);
+    }
+    count_launch();
+    prof_end(PROF_FITCH_OPS, st, vecs * vb, units * (double)a.P, req_vecs * vb);
   }
   PLG_CUDA(cudaGetLastError());
   if (out_costs && prog.n_costs) {

@@ -17,6 +17,20 @@ struct FitchOp {
   int tree;       // index of the cost accumulator this op adds to
 };
 
+// Depth-first SPR search walks for parsimony (fitch_walk.cuh fitch_search_walk_kernel): one group
+// = one pruned subtree, its visits in the order a thread runs them.  A visit arrives at a node
+// with the partial X of the reduced tree and scores the two insertion edges below it.
+//   x_in >= 0: X is a stored operand (first step of a side); -1: the partial the previous visit
+//   kept in registers; <= -2: pop stack level (-2 - x_in).  keep 1 / 2: the partial toward d1 / d2
+//   continues in registers; push >= 0: the other one is parked at that stack level.
+//   tree1 / tree2: cost accumulator of the neighbour inserted into edge x--d1 / x--d2, -1 = none.
+struct FitchWalkVisit {
+  int x_in, d1, d2, tree1, tree2, keep, push, pad;
+};
+struct FitchWalkGroup {
+  int tv, first, count, pad;
+};
+
 struct FitchProgram;
 struct FitchNbProgram;
 struct FitchWorkspace {
@@ -28,6 +42,8 @@ struct FitchWorkspace {
   DevBuf<int4> walk_ops;
   DevBuf<int> walk_scratch;
   DevBuf<int32_t> walk_rows;
+  DevBuf<int4> nbw_visits;      // search walks: FitchWalkVisit[] (two int4 each), FitchWalkGroup[]
+  DevBuf<int4> nbw_groups;
 };
 
 // Scratch pool shared by every alignment handle on the current device (grow-only; dropping a
@@ -52,6 +68,8 @@ struct FitchProgram {
   std::vector<int64_t> level_off;  // [n_levels+1] into ops
   int64_t n_scratch_slots = 0;
   int64_t n_costs = 0;
+  HostArr<FitchWalkVisit> walk_visits;  // run after the op levels
+  HostArr<FitchWalkGroup> walk_groups;  // longest first
   FitchProgram() = default;
   FitchProgram(const FitchProgram &) = delete;
   FitchProgram &operator=(const FitchProgram &) = delete;

@@ -147,4 +147,161 @@ static void launch_fitch_walk(const FitchAln &a, const WalkOp *d_ops, int64_t n_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// SPR search walk (neighbourhood scoring by edge insertion): a thread carries one column through a
+// whole search -- every regraft edge of one pruned subtree, depth first.  At a node x reached with
+// the partial X of the reduced tree, with x's other neighbours c1, c2 (directional sets D1, D2):
+//     N1 = F(X, D2)   neighbour 1 (insertion into x--c1): patterns where F(N1, D1) misses Tv
+//     N2 = F(X, D1)   neighbour 2 (insertion into x--c2): patterns where F(N2, D2) misses Tv
+// F = Fitch's binary node rule (intersection, union where empty).  The partial that continues into
+// a child stays in registers, the other one waits on the thread's local-memory stack; D1 and D2
+// are read once for two neighbours and no partial ever goes to HBM (the level-synchronous ops
+// moved 5 vectors per neighbour).
+template <int K, int VW>
+__device__ __forceinline__ void fw_node(const unsigned int (&a)[K][VW], const unsigned int (&b)[K][VW],
+                                        unsigned int (&r)[K][VW]) {
+#pragma unroll
+  for (int v = 0; v < VW; v++) {
+    unsigned int any = 0;
+#pragma unroll
+    for (int s = 0; s < K; s++) any |= a[s][v] & b[s][v];
+#pragma unroll
+    for (int s = 0; s < K; s++) r[s][v] = (a[s][v] & b[s][v]) | (~any & (a[s][v] | b[s][v]));
+  }
+}
+
+template <int K, int VW>
+__device__ __forceinline__ void fw_load(const unsigned int *__restrict__ tips, const unsigned int *__restrict__ scratch,
+                                        int n_tip_slots, int id, int64_t vec_words, int64_t words32, int64_t w0,
+                                        unsigned int (&x)[K][VW]) {
+  const unsigned int *src = (id < n_tip_slots ? tips + (int64_t)id * vec_words
+                                              : scratch + (int64_t)(id - n_tip_slots) * vec_words) + w0;
+#pragma unroll
+  for (int s = 0; s < K; s++) load_vec<VW>(src + s * words32, x[s]);
+}
+
+// weighted count of the patterns where the Fitch join of (n, d) shares no state with tv
+template <int K, int VW>
+__device__ __forceinline__ unsigned int fw_join_miss(const unsigned int (&n)[K][VW], const unsigned int (&d)[K][VW],
+                                                     const unsigned int (&tv)[K][VW], unsigned int nb,
+                                                     const unsigned int *__restrict__ wbits, int64_t words32,
+                                                     int64_t w0) {
+  unsigned int miss[VW];
+#pragma unroll
+  for (int v = 0; v < VW; v++) {
+    unsigned int any = 0, hit = 0, hit_u = 0;
+#pragma unroll
+    for (int s = 0; s < K; s++) {
+      any |= n[s][v] & d[s][v];
+      hit |= n[s][v] & d[s][v] & tv[s][v];
+      hit_u |= (n[s][v] | d[s][v]) & tv[s][v];
+    }
+    miss[v] = ~(hit | (~any & hit_u));
+  }
+  unsigned int c = 0;
+  if (nb == 0xFFu) {
+#pragma unroll
+    for (int v = 0; v < VW; v++) c += __popc(miss[v]);
+  } else {
+    for (unsigned int b = 0; b < nb; b++) {
+      unsigned int wv[VW];
+      load_vec<VW>(wbits + (int64_t)b * words32 + w0, wv);
+      unsigned int cb = 0;
+#pragma unroll
+      for (int v = 0; v < VW; v++) cb += __popc(miss[v] & wv[v]);
+      c += cb << b;
+    }
+  }
+  return c;
+}
+
+template <int K, int VW>
+__global__ void __launch_bounds__(256)
+fitch_search_walk_kernel(const unsigned int *__restrict__ tips, const unsigned int *__restrict__ scratch,
+                         int n_tip_slots, const FitchWalkGroup *__restrict__ groups,
+                         const FitchWalkVisit *__restrict__ visits, int64_t words32, int blocks_per_group,
+                         const unsigned int *__restrict__ wbits, const unsigned char *__restrict__ chunk_nb,
+                         unsigned int *__restrict__ cost) {
+  const int gi = blockIdx.x / blocks_per_group;
+  const int cb = blockIdx.x - gi * blocks_per_group;
+  const int64_t col = (int64_t)cb * blockDim.x + threadIdx.x;
+  const bool live = col * VW < words32;
+  const int64_t w0 = live ? col * VW : 0;  // idle lanes of the last block shadow column 0 and add nothing
+  const int64_t vec_words = (int64_t)K * words32;
+  const int4 gq = __ldg(reinterpret_cast<const int4 *>(groups + gi));
+  const unsigned int nb = chunk_nb[w0 >> 2];
+  unsigned int tv[K][VW], xk[K][VW];
+  unsigned int stack[WALK_MAX_LEVELS][K][VW];
+  fw_load<K, VW>(tips, scratch, n_tip_slots, gq.x, vec_words, words32, w0, tv);
+#pragma unroll
+  for (int s = 0; s < K; s++)
+#pragma unroll
+    for (int v = 0; v < VW; v++) xk[s][v] = 0;
+  const int4 *vp = reinterpret_cast<const int4 *>(visits + gq.y);
+  int4 q0 = __ldg(vp), q1 = __ldg(vp + 1);
+  for (int vi = 0; vi < gq.z; vi++) {
+    const int x_in = q0.x, d1 = q0.y, d2 = q0.z, tree1 = q0.w, tree2 = q1.x, keep = q1.y, push = q1.z;
+    if (vi + 1 < gq.z) { q0 = __ldg(vp + 2 * vi + 2); q1 = __ldg(vp + 2 * vi + 3); }
+    unsigned int D1[K][VW], D2[K][VW];
+    fw_load<K, VW>(tips, scratch, n_tip_slots, d1, vec_words, words32, w0, D1);
+    fw_load<K, VW>(tips, scratch, n_tip_slots, d2, vec_words, words32, w0, D2);
+    if (x_in >= 0) {
+      fw_load<K, VW>(tips, scratch, n_tip_slots, x_in, vec_words, words32, w0, xk);
+    } else if (x_in <= -2) {
+      const int l = -2 - x_in;
+#pragma unroll
+      for (int s = 0; s < K; s++)
+#pragma unroll
+        for (int v = 0; v < VW; v++) xk[s][v] = stack[l][s][v];
+    }
+    unsigned int n1[K][VW], n2[K][VW];
+    fw_node<K, VW>(xk, D2, n1);
+    fw_node<K, VW>(xk, D1, n2);
+    if (tree1 >= 0) {
+      unsigned int c = fw_join_miss<K, VW>(n1, D1, tv, nb, wbits, words32, w0);
+      c = __reduce_add_sync(0xffffffffu, live ? c : 0u);
+      if ((threadIdx.x & 31) == 0 && c) atomicAdd(cost + tree1, c);
+    }
+    if (tree2 >= 0) {
+      unsigned int c = fw_join_miss<K, VW>(n2, D2, tv, nb, wbits, words32, w0);
+      c = __reduce_add_sync(0xffffffffu, live ? c : 0u);
+      if ((threadIdx.x & 31) == 0 && c) atomicAdd(cost + tree2, c);
+    }
+    if (push >= 0) {
+#pragma unroll
+      for (int s = 0; s < K; s++)
+#pragma unroll
+        for (int v = 0; v < VW; v++) stack[push][s][v] = keep == 1 ? n2[s][v] : n1[s][v];
+    }
+    if (keep == 1) {
+#pragma unroll
+      for (int s = 0; s < K; s++)
+#pragma unroll
+        for (int v = 0; v < VW; v++) xk[s][v] = n1[s][v];
+    } else if (keep == 2) {
+#pragma unroll
+      for (int s = 0; s < K; s++)
+#pragma unroll
+        for (int v = 0; v < VW; v++) xk[s][v] = n2[s][v];
+    }
+  }
+}
+
+template <int K, int VW>
+static void launch_fitch_search_walk(const FitchAln &a, const unsigned int *scratch, const FitchWalkVisit *d_visits,
+                                     const FitchWalkGroup *d_groups, int n_groups, unsigned int *d_cost,
+                                     cudaStream_t st) {
+  const int64_t cols = a.words32 / VW;
+  int best_t = 256;
+  int64_t best_waste = INT64_MAX;
+  for (int t = 256; t >= 64; t -= 32) {
+    const int64_t blocks = (cols + t - 1) / t, waste = blocks * t - cols;
+    if (waste < best_waste) { best_waste = waste; best_t = t; }
+  }
+  const int64_t bpg = (cols + best_t - 1) / best_t;
+  fitch_search_walk_kernel<K, VW><<<(unsigned)(n_groups * bpg), best_t, 0, st>>>(
+      a.tips.p, scratch, a.n_cols, d_groups, d_visits, a.words32, (int)bpg, a.wbits.p, a.chunk_nb.p, d_cost);
+}
+
 }  // namespace plg

@@ -5,6 +5,7 @@
 
 #include "hostpool.h"
 #include "neighbourhood.h"
+#include "treewalk.h"
 
 // DNA x Gamma-4 neighbourhood planner: depth-first walks (lik_walk.cuh walk4_kernel) ship; the
 // level-by-level planners stay selectable for A/B measurements (PLG_LIK_NB_MODE=ops|visits|walk;
@@ -261,10 +262,15 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
   const int64_t max_slots = std::max<int64_t>(4 * n_tips, (int64_t)(budget / vec_bytes));
   static thread_local FitchNbProgram p;  // keeps its pinned staging across calls
   std::vector<int32_t> acc;
+  // PLG_FITCH_NB_MODE=ops: one level-synchronous op per search step (first formulation);
+  // default: depth-first search walks
+  const char *mode_env = std::getenv("PLG_FITCH_NB_MODE");
+  const bool walk = !(mode_env && !strcmp(mode_env, "ops")) && n_tips <= (1 << WALK_MAX_LEVELS);
   int64_t chunk = hi - lo;
   for (int64_t c0 = lo; c0 < hi;) {
     int64_t c1 = std::min(hi, c0 + chunk);
-    build_fitch_nb_program(nb, tip_rows, a.n_cols, c0, c1, p);
+    if (walk) build_fitch_nb_walk_program(nb, tip_rows, a.n_cols, c0, c1, p);
+    else build_fitch_nb_program(nb, tip_rows, a.n_cols, c0, c1, p);
     if (p.prog.n_scratch_slots > max_slots && c1 - c0 > 1) {
       chunk = std::max<int64_t>(1, (c1 - c0) / 2);
       continue;

@@ -514,6 +514,152 @@ void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, in
   prog.n_costs = out.first_move_acc + (hi - lo);
 }
 
+// Search-walk program (fitch_walk.cuh fitch_search_walk_kernel): the directional ops of the base
+// tree as level ops, then one group of visits per pruned subtree.  Search steps come in adjacent
+// pairs (2q, 2q+1) -- the two insertion edges at the node a step reaches = one visit.  The visits
+// of a search are listed depth-first; where both children continue, the smaller subtree goes
+// first and the other partial waits on the stack (depth <= log2 n).  Searches are independent, so
+// the host cores lay them out in parallel at offsets known from the subtree sizes.
+void build_fitch_nb_walk_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_tip_slots, int64_t lo,
+                                 int64_t hi, FitchNbProgram &out) {
+  const UTree &t = nb.t;
+  FitchProgram &prog = out.prog;
+  prog.clear();
+  DirOrder d = dir_order(t);
+  out.dir_acc.assign((size_t)t.n_nodes * 3, -1);
+  out.dir_kids.assign((size_t)t.n_nodes * 3, {-1, -1});
+  std::vector<int> dir_slot((size_t)t.n_nodes * 3, -1);
+  for (int x = 0; x < t.n_tips; x++)
+    for (int k = 0; k < 3; k++) dir_slot[3 * x + k] = tip_rows ? tip_rows[x] : x;
+  const int64_t n_dir = (int64_t)d.order.size();
+  prog.level_off.assign(d.max_level + 2, 0);
+  for (int e : d.order) prog.level_off[d.level[e] + 1]++;
+  for (int l = 0; l <= d.max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+  prog.ops.resize(n_dir);
+  prog.children.resize(2 * n_dir);
+  {
+    std::vector<int64_t> dcur(prog.level_off.begin(), prog.level_off.end() - 1);
+    int64_t slots = 0, accs = 0;
+    for (int e : d.order) {
+      const int x = e / 3, k = e % 3;
+      const int64_t at = dcur[d.level[e]]++;
+      FitchOp o;
+      o.dst = n_tip_slots + (int)slots++;
+      o.nchild = 2;
+      o.tree = (int)accs;
+      o.child_off = (int)(2 * at);
+      out.dir_acc[e] = (int)accs++;
+      int s = 0;
+      for (int j = 0; j < 3; j++)
+        if (j != k) {
+          const int c = t.nb[x][j];
+          const int ce = 3 * c + t.slot_of(c, x);
+          prog.children[2 * at + s] = dir_slot[ce];
+          out.dir_kids[e][s] = t.is_tip(c) ? -1 : ce;
+          s++;
+        }
+      dir_slot[e] = o.dst;
+      prog.ops[at] = o;
+    }
+  }
+  out.first_move_acc = n_dir + 1;
+  prog.n_scratch_slots = n_dir;
+  prog.n_costs = out.first_move_acc + (hi - lo);
+  const int64_t n_moves = (int64_t)nb.moves.size(), n_pairs = n_moves / 2;
+  if (n_pairs == 0) return;
+  const bool all = (lo == 0 && hi == (int64_t)nb.unique.size());
+  std::vector<char> need;
+  if (!all) need = needed_moves(nb, lo, hi);
+  // child[m]: the visit that continues below move m; sub[q]: needed visits in the subtree of visit q
+  static thread_local std::vector<int> child, sub;
+  child.assign(n_moves, -1);
+  sub.assign(n_pairs, 0);
+  for (int64_t q = n_pairs; q-- > 0;) {
+    if (!all && !need[2 * q] && !need[2 * q + 1]) continue;
+    sub[q] += 1;
+    const int pm = nb.moves[2 * q].parent;
+    if (pm >= 0) { child[pm] = (int)q; sub[pm / 2] += sub[q]; }
+  }
+  // roots of the needed searches, grouped by pruned subtree (u, k)
+  struct Root { int q, group; int64_t off; };
+  std::vector<Root> roots;
+  std::vector<FitchWalkGroup> groups;  // (HostArr does not keep its contents when it grows)
+  int cur_u = -1, cur_k = -1;
+  int64_t n_visits = 0;
+  for (int64_t q = 0; q < n_pairs; q++) {
+    const Move &r = nb.moves[2 * q];
+    if (r.parent >= 0 || sub[q] == 0) continue;
+    if (r.u != cur_u || r.k != cur_k) {
+      const int v = t.nb[r.u][r.k];
+      FitchWalkGroup g;
+      g.tv = dir_slot[3 * v + t.slot_of(v, r.u)];
+      g.first = (int)n_visits;
+      g.count = 0;
+      g.pad = 0;
+      groups.push_back(g);
+      cur_u = r.u; cur_k = r.k;
+    }
+    roots.push_back({(int)q, (int)groups.size() - 1, n_visits});
+    groups.back().count += sub[q];
+    n_visits += sub[q];
+  }
+  // longest searches first (the kernel's blocks are scheduled in group order)
+  std::stable_sort(groups.begin(), groups.end(),
+                   [](const FitchWalkGroup &a, const FitchWalkGroup &b) { return a.count > b.count; });
+  prog.walk_groups.resize(groups.size());
+  std::copy(groups.begin(), groups.end(), prog.walk_groups.data());
+  prog.walk_visits.resize(n_visits);
+  FitchWalkVisit *vis = prog.walk_visits.data();
+  const int *childp = child.data(), *subp = sub.data();  // (thread_local: the pool's workers must not name them)
+  const int64_t n_roots = (int64_t)roots.size();
+  const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(HostPool::get().size(), n_visits / 2048));
+  HostPool::get().run(n_thr, [&](int ti, int nt) {
+    struct Frame { int q, x_in; };
+    std::vector<Frame> st;
+    // contiguous blocks of roots with about equal numbers of visits
+    const int64_t v0 = n_visits * ti / nt, v1 = n_visits * (ti + 1) / nt;
+    for (int64_t ri = 0; ri < n_roots; ri++) {
+      if (roots[ri].off < v0 || roots[ri].off >= v1) continue;
+      const Move &r = nb.moves[2 * roots[ri].q];
+      const int ko = (r.k + 1 + (1 - r.side)) % 3, other = t.nb[r.u][ko];
+      int64_t at = roots[ri].off;
+      int depth = 0;
+      st.push_back({roots[ri].q, dir_slot[3 * other + t.slot_of(other, r.u)]});
+      while (!st.empty()) {
+        const Frame f = st.back();
+        st.pop_back();
+        if (f.x_in <= -2) depth--;
+        const Move &m1 = nb.moves[2 * f.q], &m2 = nb.moves[2 * f.q + 1];
+        const int x = m1.x, c1 = t.nb[x][m1.kx], c2 = t.nb[x][m2.kx];
+        FitchWalkVisit w;
+        w.x_in = f.x_in;
+        w.d1 = dir_slot[3 * c1 + t.slot_of(c1, x)];
+        w.d2 = dir_slot[3 * c2 + t.slot_of(c2, x)];
+        w.tree1 = (m1.unique_id >= lo && m1.unique_id < hi) ? (int)(out.first_move_acc + (m1.unique_id - lo)) : -1;
+        w.tree2 = (m2.unique_id >= lo && m2.unique_id < hi) ? (int)(out.first_move_acc + (m2.unique_id - lo)) : -1;
+        w.keep = 0; w.push = -1; w.pad = 0;
+        const int ch1 = (all || need[2 * f.q]) ? childp[2 * f.q] : -1;
+        const int ch2 = (all || need[2 * f.q + 1]) ? childp[2 * f.q + 1] : -1;
+        if (ch1 >= 0 && ch2 >= 0) {
+          const bool first1 = subp[ch1] <= subp[ch2];
+          w.keep = first1 ? 1 : 2;
+          w.push = depth;
+          st.push_back({first1 ? ch2 : ch1, -2 - depth});
+          st.push_back({first1 ? ch1 : ch2, -1});
+          depth++;
+        } else if (ch1 >= 0) {
+          w.keep = 1;
+          st.push_back({ch1, -1});
+        } else if (ch2 >= 0) {
+          w.keep = 2;
+          st.push_back({ch2, -1});
+        }
+        vis[at++] = w;
+      }
+    }
+  });
+}
+
 void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int32_t *acc, int64_t lo, int64_t hi,
                      int32_t *out_costs) {
   const UTree &t = nb.t;

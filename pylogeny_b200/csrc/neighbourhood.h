@@ -78,6 +78,10 @@ struct FitchNbProgram {
 };
 void build_fitch_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_tip_slots, int64_t lo,
                             int64_t hi, FitchNbProgram &out);
+// The same neighbours scored by depth-first search walks (FitchWalkVisit / FitchWalkGroup,
+// fitch_walk.cuh): no scratch slot per search step, accumulator layout as above.
+void build_fitch_nb_walk_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_tip_slots, int64_t lo,
+                                 int64_t hi, FitchNbProgram &out);
 // Combines the downloaded accumulators into one Fitch length per move in [lo, hi).
 void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int32_t *acc, int64_t lo, int64_t hi,
                      int32_t *out_costs);

@@ -152,3 +152,37 @@ def test_lnl_planners_agree(n, P, scale, monkeypatch):
     by_hash = dict(zip(all_h.tolist(), res["walk"].tolist()))
     np.testing.assert_allclose(near, [by_hash[h] for h in near_h.tolist()], rtol=1e-12)
     a.close(); m.close()
+
+
+@pytest.mark.parametrize("n,P,states,gaps", [(4, 30, 4, 0.0), (6, 200, 4, 0.1), (33, 1500, 4, 0.02), (90, 700, 4, 0.0),
+                                              (25, 300, 9, 0.0), (18, 260, 18, 0.0)])
+def test_fitch_search_walks_equal_level_ops(n, P, states, gaps, monkeypatch):
+    """Parsimony of a neighbourhood by depth-first search walks (default) == one level-synchronous op
+    per search step (PLG_FITCH_NB_MODE=ops) == full re-traversal of the materialised neighbours,
+    bit for bit; also for shards, NNI and radius-limited SPR."""
+    from pylogeny_b200 import fitch, neighbourhood as nbh
+    rng = np.random.default_rng(13 * n + P)
+    st = random_states(rng, n, P, states, gaps)
+    w = np.where(rng.random(P) < 0.3, rng.integers(1, 3000, P), 1).astype(np.int64)
+    a = fitch.FitchAlignment.from_dense(st, w)
+    d = random_desc(rng, n)
+    res = {}
+    for mode in ("walk", "ops"):
+        monkeypatch.setenv("PLG_FITCH_NB_MODE", mode)
+        res[mode] = {mt: nbh.score_parsimony(a, d, None, mt)[1] for mt in (nbh.MOVE_SPR, nbh.MOVE_NNI, nbh.MOVE_SPR_WITHIN(3))}
+    for mt in res["walk"]:
+        assert res["walk"][mt].tolist() == res["ops"][mt].tolist()
+    monkeypatch.setenv("PLG_FITCH_NB_MODE", "walk")
+    spr = res["walk"][nbh.MOVE_SPR]
+    descs, _, _ = nbh.neighbour_trees(d, None)
+    assert a.score_trees(descs).tolist() == spr.tolist()
+    M = len(spr)
+    parts = [nbh.score_parsimony(a, d, None, nbh.MOVE_SPR, shard=(i, 3))[1] for i in range(3)]
+    merged = np.concatenate([parts[i][M * i // 3: M * (i + 1) // 3] for i in range(3)])
+    assert merged.tolist() == spr.tolist()
+    perm = rng.permutation(n).astype(np.int32)
+    monkeypatch.setenv("PLG_FITCH_NB_MODE", "ops")
+    want = nbh.score_parsimony(a, d, perm)[1]
+    monkeypatch.setenv("PLG_FITCH_NB_MODE", "walk")
+    assert nbh.score_parsimony(a, d, perm)[1].tolist() == want.tolist()
+    a.close()
