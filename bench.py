@@ -207,7 +207,8 @@ def run_reference(args):
 def workload_config(n_gpus):
     return {"workload": "BASELINE configs[1]: synthetic DNA 64 taxa x 10k sites, GTR+G4 lnL (fixed branch lengths) "
                         "of all 14762 distinct SPR neighbours of a random tree",
-            "planner": "edge insertion (directional CLVs + 1 CLV update + 1 three-way evaluation per neighbour)",
+            "planner": "edge insertion by depth-first search walks (directional CLVs of the base tree, then per "
+                       "neighbour 1 CLV update + 1 three-way evaluation, partials kept on chip)",
             "neighbourhoods_per_step": n_gpus,
             "sharding": "pooled list of %d x 14762 neighbour trees in %d contiguous blocks, scores all-gathered (NCCL)" % (
                 n_gpus, n_gpus),
@@ -385,8 +386,9 @@ def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
     res = {"workload": "BASELINE configs[2] shape: synthetic DNA 256 taxa x 100k sites, Fitch length of all %d "
                        "distinct SPR neighbours of a random tree (edge insertion)" % M,
            "value": M * S / (np.mean(ms) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms)), "dtype": "u32 bitsets",
-           "roofline": {"kernel": "fitch_level_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": ncu_traffic("fitch_level_kernel", un.value / max(nl.value, 1)),
+           "roofline": {"kernel": "fitch_search_walk_kernel (+ fitch_level_kernel for the base tree's directional sets)",
+                        "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": ncu_traffic("fitch_search_walk_kernel", un.value / max(nl.value, 1)),
                         "algorithmic_bytes_per_launch": by.value / max(nl.value, 1),
                         "requested_gbs": rq.value / (kms.value * 1e-3) / 1e9, "peak_source": peak_src,
                         "launches": nl.value, "avg_launch_ms": kms.value / max(nl.value, 1),
