@@ -314,6 +314,13 @@ def run_ours(args):
                 "share_of_step": p["ms"] / total_ms}
 
     roofline = roof(dom)
+    # FP64 view of the same launches: ~640 flop per neighbour x pattern (CLV update 240, SURVEY.md 8d;
+    # 3-way evaluation ~400) against the DMMA peak measured on this pool (profiles/r1c_fp64_peak.txt)
+    if dom == "walk4m_kernel" and prof[dom]["ms"] > 0:
+        tf = prof[dom]["units"] * 640.0 / (prof[dom]["ms"] * 1e-3) / 1e12
+        roofline["fp64"] = {"achieved_tflops": tf, "peak_tflops": 37.1, "frac": tf / 37.1,
+                            "peak_source": "measured DMMA m8n8k4 (profiles/micro/fp64_peak.cu)",
+                            "flop_per_unit": 640}
     roofline["other_kernels"] = [r for r in (roof(k) for k in prof if k != dom) if r]
     if rank != 0:
         if world > 1:
@@ -394,6 +401,16 @@ def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
                         "launches": nl.value, "avg_launch_ms": kms.value / max(nl.value, 1),
                         "share_of_step": kms.value / sum(ms)},
            "checksum": int(costs.astype(np.int64).sum()), "min_cost": int(costs.min())}
+    # BASELINE configs[2] proper: the greedy hill-climb (one neighbourhood per step, move to the best
+    # neighbour while it improves), first 10 steps timed end to end on the host clock
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    path, _ = nbh.parsimony_greedy(a, d, max_steps=10)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    res["greedy_climb"] = {"steps": len(path) - 1, "ms_per_step": 1e3 * dt / max(1, len(path) - 1),
+                           "path_head": [int(x) for x in path[:4]],
+                           "note": "parsimony_greedy: score all neighbours, argmin, materialise the winner"}
     if cpu:
         res["cpu_baseline"] = cpu_fitch_sample(states, d)
     a.close()

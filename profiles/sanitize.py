@@ -27,3 +27,19 @@ print("aa trees", pa.score_trees(pm, d, br), "aa spr", nbh.score_likelihood(pa, 
 m1 = likelihood.Model(rng.uniform(0.5, 2, 6), rng.dirichlet(np.ones(4) * 5), 1.0, 1)
 print("r1", la.score_trees(m1, d, br))
 print("sanitize pass done")
+# the older planners / level programs behind their switches, and a deeper tree (stack levels > 2)
+import os
+n2 = 40
+st2 = random_states(rng, n2, 700, 4, 0.02)
+fa2 = fitch.FitchAlignment.from_dense(st2, np.ones(700, dtype=np.int64))
+d2 = random_desc(rng, n2); br2 = rng.exponential(0.1, d2.shape)
+codes2 = rng.integers(1, 16, (n2, 700)).astype(np.uint8)
+la2 = likelihood.LikAlignment(codes2, np.ones(700))
+for env, vals in (("PLG_TREE_MODE", ("walk", "levels")), ("PLG_LIK_NB_MODE", ("walkm", "walk", "visits", "ops")),
+                  ("PLG_FITCH_NB_MODE", ("walk", "ops"))):
+    for v in vals:
+        os.environ[env] = v
+        print(env, v, fa2.score_trees(np.stack([d2, d2])).sum(), la2.score_trees(m, np.stack([d2, d2]), np.stack([br2, br2])).sum(),
+              nbh.score_parsimony(fa2, d2)[1].sum(), nbh.score_likelihood(la2, m, d2, br2)[1].sum())
+    os.environ.pop(env)
+print("sanitize pass 2 done")

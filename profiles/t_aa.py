@@ -14,7 +14,7 @@ L = _lib.lib()
 for mt, name in ((nbh.MOVE_SPR, "SPR"), (nbh.MOVE_TBR, "TBR")):
     nbh.score_likelihood(a, m, d, br, move_type=mt)
     L.plg_profile_enable(1)
-    for k in range(4): L.plg_profile_read(k, None, None, None, None, None)
+    for k in range(5): L.plg_profile_read(k, None, None, None, None, None)
     t = time.perf_counter(); mv, l = nbh.score_likelihood(a, m, d, br, move_type=mt); dt = (time.perf_counter() - t) * 1e3
     out = []
     for k, kn in enumerate(("fitch", "clv_update", "root_eval", "pmatrix")):

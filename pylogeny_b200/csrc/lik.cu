@@ -309,6 +309,16 @@ LikAln::LikAln(int datatype, int n_rows_, int64_t P_, const uint8_t *h_codes, co
 // ----------------------------------------------------------------------------
 // host: programs
 // ----------------------------------------------------------------------------
+// opt-in to > 48 KB of dynamic shared memory once per device (function attributes are per context)
+template <typename F>
+static void ensure_dyn_smem(F *kernel, int bytes, bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (done[dev & 63]) return;
+  PLG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[dev & 63] = true;
+}
+
 LikWorkspace &lik_workspace() {
   static LikWorkspace *ws[64] = {nullptr};
   int dev = 0;
@@ -591,11 +601,8 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   }
   // search-step visits (two neighbours per step, operands staged once by the TMA)
   if (!prog.visits.empty()) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      PLG_CUDA(cudaFuncSetAttribute(visit4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V4_SMEM_BYTES));
-      attr_set = true;
-    }
+    static bool attr_set[64] = {false};
+    ensure_dyn_smem(visit4_kernel, V4_SMEM_BYTES, attr_set);
     ws.visits.alloc(prog.visits.size());
     PLG_CUDA(cudaMemcpyAsync(ws.visits.p, prog.visits.data(), prog.visits.size() * sizeof(LikVisit),
                              cudaMemcpyHostToDevice, st));
@@ -677,11 +684,8 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
                                                        ws.walk_stack_scl.p, levels, ws.partial.p, (int)pstride,
                                                        ws.walk_counter.p);
     } else {
-      static bool walk_attr_set = false;
-      if (!walk_attr_set) {
-        PLG_CUDA(cudaFuncSetAttribute(walk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WK_SMEM_BYTES));
-        walk_attr_set = true;
-      }
+      static bool walk_attr_set[64] = {false};
+      ensure_dyn_smem(walk4_kernel, WK_SMEM_BYTES, walk_attr_set);
       walk4_kernel<<<n_blocks, WK_THREADS, WK_SMEM_BYTES, st>>>(ws.walk_groups.p, (int)prog.walk_groups.size(),
                                                                ws.walk_visits.p, n_items, a.n_rows, a.Ppad, a.codes.p,
                                                                a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p, ws.clv.p,
@@ -865,11 +869,8 @@ void score_lik_desc_walk(LikAln &a, const Model &m, int64_t n_trees, int n_tips,
     count_launch();
     prof_end(PROF_PMATRIX, st, (double)n_slots * 64 * 8.0, (double)n_slots);
     prof_begin(PROF_WALK, st);
-    static bool tw_attr_set = false;
-    if (!tw_attr_set) {
-      PLG_CUDA(cudaFuncSetAttribute(twalk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM_BYTES));
-      tw_attr_set = true;
-    }
+    static bool tw_attr_set[64] = {false};
+    ensure_dyn_smem(twalk4_kernel, TW_SMEM_BYTES, tw_attr_set);
     twalk4_kernel<<<n_blocks, TW_THREADS, TW_SMEM_BYTES, st>>>(reinterpret_cast<const WalkOp *>(ws.tw_ops.p), ni, (int)cnt,
                                                   (unsigned long long)(cnt * tiles), a.Ppad, a.codes.p, a.weights.p,
                                                   m.d.p, ws.pmat.p, ws.walk_stack.p, ws.walk_stack_scl.p, levels,

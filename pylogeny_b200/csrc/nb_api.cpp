@@ -210,7 +210,8 @@ extern "C" int plg_neighbourhood_trees(int move_type, int n_tips, const int32_t 
     }
     return PLG_OK;
   }
-  Neighbourhood nb = enumerate_spr(utree_from_desc(n_tips, desc, brlen, tip_rows), depth_for(move_type));
+  static thread_local Neighbourhood nb;  // storage reused from call to call
+  enumerate_spr(utree_from_desc(n_tips, desc, brlen, tip_rows), depth_for(move_type), nb);
   for (int64_t i = 0; i < n_sel; i++) {
     if (sel[i] < 0 || sel[i] >= (int64_t)nb.unique.size()) PLG_FAIL(PLG_ERR_ARG, "move index out of range");
     const Move &m = nb.moves[nb.unique[sel[i]]];

@@ -176,7 +176,7 @@ void enumerate_spr(const UTree &t, int max_depth, Neighbourhood &nb) {
     for (int k = 0; k < 3; k++)
       if (t.nb[x][k] > x) base += split_term(h[3 * x + k], all);
   nb.base_hash = base;
-  if (t.n_tips < 4) { nb.moves.clear(); nb.unique.clear(); return; }
+  if (t.n_tips < 4) { nb.moves.clear(); nb.unique.clear(); nb.search_off.assign(1, 0); return; }
   // far[3*x+k] = hash of the side beyond edge x -> nb[x][k]; term[] = its split term
   std::vector<uint64_t> far((size_t)t.n_nodes * 3, 0), term((size_t)t.n_nodes * 3, 0);
   for (int x = 0; x < t.n_nodes; x++)
@@ -258,6 +258,7 @@ void enumerate_spr(const UTree &t, int max_depth, Neighbourhood &nb) {
       }
   };
   HostPool::get().run(n_thr, [&](int ti, int) { work(ti); });
+  nb.search_off = off;
   // Distinct topologies.  Only moves at distance 1 (NNI) repeat: each NNI neighbour arises from
   // 4 of the 8(n-3) distance-1 (prune, target) pairs, which accounts for all of
   // 4(n-3)(n-2) - 2(n-3)(2n-7) = 6(n-3) duplicates; tests check distinctness of every hash.
@@ -570,25 +571,38 @@ void build_fitch_nb_walk_program(const Neighbourhood &nb, const int32_t *tip_row
   const bool all = (lo == 0 && hi == (int64_t)nb.unique.size());
   std::vector<char> need;
   if (!all) need = needed_moves(nb, lo, hi);
-  // child[m]: the visit that continues below move m; sub[q]: needed visits in the subtree of visit q
+  // child[m]: the visit that continues below move m; sub[q]: needed visits in the subtree of visit q.
+  // Parent links never leave a search, so the searches are swept in parallel (last visit first).
   static thread_local std::vector<int> child, sub;
-  child.assign(n_moves, -1);
-  sub.assign(n_pairs, 0);
-  for (int64_t q = n_pairs; q-- > 0;) {
-    if (!all && !need[2 * q] && !need[2 * q + 1]) continue;
-    sub[q] += 1;
-    const int pm = nb.moves[2 * q].parent;
-    if (pm >= 0) { child[pm] = (int)q; sub[pm / 2] += sub[q]; }
-  }
-  // roots of the needed searches, grouped by pruned subtree (u, k)
+  child.resize(n_moves);
+  sub.resize(n_pairs);
+  int *childw = child.data(), *subw = sub.data();
+  const int64_t n_search = (int64_t)nb.search_off.size() - 1;
+  const int n_thr0 = (int)std::max<int64_t>(1, std::min<int64_t>(HostPool::get().size(), n_moves / 8192));
+  HostPool::get().run(n_thr0, [&](int ti, int nt) {
+    for (int64_t sidx = n_search * ti / nt; sidx < n_search * (ti + 1) / nt; sidx++) {
+      const int64_t m0 = nb.search_off[sidx], m1 = nb.search_off[sidx + 1];
+      for (int64_t m = m0; m < m1; m++) childw[m] = -1;
+      for (int64_t q = m0 / 2; q < m1 / 2; q++) subw[q] = 0;
+      for (int64_t q = m1 / 2; q-- > m0 / 2;) {
+        if (!all && !need[2 * q] && !need[2 * q + 1]) continue;
+        subw[q] += 1;
+        const int pm = nb.moves[2 * q].parent;
+        if (pm >= 0) { childw[pm] = (int)q; subw[pm / 2] += subw[q]; }
+      }
+    }
+  });
+  // roots of the needed searches (the first visit of every search), grouped by pruned subtree (u, k)
   struct Root { int q, group; int64_t off; };
   std::vector<Root> roots;
   std::vector<FitchWalkGroup> groups;  // (HostArr does not keep its contents when it grows)
   int cur_u = -1, cur_k = -1;
   int64_t n_visits = 0;
-  for (int64_t q = 0; q < n_pairs; q++) {
+  for (int64_t sidx = 0; sidx < n_search; sidx++) {
+    if (nb.search_off[sidx + 1] == nb.search_off[sidx]) continue;
+    const int64_t q = nb.search_off[sidx] / 2;
     const Move &r = nb.moves[2 * q];
-    if (r.parent >= 0 || sub[q] == 0) continue;
+    if (sub[q] == 0) continue;
     if (r.u != cur_u || r.k != cur_k) {
       const int v = t.nb[r.u][r.k];
       FitchWalkGroup g;

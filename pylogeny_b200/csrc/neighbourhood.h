@@ -49,6 +49,7 @@ struct Neighbourhood {
   UTree t;
   std::vector<Move> moves;       // every (prune, target) pair in enumeration order
   std::vector<int> unique;       // indices into moves, first occurrence of each topology
+  std::vector<int64_t> search_off;  // moves of search s = (pruned u, k, side): [search_off[s], search_off[s+1])
   uint64_t base_hash = 0;
 };
 

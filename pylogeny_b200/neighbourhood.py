@@ -67,12 +67,12 @@ def score_parsimony(aln, desc, tip_rows=None, move_type=MOVE_SPR, shard=(0, 1)):
     n = C.c_int64()
     L = _lib.lib()
     M = neighbourhood_size(d, move_type)
-    moves = np.zeros((M, 4), dtype=np.int32)
+    moves = np.empty((M, 4), dtype=np.int32)  # every row is written by the call
     costs = np.zeros(M, dtype=np.int32)
     _lib.check(L.plg_fitch_score_neighbourhood(aln._h, move_type, d.shape[0] + 1, d.ctypes.data,
                                                rows.ctypes.data if rows is not None else None, shard[0], shard[1],
                                                C.byref(n), moves.ctypes.data, costs.ctypes.data, None))
-    return moves, costs
+    return moves[:n.value], costs[:n.value]
 
 
 def score_likelihood(aln, model, desc, brlen, tip_rows=None, move_type=MOVE_SPR, shard=(0, 1)):
@@ -82,13 +82,13 @@ def score_likelihood(aln, model, desc, brlen, tip_rows=None, move_type=MOVE_SPR,
     rows = np.ascontiguousarray(tip_rows, dtype=np.int32) if tip_rows is not None else None
     n = C.c_int64()
     M = neighbourhood_size(d, move_type)
-    moves = np.zeros((M, 4), dtype=np.int32)
+    moves = np.empty((M, 4), dtype=np.int32)  # every row is written by the call
     lnl = np.zeros(M, dtype=np.float64)
     _lib.check(_lib.lib().plg_lik_score_neighbourhood(
         aln._h, model._h, move_type, d.shape[0] + 1, d.ctypes.data, b.ctypes.data,
         rows.ctypes.data if rows is not None else None, shard[0], shard[1], C.byref(n), moves.ctypes.data,
         lnl.ctypes.data, None))
-    return moves, lnl
+    return moves[:n.value], lnl[:n.value]
 
 
 def newick_to_desc(newick, taxa):
