@@ -573,7 +573,9 @@ void score_desc_walk(FitchAln &a, int64_t n_trees, int n_tips, const int32_t *de
   tm.lap("validate");
   FitchWorkspace &ws = fitch_workspace();
   const int ni = n_tips - 1;
-  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_trees, ((int64_t)512 << 20) / (36 * (int64_t)ni + 8)));
+  int64_t chunk = std::min<int64_t>(n_trees, ((int64_t)512 << 20) / (36 * (int64_t)ni + 8));
+  if (const char *e = getenv("PLG_WALK_CHUNK")) chunk = std::min<int64_t>(chunk, atoll(e));  // tests: force several chunks
+  chunk = std::max<int64_t>(1, chunk);
   ws.walk_desc.alloc((size_t)chunk * ni * 2);
   ws.walk_ops.alloc((size_t)chunk * ni);
   ws.walk_scratch.alloc((size_t)chunk * (3 * (size_t)ni + 2));

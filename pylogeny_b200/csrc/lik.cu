@@ -834,6 +834,7 @@ void score_lik_desc_walk(LikAln &a, const Model &m, int64_t n_trees, int n_tips,
   const int64_t tiles = a.Ppad / TW_THREADS;
   int64_t chunk = std::min<int64_t>(n_trees, ((int64_t)1 << 30) / ((int64_t)2 * ni * 512));
   chunk = std::min<int64_t>(chunk, ((int64_t)512 << 20) / (tiles * 8));
+  if (const char *e = getenv("PLG_WALK_CHUNK")) chunk = std::min<int64_t>(chunk, atoll(e));  // tests: force several chunks
   chunk = std::max<int64_t>(1, chunk);
   int dev = 0, n_sm = 148;
   PLG_CUDA(cudaGetDevice(&dev));

@@ -126,3 +126,45 @@ def test_walk_all_unambiguous_columns(monkeypatch):
         want = oracle.lnl(codes, np.ones(P), np.ones(6), np.full(4, 0.25), 1.0, descs[i], brs[i])
         assert abs(got[i] - want) <= 1e-8 * abs(want)
     a.close(); m.close()
+
+
+def test_walk_batches_larger_than_a_chunk(monkeypatch):
+    """Tree lists are processed in chunks that fit the planner / P-matrix buffers (config 4: 100k trees);
+    PLG_WALK_CHUNK forces several chunks on a small case -- same scores, same order."""
+    from pylogeny_b200 import fitch, likelihood
+    rng = np.random.default_rng(5)
+    n, P, T = 21, 900, 23
+    st = random_states(rng, n, P, 4, 0.03)
+    w = rng.integers(1, 40, P).astype(np.int64)
+    descs = np.stack([random_desc(rng, n) for _ in range(T)])
+    brs = rng.exponential(0.1, descs.shape)
+    codes = (1 << rng.integers(0, 4, (n, P))).astype(np.uint8)
+    fa = fitch.FitchAlignment.from_dense(st, w)
+    la = likelihood.LikAlignment(codes, w.astype(float))
+    m = likelihood.Model(rng.uniform(0.5, 2, 6), rng.dirichlet(np.ones(4) * 5), 0.8)
+    want_f, want_l = fa.score_trees(descs), la.score_trees(m, descs, brs)
+    for chunk in ("1", "5", "22"):
+        monkeypatch.setenv("PLG_WALK_CHUNK", chunk)
+        assert fa.score_trees(descs).tolist() == want_f.tolist()
+        np.testing.assert_array_equal(la.score_trees(m, descs, brs), want_l)
+    fa.close(); la.close(); m.close()
+
+
+def test_walk_rejects_bad_descriptors():
+    """Same argument errors as the level path (child id not earlier in post-order, row outside the alignment)."""
+    from pylogeny_b200 import fitch, likelihood, _lib
+    rng = np.random.default_rng(6)
+    st = random_states(rng, 3, 50, 4)
+    fa = fitch.FitchAlignment.from_dense(st, np.ones(50, dtype=np.int64))
+    la = likelihood.LikAlignment((1 << rng.integers(0, 4, (3, 50))).astype(np.uint8), np.ones(50))
+    m = likelihood.Model(np.ones(6), np.full(4, 0.25), 1.0)
+    bad = np.array([[0, 1], [3, 7]], np.int32)
+    with pytest.raises(Exception):
+        fa.score_trees(bad)
+    with pytest.raises(Exception):
+        la.score_trees(m, bad, np.ones((2, 2)))
+    with pytest.raises(Exception):
+        fa.score_trees(np.array([[0, 1], [3, 2]], np.int32), tip_rows=[0, 1, 9])
+    with pytest.raises(Exception):
+        la.score_trees(m, np.array([[0, 1], [3, 2]], np.int32), np.ones((2, 2)), tip_rows=[0, 1, -1])
+    fa.close(); la.close(); m.close()
