@@ -548,7 +548,11 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   tm.lap("    fuse+upload");
   const int64_t bpo = a.Ppad / DNA4_PATTERNS_PER_BLOCK;
   // finest block tiling among the kernels below (search walks reduce per 32-pattern slice)
-  const int64_t pstride = prog.walk_visits.empty() ? dna4_partial_stride(a) : a.Ppad / 32;
+  // PLG_LIK_NB_MODE=walk: scalar FP64 walk (lik_walk.cuh); default: the DMMA walk (lik_walkm.cuh)
+  const char *mode_env = getenv("PLG_LIK_NB_MODE");
+  const bool dmma = !(mode_env && !strcmp(mode_env, "walk"));
+  const int walk_patterns = dmma ? WM_PATTERNS : 32;
+  const int64_t pstride = prog.walk_visits.empty() ? dna4_partial_stride(a) : a.Ppad / walk_patterns;
   if (prog.n_trees) PLG_CUDA(cudaMemsetAsync(ws.partial.p, 0, (size_t)prog.n_trees * pstride * 8, st));
   const double Cb = (double)R * K * 8.0 + 4.0;
   auto opnd = [&](int id) { return id < 0 ? 0.0 : (id < a.n_rows ? 1.0 : Cb); };
@@ -639,9 +643,6 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     int dev = 0, n_sm = 148;
     PLG_CUDA(cudaGetDevice(&dev));
     PLG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    // PLG_LIK_NB_MODE=walk: scalar FP64 walk (lik_walk.cuh); default: the DMMA walk (lik_walkm.cuh)
-    const char *mode_env = getenv("PLG_LIK_NB_MODE");
-    const bool dmma = !(mode_env && !strcmp(mode_env, "walk"));
     const int n_blocks = n_sm * (dmma ? PLG_WM_MINB : PLG_WK_MINB);
     const int64_t n_warps = (int64_t)n_blocks * WK_WARPS;
     const int levels = std::max(1, prog.walk_levels);
@@ -674,7 +675,7 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
         units += 2.0;
       }
     }
-    const int64_t n_items = (a.Ppad / 32) * (int64_t)prog.walk_groups.size();
+    const int64_t n_items = (a.Ppad / walk_patterns) * (int64_t)prog.walk_groups.size();
     prof_begin(PROF_WALK, st);
     if (dmma) {
       const int smem = WM_WARPS * WM_SMEM_DOUBLES_PER_WARP * 8;
@@ -767,7 +768,7 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   ws.evals.alloc(std::max<size_t>(1, prog.evals.size()));
   const bool dna4 = (a.K == 4 && m.R == 4);
   const int64_t bpo = !dna4 ? a.Ppad / (LIK_THREADS / m.R)
-                             : (prog.walk_visits.empty() ? dna4_partial_stride(a) : a.Ppad / 32);
+                             : (prog.walk_visits.empty() ? dna4_partial_stride(a) : a.Ppad / 16);  // finest walk slicing
   ws.partial.alloc(std::max<size_t>(1, (size_t)prog.n_trees * (size_t)bpo));
   ws.lnl.alloc(std::max<size_t>(1, (size_t)prog.n_trees));
   if (!dna4 && !prog.ops.empty())

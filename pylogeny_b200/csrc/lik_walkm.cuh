@@ -35,7 +35,14 @@ constexpr int WM_THREADS = 32 * WM_WARPS;
 #ifndef PLG_WM_PARK_H2
 #define PLG_WM_PARK_H2 0   // 1: h2 waits in shared memory instead of registers
 #endif
-constexpr int WM_SMEM_DOUBLES_PER_WARP = (2 + PLG_WM_PARK_H2) * 16 * 32;  // parked: tvv, h1 (, h2)
+#ifndef PLG_WM_NG
+#define PLG_WM_NG 4        // 8-pattern groups per warp: 4 (32 patterns, 16 doubles per vector per lane) or 2
+#endif
+constexpr int WM_NG = PLG_WM_NG;
+constexpr int WM_V = 4 * WM_NG;          // doubles per vector per lane: [category r][group j] = v[r * WM_NG + j]
+constexpr int WM_PATTERNS = 8 * WM_NG;   // patterns per warp item
+static_assert(WM_NG == 4 || WM_NG == 2, "a warp carries 32 or 16 patterns");
+constexpr int WM_SMEM_DOUBLES_PER_WARP = (2 + PLG_WM_PARK_H2) * WM_V * 32;  // parked: tvv, h1 (, h2)
 
 __device__ __forceinline__ void wm_dmma(double &d0, double &d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
@@ -44,11 +51,12 @@ __device__ __forceinline__ void wm_dmma(double &d0, double &d1, double a, double
 }
 
 // (t, h) = (P_t x, P_h x) for the branch pair whose interleaved fragment is bf[r]
-__device__ __forceinline__ void wm_pair(const double (&x)[16], const double (&bf)[4], double (&t)[16], double (&h)[16]) {
+__device__ __forceinline__ void wm_pair(const double (&x)[WM_V], const double (&bf)[4], double (&t)[WM_V],
+                                        double (&h)[WM_V]) {
 #pragma unroll
   for (int r = 0; r < 4; r++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) wm_dmma(t[r * 4 + j], h[r * 4 + j], x[r * 4 + j], bf[r]);
+    for (int j = 0; j < WM_NG; j++) wm_dmma(t[r * WM_NG + j], h[r * WM_NG + j], x[r * WM_NG + j], bf[r]);
 }
 
 // fragment of a branch pair: lane (g, q) holds (g odd ? P[pm_h] : P[pm_t])[r][g >> 1][q]
@@ -63,19 +71,23 @@ __device__ __forceinline__ void wm_frag(const double *__restrict__ pmat, int pm_
 // the 32 register moves it saves).
 __device__ __forceinline__ void wm_load_raw(int id, int n_rows, int64_t Ppad, int64_t p0, int lane,
                                             const unsigned char *__restrict__ codes, const double *__restrict__ clv,
-                                            const int *__restrict__ scl, double (&x)[16], int (&s)[4]) {
+                                            const int *__restrict__ scl, double (&x)[WM_V], int (&s)[WM_NG]) {
   const int g2 = (lane >> 2) * 2, q = lane & 3;
   if (id < n_rows) {
     const unsigned char *c = codes + (int64_t)id * Ppad + p0 + g2;
+    unsigned int m[WM_NG];
     const unsigned int lo = *reinterpret_cast<const unsigned short *>(c);
-    const unsigned int hi = *reinterpret_cast<const unsigned short *>(c + 16);
-    const unsigned int m[4] = {lo & 255u, lo >> 8, hi & 255u, hi >> 8};
+    m[0] = lo & 255u; m[1] = lo >> 8;
+    if constexpr (WM_NG == 4) {
+      const unsigned int hi = *reinterpret_cast<const unsigned short *>(c + 16);
+      m[2] = hi & 255u; m[3] = hi >> 8;
+    }
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < WM_NG; j++) {
       const unsigned int mask = m[j] ? m[j] : 15u;
       const double ind = (mask >> q & 1u) ? 1.0 : 0.0;
 #pragma unroll
-      for (int r = 0; r < 4; r++) x[r * 4 + j] = ind;
+      for (int r = 0; r < 4; r++) x[r * WM_NG + j] = ind;
       s[j] = 0;
     }
   } else {
@@ -83,25 +95,33 @@ __device__ __forceinline__ void wm_load_raw(int id, int n_rows, int64_t Ppad, in
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const double2 u = __ldg(reinterpret_cast<const double2 *>(b + (int64_t)(r * 4 + q) * Ppad));
-      const double2 v = __ldg(reinterpret_cast<const double2 *>(b + (int64_t)(r * 4 + q) * Ppad + 16));
-      x[r * 4] = u.x; x[r * 4 + 1] = u.y; x[r * 4 + 2] = v.x; x[r * 4 + 3] = v.y;
+      x[r * WM_NG] = u.x; x[r * WM_NG + 1] = u.y;
+      if constexpr (WM_NG == 4) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(b + (int64_t)(r * 4 + q) * Ppad + 16));
+        x[r * WM_NG + 2] = v.x; x[r * WM_NG + 3] = v.y;
+      }
     }
     const int *sp = scl + (int64_t)(id - n_rows) * Ppad + p0 + g2;
-    const int2 a = __ldg(reinterpret_cast<const int2 *>(sp)), c = __ldg(reinterpret_cast<const int2 *>(sp + 16));
-    s[0] = a.x; s[1] = a.y; s[2] = c.x; s[3] = c.y;
+    const int2 a = __ldg(reinterpret_cast<const int2 *>(sp));
+    s[0] = a.x; s[1] = a.y;
+    if constexpr (WM_NG == 4) {
+      const int2 c = __ldg(reinterpret_cast<const int2 *>(sp + 16));
+      s[2] = c.x; s[3] = c.y;
+    }
   }
 }
 
 // per pattern: all 16 entries below 2^-256 -> multiply by 2^256 and count (libpll's scaling).
 // A pattern's entries sit in the four lanes of a quad: one vote per pattern group.
-__device__ __forceinline__ void wm_rescale(double (&n)[16], int (&sc)[4], int lane) {
+__device__ __forceinline__ void wm_rescale(double (&n)[WM_V], int (&sc)[WM_NG], int lane) {
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    int hi = max(max(__double2hiint(n[j]), __double2hiint(n[4 + j])), max(__double2hiint(n[8 + j]), __double2hiint(n[12 + j])));
+  for (int j = 0; j < WM_NG; j++) {
+    int hi = max(max(__double2hiint(n[j]), __double2hiint(n[WM_NG + j])),
+                 max(__double2hiint(n[2 * WM_NG + j]), __double2hiint(n[3 * WM_NG + j])));
     const unsigned int big = __ballot_sync(0xffffffffu, hi >= 0x2FF00000);
     if (((big >> (lane & 28)) & 15u) == 0u) {
 #pragma unroll
-      for (int r = 0; r < 4; r++) n[r * 4 + j] *= TWO256;
+      for (int r = 0; r < 4; r++) n[r * WM_NG + j] *= TWO256;
       sc[j] += 1;
     }
   }
@@ -109,19 +129,30 @@ __device__ __forceinline__ void wm_rescale(double (&n)[16], int (&sc)[4], int la
 
 // sum over the warp's 32 patterns of w (log L + scaling), L = 1/4 sum_r sum_k pi_k e[r][k];
 // the result is valid in lane 0
-__device__ __forceinline__ double wm_site_sum(const double (&e)[16], const int (&sc)[4], double w_out, double pi_q,
-                                              int lane) {
-  double v[4];
+__device__ __forceinline__ double wm_site_sum(const double (&e)[WM_V], const int (&sc)[WM_NG], double w_out,
+                                              double pi_q, int lane) {
+  double v[WM_NG];
 #pragma unroll
-  for (int j = 0; j < 4; j++) v[j] = pi_q * ((e[j] + e[4 + j]) + (e[8 + j] + e[12 + j]));
-  // transpose-reduce over the quad: lane q ends with the sum of group j = q
+  for (int j = 0; j < WM_NG; j++) v[j] = pi_q * ((e[j] + e[WM_NG + j]) + (e[2 * WM_NG + j] + e[3 * WM_NG + j]));
   const bool hi = lane & 2, odd = lane & 1;
-  double k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
-  k0 += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 2);
-  k1 += __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 2);
-  double L = odd ? k1 : k0;
-  L += __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 1);
-  const int scq = hi ? (odd ? sc[3] : sc[2]) : (odd ? sc[1] : sc[0]);
+  double L;
+  int scq;
+  if constexpr (WM_NG == 4) {
+    // transpose-reduce over the quad: lane q ends with the sum of group j = q
+    double k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
+    k0 += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 2);
+    k1 += __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 2);
+    L = odd ? k1 : k0;
+    L += __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 1);
+    scq = hi ? (odd ? sc[3] : sc[2]) : (odd ? sc[1] : sc[0]);
+  } else {
+    // two groups: lanes q = 0, 1 end with groups 0, 1 (lanes 2, 3 hold copies and contribute nothing)
+    L = odd ? v[1] : v[0];
+    L += __shfl_xor_sync(0xffffffffu, odd ? v[0] : v[1], 1);
+    L += __shfl_xor_sync(0xffffffffu, L, 2);
+    scq = odd ? sc[1] : sc[0];
+    if (hi) w_out = 0.0;
+  }
   double val = w_out != 0.0 ? w_out * (log(L * 0.25) + scq * log(MINLH)) : 0.0;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
@@ -143,12 +174,13 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
               double *__restrict__ partial, int pstride, unsigned long long *counter) {
   extern __shared__ __align__(16) double wm_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 3;
-  double(*park)[16][32] = reinterpret_cast<double(*)[16][32]>(wm_smem + warp * WM_SMEM_DOUBLES_PER_WARP);  // [0] tvv, [1] h1
+  double(*park)[WM_V][32] = reinterpret_cast<double(*)[WM_V][32]>(wm_smem + warp * WM_SMEM_DOUBLES_PER_WARP);  // [0] tvv, [1] h1
   const int64_t gw = (int64_t)blockIdx.x * WM_WARPS + warp;
-  double *stk = stack_clv + gw * stack_levels * 16 * 32 + lane;
-  int *stks = stack_scl + gw * stack_levels * 4 * 32 + lane;
+  double *stk = stack_clv + gw * stack_levels * WM_V * 32 + lane;
+  int *stks = stack_scl + gw * stack_levels * WM_NG * 32 + lane;
   const double pi_q = model->freqs[q];
-  const int out_off = 16 * (q >> 1) + 2 * (lane >> 2) + (q & 1);  // the pattern whose site term this lane ends up with
+  // the pattern whose site term this lane ends up with (wm_site_sum): pattern(j = q, g)
+  const int out_off = WM_NG == 4 ? 16 * (q >> 1) + 2 * (lane >> 2) + (q & 1) : 2 * (lane >> 2) + (q & 1);
   for (;;) {
     unsigned long long item = 0;
     if (lane == 0) item = atomicAdd(counter, 1ull);
@@ -156,7 +188,7 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
     if ((int64_t)item >= n_items) break;
     const int slice = (int)(item / (unsigned)n_groups);
     const LikWalkGroup g = groups[item - (unsigned long long)slice * n_groups];
-    const int64_t p0 = (int64_t)slice * 32;
+    const int64_t p0 = (int64_t)slice * WM_PATTERNS;
     const double w_out = weights[p0 + out_off];
     const int v_end = g.first + g.count;
     // pipeline: descriptors two visits ahead (one int per lane), matrix fragments one visit ahead
@@ -165,20 +197,22 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
     double bf1[4], bf2[4];
     wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 3), __shfl_sync(0xffffffffu, dcur, 4), lane, bf1);
     wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 6), __shfl_sync(0xffffffffu, dcur, 7), lane, bf2);
-    int st[4];
+    int st[WM_NG];
     {  // the pruned subtree seen through its branch, once per search
-      double x[16], bv[4], t[16], dump[16];
+      double x[WM_V], bv[4], t[WM_V], dump[WM_V];
       wm_load_raw(g.tv, n_rows, Ppad, p0, lane, codes, clv, scl, x, st);
       wm_frag(pmat, g.p_v, g.p_v, lane, bv);
       wm_pair(x, bv, t, dump);
       __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 16; i++) park[0][i][lane] = t[i];
+      for (int i = 0; i < WM_V; i++) park[0][i][lane] = t[i];
     }
-    double ak[16];  // a = P_in (incoming partial), handed from visit to visit
-    int sk[4] = {0, 0, 0, 0};
+    double ak[WM_V];  // a = P_in (incoming partial), handed from visit to visit
+    int sk[WM_NG];
 #pragma unroll
-    for (int i = 0; i < 16; i++) ak[i] = 0.0;
+    for (int j = 0; j < WM_NG; j++) sk[j] = 0;
+#pragma unroll
+    for (int i = 0; i < WM_V; i++) ak[i] = 0.0;
     for (int vi = g.first; vi < v_end; vi++) {
       const int x_in = __shfl_sync(0xffffffffu, dcur, 0), p_in = __shfl_sync(0xffffffffu, dcur, 1);
       const int d1 = __shfl_sync(0xffffffffu, dcur, 2), d2 = __shfl_sync(0xffffffffu, dcur, 5);
@@ -200,64 +234,64 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
       }
 #endif
       if (x_in >= 0) {  // first step of a side: a = P_in X from a stored operand
-        double x[16], bi[4], dump[16];
+        double x[WM_V], bi[4], dump[WM_V];
         wm_load_raw(x_in, n_rows, Ppad, p0, lane, codes, clv, scl, x, sk);
         wm_frag(pmat, p_in, p_in, lane, bi);
         wm_pair(x, bi, ak, dump);
       } else if (x_in <= -2) {
         const int lvl = -2 - x_in;
 #pragma unroll
-        for (int i = 0; i < 16; i++) ak[i] = stk[(lvl * 16 + i) * 32];
+        for (int i = 0; i < WM_V; i++) ak[i] = stk[(lvl * WM_V + i) * 32];
 #pragma unroll
-        for (int j = 0; j < 4; j++) sk[j] = stks[(lvl * 4 + j) * 32];
+        for (int j = 0; j < WM_NG; j++) sk[j] = stks[(lvl * WM_NG + j) * 32];
       }
       // D1 once: N2 = a o P_t1 D1 (the partial toward d2) and h1 = P_h1 D1 (far side of edge 1)
-      double n2[16];
-      int s1[4], sc2[4];
+      double n2[WM_V];
+      int s1[WM_NG], sc2[WM_NG];
       {
-        double x[16], h1[16];
+        double x[WM_V], h1[WM_V];
         wm_load_raw(d1, n_rows, Ppad, p0, lane, codes, clv, scl, x, s1);
         wm_pair(x, bf1, n2, h1);
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 16; i++) { n2[i] *= ak[i]; park[1][i][lane] = h1[i]; }
+        for (int i = 0; i < WM_V; i++) { n2[i] *= ak[i]; park[1][i][lane] = h1[i]; }
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) sc2[j] = sk[j] + s1[j];
+      for (int j = 0; j < WM_NG; j++) sc2[j] = sk[j] + s1[j];
       wm_rescale(n2, sc2, lane);
       // D2 once: N1 = a o P_t2 D2 and h2 = P_h2 D2
-      double n1[16], h2[16];
-      int s2[4], sc1[4];
+      double n1[WM_V], h2[WM_V];
+      int s2[WM_NG], sc1[WM_NG];
       {
-        double x[16];
+        double x[WM_V];
         wm_load_raw(d2, n_rows, Ppad, p0, lane, codes, clv, scl, x, s2);
         wm_pair(x, bf2, n1, h2);
 #pragma unroll
-        for (int i = 0; i < 16; i++) n1[i] *= ak[i];
+        for (int i = 0; i < WM_V; i++) n1[i] *= ak[i];
 #if PLG_WM_PARK_H2
 #pragma unroll
-        for (int i = 0; i < 16; i++) park[2][i][lane] = h2[i];
+        for (int i = 0; i < WM_V; i++) park[2][i][lane] = h2[i];
 #endif
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) sc1[j] = sk[j] + s2[j];
+      for (int j = 0; j < WM_NG; j++) sc1[j] = sk[j] + s2[j];
       wm_rescale(n1, sc1, lane);
       // pair 2 on N2: the partial handed toward c2 and neighbour 2's own side (insertion into x--c2)
       const bool cont2 = keep == 2 || (push >= 0 && keep == 1);
-      double a2[16];
+      double a2[WM_V];
       if (tree2 >= 0 || cont2) {
-        double g2[16];
+        double g2[WM_V];
         wm_pair(n2, bf2, a2, g2);
         if (tree2 >= 0) {
-          int sct[4];
+          int sct[WM_NG];
 #pragma unroll
 #if PLG_WM_PARK_H2
-          for (int i = 0; i < 16; i++) g2[i] *= park[2][i][lane] * park[0][i][lane];
+          for (int i = 0; i < WM_V; i++) g2[i] *= park[2][i][lane] * park[0][i][lane];
 #else
-          for (int i = 0; i < 16; i++) g2[i] *= h2[i] * park[0][i][lane];
+          for (int i = 0; i < WM_V; i++) g2[i] *= h2[i] * park[0][i][lane];
 #endif
 #pragma unroll
-          for (int j = 0; j < 4; j++) sct[j] = sc2[j] + s2[j] + st[j];
+          for (int j = 0; j < WM_NG; j++) sct[j] = sc2[j] + s2[j] + st[j];
           const double val = wm_site_sum(g2, sct, w_out, pi_q, lane);
           if (lane == 0) partial[(int64_t)tree2 * pstride + slice] = val;
         }
@@ -265,41 +299,41 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
       // pair 1 on N1: toward c1 and neighbour 1 (insertion into x--c1)
       const bool cont1 = keep == 1 || (push >= 0 && keep == 2);
       if (tree1 >= 0 || cont1) {
-        double a1[16], g1[16];
+        double a1[WM_V], g1[WM_V];
         wm_pair(n1, bf1, a1, g1);
         if (tree1 >= 0) {
-          int sct[4];
+          int sct[WM_NG];
 #pragma unroll
-          for (int i = 0; i < 16; i++) g1[i] *= park[1][i][lane] * park[0][i][lane];
+          for (int i = 0; i < WM_V; i++) g1[i] *= park[1][i][lane] * park[0][i][lane];
 #pragma unroll
-          for (int j = 0; j < 4; j++) sct[j] = sc1[j] + s1[j] + st[j];
+          for (int j = 0; j < WM_NG; j++) sct[j] = sc1[j] + s1[j] + st[j];
           const double val = wm_site_sum(g1, sct, w_out, pi_q, lane);
           if (lane == 0) partial[(int64_t)tree1 * pstride + slice] = val;
         }
         if (push >= 0 && keep == 2) {
 #pragma unroll
-          for (int i = 0; i < 16; i++) stk[(push * 16 + i) * 32] = a1[i];
+          for (int i = 0; i < WM_V; i++) stk[(push * WM_V + i) * 32] = a1[i];
 #pragma unroll
-          for (int j = 0; j < 4; j++) stks[(push * 4 + j) * 32] = sc1[j];
+          for (int j = 0; j < WM_NG; j++) stks[(push * WM_NG + j) * 32] = sc1[j];
         }
         if (keep == 1) {
 #pragma unroll
-          for (int i = 0; i < 16; i++) ak[i] = a1[i];
+          for (int i = 0; i < WM_V; i++) ak[i] = a1[i];
 #pragma unroll
-          for (int j = 0; j < 4; j++) sk[j] = sc1[j];
+          for (int j = 0; j < WM_NG; j++) sk[j] = sc1[j];
         }
       }
       if (push >= 0 && keep == 1) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) stk[(push * 16 + i) * 32] = a2[i];
+        for (int i = 0; i < WM_V; i++) stk[(push * WM_V + i) * 32] = a2[i];
 #pragma unroll
-        for (int j = 0; j < 4; j++) stks[(push * 4 + j) * 32] = sc2[j];
+        for (int j = 0; j < WM_NG; j++) stks[(push * WM_NG + j) * 32] = sc2[j];
       }
       if (keep == 2) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) ak[i] = a2[i];
+        for (int i = 0; i < WM_V; i++) ak[i] = a2[i];
 #pragma unroll
-        for (int j = 0; j < 4; j++) sk[j] = sc2[j];
+        for (int j = 0; j < WM_NG; j++) sk[j] = sc2[j];
       }
       dcur = dnxt; dnxt = dnn;
 #if PLG_WM_PREFETCH
