@@ -365,8 +365,85 @@ void FitchProgram::clear() {
   level_off.clear();
   walk_visits.clear();
   walk_groups.clear();
+  spr_edges.clear();
+  spr_searches.clear();
+  spr_n_visits = spr_n_unique = 0;
+  spr_first_acc = 0;
+  spr_vecs = spr_req_vecs = 0;
   n_scratch_slots = 0;
   n_costs = 0;
+}
+
+// Lays out the search walks of a full SPR neighbourhood on the device: one thread per search
+// (pruned subtree, side) runs the depth-first traversal the host planner
+// (neighbourhood.cpp build_fitch_nb_walk_program) would, and writes the FitchWalkVisit list the
+// walk kernel executes next on the same stream.  A visit's two moves get the unique ids of the
+// host enumeration (enumerate_spr): moves are numbered in pre-order with the lower neighbour
+// slot first, two per visit (higher slot's move first); only the first two moves of a search can
+// repeat an earlier topology (dup bits).  The walk itself descends into the smaller subtree first
+// and parks the other partial, so the stack never exceeds log2(n) + 1 frames.
+__global__ void __launch_bounds__(64)
+spr_plan_kernel(const int4 *__restrict__ edges, const int4 *__restrict__ searches, int n_search, int first_acc,
+                int4 *__restrict__ visits, int4 *__restrict__ out_moves) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_search) return;
+  const int4 r0 = __ldg(searches + 2 * s), r1 = __ldg(searches + 2 * s + 1);
+  const int move_cnt = r1.y;
+  if (move_cnt == 0) return;
+  const int uniq_base = r1.x, dup = r1.z & 3, complement = (r1.z >> 2) & 1, pe = r1.w;
+  const int dup0 = dup & 1, dup01 = dup0 + (dup >> 1);
+  constexpr int LV = WALK_MAX_LEVELS + 2;
+  int sx[LV], sfrom[LV], spre[LV], sin[LV], sdep[LV];
+  int sp = 0, park = 0;
+  int64_t at = r0.w;
+  sx[0] = r0.x; sfrom[0] = r0.y; spre[0] = 0; sin[0] = r0.z; sdep[0] = 1;
+  sp = 1;
+  while (sp > 0) {
+    sp--;
+    const int x = sx[sp], from = sfrom[sp], pre = spre[sp], x_in = sin[sp], dep = sdep[sp];
+    if (x_in <= -2) park--;
+    const int4 e0 = __ldg(edges + 3 * x), e1 = __ldg(edges + 3 * x + 1), e2 = __ldg(edges + 3 * x + 2);
+    // the two neighbours other than `from`: E1 = higher slot (move 2*pre), E2 = lower slot (2*pre + 1)
+    const int4 E1 = e2.x == from ? e1 : e2;
+    const int4 E2 = e0.x == from ? e1 : e0;
+    const int i1 = 2 * pre, i2 = i1 + 1;
+    int uid1, uid2;
+    if (pre == 0) {
+      uid1 = dup0 ? -1 : uniq_base;
+      uid2 = (dup >> 1) ? -1 : uniq_base + 1 - dup0;
+    } else {
+      uid1 = uniq_base + i1 - dup01;
+      uid2 = uniq_base + i2 - dup01;
+    }
+    const int sub1 = E1.z, sub2 = E2.z;  // visits below: 0 = the neighbour is a tip
+    const int pre2 = pre + 1, pre1 = pre + 1 + sub2;
+    int keep = 0, push = -1;
+    if (sub1 > 0 && sub2 > 0) {
+      const bool first1 = sub1 <= sub2;
+      keep = first1 ? 1 : 2;
+      push = park;
+      sx[sp] = first1 ? E2.x : E1.x; sfrom[sp] = x; spre[sp] = first1 ? pre2 : pre1; sin[sp] = -2 - park; sdep[sp] = dep + 1;
+      sp++;
+      sx[sp] = first1 ? E1.x : E2.x; sfrom[sp] = x; spre[sp] = first1 ? pre1 : pre2; sin[sp] = -1; sdep[sp] = dep + 1;
+      sp++;
+      park++;
+    } else if (sub1 > 0) {
+      keep = 1;
+      sx[sp] = E1.x; sfrom[sp] = x; spre[sp] = pre1; sin[sp] = -1; sdep[sp] = dep + 1;
+      sp++;
+    } else if (sub2 > 0) {
+      keep = 2;
+      sx[sp] = E2.x; sfrom[sp] = x; spre[sp] = pre2; sin[sp] = -1; sdep[sp] = dep + 1;
+      sp++;
+    }
+    visits[2 * at] = make_int4(x_in, E1.y, E2.y, uid1 >= 0 ? first_acc + uid1 : -1);
+    visits[2 * at + 1] = make_int4(uid2 >= 0 ? first_acc + uid2 : -1, keep, push, 0);
+    at++;
+    if (out_moves) {
+      if (uid1 >= 0) out_moves[uid1] = make_int4(pe, complement, E1.w, dep);
+      if (uid2 >= 0) out_moves[uid2] = make_int4(pe, complement, E2.w, dep);
+    }
+  }
 }
 
 // Full re-traversal of trees [t0, t1) of a batch: every internal node is one op.
@@ -443,7 +520,7 @@ static void launch_level(const FitchAln &a, FitchWorkspace &ws, int64_t op0, int
 }
 
 void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram &prog, int32_t *out_costs,
-                       cudaStream_t st) {
+                       cudaStream_t st, int32_t *out_moves) {
   const size_t vec_words = (size_t)a.K * a.words32;
   ws.scratch.alloc(std::max<size_t>(1, (size_t)prog.n_scratch_slots * vec_words));
   ws.ops.alloc(std::max<size_t>(1, prog.ops.size()));
@@ -484,19 +561,45 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
       default: PLG_FAIL(PLG_ERR_STATES, "no kernel for %d planes", a.K);
     }
   }
+  const bool device_plan = !prog.spr_searches.empty() && prog.spr_n_visits > 0;
   if (!prog.walk_groups.empty()) {
-    ws.nbw_visits.alloc(prog.walk_visits.size() * 2);
+    ws.nbw_visits.alloc((device_plan ? (size_t)prog.spr_n_visits : prog.walk_visits.size()) * 2);
     ws.nbw_groups.alloc(prog.walk_groups.size());
-    PLG_CUDA(cudaMemcpyAsync(ws.nbw_visits.p, prog.walk_visits.data(), prog.walk_visits.size() * sizeof(FitchWalkVisit),
-                             cudaMemcpyHostToDevice, st));
+    if (device_plan) {
+      // the visit list is written by spr_plan_kernel from O(n) records, not uploaded
+      ws.spr_edges.alloc(prog.spr_edges.size());
+      ws.spr_searches.alloc(prog.spr_searches.size() * 2);
+      if (out_moves) ws.spr_moves.alloc((size_t)prog.spr_n_unique);
+      PLG_CUDA(cudaMemcpyAsync(ws.spr_edges.p, prog.spr_edges.data(), prog.spr_edges.size() * sizeof(SprEdgeRec),
+                               cudaMemcpyHostToDevice, st));
+      PLG_CUDA(cudaMemcpyAsync(ws.spr_searches.p, prog.spr_searches.data(),
+                               prog.spr_searches.size() * sizeof(SprSearchRec), cudaMemcpyHostToDevice, st));
+      const int n_search = (int)prog.spr_searches.size();
+      spr_plan_kernel<<<(n_search + 63) / 64, 64, 0, st>>>(ws.spr_edges.p, ws.spr_searches.p, n_search,
+                                                          prog.spr_first_acc, ws.nbw_visits.p,
+                                                          out_moves ? ws.spr_moves.p : nullptr);
+      count_launch();
+      if (out_moves)
+        PLG_CUDA(cudaMemcpyAsync(out_moves, ws.spr_moves.p, (size_t)prog.spr_n_unique * sizeof(int4),
+                                 cudaMemcpyDeviceToHost, st));
+    } else {
+      PLG_CUDA(cudaMemcpyAsync(ws.nbw_visits.p, prog.walk_visits.data(),
+                               prog.walk_visits.size() * sizeof(FitchWalkVisit), cudaMemcpyHostToDevice, st));
+    }
     PLG_CUDA(cudaMemcpyAsync(ws.nbw_groups.p, prog.walk_groups.data(), prog.walk_groups.size() * sizeof(FitchWalkGroup),
                              cudaMemcpyHostToDevice, st));
     // algorithmic bytes as for the per-step ops it replaces: a scored neighbour = fold (2 in, 1 out)
     // + 3-way join (3 in); requested: D1, D2 per visit, a stored X at the first step of a side,
     // Tv per search (partials stay on chip)
     double vecs = 0, req_vecs = 0, units = 0;
-    for (size_t g = 0; g < prog.walk_groups.size(); g++) req_vecs += 1;
-    for (size_t v = 0; v < prog.walk_visits.size(); v++) {
+    if (device_plan) {
+      vecs = prog.spr_vecs;
+      req_vecs = prog.spr_req_vecs;
+      units = 2.0 * (double)prog.spr_n_visits;
+    } else {
+      for (size_t g = 0; g < prog.walk_groups.size(); g++) req_vecs += 1;
+    }
+    for (size_t v = 0; !device_plan && v < prog.walk_visits.size(); v++) {
       const FitchWalkVisit &w = prog.walk_visits[v];
       const bool n1 = w.tree1 >= 0 || w.keep == 1 || (w.push >= 0 && w.keep == 2);
       const bool n2 = w.tree2 >= 0 || w.keep == 2 || (w.push >= 0 && w.keep == 1);

@@ -31,6 +31,25 @@ struct FitchWalkGroup {
   int tv, first, count, pad;
 };
 
+// Device-side planning of a full SPR neighbourhood (spr_plan_kernel): what the host uploads
+// instead of the visit list.  One SprEdgeRec per directed edge 3*x+j of the base tree, one
+// SprSearchRec per (pruned subtree, side).
+struct SprEdgeRec {
+  int c;          // nb[x][j], -1 = none
+  int far_slot;   // operand id of D[c->x], the partial of c's side
+  int far_sub;    // internal nodes on c's side = visits of a search that continues into c
+  int child_end;  // rooted name of the edge (out_moves)
+};
+struct SprSearchRec {
+  int start, from;       // first node reached and the suppressed node u it is reached from
+  int x_in;              // operand id of D[other->u], the partial that enters `start`
+  int visit_off;         // first visit of the search
+  int uniq_base;         // unique id of the search's first kept move
+  int move_cnt;          // 2 per visit
+  int dup_flag;          // bit e (e < 2): the e-th move repeats an earlier topology; bit 2: the complement moves
+  int pe;                // rooted name of the pruned branch (out_moves)
+};
+
 struct FitchProgram;
 struct FitchNbProgram;
 struct FitchWorkspace {
@@ -44,6 +63,7 @@ struct FitchWorkspace {
   DevBuf<int32_t> walk_rows;
   DevBuf<int4> nbw_visits;      // search walks: FitchWalkVisit[] (two int4 each), FitchWalkGroup[]
   DevBuf<int4> nbw_groups;
+  DevBuf<int4> spr_edges, spr_searches, spr_moves;  // device-planned SPR neighbourhoods
 };
 
 // Scratch pool shared by every alignment handle on the current device (grow-only; dropping a
@@ -70,6 +90,12 @@ struct FitchProgram {
   int64_t n_costs = 0;
   HostArr<FitchWalkVisit> walk_visits;  // run after the op levels
   HostArr<FitchWalkGroup> walk_groups;  // longest first
+  // device-planned SPR neighbourhood: walk_visits stays empty, spr_plan_kernel writes the visits
+  HostArr<SprEdgeRec> spr_edges;
+  HostArr<SprSearchRec> spr_searches;
+  int64_t spr_n_visits = 0, spr_n_unique = 0;
+  int spr_first_acc = 0;
+  double spr_vecs = 0, spr_req_vecs = 0;  // algorithmic / requested vectors of the walk launch
   FitchProgram() = default;
   FitchProgram(const FitchProgram &) = delete;
   FitchProgram &operator=(const FitchProgram &) = delete;
@@ -77,8 +103,9 @@ struct FitchProgram {
 };
 
 void build_full_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_tip_slots, FitchProgram &prog);
+// out_moves (device-planned SPR neighbourhoods only): int32 [spr_n_unique][4] on the host, or null
 void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram &prog, int32_t *out_costs,
-                       cudaStream_t st);
+                       cudaStream_t st, int32_t *out_moves = nullptr);
 void score_batch_full(FitchAln &a, const TreeBatch &b, int32_t *out_costs, cudaStream_t st);
 // binary descriptor batches by on-chip tree walks (PLG_TREE_MODE=levels selects the level programs)
 bool tree_walk_enabled();

@@ -246,8 +246,36 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
   if (move_type == PLG_MOVE_TBR)
     return score_tbr_fitch(a, n_tips, desc, tip_rows, shard_index, shard_count, n_moves, out_moves, out_costs,
                            (cudaStream_t)stream);
+  const int depth = depth_for(move_type);
+  const char *mode_env = std::getenv("PLG_FITCH_NB_MODE");
+  const bool walk = !(mode_env && !strcmp(mode_env, "ops")) && n_tips <= (1 << WALK_MAX_LEVELS);
+  // A whole SPR neighbourhood on one device: the host prepares O(n) records and the search walks
+  // are laid out by spr_plan_kernel (PLG_FITCH_NB_PLAN=host keeps the host planner for A/B tests;
+  // shards, NNI and radius-limited searches use it too).
+  const char *plan_env = std::getenv("PLG_FITCH_NB_PLAN");
+  if (walk && depth < 0 && shard_count == 1 && shard_index == 0 && n_tips >= 4 &&
+      !(plan_env && !strcmp(plan_env, "host"))) {
+    static thread_local SprDevicePlan plan;  // keeps its pinned staging across calls
+    static thread_local std::vector<int32_t> acc;
+    const UTree t = utree_from_desc(n_tips, desc, nullptr);
+    prepare_spr_device_plan(t, tip_rows, a.n_cols, plan);
+    tm.lap("prepare");
+    *n_moves = plan.n_unique;
+    if (!out_costs) {  // moves only: the host enumeration
+      static thread_local Neighbourhood nb0;
+      enumerate_spr(t, depth, nb0);
+      fill_moves(nb0, out_moves);
+      return PLG_OK;
+    }
+    acc.resize(plan.base.prog.n_costs);
+    run_fitch_program(a, fitch_workspace(), plan.base.prog, acc.data(), (cudaStream_t)stream, out_moves);
+    tm.lap("run");
+    finish_fitch_spr_plan(t, plan, acc.data(), out_costs);
+    tm.lap("finish");
+    return PLG_OK;
+  }
   static thread_local Neighbourhood nb;  // storage reused from call to call (one neighbourhood per climb step)
-  enumerate_spr(utree_from_desc(n_tips, desc, nullptr), depth_for(move_type), nb);
+  enumerate_spr(utree_from_desc(n_tips, desc, nullptr), depth, nb);
   tm.lap("enumerate");
   const int64_t M = (int64_t)nb.unique.size();
   *n_moves = M;
@@ -265,8 +293,6 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
   std::vector<int32_t> acc;
   // PLG_FITCH_NB_MODE=ops: one level-synchronous op per search step (first formulation);
   // default: depth-first search walks
-  const char *mode_env = std::getenv("PLG_FITCH_NB_MODE");
-  const bool walk = !(mode_env && !strcmp(mode_env, "ops")) && n_tips <= (1 << WALK_MAX_LEVELS);
   int64_t chunk = hi - lo;
   for (int64_t c0 = lo; c0 < hi;) {
     int64_t c1 = std::min(hi, c0 + chunk);

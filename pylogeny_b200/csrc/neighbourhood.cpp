@@ -674,6 +674,190 @@ void build_fitch_nb_walk_program(const Neighbourhood &nb, const int32_t *tip_row
   });
 }
 
+// Directional ops of the base tree as a level program (shared by the walk planners).
+static void emit_dir_program(const UTree &t, const DirOrder &d, const int32_t *tip_rows, int n_tip_slots,
+                             FitchNbProgram &out, std::vector<int> &dir_slot) {
+  FitchProgram &prog = out.prog;
+  prog.clear();
+  out.dir_acc.assign((size_t)t.n_nodes * 3, -1);
+  out.dir_kids.assign((size_t)t.n_nodes * 3, {-1, -1});
+  dir_slot.assign((size_t)t.n_nodes * 3, -1);
+  for (int x = 0; x < t.n_tips; x++)
+    for (int k = 0; k < 3; k++) dir_slot[3 * x + k] = tip_rows ? tip_rows[x] : x;
+  const int64_t n_dir = (int64_t)d.order.size();
+  prog.level_off.assign(d.max_level + 2, 0);
+  for (int e : d.order) prog.level_off[d.level[e] + 1]++;
+  for (int l = 0; l <= d.max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+  prog.ops.resize(n_dir);
+  prog.children.resize(2 * n_dir);
+  std::vector<int64_t> dcur(prog.level_off.begin(), prog.level_off.end() - 1);
+  int64_t slots = 0, accs = 0;
+  for (int e : d.order) {
+    const int x = e / 3, k = e % 3;
+    const int64_t at = dcur[d.level[e]]++;
+    FitchOp o;
+    o.dst = n_tip_slots + (int)slots++;
+    o.nchild = 2;
+    o.tree = (int)accs;
+    o.child_off = (int)(2 * at);
+    out.dir_acc[e] = (int)accs++;
+    int s = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        const int c = t.nb[x][j];
+        const int ce = 3 * c + t.slot_of(c, x);
+        prog.children[2 * at + s] = dir_slot[ce];
+        out.dir_kids[e][s] = t.is_tip(c) ? -1 : ce;
+        s++;
+      }
+    dir_slot[e] = o.dst;
+    prog.ops[at] = o;
+  }
+  out.first_move_acc = n_dir + 1;
+  prog.n_scratch_slots = n_dir;
+}
+
+void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_slots, SprDevicePlan &out) {
+  out.search_edge.clear();
+  out.search_uniq.assign(1, 0);
+  out.n_visits = out.n_unique = 0;
+  DirOrder d = dir_order(t);
+  std::vector<int> dir_slot;
+  emit_dir_program(t, d, tip_rows, n_tip_slots, out.base, dir_slot);
+  out.order = d.order;
+  FitchProgram &prog = out.base.prog;
+  prog.spr_edges.clear();
+  prog.spr_searches.clear();
+  prog.spr_n_visits = prog.spr_n_unique = 0;
+  prog.spr_first_acc = (int)out.base.first_move_acc;
+  prog.spr_vecs = prog.spr_req_vecs = 0;
+  prog.n_costs = out.base.first_move_acc;
+  if (t.n_tips < 4) return;
+  // leaves on x's side of edge x -> nb[x][k]
+  std::vector<int> leaves((size_t)t.n_nodes * 3, 0);
+  for (int x = 0; x < t.n_tips; x++) leaves[3 * x] = leaves[3 * x + 1] = leaves[3 * x + 2] = 1;
+  for (int e : d.order) {
+    const int x = e / 3, k = e % 3;
+    int c = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) c += leaves[3 * t.nb[x][j] + t.slot_of(t.nb[x][j], x)];
+    leaves[e] = c;
+  }
+  prog.spr_edges.resize((size_t)t.n_nodes * 3);
+  for (int x = 0; x < t.n_nodes; x++)
+    for (int j = 0; j < 3; j++) {
+      SprEdgeRec r;
+      r.c = t.nb[x][j];
+      r.far_slot = r.far_sub = 0;
+      r.child_end = -1;
+      if (r.c >= 0) {
+        const int back = 3 * r.c + t.slot_of(r.c, x);
+        r.far_slot = dir_slot[back];
+        r.far_sub = leaves[back] - 1;
+        r.child_end = t.rooted_child_end[3 * x + j];
+      }
+      prog.spr_edges[3 * (size_t)x + j] = r;
+    }
+  // hashes of the distance-1 moves (as enumerate_spr computes them) for the de-duplication
+  uint64_t all;
+  std::vector<uint64_t> h = side_hashes(t, d, &all);
+  uint64_t base = 0;
+  for (int x = 0; x < t.n_nodes; x++)
+    for (int k = 0; k < 3; k++)
+      if (t.nb[x][k] > x) base += split_term(h[3 * x + k], all);
+  auto far = [&](int x, int k) { const int y = t.nb[x][k]; return h[3 * y + t.slot_of(y, x)]; };
+  std::unordered_map<uint64_t, int> seen;
+  seen.reserve(32 * (size_t)t.n_tips);
+  std::vector<FitchWalkGroup> groups;
+  const int n_int = t.n_nodes - t.n_tips;
+  prog.spr_searches.resize((size_t)n_int * 6);
+  int64_t move_off = 0, dups = 0, dup_internal = 0, n_started = 0;
+  size_t si = 0;
+  for (int u = t.n_tips; u < t.n_nodes; u++)
+    for (int k = 0; k < 3; k++) {
+      int cur_group = -1;
+      const uint64_t hv = far(u, k);
+      const int v = t.nb[u][k], pe = t.rooted_child_end[3 * u + k];
+      for (int side = 0; side < 2; side++) {
+        const int ks = (k + 1 + side) % 3, ko = (k + 1 + (1 - side)) % 3;
+        const int start = t.nb[u][ks], other = t.nb[u][ko];
+        SprSearchRec r;
+        r.start = start;
+        r.from = u;
+        r.x_in = dir_slot[3 * other + t.slot_of(other, u)];
+        r.visit_off = (int)(move_off / 2);
+        r.uniq_base = (int)(move_off - dups);
+        r.move_cnt = t.is_tip(start) ? 0 : 2 * leaves[3 * start + t.slot_of(start, u)] - 2;
+        r.dup_flag = pe == v ? 0 : 4;
+        r.pe = pe;
+        if (r.move_cnt > 0) {
+          const uint64_t rem = split_term(far(u, ks), all);
+          int e = 0;
+          for (int j = 2; j >= 0; j--) {  // enumerate_spr writes the higher slot's move first
+            if (t.nb[start][j] == u) continue;
+            const uint64_t joined = split_term(far(start, j) ^ hv, all);
+            if (!seen.emplace(base - rem + joined, 1).second) {
+              r.dup_flag |= 1 << e;
+              dups++;
+              if (!t.is_tip(t.nb[start][j])) dup_internal++;
+            }
+            e++;
+          }
+          if (cur_group < 0) {
+            FitchWalkGroup g;
+            g.tv = dir_slot[3 * v + t.slot_of(v, u)];
+            g.first = r.visit_off;
+            g.count = 0;
+            g.pad = 0;
+            groups.push_back(g);
+            cur_group = (int)groups.size() - 1;
+          }
+          groups[cur_group].count += r.move_cnt / 2;
+          n_started++;
+        }
+        prog.spr_searches[si++] = r;
+        out.search_edge.push_back(3 * u + k);
+        move_off += r.move_cnt;
+        out.search_uniq.push_back(move_off - dups);
+      }
+    }
+  out.n_visits = move_off / 2;
+  out.n_unique = move_off - dups;
+  // longest searches first (the kernel's blocks are scheduled in group order)
+  std::stable_sort(groups.begin(), groups.end(),
+                   [](const FitchWalkGroup &a, const FitchWalkGroup &b) { return a.count > b.count; });
+  prog.walk_groups.resize(groups.size());
+  std::copy(groups.begin(), groups.end(), prog.walk_groups.data());
+  prog.spr_n_visits = out.n_visits;
+  prog.spr_n_unique = out.n_unique;
+  prog.n_costs = out.base.first_move_acc + out.n_unique;
+  // byte accounting of the walk launch (run_fitch_program): a scored neighbour = fold + 3-way join
+  // (6 vectors); a repeated distance-1 move still folds when the search continues below it
+  prog.spr_vecs = 6.0 * (double)out.n_unique + 3.0 * (double)dup_internal;
+  prog.spr_req_vecs = (double)groups.size() + 2.0 * (double)out.n_visits + (double)n_started;
+}
+
+void finish_fitch_spr_plan(const UTree &t, const SprDevicePlan &p, const int32_t *acc, int32_t *out_costs) {
+  std::vector<uint32_t> total((size_t)t.n_nodes * 3, 0);
+  for (int e : p.order) {
+    uint32_t s = (uint32_t)acc[p.base.dir_acc[e]];
+    for (int j = 0; j < 2; j++)
+      if (p.base.dir_kids[e][j] >= 0) s += total[p.base.dir_kids[e][j]];
+    total[e] = s;
+  }
+  const int64_t n_search = (int64_t)p.search_edge.size();
+  const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(HostPool::get().size(), p.n_unique / 32768));
+  HostPool::get().run(n_thr, [&](int ti, int nt) {
+    for (int64_t s = n_search * ti / nt; s < n_search * (ti + 1) / nt; s++) {
+      const int e = p.search_edge[s], u = e / 3, k = e % 3, v = t.nb[u][k];
+      // length(T') = length(pruned subtree) + length(rest) + [their state sets miss at the new edge]
+      const uint32_t parts = total[e] + (t.is_tip(v) ? 0u : total[3 * v + t.slot_of(v, u)]);
+      for (int64_t i = p.search_uniq[s]; i < p.search_uniq[s + 1]; i++)
+        out_costs[i] = (int32_t)(parts + (uint32_t)acc[p.base.first_move_acc + i]);
+    }
+  });
+}
+
 void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int32_t *acc, int64_t lo, int64_t hi,
                      int32_t *out_costs) {
   const UTree &t = nb.t;

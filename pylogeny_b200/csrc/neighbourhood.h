@@ -94,6 +94,23 @@ void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int
 void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
                           LikProgram &out, int mode = LIK_NB_OPS);
 
+// Device-planned full SPR neighbourhood (parsimony).  The host does O(n) work only: the base tree's
+// directional ops, one SprEdgeRec per directed edge, one SprSearchRec per search (pruned subtree
+// u--nb[u][k], side) and the de-duplication of the 8(n-3) distance-1 moves (the only ones that can
+// repeat).  The search walks themselves -- one FitchWalkVisit per node reached, in the same
+// depth-first order and with the same neighbour numbering as enumerate_spr +
+// build_fitch_nb_walk_program -- are laid out by spr_plan_kernel (fitch.cu), one thread per search.
+struct SprDevicePlan {
+  FitchNbProgram base;               // directional level ops + prog.spr_* (what run_fitch_program uploads)
+  std::vector<int> order;            // directed edges, dependencies first (finish pass)
+  std::vector<int> search_edge;      // per search: pruned directed edge 3*u+k
+  std::vector<int64_t> search_uniq;  // per search: unique id of its first kept move; [n_search] = n_unique
+  int64_t n_visits = 0, n_unique = 0;
+};
+void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_slots, SprDevicePlan &out);
+// Fitch length of every distinct neighbour from the downloaded accumulators (no move array).
+void finish_fitch_spr_plan(const UTree &t, const SprDevicePlan &p, const int32_t *acc, int32_t *out_costs);
+
 // lnL of the distinct neighbours [lo, hi) of an enumerated SPR/NNI neighbourhood (nb_api.cpp).
 void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *tip_rows, int64_t lo, int64_t hi,
                    double *out_lnl, cudaStream_t stream);

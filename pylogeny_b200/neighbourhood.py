@@ -59,20 +59,23 @@ def neighbour_trees(desc, brlen=None, sel=None, move_type=MOVE_SPR, tip_rows=Non
     return out_d, out_b, out_h
 
 
-def score_parsimony(aln, desc, tip_rows=None, move_type=MOVE_SPR, shard=(0, 1)):
+def score_parsimony(aln, desc, tip_rows=None, move_type=MOVE_SPR, shard=(0, 1), want_moves=True):
     """Fitch length of every distinct neighbour. aln: fitch.FitchAlignment.
-    Returns (moves int32 [M, 4], costs int32 [M]); with shard=(i, c) only block i of c is filled."""
+    Returns (moves int32 [M, 4], costs int32 [M]); with shard=(i, c) only block i of c is filled.
+    want_moves=False skips the move table (moves is None): a climb only needs the argmin, which
+    `neighbour_trees(desc, sel=[i])` materialises."""
     d = _desc(desc)
     rows = np.ascontiguousarray(tip_rows, dtype=np.int32) if tip_rows is not None else None
     n = C.c_int64()
     L = _lib.lib()
     M = neighbourhood_size(d, move_type)
-    moves = np.empty((M, 4), dtype=np.int32)  # every row is written by the call
+    moves = np.empty((M, 4), dtype=np.int32) if want_moves else None  # every row is written by the call
     costs = np.zeros(M, dtype=np.int32)
     _lib.check(L.plg_fitch_score_neighbourhood(aln._h, move_type, d.shape[0] + 1, d.ctypes.data,
                                                rows.ctypes.data if rows is not None else None, shard[0], shard[1],
-                                               C.byref(n), moves.ctypes.data, costs.ctypes.data, None))
-    return moves[:n.value], costs[:n.value]
+                                               C.byref(n), moves.ctypes.data if want_moves else None,
+                                               costs.ctypes.data, None))
+    return (moves[:n.value] if want_moves else None), costs[:n.value]
 
 
 def score_likelihood(aln, model, desc, brlen, tip_rows=None, move_type=MOVE_SPR, shard=(0, 1)):
@@ -181,7 +184,7 @@ def parsimony_greedy(aln, desc, tip_rows=None, move_type=MOVE_SPR, max_steps=100
     cur = int(aln.score_trees(d[None], tip_rows)[0])
     path = [cur]
     for _ in range(max_steps):
-        _, costs = score_parsimony(aln, d, tip_rows, move_type)
+        _, costs = score_parsimony(aln, d, tip_rows, move_type, want_moves=False)
         if len(costs) == 0:
             break
         best = int(np.argmin(costs))

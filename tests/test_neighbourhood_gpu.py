@@ -186,3 +186,44 @@ def test_fitch_search_walks_equal_level_ops(n, P, states, gaps, monkeypatch):
     monkeypatch.setenv("PLG_FITCH_NB_MODE", "walk")
     assert nbh.score_parsimony(a, d, perm)[1].tolist() == want.tolist()
     a.close()
+
+
+@pytest.mark.parametrize("n,P,shape", [(4, 40, "random"), (5, 64, "random"), (12, 333, "random"), (40, 1000, "caterpillar"),
+                                        (64, 900, "balanced"), (130, 520, "random"), (257, 300, "random")])
+def test_fitch_device_planned_spr_equals_host_planner(n, P, shape, monkeypatch):
+    """Full SPR neighbourhoods are laid out on the device (spr_plan_kernel, default) from O(n) host
+    records; the host planner (PLG_FITCH_NB_PLAN=host: enumerate_spr + build_fitch_nb_walk_program)
+    must give the same move list (every field, same order) and the same costs, bit for bit."""
+    from pylogeny_b200 import fitch, neighbourhood as nbh
+    rng = np.random.default_rng(7 * n + P)
+    st = random_states(rng, n, P, 4, 0.03)
+    w = np.where(rng.random(P) < 0.4, rng.integers(1, 900, P), 1).astype(np.int64)
+    a = fitch.FitchAlignment.from_dense(st, w)
+    if shape == "caterpillar":
+        d = np.array([(0, 1)] + [(n + i - 1, i + 1) for i in range(1, n - 1)], dtype=np.int32)
+    elif shape == "balanced":
+        ids = list(range(n))
+        rows = []
+        while len(ids) > 1:
+            nxt = []
+            for i in range(0, len(ids) - 1, 2):
+                rows.append((ids[i], ids[i + 1]))
+                nxt.append(n + len(rows) - 1)
+            if len(ids) % 2:
+                nxt.append(ids[-1])
+            ids = nxt
+        d = np.array(rows, dtype=np.int32)
+    else:
+        d = random_desc(rng, n)
+    perm = rng.permutation(n).astype(np.int32)
+    got = {}
+    for plan in ("device", "host"):
+        monkeypatch.setenv("PLG_FITCH_NB_PLAN", plan)
+        got[plan] = nbh.score_parsimony(a, d, perm)
+    assert got["device"][0].shape == got["host"][0].shape == (nbh.neighbourhood_size(d), 4)
+    assert got["device"][0].tolist() == got["host"][0].tolist()
+    assert got["device"][1].tolist() == got["host"][1].tolist()
+    monkeypatch.setenv("PLG_FITCH_NB_PLAN", "device")
+    descs, _, _ = nbh.neighbour_trees(d)
+    assert a.score_trees(descs, perm).tolist() == got["device"][1].tolist()
+    a.close()
