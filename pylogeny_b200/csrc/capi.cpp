@@ -80,6 +80,7 @@ cudaEvent_t prof_event() {
   return e;
 }
 }  // namespace
+bool prof_enabled() { return g_prof_on; }
 void prof_begin(int kind, cudaStream_t st) {
   if (!g_prof_on) return;
   g_prof_open[kind] = prof_event();

@@ -61,6 +61,7 @@ inline void count_launch(int64_t n = 1) { g_launches.fetch_add(n, std::memory_or
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
 enum ProfKind { PROF_FITCH_OPS = 0, PROF_CLV_UPDATE = 1, PROF_ROOT_EVAL = 2, PROF_PMATRIX = 3, PROF_WALK = 4, PROF_KINDS = 5 };
+bool prof_enabled();
 void prof_begin(int kind, cudaStream_t st);
 // algorithmic_bytes: SURVEY.md 8d per-node-op figures (independent of fusion / operand sharing);
 // requested_bytes: what this implementation actually loads and stores (< 0: same as algorithmic)

@@ -333,6 +333,9 @@ void LikProgram::clear() {
   walk_visits.clear();
   walk_groups.clear();
   walk_levels = 0;
+  spr_edges.clear();
+  spr_searches.clear();
+  spr_n_visits = spr_n_unique = 0;
   ops.clear();
   level_off.clear();
   evals.clear();
@@ -483,11 +486,103 @@ static void run_typed(const LikAln &a, const Model &m, LikWorkspace &ws, const L
   }
 }
 
+// Lays out the search walks of a full SPR neighbourhood on the device (likelihood twin of
+// fitch.cu spr_plan_kernel): one thread per search runs the depth-first traversal of the host
+// planner (neighbourhood.cpp build_lik_nb_program, mode walk) and writes the LikWalkVisit list the
+// walk kernel executes next on the same stream; unique ids follow the host enumeration
+// (enumerate_spr).  acct (profiling only): [0] algorithmic, [1] requested bytes per pattern of the
+// walk launch, the same per-visit sums run_dna4 takes over a host-built visit list.
+__global__ void __launch_bounds__(64)
+spr_lik_plan_kernel(const int4 *__restrict__ edges, const int4 *__restrict__ searches, int n_search, int n_rows,
+                    int4 *__restrict__ visits, int4 *__restrict__ out_moves, double *__restrict__ acct) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_search) return;
+  const int4 r0 = __ldg(searches + 3 * s), r1 = __ldg(searches + 3 * s + 1), r2 = __ldg(searches + 3 * s + 2);
+  const int move_cnt = r1.y;
+  if (move_cnt == 0) return;
+  const int uniq_base = r1.x, dup = r1.z & 3, complement = (r1.z >> 2) & 1, pe = r1.w;
+  const int dup0 = dup & 1, dup01 = dup0 + (dup >> 1);
+  constexpr double Cb = 4 * 4 * 8.0 + 4.0;
+  const double o_tv = r2.y < n_rows ? 1.0 : Cb;
+  double bytes = 0.0, req = 0.0;
+  constexpr int LV = WALK_MAX_LEVELS + 2;
+  int sx[LV], sfrom[LV], spre[LV], sin[LV], sdep[LV], spin[LV];
+  int sp = 1, park = 0;
+  int64_t at = r0.w;
+  sx[0] = r0.x; sfrom[0] = r0.y; spre[0] = 0; sin[0] = r0.z; sdep[0] = 1; spin[0] = r2.x;
+  while (sp > 0) {
+    sp--;
+    const int x = sx[sp], from = sfrom[sp], pre = spre[sp], x_in = sin[sp], dep = sdep[sp], p_in = spin[sp];
+    if (x_in <= -2) park--;
+    const int4 *ep = edges + 6 * x;
+    const int4 e0 = __ldg(ep), e1 = __ldg(ep + 2), e2 = __ldg(ep + 4);
+    // the two neighbours other than `from`: j1 = higher slot (move 2*pre), j2 = lower slot (2*pre + 1)
+    const int j1 = e2.x == from ? 1 : 2, j2 = e0.x == from ? 1 : 0;
+    const int4 E1 = j1 == 1 ? e1 : e2, E2 = j2 == 1 ? e1 : e0;
+    const int4 Q1 = __ldg(ep + 2 * j1 + 1), Q2 = __ldg(ep + 2 * j2 + 1);
+    int uid1, uid2;
+    if (pre == 0) {
+      uid1 = dup0 ? -1 : uniq_base;
+      uid2 = (dup >> 1) ? -1 : uniq_base + 1 - dup0;
+    } else {
+      uid1 = uniq_base + 2 * pre - dup01;
+      uid2 = uid1 + 1;
+    }
+    const int sub1 = E1.z, sub2 = E2.z;  // visits below: 0 = the neighbour is a tip
+    const int pre2 = pre + 1, pre1 = pre + 1 + sub2;
+    int keep = 0, push = -1;
+    if (sub1 > 0 && sub2 > 0) {
+      const bool first1 = sub1 <= sub2;
+      keep = first1 ? 1 : 2;
+      push = park;
+      sx[sp] = first1 ? E2.x : E1.x; sfrom[sp] = x; spre[sp] = first1 ? pre2 : pre1; sin[sp] = -2 - park;
+      sdep[sp] = dep + 1; spin[sp] = first1 ? Q2.x : Q1.x;
+      sp++;
+      sx[sp] = first1 ? E1.x : E2.x; sfrom[sp] = x; spre[sp] = first1 ? pre1 : pre2; sin[sp] = -1;
+      sdep[sp] = dep + 1; spin[sp] = first1 ? Q1.x : Q2.x;
+      sp++;
+      park++;
+    } else if (sub1 > 0) {
+      keep = 1;
+      sx[sp] = E1.x; sfrom[sp] = x; spre[sp] = pre1; sin[sp] = -1; sdep[sp] = dep + 1; spin[sp] = Q1.x;
+      sp++;
+    } else if (sub2 > 0) {
+      keep = 2;
+      sx[sp] = E2.x; sfrom[sp] = x; spre[sp] = pre2; sin[sp] = -1; sdep[sp] = dep + 1; spin[sp] = Q2.x;
+      sp++;
+    }
+    int4 *vp = visits + 4 * at;
+    vp[0] = make_int4(x_in, p_in, E1.y, Q1.x);
+    vp[1] = make_int4(Q1.y, E2.y, Q2.x, Q2.y);
+    vp[2] = make_int4(uid1, uid2, keep, push);
+    vp[3] = make_int4(0, 0, 0, 0);
+    at++;
+    if (out_moves) {
+      if (uid1 >= 0) out_moves[uid1] = make_int4(pe, complement, E1.w, dep);
+      if (uid2 >= 0) out_moves[uid2] = make_int4(pe, complement, E2.w, dep);
+    }
+    if (acct) {
+      const double o1 = E1.y < n_rows ? 1.0 : Cb, o2 = E2.y < n_rows ? 1.0 : Cb;
+      const double xin = x_in >= 0 ? (x_in < n_rows ? 1.0 : Cb) : Cb;
+      const bool n1 = uid1 >= 0 || sub1 > 0, n2 = uid2 >= 0 || sub2 > 0;
+      if (n1) bytes += Cb + xin + o2 + (uid1 >= 0 ? Cb + o1 + o_tv + 8.0 : 0.0);
+      if (n2) bytes += Cb + xin + o1 + (uid2 >= 0 ? Cb + o2 + o_tv + 8.0 : 0.0);
+      req += (x_in >= 0 ? xin : (x_in <= -2 ? Cb : 0.0)) + o1 + o2 + (push >= 0 ? Cb : 0.0) +
+             (uid1 >= 0 ? 0.25 : 0.0) + (uid2 >= 0 ? 0.25 : 0.0);
+    }
+  }
+  if (acct) {
+    atomicAdd(acct, bytes);
+    atomicAdd(acct + 1, req);
+  }
+}
+
 // DNA x Gamma-4 path: thread-per-pattern kernels, evaluations fused into the CLV update that
 // produces their first operand whenever the other operands are ready by then.
 static int64_t dna4_partial_stride(const LikAln &a) { return a.Ppad / (PLG_DNA4_WARP_PER_RATE ? R4_PATTERNS : D4_THREADS); }
 
-static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, cudaStream_t st) {
+static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, cudaStream_t st,
+                     int32_t *out_moves) {
   constexpr int K = 4, R = 4, KKP = 17, NC = 16;
   StageTimer tm;
   const int n_pm = (int)prog.brlens.size();
@@ -552,7 +647,9 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   const char *mode_env = getenv("PLG_LIK_NB_MODE");
   const bool dmma = !(mode_env && !strcmp(mode_env, "walk"));
   const int walk_patterns = dmma ? WM_PATTERNS : 32;
-  const int64_t pstride = prog.walk_visits.empty() ? dna4_partial_stride(a) : a.Ppad / walk_patterns;
+  const bool device_plan = prog.spr_n_visits > 0;
+  const bool walks = device_plan || !prog.walk_visits.empty();
+  const int64_t pstride = !walks ? dna4_partial_stride(a) : a.Ppad / walk_patterns;
   if (prog.n_trees) PLG_CUDA(cudaMemsetAsync(ws.partial.p, 0, (size_t)prog.n_trees * pstride * 8, st));
   const double Cb = (double)R * K * 8.0 + 4.0;
   auto opnd = [&](int id) { return id < 0 ? 0.0 : (id < a.n_rows ? 1.0 : Cb); };
@@ -639,20 +736,18 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   }
   tm.lap("    level launches");
   // depth-first search walks: one persistent launch, a warp per (pattern slice, pruned subtree)
-  if (!prog.walk_visits.empty()) {
+  if (walks) {
     int dev = 0, n_sm = 148;
     PLG_CUDA(cudaGetDevice(&dev));
     PLG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     const int n_blocks = n_sm * (dmma ? PLG_WM_MINB : PLG_WK_MINB);
     const int64_t n_warps = (int64_t)n_blocks * WK_WARPS;
     const int levels = std::max(1, prog.walk_levels);
-    ws.walk_visits.alloc(prog.walk_visits.size());
+    ws.walk_visits.alloc(device_plan ? (size_t)prog.spr_n_visits : prog.walk_visits.size());
     ws.walk_groups.alloc(prog.walk_groups.size());
     ws.walk_stack.alloc((size_t)n_warps * levels * 16 * 32);
     ws.walk_stack_scl.alloc((size_t)n_warps * levels * 4 * 32);
     ws.walk_counter.alloc(1);
-    PLG_CUDA(cudaMemcpyAsync(ws.walk_visits.p, prog.walk_visits.data(), prog.walk_visits.size() * sizeof(LikWalkVisit),
-                             cudaMemcpyHostToDevice, st));
     PLG_CUDA(cudaMemcpyAsync(ws.walk_groups.p, prog.walk_groups.data(), prog.walk_groups.size() * sizeof(LikWalkGroup),
                              cudaMemcpyHostToDevice, st));
     PLG_CUDA(cudaMemsetAsync(ws.walk_counter.p, 0, sizeof(unsigned long long), st));
@@ -661,7 +756,40 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     // really loads and stores (far-side operands, first partial of a side, stack traffic, Tv once
     // per search)
     double bytes = 0, req = 0, units = 0;
-    for (const LikWalkGroup &g : prog.walk_groups) {
+    const bool acct_on = device_plan && prof_enabled();
+    if (device_plan) {
+      // the visit list is written by spr_lik_plan_kernel from O(n) records, not uploaded
+      ws.spr_edges.alloc(prog.spr_edges.size() * 2);
+      ws.spr_searches.alloc(prog.spr_searches.size() * 3);
+      if (out_moves) ws.spr_moves.alloc((size_t)prog.spr_n_unique);
+      ws.spr_acct.alloc(2);
+      PLG_CUDA(cudaMemcpyAsync(ws.spr_edges.p, prog.spr_edges.data(), prog.spr_edges.size() * sizeof(LikSprEdge),
+                               cudaMemcpyHostToDevice, st));
+      PLG_CUDA(cudaMemcpyAsync(ws.spr_searches.p, prog.spr_searches.data(),
+                               prog.spr_searches.size() * sizeof(LikSprSearch), cudaMemcpyHostToDevice, st));
+      if (acct_on) PLG_CUDA(cudaMemsetAsync(ws.spr_acct.p, 0, 2 * sizeof(double), st));
+      const int n_search = (int)prog.spr_searches.size();
+      spr_lik_plan_kernel<<<(n_search + 63) / 64, 64, 0, st>>>(
+          ws.spr_edges.p, ws.spr_searches.p, n_search, a.n_rows, reinterpret_cast<int4 *>(ws.walk_visits.p),
+          out_moves ? ws.spr_moves.p : nullptr, acct_on ? ws.spr_acct.p : nullptr);
+      count_launch();
+      if (out_moves)
+        PLG_CUDA(cudaMemcpyAsync(out_moves, ws.spr_moves.p, (size_t)prog.spr_n_unique * sizeof(int4),
+                                 cudaMemcpyDeviceToHost, st));
+      if (acct_on) {  // (profiling only: one extra round trip before the walk is launched)
+        double h[2];
+        PLG_CUDA(cudaMemcpyAsync(h, ws.spr_acct.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        PLG_CUDA(cudaStreamSynchronize(st));
+        bytes = h[0]; req = h[1];
+        for (const LikWalkGroup &g : prog.walk_groups) req += opnd(g.tv) + 8.0;
+      }
+      units = 2.0 * (double)prog.spr_n_visits;
+    } else {
+      PLG_CUDA(cudaMemcpyAsync(ws.walk_visits.p, prog.walk_visits.data(),
+                               prog.walk_visits.size() * sizeof(LikWalkVisit), cudaMemcpyHostToDevice, st));
+    }
+    for (size_t gi = 0; !device_plan && gi < prog.walk_groups.size(); gi++) {
+      const LikWalkGroup &g = prog.walk_groups[gi];
       req += opnd(g.tv) + 8.0;
       for (int q = g.first; q < g.first + g.count; q++) {
         const LikWalkVisit &v = prog.walk_visits[q];
@@ -759,7 +887,7 @@ static void run_aa20(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
 }
 
 void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, double *out_lnl,
-                     cudaStream_t st) {
+                     cudaStream_t st, int32_t *out_moves) {
   if (m.K != a.K) PLG_FAIL(PLG_ERR_ARG, "model has %d states but the alignment has %d", m.K, a.K);
   const size_t RK = (size_t)m.R * a.K;
   ws.clv.alloc(std::max<size_t>(1, (size_t)prog.n_slots * RK * a.Ppad));
@@ -768,7 +896,8 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   ws.evals.alloc(std::max<size_t>(1, prog.evals.size()));
   const bool dna4 = (a.K == 4 && m.R == 4);
   const int64_t bpo = !dna4 ? a.Ppad / (LIK_THREADS / m.R)
-                             : (prog.walk_visits.empty() ? dna4_partial_stride(a) : a.Ppad / 16);  // finest walk slicing
+                             : (prog.walk_visits.empty() && prog.spr_n_visits == 0 ? dna4_partial_stride(a)
+                                                                                    : a.Ppad / 16);  // finest walk slicing
   ws.partial.alloc(std::max<size_t>(1, (size_t)prog.n_trees * (size_t)bpo));
   ws.lnl.alloc(std::max<size_t>(1, (size_t)prog.n_trees));
   if (!dna4 && !prog.ops.empty())
@@ -777,7 +906,7 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     PLG_CUDA(cudaMemcpyAsync(ws.evals.p, prog.evals.data(), prog.evals.size() * sizeof(LikEval),
                              cudaMemcpyHostToDevice, st));
   PLG_CUDA(cudaMemsetAsync(ws.lnl.p, 0, std::max<size_t>(1, (size_t)prog.n_trees) * 8, st));
-  if (dna4) run_dna4(a, m, ws, prog, st);
+  if (dna4) run_dna4(a, m, ws, prog, st, out_moves);
   else if (a.K == 4 && m.R == 1) run_typed<4, 1>(a, m, ws, prog, st);
   else if (a.K == 20 && m.R == 4) run_aa20(a, m, ws, prog, st);
   else if (a.K == 20 && m.R == 1) run_typed<20, 1>(a, m, ws, prog, st);

@@ -37,6 +37,19 @@ struct LikWalkGroup {
   int tv, p_v, first, count;
 };
 
+// Device-side planning of a full SPR neighbourhood (spr_lik_plan_kernel): per directed edge 3*x+j
+// and per (pruned subtree, side); the Fitch records (fitch.h SprEdgeRec / SprSearchRec) plus the
+// P-matrix ids the likelihood visit needs.
+struct LikSprEdge {
+  int c, far_slot, far_sub, child_end;  // as SprEdgeRec
+  int p_t, p_h, pad0, pad1;             // P-matrix of the branch x--c, and of its half
+};
+struct LikSprSearch {
+  int start, from, x_in, visit_off;      // as SprSearchRec
+  int uniq_base, move_cnt, dup_flag, pe;
+  int p_in, tv, pad0, pad1;              // P-matrix of the merged branch other--start; operand id of the pruned subtree
+};
+
 struct LikWorkspace {
   DevBuf<double> clv;      // [slot][R*K][Ppad]
   DevBuf<int> scl;         // [slot][Ppad] per-pattern 2^-256 scaling counters
@@ -51,6 +64,8 @@ struct LikWorkspace {
   DevBuf<double> walk_stack;   // [warp][level][16][32]
   DevBuf<int> walk_stack_scl;  // [warp][level][32]
   DevBuf<unsigned long long> walk_counter;
+  DevBuf<int4> spr_edges, spr_searches, spr_moves;  // device-planned SPR neighbourhoods
+  DevBuf<double> spr_acct;                          // byte accounting of the planned walk (profiling)
   DevBuf<int32_t> tw_desc;     // tree walks (treewalk.h): raw descriptors, planned ops, planner scratch
   DevBuf<int4> tw_ops;
   DevBuf<int> tw_scratch;
@@ -81,6 +96,10 @@ struct LikProgram {
   std::vector<LikWalkVisit> walk_visits;  // depth-first search walks, run after the op levels
   std::vector<LikWalkGroup> walk_groups;  // longest first
   int walk_levels = 0;                    // stack levels a walk needs
+  // device-planned SPR neighbourhood: walk_visits stays empty, spr_lik_plan_kernel writes the visits
+  std::vector<LikSprEdge> spr_edges;
+  std::vector<LikSprSearch> spr_searches;
+  int64_t spr_n_visits = 0, spr_n_unique = 0;
   std::vector<double> brlens;      // unique branch lengths -> P-matrix index
   std::unordered_map<uint64_t, int> pm_index;
   int64_t n_slots = 0, n_trees = 0;
@@ -89,8 +108,9 @@ struct LikProgram {
 };
 
 void build_full_lik_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_rows, LikProgram &prog);
+// out_moves (device-planned SPR neighbourhoods only): int32 [spr_n_unique][4] on the host, or null
 void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, double *out_lnl,
-                     cudaStream_t st);
+                     cudaStream_t st, int32_t *out_moves = nullptr);
 void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double *out_lnl, cudaStream_t st);
 
 }  // namespace plg

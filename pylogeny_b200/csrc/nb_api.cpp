@@ -328,8 +328,30 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
   if (move_type == PLG_MOVE_TBR)
     return score_tbr_lik(a, m->impl, n_tips, desc, brlen, tip_rows, shard_index, shard_count, n_moves, out_moves,
                          out_lnl, (cudaStream_t)stream);
+  const int depth = depth_for(move_type);
+  // A whole SPR neighbourhood on one device (DNA x Gamma-4 walks): O(n) host records, the search
+  // walks are laid out by spr_lik_plan_kernel (PLG_LIK_NB_PLAN=host keeps the host planner)
+  const char *plan_env = std::getenv("PLG_LIK_NB_PLAN");
+  if (out_lnl && depth < 0 && shard_count == 1 && shard_index == 0 && n_tips >= 4 &&
+      n_tips <= (1 << WALK_MAX_LEVELS) && a.K == 4 && m->impl.R == 4 && lik_nb_mode() == LIK_NB_WALK &&
+      !(plan_env && !strcmp(plan_env, "host"))) {
+    size_t free_b = 0, total_b = 0;
+    PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t slot_bytes = ((size_t)m->impl.R * a.K * 8 + 4) * a.Ppad;
+    const size_t held = lik_workspace().clv.n * 8 + lik_workspace().scl.n * 4;
+    tm.lap("meminfo");
+    if ((size_t)3 * (n_tips - 2) * slot_bytes <= std::min<size_t>((free_b + held) / 2, (size_t)80 << 30)) {
+      static thread_local LikProgram p;
+      build_lik_spr_device_plan(utree_from_desc(n_tips, desc, brlen), tip_rows, a.n_rows, p);
+      tm.lap("prepare");
+      *n_moves = p.spr_n_unique;
+      run_lik_program(a, m->impl, lik_workspace(), p, out_lnl, (cudaStream_t)stream, out_moves);
+      tm.lap("run");
+      return PLG_OK;
+    }
+  }
   static thread_local Neighbourhood nb;
-  enumerate_spr(utree_from_desc(n_tips, desc, brlen), depth_for(move_type), nb);
+  enumerate_spr(utree_from_desc(n_tips, desc, brlen), depth, nb);
   tm.lap("enumerate");
   const int64_t M = (int64_t)nb.unique.size();
   *n_moves = M;

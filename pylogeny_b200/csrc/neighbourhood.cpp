@@ -717,21 +717,23 @@ static void emit_dir_program(const UTree &t, const DirOrder &d, const int32_t *t
   prog.n_scratch_slots = n_dir;
 }
 
-void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_slots, SprDevicePlan &out) {
-  out.search_edge.clear();
+// What the device planners share: one SprEdgeRec per directed edge, one SprSearchRec per search
+// (6 per internal node, enumeration order), one group per pruned subtree with a non-empty search
+// (pad = its directed edge 3*u+k; longest first), and the de-duplication of the distance-1 moves.
+namespace {
+struct SprSearchLayout {
+  std::vector<SprEdgeRec> edges;
+  std::vector<SprSearchRec> searches;
+  std::vector<FitchWalkGroup> groups;
+  std::vector<int> search_edge;
+  std::vector<int64_t> search_uniq;
+  int64_t n_visits = 0, n_unique = 0, dup_internal = 0, n_started = 0;
+};
+
+void layout_spr_searches(const UTree &t, const DirOrder &d, const std::vector<int> &dir_slot, SprSearchLayout &out) {
+  out.edges.clear(); out.searches.clear(); out.groups.clear(); out.search_edge.clear();
   out.search_uniq.assign(1, 0);
-  out.n_visits = out.n_unique = 0;
-  DirOrder d = dir_order(t);
-  std::vector<int> dir_slot;
-  emit_dir_program(t, d, tip_rows, n_tip_slots, out.base, dir_slot);
-  out.order = d.order;
-  FitchProgram &prog = out.base.prog;
-  prog.spr_edges.clear();
-  prog.spr_searches.clear();
-  prog.spr_n_visits = prog.spr_n_unique = 0;
-  prog.spr_first_acc = (int)out.base.first_move_acc;
-  prog.spr_vecs = prog.spr_req_vecs = 0;
-  prog.n_costs = out.base.first_move_acc;
+  out.n_visits = out.n_unique = out.dup_internal = out.n_started = 0;
   if (t.n_tips < 4) return;
   // leaves on x's side of edge x -> nb[x][k]
   std::vector<int> leaves((size_t)t.n_nodes * 3, 0);
@@ -743,7 +745,7 @@ void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_
       if (j != k) c += leaves[3 * t.nb[x][j] + t.slot_of(t.nb[x][j], x)];
     leaves[e] = c;
   }
-  prog.spr_edges.resize((size_t)t.n_nodes * 3);
+  out.edges.resize((size_t)t.n_nodes * 3);
   for (int x = 0; x < t.n_nodes; x++)
     for (int j = 0; j < 3; j++) {
       SprEdgeRec r;
@@ -756,7 +758,7 @@ void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_
         r.far_sub = leaves[back] - 1;
         r.child_end = t.rooted_child_end[3 * x + j];
       }
-      prog.spr_edges[3 * (size_t)x + j] = r;
+      out.edges[3 * (size_t)x + j] = r;
     }
   // hashes of the distance-1 moves (as enumerate_spr computes them) for the de-duplication
   uint64_t all;
@@ -766,13 +768,21 @@ void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_
     for (int k = 0; k < 3; k++)
       if (t.nb[x][k] > x) base += split_term(h[3 * x + k], all);
   auto far = [&](int x, int k) { const int y = t.nb[x][k]; return h[3 * y + t.slot_of(y, x)]; };
-  std::unordered_map<uint64_t, int> seen;
-  seen.reserve(32 * (size_t)t.n_tips);
-  std::vector<FitchWalkGroup> groups;
+  // open-addressing set of the 8(n-3) distance-1 hashes (0 = empty; a hash of 0 is stored as 1)
+  size_t cap = 64;
+  while (cap < 32 * (size_t)t.n_tips) cap <<= 1;
+  static thread_local std::vector<uint64_t> seen;
+  seen.assign(cap, 0);
+  auto first_time = [&](uint64_t key) {
+    if (key == 0) key = 1;
+    for (size_t i = splitmix(key) & (cap - 1);; i = (i + 1) & (cap - 1)) {
+      if (seen[i] == key) return false;
+      if (seen[i] == 0) { seen[i] = key; return true; }
+    }
+  };
   const int n_int = t.n_nodes - t.n_tips;
-  prog.spr_searches.resize((size_t)n_int * 6);
-  int64_t move_off = 0, dups = 0, dup_internal = 0, n_started = 0;
-  size_t si = 0;
+  out.searches.reserve((size_t)n_int * 6);
+  int64_t move_off = 0, dups = 0, vis_off = 0;
   for (int u = t.n_tips; u < t.n_nodes; u++)
     for (int k = 0; k < 3; k++) {
       int cur_group = -1;
@@ -785,56 +795,156 @@ void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_
         r.start = start;
         r.from = u;
         r.x_in = dir_slot[3 * other + t.slot_of(other, u)];
-        r.visit_off = (int)(move_off / 2);
+        r.visit_off = (int)vis_off;
         r.uniq_base = (int)(move_off - dups);
         r.move_cnt = t.is_tip(start) ? 0 : 2 * leaves[3 * start + t.slot_of(start, u)] - 2;
         r.dup_flag = pe == v ? 0 : 4;
         r.pe = pe;
+        const int n_moves = r.move_cnt;
         if (r.move_cnt > 0) {
           const uint64_t rem = split_term(far(u, ks), all);
-          int e = 0;
+          int e = 0, dup_int = 0;
           for (int j = 2; j >= 0; j--) {  // enumerate_spr writes the higher slot's move first
             if (t.nb[start][j] == u) continue;
             const uint64_t joined = split_term(far(start, j) ^ hv, all);
-            if (!seen.emplace(base - rem + joined, 1).second) {
+            if (!first_time(base - rem + joined)) {
               r.dup_flag |= 1 << e;
               dups++;
-              if (!t.is_tip(t.nb[start][j])) dup_internal++;
+              if (!t.is_tip(t.nb[start][j])) dup_int++;
             }
             e++;
           }
+          // a one-visit search whose two moves both repeat earlier topologies has nothing to do
+          // (the host planner drops it as well)
+          if (r.move_cnt == 2 && (r.dup_flag & 3) == 3) r.move_cnt = 0;
+          else out.dup_internal += dup_int;
+        }
+        if (r.move_cnt > 0) {
           if (cur_group < 0) {
             FitchWalkGroup g;
             g.tv = dir_slot[3 * v + t.slot_of(v, u)];
             g.first = r.visit_off;
             g.count = 0;
-            g.pad = 0;
-            groups.push_back(g);
-            cur_group = (int)groups.size() - 1;
+            g.pad = 3 * u + k;
+            out.groups.push_back(g);
+            cur_group = (int)out.groups.size() - 1;
           }
-          groups[cur_group].count += r.move_cnt / 2;
-          n_started++;
+          out.groups[cur_group].count += r.move_cnt / 2;
+          out.n_started++;
+          vis_off += r.move_cnt / 2;
         }
-        prog.spr_searches[si++] = r;
+        out.searches.push_back(r);
         out.search_edge.push_back(3 * u + k);
-        move_off += r.move_cnt;
+        move_off += n_moves;
         out.search_uniq.push_back(move_off - dups);
       }
     }
-  out.n_visits = move_off / 2;
+  out.n_visits = vis_off;
   out.n_unique = move_off - dups;
-  // longest searches first (the kernel's blocks are scheduled in group order)
-  std::stable_sort(groups.begin(), groups.end(),
+  // longest searches first (the kernels take groups in this order)
+  std::stable_sort(out.groups.begin(), out.groups.end(),
                    [](const FitchWalkGroup &a, const FitchWalkGroup &b) { return a.count > b.count; });
-  prog.walk_groups.resize(groups.size());
-  std::copy(groups.begin(), groups.end(), prog.walk_groups.data());
+}
+}  // namespace
+
+void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_slots, SprDevicePlan &out) {
+  DirOrder d = dir_order(t);
+  std::vector<int> dir_slot;
+  emit_dir_program(t, d, tip_rows, n_tip_slots, out.base, dir_slot);
+  out.order = d.order;
+  FitchProgram &prog = out.base.prog;
+  prog.spr_first_acc = (int)out.base.first_move_acc;
+  static thread_local SprSearchLayout lay;
+  layout_spr_searches(t, d, dir_slot, lay);
+  out.search_edge = lay.search_edge;
+  out.search_uniq = lay.search_uniq;
+  out.n_visits = lay.n_visits;
+  out.n_unique = lay.n_unique;
+  prog.spr_edges.resize(lay.edges.size());
+  std::copy(lay.edges.begin(), lay.edges.end(), prog.spr_edges.data());
+  prog.spr_searches.resize(lay.searches.size());
+  std::copy(lay.searches.begin(), lay.searches.end(), prog.spr_searches.data());
+  prog.walk_groups.resize(lay.groups.size());
+  std::copy(lay.groups.begin(), lay.groups.end(), prog.walk_groups.data());
   prog.spr_n_visits = out.n_visits;
   prog.spr_n_unique = out.n_unique;
   prog.n_costs = out.base.first_move_acc + out.n_unique;
   // byte accounting of the walk launch (run_fitch_program): a scored neighbour = fold + 3-way join
   // (6 vectors); a repeated distance-1 move still folds when the search continues below it
-  prog.spr_vecs = 6.0 * (double)out.n_unique + 3.0 * (double)dup_internal;
-  prog.spr_req_vecs = (double)groups.size() + 2.0 * (double)out.n_visits + (double)n_started;
+  prog.spr_vecs = 6.0 * (double)out.n_unique + 3.0 * (double)lay.dup_internal;
+  prog.spr_req_vecs = (double)lay.groups.size() + 2.0 * (double)out.n_visits + (double)lay.n_started;
+}
+
+// Likelihood twin of prepare_spr_device_plan: directional CLV updates of the base tree as level
+// ops, P-matrix ids of every branch (whole, halved) and of the three merged branches around every
+// internal node, and the records spr_lik_plan_kernel (lik.cu) expands into LikWalkVisits.
+void build_lik_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_rows, LikProgram &prog) {
+  prog.clear();
+  DirOrder d = dir_order(t);
+  std::vector<int> dir_slot((size_t)t.n_nodes * 3, -1);
+  for (int x = 0; x < t.n_tips; x++)
+    for (int k = 0; k < 3; k++) dir_slot[3 * x + k] = tip_rows ? tip_rows[x] : x;
+  prog.level_off.assign(d.max_level + 2, 0);
+  for (int e : d.order) prog.level_off[d.level[e] + 1]++;
+  for (int l = 0; l <= d.max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+  std::vector<int64_t> cur(prog.level_off.begin(), prog.level_off.end() - 1);
+  prog.ops.resize(d.order.size());
+  int64_t slots = 0;
+  for (int e : d.order) {
+    const int x = e / 3, k = e % 3;
+    LikOp o;
+    o.dst = n_rows + (int)slots++;
+    int s = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        const int c = t.nb[x][j];
+        const int id = dir_slot[3 * c + t.slot_of(c, x)];
+        const int pm = prog.pm(t.len[x][j]);
+        if (s == 0) { o.a = id; o.pa = pm; } else { o.b = id; o.pb = pm; }
+        s++;
+      }
+    dir_slot[e] = o.dst;
+    prog.ops[cur[d.level[e]]++] = o;
+  }
+  prog.n_slots = slots;
+  static thread_local SprSearchLayout lay;
+  layout_spr_searches(t, d, dir_slot, lay);
+  prog.spr_edges.resize(lay.edges.size());
+  for (size_t e = 0; e < lay.edges.size(); e++) {
+    const SprEdgeRec &r = lay.edges[e];
+    LikSprEdge &o = prog.spr_edges[e];
+    o.c = r.c; o.far_slot = r.far_slot; o.far_sub = r.far_sub; o.child_end = r.child_end;
+    o.p_t = o.p_h = 0; o.pad0 = o.pad1 = 0;
+    if (r.c >= 0) {
+      const double len = t.len[e / 3][e % 3];
+      o.p_t = prog.pm(len);
+      o.p_h = prog.pm(len / 2.0);  // target branch broken in half (rearrangement.py:466-470)
+    }
+  }
+  prog.spr_searches.resize(lay.searches.size());
+  for (size_t s = 0; s < lay.searches.size(); s++) {
+    const SprSearchRec &r = lay.searches[s];
+    LikSprSearch &o = prog.spr_searches[s];
+    o.start = r.start; o.from = r.from; o.x_in = r.x_in; o.visit_off = r.visit_off;
+    o.uniq_base = r.uniq_base; o.move_cnt = r.move_cnt; o.dup_flag = r.dup_flag; o.pe = r.pe;
+    const int e = lay.search_edge[s], u = e / 3, k = e % 3, side = (int)(s & 1);
+    const int ks = (k + 1 + side) % 3, ko = (k + 1 + (1 - side)) % 3, v = t.nb[u][k];
+    o.p_in = prog.pm(t.len[u][ko] + t.len[u][ks]);  // merged edge other -- start (rearrangement.py:480-490)
+    o.tv = dir_slot[3 * v + t.slot_of(v, u)];
+    o.pad0 = o.pad1 = 0;
+  }
+  prog.walk_groups.resize(lay.groups.size());
+  for (size_t g = 0; g < lay.groups.size(); g++) {
+    const FitchWalkGroup &f = lay.groups[g];
+    LikWalkGroup &o = prog.walk_groups[g];
+    o.tv = f.tv; o.p_v = prog.pm(t.len[f.pad / 3][f.pad % 3]); o.first = f.first; o.count = f.count;
+  }
+  prog.spr_n_visits = lay.n_visits;
+  prog.spr_n_unique = lay.n_unique;
+  prog.n_trees = lay.n_unique;
+  int lv = 1;
+  while ((1 << lv) < t.n_tips) lv++;
+  prog.walk_levels = lv + 1;  // the walk parks the larger side: depth <= log2(visits of a search) + 1
 }
 
 void finish_fitch_spr_plan(const UTree &t, const SprDevicePlan &p, const int32_t *acc, int32_t *out_costs) {

@@ -111,6 +111,10 @@ void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_
 // Fitch length of every distinct neighbour from the downloaded accumulators (no move array).
 void finish_fitch_spr_plan(const UTree &t, const SprDevicePlan &p, const int32_t *acc, int32_t *out_costs);
 
+// Likelihood twin: level ops of the base tree + the records spr_lik_plan_kernel expands (full SPR
+// neighbourhood, all distinct neighbours; prog.n_trees = their number).
+void build_lik_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_rows, LikProgram &prog);
+
 // lnL of the distinct neighbours [lo, hi) of an enumerated SPR/NNI neighbourhood (nb_api.cpp).
 void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *tip_rows, int64_t lo, int64_t hi,
                    double *out_lnl, cudaStream_t stream);

@@ -78,20 +78,21 @@ def score_parsimony(aln, desc, tip_rows=None, move_type=MOVE_SPR, shard=(0, 1), 
     return (moves[:n.value] if want_moves else None), costs[:n.value]
 
 
-def score_likelihood(aln, model, desc, brlen, tip_rows=None, move_type=MOVE_SPR, shard=(0, 1)):
-    """lnL (fixed branch lengths) of every distinct neighbour. aln: likelihood.LikAlignment."""
+def score_likelihood(aln, model, desc, brlen, tip_rows=None, move_type=MOVE_SPR, shard=(0, 1), want_moves=True):
+    """lnL (fixed branch lengths) of every distinct neighbour. aln: likelihood.LikAlignment.
+    Returns (moves int32 [M, 4] or None, lnl float64 [M])."""
     d = _desc(desc)
     b = np.ascontiguousarray(brlen, dtype=np.float64)
     rows = np.ascontiguousarray(tip_rows, dtype=np.int32) if tip_rows is not None else None
     n = C.c_int64()
     M = neighbourhood_size(d, move_type)
-    moves = np.empty((M, 4), dtype=np.int32)  # every row is written by the call
+    moves = np.empty((M, 4), dtype=np.int32) if want_moves else None  # every row is written by the call
     lnl = np.zeros(M, dtype=np.float64)
     _lib.check(_lib.lib().plg_lik_score_neighbourhood(
         aln._h, model._h, move_type, d.shape[0] + 1, d.ctypes.data, b.ctypes.data,
-        rows.ctypes.data if rows is not None else None, shard[0], shard[1], C.byref(n), moves.ctypes.data,
-        lnl.ctypes.data, None))
-    return moves[:n.value], lnl[:n.value]
+        rows.ctypes.data if rows is not None else None, shard[0], shard[1], C.byref(n),
+        moves.ctypes.data if want_moves else None, lnl.ctypes.data, None))
+    return (moves[:n.value] if want_moves else None), lnl[:n.value]
 
 
 def newick_to_desc(newick, taxa):

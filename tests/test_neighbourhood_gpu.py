@@ -227,3 +227,37 @@ def test_fitch_device_planned_spr_equals_host_planner(n, P, shape, monkeypatch):
     descs, _, _ = nbh.neighbour_trees(d)
     assert a.score_trees(descs, perm).tolist() == got["device"][1].tolist()
     a.close()
+
+
+@pytest.mark.parametrize("n,P", [(4, 40), (5, 70), (13, 333), (64, 500), (131, 200)])
+def test_lnl_device_planned_spr_equals_host_planner(n, P, monkeypatch):
+    """GTR+G4 lnL of a full SPR neighbourhood: search walks laid out on the device
+    (spr_lik_plan_kernel, default) vs by the host planner (PLG_LIK_NB_PLAN=host) -- same move table,
+    bit-identical lnL, and the same byte accounting in the profile records."""
+    import ctypes as C
+    from pylogeny_b200 import _lib, likelihood, neighbourhood as nbh
+    rng = np.random.default_rng(11 * n + P)
+    codes = (1 << rng.integers(0, 4, (n, P))).astype(np.uint8)
+    codes[rng.random((n, P)) < 0.02] = 15
+    w = rng.integers(1, 4, P).astype(np.float64)
+    a = likelihood.LikAlignment(codes, w)
+    m = likelihood.Model(rng.uniform(0.5, 2.0, 6), rng.dirichlet(np.ones(4) * 8), 0.6)
+    d = random_desc(rng, n)
+    br = rng.exponential(0.1, d.shape)
+    perm = rng.permutation(n).astype(np.int32)
+    L = _lib.lib()
+    got, acct = {}, {}
+    for plan in ("device", "host"):
+        monkeypatch.setenv("PLG_LIK_NB_PLAN", plan)
+        L.plg_profile_enable(1)
+        L.plg_profile_read(4, None, None, None, None, None)
+        got[plan] = nbh.score_likelihood(a, m, d, br, perm)
+        ms, by, un, nl, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
+        L.plg_profile_read(4, C.byref(ms), C.byref(by), C.byref(un), C.byref(nl), C.byref(rq))
+        L.plg_profile_enable(0)
+        acct[plan] = (by.value, un.value, nl.value, rq.value)
+        assert nbh.score_likelihood(a, m, d, br, perm, want_moves=False)[1].tolist() == got[plan][1].tolist()
+    assert got["device"][0].tolist() == got["host"][0].tolist()
+    assert got["device"][1].tolist() == got["host"][1].tolist()  # bit-identical
+    assert acct["device"] == pytest.approx(acct["host"], rel=1e-12)
+    a.close(); m.close()
