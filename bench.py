@@ -351,7 +351,8 @@ def run_ours(args):
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
     h2d = codes.nbytes + w.nbytes + d0.nbytes + br0.nbytes
     out["e2e"] = {"value": M * N_SITES / (np.mean(e2e_ms) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                  "d2h_bytes_per_step": int(lnl.nbytes), "ms_per_step": float(np.mean(e2e_ms)),
+                  "d2h_bytes_per_step": int(lnl.nbytes + moves.nbytes), "ms_per_step": float(np.mean(e2e_ms)),
+                  "ms_samples": [round(x, 3) for x in e2e_ms],
                   "note": "1 GPU, plg_lik_aln_create + plg_lik_score_neighbourhood + destroy per step"}
     if world == 1:
         if not args.no_cpu:

@@ -92,6 +92,17 @@ void prof_end(int kind, cudaStream_t st, double bytes, double units, double requ
   cudaEventRecord(b, st);
   g_prof_recs.push_back({kind, g_prof_open[kind], b, bytes, units, requested < 0 ? bytes : requested});
 }
+// fills in the byte accounting of the most recent record of a kind (device-planned walks learn it
+// from the GPU only when the call's results come back)
+void prof_patch_last(int kind, double bytes, double units, double requested) {
+  for (size_t i = g_prof_recs.size(); i-- > 0;)
+    if (g_prof_recs[i].kind == kind) {
+      g_prof_recs[i].bytes = bytes;
+      g_prof_recs[i].units = units;
+      g_prof_recs[i].requested = requested < 0 ? bytes : requested;
+      return;
+    }
+}
 }  // namespace plg
 
 extern "C" int plg_profile_enable(int on) {

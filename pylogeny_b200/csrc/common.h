@@ -66,6 +66,7 @@ void prof_begin(int kind, cudaStream_t st);
 // algorithmic_bytes: SURVEY.md 8d per-node-op figures (independent of fusion / operand sharing);
 // requested_bytes: what this implementation actually loads and stores (< 0: same as algorithmic)
 void prof_end(int kind, cudaStream_t st, double algorithmic_bytes, double units, double requested_bytes = -1.0);
+void prof_patch_last(int kind, double algorithmic_bytes, double units, double requested_bytes);
 
 // PLG_TIMING=1: host-side stage times on stderr.
 struct StageTimer {

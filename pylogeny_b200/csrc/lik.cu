@@ -776,13 +776,7 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       if (out_moves)
         PLG_CUDA(cudaMemcpyAsync(out_moves, ws.spr_moves.p, (size_t)prog.spr_n_unique * sizeof(int4),
                                  cudaMemcpyDeviceToHost, st));
-      if (acct_on) {  // (profiling only: one extra round trip before the walk is launched)
-        double h[2];
-        PLG_CUDA(cudaMemcpyAsync(h, ws.spr_acct.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-        PLG_CUDA(cudaStreamSynchronize(st));
-        bytes = h[0]; req = h[1];
-        for (const LikWalkGroup &g : prog.walk_groups) req += opnd(g.tv) + 8.0;
-      }
+      // (profiling: the accounting sums come back with the results, run_lik_program patches the record)
       units = 2.0 * (double)prog.spr_n_visits;
     } else {
       PLG_CUDA(cudaMemcpyAsync(ws.walk_visits.p, prog.walk_visits.data(),
@@ -807,6 +801,8 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     prof_begin(PROF_WALK, st);
     if (dmma) {
       const int smem = WM_WARPS * WM_SMEM_DOUBLES_PER_WARP * 8;
+      static bool wm_attr_set[64] = {false};
+      ensure_dyn_smem(walk4m_kernel, smem, wm_attr_set);
       walk4m_kernel<<<n_blocks, WM_THREADS, smem, st>>>(ws.walk_groups.p, (int)prog.walk_groups.size(), ws.walk_visits.p,
                                                        n_items, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p,
                                                        ws.pmat.p, ws.clv.p, ws.scl.p, ws.walk_stack.p,
@@ -915,7 +911,15 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   if (out_lnl && prog.n_trees) {
     StageTimer tm;
     PLG_CUDA(cudaMemcpyAsync(out_lnl, ws.lnl.p, (size_t)prog.n_trees * 8, cudaMemcpyDeviceToHost, st));
+    const bool acct = dna4 && prog.spr_n_visits > 0 && prof_enabled();
+    double h[2] = {0.0, 0.0};
+    if (acct) PLG_CUDA(cudaMemcpyAsync(h, ws.spr_acct.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     PLG_CUDA(cudaStreamSynchronize(st));
+    if (acct) {  // byte accounting of the device-planned walk (per pattern) -> its profile record
+      const double Cb = 4 * 4 * 8.0 + 4.0;
+      for (const LikWalkGroup &g : prog.walk_groups) h[1] += (g.tv < a.n_rows ? 1.0 : Cb) + 8.0;
+      prof_patch_last(PROF_WALK, h[0] * (double)a.P, 2.0 * (double)prog.spr_n_visits * (double)a.P, h[1] * (double)a.P);
+    }
     tm.lap("    sync+D2H");
   }
 }

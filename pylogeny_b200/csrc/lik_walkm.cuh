@@ -42,7 +42,18 @@ constexpr int WM_NG = PLG_WM_NG;
 constexpr int WM_V = 4 * WM_NG;          // doubles per vector per lane: [category r][group j] = v[r * WM_NG + j]
 constexpr int WM_PATTERNS = 8 * WM_NG;   // patterns per warp item
 static_assert(WM_NG == 4 || WM_NG == 2, "a warp carries 32 or 16 patterns");
-constexpr int WM_SMEM_DOUBLES_PER_WARP = (2 + PLG_WM_PARK_H2) * WM_V * 32;  // parked: tvv, h1 (, h2)
+#ifndef PLG_WM_STAGE
+#define PLG_WM_STAGE 0     // 1: the far-side operands of the NEXT visit are fetched by cp.async into shared memory during this one
+                           //    (B200: 9.2 vs 7.9 ms -- 209 KB of shared memory leave no L1 for the spills and fragments)
+#endif
+#ifndef PLG_WM_PF
+#define PLG_WM_PF 0        // 1: ... or pulled into L1 by one prefetch instruction per operand (32 lines, one per lane): 8.03 vs 7.76 ms
+#endif
+// staging area of one operand: 9 rows of 16 B per lane (8 rows CLV + 1 row scaling counters; a tip uses 8 B of row 0)
+constexpr int WM_STAGE_ROWS = 9;
+constexpr int WM_STAGE_DOUBLES = PLG_WM_STAGE ? 2 * WM_STAGE_ROWS * 2 * 32 : 0;  // two operands
+static_assert(!PLG_WM_STAGE || WM_NG == 4, "operand staging is written for 32 patterns per warp");
+constexpr int WM_SMEM_DOUBLES_PER_WARP = (2 + PLG_WM_PARK_H2) * WM_V * 32 + WM_STAGE_DOUBLES;  // parked: tvv, h1 (, h2); staged D1, D2
 
 __device__ __forceinline__ void wm_dmma(double &d0, double &d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
@@ -111,6 +122,73 @@ __device__ __forceinline__ void wm_load_raw(int id, int n_rows, int64_t Ppad, in
   }
 }
 
+// Asynchronous copy of operand `id` (as wm_load_raw reads it) into this lane's staging slots:
+// every lane fetches exactly the bytes it will consume, so no cross-lane synchronisation is needed
+// (cp.async.wait_group is per thread).  sdst = shared address of row 0 of this lane; rows are 512 B apart.
+__device__ __forceinline__ void wm_stage(int id, int n_rows, int64_t Ppad, int64_t p0, int lane,
+                                         const unsigned char *__restrict__ codes, const double *__restrict__ clv,
+                                         const int *__restrict__ scl, unsigned int sdst) {
+  const int g2 = (lane >> 2) * 2, q = lane & 3;
+  if (id < n_rows) {
+    const unsigned char *c = codes + (int64_t)id * Ppad + p0 + (g2 & ~3);  // the aligned word holding codes g2, g2+1
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sdst), "l"(c));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sdst + 4), "l"(c + 16));
+  } else {
+    const double *b = clv + (int64_t)(id - n_rows) * 16 * Ppad + p0 + g2;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const double *src = b + (int64_t)(r * 4 + q) * Ppad;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst + (2 * r) * 512), "l"(src));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst + (2 * r + 1) * 512), "l"(src + 16));
+    }
+    const int *sp = scl + (int64_t)(id - n_rows) * Ppad + p0 + g2;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst + 8 * 512), "l"(sp));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst + 8 * 512 + 8), "l"(sp + 16));
+  }
+}
+
+// the staged operand in layout V (what wm_load_raw returns); src = this lane's row 0
+__device__ __forceinline__ void wm_unstage(int id, int n_rows, int lane, const double2 *src, double (&x)[WM_V],
+                                           int (&s)[WM_NG]) {
+  const int q = lane & 3;
+  if (id < n_rows) {
+    const uint2 w = *reinterpret_cast<const uint2 *>(src);
+    const int sh = ((lane >> 2) & 1) * 16;  // (g2 & 2) * 8: which half of the aligned word
+    const unsigned int lo = (w.x >> sh) & 0xFFFFu, hi = (w.y >> sh) & 0xFFFFu;
+    unsigned int m[4] = {lo & 255u, lo >> 8, hi & 255u, hi >> 8};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned int mask = m[j] ? m[j] : 15u;
+      const double ind = (mask >> q & 1u) ? 1.0 : 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) x[r * 4 + j] = ind;
+      s[j] = 0;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const double2 u = src[(2 * r) * 32], v = src[(2 * r + 1) * 32];
+      x[r * 4] = u.x; x[r * 4 + 1] = u.y; x[r * 4 + 2] = v.x; x[r * 4 + 3] = v.y;
+    }
+    const int4 c = *reinterpret_cast<const int4 *>(src + 8 * 32);
+    s[0] = c.x; s[1] = c.y; s[2] = c.z; s[3] = c.w;
+  }
+}
+
+// L1 prefetch of operand `id` for this warp's slice: an inner CLV is 16 rows x 2 half-slices of
+// 128 B (one line per lane) + one line of scaling counters; a tip is one 32-byte piece of a code row.
+__device__ __forceinline__ void wm_prefetch(int id, int n_rows, int64_t Ppad, int64_t p0, int lane,
+                                            const unsigned char *__restrict__ codes, const double *__restrict__ clv,
+                                            const int *__restrict__ scl) {
+  if (id < n_rows) {
+    if (lane == 0) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(codes + (int64_t)id * Ppad + p0));
+  } else {
+    const double *b = clv + (int64_t)(id - n_rows) * 16 * Ppad + p0 + (int64_t)(lane >> 1) * Ppad + (lane & 1) * 16;
+    asm volatile("prefetch.global.L1 [%0];\n" ::"l"(b));
+    if (lane == 0) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(scl + (int64_t)(id - n_rows) * Ppad + p0));
+  }
+}
+
 // per pattern: all 16 entries below 2^-256 -> multiply by 2^256 and count (libpll's scaling).
 // A pattern's entries sit in the four lanes of a quad: one vote per pattern group.
 __device__ __forceinline__ void wm_rescale(double (&n)[WM_V], int (&sc)[WM_NG], int lane) {
@@ -175,6 +253,12 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
   extern __shared__ __align__(16) double wm_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 3;
   double(*park)[WM_V][32] = reinterpret_cast<double(*)[WM_V][32]>(wm_smem + warp * WM_SMEM_DOUBLES_PER_WARP);  // [0] tvv, [1] h1
+#if PLG_WM_STAGE
+  // staged far-side operands of the visit about to run: [operand][row][lane] 16-byte units
+  const double2 *stg = reinterpret_cast<const double2 *>(wm_smem + warp * WM_SMEM_DOUBLES_PER_WARP +
+                                                         (2 + PLG_WM_PARK_H2) * WM_V * 32) + lane;
+  const unsigned int stg_s = (unsigned int)__cvta_generic_to_shared(stg);
+#endif
   const int64_t gw = (int64_t)blockIdx.x * WM_WARPS + warp;
   double *stk = stack_clv + gw * stack_levels * WM_V * 32 + lane;
   int *stks = stack_scl + gw * stack_levels * WM_NG * 32 + lane;
@@ -194,6 +278,11 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
     // pipeline: descriptors two visits ahead (one int per lane), matrix fragments one visit ahead
     int dcur = wm_desc_load(visits, g.first, lane);
     int dnxt = g.count > 1 ? wm_desc_load(visits, g.first + 1, lane) : 0;
+#if PLG_WM_STAGE
+    wm_stage(__shfl_sync(0xffffffffu, dcur, 2), n_rows, Ppad, p0, lane, codes, clv, scl, stg_s);
+    wm_stage(__shfl_sync(0xffffffffu, dcur, 5), n_rows, Ppad, p0, lane, codes, clv, scl, stg_s + WM_STAGE_ROWS * 512);
+    asm volatile("cp.async.commit_group;\n" ::);
+#endif
     double bf1[4], bf2[4];
     wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 3), __shfl_sync(0xffffffffu, dcur, 4), lane, bf1);
     wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 6), __shfl_sync(0xffffffffu, dcur, 7), lane, bf2);
@@ -250,7 +339,12 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
       int s1[WM_NG], sc2[WM_NG];
       {
         double x[WM_V], h1[WM_V];
+#if PLG_WM_STAGE
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        wm_unstage(d1, n_rows, lane, stg, x, s1);
+#else
         wm_load_raw(d1, n_rows, Ppad, p0, lane, codes, clv, scl, x, s1);
+#endif
         wm_pair(x, bf1, n2, h1);
         __syncwarp();
 #pragma unroll
@@ -264,7 +358,23 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
       int s2[WM_NG], sc1[WM_NG];
       {
         double x[WM_V];
+#if PLG_WM_STAGE
+        wm_unstage(d2, n_rows, lane, stg + WM_STAGE_ROWS * 32, x, s2);
+        if (vi + 1 < v_end) {  // both operands are in registers: fetch the next visit's into the same slots
+          wm_stage(__shfl_sync(0xffffffffu, dnxt, 2), n_rows, Ppad, p0, lane, codes, clv, scl, stg_s);
+          wm_stage(__shfl_sync(0xffffffffu, dnxt, 5), n_rows, Ppad, p0, lane, codes, clv, scl,
+                   stg_s + WM_STAGE_ROWS * 512);
+          asm volatile("cp.async.commit_group;\n" ::);
+        }
+#else
         wm_load_raw(d2, n_rows, Ppad, p0, lane, codes, clv, scl, x, s2);
+#if PLG_WM_PF
+        if (vi + 1 < v_end) {
+          wm_prefetch(__shfl_sync(0xffffffffu, dnxt, 2), n_rows, Ppad, p0, lane, codes, clv, scl);
+          wm_prefetch(__shfl_sync(0xffffffffu, dnxt, 5), n_rows, Ppad, p0, lane, codes, clv, scl);
+        }
+#endif
+#endif
         wm_pair(x, bf2, n1, h2);
 #pragma unroll
         for (int i = 0; i < WM_V; i++) n1[i] *= ak[i];
