@@ -26,6 +26,9 @@ namespace plg {
 
 constexpr double TWO256 = 1.15792089237316195423570985008687907853269984665640564039457584007913129639936e77;
 constexpr double MINLH = 1.0 / TWO256;
+// log(2^-256) = -256 RN(ln 2) exactly (a power-of-two multiple of the correctly rounded ln 2); spelling it
+// log(MINLH) in device code costs a full FP64 log evaluation per site term -- nvcc does not fold it
+constexpr double LOG_MINLH = -256.0 * 0.693147180559945309417232121458176568;
 constexpr int LIK_THREADS = 256;
 
 template <int K>
@@ -212,7 +215,7 @@ root_eval_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_r
   double val = 0.0;
   if (r == 0) {
     const double w = weights[p];
-    if (w != 0.0) val = w * (log(term * (1.0 / R)) + sc * log(MINLH));
+    if (w != 0.0) val = w * (log(term * (1.0 / R)) + sc * LOG_MINLH);
   }
   // fixed-shape block reduction (deterministic order)
 #pragma unroll

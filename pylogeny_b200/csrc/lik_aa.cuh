@@ -229,7 +229,7 @@ eval20_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_rows
       if (ev.a >= n_rows) sc += scl[(int64_t)(ev.a - n_rows) * Ppad + p];
       if (ev.b >= n_rows) sc += scl[(int64_t)(ev.b - n_rows) * Ppad + p];
       if (ev.c >= n_rows) sc += scl[(int64_t)(ev.c - n_rows) * Ppad + p];
-      val = w * (log(term * 0.25) + sc * log(MINLH));
+      val = w * (log(term * 0.25) + sc * LOG_MINLH);
     }
   }
   if (threadIdx.x < A20_TILE) {  // warps 0 and 1 hold the 64 site values: fixed-order reduction

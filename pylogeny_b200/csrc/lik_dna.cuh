@@ -119,7 +119,7 @@ __device__ __forceinline__ void d4_site_sum(const double (&v)[16], int sc, int64
   for (int k = 0; k < 4; k++) term = fma(model->freqs[k], (v[k] + v[4 + k]) + (v[8 + k] + v[12 + k]), term);
   const double w = weights[p];
   double val = 0.0;
-  if (w != 0.0) val = w * (log(term * 0.25) + sc * log(MINLH));
+  if (w != 0.0) val = w * (log(term * 0.25) + sc * LOG_MINLH);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
   if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = val;
@@ -338,7 +338,7 @@ clv4r_kernel(const LikOpF *__restrict__ ops, int blocks_per_op, int n_rows, int6
     if (r == 0) {
       const double w = weights[p];
       double val = 0.0;
-      if (w != 0.0) val = w * (log(((xr[0][lane] + xr[1][lane]) + (xr[2][lane] + xr[3][lane])) * 0.25) + sc * log(MINLH));
+      if (w != 0.0) val = w * (log(((xr[0][lane] + xr[1][lane]) + (xr[2][lane] + xr[3][lane])) * 0.25) + sc * LOG_MINLH);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
       if (lane == 0) partial[(int64_t)op.tree * pstride + pb] = val;

@@ -85,7 +85,7 @@ __device__ __forceinline__ double v4_site(const double (&e)[16], int sc, double 
   double term = 0.0;
 #pragma unroll
   for (int k = 0; k < 4; k++) term = fma(model->freqs[k], (e[k] + e[4 + k]) + (e[8 + k] + e[12 + k]), term);
-  return w != 0.0 ? w * (log(term * 0.25) + sc * log(MINLH)) : 0.0;
+  return w != 0.0 ? w * (log(term * 0.25) + sc * LOG_MINLH) : 0.0;
 }
 
 __global__ void __launch_bounds__(V4_THREADS, 3)

@@ -231,7 +231,7 @@ __device__ __forceinline__ double wm_site_sum(const double (&e)[WM_V], const int
     scq = odd ? sc[1] : sc[0];
     if (hi) w_out = 0.0;
   }
-  double val = w_out != 0.0 ? w_out * (log(L * 0.25) + scq * log(MINLH)) : 0.0;
+  double val = w_out != 0.0 ? w_out * (log(L * 0.25) + scq * LOG_MINLH) : 0.0;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
   return val;

@@ -29,6 +29,7 @@ namespace plg {
 
 constexpr double PLL_ZMIN = 1.0e-15, PLL_ZMAX = 1.0 - 1.0e-6, PLL_DEFAULTZ = 0.9, PLL_DELTAZ = 1.0e-5;
 constexpr double SM_MINLH = 8.636168555094445e-78;  // 2^-256
+constexpr double SM_LOG_MINLH = -256.0 * 0.693147180559945309417232121458176568;  // log(2^-256), folded
 constexpr int SM_THREADS = 256;
 
 extern const double *const WAG_EXCH_PTR;  // protein_models.cpp
@@ -102,7 +103,7 @@ deriv_kernel(const double *__restrict__ S, const int *__restrict__ sc, const dou
   const double w = weights[p];
   if (r == 0 && w != 0.0) {
     const double inv = 1.0 / l0, d1 = l1 * inv;
-    v0 = w * (log(l0 * (1.0 / R)) + sc[p] * log(SM_MINLH));
+    v0 = w * (log(l0 * (1.0 / R)) + sc[p] * SM_LOG_MINLH);
     v1 = w * d1;
     v2 = w * (l2 * inv - d1 * d1);
   }
