@@ -864,7 +864,39 @@ static void run_aa20(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, (double)c * (double)a.P);
     }
   }
-  const int64_t n_ev = (int64_t)prog.evals.size();
+  int64_t n_ev = (int64_t)prog.evals.size();
+  // evaluations without matrices whose first operand repeats (TBR pairs): one block keeps that
+  // operand's tile in registers for the whole row (PLG_AA_EVAL_ROWS=0: the per-evaluation kernel)
+  bool rows_ok = n_ev > 0;
+  if (const char *e = getenv("PLG_AA_EVAL_ROWS")) rows_ok = rows_ok && atoi(e) != 0;
+  for (int64_t q = 0; rows_ok && q < n_ev; q++)
+    rows_ok = prog.evals[q].pa < 0 && prog.evals[q].pb < 0 && prog.evals[q].c < 0;
+  if (rows_ok) {
+    std::vector<LikEvalRow> rows;
+    double bytes = 0, req = 0;
+    for (int64_t q = 0; q < n_ev;) {
+      int64_t j = q + 1;
+      while (j < n_ev && prog.evals[j].a == prog.evals[q].a) j++;
+      rows.push_back({prog.evals[q].a, (int)q, (int)(j - q), 0});
+      req += opnd(prog.evals[q].a);
+      for (int64_t i = q; i < j; i++) {
+        bytes += 8.0 + opnd(prog.evals[i].a) + opnd(prog.evals[i].b);
+        req += 8.0 + opnd(prog.evals[i].b);
+      }
+      q = j;
+    }
+    static thread_local DevBuf<int4> d_rows;
+    d_rows.alloc(rows.size());
+    PLG_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), rows.size() * sizeof(LikEvalRow), cudaMemcpyHostToDevice, st));
+    prof_begin(PROF_ROOT_EVAL, st);
+    eval20_rows_kernel<<<(unsigned)(rows.size() * bpo), A20_THREADS, 0, st>>>(
+        reinterpret_cast<const LikEvalRow *>(d_rows.p), (int)rows.size(), ws.evals.p, (int)bpo, a.n_rows, a.Ppad,
+        a.codes.p, a.masks.p, a.weights.p, m.d.p, ws.clv.p, ws.scl.p, ws.partial.p);
+    count_launch();
+    prof_end(PROF_ROOT_EVAL, st, bytes * (double)a.P, (double)n_ev * (double)a.P, req * (double)a.P);
+    PLG_CUDA(cudaStreamSynchronize(st));  // `rows` is pageable host memory
+    n_ev = 0;
+  }
   const int64_t max_ev = std::max<int64_t>(1, ((int64_t)1 << 30) / bpo);
   for (int64_t e = 0; e < n_ev; e += max_ev) {
     const int64_t c = std::min(max_ev, n_ev - e);

@@ -241,4 +241,76 @@ eval20_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_rows
   if (threadIdx.x == 0) partial[(int64_t)ev.tree * blocks_per_eval + pb] = wsum[0] + wsum[1];
 }
 
+// Rows of evaluations that share their first operand and need no matrix (TBR pairs: one rooted
+// vector of part 1 against every candidate of part 2 already pushed through the reconnecting
+// branch).  The shared operand's tile stays in registers while the row's second operands stream
+// past it: 644 instead of 1288 bytes per pair and pattern.  Blocks are ordered tile-major, so the
+// rows in flight at any time read the same pattern tile of the same candidate set and hit in L2.
+// Arithmetic and reduction order are those of eval20_kernel (bit-identical results).
+struct LikEvalRow {
+  int a, first, count, pad;
+};
+
+__global__ void __launch_bounds__(A20_THREADS)
+eval20_rows_kernel(const LikEvalRow *__restrict__ rows, int n_ev_rows, const LikEval *__restrict__ evals, int tiles,
+                   int n_rows, int64_t Ppad, const unsigned char *__restrict__ codes,
+                   const unsigned int *__restrict__ masks, const double *__restrict__ weights,
+                   const ModelDev *__restrict__ model, const double *__restrict__ clv, const int *__restrict__ scl,
+                   double *__restrict__ partial) {
+  __shared__ double sterm[4][A20_TILE];
+  __shared__ double wsum[2];
+  const int tile = blockIdx.x / n_ev_rows;
+  const LikEvalRow rw = rows[blockIdx.x - tile * n_ev_rows];
+  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int64_t pbase = (int64_t)tile * A20_TILE;
+  double fr[3];
+#pragma unroll
+  for (int mt = 0; mt < 3; mt++) fr[mt] = (mt * 8 + g) < 20 ? model->freqs[mt * 8 + g] : 0.0;
+  double av[A20_TILE / 8][3][2];
+#pragma unroll
+  for (int nt = 0; nt < A20_TILE / 8; nt++) a20_raw(rw.a, n_rows, r, pbase + nt * 8, lane, Ppad, codes, masks, clv, av[nt]);
+  double w = 0.0;
+  int sa = 0;
+  if (threadIdx.x < A20_TILE) {
+    w = weights[pbase + threadIdx.x];
+    if (rw.a >= n_rows) sa = scl[(int64_t)(rw.a - n_rows) * Ppad + pbase + threadIdx.x];
+  }
+  for (int e = rw.first; e < rw.first + rw.count; e++) {
+    const int b = evals[e].b, tree = evals[e].tree;
+#pragma unroll
+    for (int nt = 0; nt < A20_TILE / 8; nt++) {
+      double x[3][2];
+      a20_raw(b, n_rows, r, pbase + nt * 8, lane, Ppad, codes, masks, clv, x);
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int mt = 0; mt < 3; mt++) {
+        s0 = fma(fr[mt], av[nt][mt][0] * x[mt][0], s0);
+        s1 = fma(fr[mt], av[nt][mt][1] * x[mt][1], s1);
+      }
+#pragma unroll
+      for (int d = 4; d < 32; d <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+      }
+      if (g == 0) { sterm[r][nt * 8 + 2 * t] = s0; sterm[r][nt * 8 + 2 * t + 1] = s1; }
+    }
+    __syncthreads();
+    if (threadIdx.x < A20_TILE) {
+      const int q = threadIdx.x;
+      double val = 0.0;
+      if (w != 0.0) {
+        const double term = (sterm[0][q] + sterm[1][q]) + (sterm[2][q] + sterm[3][q]);
+        int sc = sa;
+        if (b >= n_rows) sc += scl[(int64_t)(b - n_rows) * Ppad + pbase + q];
+        val = w * (log(term * 0.25) + sc * LOG_MINLH);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
+      if (lane == 0) wsum[r] = val;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) partial[(int64_t)tree * tiles + tile] = wsum[0] + wsum[1];
+  }
+}
+
 }  // namespace plg

@@ -160,7 +160,8 @@ void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *
   int64_t chunk = hi - lo;
   for (int64_t c0 = lo; c0 < hi;) {
     int64_t c1 = std::min(hi, c0 + chunk);
-    build_lik_nb_program(nb, tip_rows, a.n_rows, c0, c1, p, a.K == 4 && m.R == 4 ? lik_nb_mode() : LIK_NB_OPS);
+    const bool dna4 = a.K == 4 && m.R == 4;
+    build_lik_nb_program(nb, tip_rows, a.n_rows, c0, c1, p, dna4 ? lik_nb_mode() : LIK_NB_OPS, !dna4);
     if (p.n_slots > max_slots && c1 - c0 > 1) {
       chunk = std::max<int64_t>(1, (c1 - c0) / 2);
       continue;

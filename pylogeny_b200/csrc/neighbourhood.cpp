@@ -998,7 +998,7 @@ void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int
 }
 
 void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
-                          LikProgram &prog, int mode) {
+                          LikProgram &prog, int mode, bool hoist_eval) {
   const bool use_visits = mode == LIK_NB_VISITS;
   const UTree &t = nb.t;
   prog.clear();
@@ -1214,6 +1214,22 @@ void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int 
     n_slot[i] = o.op.dst;
     tmp.push_back(o);
   }
+  // hoisted operands: H[x, kx] = P_half D[c->x], TVV[u, k] = P_v D[v->u] (directional partials only,
+  // so they all sit one level above the base tree's pass)
+  std::vector<int> h_slot, tvv_slot;
+  if (hoist_eval) { h_slot.assign((size_t)t.n_nodes * 3, -1); tvv_slot.assign((size_t)t.n_nodes * 3, -1); }
+  auto hoisted = [&](std::vector<int> &memo, int e, int operand, double len) {
+    if (memo[e] < 0) {
+      Tmp o;
+      o.op.dst = n_rows + (int)slots++;
+      o.op.a = operand; o.op.pa = prog.pm(len);
+      o.op.b = -1; o.op.pb = -1;
+      o.level = d.max_level + 1;
+      memo[e] = o.op.dst;
+      tmp.push_back(o);
+    }
+    return memo[e];
+  };
   for (int64_t i = lo; i < hi; i++) {
     const int mi = nb.unique[i];
     const Move &m = nb.moves[mi];
@@ -1223,6 +1239,10 @@ void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int 
     ev.a = n_slot[mi]; ev.pa = prog.pm(half);
     ev.b = dir_slot[3 * c + t.slot_of(c, m.x)]; ev.pb = prog.pm(half);
     ev.c = dir_slot[3 * v + t.slot_of(v, m.u)]; ev.pc = prog.pm(t.len[m.u][m.k]);
+    if (hoist_eval) {
+      ev.b = hoisted(h_slot, 3 * m.x + m.kx, ev.b, half); ev.pb = -1;
+      ev.c = hoisted(tvv_slot, 3 * m.u + m.k, ev.c, t.len[m.u][m.k]); ev.pc = -1;
+    }
     ev.tree = (int)(i - lo);
     ev.pad = 0;
     prog.evals.push_back(ev);
@@ -1343,7 +1363,8 @@ UTree apply_tbr(const TbrNeighbourhood &nb, const TbrPair &p) {
 }
 
 int64_t tbr_slots_needed(const TbrNeighbourhood &nb, int e0, int e1) {
-  return 3 * (int64_t)nb.t.n_nodes + 2 * (nb.edge_cand_off[2 * e1] - nb.edge_cand_off[2 * e0]);
+  // per candidate: search-step partial N, rooted vector R and (likelihood) R pushed through the reconnecting branch
+  return 3 * (int64_t)nb.t.n_nodes + 3 * (nb.edge_cand_off[2 * e1] - nb.edge_cand_off[2 * e0]);
 }
 
 namespace {
@@ -1556,15 +1577,36 @@ void build_lik_tbr_program(const TbrNeighbourhood &nb, const int32_t *tip_rows, 
     r_slot[ci - c_lo] = q.op.dst;
     tmp.push_back(q);
   }
+  // The reconnecting branch is the same for every pair of a bisection: push each second-part
+  // candidate through it ONCE (Q = P_v R2, a one-operand update) instead of once per pair; a pair
+  // is then an elementwise product of two stored vectors.
+  int top_level = 0;
+  for (auto &o : tmp) top_level = std::max(top_level, o.level);
+  std::vector<int> q_slot(c_hi - c_lo, -1);
   const int64_t p_lo = nb.edge_pair_off[e0];
   for (int e = e0; e < e1; e++) {
     const int u = nb.edges[e][0], k = nb.edges[e][1];
     const int pmv = prog.pm(t.len[u][k]);  // the reconnecting branch keeps the removed branch's length
+    // ... on the side with fewer candidates (the model is reversible: pi_k a_k (P b)_k sums to the
+    // same as pi_k (P a)_k b_k); a pendant branch has ONE candidate on its tip side
+    const bool push_second = nb.edge_cand_off[2 * e + 2] - nb.edge_cand_off[2 * e + 1] <=
+                             nb.edge_cand_off[2 * e + 1] - nb.edge_cand_off[2 * e];
     for (int64_t pi = nb.edge_pair_off[e]; pi < nb.edge_pair_off[e + 1]; pi++) {
       const TbrPair &p = nb.pairs[pi];
-      LikEval ev;
-      ev.a = r_slot[p.c1 - c_lo]; ev.pa = -1;
-      ev.b = r_slot[p.c2 - c_lo]; ev.pb = pmv;
+      const int64_t cq = push_second ? p.c2 : p.c1, cr = push_second ? p.c1 : p.c2;
+      int &q = q_slot[cq - c_lo];
+      if (q < 0) {
+        Tmp o;
+        o.op.dst = n_rows + (int)slots++;
+        o.op.a = r_slot[cq - c_lo]; o.op.pa = pmv;
+        o.op.b = -1; o.op.pb = -1;
+        o.level = top_level + 1;
+        q = o.op.dst;
+        tmp.push_back(o);
+      }
+      LikEval ev;  // pairs are listed c1-major: operand a is the one that stays while c2 runs
+      ev.a = push_second ? r_slot[cr - c_lo] : q; ev.pa = -1;
+      ev.b = push_second ? q : r_slot[cr - c_lo]; ev.pb = -1;
       ev.c = -1; ev.pc = -1; ev.pad = 0;
       ev.tree = (int)(pi - p_lo);
       prog.evals.push_back(ev);

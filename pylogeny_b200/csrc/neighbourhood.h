@@ -87,12 +87,16 @@ void build_fitch_nb_walk_program(const Neighbourhood &nb, const int32_t *tip_row
 void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int32_t *acc, int64_t lo, int64_t hi,
                      int32_t *out_costs);
 
+// hoist_eval (mode LIK_NB_OPS): the far side of every target branch and every pruned subtree are
+// pushed through their branches once (one-operand updates) instead of once per neighbour, so an
+// evaluation multiplies one matrix instead of three (the 20-state kernels; the DNA level kernels
+// fuse the whole evaluation into the update instead).
 // mode: LIK_NB_OPS one CLV update + one 3-way evaluation per neighbour (any state count);
 // LIK_NB_WALK depth-first search walks (LikWalkVisit, lik_walk.cuh; DNA x Gamma-4);
 // LIK_NB_VISITS: emit one LikVisit per search step (both neighbours at the node it reaches; DNA x
 // Gamma-4 kernels) instead of one CLV update + one 3-way evaluation per neighbour.
 void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
-                          LikProgram &out, int mode = LIK_NB_OPS);
+                          LikProgram &out, int mode = LIK_NB_OPS, bool hoist_eval = false);
 
 // Device-planned full SPR neighbourhood (parsimony).  The host does O(n) work only: the base tree's
 // directional ops, one SprEdgeRec per directed edge, one SprSearchRec per search (pruned subtree
