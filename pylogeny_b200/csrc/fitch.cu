@@ -382,9 +382,19 @@ void FitchProgram::clear() {
 // slot first, two per visit (higher slot's move first); only the first two moves of a search can
 // repeat an earlier topology (dup bits).  The walk itself descends into the smaller subtree first
 // and parks the other partial, so the stack never exceeds log2(n) + 1 frames.
+constexpr size_t SPR_PLAN_SMEM_MAX = 200 << 10;  // edge records of trees up to ~4,000 (parsimony) / ~2,000 (likelihood) taxa
 __global__ void __launch_bounds__(64)
-spr_plan_kernel(const int4 *__restrict__ edges, const int4 *__restrict__ searches, int n_search, int first_acc,
-                int4 *__restrict__ visits, int4 *__restrict__ out_moves) {
+spr_plan_kernel(const int4 *__restrict__ edges_g, int n_edge_recs, const int4 *__restrict__ searches, int n_search,
+                int first_acc, int4 *__restrict__ visits, int4 *__restrict__ out_moves) {
+  // a search is one long chain of dependent edge-record lookups: keep the records in shared
+  // memory when they fit (n_edge_recs > 0), 155 -> 30 us per 256-taxon neighbourhood
+  extern __shared__ int4 spr_edges_s[];
+  const int4 *edges = edges_g;
+  if (n_edge_recs > 0) {
+    for (int i = threadIdx.x; i < n_edge_recs; i += blockDim.x) spr_edges_s[i] = __ldg(edges_g + i);
+    __syncthreads();
+    edges = spr_edges_s;
+  }
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_search) return;
   const int4 r0 = __ldg(searches + 2 * s), r1 = __ldg(searches + 2 * s + 1);
@@ -402,7 +412,7 @@ spr_plan_kernel(const int4 *__restrict__ edges, const int4 *__restrict__ searche
     sp--;
     const int x = sx[sp], from = sfrom[sp], pre = spre[sp], x_in = sin[sp], dep = sdep[sp];
     if (x_in <= -2) park--;
-    const int4 e0 = __ldg(edges + 3 * x), e1 = __ldg(edges + 3 * x + 1), e2 = __ldg(edges + 3 * x + 2);
+    const int4 e0 = edges[3 * x], e1 = edges[3 * x + 1], e2 = edges[3 * x + 2];
     // the two neighbours other than `from`: E1 = higher slot (move 2*pre), E2 = lower slot (2*pre + 1)
     const int4 E1 = e2.x == from ? e1 : e2;
     const int4 E2 = e0.x == from ? e1 : e0;
@@ -575,9 +585,18 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
       PLG_CUDA(cudaMemcpyAsync(ws.spr_searches.p, prog.spr_searches.data(),
                                prog.spr_searches.size() * sizeof(SprSearchRec), cudaMemcpyHostToDevice, st));
       const int n_search = (int)prog.spr_searches.size();
-      spr_plan_kernel<<<(n_search + 63) / 64, 64, 0, st>>>(ws.spr_edges.p, ws.spr_searches.p, n_search,
-                                                          prog.spr_first_acc, ws.nbw_visits.p,
-                                                          out_moves ? ws.spr_moves.p : nullptr);
+      const size_t edge_bytes = prog.spr_edges.size() * sizeof(SprEdgeRec);
+      const bool in_smem = edge_bytes <= SPR_PLAN_SMEM_MAX && !getenv("PLG_SPR_PLAN_GLOBAL");  // (tests: the fallback for huge trees)
+      static bool plan_attr_set[64] = {false};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!plan_attr_set[dev & 63]) {
+        PLG_CUDA(cudaFuncSetAttribute(spr_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPR_PLAN_SMEM_MAX));
+        plan_attr_set[dev & 63] = true;
+      }
+      spr_plan_kernel<<<(n_search + 63) / 64, 64, in_smem ? edge_bytes : 0, st>>>(
+          ws.spr_edges.p, in_smem ? (int)prog.spr_edges.size() : 0, ws.spr_searches.p, n_search, prog.spr_first_acc,
+          ws.nbw_visits.p, out_moves ? ws.spr_moves.p : nullptr);
       count_launch();
       if (out_moves)
         PLG_CUDA(cudaMemcpyAsync(out_moves, ws.spr_moves.p, (size_t)prog.spr_n_unique * sizeof(int4),

@@ -495,9 +495,18 @@ static void run_typed(const LikAln &a, const Model &m, LikWorkspace &ws, const L
 // walk kernel executes next on the same stream; unique ids follow the host enumeration
 // (enumerate_spr).  acct (profiling only): [0] algorithmic, [1] requested bytes per pattern of the
 // walk launch, the same per-visit sums run_dna4 takes over a host-built visit list.
+constexpr size_t SPR_LIK_PLAN_SMEM_MAX = 200 << 10;
 __global__ void __launch_bounds__(64)
-spr_lik_plan_kernel(const int4 *__restrict__ edges, const int4 *__restrict__ searches, int n_search, int n_rows,
-                    int4 *__restrict__ visits, int4 *__restrict__ out_moves, double *__restrict__ acct) {
+spr_lik_plan_kernel(const int4 *__restrict__ edges_g, int n_edge_int4, const int4 *__restrict__ searches,
+                    int n_search, int n_rows, int4 *__restrict__ visits, int4 *__restrict__ out_moves,
+                    double *__restrict__ acct) {
+  extern __shared__ int4 spr_lik_edges_s[];  // the edge records, when they fit (n_edge_int4 > 0)
+  const int4 *edges = edges_g;
+  if (n_edge_int4 > 0) {
+    for (int i = threadIdx.x; i < n_edge_int4; i += blockDim.x) spr_lik_edges_s[i] = __ldg(edges_g + i);
+    __syncthreads();
+    edges = spr_lik_edges_s;
+  }
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_search) return;
   const int4 r0 = __ldg(searches + 3 * s), r1 = __ldg(searches + 3 * s + 1), r2 = __ldg(searches + 3 * s + 2);
@@ -518,11 +527,11 @@ spr_lik_plan_kernel(const int4 *__restrict__ edges, const int4 *__restrict__ sea
     const int x = sx[sp], from = sfrom[sp], pre = spre[sp], x_in = sin[sp], dep = sdep[sp], p_in = spin[sp];
     if (x_in <= -2) park--;
     const int4 *ep = edges + 6 * x;
-    const int4 e0 = __ldg(ep), e1 = __ldg(ep + 2), e2 = __ldg(ep + 4);
+    const int4 e0 = ep[0], e1 = ep[2], e2 = ep[4];
     // the two neighbours other than `from`: j1 = higher slot (move 2*pre), j2 = lower slot (2*pre + 1)
     const int j1 = e2.x == from ? 1 : 2, j2 = e0.x == from ? 1 : 0;
     const int4 E1 = j1 == 1 ? e1 : e2, E2 = j2 == 1 ? e1 : e0;
-    const int4 Q1 = __ldg(ep + 2 * j1 + 1), Q2 = __ldg(ep + 2 * j2 + 1);
+    const int4 Q1 = ep[2 * j1 + 1], Q2 = ep[2 * j2 + 1];
     int uid1, uid2;
     if (pre == 0) {
       uid1 = dup0 ? -1 : uniq_base;
@@ -772,9 +781,14 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
                                prog.spr_searches.size() * sizeof(LikSprSearch), cudaMemcpyHostToDevice, st));
       if (acct_on) PLG_CUDA(cudaMemsetAsync(ws.spr_acct.p, 0, 2 * sizeof(double), st));
       const int n_search = (int)prog.spr_searches.size();
-      spr_lik_plan_kernel<<<(n_search + 63) / 64, 64, 0, st>>>(
-          ws.spr_edges.p, ws.spr_searches.p, n_search, a.n_rows, reinterpret_cast<int4 *>(ws.walk_visits.p),
-          out_moves ? ws.spr_moves.p : nullptr, acct_on ? ws.spr_acct.p : nullptr);
+      const size_t edge_bytes = prog.spr_edges.size() * sizeof(LikSprEdge);
+      const bool in_smem = edge_bytes <= SPR_LIK_PLAN_SMEM_MAX && !getenv("PLG_SPR_PLAN_GLOBAL");  // (tests: the fallback for huge trees)
+      static bool plan_attr_set[64] = {false};
+      ensure_dyn_smem(spr_lik_plan_kernel, (int)SPR_LIK_PLAN_SMEM_MAX, plan_attr_set);
+      spr_lik_plan_kernel<<<(n_search + 63) / 64, 64, in_smem ? edge_bytes : 0, st>>>(
+          ws.spr_edges.p, in_smem ? (int)(edge_bytes / 16) : 0, ws.spr_searches.p, n_search, a.n_rows,
+          reinterpret_cast<int4 *>(ws.walk_visits.p), out_moves ? ws.spr_moves.p : nullptr,
+          acct_on ? ws.spr_acct.p : nullptr);
       count_launch();
       if (out_moves)
         PLG_CUDA(cudaMemcpyAsync(out_moves, ws.spr_moves.p, (size_t)prog.spr_n_unique * sizeof(int4),

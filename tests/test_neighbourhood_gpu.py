@@ -261,3 +261,25 @@ def test_lnl_device_planned_spr_equals_host_planner(n, P, monkeypatch):
     assert got["device"][1].tolist() == got["host"][1].tolist()  # bit-identical
     assert acct["device"] == pytest.approx(acct["host"], rel=1e-12)
     a.close(); m.close()
+
+
+def test_device_planner_global_memory_fallback(monkeypatch):
+    """Edge records too large for shared memory are read from global memory (forced here): same results."""
+    from pylogeny_b200 import fitch, likelihood, neighbourhood as nbh
+    rng = np.random.default_rng(99)
+    n, P = 37, 260
+    st = random_states(rng, n, P, 4, 0.02)
+    fa = fitch.FitchAlignment.from_dense(st, np.ones(P, dtype=np.int64))
+    codes = (1 << rng.integers(0, 4, (n, P))).astype(np.uint8)
+    la = likelihood.LikAlignment(codes, np.ones(P))
+    m = likelihood.Model(rng.uniform(0.5, 2.0, 6), rng.dirichlet(np.ones(4) * 8), 0.8)
+    d = random_desc(rng, n)
+    br = rng.exponential(0.1, d.shape)
+    want_f = nbh.score_parsimony(fa, d)
+    want_l = nbh.score_likelihood(la, m, d, br)
+    monkeypatch.setenv("PLG_SPR_PLAN_GLOBAL", "1")
+    got_f = nbh.score_parsimony(fa, d)
+    got_l = nbh.score_likelihood(la, m, d, br)
+    assert got_f[0].tolist() == want_f[0].tolist() and got_f[1].tolist() == want_f[1].tolist()
+    assert got_l[0].tolist() == want_l[0].tolist() and got_l[1].tolist() == want_l[1].tolist()
+    fa.close(); la.close(); m.close()
