@@ -211,6 +211,19 @@ extern "C" int plg_neighbourhood_trees(int move_type, int n_tips, const int32_t 
     }
     return PLG_OK;
   }
+  if (depth_for(move_type) < 0 && n_sel <= 64 && n_tips >= 4) {  // a few moves (the winner of a climb step)
+    const UTree t = utree_from_desc(n_tips, desc, brlen, tip_rows);
+    std::vector<Move> mv(n_sel);
+    spr_moves_by_unique_id(t, n_sel, sel, mv.data());
+    for (int64_t i = 0; i < n_sel; i++) {
+      if (out_desc) {
+        UTree r = apply_move(t, mv[i]);
+        desc_from_utree(r, out_desc + i * stride, out_brlen ? out_brlen + i * stride : nullptr);
+      }
+      if (out_hash) out_hash[i] = mv[i].hash;
+    }
+    return PLG_OK;
+  }
   static thread_local Neighbourhood nb;  // storage reused from call to call
   enumerate_spr(utree_from_desc(n_tips, desc, brlen, tip_rows), depth_for(move_type), nb);
   for (int64_t i = 0; i < n_sel; i++) {

@@ -847,6 +847,61 @@ void layout_spr_searches(const UTree &t, const DirOrder &d, const std::vector<in
 }
 }  // namespace
 
+// A few moves of the full SPR neighbourhood by unique id, without enumerating it: the search
+// layout (O(n)) says which search holds the id, and only that search is expanded -- in
+// enumerate_spr's order, with its hashes.  What a hill climb needs to materialise the winner.
+void spr_moves_by_unique_id(const UTree &t, int64_t n_sel, const int64_t *sel, Move *out) {
+  DirOrder d = dir_order(t);
+  std::vector<int> dir_slot((size_t)t.n_nodes * 3, 0);
+  static thread_local SprSearchLayout lay;
+  layout_spr_searches(t, d, dir_slot, lay);
+  uint64_t all;
+  std::vector<uint64_t> h = side_hashes(t, d, &all);
+  uint64_t base = 0;
+  for (int x = 0; x < t.n_nodes; x++)
+    for (int k = 0; k < 3; k++)
+      if (t.nb[x][k] > x) base += split_term(h[3 * x + k], all);
+  auto far = [&](int x, int k) { const int y = t.nb[x][k]; return h[3 * y + t.slot_of(y, x)]; };
+  struct Frame { int x, from, parent_move, depth; uint64_t rem, add; };
+  std::vector<Frame> st;
+  std::vector<Move> moves;
+  for (int64_t q = 0; q < n_sel; q++) {
+    const int64_t uid = sel[q];
+    if (uid < 0 || uid >= lay.n_unique) PLG_FAIL(PLG_ERR_ARG, "move index out of range");
+    const size_t s = std::upper_bound(lay.search_uniq.begin(), lay.search_uniq.end(), uid) - lay.search_uniq.begin() - 1;
+    const int e = lay.search_edge[s], u = e / 3, k = e % 3, side = (int)(s & 1), ks = (k + 1 + side) % 3;
+    const uint64_t hv = far(u, k);
+    moves.clear();
+    st.push_back({t.nb[u][ks], u, -1, 0, split_term(far(u, ks), all), 0});
+    while (!st.empty()) {
+      const Frame f = st.back();
+      st.pop_back();
+      if (t.is_tip(f.x)) continue;
+      for (int j = 2; j >= 0; j--) {
+        const int c = t.nb[f.x][j];
+        if (c == f.from) continue;
+        const uint64_t joined = split_term(far(f.x, j) ^ hv, all);
+        Move m;
+        m.u = u; m.k = k; m.x = f.x; m.kx = j; m.depth = f.depth + 1; m.parent = f.parent_move; m.side = side;
+        m.hash = base - f.rem + f.add + joined;
+        m.unique_id = -1;
+        st.push_back({c, f.x, (int)moves.size(), f.depth + 1, f.rem + split_term(far(f.x, j), all), f.add + joined});
+        moves.push_back(m);
+      }
+    }
+    // the id-th kept move of the search: only its first two moves can be repeats
+    const int dup = lay.searches[s].dup_flag & 3;
+    int64_t want = uid - lay.search_uniq[s], at = -1;
+    for (size_t i = 0; i < moves.size(); i++) {
+      if (i < 2 && (dup >> i & 1)) continue;
+      if (want-- == 0) { at = (int64_t)i; break; }
+    }
+    if (at < 0) PLG_FAIL(PLG_ERR_ARG, "internal: move %lld not found in its search", (long long)uid);
+    out[q] = moves[at];
+    out[q].unique_id = (int)uid;
+  }
+}
+
 void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_slots, SprDevicePlan &out) {
   DirOrder d = dir_order(t);
   std::vector<int> dir_slot;

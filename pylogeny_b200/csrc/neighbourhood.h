@@ -61,6 +61,8 @@ Neighbourhood enumerate_spr(const UTree &t, int max_depth);
 // enumerates one neighbourhood per step; a fresh 12 MB move array costs more in page faults than
 // the enumeration itself)
 void enumerate_spr(const UTree &t, int max_depth, Neighbourhood &out);
+// Moves `sel` (unique ids) of the FULL SPR neighbourhood without enumerating it (O(n) per move).
+void spr_moves_by_unique_id(const UTree &t, int64_t n_sel, const int64_t *sel, Move *out);
 // The neighbour tree of one move, with the reference's branch-length rule (rearrangement.py:466-497).
 UTree apply_move(const UTree &t, const Move &m);
 // Rooted post-order descriptor of an unrooted tree, rooted on tip 0's pendant edge

@@ -164,3 +164,28 @@ def test_radius_limited_spr_vs_split_distance(n, radius):
         assert M == nbh.neighbourhood_size(d, nbh.MOVE_NNI)
     if radius >= n:
         assert M == nbh.neighbourhood_size(d, nbh.MOVE_SPR)
+
+
+@pytest.mark.parametrize("n", [4, 5, 9, 40, 130])
+def test_single_moves_without_enumeration(n):
+    """neighbour_trees(sel=few) expands only the searches that hold the requested ids (what a climb
+    step uses to materialise its winner); it must agree with the full enumeration: descriptors,
+    branch lengths and topology hashes."""
+    from pylogeny_b200 import neighbourhood as nbh
+    rng = np.random.default_rng(3 * n + 1)
+    d = random_desc(rng, n)
+    br = rng.exponential(0.1, d.shape)
+    perm = rng.permutation(n).astype(np.int32)
+    M = nbh.neighbourhood_size(d)
+    sel_all = np.arange(M, dtype=np.int64)
+    if M <= 64:  # force the enumeration path with a padded selection
+        sel_all = np.concatenate([sel_all, np.zeros(65 - M, dtype=np.int64)])
+    full_d, full_b, full_h = nbh.neighbour_trees(d, br, sel_all, tip_rows=perm)
+    pick = np.unique(np.concatenate([[0, M - 1], rng.integers(0, M, 20)])).astype(np.int64)
+    for chunk in (pick[:1], pick):
+        few_d, few_b, few_h = nbh.neighbour_trees(d, br, chunk, tip_rows=perm)
+        assert few_d.tolist() == full_d[chunk].tolist()
+        assert few_b.tolist() == full_b[chunk].tolist()
+        assert few_h.tolist() == full_h[chunk].tolist()
+    with pytest.raises(Exception):
+        nbh.neighbour_trees(d, br, np.array([M], dtype=np.int64))
