@@ -12,10 +12,13 @@ d = random_desc(np.random.default_rng(6), n); br = np.random.default_rng(7).expo
 L = _lib.lib()
 for i in range(3):
     nbh.score_likelihood(la, m, d, br)
-L.plg_profile_enable(1); L.plg_profile_read(1, None, None, None, None, None)
+L.plg_profile_enable(1); L.plg_profile_read(1, None, None, None, None, None); L.plg_profile_read(4, None, None, None, None, None)
 ts = []
-for i in range(5):
+REPS = 10
+for i in range(REPS):
     t = time.perf_counter(); mv, l = nbh.score_likelihood(la, m, d, br); ts.append((time.perf_counter() - t) * 1e3)
 ms, by, un, nl = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
 L.plg_profile_read(1, C.byref(ms), C.byref(by), C.byref(un), C.byref(nl), None)
-print("call ms %.2f  kernel ms/step %.2f  GB/s %.0f  checksum %.6f" % (np.median(ts), ms.value / 5, by.value / ms.value / 1e6, l.sum()))
+wms = C.c_double()
+L.plg_profile_read(4, C.byref(wms), None, None, None, None)
+print("call ms %.2f (min %.2f)  walk kernel ms %.3f  base-tree kernels ms/step %.2f  checksum %.6f" % (np.median(ts), min(ts), wms.value / REPS, ms.value / REPS, l.sum()))

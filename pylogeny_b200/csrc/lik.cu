@@ -563,10 +563,18 @@ spr_lik_plan_kernel(const int4 *__restrict__ edges_g, int n_edge_int4, const int
       sx[sp] = E2.x; sfrom[sp] = x; spre[sp] = pre2; sin[sp] = -1; sdep[sp] = dep + 1; spin[sp] = Q2.x;
       sp++;
     }
+    // normal form (walk4m_kernel relies on it): the partial that continues in registers is the one
+    // toward d1, so the visit's "2" side is the one that may be parked
     int4 *vp = visits + 4 * at;
-    vp[0] = make_int4(x_in, p_in, E1.y, Q1.x);
-    vp[1] = make_int4(Q1.y, E2.y, Q2.x, Q2.y);
-    vp[2] = make_int4(uid1, uid2, keep, push);
+    if (keep == 2) {
+      vp[0] = make_int4(x_in, p_in, E2.y, Q2.x);
+      vp[1] = make_int4(Q2.y, E1.y, Q1.x, Q1.y);
+      vp[2] = make_int4(uid2, uid1, 1, push);
+    } else {
+      vp[0] = make_int4(x_in, p_in, E1.y, Q1.x);
+      vp[1] = make_int4(Q1.y, E2.y, Q2.x, Q2.y);
+      vp[2] = make_int4(uid1, uid2, keep, push);
+    }
     vp[3] = make_int4(0, 0, 0, 0);
     at++;
     if (out_moves) {
@@ -753,7 +761,7 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     PLG_CUDA(cudaGetDevice(&dev));
     PLG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     const int n_blocks = n_sm * (dmma ? PLG_WM_MINB : PLG_WK_MINB);
-    const int64_t n_warps = (int64_t)n_blocks * WK_WARPS;
+    const int64_t n_warps = (int64_t)n_blocks * (dmma ? WM_WARPS : WK_WARPS);
     const int levels = std::max(1, prog.walk_levels);
     ws.walk_visits.alloc(device_plan ? (size_t)prog.spr_n_visits : prog.walk_visits.size());
     ws.walk_groups.alloc(prog.walk_groups.size());

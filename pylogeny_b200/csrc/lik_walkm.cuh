@@ -24,7 +24,10 @@
 
 namespace plg {
 
-constexpr int WM_WARPS = 4;
+#ifndef PLG_WM_WARPS
+#define PLG_WM_WARPS 4
+#endif
+constexpr int WM_WARPS = PLG_WM_WARPS;
 constexpr int WM_THREADS = 32 * WM_WARPS;
 #ifndef PLG_WM_MINB
 #define PLG_WM_MINB 3
@@ -237,6 +240,52 @@ __device__ __forceinline__ double wm_site_sum(const double (&e)[WM_V], const int
   return val;
 }
 
+// same from the per-group sums u[j] = (e0 + e1) + (e2 + e3) over the categories (not yet weighted by pi)
+__device__ __forceinline__ double wm_site_sum_u(const double (&u)[WM_NG], const int (&sc)[WM_NG], double w_out,
+                                                double pi_q, int lane) {
+  static_assert(WM_NG == 4, "32 patterns per warp");
+  double v[WM_NG];
+#pragma unroll
+  for (int j = 0; j < WM_NG; j++) v[j] = pi_q * u[j];
+  const bool hi = lane & 2, odd = lane & 1;
+  double k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
+  k0 += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 2);
+  k1 += __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 2);
+  double L = odd ? k1 : k0;
+  L += __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 1);
+  const int scq = hi ? (odd ? sc[3] : sc[2]) : (odd ? sc[1] : sc[0]);
+  double val = w_out != 0.0 ? w_out * (log(L * 0.25) + scq * LOG_MINLH) : 0.0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
+  return val;
+}
+
+// One neighbour chain of a visit in straight-line form: (a, g) = (P_t n, P_h n) category by
+// category; g is consumed at once into the per-group sums of g o h o tvv (same summation order as
+// wm_site_sum), a goes to `a_out` (registers) and/or the stack -- so neither a nor g is ever live
+// as a whole vector (the register allocator spills them otherwise at 168 registers).
+template <bool TO_REGS>
+__device__ __forceinline__ void wm_chain(const double (&n)[WM_V], const double (&bf)[4], const double (&h)[WM_V],
+                                         const double (*tvv)[32], int lane, double (&a_out)[WM_V], double *stk_dst,
+                                         bool push, double (&u)[WM_NG]) {
+  double s01[WM_NG], e2[WM_NG];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int j = 0; j < WM_NG; j++) {
+      const int i = r * WM_NG + j;
+      double a, g;
+      wm_dmma(a, g, n[i], bf[r]);
+      if (TO_REGS) a_out[i] = a;
+      if (push) stk_dst[i * 32] = a;
+      const double t = g * (h[i] * tvv[i][lane]);
+      if (r == 0) s01[j] = t;
+      else if (r == 1) s01[j] += t;
+      else if (r == 2) e2[j] = t;
+      else u[j] = s01[j] + (e2[j] + t);
+    }
+}
+
 __device__ __forceinline__ int wm_desc_load(const LikWalkVisit *__restrict__ visits, int vi, int lane) {
   int v = 0;
   if (lane < 12) asm volatile("ld.global.nc.b32 %0, [%1];\n" : "=r"(v) : "l"(reinterpret_cast<const int *>(visits + vi) + lane));
@@ -386,64 +435,42 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
 #pragma unroll
       for (int j = 0; j < WM_NG; j++) sc1[j] = sk[j] + s2[j];
       wm_rescale(n1, sc1, lane);
-      // pair 2 on N2: the partial handed toward c2 and neighbour 2's own side (insertion into x--c2)
-      const bool cont2 = keep == 2 || (push >= 0 && keep == 1);
-      double a2[WM_V];
-      if (tree2 >= 0 || cont2) {
-        double g2[WM_V];
-        wm_pair(n2, bf2, a2, g2);
+      // Visits come in normal form (planners): keep is 0 or 1 -- the partial toward c1 continues in
+      // registers, the one toward c2 is at most parked.  Side 2 first, so that its hand-over is on
+      // the stack (and dead) before side 1's lands directly in ak.
+      {  // side 2: toward c2 (at most parked) and neighbour 2 (insertion into x--c2)
+        double u[WM_NG], dummy[WM_V];
+#if PLG_WM_PARK_H2
+#pragma unroll
+        for (int i = 0; i < WM_V; i++) h2[i] = park[2][i][lane];
+#endif
+        wm_chain<false>(n2, bf2, h2, park[0], lane, dummy, stk + (int64_t)(push >= 0 ? push : 0) * WM_V * 32, push >= 0, u);
+        if (push >= 0) {
+#pragma unroll
+          for (int j = 0; j < WM_NG; j++) stks[(push * WM_NG + j) * 32] = sc2[j];
+        }
         if (tree2 >= 0) {
           int sct[WM_NG];
 #pragma unroll
-#if PLG_WM_PARK_H2
-          for (int i = 0; i < WM_V; i++) g2[i] *= park[2][i][lane] * park[0][i][lane];
-#else
-          for (int i = 0; i < WM_V; i++) g2[i] *= h2[i] * park[0][i][lane];
-#endif
-#pragma unroll
           for (int j = 0; j < WM_NG; j++) sct[j] = sc2[j] + s2[j] + st[j];
-          const double val = wm_site_sum(g2, sct, w_out, pi_q, lane);
+          const double val = wm_site_sum_u(u, sct, w_out, pi_q, lane);
           if (lane == 0) partial[(int64_t)tree2 * pstride + slice] = val;
         }
       }
-      // pair 1 on N1: toward c1 and neighbour 1 (insertion into x--c1)
-      const bool cont1 = keep == 1 || (push >= 0 && keep == 2);
-      if (tree1 >= 0 || cont1) {
-        double a1[WM_V], g1[WM_V];
-        wm_pair(n1, bf1, a1, g1);
+      {  // side 1: toward c1 (straight into ak) and neighbour 1 (insertion into x--c1)
+        double u[WM_NG], h1[WM_V];
+#pragma unroll
+        for (int i = 0; i < WM_V; i++) h1[i] = park[1][i][lane];
+        wm_chain<true>(n1, bf1, h1, park[0], lane, ak, nullptr, false, u);
+#pragma unroll
+        for (int j = 0; j < WM_NG; j++) sk[j] = sc1[j];
         if (tree1 >= 0) {
           int sct[WM_NG];
 #pragma unroll
-          for (int i = 0; i < WM_V; i++) g1[i] *= park[1][i][lane] * park[0][i][lane];
-#pragma unroll
           for (int j = 0; j < WM_NG; j++) sct[j] = sc1[j] + s1[j] + st[j];
-          const double val = wm_site_sum(g1, sct, w_out, pi_q, lane);
+          const double val = wm_site_sum_u(u, sct, w_out, pi_q, lane);
           if (lane == 0) partial[(int64_t)tree1 * pstride + slice] = val;
         }
-        if (push >= 0 && keep == 2) {
-#pragma unroll
-          for (int i = 0; i < WM_V; i++) stk[(push * WM_V + i) * 32] = a1[i];
-#pragma unroll
-          for (int j = 0; j < WM_NG; j++) stks[(push * WM_NG + j) * 32] = sc1[j];
-        }
-        if (keep == 1) {
-#pragma unroll
-          for (int i = 0; i < WM_V; i++) ak[i] = a1[i];
-#pragma unroll
-          for (int j = 0; j < WM_NG; j++) sk[j] = sc1[j];
-        }
-      }
-      if (push >= 0 && keep == 1) {
-#pragma unroll
-        for (int i = 0; i < WM_V; i++) stk[(push * WM_V + i) * 32] = a2[i];
-#pragma unroll
-        for (int j = 0; j < WM_NG; j++) stks[(push * WM_NG + j) * 32] = sc2[j];
-      }
-      if (keep == 2) {
-#pragma unroll
-        for (int i = 0; i < WM_V; i++) ak[i] = a2[i];
-#pragma unroll
-        for (int j = 0; j < WM_NG; j++) sk[j] = sc2[j];
       }
       dcur = dnxt; dnxt = dnn;
 #if PLG_WM_PREFETCH

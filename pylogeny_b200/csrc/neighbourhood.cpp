@@ -1156,6 +1156,10 @@ void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int 
           w.keep = 2;
           st.push_back({ch2, -1});
         }
+        if (w.keep == 2) {  // normal form (walk4m_kernel): the partial toward d1 is the one that continues
+          std::swap(w.d1, w.d2); std::swap(w.p_t1, w.p_t2); std::swap(w.p_h1, w.p_h2); std::swap(w.tree1, w.tree2);
+          w.keep = 1;
+        }
         prog.walk_visits.push_back(w);
         prog.walk_groups.back().count++;
       }
