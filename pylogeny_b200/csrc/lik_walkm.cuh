@@ -49,6 +49,9 @@ static_assert(WM_NG == 4 || WM_NG == 2, "a warp carries 32 or 16 patterns");
 #define PLG_WM_STAGE 0     // 1: the far-side operands of the NEXT visit are fetched by cp.async into shared memory during this one
                            //    (B200: 9.2 vs 7.9 ms -- 209 KB of shared memory leave no L1 for the spills and fragments)
 #endif
+#ifndef PLG_WM_REFRAG
+#define PLG_WM_REFRAG 0
+#endif
 #ifndef PLG_WM_PF
 #define PLG_WM_PF 0        // 1: ... or pulled into L1 by one prefetch instruction per operand (32 lines, one per lane): 8.03 vs 7.76 ms
 #endif
@@ -243,17 +246,26 @@ __device__ __forceinline__ double wm_site_sum(const double (&e)[WM_V], const int
 // same from the per-group sums u[j] = (e0 + e1) + (e2 + e3) over the categories (not yet weighted by pi)
 __device__ __forceinline__ double wm_site_sum_u(const double (&u)[WM_NG], const int (&sc)[WM_NG], double w_out,
                                                 double pi_q, int lane) {
-  static_assert(WM_NG == 4, "32 patterns per warp");
   double v[WM_NG];
 #pragma unroll
   for (int j = 0; j < WM_NG; j++) v[j] = pi_q * u[j];
   const bool hi = lane & 2, odd = lane & 1;
-  double k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
-  k0 += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 2);
-  k1 += __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 2);
-  double L = odd ? k1 : k0;
-  L += __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 1);
-  const int scq = hi ? (odd ? sc[3] : sc[2]) : (odd ? sc[1] : sc[0]);
+  double L;
+  int scq;
+  if constexpr (WM_NG == 4) {
+    double k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
+    k0 += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 2);
+    k1 += __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 2);
+    L = odd ? k1 : k0;
+    L += __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 1);
+    scq = hi ? (odd ? sc[3] : sc[2]) : (odd ? sc[1] : sc[0]);
+  } else {
+    L = odd ? v[1] : v[0];
+    L += __shfl_xor_sync(0xffffffffu, odd ? v[0] : v[1], 1);
+    L += __shfl_xor_sync(0xffffffffu, L, 2);
+    scq = odd ? sc[1] : sc[0];
+    if (hi) w_out = 0.0;
+  }
   double val = w_out != 0.0 ? w_out * (log(L * 0.25) + scq * LOG_MINLH) : 0.0;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
@@ -459,6 +471,10 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
       }
       {  // side 1: toward c1 (straight into ak) and neighbour 1 (insertion into x--c1)
         double u[WM_NG], h1[WM_V];
+#if PLG_WM_REFRAG
+        // bf1 is not kept across the D2 stage and chain 2: fetched again (L1) where chain 1 needs it
+        wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 3), __shfl_sync(0xffffffffu, dcur, 4), lane, bf1);
+#endif
 #pragma unroll
         for (int i = 0; i < WM_V; i++) h1[i] = park[1][i][lane];
         wm_chain<true>(n1, bf1, h1, park[0], lane, ak, nullptr, false, u);
