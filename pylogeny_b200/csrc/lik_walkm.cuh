@@ -86,9 +86,9 @@ __device__ __forceinline__ void wm_frag(const double *__restrict__ pmat, int pm_
 // Operand `id` as it sits at its node, in layout V (tips: indicator of the code's states; one code
 // path for both kinds -- a separate tip path doubles the DMMA blocks and costs more in spills than
 // the 32 register moves it saves).
-__device__ __forceinline__ void wm_load_raw(int id, int n_rows, int64_t Ppad, int64_t p0, int lane,
+__device__ __forceinline__ void wm_load_raw(int id, int n_rows, int64_t Ppad, int64_t p0, int lane, int out_off,
                                             const unsigned char *__restrict__ codes, const double *__restrict__ clv,
-                                            const int *__restrict__ scl, double (&x)[WM_V], int (&s)[WM_NG]) {
+                                            const int *__restrict__ scl, double (&x)[WM_V], int &s) {
   const int g2 = (lane >> 2) * 2, q = lane & 3;
   if (id < n_rows) {
     const unsigned char *c = codes + (int64_t)id * Ppad + p0 + g2;
@@ -105,8 +105,8 @@ __device__ __forceinline__ void wm_load_raw(int id, int n_rows, int64_t Ppad, in
       const double ind = (mask >> q & 1u) ? 1.0 : 0.0;
 #pragma unroll
       for (int r = 0; r < 4; r++) x[r * WM_NG + j] = ind;
-      s[j] = 0;
     }
+    s = 0;
   } else {
     const double *b = clv + (int64_t)(id - n_rows) * 16 * Ppad + p0 + g2;
 #pragma unroll
@@ -118,13 +118,8 @@ __device__ __forceinline__ void wm_load_raw(int id, int n_rows, int64_t Ppad, in
         x[r * WM_NG + 2] = v.x; x[r * WM_NG + 3] = v.y;
       }
     }
-    const int *sp = scl + (int64_t)(id - n_rows) * Ppad + p0 + g2;
-    const int2 a = __ldg(reinterpret_cast<const int2 *>(sp));
-    s[0] = a.x; s[1] = a.y;
-    if constexpr (WM_NG == 4) {
-      const int2 c = __ldg(reinterpret_cast<const int2 *>(sp + 16));
-      s[2] = c.x; s[3] = c.y;
-    }
+    // scaling counter of THIS LANE's output pattern only (see wm_rescale)
+    s = __ldg(scl + (int64_t)(id - n_rows) * Ppad + p0 + out_off);
   }
 }
 
@@ -155,7 +150,7 @@ __device__ __forceinline__ void wm_stage(int id, int n_rows, int64_t Ppad, int64
 
 // the staged operand in layout V (what wm_load_raw returns); src = this lane's row 0
 __device__ __forceinline__ void wm_unstage(int id, int n_rows, int lane, const double2 *src, double (&x)[WM_V],
-                                           int (&s)[WM_NG]) {
+                                           int &s) {
   const int q = lane & 3;
   if (id < n_rows) {
     const uint2 w = *reinterpret_cast<const uint2 *>(src);
@@ -168,8 +163,8 @@ __device__ __forceinline__ void wm_unstage(int id, int n_rows, int lane, const d
       const double ind = (mask >> q & 1u) ? 1.0 : 0.0;
 #pragma unroll
       for (int r = 0; r < 4; r++) x[r * 4 + j] = ind;
-      s[j] = 0;
     }
+    s = 0;
   } else {
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -177,7 +172,7 @@ __device__ __forceinline__ void wm_unstage(int id, int n_rows, int lane, const d
       x[r * 4] = u.x; x[r * 4 + 1] = u.y; x[r * 4 + 2] = v.x; x[r * 4 + 3] = v.y;
     }
     const int4 c = *reinterpret_cast<const int4 *>(src + 8 * 32);
-    s[0] = c.x; s[1] = c.y; s[2] = c.z; s[3] = c.w;
+    s = q == 0 ? c.x : (q == 1 ? c.y : (q == 2 ? c.z : c.w));
   }
 }
 
@@ -196,8 +191,12 @@ __device__ __forceinline__ void wm_prefetch(int id, int n_rows, int64_t Ppad, in
 }
 
 // per pattern: all 16 entries below 2^-256 -> multiply by 2^256 and count (libpll's scaling).
-// A pattern's entries sit in the four lanes of a quad: one vote per pattern group.
-__device__ __forceinline__ void wm_rescale(double (&n)[WM_V], int (&sc)[WM_NG], int lane) {
+// A pattern's entries sit in the four lanes of a quad: one vote per pattern group.  The four lanes
+// of a quad would keep identical counters for their four groups; each lane keeps only the one its
+// own site term needs (group jq = lane & 3; lane & 1 with two groups) -- one register instead of four
+// for each of the six counters a visit carries.
+__device__ __forceinline__ void wm_rescale(double (&n)[WM_V], int &sc, int lane) {
+  const int jq = WM_NG == 4 ? (lane & 3) : (lane & 1);
 #pragma unroll
   for (int j = 0; j < WM_NG; j++) {
     int hi = max(max(__double2hiint(n[j]), __double2hiint(n[WM_NG + j])),
@@ -206,21 +205,20 @@ __device__ __forceinline__ void wm_rescale(double (&n)[WM_V], int (&sc)[WM_NG], 
     if (((big >> (lane & 28)) & 15u) == 0u) {
 #pragma unroll
       for (int r = 0; r < 4; r++) n[r * WM_NG + j] *= TWO256;
-      sc[j] += 1;
+      sc += (j == jq) ? 1 : 0;
     }
   }
 }
 
 // sum over the warp's 32 patterns of w (log L + scaling), L = 1/4 sum_r sum_k pi_k e[r][k];
 // the result is valid in lane 0
-__device__ __forceinline__ double wm_site_sum(const double (&e)[WM_V], const int (&sc)[WM_NG], double w_out,
+__device__ __forceinline__ double wm_site_sum(const double (&e)[WM_V], int scq, double w_out,
                                               double pi_q, int lane) {
   double v[WM_NG];
 #pragma unroll
   for (int j = 0; j < WM_NG; j++) v[j] = pi_q * ((e[j] + e[WM_NG + j]) + (e[2 * WM_NG + j] + e[3 * WM_NG + j]));
   const bool hi = lane & 2, odd = lane & 1;
   double L;
-  int scq;
   if constexpr (WM_NG == 4) {
     // transpose-reduce over the quad: lane q ends with the sum of group j = q
     double k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
@@ -228,13 +226,11 @@ __device__ __forceinline__ double wm_site_sum(const double (&e)[WM_V], const int
     k1 += __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 2);
     L = odd ? k1 : k0;
     L += __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 1);
-    scq = hi ? (odd ? sc[3] : sc[2]) : (odd ? sc[1] : sc[0]);
   } else {
     // two groups: lanes q = 0, 1 end with groups 0, 1 (lanes 2, 3 hold copies and contribute nothing)
     L = odd ? v[1] : v[0];
     L += __shfl_xor_sync(0xffffffffu, odd ? v[0] : v[1], 1);
     L += __shfl_xor_sync(0xffffffffu, L, 2);
-    scq = odd ? sc[1] : sc[0];
     if (hi) w_out = 0.0;
   }
   double val = w_out != 0.0 ? w_out * (log(L * 0.25) + scq * LOG_MINLH) : 0.0;
@@ -244,26 +240,23 @@ __device__ __forceinline__ double wm_site_sum(const double (&e)[WM_V], const int
 }
 
 // same from the per-group sums u[j] = (e0 + e1) + (e2 + e3) over the categories (not yet weighted by pi)
-__device__ __forceinline__ double wm_site_sum_u(const double (&u)[WM_NG], const int (&sc)[WM_NG], double w_out,
+__device__ __forceinline__ double wm_site_sum_u(const double (&u)[WM_NG], int scq, double w_out,
                                                 double pi_q, int lane) {
   double v[WM_NG];
 #pragma unroll
   for (int j = 0; j < WM_NG; j++) v[j] = pi_q * u[j];
   const bool hi = lane & 2, odd = lane & 1;
   double L;
-  int scq;
   if constexpr (WM_NG == 4) {
     double k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
     k0 += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 2);
     k1 += __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 2);
     L = odd ? k1 : k0;
     L += __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 1);
-    scq = hi ? (odd ? sc[3] : sc[2]) : (odd ? sc[1] : sc[0]);
   } else {
     L = odd ? v[1] : v[0];
     L += __shfl_xor_sync(0xffffffffu, odd ? v[0] : v[1], 1);
     L += __shfl_xor_sync(0xffffffffu, L, 2);
-    scq = odd ? sc[1] : sc[0];
     if (hi) w_out = 0.0;
   }
   double val = w_out != 0.0 ? w_out * (log(L * 0.25) + scq * LOG_MINLH) : 0.0;
@@ -347,10 +340,10 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
     double bf1[4], bf2[4];
     wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 3), __shfl_sync(0xffffffffu, dcur, 4), lane, bf1);
     wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 6), __shfl_sync(0xffffffffu, dcur, 7), lane, bf2);
-    int st[WM_NG];
+    int st;  // scaling counters: this lane's output pattern only (wm_rescale)
     {  // the pruned subtree seen through its branch, once per search
       double x[WM_V], bv[4], t[WM_V], dump[WM_V];
-      wm_load_raw(g.tv, n_rows, Ppad, p0, lane, codes, clv, scl, x, st);
+      wm_load_raw(g.tv, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, st);
       wm_frag(pmat, g.p_v, g.p_v, lane, bv);
       wm_pair(x, bv, t, dump);
       __syncwarp();
@@ -358,9 +351,7 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
       for (int i = 0; i < WM_V; i++) park[0][i][lane] = t[i];
     }
     double ak[WM_V];  // a = P_in (incoming partial), handed from visit to visit
-    int sk[WM_NG];
-#pragma unroll
-    for (int j = 0; j < WM_NG; j++) sk[j] = 0;
+    int sk = 0;
 #pragma unroll
     for (int i = 0; i < WM_V; i++) ak[i] = 0.0;
     for (int vi = g.first; vi < v_end; vi++) {
@@ -385,38 +376,36 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
 #endif
       if (x_in >= 0) {  // first step of a side: a = P_in X from a stored operand
         double x[WM_V], bi[4], dump[WM_V];
-        wm_load_raw(x_in, n_rows, Ppad, p0, lane, codes, clv, scl, x, sk);
+        wm_load_raw(x_in, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, sk);
         wm_frag(pmat, p_in, p_in, lane, bi);
         wm_pair(x, bi, ak, dump);
       } else if (x_in <= -2) {
         const int lvl = -2 - x_in;
 #pragma unroll
         for (int i = 0; i < WM_V; i++) ak[i] = stk[(lvl * WM_V + i) * 32];
-#pragma unroll
-        for (int j = 0; j < WM_NG; j++) sk[j] = stks[(lvl * WM_NG + j) * 32];
+        sk = stks[lvl * WM_NG * 32];
       }
       // D1 once: N2 = a o P_t1 D1 (the partial toward d2) and h1 = P_h1 D1 (far side of edge 1)
       double n2[WM_V];
-      int s1[WM_NG], sc2[WM_NG];
+      int s1, sc2;
       {
         double x[WM_V], h1[WM_V];
 #if PLG_WM_STAGE
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         wm_unstage(d1, n_rows, lane, stg, x, s1);
 #else
-        wm_load_raw(d1, n_rows, Ppad, p0, lane, codes, clv, scl, x, s1);
+        wm_load_raw(d1, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, s1);
 #endif
         wm_pair(x, bf1, n2, h1);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < WM_V; i++) { n2[i] *= ak[i]; park[1][i][lane] = h1[i]; }
       }
-#pragma unroll
-      for (int j = 0; j < WM_NG; j++) sc2[j] = sk[j] + s1[j];
+      sc2 = sk + s1;
       wm_rescale(n2, sc2, lane);
       // D2 once: N1 = a o P_t2 D2 and h2 = P_h2 D2
       double n1[WM_V], h2[WM_V];
-      int s2[WM_NG], sc1[WM_NG];
+      int s2, sc1;
       {
         double x[WM_V];
 #if PLG_WM_STAGE
@@ -428,7 +417,7 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
           asm volatile("cp.async.commit_group;\n" ::);
         }
 #else
-        wm_load_raw(d2, n_rows, Ppad, p0, lane, codes, clv, scl, x, s2);
+        wm_load_raw(d2, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, s2);
 #if PLG_WM_PF
         if (vi + 1 < v_end) {
           wm_prefetch(__shfl_sync(0xffffffffu, dnxt, 2), n_rows, Ppad, p0, lane, codes, clv, scl);
@@ -444,8 +433,7 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
         for (int i = 0; i < WM_V; i++) park[2][i][lane] = h2[i];
 #endif
       }
-#pragma unroll
-      for (int j = 0; j < WM_NG; j++) sc1[j] = sk[j] + s2[j];
+      sc1 = sk + s2;
       wm_rescale(n1, sc1, lane);
       // Visits come in normal form (planners): keep is 0 or 1 -- the partial toward c1 continues in
       // registers, the one toward c2 is at most parked.  Side 2 first, so that its hand-over is on
@@ -457,15 +445,9 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
         for (int i = 0; i < WM_V; i++) h2[i] = park[2][i][lane];
 #endif
         wm_chain<false>(n2, bf2, h2, park[0], lane, dummy, stk + (int64_t)(push >= 0 ? push : 0) * WM_V * 32, push >= 0, u);
-        if (push >= 0) {
-#pragma unroll
-          for (int j = 0; j < WM_NG; j++) stks[(push * WM_NG + j) * 32] = sc2[j];
-        }
+        if (push >= 0) stks[push * WM_NG * 32] = sc2;
         if (tree2 >= 0) {
-          int sct[WM_NG];
-#pragma unroll
-          for (int j = 0; j < WM_NG; j++) sct[j] = sc2[j] + s2[j] + st[j];
-          const double val = wm_site_sum_u(u, sct, w_out, pi_q, lane);
+          const double val = wm_site_sum_u(u, sc2 + s2 + st, w_out, pi_q, lane);
           if (lane == 0) partial[(int64_t)tree2 * pstride + slice] = val;
         }
       }
@@ -478,13 +460,9 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
 #pragma unroll
         for (int i = 0; i < WM_V; i++) h1[i] = park[1][i][lane];
         wm_chain<true>(n1, bf1, h1, park[0], lane, ak, nullptr, false, u);
-#pragma unroll
-        for (int j = 0; j < WM_NG; j++) sk[j] = sc1[j];
+        sk = sc1;
         if (tree1 >= 0) {
-          int sct[WM_NG];
-#pragma unroll
-          for (int j = 0; j < WM_NG; j++) sct[j] = sc1[j] + s1[j] + st[j];
-          const double val = wm_site_sum_u(u, sct, w_out, pi_q, lane);
+          const double val = wm_site_sum_u(u, sc1 + s1 + st, w_out, pi_q, lane);
           if (lane == 0) partial[(int64_t)tree1 * pstride + slice] = val;
         }
       }
