@@ -379,6 +379,7 @@ def run_ours(args):
             out["cpu_baseline"] = cpu_lnl_sample()[0]
         out["parsimony"] = parsimony_leg(fitch, nbh, L, peak, peak_src, not args.no_cpu)
         out["streaming"] = streaming_leg(fitch, likelihood, L, peak, peak_src)
+        out["target_shape_lnl"] = target_lnl_leg(likelihood, nbh, L, peak, peak_src)
     emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -437,6 +438,40 @@ def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
         res["cpu_baseline"] = cpu_fitch_sample(states, d)
     a.close()
     return res
+
+
+def target_lnl_leg(likelihood, nbh, L, peak, peak_src):
+    """north_star target shape for likelihood: GTR+G4 lnL of all 255,530 SPR neighbours of a
+    256-taxon x 100k-site tree (the parsimony leg is the same shape).  One call, ~1 s."""
+    import ctypes as C
+    import torch
+    n, S = 256, 100_000
+    rng = np.random.default_rng(1002)
+    codes = (1 << rng.integers(0, 4, (n, S))).astype(np.uint8)
+    la = likelihood.LikAlignment(codes, np.ones(S))
+    m = likelihood.Model(EXCH, FREQS, ALPHA)
+    d = random_desc(np.random.default_rng(1002 + 7919), n)
+    br = np.random.default_rng(1002 + 7920).exponential(0.1, d.shape)
+    nbh.score_likelihood(la, m, d, br, want_moves=False)
+    L.plg_profile_enable(1)
+    L.plg_profile_read(4, None, None, None, None, None)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, lnl = nbh.score_likelihood(la, m, d, br, want_moves=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    kms, by, un, nl, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
+    L.plg_profile_read(4, C.byref(kms), C.byref(by), C.byref(un), C.byref(nl), C.byref(rq))
+    L.plg_profile_enable(0)
+    la.close()
+    ach = by.value / (kms.value * 1e-3) / 1e9
+    return {"workload": "synthetic DNA 256 taxa x 100k sites, GTR+G4 lnL (fixed branch lengths) of all %d distinct "
+                        "SPR neighbours of a random tree" % len(lnl),
+            "value": len(lnl) * S / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "checksum": float(lnl.sum()),
+            "roofline": {"kernel": "walk4m_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "requested_gbs": rq.value / (kms.value * 1e-3) / 1e9,
+                         "launches": nl.value, "avg_launch_ms": kms.value / max(nl.value, 1), "peak_source": peak_src,
+                         "fp64_tflops": un.value * 640.0 / (kms.value * 1e-3) / 1e12}}
 
 
 def streaming_leg(fitch, likelihood, L, peak, peak_src):
