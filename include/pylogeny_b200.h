@@ -173,7 +173,10 @@ typedef struct plg_pll plg_pll;
  * "DNA, p1 = 1-N" | "WAG, p1 = 1-N" (pll.py:112-115).  Input branch lengths are discarded
  * (useDefaultz, :152): every branch starts at z = 0.9.  DNA = GTR with all rates 1 and
  * empirical base frequencies, alpha = 1, 4 Gamma categories; WAG table provenance: see
- * csrc/protein_models.cpp. */
+ * csrc/protein_models.cpp.  The reference makes one instance per tree and re-parses the alignment
+ * each time (:138); here the parsed, pattern-compressed, device-resident alignment is shared by
+ * all handles on the same file (path, size, mtime, inode, device), most recent four files kept;
+ * PLG_PLL_ALN_CACHE=0 turns the sharing off. */
 int plg_pll_new(const char *phylip_path, const char *newick, const char *partition_path,
                 plg_pll **out);
 int plg_pll_destroy(plg_pll *p);

@@ -20,6 +20,7 @@
 #include <fstream>
 #include <memory>
 #include <sstream>
+#include <sys/stat.h>
 #include <unordered_map>
 
 #include "lik.h"
@@ -126,8 +127,8 @@ deriv_kernel(const double *__restrict__ S, const int *__restrict__ sc, const dou
 
 // ---------------------------------------------------------------------------------------------
 struct PllProblem {
-  std::unique_ptr<LikAln> aln;
-  std::unique_ptr<Model> model;
+  std::shared_ptr<LikAln> aln;   // shared with the alignment cache (read-only after construction)
+  std::shared_ptr<Model> model;
   UTree tree;
   std::vector<std::string> tip_names;  // tip id -> label
   std::vector<int32_t> tip_rows;       // tip id -> alignment row
@@ -438,34 +439,24 @@ struct plg_pll {
   PllProblem p;
 };
 
-extern "C" int plg_pll_new(const char *phylip_path, const char *newick, const char *partition_path, plg_pll **out) {
-  PLG_API_BEGIN_LOCKED
-  if (!phylip_path || !newick || !partition_path || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
-  int dev_count = 0;
-  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
-    PLG_FAIL(PLG_ERR_CUDA, "no CUDA device: pylogeny_b200 has no CPU fallback");
-  std::vector<std::string> names, seqs;
-  read_phylip(phylip_path, names, seqs);
-  const std::string model_name = read_partition_model(partition_path);
-  const bool dna = (model_name == "DNA");
-  if (!dna && model_name != "WAG")
-    PLG_FAIL(PLG_ERR_UNSUPPORTED, "protein model '%s': only WAG ships with the engine (pll.py:102 default); "
-             "use plg_model_create for other matrices", model_name.c_str());
-  std::unique_ptr<plg_pll> h(new plg_pll());
-  PllProblem &pr = h->p;
-  HostTree ht = parse_newick(newick);
-  pr.tree = utree_from_newick(ht, pr.tip_names);
+namespace {
+struct PllAlignment {
+  std::vector<std::string> names;
   std::unordered_map<std::string, int> row_of;
-  for (size_t i = 0; i < names.size(); i++) row_of.emplace(names[i], (int)i);
-  if ((size_t)pr.tree.n_tips != names.size())
-    PLG_FAIL(PLG_ERR_IO, "Could not find correct correspondances.");  // libpllWrapper.c:153-156
-  for (auto &nm : pr.tip_names) {
-    auto it = row_of.find(nm);
-    if (it == row_of.end()) PLG_FAIL(PLG_ERR_IO, "Could not find correct correspondances.");
-    pr.tip_rows.push_back(it->second);
-  }
-  // default branch lengths (useDefaultz = PLL_TRUE, libpllWrapper.c:152): every z = 0.9
-  for (auto &l : pr.tree.len) for (auto &x : l) x = -std::log(PLL_DEFAULTZ);
+  std::shared_ptr<LikAln> aln;
+  std::shared_ptr<Model> model;
+  // identity of the file it was read from
+  std::string path, model_name;
+  long long size = 0, mtime_ns = 0, ino = 0;
+  int device = 0;
+};
+
+std::shared_ptr<PllAlignment> load_alignment(const char *phylip_path, bool dna) {
+  std::shared_ptr<PllAlignment> al(new PllAlignment());
+  std::vector<std::string> seqs;
+  read_phylip(phylip_path, al->names, seqs);
+  const std::vector<std::string> &names = al->names;
+  for (size_t i = 0; i < names.size(); i++) al->row_of.emplace(names[i], (int)i);
   // encode + compress identical columns (weights = multiplicities; lnL is unchanged)
   const size_t n = names.size(), m = seqs[0].size();
   std::vector<uint8_t> codes(n * m);
@@ -485,7 +476,7 @@ extern "C" int plg_pll_new(const char *phylip_path, const char *newick, const ch
   std::vector<uint8_t> packed(n * P);
   for (size_t r = 0; r < n; r++)
     for (size_t q = 0; q < P; q++) packed[r * P + q] = codes[r * m + first[q]];
-  pr.aln.reset(new LikAln(dna ? PLG_DATA_DNA : PLG_DATA_AA, (int)n, (int64_t)P, packed.data(), w.data()));
+  al->aln.reset(new LikAln(dna ? PLG_DATA_DNA : PLG_DATA_AA, (int)n, (int64_t)P, packed.data(), w.data()));
   if (dna) {
     // GTR with all six rates 1.0 and empirical base frequencies; ambiguity codes share their
     // count among compatible bases in proportion to the current estimate (8 rounds)
@@ -505,10 +496,76 @@ extern "C" int plg_pll_new(const char *phylip_path, const char *newick, const ch
       for (int k = 0; k < 4; k++) f[k] = std::max(cnt[k] / s, 1e-6);
     }
     const double ones[6] = {1, 1, 1, 1, 1, 1};
-    pr.model.reset(new Model(4, ones, f, 1.0, 4));
+    al->model.reset(new Model(4, ones, f, 1.0, 4));
   } else {
-    pr.model.reset(new Model(20, WAG_EXCH_PTR, WAG_FREQS, 1.0, 4));
+    al->model.reset(new Model(20, WAG_EXCH_PTR, WAG_FREQS, 1.0, 4));
   }
+  return al;
+}
+
+// most recently used first; entries keep device memory, so only a few are held
+// (PLG_PLL_ALN_CACHE=0 disables the cache).  Callers hold g_api_mutex.
+std::vector<std::shared_ptr<PllAlignment>> g_aln_cache;
+
+std::shared_ptr<PllAlignment> cached_alignment(const char *phylip_path, const std::string &model_name, bool dna) {
+  const char *env = getenv("PLG_PLL_ALN_CACHE");
+  const size_t keep = env ? (size_t)std::max(0, atoi(env)) : 4;
+  struct stat sb;
+  if (keep == 0 || stat(phylip_path, &sb) != 0) return load_alignment(phylip_path, dna);  // (a missing file fails inside)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const long long mt = (long long)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec;
+  for (size_t i = 0; i < g_aln_cache.size(); i++) {
+    const PllAlignment &c = *g_aln_cache[i];
+    if (c.path == phylip_path && c.model_name == model_name && c.size == (long long)sb.st_size && c.mtime_ns == mt &&
+        c.ino == (long long)sb.st_ino && c.device == dev) {
+      std::shared_ptr<PllAlignment> hit = g_aln_cache[i];
+      g_aln_cache.erase(g_aln_cache.begin() + i);
+      g_aln_cache.insert(g_aln_cache.begin(), hit);
+      return hit;
+    }
+  }
+  std::shared_ptr<PllAlignment> al = load_alignment(phylip_path, dna);
+  al->path = phylip_path; al->model_name = model_name;
+  al->size = (long long)sb.st_size; al->mtime_ns = mt; al->ino = (long long)sb.st_ino; al->device = dev;
+  g_aln_cache.insert(g_aln_cache.begin(), al);
+  if (g_aln_cache.size() > keep) g_aln_cache.resize(keep);
+  return al;
+}
+}  // namespace
+
+extern "C" int plg_pll_new(const char *phylip_path, const char *newick, const char *partition_path, plg_pll **out) {
+  PLG_API_BEGIN_LOCKED
+  if (!phylip_path || !newick || !partition_path || !out) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+    PLG_FAIL(PLG_ERR_CUDA, "no CUDA device: pylogeny_b200 has no CPU fallback");
+  // The reference creates one instance per TREE and re-parses the alignment each time
+  // (libpllWrapper.c:138, scoring.py:41-75).  Here the parsed, pattern-compressed, device-resident
+  // alignment and its model are kept per (file identity, partition model, device) and shared by
+  // the handles: a hill climb pays the 45 ms of parsing once, not per neighbour.
+  const std::string model_name = read_partition_model(partition_path);
+  const bool dna = (model_name == "DNA");
+  if (!dna && model_name != "WAG")
+    PLG_FAIL(PLG_ERR_UNSUPPORTED, "protein model '%s': only WAG ships with the engine (pll.py:102 default); "
+             "use plg_model_create for other matrices", model_name.c_str());
+  std::shared_ptr<PllAlignment> al = cached_alignment(phylip_path, model_name, dna);
+  const std::vector<std::string> &names = al->names;
+  std::unique_ptr<plg_pll> h(new plg_pll());
+  PllProblem &pr = h->p;
+  HostTree ht = parse_newick(newick);
+  pr.tree = utree_from_newick(ht, pr.tip_names);
+  if ((size_t)pr.tree.n_tips != names.size())
+    PLG_FAIL(PLG_ERR_IO, "Could not find correct correspondances.");  // libpllWrapper.c:153-156
+  for (auto &nm : pr.tip_names) {
+    auto it = al->row_of.find(nm);
+    if (it == al->row_of.end()) PLG_FAIL(PLG_ERR_IO, "Could not find correct correspondances.");
+    pr.tip_rows.push_back(it->second);
+  }
+  // default branch lengths (useDefaultz = PLL_TRUE, libpllWrapper.c:152): every z = 0.9
+  for (auto &l : pr.tree.len) for (auto &x : l) x = -std::log(PLL_DEFAULTZ);
+  pr.aln = al->aln;
+  pr.model = al->model;
   *out = h.release();
   PLG_API_END
 }

@@ -163,3 +163,45 @@ def test_moves_in_distance_vs_oracle():
         W.getSPRMovesInDistance(h, "2")
     W.destroy(h)
     pm.close(); ali.close()
+
+
+def test_alignment_cache_is_keyed_by_file_identity(tmp_path):
+    """Handles on the same PHYLIP file share one parsed, device-resident alignment (the reference
+    re-parses it per tree, libpllWrapper.c:138); rewriting the file must not serve stale data."""
+    import os
+    import time
+    from pylogeny_b200 import libpllWrapper as W, pll
+    ali, d = _case(n=9, S=600, seed=11)
+    labels = ali.getTaxa()
+    nw = desc_to_newick(d, labels)
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    path = str(tmp_path / "a.phy")
+    text = open(ali.getPhylip()).read()
+    open(path, "w").write(text)
+    h1 = W.new(path, nw, pm.getFileName())
+    h2 = W.new(path, nw, pm.getFileName())          # cache hit
+    l1, l2 = W.evaluate(h1), W.evaluate(h2)
+    assert l1 == l2
+    W.destroy(h1)
+    assert W.evaluate(h2) == l2                      # the shared alignment outlives the first handle
+    # same path, different content (first sequence altered): a fresh parse, a different likelihood
+    lines = text.split("\n")
+    name, seq = lines[1].split()
+    flipped = seq.translate(str.maketrans("ACGT", "CATG"))
+    lines[1] = "%s %s" % (name, flipped)
+    time.sleep(0.01)
+    open(path, "w").write("\n".join(lines))
+    os.utime(path, None)
+    h3 = W.new(path, nw, pm.getFileName())
+    l3 = W.evaluate(h3)
+    assert l3 != l2
+    os.environ["PLG_PLL_ALN_CACHE"] = "0"
+    try:
+        h4 = W.new(path, nw, pm.getFileName())       # cache off: same answer as the cached fresh parse
+        assert W.evaluate(h4) == l3
+        W.destroy(h4)
+    finally:
+        del os.environ["PLG_PLL_ALN_CACHE"]
+    W.destroy(h2); W.destroy(h3)
+    pm.close(); ali.close()
