@@ -43,3 +43,13 @@ for env, vals in (("PLG_TREE_MODE", ("walk", "levels")), ("PLG_LIK_NB_MODE", ("w
               nbh.score_parsimony(fa2, d2)[1].sum(), nbh.score_likelihood(la2, m, d2, br2)[1].sum())
     os.environ.pop(env)
 print("sanitize pass 2 done")
+# device-planned vs host-planned neighbourhoods, the global-memory fallback of the plan kernels, and
+# the 20-state TBR path (hoisted reconnecting branch + row evaluations)
+for env, vals in (("PLG_FITCH_NB_PLAN", ("device", "host")), ("PLG_LIK_NB_PLAN", ("device", "host")),
+                  ("PLG_SPR_PLAN_GLOBAL", ("1",)), ("PLG_AA_EVAL_ROWS", ("1", "0"))):
+    for v in vals:
+        os.environ[env] = v
+        print(env, v, nbh.score_parsimony(fa2, d2)[1].sum(), nbh.score_likelihood(la2, m, d2, br2)[1].sum(),
+              nbh.score_likelihood(pa, pm, d, br, move_type=nbh.MOVE_TBR)[1].sum())
+    os.environ.pop(env)
+print("sanitize pass 3 done")
