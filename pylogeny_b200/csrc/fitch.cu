@@ -529,6 +529,24 @@ static void launch_level(const FitchAln &a, FitchWorkspace &ws, int64_t op0, int
   }
 }
 
+// one helper stream per device for work that is independent of the level launches
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ready = nullptr, planned = nullptr;
+};
+static SideStream &side_stream() {
+  static SideStream ss[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideStream &x = ss[dev & 63];
+  if (!x.s) {
+    PLG_CUDA(cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking));
+    PLG_CUDA(cudaEventCreateWithFlags(&x.ready, cudaEventDisableTiming));
+    PLG_CUDA(cudaEventCreateWithFlags(&x.planned, cudaEventDisableTiming));
+  }
+  return x;
+}
+
 void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram &prog, int32_t *out_costs,
                        cudaStream_t st, int32_t *out_moves) {
   const size_t vec_words = (size_t)a.K * a.words32;
@@ -542,6 +560,41 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
                              cudaMemcpyHostToDevice, st));
   }
   PLG_CUDA(cudaMemsetAsync(ws.cost.p, 0, std::max<size_t>(1, (size_t)prog.n_costs) * sizeof(unsigned int), st));
+  const bool device_plan = !prog.spr_searches.empty() && prog.spr_n_visits > 0;
+  SideStream &side = side_stream();
+  if (device_plan) {
+    // Device-planned SPR neighbourhood: the visit list is written by spr_plan_kernel from O(n)
+    // records, not uploaded -- on a side stream, so that its one-warp-per-search latency chain
+    // (~0.12 ms at 256 taxa) overlaps the base tree's level launches instead of preceding the walk.
+    ws.nbw_visits.alloc((size_t)prog.spr_n_visits * 2);
+    ws.spr_edges.alloc(prog.spr_edges.size());
+    ws.spr_searches.alloc(prog.spr_searches.size() * 2);
+    if (out_moves) { ws.spr_moves.alloc((size_t)prog.spr_n_unique); ws.spr_moves_host.alloc((size_t)prog.spr_n_unique); }
+    PLG_CUDA(cudaEventRecord(side.ready, st));  // (the buffers above are stream-ordered allocations of `st`)
+    PLG_CUDA(cudaStreamWaitEvent(side.s, side.ready, 0));
+    PLG_CUDA(cudaMemcpyAsync(ws.spr_edges.p, prog.spr_edges.data(), prog.spr_edges.size() * sizeof(SprEdgeRec),
+                             cudaMemcpyHostToDevice, side.s));
+    PLG_CUDA(cudaMemcpyAsync(ws.spr_searches.p, prog.spr_searches.data(),
+                             prog.spr_searches.size() * sizeof(SprSearchRec), cudaMemcpyHostToDevice, side.s));
+    const int n_search = (int)prog.spr_searches.size();
+    const size_t edge_bytes = prog.spr_edges.size() * sizeof(SprEdgeRec);
+    const bool in_smem = edge_bytes <= SPR_PLAN_SMEM_MAX && !getenv("PLG_SPR_PLAN_GLOBAL");  // (tests: the fallback for huge trees)
+    static bool plan_attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!plan_attr_set[dev & 63]) {
+      PLG_CUDA(cudaFuncSetAttribute(spr_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPR_PLAN_SMEM_MAX));
+      plan_attr_set[dev & 63] = true;
+    }
+    spr_plan_kernel<<<(n_search + 63) / 64, 64, in_smem ? edge_bytes : 0, side.s>>>(
+        ws.spr_edges.p, in_smem ? (int)prog.spr_edges.size() : 0, ws.spr_searches.p, n_search, prog.spr_first_acc,
+        ws.nbw_visits.p, out_moves ? ws.spr_moves.p : nullptr);
+    count_launch();
+    PLG_CUDA(cudaEventRecord(side.planned, side.s));
+    if (out_moves)  // the move table comes back while the walk runs; copied out after the final sync
+      PLG_CUDA(cudaMemcpyAsync(ws.spr_moves_host.p, ws.spr_moves.p, (size_t)prog.spr_n_unique * sizeof(int4),
+                               cudaMemcpyDeviceToHost, side.s));
+  }
   for (size_t l = 0; l + 1 < prog.level_off.size(); l++) {
     const int64_t o0 = prog.level_off[l], cnt = prog.level_off[l + 1] - o0;
     if (!cnt) continue;
@@ -571,36 +624,12 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
       default: PLG_FAIL(PLG_ERR_STATES, "no kernel for %d planes", a.K);
     }
   }
-  const bool device_plan = !prog.spr_searches.empty() && prog.spr_n_visits > 0;
   if (!prog.walk_groups.empty()) {
-    ws.nbw_visits.alloc((device_plan ? (size_t)prog.spr_n_visits : prog.walk_visits.size()) * 2);
+    if (!device_plan) ws.nbw_visits.alloc(prog.walk_visits.size() * 2);
     ws.nbw_groups.alloc(prog.walk_groups.size());
     if (device_plan) {
-      // the visit list is written by spr_plan_kernel from O(n) records, not uploaded
-      ws.spr_edges.alloc(prog.spr_edges.size());
-      ws.spr_searches.alloc(prog.spr_searches.size() * 2);
-      if (out_moves) ws.spr_moves.alloc((size_t)prog.spr_n_unique);
-      PLG_CUDA(cudaMemcpyAsync(ws.spr_edges.p, prog.spr_edges.data(), prog.spr_edges.size() * sizeof(SprEdgeRec),
-                               cudaMemcpyHostToDevice, st));
-      PLG_CUDA(cudaMemcpyAsync(ws.spr_searches.p, prog.spr_searches.data(),
-                               prog.spr_searches.size() * sizeof(SprSearchRec), cudaMemcpyHostToDevice, st));
-      const int n_search = (int)prog.spr_searches.size();
-      const size_t edge_bytes = prog.spr_edges.size() * sizeof(SprEdgeRec);
-      const bool in_smem = edge_bytes <= SPR_PLAN_SMEM_MAX && !getenv("PLG_SPR_PLAN_GLOBAL");  // (tests: the fallback for huge trees)
-      static bool plan_attr_set[64] = {false};
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (!plan_attr_set[dev & 63]) {
-        PLG_CUDA(cudaFuncSetAttribute(spr_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPR_PLAN_SMEM_MAX));
-        plan_attr_set[dev & 63] = true;
-      }
-      spr_plan_kernel<<<(n_search + 63) / 64, 64, in_smem ? edge_bytes : 0, st>>>(
-          ws.spr_edges.p, in_smem ? (int)prog.spr_edges.size() : 0, ws.spr_searches.p, n_search, prog.spr_first_acc,
-          ws.nbw_visits.p, out_moves ? ws.spr_moves.p : nullptr);
-      count_launch();
-      if (out_moves)
-        PLG_CUDA(cudaMemcpyAsync(out_moves, ws.spr_moves.p, (size_t)prog.spr_n_unique * sizeof(int4),
-                                 cudaMemcpyDeviceToHost, st));
+      // the visit list was written by spr_plan_kernel on the side stream while the levels ran
+      PLG_CUDA(cudaStreamWaitEvent(st, side.planned, 0));
     } else {
       PLG_CUDA(cudaMemcpyAsync(ws.nbw_visits.p, prog.walk_visits.data(),
                                prog.walk_visits.size() * sizeof(FitchWalkVisit), cudaMemcpyHostToDevice, st));
@@ -651,6 +680,10 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
   if (out_costs && prog.n_costs) {
     PLG_CUDA(cudaMemcpyAsync(out_costs, ws.cost.p, (size_t)prog.n_costs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PLG_CUDA(cudaStreamSynchronize(st));
+  }
+  if (device_plan && out_moves) {
+    PLG_CUDA(cudaStreamSynchronize(side.s));
+    memcpy(out_moves, ws.spr_moves_host.p, (size_t)prog.spr_n_unique * sizeof(int4));
   }
 }
 

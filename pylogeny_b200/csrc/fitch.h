@@ -64,6 +64,7 @@ struct FitchWorkspace {
   DevBuf<int4> nbw_visits;      // search walks: FitchWalkVisit[] (two int4 each), FitchWalkGroup[]
   DevBuf<int4> nbw_groups;
   DevBuf<int4> spr_edges, spr_searches, spr_moves;  // device-planned SPR neighbourhoods
+  PinBuf<int4> spr_moves_host;                      // move table staging (pinned)
 };
 
 // Scratch pool shared by every alignment handle on the current device (grow-only; dropping a

@@ -216,8 +216,11 @@ __device__ __forceinline__ unsigned int fw_join_miss(const unsigned int (&n)[K][
   return c;
 }
 
+#ifndef PLG_FSW_MINB
+#define PLG_FSW_MINB 2  // 120 registers, no spills (1: 147 registers, 3.2 vs 2.66 ms per 256x100k step; 3: 80 registers with spills, 3.6)
+#endif
 template <int K, int VW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PLG_FSW_MINB)
 fitch_search_walk_kernel(const unsigned int *__restrict__ tips, const unsigned int *__restrict__ scratch,
                          int n_tip_slots, const FitchWalkGroup *__restrict__ groups,
                          const FitchWalkVisit *__restrict__ visits, int64_t words32, int blocks_per_group,
