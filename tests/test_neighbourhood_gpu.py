@@ -283,3 +283,31 @@ def test_device_planner_global_memory_fallback(monkeypatch):
     assert got_f[0].tolist() == want_f[0].tolist() and got_f[1].tolist() == want_f[1].tolist()
     assert got_l[0].tolist() == want_l[0].tolist() and got_l[1].tolist() == want_l[1].tolist()
     fa.close(); la.close(); m.close()
+
+
+def test_device_planner_many_small_trees(monkeypatch):
+    """Every tree size from 4 to 24 tips, three random shapes each: device-planned neighbourhoods
+    (parsimony and GTR+G4) equal the host-planned ones, move tables included."""
+    from pylogeny_b200 import fitch, likelihood, neighbourhood as nbh
+    rng = np.random.default_rng(2024)
+    P = 96
+    for n in range(4, 25):
+        st = random_states(rng, n, P, 4, 0.05)
+        w = rng.integers(1, 6, P).astype(np.int64)
+        fa = fitch.FitchAlignment.from_dense(st, w)
+        codes = (1 << rng.integers(0, 4, (n, P))).astype(np.uint8)
+        la = likelihood.LikAlignment(codes, w.astype(float))
+        m = likelihood.Model(rng.uniform(0.5, 2.0, 6), rng.dirichlet(np.ones(4) * 8), 0.9)
+        for _ in range(3):
+            d = random_desc(rng, n)
+            br = rng.exponential(0.1, d.shape)
+            res = {}
+            for plan in ("device", "host"):
+                monkeypatch.setenv("PLG_FITCH_NB_PLAN", plan)
+                monkeypatch.setenv("PLG_LIK_NB_PLAN", plan)
+                res[plan] = (nbh.score_parsimony(fa, d), nbh.score_likelihood(la, m, d, br))
+            for k in (0, 1):
+                assert res["device"][k][0].tolist() == res["host"][k][0].tolist(), (n, k)
+                assert res["device"][k][1].tolist() == res["host"][k][1].tolist(), (n, k)
+            assert len(res["device"][0][1]) == nbh.neighbourhood_size(d)
+        fa.close(); la.close(); m.close()
