@@ -185,6 +185,15 @@ int plg_pll_destroy(plg_pll *p);
 int plg_pll_loglik(plg_pll *p, double *out);
 /* lnL at the current branch lengths without optimisation (pllEvaluateLikelihood, :77-78). */
 int plg_pll_evaluate(plg_pll *p, double *out);
+/* Batched scoring.getLogLikelihood (scoring.py:41-75: new / getLogLikelihood / getNewickString /
+ * destroy per tree): every tree starts at z = 0.9, gets up to `passes` smoothing passes (the
+ * reference: 3) and its lnL.  Trees must hold the alignment's taxa.  DNA runs all trees in lockstep
+ * on the device; *newick_bytes = room needed by plg_pll_batch_newicks, which copies the optimised
+ * trees of the calling thread's last batch, NUL-separated, in input order. */
+int plg_pll_loglik_batch(const char *phylip_path, const char *partition_path, int64_t n_trees,
+                         const char *const *newicks, int passes, double *out_lnl,
+                         size_t *newick_bytes);
+int plg_pll_batch_newicks(char *buf, size_t bytes);
 /* getNewickString(handle) (:217-239): unrooted Newick with the current branch lengths.  *len in:
  * buffer size, out: bytes needed incl. NUL; call with buf == NULL to size the buffer. */
 int plg_pll_newick(plg_pll *p, char *buf, size_t *len);

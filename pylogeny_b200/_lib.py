@@ -90,3 +90,5 @@ def _declare(L):
     L.plg_pll_moves_compute.argtypes = [vp, C.c_int, C.c_int, i64p, C.POINTER(C.c_size_t)]
     L.plg_pll_moves_fetch.argtypes = [vp, vp, vp, vp, C.c_size_t]
     L.plg_pll_info.argtypes = [vp, C.POINTER(C.c_int), i64p, dp, dp]
+    L.plg_pll_loglik_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, strs, C.c_int, vp, C.POINTER(C.c_size_t)]
+    L.plg_pll_batch_newicks.argtypes = [C.c_char_p, C.c_size_t]

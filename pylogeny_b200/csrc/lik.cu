@@ -40,11 +40,11 @@ struct NCodes { static constexpr int value = K == 4 ? 16 : 23; };
 template <int K, int R>
 __global__ void pmatrix_kernel(const ModelDev *__restrict__ model, const double *__restrict__ brlen,
                                const unsigned int *__restrict__ masks, double *__restrict__ pmat,
-                               double *__restrict__ tiptab) {
+                               double *__restrict__ tiptab, const int *__restrict__ idx = nullptr) {
   constexpr int KK = K * K, KKP = KK + 1, NC = NCodes<K>::value;
   __shared__ double ex[R * K];
   __shared__ double Pm[R * KKP];
-  const int pm = blockIdx.x;
+  const int pm = idx ? idx[blockIdx.x] : blockIdx.x;  // (idx: only the entries whose length changed)
   const double t = brlen[pm];
   for (int e = threadIdx.x; e < R * K; e += blockDim.x)
     ex[e] = exp(model->eval[e % K] * t * model->rates[e / K]);
@@ -979,6 +979,43 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     }
     tm.lap("    sync+D2H");
   }
+}
+
+void dna4_pmatrices(const LikAln &a, const Model &m, const double *d_brlen, const int *d_idx, int64_t n,
+                    double *d_pmat, double *d_tiptab, cudaStream_t st) {
+  if (n <= 0) return;
+  prof_begin(PROF_PMATRIX, st);
+  pmatrix_kernel<4, 4><<<(unsigned)n, 128, 0, st>>>(m.d.p, d_brlen, a.masks.p, d_pmat, d_tiptab, d_idx);
+  count_launch();
+  prof_end(PROF_PMATRIX, st, (double)n * (4 * 17 + 16 * 16) * 8.0, (double)n);
+}
+
+void dna4_updates(const LikAln &a, const Model &m, const LikOpF *d_ops, int64_t n, const double *d_pmat,
+                  const double *d_tiptab, double *d_clv, int *d_scl, cudaStream_t st) {
+  if (n <= 0) return;
+  const int64_t bpo = a.Ppad / DNA4_PATTERNS_PER_BLOCK;
+  prof_begin(PROF_CLV_UPDATE, st);
+  clv4_kernel<<<(unsigned)(n * bpo), D4_THREADS, 0, st>>>(d_ops, (int)bpo, a.n_rows, a.Ppad, a.codes.p, a.masks.p,
+                                                         a.weights.p, m.d.p, d_pmat, d_tiptab, d_clv, d_scl, nullptr, 0);
+  count_launch();
+  // (operand kinds are not known here: counted as inner/inner, 3C + 12 per pattern)
+  prof_end(PROF_CLV_UPDATE, st, (double)n * 3.0 * 132.0 * (double)a.P, (double)n * (double)a.P);
+}
+
+void dna4_evals(const LikAln &a, const Model &m, const LikEval *d_evals, int64_t n, const double *d_pmat,
+                const double *d_tiptab, const double *d_clv, const int *d_scl, double *d_partial, double *d_lnl,
+                cudaStream_t st) {
+  if (n <= 0) return;
+  const int64_t ebpo = a.Ppad / D4_THREADS;
+  PLG_CUDA(cudaMemsetAsync(d_partial, 0, (size_t)n * ebpo * 8, st));
+  prof_begin(PROF_ROOT_EVAL, st);
+  eval4_kernel<<<(unsigned)(n * ebpo), D4_THREADS, 0, st>>>(d_evals, (int)ebpo, a.n_rows, a.Ppad, a.codes.p, a.masks.p,
+                                                           a.weights.p, m.d.p, d_pmat, d_tiptab, d_clv, d_scl, d_partial,
+                                                           (int)ebpo);
+  count_launch();
+  prof_end(PROF_ROOT_EVAL, st, (double)n * (2.0 * 132.0 + 8.0) * (double)a.P, (double)n * (double)a.P);
+  reduce_partials_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>((int)n, (int)ebpo, d_partial, d_lnl);
+  count_launch();
 }
 
 void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double *out_lnl, cudaStream_t st) {

@@ -18,6 +18,14 @@ struct LikEval {
   int a, pa, b, pb, c, pc, tree, pad;
 };
 
+// DNA x Gamma-4 update with an optional fused evaluation (csrc/lik_dna.cuh clv4_kernel); 48 bytes
+struct LikOpF {
+  int dst, a, b, pa, pb;             // as LikOp
+  int tree;                          // >= 0: fused evaluation writes partial[tree]
+  int e_pa, e_b, e_pb, e_c, e_pc;    // evaluation operands: (P[e_pa] N) (P[e_pb] b) (P[e_pc] c)
+  int pad;                           // 1: do not store dst (no reader)
+};
+
 // One search step of the SPR edge-insertion walk scoring both neighbours at the node it reaches
 // (DNA x Gamma-4 path, csrc/lik_visit.cuh).  Operand ids as in LikOp; 64 bytes.
 struct LikVisit {
@@ -112,6 +120,19 @@ void build_full_lik_program(const TreeBatch &b, int64_t t0, int64_t t1, int n_ro
 void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, double *out_lnl,
                      cudaStream_t st, int32_t *out_moves = nullptr);
 void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double *out_lnl, cudaStream_t st);
+
+// Building blocks of the DNA x Gamma-4 level kernels for callers that keep their own device
+// state (batched branch-length smoothing, pll_api.cu): everything is passed as device pointers.
+//   dna4_pmatrices: P-matrix + tip table of entries idx[0..n) (idx == nullptr: entries 0..n) from
+//   brlen[entry]; dna4_updates: n ops, independent of each other; dna4_evals: lnl[ev.tree] for n
+//   evaluations (partial: >= n * Ppad / 128 doubles of scratch).
+void dna4_pmatrices(const LikAln &a, const Model &m, const double *d_brlen, const int *d_idx, int64_t n,
+                    double *d_pmat, double *d_tiptab, cudaStream_t st);
+void dna4_updates(const LikAln &a, const Model &m, const LikOpF *d_ops, int64_t n, const double *d_pmat,
+                  const double *d_tiptab, double *d_clv, int *d_scl, cudaStream_t st);
+void dna4_evals(const LikAln &a, const Model &m, const LikEval *d_evals, int64_t n, const double *d_pmat,
+                const double *d_tiptab, const double *d_clv, const int *d_scl, double *d_partial, double *d_lnl,
+                cudaStream_t st);
 
 }  // namespace plg
 

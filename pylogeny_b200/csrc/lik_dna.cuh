@@ -27,13 +27,6 @@ namespace plg {
 #endif
 constexpr int D4_THREADS = PLG_D4_THREADS;
 
-struct LikOpF {                      // 48 bytes
-  int dst, a, b, pa, pb;             // as LikOp
-  int tree;                          // >= 0: fused evaluation writes partial[tree]
-  int e_pa, e_b, e_pb, e_c, e_pc;    // evaluation operands: (P[e_pa] N) (P[e_pb] b) (P[e_pc] c)
-  int pad;                           // 1: do not store dst (no reader)
-};
-
 __device__ __forceinline__ void d4_load16(const double *__restrict__ base, int64_t Ppad, double (&x)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; i++) x[i] = __ldg(base + (int64_t)i * Ppad);

@@ -23,6 +23,7 @@
 #include <sys/stat.h>
 #include <unordered_map>
 
+#include "hostpool.h"
 #include "lik.h"
 #include "neighbourhood.h"
 
@@ -431,6 +432,351 @@ static UTree utree_from_newick(const HostTree &ht, std::vector<std::string> &tip
   return utree_from_desc(n_tips, desc.data(), br.data());
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched getLogLikelihood: many trees on one alignment, each with the reference's treatment
+// (default z = 0.9, up to `passes` smoothing passes, lnL; libpllWrapper.c:152, :205).  The smoothing
+// traversal of a tree is a fixed action list -- OPT(x, from): one Newton step on the branch above
+// x; CLV(x, k): re-orient x's conditional vector toward neighbour k -- whose LENGTH is the same
+// for every binary tree of n tips ((2n-3) OPT + 3(n-2) CLV) although the order differs.  So B
+// trees advance in lockstep: step i runs the i-th action of every tree, CLV actions as one
+// clv4_kernel launch, OPT actions as sumtable -> opt4_batch_kernel (the whole makenewz step of a
+// branch in one block: derivative sums, bad-curvature guard, Newton update) -> P-matrices of the
+// changed branches.  Nothing comes back to the host until the scores: the per-tree path pays a
+// device round trip per branch (~20 ms per 64-taxon tree); here it is ~1 ms per tree.
+// One conditional vector per inner node is enough (libpll's x-pointer orientation): while
+// smooth(x) runs, the parent's vector keeps pointing at x and a finished child's points back at x.
+// ---------------------------------------------------------------------------------------------
+struct OptItem {
+  int a_id, b_id, tree, branch;  // operand ids of the branch's two ends; tree of the chunk; global branch index
+};
+
+__global__ void __launch_bounds__(SM_THREADS)
+sumtable4_batch_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
+                       const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
+                       const ModelDev *__restrict__ model, const double *__restrict__ clv,
+                       const int *__restrict__ scl, double *__restrict__ S, int *__restrict__ Ssc) {
+  constexpr int K = 4, R = 4;
+  const int item = blockIdx.x / blocks_per_item;
+  const OptItem it = items[item];
+  const int r = threadIdx.x % R;
+  const int64_t p = (int64_t)(blockIdx.x - item * blocks_per_item) * (SM_THREADS / R) + threadIdx.x / R;
+  double A[K], B[K];
+  int sc = 0;
+  auto fetch = [&](int id, double(&x)[K]) {
+    if (id < n_rows) {
+      const unsigned int m = masks[codes[(int64_t)id * Ppad + p]];
+#pragma unroll
+      for (int k = 0; k < K; k++) x[k] = (m >> k & 1) ? 1.0 : 0.0;
+    } else {
+      const double *src = clv + ((int64_t)(id - n_rows) * R * K + r * K) * Ppad + p;
+#pragma unroll
+      for (int k = 0; k < K; k++) x[k] = src[(int64_t)k * Ppad];
+      sc += scl[(int64_t)(id - n_rows) * Ppad + p];
+    }
+  };
+  fetch(it.a_id, A);
+  fetch(it.b_id, B);
+#pragma unroll
+  for (int i = 0; i < K; i++) A[i] *= model->freqs[i];
+  double *So = S + (int64_t)it.tree * R * K * Ppad;
+  for (int k = 0; k < K; k++) {
+    double l = 0.0, rr = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      l = fma(A[i], model->U[i * K + k], l);
+      rr = fma(model->Uinv[k * K + i], B[i], rr);
+    }
+    So[((int64_t)r * K + k) * Ppad + p] = l * rr;
+  }
+  if (r == 0) Ssc[(int64_t)it.tree * Ppad + p] = sc;
+}
+
+// One makenewz step (optimise_branch with maxiter = 1) per block, on the tree's sum table.
+__global__ void __launch_bounds__(SM_THREADS)
+opt4_batch_kernel(const OptItem *__restrict__ items, int64_t Ppad, const double *__restrict__ weights,
+                  const ModelDev *__restrict__ model, const double *__restrict__ S, const int *__restrict__ Ssc,
+                  double *__restrict__ brlen, const int *__restrict__ active, int *__restrict__ changed) {
+  constexpr int RK = 16;
+  const OptItem it = items[blockIdx.x];
+  if (!active[it.tree]) return;
+  __shared__ double tab[3][RK];
+  __shared__ double red[3][SM_THREADS / 32];
+  __shared__ double sh_lz;
+  __shared__ int sh_go;
+  const double *Sb = S + (int64_t)it.tree * RK * Ppad;
+  const int *sc = Ssc + (int64_t)it.tree * Ppad;
+  double z0 = 0.0, z = 0.0, zprev = 0.0, d1 = 0.0, d2 = 0.0;
+  if (threadIdx.x == 0) {
+    z0 = exp(-brlen[it.branch]);
+    z = fmin(fmax(z0, PLL_ZMIN), PLL_ZMAX);
+    zprev = z;
+  }
+  for (int guard = 0; guard < 64; guard++) {  // "bad curvature: shorten the branch" loop
+    if (threadIdx.x == 0) sh_lz = log(fmax(z, PLL_ZMIN));
+    __syncthreads();
+    if (threadIdx.x < RK) {
+      const int r = threadIdx.x >> 2, k = threadIdx.x & 3;
+      const double g = -model->eval[k] * model->rates[r];  // t = -lz: d/dlz exp(eval*rate*t) = g * exp(.)
+      const double e = exp(g * sh_lz);
+      tab[0][threadIdx.x] = e; tab[1][threadIdx.x] = g * e; tab[2][threadIdx.x] = g * g * e;
+    }
+    __syncthreads();
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    for (int64_t p = threadIdx.x; p < Ppad; p += SM_THREADS) {
+      const double w = weights[p];
+      if (w == 0.0) continue;
+      double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+      for (int e = 0; e < RK; e++) {
+        const double sv = Sb[(int64_t)e * Ppad + p];
+        l0 = fma(sv, tab[0][e], l0);
+        l1 = fma(sv, tab[1][e], l1);
+        l2 = fma(sv, tab[2][e], l2);
+      }
+      const double inv = 1.0 / l0, q1 = l1 * inv;
+      v0 += w * (log(l0 * 0.25) + sc[p] * SM_LOG_MINLH);
+      v1 += w * q1;
+      v2 += w * (l2 * inv - q1 * q1);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      v0 += __shfl_down_sync(0xffffffffu, v0, d);
+      v1 += __shfl_down_sync(0xffffffffu, v1, d);
+      v2 += __shfl_down_sync(0xffffffffu, v2, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = v0; red[1][threadIdx.x >> 5] = v1; red[2][threadIdx.x >> 5] = v2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      d1 = d2 = 0.0;
+      for (int i = 0; i < SM_THREADS / 32; i++) { d1 += red[1][i]; d2 += red[2][i]; }  // fixed order
+      if (d2 >= 0.0 && z < PLL_ZMAX) { zprev = z = 0.37 * z + 0.63; sh_go = 1; }
+      else sh_go = 0;
+    }
+    __syncthreads();
+    if (!sh_go) break;
+  }
+  if (threadIdx.x == 0) {
+    if (d2 < 0.0) {
+      const double tantmp = -d1 / d2;
+      if (tantmp < 100.0) {
+        z *= exp(tantmp);
+        if (z < PLL_ZMIN) z = PLL_ZMIN;
+        if (z > 0.25 * zprev + 0.75) z = 0.25 * zprev + 0.75;
+      } else {
+        z = 0.25 * zprev + 0.75;
+      }
+    }
+    if (z > PLL_ZMAX) z = PLL_ZMAX;
+    brlen[it.branch] = -log(z);
+    if (fabs(z - z0) > PLL_DELTAZ) changed[it.tree] = 1;
+  }
+}
+
+__global__ void next_pass_kernel(int n, int *__restrict__ active, int *__restrict__ changed) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) { active[t] = active[t] && changed[t]; changed[t] = 0; }  // smoothTree stops once a pass moved nothing
+}
+
+// Per tree: the action lists of the down pass and of one smoothing pass (the same for every pass).
+struct TreePlan {
+  std::vector<LikOpF> down;   // n - 2 updates, leaves first
+  struct Act { int is_opt; LikOpF op; OptItem it; };
+  std::vector<Act> acts;      // (2n - 3) OPT + 3(n - 2) CLV, smooth() order
+  LikEval eval;
+};
+
+static TreePlan plan_tree(const UTree &t, const std::vector<int32_t> &tip_rows, int n_rows, int tree_idx,
+                          int64_t slot0, int64_t branch0) {
+  TreePlan out;
+  const int n = t.n_tips;
+  // branch ids: undirected edges numbered by their first appearance (x, k) with x < nb[x][k]
+  std::vector<int> branch_of((size_t)t.n_nodes * 3, -1);
+  int nb_count = 0;
+  for (int x = 0; x < t.n_nodes; x++)
+    for (int k = 0; k < 3; k++) {
+      const int y = t.nb[x][k];
+      if (y > x) { branch_of[3 * x + k] = nb_count; branch_of[3 * y + t.slot_of(y, x)] = nb_count; nb_count++; }
+    }
+  auto operand = [&](int x) { return x < n ? (int)tip_rows[x] : (int)(n_rows + slot0 + (x - n)); };
+  auto pm = [&](int x, int k) { return (int)(branch0 + branch_of[3 * x + k]); };
+  auto clv_op = [&](int x, int k) {  // x's vector re-oriented toward nb[x][k]
+    LikOpF f;
+    f.dst = operand(x);
+    int s = 0;
+    for (int j = 0; j < 3; j++)
+      if (j != k) {
+        const int c = t.nb[x][j];
+        if (s == 0) { f.a = operand(c); f.pa = pm(x, j); } else { f.b = operand(c); f.pb = pm(x, j); }
+        s++;
+      }
+    f.tree = -1; f.e_pa = f.e_b = f.e_pb = f.e_c = f.e_pc = -1; f.pad = 0;
+    return f;
+  };
+  // down pass toward tip 0
+  std::vector<int> par(t.n_nodes, -1), bfs{0};
+  for (size_t i = 0; i < bfs.size(); i++)
+    for (int k = 0; k < 3; k++) {
+      const int y = t.nb[bfs[i]][k];
+      if (y >= 0 && y != par[bfs[i]]) { par[y] = bfs[i]; bfs.push_back(y); }
+    }
+  for (size_t i = bfs.size(); i-- > 1;)
+    if (!t.is_tip(bfs[i])) out.down.push_back(clv_op(bfs[i], t.slot_of(bfs[i], par[bfs[i]])));
+  // smooth(nb[0][0], 0), iteratively
+  struct Fr { int x, from, state; };
+  std::vector<Fr> st{{t.nb[0][0], 0, 0}};
+  while (!st.empty()) {
+    Fr &f = st.back();
+    const int x = f.x, from = f.from, kf = t.slot_of(x, from);
+    if (f.state == 0) {
+      TreePlan::Act a;
+      a.is_opt = 1;
+      a.it.a_id = operand(x); a.it.b_id = operand(from); a.it.tree = tree_idx; a.it.branch = pm(x, kf);
+      out.acts.push_back(a);
+      if (t.is_tip(x)) { st.pop_back(); continue; }
+      f.state = 1;
+      continue;
+    }
+    if (f.state <= 2) {
+      int seen = 0, j = 0;
+      for (; j < 3; j++)
+        if (j != kf && ++seen == f.state) break;
+      TreePlan::Act a;
+      a.is_opt = 0;
+      a.op = clv_op(x, j);
+      out.acts.push_back(a);
+      f.state++;
+      st.push_back({t.nb[x][j], x, 0});  // (invalidates f)
+      continue;
+    }
+    TreePlan::Act a;
+    a.is_opt = 0;
+    a.op = clv_op(x, kf);
+    out.acts.push_back(a);
+    st.pop_back();
+  }
+  const int w = t.nb[0][0];
+  out.eval.a = tip_rows[0]; out.eval.pa = -1;
+  out.eval.b = operand(w); out.eval.pb = pm(0, 0);
+  out.eval.c = -1; out.eval.pc = -1; out.eval.tree = tree_idx; out.eval.pad = 0;
+  return out;
+}
+
+// lnL and optimised branch lengths (per tree: len[x][k] as in the UTree) of trees [0, n_trees)
+static void pll_loglik_batch_dna4(const LikAln &aln, const Model &model, std::vector<UTree> &trees,
+                                  const std::vector<std::vector<int32_t>> &tip_rows, int passes, double *out_lnl) {
+  const int64_t n_trees = (int64_t)trees.size();
+  if (n_trees == 0) return;
+  const int n = trees[0].n_tips, n_inner = n - 2, n_br = 2 * n - 3;
+  const int64_t Ppad = aln.Ppad;
+  size_t free_b = 0, total_b = 0;
+  PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t per_tree = ((size_t)n_inner * (16 * 8 + 4) + 16 * 8 + 4) * Ppad + (size_t)n_br * (68 + 256) * 8;
+  const int64_t B = std::max<int64_t>(1, std::min<int64_t>(n_trees, (int64_t)(std::min<size_t>(free_b / 2, (size_t)64 << 30) / per_tree)));
+  DevBuf<double> clv, S, pmat, tiptab, brlen, partial, lnl;
+  DevBuf<int> scl, Ssc, idx, flags;
+  DevBuf<LikOpF> d_ops;
+  DevBuf<OptItem> d_items;
+  DevBuf<LikEval> d_evals;
+  clv.alloc((size_t)B * n_inner * 16 * Ppad);
+  scl.alloc((size_t)B * n_inner * Ppad);
+  S.alloc((size_t)B * 16 * Ppad);
+  Ssc.alloc((size_t)B * Ppad);
+  pmat.alloc((size_t)B * n_br * 68);
+  tiptab.alloc((size_t)B * n_br * 256);
+  brlen.alloc((size_t)B * n_br);
+  const int64_t ebpo = Ppad / 128;
+  partial.alloc((size_t)B * std::max<int64_t>(1, ebpo) * 2);
+  lnl.alloc((size_t)B);
+  flags.alloc((size_t)2 * B);
+  d_evals.alloc((size_t)B);
+  const int n_steps = n_br + 3 * n_inner;
+  d_ops.alloc((size_t)B * (n_inner + 3 * n_inner));
+  d_items.alloc((size_t)B * n_br);
+  idx.alloc((size_t)B * n_br);
+  const int bpi = (int)(Ppad / (SM_THREADS / 4));
+  std::vector<LikOpF> h_ops;
+  std::vector<OptItem> h_items;
+  std::vector<int> h_idx, h_flags;
+  std::vector<LikEval> h_evals;
+  std::vector<double> h_brlen, h_lnl;
+  for (int64_t t0 = 0; t0 < n_trees; t0 += B) {
+    const int64_t cnt = std::min(B, n_trees - t0);
+    std::vector<TreePlan> plans(cnt);
+    for (int64_t i = 0; i < cnt; i++)  // (checked here: the pool's workers must not throw)
+      if (trees[t0 + i].n_tips != n) PLG_FAIL(PLG_ERR_ARG, "trees of a batch must have the same number of taxa");
+    HostPool::get().run((int)std::min<int64_t>(HostPool::get().size(), std::max<int64_t>(1, cnt / 8)), [&](int ti, int nt) {
+      for (int64_t i = cnt * ti / nt; i < cnt * (ti + 1) / nt; i++)
+        plans[i] = plan_tree(trees[t0 + i], tip_rows[t0 + i], aln.n_rows, (int)i, i * n_inner, i * n_br);
+    });
+    // step-major layout: down-pass steps first, then the steps of one smoothing pass
+    h_ops.clear(); h_items.clear(); h_idx.clear(); h_evals.clear();
+    std::vector<int64_t> down_off(n_inner + 1, 0), clv_off(n_steps + 1, 0), opt_off(n_steps + 1, 0);
+    for (int j = 0; j < n_inner; j++) {
+      for (int64_t i = 0; i < cnt; i++) h_ops.push_back(plans[i].down[j]);
+      down_off[j + 1] = (int64_t)h_ops.size();
+    }
+    const int64_t pass_ops0 = (int64_t)h_ops.size();
+    for (int s = 0; s < n_steps; s++) {
+      for (int64_t i = 0; i < cnt; i++) {
+        const TreePlan::Act &a = plans[i].acts[s];
+        if (a.is_opt) { h_items.push_back(a.it); h_idx.push_back(a.it.branch); }
+        else h_ops.push_back(a.op);
+      }
+      clv_off[s + 1] = (int64_t)h_ops.size() - pass_ops0;
+      opt_off[s + 1] = (int64_t)h_items.size();
+    }
+    for (int64_t i = 0; i < cnt; i++) h_evals.push_back(plans[i].eval);
+    h_brlen.assign((size_t)cnt * n_br, -std::log(PLL_DEFAULTZ));  // useDefaultz (libpllWrapper.c:152)
+    h_flags.assign((size_t)2 * cnt, 0);
+    for (int64_t i = 0; i < cnt; i++) h_flags[i] = 1;  // active; changed = 0
+    PLG_CUDA(cudaMemcpy(d_ops.p, h_ops.data(), h_ops.size() * sizeof(LikOpF), cudaMemcpyHostToDevice));
+    PLG_CUDA(cudaMemcpy(d_items.p, h_items.data(), h_items.size() * sizeof(OptItem), cudaMemcpyHostToDevice));
+    PLG_CUDA(cudaMemcpy(idx.p, h_idx.data(), h_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    PLG_CUDA(cudaMemcpy(d_evals.p, h_evals.data(), h_evals.size() * sizeof(LikEval), cudaMemcpyHostToDevice));
+    PLG_CUDA(cudaMemcpy(brlen.p, h_brlen.data(), h_brlen.size() * 8, cudaMemcpyHostToDevice));
+    PLG_CUDA(cudaMemcpy(flags.p, h_flags.data(), h_flags.size() * sizeof(int), cudaMemcpyHostToDevice));
+    int *active = flags.p, *changed = flags.p + cnt;
+    cudaStream_t st = 0;
+    dna4_pmatrices(aln, model, brlen.p, nullptr, cnt * n_br, pmat.p, tiptab.p, st);
+    for (int j = 0; j < n_inner; j++)
+      dna4_updates(aln, model, d_ops.p + down_off[j], down_off[j + 1] - down_off[j], pmat.p, tiptab.p, clv.p, scl.p, st);
+    for (int pass = 0; pass < passes; pass++) {
+      for (int s = 0; s < n_steps; s++) {
+        const int64_t nc = clv_off[s + 1] - clv_off[s], no = opt_off[s + 1] - opt_off[s];
+        if (nc) dna4_updates(aln, model, d_ops.p + pass_ops0 + clv_off[s], nc, pmat.p, tiptab.p, clv.p, scl.p, st);
+        if (no) {
+          const OptItem *its = d_items.p + opt_off[s];
+          sumtable4_batch_kernel<<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(its, bpi, aln.n_rows, Ppad, aln.codes.p,
+                                                                               aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p);
+          opt4_batch_kernel<<<(unsigned)no, SM_THREADS, 0, st>>>(its, Ppad, aln.weights.p, model.d.p, S.p, Ssc.p, brlen.p,
+                                                                 active, changed);
+          count_launch(2);
+          dna4_pmatrices(aln, model, brlen.p, idx.p + opt_off[s], no, pmat.p, tiptab.p, st);
+        }
+      }
+      next_pass_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((int)cnt, active, changed);
+      count_launch();
+    }
+    dna4_evals(aln, model, d_evals.p, cnt, pmat.p, tiptab.p, clv.p, scl.p, partial.p, lnl.p, st);
+    PLG_CUDA(cudaGetLastError());
+    h_lnl.resize(cnt);
+    PLG_CUDA(cudaMemcpy(h_lnl.data(), lnl.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
+    PLG_CUDA(cudaMemcpy(h_brlen.data(), brlen.p, (size_t)cnt * n_br * 8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < cnt; i++) {
+      out_lnl[t0 + i] = h_lnl[i];
+      UTree &t = trees[t0 + i];
+      int b = 0;
+      for (int x = 0; x < t.n_nodes; x++)  // same numbering as plan_tree
+        for (int k = 0; k < 3; k++) {
+          const int y = t.nb[x][k];
+          if (y > x) { const double len = h_brlen[(size_t)i * n_br + b++]; t.len[x][k] = len; t.len[y][t.slot_of(y, x)] = len; }
+        }
+    }
+  }
+}
+
 }  // namespace plg
 
 using namespace plg;
@@ -664,5 +1010,83 @@ extern "C" int plg_pll_info(plg_pll *p, int *n_states, int64_t *n_patterns, doub
   if (n_patterns) *n_patterns = p->p.aln->P;
   if (freqs) for (int k = 0; k < p->p.aln->K; k++) freqs[k] = p->p.model->h.freqs[k];
   if (rates) for (int r = 0; r < p->p.model->R; r++) rates[r] = p->p.model->h.rates[r];
+  PLG_API_END
+}
+
+// ---- batched getLogLikelihood ----------------------------------------------------------------
+namespace {
+thread_local std::vector<std::string> g_batch_newicks;  // optimised trees of the last batch on this thread
+}
+
+// lnL of every tree after the reference's per-tree treatment (scoring.getLogLikelihood ->
+// libpllWrapper new / getLogLikelihood / getNewickString / destroy, scoring.py:41-75): default
+// branch lengths z = 0.9, up to `passes` smoothing passes (the reference uses 3), likelihood.
+// DNA x Gamma-4 runs the lockstep batch above; other models fall back to one handle per tree.
+extern "C" int plg_pll_loglik_batch(const char *phylip_path, const char *partition_path, int64_t n_trees,
+                                    const char *const *newicks, int passes, double *out_lnl,
+                                    size_t *newick_bytes) {
+  PLG_API_BEGIN_LOCKED
+  if (!phylip_path || !partition_path || (n_trees > 0 && (!newicks || !out_lnl)))
+    PLG_FAIL(PLG_ERR_ARG, "null argument");
+  if (passes < 0) PLG_FAIL(PLG_ERR_ARG, "negative number of smoothing passes");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+    PLG_FAIL(PLG_ERR_CUDA, "no CUDA device: pylogeny_b200 has no CPU fallback");
+  const std::string model_name = read_partition_model(partition_path);
+  const bool dna = (model_name == "DNA");
+  if (!dna && model_name != "WAG")
+    PLG_FAIL(PLG_ERR_UNSUPPORTED, "protein model '%s': only WAG ships with the engine", model_name.c_str());
+  std::shared_ptr<PllAlignment> al = cached_alignment(phylip_path, model_name, dna);
+  std::vector<UTree> trees(n_trees);
+  std::vector<std::vector<std::string>> names(n_trees);
+  std::vector<std::vector<int32_t>> rows(n_trees);
+  for (int64_t i = 0; i < n_trees; i++) {
+    if (!newicks[i]) PLG_FAIL(PLG_ERR_ARG, "tree %lld is NULL", (long long)i);
+    HostTree ht = parse_newick(newicks[i]);
+    trees[i] = utree_from_newick(ht, names[i]);
+    if ((size_t)trees[i].n_tips != al->names.size())
+      PLG_FAIL(PLG_ERR_IO, "Could not find correct correspondances.");  // libpllWrapper.c:153-156
+    for (auto &nm : names[i]) {
+      auto it = al->row_of.find(nm);
+      if (it == al->row_of.end()) PLG_FAIL(PLG_ERR_IO, "Could not find correct correspondances.");
+      rows[i].push_back(it->second);
+    }
+    for (auto &l : trees[i].len) for (auto &x : l) x = -std::log(PLL_DEFAULTZ);
+  }
+  g_batch_newicks.assign(n_trees, std::string());
+  if (al->aln->K == 4 && al->model->R == 4) {
+    pll_loglik_batch_dna4(*al->aln, *al->model, trees, rows, passes, out_lnl);
+    PllProblem writer;  // (only its Newick writer is used)
+    for (int64_t i = 0; i < n_trees; i++) {
+      writer.tip_names = names[i];
+      g_batch_newicks[i] = writer.newick_of(trees[i]);
+    }
+  } else {
+    for (int64_t i = 0; i < n_trees; i++) {
+      PllProblem pr;
+      pr.tree = trees[i]; pr.tip_names = names[i]; pr.tip_rows = rows[i];
+      pr.aln = al->aln; pr.model = al->model;
+      out_lnl[i] = pr.loglik(passes);
+      g_batch_newicks[i] = pr.newick();
+    }
+  }
+  if (newick_bytes) {
+    size_t b = 0;
+    for (auto &s : g_batch_newicks) b += s.size() + 1;
+    *newick_bytes = b;
+  }
+  PLG_API_END
+}
+
+// The optimised trees of the last plg_pll_loglik_batch on this thread, NUL-separated, in input order.
+extern "C" int plg_pll_batch_newicks(char *buf, size_t bytes) {
+  PLG_API_BEGIN
+  if (!buf) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  size_t at = 0;
+  for (auto &s : g_batch_newicks) {
+    if (at + s.size() + 1 > bytes) PLG_FAIL(PLG_ERR_ARG, "buffer too small for the Newick strings");
+    memcpy(buf + at, s.c_str(), s.size() + 1);
+    at += s.size() + 1;
+  }
   PLG_API_END
 }

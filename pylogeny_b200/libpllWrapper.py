@@ -76,6 +76,27 @@ def getLogLikelihood(handle):
     return out.value
 
 
+def getLogLikelihoodBatch(alignf, newicks, partf, passes=3):
+    """Extension: what new() + getLogLikelihood() + getNewickString() + destroy() give for every
+    tree of `newicks` (default branch lengths, `passes` smoothing passes, likelihood), all trees
+    advancing in lockstep on the device.  Returns (list of lnL, list of optimised Newick strings)."""
+    import numpy as np
+    L = _lib.lib()
+    n = len(newicks)
+    arr = (C.c_char_p * max(n, 1))(*[s.encode() for s in newicks])
+    lnl = np.zeros(n, dtype=np.float64)
+    nbytes = C.c_size_t(0)
+    rc = L.plg_pll_loglik_batch(alignf.encode(), partf.encode(), n, arr, int(passes), lnl.ctypes.data, C.byref(nbytes))
+    if rc:
+        _raise(rc)
+    buf = C.create_string_buffer(max(1, nbytes.value))
+    rc = L.plg_pll_batch_newicks(buf, nbytes.value)
+    if rc:
+        _raise(rc)
+    out = buf.raw[:nbytes.value].split(b"\0")[:n]
+    return lnl.tolist(), [b.decode() for b in out]
+
+
 def evaluate(handle):
     """lnL at the current branch lengths, no optimisation (extension; pllEvaluateLikelihood)."""
     out = C.c_double()

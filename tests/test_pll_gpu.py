@@ -205,3 +205,49 @@ def test_alignment_cache_is_keyed_by_file_identity(tmp_path):
         del os.environ["PLG_PLL_ALN_CACHE"]
     W.destroy(h2); W.destroy(h3)
     pm.close(); ali.close()
+
+
+def test_batched_getLogLikelihood_equals_per_tree_path():
+    """plg_pll_loglik_batch (all trees smoothed in lockstep on the device) against one handle per
+    tree: same lnL and branch lengths up to the summation order of the derivative sums, and the
+    returned lnL equals the oracle's at the returned branch lengths (1e-8)."""
+    from pylogeny_b200 import _lib, libpllWrapper as W, likelihood, neighbourhood as nbh, pll
+    ali, d = _case(n=14, S=1200, seed=5)
+    labels = ali.getTaxa()
+    taxa = {l: i for i, l in enumerate(labels)}
+    rng = np.random.default_rng(8)
+    descs = [d] + [random_desc(rng, len(labels)) for _ in range(11)] + [d]
+    newicks = [desc_to_newick(x, labels) for x in descs]
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    per_tree, per_nw = [], []
+    for nw in newicks:
+        h = W.new(ali.getPhylip(), nw, pm.getFileName())
+        per_tree.append(W.getLogLikelihood(h))
+        per_nw.append(W.getNewickString(h))
+        W.destroy(h)
+    lnl, opt = W.getLogLikelihoodBatch(ali.getPhylip(), newicks, pm.getFileName())
+    assert len(lnl) == len(opt) == len(newicks)
+    np.testing.assert_allclose(lnl, per_tree, rtol=1e-9)
+    assert lnl[0] == lnl[-1]                                    # the same tree twice in one batch
+    codes = likelihood.encode_sequences(ali.toStrList(), _lib.DATA_DNA)
+    h = W.new(ali.getPhylip(), newicks[0], pm.getFileName())
+    K, P = C.c_int(), C.c_int64()
+    freqs, rates = np.zeros(4), np.zeros(4)
+    dp = C.POINTER(C.c_double)
+    _lib.check(_lib.lib().plg_pll_info(h.ptr, C.byref(K), C.byref(P), freqs.ctypes.data_as(dp), rates.ctypes.data_as(dp)))
+    W.destroy(h)
+    w = np.ones(ali.getSize())
+    for i in (0, 3, 7):
+        want = _oracle_at(opt[i], taxa, codes, w, np.ones(6), freqs, 1.0)
+        assert abs(lnl[i] - want) <= 1e-8 * abs(want)
+        _, b_batch, _, _ = nbh.newick_to_desc(opt[i], taxa)
+        _, b_tree, _, _ = nbh.newick_to_desc(per_nw[i], taxa)
+        np.testing.assert_allclose(b_batch, b_tree, rtol=1e-6, atol=1e-9)
+    one, _ = W.getLogLikelihoodBatch(ali.getPhylip(), newicks[:1], pm.getFileName(), passes=0)
+    h = W.new(ali.getPhylip(), newicks[0], pm.getFileName())
+    assert abs(one[0] - W.evaluate(h)) <= 1e-10 * abs(one[0])   # no smoothing: lnL at z = 0.9
+    W.destroy(h)
+    with pytest.raises(IOError):
+        W.getLogLikelihoodBatch(ali.getPhylip(), ["(a,b,c);"], pm.getFileName())
+    pm.close(); ali.close()
