@@ -380,6 +380,7 @@ def run_ours(args):
         out["parsimony"] = parsimony_leg(fitch, nbh, L, peak, peak_src, not args.no_cpu)
         out["streaming"] = streaming_leg(fitch, likelihood, L, peak, peak_src)
         out["target_shape_lnl"] = target_lnl_leg(likelihood, nbh, L, peak, peak_src)
+        out["smoothed_lnl"] = smoothed_lnl_leg(nbh)
     emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -472,6 +473,44 @@ def target_lnl_leg(likelihood, nbh, L, peak, peak_src):
                          "frac": ach / peak, "requested_gbs": rq.value / (kms.value * 1e-3) / 1e9,
                          "launches": nl.value, "avg_launch_ms": kms.value / max(nl.value, 1), "peak_source": peak_src,
                          "fp64_tflops": un.value * 640.0 / (kms.value * 1e-3) / 1e12}}
+
+
+def smoothed_lnl_leg(nbh, T=1024):
+    """What scoring.getLogLikelihood returns per tree in the reference (libpllWrapper.c:152, :205:
+    default branch lengths, 3 smoothing passes, lnL) for the first T SPR neighbours of the bench
+    tree, through plg_pll_loglik_batch (all trees in lockstep on the device) and, on 8 of them,
+    through one handle per tree as the reference does it."""
+    import torch
+    from pylogeny_b200 import alignment, libpllWrapper as W, pll
+    codes, _ = make_alignment()
+    letters = np.array(list("?AC?G???T"))
+    seqs = ["".join(letters[row]) for row in codes]
+    ali = alignment.phylipFriendlyAlignment(names=["T%d" % i for i in range(N_TAXA)], seqs=seqs)
+    labels = ali.getTaxa()
+    d, _ = make_tree(SEED)
+    descs, _, _ = nbh.neighbour_trees(d, None, np.arange(T, dtype=np.int64))
+    newicks = [nbh.desc_to_newick(x, labels) for x in descs]
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    W.getLogLikelihoodBatch(ali.getPhylip(), newicks[:8], pm.getFileName())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lnl, _ = W.getLogLikelihoodBatch(ali.getPhylip(), newicks, pm.getFileName())
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref = []
+    for nw in newicks[:8]:
+        h = W.new(ali.getPhylip(), nw, pm.getFileName())
+        ref.append(W.getLogLikelihood(h))
+        W.destroy(h)
+    dt1 = (time.perf_counter() - t0) / 8
+    pm.close()
+    ali.close()
+    return {"workload": "GTR+G4 lnL after 3 branch-length smoothing passes from z = 0.9 (scoring.getLogLikelihood "
+                        "semantics) of the first %d SPR neighbours, 64 taxa x 10k sites" % T,
+            "value": T * N_SITES / dt, "unit": UNIT, "ms_per_tree": 1e3 * dt / T,
+            "per_tree_handle_ms": 1e3 * dt1,
+            "max_rel_diff_vs_per_tree": float(np.max(np.abs((np.array(ref) - np.array(lnl[:8])) / np.array(ref))))}
 
 
 def streaming_leg(fitch, likelihood, L, peak, peak_src):
