@@ -15,6 +15,9 @@ Tie rule: neighbours are inserted in the engine's enumeration order (pruned bran
 then depth-first by target), so among equal scores `sorted(...)[0]` (heuristic.py:92-95) may pick
 a different tree than the reference's enumeration order would.
 
+Likelihood: `scoreLikelihoodFor(indices)` scores many nodes in one engine call (batched branch-length
+smoothing); with `batch_likelihood = True` every explored neighbourhood is scored that way.
+
 Falls back to the reference method when locks are set (rearrangement.py:228-240 semantics are not
 reproduced here) or for move types the engine does not enumerate.
 """
@@ -78,4 +81,19 @@ class BatchedExploreMixin(object):
             self.graph.add_edge(i, k)
             self.getEdge(i, k)['weight'] = self.defaultWeight
         node['explored'] = True
+        if getattr(self, "batch_likelihood", False):
+            self.scoreLikelihoodFor(neighbors)
         return neighbors
+
+    def scoreLikelihoodFor(self, indices):
+        """`vertex.scoreLikelihood()` (landscape.py:1302-1314) for many nodes in ONE engine call:
+        every tree without a likelihood gets the reference's per-tree treatment (3 smoothing passes
+        from default branch lengths, lnL, Newick updated) through scoring.getLogLikelihoodBatch.
+        likelihoodGreedy / smoothGreedy (heuristic.py:107-260) then find the scores in place.  Set
+        `batch_likelihood = True` on the landscape to do this for every explored neighbourhood."""
+        nodes = [self.getNode(i) for i in indices]
+        todo = [nd for nd in nodes if nd['tree'].score[0] is None]
+        scores = scoring.getLogLikelihoodBatch([nd['tree'] for nd in todo], self.alignment)
+        for nd, sc in zip(todo, scores):
+            nd['tree'].score = (sc, nd['tree'].score[1])
+        return [nd['tree'].score[0] for nd in nodes]
