@@ -68,15 +68,50 @@ def make_tree(seed, n=N_TAXA):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML thread
+    (pynvml) when available: an `nvidia-smi -lms` child process perturbed the timed steps by up to
+    a millisecond per sample (it takes the driver lock for tens of fields); the NVML calls used here
+    are two cheap queries per sample.  Falls back to nvidia-smi."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index):
-        self.gpu, self.proc, self.path = gpu_index, None, None
+    def __init__(self, gpu_index, uuid=None):
+        self.gpu, self.uuid, self.proc, self.path = gpu_index, uuid, None, None
+        self.thread, self.stop_flag, self.samples, self.max_mhz, self.mask = None, False, [], None, 0
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode())
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
 
     def start(self):
+        try:
+            import threading
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        self.mask |= int(reasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.01)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -87,6 +122,12 @@ class ClockSampler(object):
             self.proc = None
 
     def stop(self):
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join()
+            return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(name for bit, name in self.REASONS if self.mask & bit),
+                    "samples": len(self.samples), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -107,7 +148,14 @@ class ClockSampler(object):
                     reasons.add(name)
         os.unlink(self.path)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
 _JSON_OUT = None
@@ -128,13 +176,6 @@ def emit(line):
     out = _JSON_OUT or sys.stdout
     out.write(line + "\n")
     out.flush()
-
-
-def measured_peaks():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
 def ncu_traffic(kernel, units_per_launch):
@@ -279,7 +320,11 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local)
+    try:
+        uuid = torch.cuda.get_device_properties(local).uuid
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     if rank == 0:
         sampler.start()
     L.plg_profile_enable(1)

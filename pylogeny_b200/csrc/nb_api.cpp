@@ -349,12 +349,13 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
   if (out_lnl && depth < 0 && shard_count == 1 && shard_index == 0 && n_tips >= 4 &&
       n_tips <= (1 << WALK_MAX_LEVELS) && a.K == 4 && m->impl.R == 4 && lik_nb_mode() == LIK_NB_WALK &&
       !(plan_env && !strcmp(plan_env, "host"))) {
-    size_t free_b = 0, total_b = 0;
-    PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t slot_bytes = ((size_t)m->impl.R * a.K * 8 + 4) * a.Ppad;
     const size_t held = lik_workspace().clv.n * 8 + lik_workspace().scl.n * 4;
+    const size_t need = (size_t)3 * (n_tips - 2) * slot_bytes;
+    size_t free_b = 0, total_b = 0;
+    if (need > held) PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));  // (a driver call: skipped once the pool is big enough)
     tm.lap("meminfo");
-    if ((size_t)3 * (n_tips - 2) * slot_bytes <= std::min<size_t>((free_b + held) / 2, (size_t)80 << 30)) {
+    if (need <= held || need <= std::min<size_t>((free_b + held) / 2, (size_t)80 << 30)) {
       static thread_local LikProgram p;
       build_lik_spr_device_plan(utree_from_desc(n_tips, desc, brlen), tip_rows, a.n_rows, p);
       tm.lap("prepare");
