@@ -21,6 +21,59 @@ def test_c1_greedy_climb_al_fasta(al_profiles, al_fitch, al_greedy):
     a.close()
 
 
+def test_c2_full_size_lnl_spr_neighbourhood():
+    """C2: 64 taxa x 10k sites, GTR+G4 lnL of all 14,762 SPR neighbours.  Size-independent
+    properties at full size: (i) a sample of neighbours equals the full re-traversal of the
+    materialised tree and the FP64 oracle (1e-8); (ii) lnL is linear in the pattern weights --
+    doubling them doubles every lnL exactly, splitting them splits it; (iii) relabelling the tips
+    (another descriptor of the same tree on the same taxa) gives the same lnL per topology hash."""
+    from pylogeny_b200 import likelihood, neighbourhood as nbh
+    from util import simulate_dna
+    rng = np.random.default_rng(1001)
+    n, S = 64, 10_000
+    exch, freqs, alpha = np.array([1.2, 3.4, 0.8, 1.1, 4.1, 1.0]), np.array([0.28, 0.22, 0.24, 0.26]), 0.7
+    hidden = random_desc(rng, n)
+    seqs = simulate_dna(rng, hidden, rng.exponential(0.05, hidden.shape) + 0.005, S, exch, freqs)
+    codes = np.array([[{"A": 1, "C": 2, "G": 4, "T": 8}[c] for c in s] for s in seqs], dtype=np.uint8)
+    holes = rng.random(codes.shape)
+    codes[holes < 0.01] = 15                     # gaps
+    codes[(holes >= 0.01) & (holes < 0.015)] = 5  # R = A or G
+    w = rng.integers(1, 4, S).astype(np.float64)
+    d = random_desc(rng, n)
+    br = rng.exponential(0.1, d.shape)
+    a = likelihood.LikAlignment(codes, w)
+    m = likelihood.Model(exch, freqs, alpha)
+    moves, lnl = nbh.score_likelihood(a, m, d, br)
+    M = 2 * (n - 3) * (2 * n - 7)
+    assert len(lnl) == M == 14762 and np.all(np.isfinite(lnl)) and np.all(lnl < 0)
+    sel = np.linspace(0, M - 1, 40).astype(np.int64)
+    descs, brs, hashes = nbh.neighbour_trees(d, br, sel)
+    np.testing.assert_allclose(lnl[sel], a.score_trees(m, descs, brs), rtol=1e-11)
+    for i in (0, 13, 39):
+        want = oracle.lnl(codes, w, exch, freqs, alpha, descs[i], brs[i])
+        assert abs(lnl[sel[i]] - want) <= 1e-8 * abs(want)   # north_star tolerance
+    a2 = likelihood.LikAlignment(codes, 2.0 * w)
+    assert nbh.score_likelihood(a2, m, d, br, want_moves=False)[1].tolist() == (2.0 * lnl).tolist()
+    wa = np.where(rng.random(S) < 0.5, w, 0.0)
+    a3, a4 = likelihood.LikAlignment(codes, wa), likelihood.LikAlignment(codes, w - wa)
+    parts = nbh.score_likelihood(a3, m, d, br, want_moves=False)[1] + nbh.score_likelihood(a4, m, d, br, want_moves=False)[1]
+    np.testing.assert_allclose(parts, lnl, rtol=1e-12)
+    # the same tree with its tips renumbered: descriptor ids permuted, tip_rows maps them back
+    sigma = rng.permutation(n)
+    d2 = np.where(d < n, sigma[np.minimum(d, n - 1)], d).astype(np.int32)
+    rows2 = np.empty(n, dtype=np.int32)
+    rows2[sigma] = np.arange(n, dtype=np.int32)
+    _, lnl2 = nbh.score_likelihood(a, m, d2, br, rows2)
+    _, _, h1 = nbh.neighbour_trees(d, br)
+    _, _, h2 = nbh.neighbour_trees(d2, br, tip_rows=rows2)
+    assert len(set(h1.tolist())) == M and set(h1.tolist()) == set(h2.tolist())
+    by_hash = dict(zip(h1.tolist(), lnl.tolist()))
+    np.testing.assert_allclose(lnl2, [by_hash[h] for h in h2.tolist()], rtol=1e-11)
+    for x in (a, a2, a3, a4):
+        x.close()
+    m.close()
+
+
 def test_c3_greedy_climb_full_size():
     """C3: 256 taxa x 100k sites, parsimonyGreedy over the SPR landscape.  Size-independent
     properties: the path is strictly decreasing, every accepted score equals a from-scratch
