@@ -673,7 +673,8 @@ static void pll_loglik_batch_dna4(const LikAln &aln, const Model &model, std::ve
   size_t free_b = 0, total_b = 0;
   PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t per_tree = ((size_t)n_inner * (16 * 8 + 4) + 16 * 8 + 4) * Ppad + (size_t)n_br * (68 + 256) * 8;
-  const int64_t B = std::max<int64_t>(1, std::min<int64_t>(n_trees, (int64_t)(std::min<size_t>(free_b / 2, (size_t)64 << 30) / per_tree)));
+  int64_t B = std::max<int64_t>(1, std::min<int64_t>(n_trees, (int64_t)(std::min<size_t>(free_b / 2, (size_t)64 << 30) / per_tree)));
+  if (const char *e = getenv("PLG_PLL_BATCH_CHUNK")) B = std::max<int64_t>(1, std::min<int64_t>(B, atoll(e)));  // tests: several chunks
   DevBuf<double> clv, S, pmat, tiptab, brlen, partial, lnl;
   DevBuf<int> scl, Ssc, idx, flags;
   DevBuf<LikOpF> d_ops;

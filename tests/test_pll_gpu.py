@@ -251,3 +251,38 @@ def test_batched_getLogLikelihood_equals_per_tree_path():
     with pytest.raises(IOError):
         W.getLogLikelihoodBatch(ali.getPhylip(), ["(a,b,c);"], pm.getFileName())
     pm.close(); ali.close()
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 9])
+def test_batched_getLogLikelihood_small_trees_and_chunks(n, monkeypatch):
+    """Smallest trees (one inner node at n = 3), a trifurcating input Newick, and a batch cut into
+    several device chunks: same answers as one handle per tree."""
+    from pylogeny_b200 import libpllWrapper as W, pll
+    ali, d = _case(n=max(n, 4), S=400, seed=20 + n)
+    if n == 3:
+        from pylogeny_b200 import alignment
+        seqs = ali.toStrList()[:3]
+        ali.close()
+        ali = alignment.phylipFriendlyAlignment(names=["tax%d" % i for i in range(3)], seqs=seqs)
+    labels = ali.getTaxa()
+    rng = np.random.default_rng(n)
+    if n == 3:
+        newicks = ["(%s,%s,%s);" % tuple(labels), "((%s,%s),%s);" % (labels[2], labels[0], labels[1])]
+    else:
+        newicks = [desc_to_newick(random_desc(rng, n), labels) for _ in range(11)]
+        newicks.append("(%s,%s,(%s));" % (labels[0], labels[1], ",".join(labels[2:])) if n == 4 else newicks[0])
+        if n == 4:
+            newicks[-1] = "(%s,%s,(%s,%s));" % tuple(labels)   # trifurcating root, as toUnrootedNewick writes
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    want = []
+    for nw in newicks:
+        h = W.new(ali.getPhylip(), nw, pm.getFileName())
+        want.append(W.getLogLikelihood(h))
+        W.destroy(h)
+    monkeypatch.setenv("PLG_PLL_BATCH_CHUNK", "5")
+    got, opt = W.getLogLikelihoodBatch(ali.getPhylip(), newicks, pm.getFileName())
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    assert len(opt) == len(newicks) and all(s.endswith(";") for s in opt)
+    assert W.getLogLikelihoodBatch(ali.getPhylip(), [], pm.getFileName()) == ([], [])
+    pm.close(); ali.close()
