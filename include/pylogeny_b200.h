@@ -187,8 +187,8 @@ int plg_pll_loglik(plg_pll *p, double *out);
 int plg_pll_evaluate(plg_pll *p, double *out);
 /* Batched scoring.getLogLikelihood (scoring.py:41-75: new / getLogLikelihood / getNewickString /
  * destroy per tree): every tree starts at z = 0.9, gets up to `passes` smoothing passes (the
- * reference: 3) and its lnL.  Trees must hold the alignment's taxa.  DNA runs all trees in lockstep
- * on the device; *newick_bytes = room needed by plg_pll_batch_newicks, which copies the optimised
+ * reference: 3) and its lnL.  Trees must hold the alignment's taxa.  DNA and WAG (4 Gamma categories)
+ * run all trees in lockstep on the device; *newick_bytes = room needed by plg_pll_batch_newicks, which copies the optimised
  * trees of the calling thread's last batch, NUL-separated, in input order. */
 int plg_pll_loglik_batch(const char *phylip_path, const char *partition_path, int64_t n_trees,
                          const char *const *newicks, int passes, double *out_lnl,

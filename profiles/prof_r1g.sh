@@ -18,5 +18,5 @@ ncu --set full --clock-control none --import-source on -k regex:eval20_rows -s 1
 tail -n 2 gpurun_out/ncug1.log gpurun_out/ncug2.log gpurun_out/ncug3.log gpurun_out/ncug4.log gpurun_out/ncug5.log | cut -c1-300
 CMD3="python profiles/t_pll_batch.py"
 $CMD3 > gpurun_out/plaing6.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:opt4_batch -s 200 -c 1 -o gpurun_out/prof_opt4_batch_g $CMD3 > gpurun_out/ncug6.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:opt_batch -s 200 -c 1 -o gpurun_out/prof_opt4_batch_g $CMD3 > gpurun_out/ncug6.log 2>&1
 tail -n 2 gpurun_out/ncug6.log | cut -c1-300

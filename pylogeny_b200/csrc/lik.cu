@@ -1018,6 +1018,39 @@ void dna4_evals(const LikAln &a, const Model &m, const LikEval *d_evals, int64_t
   count_launch();
 }
 
+void aa20_pmatrices(const LikAln &a, const Model &m, const double *d_brlen, const int *d_idx, int64_t n,
+                    double *d_pmat, double *d_tiptab, cudaStream_t st) {
+  if (n <= 0) return;
+  prof_begin(PROF_PMATRIX, st);
+  pmatrix_kernel<20, 4><<<(unsigned)n, 128, 0, st>>>(m.d.p, d_brlen, a.masks.p, d_pmat, d_tiptab, d_idx);
+  count_launch();
+  prof_end(PROF_PMATRIX, st, (double)n * (4 * 401 + 23 * 80) * 8.0, (double)n);
+}
+
+void aa20_updates(const LikAln &a, const Model &m, const LikOp *d_ops, int64_t n, const double *d_pmat,
+                  double *d_clv, int *d_scl, cudaStream_t st) {
+  if (n <= 0) return;
+  const int64_t bpo = a.Ppad / A20_TILE;
+  prof_begin(PROF_CLV_UPDATE, st);
+  clv20_kernel<<<(unsigned)(n * bpo), A20_THREADS, 0, st>>>(d_ops, (int)bpo, a.n_rows, a.Ppad, a.codes.p, a.masks.p,
+                                                           d_pmat, d_clv, d_scl);
+  count_launch();
+  prof_end(PROF_CLV_UPDATE, st, (double)n * 3.0 * 644.0 * (double)a.P, (double)n * (double)a.P);
+}
+
+void aa20_evals(const LikAln &a, const Model &m, const LikEval *d_evals, int64_t n, const double *d_pmat,
+                const double *d_clv, const int *d_scl, double *d_partial, double *d_lnl, cudaStream_t st) {
+  if (n <= 0) return;
+  const int64_t bpo = a.Ppad / A20_TILE;
+  prof_begin(PROF_ROOT_EVAL, st);
+  eval20_kernel<<<(unsigned)(n * bpo), A20_THREADS, 0, st>>>(d_evals, (int)bpo, a.n_rows, a.Ppad, a.codes.p, a.masks.p,
+                                                            a.weights.p, m.d.p, d_pmat, d_clv, d_scl, d_partial);
+  count_launch();
+  prof_end(PROF_ROOT_EVAL, st, (double)n * (2.0 * 644.0 + 8.0) * (double)a.P, (double)n * (double)a.P);
+  reduce_partials_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>((int)n, (int)bpo, d_partial, d_lnl);
+  count_launch();
+}
+
 void score_lik_batch_full(LikAln &a, const Model &m, const TreeBatch &b, double *out_lnl, cudaStream_t st) {
   const int64_t n_trees = b.n_trees();
   if (n_trees == 0) return;

@@ -133,6 +133,14 @@ void dna4_updates(const LikAln &a, const Model &m, const LikOpF *d_ops, int64_t 
 void dna4_evals(const LikAln &a, const Model &m, const LikEval *d_evals, int64_t n, const double *d_pmat,
                 const double *d_tiptab, const double *d_clv, const int *d_scl, double *d_partial, double *d_lnl,
                 cudaStream_t st);
+// the same for 20 states x Gamma-4 (lik_aa.cuh); P-matrix stride 4 * 401, tip table 23 * 80 per entry,
+// partial: >= n * Ppad / 64 doubles
+void aa20_pmatrices(const LikAln &a, const Model &m, const double *d_brlen, const int *d_idx, int64_t n,
+                    double *d_pmat, double *d_tiptab, cudaStream_t st);
+void aa20_updates(const LikAln &a, const Model &m, const LikOp *d_ops, int64_t n, const double *d_pmat,
+                  double *d_clv, int *d_scl, cudaStream_t st);
+void aa20_evals(const LikAln &a, const Model &m, const LikEval *d_evals, int64_t n, const double *d_pmat,
+                const double *d_clv, const int *d_scl, double *d_partial, double *d_lnl, cudaStream_t st);
 
 }  // namespace plg
 

@@ -450,12 +450,12 @@ struct OptItem {
   int a_id, b_id, tree, branch;  // operand ids of the branch's two ends; tree of the chunk; global branch index
 };
 
+template <int K, int R>
 __global__ void __launch_bounds__(SM_THREADS)
-sumtable4_batch_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
-                       const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
-                       const ModelDev *__restrict__ model, const double *__restrict__ clv,
-                       const int *__restrict__ scl, double *__restrict__ S, int *__restrict__ Ssc) {
-  constexpr int K = 4, R = 4;
+sumtable_batch_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
+                      const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
+                      const ModelDev *__restrict__ model, const double *__restrict__ clv,
+                      const int *__restrict__ scl, double *__restrict__ S, int *__restrict__ Ssc) {
   const int item = blockIdx.x / blocks_per_item;
   const OptItem it = items[item];
   const int r = threadIdx.x % R;
@@ -492,11 +492,12 @@ sumtable4_batch_kernel(const OptItem *__restrict__ items, int blocks_per_item, i
 }
 
 // One makenewz step (optimise_branch with maxiter = 1) per block, on the tree's sum table.
+template <int K, int R>
 __global__ void __launch_bounds__(SM_THREADS)
-opt4_batch_kernel(const OptItem *__restrict__ items, int64_t Ppad, const double *__restrict__ weights,
-                  const ModelDev *__restrict__ model, const double *__restrict__ S, const int *__restrict__ Ssc,
-                  double *__restrict__ brlen, const int *__restrict__ active, int *__restrict__ changed) {
-  constexpr int RK = 16;
+opt_batch_kernel(const OptItem *__restrict__ items, int64_t Ppad, const double *__restrict__ weights,
+                 const ModelDev *__restrict__ model, const double *__restrict__ S, const int *__restrict__ Ssc,
+                 double *__restrict__ brlen, const int *__restrict__ active, int *__restrict__ changed) {
+  constexpr int RK = R * K;
   const OptItem it = items[blockIdx.x];
   if (!active[it.tree]) return;
   __shared__ double tab[3][RK];
@@ -515,7 +516,7 @@ opt4_batch_kernel(const OptItem *__restrict__ items, int64_t Ppad, const double 
     if (threadIdx.x == 0) sh_lz = log(fmax(z, PLL_ZMIN));
     __syncthreads();
     if (threadIdx.x < RK) {
-      const int r = threadIdx.x >> 2, k = threadIdx.x & 3;
+      const int r = threadIdx.x / K, k = threadIdx.x % K;
       const double g = -model->eval[k] * model->rates[r];  // t = -lz: d/dlz exp(eval*rate*t) = g * exp(.)
       const double e = exp(g * sh_lz);
       tab[0][threadIdx.x] = e; tab[1][threadIdx.x] = g * e; tab[2][threadIdx.x] = g * g * e;
@@ -534,7 +535,7 @@ opt4_batch_kernel(const OptItem *__restrict__ items, int64_t Ppad, const double 
         l2 = fma(sv, tab[2][e], l2);
       }
       const double inv = 1.0 / l0, q1 = l1 * inv;
-      v0 += w * (log(l0 * 0.25) + sc[p] * SM_LOG_MINLH);
+      v0 += w * (log(l0 * (1.0 / R)) + sc[p] * SM_LOG_MINLH);
       v1 += w * q1;
       v2 += w * (l2 * inv - q1 * q1);
     }
@@ -581,8 +582,8 @@ __global__ void next_pass_kernel(int n, int *__restrict__ active, int *__restric
 
 // Per tree: the action lists of the down pass and of one smoothing pass (the same for every pass).
 struct TreePlan {
-  std::vector<LikOpF> down;   // n - 2 updates, leaves first
-  struct Act { int is_opt; LikOpF op; OptItem it; };
+  std::vector<LikOp> down;    // n - 2 updates, leaves first
+  struct Act { int is_opt; LikOp op; OptItem it; };
   std::vector<Act> acts;      // (2n - 3) OPT + 3(n - 2) CLV, smooth() order
   LikEval eval;
 };
@@ -602,7 +603,7 @@ static TreePlan plan_tree(const UTree &t, const std::vector<int32_t> &tip_rows, 
   auto operand = [&](int x) { return x < n ? (int)tip_rows[x] : (int)(n_rows + slot0 + (x - n)); };
   auto pm = [&](int x, int k) { return (int)(branch0 + branch_of[3 * x + k]); };
   auto clv_op = [&](int x, int k) {  // x's vector re-oriented toward nb[x][k]
-    LikOpF f;
+    LikOp f;
     f.dst = operand(x);
     int s = 0;
     for (int j = 0; j < 3; j++)
@@ -611,7 +612,6 @@ static TreePlan plan_tree(const UTree &t, const std::vector<int32_t> &tip_rows, 
         if (s == 0) { f.a = operand(c); f.pa = pm(x, j); } else { f.b = operand(c); f.pb = pm(x, j); }
         s++;
       }
-    f.tree = -1; f.e_pa = f.e_b = f.e_pb = f.e_c = f.e_pc = -1; f.pad = 0;
     return f;
   };
   // down pass toward tip 0
@@ -664,30 +664,66 @@ static TreePlan plan_tree(const UTree &t, const std::vector<int32_t> &tip_rows, 
 }
 
 // lnL and optimised branch lengths (per tree: len[x][k] as in the UTree) of trees [0, n_trees)
-static void pll_loglik_batch_dna4(const LikAln &aln, const Model &model, std::vector<UTree> &trees,
-                                  const std::vector<std::vector<int32_t>> &tip_rows, int passes, double *out_lnl) {
+// the two model families with batch kernels: how their level kernels are launched and laid out
+struct Dna4Family {
+  static constexpr int K = 4, R = 4, PM_STRIDE = 68, TIP_STRIDE = 256, EVAL_TILE = 128;
+  using Op = LikOpF;
+  static Op make(const LikOp &o) {
+    Op f;
+    f.dst = o.dst; f.a = o.a; f.b = o.b; f.pa = o.pa; f.pb = o.pb;
+    f.tree = -1; f.e_pa = f.e_b = f.e_pb = f.e_c = f.e_pc = -1; f.pad = 0;
+    return f;
+  }
+  static void pmatrices(const LikAln &a, const Model &m, const double *bl, const int *idx, int64_t n, double *pm, double *tt,
+                        cudaStream_t st) { dna4_pmatrices(a, m, bl, idx, n, pm, tt, st); }
+  static void updates(const LikAln &a, const Model &m, const Op *ops, int64_t n, const double *pm, const double *tt,
+                      double *clv, int *scl, cudaStream_t st) { dna4_updates(a, m, ops, n, pm, tt, clv, scl, st); }
+  static void evals(const LikAln &a, const Model &m, const LikEval *ev, int64_t n, const double *pm, const double *tt,
+                    const double *clv, const int *scl, double *partial, double *lnl, cudaStream_t st) {
+    dna4_evals(a, m, ev, n, pm, tt, clv, scl, partial, lnl, st);
+  }
+};
+struct Aa20Family {
+  static constexpr int K = 20, R = 4, PM_STRIDE = 4 * 401, TIP_STRIDE = 23 * 80, EVAL_TILE = 64;
+  using Op = LikOp;
+  static Op make(const LikOp &o) { return o; }
+  static void pmatrices(const LikAln &a, const Model &m, const double *bl, const int *idx, int64_t n, double *pm, double *tt,
+                        cudaStream_t st) { aa20_pmatrices(a, m, bl, idx, n, pm, tt, st); }
+  static void updates(const LikAln &a, const Model &m, const Op *ops, int64_t n, const double *pm, const double *,
+                      double *clv, int *scl, cudaStream_t st) { aa20_updates(a, m, ops, n, pm, clv, scl, st); }
+  static void evals(const LikAln &a, const Model &m, const LikEval *ev, int64_t n, const double *pm, const double *,
+                    const double *clv, const int *scl, double *partial, double *lnl, cudaStream_t st) {
+    aa20_evals(a, m, ev, n, pm, clv, scl, partial, lnl, st);
+  }
+};
+
+template <typename F>
+static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<UTree> &trees,
+                             const std::vector<std::vector<int32_t>> &tip_rows, int passes, double *out_lnl) {
+  constexpr int K = F::K, R = F::R, RK = K * R;
+  using Op = typename F::Op;
   const int64_t n_trees = (int64_t)trees.size();
   if (n_trees == 0) return;
   const int n = trees[0].n_tips, n_inner = n - 2, n_br = 2 * n - 3;
   const int64_t Ppad = aln.Ppad;
   size_t free_b = 0, total_b = 0;
   PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const size_t per_tree = ((size_t)n_inner * (16 * 8 + 4) + 16 * 8 + 4) * Ppad + (size_t)n_br * (68 + 256) * 8;
+  const size_t per_tree = ((size_t)n_inner * (RK * 8 + 4) + RK * 8 + 4) * Ppad + (size_t)n_br * (F::PM_STRIDE + F::TIP_STRIDE) * 8;
   int64_t B = std::max<int64_t>(1, std::min<int64_t>(n_trees, (int64_t)(std::min<size_t>(free_b / 2, (size_t)64 << 30) / per_tree)));
   if (const char *e = getenv("PLG_PLL_BATCH_CHUNK")) B = std::max<int64_t>(1, std::min<int64_t>(B, atoll(e)));  // tests: several chunks
   DevBuf<double> clv, S, pmat, tiptab, brlen, partial, lnl;
   DevBuf<int> scl, Ssc, idx, flags;
-  DevBuf<LikOpF> d_ops;
+  DevBuf<Op> d_ops;
   DevBuf<OptItem> d_items;
   DevBuf<LikEval> d_evals;
-  clv.alloc((size_t)B * n_inner * 16 * Ppad);
+  clv.alloc((size_t)B * n_inner * RK * Ppad);
   scl.alloc((size_t)B * n_inner * Ppad);
-  S.alloc((size_t)B * 16 * Ppad);
+  S.alloc((size_t)B * RK * Ppad);
   Ssc.alloc((size_t)B * Ppad);
-  pmat.alloc((size_t)B * n_br * 68);
-  tiptab.alloc((size_t)B * n_br * 256);
+  pmat.alloc((size_t)B * n_br * F::PM_STRIDE);
+  tiptab.alloc((size_t)B * n_br * F::TIP_STRIDE);
   brlen.alloc((size_t)B * n_br);
-  const int64_t ebpo = Ppad / 128;
+  const int64_t ebpo = Ppad / F::EVAL_TILE;
   partial.alloc((size_t)B * std::max<int64_t>(1, ebpo) * 2);
   lnl.alloc((size_t)B);
   flags.alloc((size_t)2 * B);
@@ -696,8 +732,8 @@ static void pll_loglik_batch_dna4(const LikAln &aln, const Model &model, std::ve
   d_ops.alloc((size_t)B * (n_inner + 3 * n_inner));
   d_items.alloc((size_t)B * n_br);
   idx.alloc((size_t)B * n_br);
-  const int bpi = (int)(Ppad / (SM_THREADS / 4));
-  std::vector<LikOpF> h_ops;
+  const int bpi = (int)(Ppad / (SM_THREADS / R));
+  std::vector<Op> h_ops;
   std::vector<OptItem> h_items;
   std::vector<int> h_idx, h_flags;
   std::vector<LikEval> h_evals;
@@ -715,7 +751,7 @@ static void pll_loglik_batch_dna4(const LikAln &aln, const Model &model, std::ve
     h_ops.clear(); h_items.clear(); h_idx.clear(); h_evals.clear();
     std::vector<int64_t> down_off(n_inner + 1, 0), clv_off(n_steps + 1, 0), opt_off(n_steps + 1, 0);
     for (int j = 0; j < n_inner; j++) {
-      for (int64_t i = 0; i < cnt; i++) h_ops.push_back(plans[i].down[j]);
+      for (int64_t i = 0; i < cnt; i++) h_ops.push_back(F::make(plans[i].down[j]));
       down_off[j + 1] = (int64_t)h_ops.size();
     }
     const int64_t pass_ops0 = (int64_t)h_ops.size();
@@ -723,7 +759,7 @@ static void pll_loglik_batch_dna4(const LikAln &aln, const Model &model, std::ve
       for (int64_t i = 0; i < cnt; i++) {
         const TreePlan::Act &a = plans[i].acts[s];
         if (a.is_opt) { h_items.push_back(a.it); h_idx.push_back(a.it.branch); }
-        else h_ops.push_back(a.op);
+        else h_ops.push_back(F::make(a.op));
       }
       clv_off[s + 1] = (int64_t)h_ops.size() - pass_ops0;
       opt_off[s + 1] = (int64_t)h_items.size();
@@ -732,7 +768,7 @@ static void pll_loglik_batch_dna4(const LikAln &aln, const Model &model, std::ve
     h_brlen.assign((size_t)cnt * n_br, -std::log(PLL_DEFAULTZ));  // useDefaultz (libpllWrapper.c:152)
     h_flags.assign((size_t)2 * cnt, 0);
     for (int64_t i = 0; i < cnt; i++) h_flags[i] = 1;  // active; changed = 0
-    PLG_CUDA(cudaMemcpy(d_ops.p, h_ops.data(), h_ops.size() * sizeof(LikOpF), cudaMemcpyHostToDevice));
+    PLG_CUDA(cudaMemcpy(d_ops.p, h_ops.data(), h_ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(d_items.p, h_items.data(), h_items.size() * sizeof(OptItem), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(idx.p, h_idx.data(), h_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(d_evals.p, h_evals.data(), h_evals.size() * sizeof(LikEval), cudaMemcpyHostToDevice));
@@ -740,27 +776,27 @@ static void pll_loglik_batch_dna4(const LikAln &aln, const Model &model, std::ve
     PLG_CUDA(cudaMemcpy(flags.p, h_flags.data(), h_flags.size() * sizeof(int), cudaMemcpyHostToDevice));
     int *active = flags.p, *changed = flags.p + cnt;
     cudaStream_t st = 0;
-    dna4_pmatrices(aln, model, brlen.p, nullptr, cnt * n_br, pmat.p, tiptab.p, st);
+    F::pmatrices(aln, model, brlen.p, nullptr, cnt * n_br, pmat.p, tiptab.p, st);
     for (int j = 0; j < n_inner; j++)
-      dna4_updates(aln, model, d_ops.p + down_off[j], down_off[j + 1] - down_off[j], pmat.p, tiptab.p, clv.p, scl.p, st);
+      F::updates(aln, model, d_ops.p + down_off[j], down_off[j + 1] - down_off[j], pmat.p, tiptab.p, clv.p, scl.p, st);
     for (int pass = 0; pass < passes; pass++) {
       for (int s = 0; s < n_steps; s++) {
         const int64_t nc = clv_off[s + 1] - clv_off[s], no = opt_off[s + 1] - opt_off[s];
-        if (nc) dna4_updates(aln, model, d_ops.p + pass_ops0 + clv_off[s], nc, pmat.p, tiptab.p, clv.p, scl.p, st);
+        if (nc) F::updates(aln, model, d_ops.p + pass_ops0 + clv_off[s], nc, pmat.p, tiptab.p, clv.p, scl.p, st);
         if (no) {
           const OptItem *its = d_items.p + opt_off[s];
-          sumtable4_batch_kernel<<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(its, bpi, aln.n_rows, Ppad, aln.codes.p,
-                                                                               aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p);
-          opt4_batch_kernel<<<(unsigned)no, SM_THREADS, 0, st>>>(its, Ppad, aln.weights.p, model.d.p, S.p, Ssc.p, brlen.p,
-                                                                 active, changed);
+          sumtable_batch_kernel<K, R><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
+              its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p);
+          opt_batch_kernel<K, R><<<(unsigned)no, SM_THREADS, 0, st>>>(its, Ppad, aln.weights.p, model.d.p, S.p, Ssc.p,
+                                                                      brlen.p, active, changed);
           count_launch(2);
-          dna4_pmatrices(aln, model, brlen.p, idx.p + opt_off[s], no, pmat.p, tiptab.p, st);
+          F::pmatrices(aln, model, brlen.p, idx.p + opt_off[s], no, pmat.p, tiptab.p, st);
         }
       }
       next_pass_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((int)cnt, active, changed);
       count_launch();
     }
-    dna4_evals(aln, model, d_evals.p, cnt, pmat.p, tiptab.p, clv.p, scl.p, partial.p, lnl.p, st);
+    F::evals(aln, model, d_evals.p, cnt, pmat.p, tiptab.p, clv.p, scl.p, partial.p, lnl.p, st);
     PLG_CUDA(cudaGetLastError());
     h_lnl.resize(cnt);
     PLG_CUDA(cudaMemcpy(h_lnl.data(), lnl.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
@@ -1055,8 +1091,10 @@ extern "C" int plg_pll_loglik_batch(const char *phylip_path, const char *partiti
     for (auto &l : trees[i].len) for (auto &x : l) x = -std::log(PLL_DEFAULTZ);
   }
   g_batch_newicks.assign(n_trees, std::string());
-  if (al->aln->K == 4 && al->model->R == 4) {
-    pll_loglik_batch_dna4(*al->aln, *al->model, trees, rows, passes, out_lnl);
+  const bool dna4 = al->aln->K == 4 && al->model->R == 4, aa20 = al->aln->K == 20 && al->model->R == 4;
+  if (dna4 || aa20) {
+    if (dna4) pll_loglik_batch<Dna4Family>(*al->aln, *al->model, trees, rows, passes, out_lnl);
+    else pll_loglik_batch<Aa20Family>(*al->aln, *al->model, trees, rows, passes, out_lnl);
     PllProblem writer;  // (only its Newick writer is used)
     for (int64_t i = 0; i < n_trees; i++) {
       writer.tip_names = names[i];

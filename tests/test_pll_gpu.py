@@ -286,3 +286,38 @@ def test_batched_getLogLikelihood_small_trees_and_chunks(n, monkeypatch):
     assert len(opt) == len(newicks) and all(s.endswith(";") for s in opt)
     assert W.getLogLikelihoodBatch(ali.getPhylip(), [], pm.getFileName()) == ([], [])
     pm.close(); ali.close()
+
+
+def test_batched_getLogLikelihood_wag():
+    """The 20-state family of the batched smoother (clv20 / eval20 kernels, 80-entry sum tables)
+    against one handle per tree."""
+    from pylogeny_b200 import alignment, libpllWrapper as W, pll
+    rng = np.random.default_rng(44)
+    aa = "ARNDCQEGHILKMFPSTWYV"
+    n = 9
+    base = rng.integers(0, 20, 300)
+    seqs = []
+    for _ in range(n):
+        s = base.copy()
+        mut = rng.random(300) < 0.25
+        s[mut] = rng.integers(0, 20, mut.sum())
+        seqs.append("".join(aa[i] for i in s))
+    seqs[2] = seqs[2][:10] + "XB-Z" + seqs[2][14:]
+    ali = alignment.phylipFriendlyAlignment(names=["p%d" % i for i in range(n)], seqs=seqs)
+    labels = ali.getTaxa()
+    newicks = [desc_to_newick(random_desc(rng, n), labels) for _ in range(7)]
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    want, want_nw = [], []
+    for nw in newicks:
+        h = W.new(ali.getPhylip(), nw, pm.getFileName())
+        want.append(W.getLogLikelihood(h))
+        want_nw.append(W.getNewickString(h))
+        W.destroy(h)
+    got, opt = W.getLogLikelihoodBatch(ali.getPhylip(), newicks, pm.getFileName())
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    from pylogeny_b200 import neighbourhood as nbh
+    taxa = {l: i for i, l in enumerate(labels)}
+    for a, b in zip(opt, want_nw):
+        np.testing.assert_allclose(nbh.newick_to_desc(a, taxa)[1], nbh.newick_to_desc(b, taxa)[1], rtol=1e-6, atol=1e-9)
+    pm.close(); ali.close()
