@@ -455,9 +455,24 @@ __global__ void __launch_bounds__(SM_THREADS)
 sumtable_batch_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
                       const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
                       const ModelDev *__restrict__ model, const double *__restrict__ clv,
-                      const int *__restrict__ scl, double *__restrict__ S, int *__restrict__ Ssc) {
+                      const int *__restrict__ scl, double *__restrict__ S, int *__restrict__ Ssc,
+                      const double *__restrict__ weights, const double *__restrict__ brlen,
+                      double *__restrict__ dpart) {
+  // Besides the table, the block's share of the derivative sums at the branch's CURRENT length:
+  // the Newton step that follows (opt_batch_kernel) normally needs nothing else, so the table is
+  // read back only when the bad-curvature guard has to try another length.
+  __shared__ double tab[3][R * K];
+  __shared__ double red[3][SM_THREADS / 32];
   const int item = blockIdx.x / blocks_per_item;
   const OptItem it = items[item];
+  if (threadIdx.x < R * K) {
+    const double z = fmin(fmax(exp(-brlen[it.branch]), PLL_ZMIN), PLL_ZMAX);
+    const double lz = log(fmax(z, PLL_ZMIN));
+    const double g = -model->eval[threadIdx.x % K] * model->rates[threadIdx.x / K];
+    const double e = exp(g * lz);
+    tab[0][threadIdx.x] = e; tab[1][threadIdx.x] = g * e; tab[2][threadIdx.x] = g * g * e;
+  }
+  __syncthreads();
   const int r = threadIdx.x % R;
   const int64_t p = (int64_t)(blockIdx.x - item * blocks_per_item) * (SM_THREADS / R) + threadIdx.x / R;
   double A[K], B[K];
@@ -479,6 +494,7 @@ sumtable_batch_kernel(const OptItem *__restrict__ items, int blocks_per_item, in
 #pragma unroll
   for (int i = 0; i < K; i++) A[i] *= model->freqs[i];
   double *So = S + (int64_t)it.tree * R * K * Ppad;
+  double l0 = 0.0, l1 = 0.0, l2 = 0.0;
   for (int k = 0; k < K; k++) {
     double l = 0.0, rr = 0.0;
 #pragma unroll
@@ -486,9 +502,42 @@ sumtable_batch_kernel(const OptItem *__restrict__ items, int blocks_per_item, in
       l = fma(A[i], model->U[i * K + k], l);
       rr = fma(model->Uinv[k * K + i], B[i], rr);
     }
-    So[((int64_t)r * K + k) * Ppad + p] = l * rr;
+    const double sv = l * rr;
+    So[((int64_t)r * K + k) * Ppad + p] = sv;
+    l0 = fma(sv, tab[0][r * K + k], l0);
+    l1 = fma(sv, tab[1][r * K + k], l1);
+    l2 = fma(sv, tab[2][r * K + k], l2);
   }
   if (r == 0) Ssc[(int64_t)it.tree * Ppad + p] = sc;
+#pragma unroll
+  for (int d = 1; d < R; d <<= 1) {
+    l0 += __shfl_xor_sync(0xffffffffu, l0, d);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, d);
+    l2 += __shfl_xor_sync(0xffffffffu, l2, d);
+  }
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  const double w = weights[p];
+  if (r == 0 && w != 0.0) {
+    const double inv = 1.0 / l0, q1 = l1 * inv;
+    v0 = w * (log(l0 * (1.0 / R)) + sc * SM_LOG_MINLH);
+    v1 = w * q1;
+    v2 = w * (l2 * inv - q1 * q1);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v0 += __shfl_down_sync(0xffffffffu, v0, d);
+    v1 += __shfl_down_sync(0xffffffffu, v1, d);
+    v2 += __shfl_down_sync(0xffffffffu, v2, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = v0; red[1][threadIdx.x >> 5] = v1; red[2][threadIdx.x >> 5] = v2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int i = 0; i < SM_THREADS / 32; i++) t += red[threadIdx.x][i];
+    dpart[((int64_t)item * 3 + threadIdx.x) * blocks_per_item + (blockIdx.x - item * blocks_per_item)] = t;
+  }
 }
 
 // One makenewz step (optimise_branch with maxiter = 1) per block, on the tree's sum table.
@@ -496,7 +545,8 @@ template <int K, int R>
 __global__ void __launch_bounds__(SM_THREADS)
 opt_batch_kernel(const OptItem *__restrict__ items, int64_t Ppad, const double *__restrict__ weights,
                  const ModelDev *__restrict__ model, const double *__restrict__ S, const int *__restrict__ Ssc,
-                 double *__restrict__ brlen, const int *__restrict__ active, int *__restrict__ changed) {
+                 double *__restrict__ brlen, const int *__restrict__ active, int *__restrict__ changed,
+                 const double *__restrict__ dpart, int blocks_per_item) {
   constexpr int RK = R * K;
   const OptItem it = items[blockIdx.x];
   if (!active[it.tree]) return;
@@ -523,7 +573,13 @@ opt_batch_kernel(const OptItem *__restrict__ items, int64_t Ppad, const double *
     }
     __syncthreads();
     double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-    for (int64_t p = threadIdx.x; p < Ppad; p += SM_THREADS) {
+    if (guard == 0) {  // the sums at the current length came with the table (sumtable_batch_kernel)
+      const double *dp = dpart + (int64_t)blockIdx.x * 3 * blocks_per_item;
+      for (int b = threadIdx.x; b < blocks_per_item; b += SM_THREADS) {
+        v0 += dp[b]; v1 += dp[blocks_per_item + b]; v2 += dp[2 * blocks_per_item + b];
+      }
+    }
+    for (int64_t p = threadIdx.x; guard > 0 && p < Ppad; p += SM_THREADS) {
       const double w = weights[p];
       if (w == 0.0) continue;
       double l0 = 0.0, l1 = 0.0, l2 = 0.0;
@@ -711,7 +767,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   const size_t per_tree = ((size_t)n_inner * (RK * 8 + 4) + RK * 8 + 4) * Ppad + (size_t)n_br * (F::PM_STRIDE + F::TIP_STRIDE) * 8;
   int64_t B = std::max<int64_t>(1, std::min<int64_t>(n_trees, (int64_t)(std::min<size_t>(free_b / 2, (size_t)64 << 30) / per_tree)));
   if (const char *e = getenv("PLG_PLL_BATCH_CHUNK")) B = std::max<int64_t>(1, std::min<int64_t>(B, atoll(e)));  // tests: several chunks
-  DevBuf<double> clv, S, pmat, tiptab, brlen, partial, lnl;
+  DevBuf<double> clv, S, pmat, tiptab, brlen, partial, lnl, dpart;
   DevBuf<int> scl, Ssc, idx, flags;
   DevBuf<Op> d_ops;
   DevBuf<OptItem> d_items;
@@ -733,6 +789,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   d_items.alloc((size_t)B * n_br);
   idx.alloc((size_t)B * n_br);
   const int bpi = (int)(Ppad / (SM_THREADS / R));
+  dpart.alloc((size_t)B * 3 * bpi);
   std::vector<Op> h_ops;
   std::vector<OptItem> h_items;
   std::vector<int> h_idx, h_flags;
@@ -786,9 +843,10 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
         if (no) {
           const OptItem *its = d_items.p + opt_off[s];
           sumtable_batch_kernel<K, R><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
-              its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p);
+              its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
+              aln.weights.p, brlen.p, dpart.p);
           opt_batch_kernel<K, R><<<(unsigned)no, SM_THREADS, 0, st>>>(its, Ppad, aln.weights.p, model.d.p, S.p, Ssc.p,
-                                                                      brlen.p, active, changed);
+                                                                      brlen.p, active, changed, dpart.p, bpi);
           count_launch(2);
           F::pmatrices(aln, model, brlen.p, idx.p + opt_off[s], no, pmat.p, tiptab.p, st);
         }
