@@ -49,6 +49,9 @@ static_assert(WM_NG == 4 || WM_NG == 2, "a warp carries 32 or 16 patterns");
 #define PLG_WM_STAGE 0     // 1: the far-side operands of the NEXT visit are fetched by cp.async into shared memory during this one
                            //    (B200: 9.2 vs 7.9 ms -- 209 KB of shared memory leave no L1 for the spills and fragments)
 #endif
+#ifndef PLG_WM_FUSE2
+#define PLG_WM_FUSE2 0     // 1: the D2 stage and neighbour chain 2 in one straight-line loop (h2 never a vector): 5.76 vs 5.58 ms
+#endif
 #ifndef PLG_WM_REFRAG
 #define PLG_WM_REFRAG 0
 #endif
@@ -403,6 +406,42 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
       }
       sc2 = sk + s1;
       wm_rescale(n2, sc2, lane);
+#if PLG_WM_FUSE2 && !PLG_WM_STAGE
+      // D2 once, fused with neighbour chain 2: (P_t2 D2, P_h2 D2) and (P_t2 N2, P_h2 N2) element by
+      // element -- N1 = a o P_t2 D2 is the only vector this stage leaves behind; h2 = P_h2 D2 is
+      // consumed on the spot by neighbour 2's site sums and never exists as a vector.
+      double n1[WM_V];
+      int s2, sc1;
+      {
+        double x[WM_V], u[WM_NG], s01[WM_NG], e2[WM_NG];
+        wm_load_raw(d2, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, s2);
+        double *stk_dst = stk + (int64_t)(push >= 0 ? push : 0) * WM_V * 32;
+        const bool do_push = push >= 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+          for (int j = 0; j < WM_NG; j++) {
+            const int i = r * WM_NG + j;
+            double t, h, a, g;
+            wm_dmma(t, h, x[i], bf2[r]);
+            n1[i] = t * ak[i];
+            wm_dmma(a, g, n2[i], bf2[r]);
+            if (do_push) stk_dst[i * 32] = a;
+            const double tt = g * (h * park[0][i][lane]);
+            if (r == 0) s01[j] = tt;
+            else if (r == 1) s01[j] += tt;
+            else if (r == 2) e2[j] = tt;
+            else u[j] = s01[j] + (e2[j] + tt);
+          }
+        if (push >= 0) stks[push * WM_NG * 32] = sc2;
+        if (tree2 >= 0) {
+          const double val = wm_site_sum_u(u, sc2 + s2 + st, w_out, pi_q, lane);
+          if (lane == 0) partial[(int64_t)tree2 * pstride + slice] = val;
+        }
+      }
+      sc1 = sk + s2;
+      wm_rescale(n1, sc1, lane);
+#else
       // D2 once: N1 = a o P_t2 D2 and h2 = P_h2 D2
       double n1[WM_V], h2[WM_V];
       int s2, sc1;
@@ -451,6 +490,7 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
           if (lane == 0) partial[(int64_t)tree2 * pstride + slice] = val;
         }
       }
+#endif
       {  // side 1: toward c1 (straight into ak) and neighbour 1 (insertion into x--c1)
         double u[WM_NG], h1[WM_V];
 #if PLG_WM_REFRAG
