@@ -907,7 +907,7 @@ static void run_aa20(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       }
       q = j;
     }
-    static thread_local DevBuf<int4> d_rows;
+    DevBuf<int4> &d_rows = ws.eval_rows;  // (per-device workspace)
     d_rows.alloc(rows.size());
     PLG_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), rows.size() * sizeof(LikEvalRow), cudaMemcpyHostToDevice, st));
     prof_begin(PROF_ROOT_EVAL, st);

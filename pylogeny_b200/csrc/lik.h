@@ -74,6 +74,7 @@ struct LikWorkspace {
   DevBuf<unsigned long long> walk_counter;
   DevBuf<int4> spr_edges, spr_searches, spr_moves;  // device-planned SPR neighbourhoods
   DevBuf<double> spr_acct;                          // byte accounting of the planned walk (profiling)
+  DevBuf<int4> eval_rows;                           // LikEvalRow[] (lik_aa.cuh eval20_rows_kernel)
   DevBuf<int32_t> tw_desc;     // tree walks (treewalk.h): raw descriptors, planned ops, planner scratch
   DevBuf<int4> tw_ops;
   DevBuf<int> tw_scratch;
