@@ -663,7 +663,7 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
     switch (a.K) {
       case 2: launch_fitch_search_walk<2, 4>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
       case 3: launch_fitch_search_walk<3, 4>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
-      case 4: launch_fitch_search_walk<4, 4>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
+      case 4: launch_fitch_search_walk<4, PLG_FSW_VW_DNA>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
       case 5: launch_fitch_search_walk<5, 4>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
       case 6: launch_fitch_search_walk<6, 4>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;
       case 8: launch_fitch_search_walk<8, 2>(a, ws.scratch.p, dv, dg, ng, ws.cost.p, st); break;

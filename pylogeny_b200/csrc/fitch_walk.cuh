@@ -216,6 +216,9 @@ __device__ __forceinline__ unsigned int fw_join_miss(const unsigned int (&n)[K][
   return c;
 }
 
+#ifndef PLG_FSW_VW_DNA
+#define PLG_FSW_VW_DNA 4  // 32-bit words per plane a thread carries through a 4-plane search walk (4 = 128 patterns; 2: 2.79 vs 2.59 ms per 256x100k step at best)
+#endif
 #ifndef PLG_FSW_MINB
 #define PLG_FSW_MINB 2  // 120 registers, no spills (1: 147 registers, 3.2 vs 2.66 ms per 256x100k step; 3: 80 registers with spills, 3.6)
 #endif
