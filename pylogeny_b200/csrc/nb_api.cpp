@@ -270,7 +270,7 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
   if (walk && depth < 0 && shard_count == 1 && shard_index == 0 && n_tips >= 4 &&
       !(plan_env && !strcmp(plan_env, "host"))) {
     static thread_local SprDevicePlan plan;  // keeps its pinned staging across calls
-    static thread_local std::vector<int32_t> acc;
+    static thread_local HostArr<int32_t> acc;  // pinned: the 1 MB of accumulators comes back at full PCIe rate
     const UTree t = utree_from_desc(n_tips, desc, nullptr);
     prepare_spr_device_plan(t, tip_rows, a.n_cols, plan);
     tm.lap("prepare");
