@@ -64,6 +64,20 @@ def test_batched_explore_matches_reference_run(monkeypatch, al_greedy, al_fitch)
         assert scores == sorted(by_topo.values())
         assert {ls._b200_hash_of(ls.getTree(j).getNewick(), ls.parsimony_profiles.taxa) for j in nbrs} == set(by_topo)
         assert ls.exploreTree(ls.root) == []                       # explored flag
+        # likelihood for many nodes in one call: the engine call is stubbed, the wiring is under test
+        calls = []
+
+        def fake_batch(trees, alignment_, updateBranchLengths=True):
+            calls.append(len(trees))
+            return [-1000.0 - k for k in range(len(trees))]
+
+        monkeypatch.setattr(scoring, "getLogLikelihoodBatch", fake_batch)
+        got = ls.scoreLikelihoodFor(nbrs[:7])
+        assert calls == [7] and got == [-1000.0 - k for k in range(7)]
+        assert [ls.getTree(j).score[0] for j in nbrs[:7]] == got
+        assert all(ls.getTree(j).score[1] is not None for j in nbrs[:7])      # parsimony kept
+        assert ls.scoreLikelihoodFor(nbrs[:9])[:7] == got and calls == [7, 2]  # only the unscored ones go out
+        assert ls.getVertex(nbrs[0]).scoreLikelihood() == got[0]               # the reference finds it cached
         # greedy climb over the batched landscape: same path scores as the unchanged reference run
         ls2 = batchedLandscape(ali, starting_tree=mods["tree"].tree(cat + ";"), root=True, operator="SPR")
         h = mods["heuristic"].parsimonyGreedy(ls2, ls2.getNode(ls2.root))
