@@ -30,7 +30,6 @@
 namespace plg {
 
 constexpr double PLL_ZMIN = 1.0e-15, PLL_ZMAX = 1.0 - 1.0e-6, PLL_DEFAULTZ = 0.9, PLL_DELTAZ = 1.0e-5;
-constexpr double SM_MINLH = 8.636168555094445e-78;  // 2^-256
 constexpr double SM_LOG_MINLH = -256.0 * 0.693147180559945309417232121458176568;  // log(2^-256), folded
 constexpr int SM_THREADS = 256;
 
