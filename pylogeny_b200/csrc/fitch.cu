@@ -368,6 +368,7 @@ void FitchProgram::clear() {
   spr_edges.clear();
   spr_searches.clear();
   spr_n_visits = spr_n_unique = 0;
+  spr_lo = spr_hi = 0;
   spr_first_acc = 0;
   spr_vecs = spr_req_vecs = 0;
   n_scratch_slots = 0;
@@ -385,7 +386,7 @@ void FitchProgram::clear() {
 constexpr size_t SPR_PLAN_SMEM_MAX = 200 << 10;  // edge records of trees up to ~4,000 (parsimony) / ~2,000 (likelihood) taxa
 __global__ void __launch_bounds__(64)
 spr_plan_kernel(const int4 *__restrict__ edges_g, int n_edge_recs, const int4 *__restrict__ searches, int n_search,
-                int first_acc, int4 *__restrict__ visits, int4 *__restrict__ out_moves) {
+                int first_acc, int id_lo, int id_hi, int4 *__restrict__ visits, int4 *__restrict__ out_moves) {
   // a search is one long chain of dependent edge-record lookups: keep the records in shared
   // memory when they fit (n_edge_recs > 0), 155 -> 30 us per 256-taxon neighbourhood
   extern __shared__ int4 spr_edges_s[];
@@ -446,8 +447,11 @@ spr_plan_kernel(const int4 *__restrict__ edges_g, int n_edge_recs, const int4 *_
       sx[sp] = E2.x; sfrom[sp] = x; spre[sp] = pre2; sin[sp] = -1; sdep[sp] = dep + 1;
       sp++;
     }
-    visits[2 * at] = make_int4(x_in, E1.y, E2.y, uid1 >= 0 ? first_acc + uid1 : -1);
-    visits[2 * at + 1] = make_int4(uid2 >= 0 ? first_acc + uid2 : -1, keep, push, 0);
+    // accumulators exist for the scored range of unique ids only (a shard scores [id_lo, id_hi))
+    const int t1 = uid1 >= id_lo && uid1 < id_hi ? first_acc + (uid1 - id_lo) : -1;
+    const int t2 = uid2 >= id_lo && uid2 < id_hi ? first_acc + (uid2 - id_lo) : -1;
+    visits[2 * at] = make_int4(x_in, E1.y, E2.y, t1);
+    visits[2 * at + 1] = make_int4(t2, keep, push, 0);
     at++;
     if (out_moves) {
       if (uid1 >= 0) out_moves[uid1] = make_int4(pe, complement, E1.w, dep);
@@ -588,7 +592,7 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
     }
     spr_plan_kernel<<<(n_search + 63) / 64, 64, in_smem ? edge_bytes : 0, side.s>>>(
         ws.spr_edges.p, in_smem ? (int)prog.spr_edges.size() : 0, ws.spr_searches.p, n_search, prog.spr_first_acc,
-        ws.nbw_visits.p, out_moves ? ws.spr_moves.p : nullptr);
+        (int)prog.spr_lo, (int)prog.spr_hi, ws.nbw_visits.p, out_moves ? ws.spr_moves.p : nullptr);
     count_launch();
     PLG_CUDA(cudaEventRecord(side.planned, side.s));
     if (out_moves)  // the move table comes back while the walk runs; copied out after the final sync

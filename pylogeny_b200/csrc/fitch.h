@@ -95,6 +95,7 @@ struct FitchProgram {
   HostArr<SprEdgeRec> spr_edges;
   HostArr<SprSearchRec> spr_searches;
   int64_t spr_n_visits = 0, spr_n_unique = 0;
+  int64_t spr_lo = 0, spr_hi = 0;  // unique ids scored by this program (accumulator spr_first_acc + id - spr_lo)
   int spr_first_acc = 0;
   double spr_vecs = 0, spr_req_vecs = 0;  // algorithmic / requested vectors of the walk launch
   FitchProgram() = default;

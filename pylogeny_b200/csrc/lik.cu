@@ -339,6 +339,7 @@ void LikProgram::clear() {
   spr_edges.clear();
   spr_searches.clear();
   spr_n_visits = spr_n_unique = 0;
+  spr_lo = spr_hi = 0;
   ops.clear();
   level_off.clear();
   evals.clear();
@@ -498,8 +499,8 @@ static void run_typed(const LikAln &a, const Model &m, LikWorkspace &ws, const L
 constexpr size_t SPR_LIK_PLAN_SMEM_MAX = 200 << 10;
 __global__ void __launch_bounds__(64)
 spr_lik_plan_kernel(const int4 *__restrict__ edges_g, int n_edge_int4, const int4 *__restrict__ searches,
-                    int n_search, int n_rows, int4 *__restrict__ visits, int4 *__restrict__ out_moves,
-                    double *__restrict__ acct) {
+                    int n_search, int n_rows, int id_lo, int id_hi, int4 *__restrict__ visits,
+                    int4 *__restrict__ out_moves, double *__restrict__ acct) {
   extern __shared__ int4 spr_lik_edges_s[];  // the edge records, when they fit (n_edge_int4 > 0)
   const int4 *edges = edges_g;
   if (n_edge_int4 > 0) {
@@ -565,6 +566,13 @@ spr_lik_plan_kernel(const int4 *__restrict__ edges_g, int n_edge_int4, const int
     }
     // normal form (walk4m_kernel relies on it): the partial that continues in registers is the one
     // toward d1, so the visit's "2" side is the one that may be parked
+    if (out_moves) {
+      if (uid1 >= 0) out_moves[uid1] = make_int4(pe, complement, E1.w, dep);
+      if (uid2 >= 0) out_moves[uid2] = make_int4(pe, complement, E2.w, dep);
+    }
+    // trees exist for the scored range of unique ids only (a shard scores [id_lo, id_hi))
+    uid1 = uid1 >= id_lo && uid1 < id_hi ? uid1 - id_lo : -1;
+    uid2 = uid2 >= id_lo && uid2 < id_hi ? uid2 - id_lo : -1;
     int4 *vp = visits + 4 * at;
     if (keep == 2) {
       vp[0] = make_int4(x_in, p_in, E2.y, Q2.x);
@@ -577,10 +585,6 @@ spr_lik_plan_kernel(const int4 *__restrict__ edges_g, int n_edge_int4, const int
     }
     vp[3] = make_int4(0, 0, 0, 0);
     at++;
-    if (out_moves) {
-      if (uid1 >= 0) out_moves[uid1] = make_int4(pe, complement, E1.w, dep);
-      if (uid2 >= 0) out_moves[uid2] = make_int4(pe, complement, E2.w, dep);
-    }
     if (acct) {
       const double o1 = E1.y < n_rows ? 1.0 : Cb, o2 = E2.y < n_rows ? 1.0 : Cb;
       const double xin = x_in >= 0 ? (x_in < n_rows ? 1.0 : Cb) : Cb;
@@ -795,7 +799,8 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       ensure_dyn_smem(spr_lik_plan_kernel, (int)SPR_LIK_PLAN_SMEM_MAX, plan_attr_set);
       spr_lik_plan_kernel<<<(n_search + 63) / 64, 64, in_smem ? edge_bytes : 0, st>>>(
           ws.spr_edges.p, in_smem ? (int)(edge_bytes / 16) : 0, ws.spr_searches.p, n_search, a.n_rows,
-          reinterpret_cast<int4 *>(ws.walk_visits.p), out_moves ? ws.spr_moves.p : nullptr,
+          (int)prog.spr_lo, (int)prog.spr_hi, reinterpret_cast<int4 *>(ws.walk_visits.p),
+          out_moves ? ws.spr_moves.p : nullptr,
           acct_on ? ws.spr_acct.p : nullptr);
       count_launch();
       if (out_moves)

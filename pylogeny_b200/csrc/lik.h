@@ -109,6 +109,7 @@ struct LikProgram {
   std::vector<LikSprEdge> spr_edges;
   std::vector<LikSprSearch> spr_searches;
   int64_t spr_n_visits = 0, spr_n_unique = 0;
+  int64_t spr_lo = 0, spr_hi = 0;         // unique ids scored by this program (tree id = unique id - spr_lo)
   std::vector<double> brlens;      // unique branch lengths -> P-matrix index
   std::unordered_map<uint64_t, int> pm_index;
   int64_t n_slots = 0, n_trees = 0;

@@ -267,22 +267,27 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
   // are laid out by spr_plan_kernel (PLG_FITCH_NB_PLAN=host keeps the host planner for A/B tests;
   // shards, NNI and radius-limited searches use it too).
   const char *plan_env = std::getenv("PLG_FITCH_NB_PLAN");
-  if (walk && depth < 0 && shard_count == 1 && shard_index == 0 && n_tips >= 4 &&
-      !(plan_env && !strcmp(plan_env, "host"))) {
+  if (walk && depth < 0 && n_tips >= 4 && !(plan_env && !strcmp(plan_env, "host"))) {
     static thread_local SprDevicePlan plan;  // keeps its pinned staging across calls
     static thread_local HostArr<int32_t> acc;  // pinned: the 1 MB of accumulators comes back at full PCIe rate
     const UTree t = utree_from_desc(n_tips, desc, nullptr);
-    prepare_spr_device_plan(t, tip_rows, a.n_cols, plan);
+    const int64_t M = 2 * ((int64_t)n_tips - 3) * (2 * (int64_t)n_tips - 7);  // distinct SPR neighbours
+    int64_t lo, hi;
+    shard_range(M, shard_index, shard_count, &lo, &hi);
+    const bool whole = lo == 0 && hi == M;
+    prepare_spr_device_plan(t, tip_rows, a.n_cols, plan, lo, hi);
     tm.lap("prepare");
-    *n_moves = plan.n_unique;
-    if (!out_costs) {  // moves only: the host enumeration
+    if (plan.n_unique != M) PLG_FAIL(PLG_ERR_ARG, "internal: %lld distinct SPR neighbours planned, %lld expected",
+                                     (long long)plan.n_unique, (long long)M);
+    *n_moves = M;
+    if (out_moves && (!out_costs || !whole)) {  // the move table of the WHOLE neighbourhood: host enumeration
       static thread_local Neighbourhood nb0;
       enumerate_spr(t, depth, nb0);
       fill_moves(nb0, out_moves);
-      return PLG_OK;
     }
+    if (!out_costs || hi == lo) return PLG_OK;
     acc.resize(plan.base.prog.n_costs);
-    run_fitch_program(a, fitch_workspace(), plan.base.prog, acc.data(), (cudaStream_t)stream, out_moves);
+    run_fitch_program(a, fitch_workspace(), plan.base.prog, acc.data(), (cudaStream_t)stream, whole ? out_moves : nullptr);
     tm.lap("run");
     finish_fitch_spr_plan(t, plan, acc.data(), out_costs);
     tm.lap("finish");
@@ -346,9 +351,8 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
   // A whole SPR neighbourhood on one device (DNA x Gamma-4 walks): O(n) host records, the search
   // walks are laid out by spr_lik_plan_kernel (PLG_LIK_NB_PLAN=host keeps the host planner)
   const char *plan_env = std::getenv("PLG_LIK_NB_PLAN");
-  if (out_lnl && depth < 0 && shard_count == 1 && shard_index == 0 && n_tips >= 4 &&
-      n_tips <= (1 << WALK_MAX_LEVELS) && a.K == 4 && m->impl.R == 4 && lik_nb_mode() == LIK_NB_WALK &&
-      !(plan_env && !strcmp(plan_env, "host"))) {
+  if (out_lnl && depth < 0 && n_tips >= 4 && n_tips <= (1 << WALK_MAX_LEVELS) && a.K == 4 && m->impl.R == 4 &&
+      lik_nb_mode() == LIK_NB_WALK && !(plan_env && !strcmp(plan_env, "host"))) {
     const size_t slot_bytes = ((size_t)m->impl.R * a.K * 8 + 4) * a.Ppad;
     const size_t held = lik_workspace().clv.n * 8 + lik_workspace().scl.n * 4;
     const size_t need = (size_t)3 * (n_tips - 2) * slot_bytes;
@@ -357,10 +361,23 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
     tm.lap("meminfo");
     if (need <= held || need <= std::min<size_t>((free_b + held) / 2, (size_t)80 << 30)) {
       static thread_local LikProgram p;
-      build_lik_spr_device_plan(utree_from_desc(n_tips, desc, brlen), tip_rows, a.n_rows, p);
+      const UTree t = utree_from_desc(n_tips, desc, brlen);
+      const int64_t M = 2 * ((int64_t)n_tips - 3) * (2 * (int64_t)n_tips - 7);
+      int64_t lo, hi;
+      shard_range(M, shard_index, shard_count, &lo, &hi);
+      const bool whole = lo == 0 && hi == M;
+      build_lik_spr_device_plan(t, tip_rows, a.n_rows, p, lo, hi);
       tm.lap("prepare");
-      *n_moves = p.spr_n_unique;
-      run_lik_program(a, m->impl, lik_workspace(), p, out_lnl, (cudaStream_t)stream, out_moves);
+      if (p.spr_n_unique != M) PLG_FAIL(PLG_ERR_ARG, "internal: %lld distinct SPR neighbours planned, %lld expected",
+                                        (long long)p.spr_n_unique, (long long)M);
+      *n_moves = M;
+      if (out_moves && !whole) {  // the move table of the WHOLE neighbourhood: host enumeration
+        static thread_local Neighbourhood nb0;
+        enumerate_spr(t, depth, nb0);
+        fill_moves(nb0, out_moves);
+      }
+      if (hi > lo)  // (out_lnl is indexed by neighbour: the shard's block starts at lo)
+        run_lik_program(a, m->impl, lik_workspace(), p, out_lnl + lo, (cudaStream_t)stream, whole ? out_moves : nullptr);
       tm.lap("run");
       return PLG_OK;
     }

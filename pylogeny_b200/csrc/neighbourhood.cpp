@@ -727,13 +727,17 @@ struct SprSearchLayout {
   std::vector<FitchWalkGroup> groups;
   std::vector<int> search_edge;
   std::vector<int64_t> search_uniq;
-  int64_t n_visits = 0, n_unique = 0, dup_internal = 0, n_started = 0;
+  int64_t n_visits = 0, n_unique = 0, dup_internal = 0, n_started = 0, unscored = 0;
 };
 
-void layout_spr_searches(const UTree &t, const DirOrder &d, const std::vector<int> &dir_slot, SprSearchLayout &out) {
+// [lo, hi): the unique ids a call scores.  Searches that hold none of them get no visits (a shard
+// of the neighbourhood plans and walks only its own searches; the two at its borders are walked
+// whole and score only their ids inside the range).
+void layout_spr_searches(const UTree &t, const DirOrder &d, const std::vector<int> &dir_slot, SprSearchLayout &out,
+                         int64_t lo = 0, int64_t hi = INT64_MAX) {
   out.edges.clear(); out.searches.clear(); out.groups.clear(); out.search_edge.clear();
   out.search_uniq.assign(1, 0);
-  out.n_visits = out.n_unique = out.dup_internal = out.n_started = 0;
+  out.n_visits = out.n_unique = out.dup_internal = out.n_started = out.unscored = 0;
   if (t.n_tips < 4) return;
   // leaves on x's side of edge x -> nb[x][k]
   std::vector<int> leaves((size_t)t.n_nodes * 3, 0);
@@ -814,10 +818,14 @@ void layout_spr_searches(const UTree &t, const DirOrder &d, const std::vector<in
             }
             e++;
           }
+          const int64_t u0 = r.uniq_base, u1 = u0 + n_moves - ((r.dup_flag & 1) + ((r.dup_flag >> 1) & 1));
           // a one-visit search whose two moves both repeat earlier topologies has nothing to do
-          // (the host planner drops it as well)
-          if (r.move_cnt == 2 && (r.dup_flag & 3) == 3) r.move_cnt = 0;
-          else out.dup_internal += dup_int;
+          // (the host planner drops it as well); neither has a search outside the scored range
+          if ((r.move_cnt == 2 && (r.dup_flag & 3) == 3) || u1 <= lo || u0 >= hi) r.move_cnt = 0;
+          else {
+            out.dup_internal += dup_int;
+            out.unscored += (int64_t)n_moves - (std::min(u1, hi) - std::max(u0, lo));  // repeats and ids outside the range
+          }
         }
         if (r.move_cnt > 0) {
           if (cur_group < 0) {
@@ -902,7 +910,8 @@ void spr_moves_by_unique_id(const UTree &t, int64_t n_sel, const int64_t *sel, M
   }
 }
 
-void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_slots, SprDevicePlan &out) {
+void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_slots, SprDevicePlan &out,
+                             int64_t lo, int64_t hi) {
   DirOrder d = dir_order(t);
   std::vector<int> dir_slot;
   emit_dir_program(t, d, tip_rows, n_tip_slots, out.base, dir_slot);
@@ -910,11 +919,15 @@ void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_
   FitchProgram &prog = out.base.prog;
   prog.spr_first_acc = (int)out.base.first_move_acc;
   static thread_local SprSearchLayout lay;
-  layout_spr_searches(t, d, dir_slot, lay);
+  layout_spr_searches(t, d, dir_slot, lay, lo, hi);
   out.search_edge = lay.search_edge;
   out.search_uniq = lay.search_uniq;
   out.n_visits = lay.n_visits;
   out.n_unique = lay.n_unique;
+  out.lo = std::max<int64_t>(0, lo);
+  out.hi = std::min<int64_t>(hi, lay.n_unique);
+  prog.spr_lo = out.lo;
+  prog.spr_hi = out.hi;
   prog.spr_edges.resize(lay.edges.size());
   std::copy(lay.edges.begin(), lay.edges.end(), prog.spr_edges.data());
   prog.spr_searches.resize(lay.searches.size());
@@ -923,17 +936,22 @@ void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_
   std::copy(lay.groups.begin(), lay.groups.end(), prog.walk_groups.data());
   prog.spr_n_visits = out.n_visits;
   prog.spr_n_unique = out.n_unique;
-  prog.n_costs = out.base.first_move_acc + out.n_unique;
+  prog.n_costs = out.base.first_move_acc + (out.hi - out.lo);
   // byte accounting of the walk launch (run_fitch_program): a scored neighbour = fold + 3-way join
-  // (6 vectors); a repeated distance-1 move still folds when the search continues below it
-  prog.spr_vecs = 6.0 * (double)out.n_unique + 3.0 * (double)lay.dup_internal;
+  // (6 vectors); a repeated distance-1 move still folds when the search continues below it (exact for
+  // a whole neighbourhood; in a shard the unscored moves of its two border searches are taken to
+  // continue half of the time)
+  const bool whole = out.lo == 0 && out.hi == lay.n_unique;
+  prog.spr_vecs = 6.0 * (double)(out.hi - out.lo) +
+                  (whole ? 3.0 * (double)lay.dup_internal : 1.5 * (double)lay.unscored);
   prog.spr_req_vecs = (double)lay.groups.size() + 2.0 * (double)out.n_visits + (double)lay.n_started;
 }
 
 // Likelihood twin of prepare_spr_device_plan: directional CLV updates of the base tree as level
 // ops, P-matrix ids of every branch (whole, halved) and of the three merged branches around every
 // internal node, and the records spr_lik_plan_kernel (lik.cu) expands into LikWalkVisits.
-void build_lik_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_rows, LikProgram &prog) {
+void build_lik_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_rows, LikProgram &prog, int64_t lo,
+                               int64_t hi) {
   prog.clear();
   DirOrder d = dir_order(t);
   std::vector<int> dir_slot((size_t)t.n_nodes * 3, -1);
@@ -963,7 +981,9 @@ void build_lik_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_ro
   }
   prog.n_slots = slots;
   static thread_local SprSearchLayout lay;
-  layout_spr_searches(t, d, dir_slot, lay);
+  layout_spr_searches(t, d, dir_slot, lay, lo, hi);
+  prog.spr_lo = std::max<int64_t>(0, lo);
+  prog.spr_hi = std::min<int64_t>(hi, lay.n_unique);
   prog.spr_edges.resize(lay.edges.size());
   for (size_t e = 0; e < lay.edges.size(); e++) {
     const SprEdgeRec &r = lay.edges[e];
@@ -996,7 +1016,7 @@ void build_lik_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_ro
   }
   prog.spr_n_visits = lay.n_visits;
   prog.spr_n_unique = lay.n_unique;
-  prog.n_trees = lay.n_unique;
+  prog.n_trees = prog.spr_hi - prog.spr_lo;
   int lv = 1;
   while ((1 << lv) < t.n_tips) lv++;
   prog.walk_levels = lv + 1;  // the walk parks the larger side: depth <= log2(visits of a search) + 1
@@ -1017,8 +1037,8 @@ void finish_fitch_spr_plan(const UTree &t, const SprDevicePlan &p, const int32_t
       const int e = p.search_edge[s], u = e / 3, k = e % 3, v = t.nb[u][k];
       // length(T') = length(pruned subtree) + length(rest) + [their state sets miss at the new edge]
       const uint32_t parts = total[e] + (t.is_tip(v) ? 0u : total[3 * v + t.slot_of(v, u)]);
-      for (int64_t i = p.search_uniq[s]; i < p.search_uniq[s + 1]; i++)
-        out_costs[i] = (int32_t)(parts + (uint32_t)acc[p.base.first_move_acc + i]);
+      for (int64_t i = std::max(p.search_uniq[s], p.lo); i < std::min(p.search_uniq[s + 1], p.hi); i++)
+        out_costs[i] = (int32_t)(parts + (uint32_t)acc[p.base.first_move_acc + (i - p.lo)]);
     }
   });
 }

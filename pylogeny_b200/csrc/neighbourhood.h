@@ -112,14 +112,19 @@ struct SprDevicePlan {
   std::vector<int> search_edge;      // per search: pruned directed edge 3*u+k
   std::vector<int64_t> search_uniq;  // per search: unique id of its first kept move; [n_search] = n_unique
   int64_t n_visits = 0, n_unique = 0;
+  int64_t lo = 0, hi = 0;            // the unique ids this plan scores (a shard), [0, n_unique) = all
 };
-void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_slots, SprDevicePlan &out);
-// Fitch length of every distinct neighbour from the downloaded accumulators (no move array).
+// [lo, hi): only searches that hold ids of the range are planned (shards of one neighbourhood).
+void prepare_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_tip_slots, SprDevicePlan &out,
+                             int64_t lo = 0, int64_t hi = INT64_MAX);
+// Fitch length of the distinct neighbours [lo, hi) from the downloaded accumulators (no move array);
+// out_costs is indexed by neighbour.
 void finish_fitch_spr_plan(const UTree &t, const SprDevicePlan &p, const int32_t *acc, int32_t *out_costs);
 
 // Likelihood twin: level ops of the base tree + the records spr_lik_plan_kernel expands (full SPR
 // neighbourhood, all distinct neighbours; prog.n_trees = their number).
-void build_lik_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_rows, LikProgram &prog);
+void build_lik_spr_device_plan(const UTree &t, const int32_t *tip_rows, int n_rows, LikProgram &prog,
+                               int64_t lo = 0, int64_t hi = INT64_MAX);
 
 // lnL of the distinct neighbours [lo, hi) of an enumerated SPR/NNI neighbourhood (nb_api.cpp).
 void score_spr_lik(LikAln &a, Model &m, const Neighbourhood &nb, const int32_t *tip_rows, int64_t lo, int64_t hi,

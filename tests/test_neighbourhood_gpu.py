@@ -224,6 +224,12 @@ def test_fitch_device_planned_spr_equals_host_planner(n, P, shape, monkeypatch):
     assert got["device"][0].tolist() == got["host"][0].tolist()
     assert got["device"][1].tolist() == got["host"][1].tolist()
     monkeypatch.setenv("PLG_FITCH_NB_PLAN", "device")
+    M = len(got["device"][1])
+    for count in (2, 7):
+        parts = [nbh.score_parsimony(a, d, perm, shard=(i, count)) for i in range(count)]
+        merged = np.concatenate([parts[i][1][M * i // count: M * (i + 1) // count] for i in range(count)])
+        assert merged.tolist() == got["device"][1].tolist(), count
+        assert all(p[0].tolist() == got["device"][0].tolist() for p in parts)
     descs, _, _ = nbh.neighbour_trees(d)
     assert a.score_trees(descs, perm).tolist() == got["device"][1].tolist()
     a.close()
@@ -260,6 +266,15 @@ def test_lnl_device_planned_spr_equals_host_planner(n, P, monkeypatch):
     assert got["device"][0].tolist() == got["host"][0].tolist()
     assert got["device"][1].tolist() == got["host"][1].tolist()  # bit-identical
     assert acct["device"] == pytest.approx(acct["host"], rel=1e-12)
+    # shards of the neighbourhood: each plans and walks only the searches that hold its ids
+    M = len(got["device"][1])
+    for count in (2, 5):
+        for plan in ("device", "host"):
+            monkeypatch.setenv("PLG_LIK_NB_PLAN", plan)
+            parts = [nbh.score_likelihood(a, m, d, br, perm, shard=(i, count)) for i in range(count)]
+            merged = np.concatenate([parts[i][1][M * i // count: M * (i + 1) // count] for i in range(count)])
+            assert merged.tolist() == got["device"][1].tolist(), (plan, count)
+            assert all(p[0].tolist() == got["device"][0].tolist() for p in parts)   # the move table is whole in every shard
     a.close(); m.close()
 
 
