@@ -387,6 +387,42 @@ def run_ours(args):
                             "peak_source": "measured DMMA m8n8k4 (profiles/micro/fp64_peak.cu)",
                             "flop_per_unit": 640}
     roofline["other_kernels"] = [r for r in (roof(k) for k in prof if k != dom) if r]
+    sharded = None
+    if world > 1:
+        # north_star (4), literally: ONE neighbourhood -- the target shape, 256 taxa x 100k sites, all
+        # 255,530 SPR neighbours by GTR+G4 -- sharded across the ranks (each plans and walks only the
+        # searches that hold its block of neighbours), scores combined over NCCL.  Strong scaling.
+        n2, s2 = 256, 100_000
+        rng2 = np.random.default_rng(1002)
+        codes2 = (1 << rng2.integers(0, 4, (n2, s2))).astype(np.uint8)
+        la2 = likelihood.LikAlignment(codes2, np.ones(s2))
+        d2 = random_desc(np.random.default_rng(1002 + 7919), n2)
+        br2 = np.random.default_rng(1002 + 7920).exponential(0.1, d2.shape)
+        M2 = nbh.neighbourhood_size(d2)
+        buf = torch.zeros(M2, dtype=torch.float64, device=dev)
+
+        def shard_step():
+            _, part = nbh.score_likelihood(la2, model, d2, br2, shard=(rank, world), want_moves=False)
+            lo, hi = M2 * rank // world, M2 * (rank + 1) // world
+            buf.zero_()
+            buf[lo:hi] = torch.from_numpy(part[lo:hi]).to(dev)
+            dist.all_reduce(buf)  # disjoint blocks: the sum is the concatenation
+            return buf
+
+        shard_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res2 = shard_step()
+        e1.record()
+        torch.cuda.synchronize()
+        t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        sharded = {"workload": "ONE SPR neighbourhood sharded across the ranks: synthetic DNA 256 taxa x 100k sites, "
+                               "GTR+G4 lnL of all %d neighbours" % M2,
+                   "value": M2 * s2 / (float(t2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t2.item()),
+                   "scaling": "strong", "checksum": float(res2.sum().item())}
+        la2.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -398,6 +434,8 @@ def run_ours(args):
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
            "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
            "wall_s_timed_region": wall, "trees_per_step": world * M}
+    if sharded:
+        out["one_neighbourhood_sharded"] = sharded
 
     # e2e: same metric through the public API with HOST buffers; the alignment goes up and the
     # scores come down inside the timed region, every step
