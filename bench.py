@@ -10,9 +10,10 @@ the hot path over that batch: plan (host) + score (device) + read back the per-t
 At N > 1 the job is the pooled neighbour-tree list of N such neighbourhoods (base trees seeded
 1001+b): N x 14,762 trees, sharded across the ranks in contiguous blocks (rank r scores block r
 = the neighbours of base tree r; full alignment on every GPU, no data-path collective) and the
-per-tree scores come back through one NCCL all-gather -- weak scaling.  (Splitting ONE
-neighbourhood across ranks is also supported -- shard=(rank, world) in the C-ABI, tested in
-tests/test_neighbourhood_gpu.py -- and is what a single hill-climb would use.)
+per-tree scores come back through one NCCL all-gather -- weak scaling.  Splitting ONE
+neighbourhood across ranks (shard=(rank, world) in the C-ABI: each rank plans and walks only its
+block of neighbours) is measured too at N > 1, on the north_star target shape (256 taxa x 100k
+sites, all 255,530 SPR neighbours): the "one_neighbourhood_sharded" object, strong scaling.
 
 One JSON line on stdout (rank 0).  Extra objects: "roofline" (dominant kernel, CUDA-event timed
 inside the timed region), "cpu_baseline" (CPU oracle on a bounded sample of the same workload),
