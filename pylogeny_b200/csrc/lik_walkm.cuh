@@ -49,6 +49,9 @@ static_assert(WM_NG == 4 || WM_NG == 2, "a warp carries 32 or 16 patterns");
 #define PLG_WM_STAGE 0     // 1: the far-side operands of the NEXT visit are fetched by cp.async into shared memory during this one
                            //    (B200: 9.2 vs 7.9 ms -- 209 KB of shared memory leave no L1 for the spills and fragments)
 #endif
+#ifndef PLG_WM_EARLY2
+#define PLG_WM_EARLY2 0     // 1: the second operand loaded before the first one is multiplied out: 5.72 vs 5.59 ms
+#endif
 #ifndef PLG_WM_FUSE2
 #define PLG_WM_FUSE2 0     // 1: the D2 stage and neighbour chain 2 in one straight-line loop (h2 never a vector): 5.76 vs 5.58 ms
 #endif
@@ -388,6 +391,13 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
         for (int i = 0; i < WM_V; i++) ak[i] = stk[(lvl * WM_V + i) * 32];
         sk = stks[lvl * WM_NG * 32];
       }
+#if PLG_WM_EARLY2 && !PLG_WM_STAGE
+      // the second operand's loads are issued before the first one's products: __syncwarp() and the
+      // rescale vote keep the compiler from hoisting them itself
+      double x2e[WM_V];
+      int s2e;
+      wm_load_raw(d2, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x2e, s2e);
+#endif
       // D1 once: N2 = a o P_t1 D1 (the partial toward d2) and h1 = P_h1 D1 (far side of edge 1)
       double n2[WM_V];
       int s1, sc2;
@@ -456,7 +466,13 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
           asm volatile("cp.async.commit_group;\n" ::);
         }
 #else
+#if PLG_WM_EARLY2
+#pragma unroll
+        for (int i = 0; i < WM_V; i++) x[i] = x2e[i];
+        s2 = s2e;
+#else
         wm_load_raw(d2, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, s2);
+#endif
 #if PLG_WM_PF
         if (vi + 1 < v_end) {
           wm_prefetch(__shfl_sync(0xffffffffu, dnxt, 2), n_rows, Ppad, p0, lane, codes, clv, scl);
