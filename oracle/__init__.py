@@ -2,7 +2,7 @@
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import this package; nothing under ``pylogeny_b200/``
-does (tests/test_boundary_cpu.py greps for it).
+does (tests/test_host_cpu.py::test_product_never_touches_the_oracle greps for it).
 
 * ``fitch_cost``      -- plain-C restatement of /root/reference/pylogeny/fitch.cpp
                          (oracle/fitch_oracle.c); parity pinned by tests/golden/.
