@@ -263,9 +263,9 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
   const int depth = depth_for(move_type);
   const char *mode_env = std::getenv("PLG_FITCH_NB_MODE");
   const bool walk = !(mode_env && !strcmp(mode_env, "ops")) && n_tips <= (1 << WALK_MAX_LEVELS);
-  // A whole SPR neighbourhood on one device: the host prepares O(n) records and the search walks
-  // are laid out by spr_plan_kernel (PLG_FITCH_NB_PLAN=host keeps the host planner for A/B tests;
-  // shards, NNI and radius-limited searches use it too).
+  // Full-radius SPR neighbourhood (whole, or one shard of it): the host prepares O(n) records and
+  // the search walks are laid out by spr_plan_kernel (PLG_FITCH_NB_PLAN=host keeps the host planner
+  // for A/B tests; NNI and radius-limited searches use it too).
   const char *plan_env = std::getenv("PLG_FITCH_NB_PLAN");
   if (walk && depth < 0 && n_tips >= 4 && !(plan_env && !strcmp(plan_env, "host"))) {
     static thread_local SprDevicePlan plan;  // keeps its pinned staging across calls
@@ -348,8 +348,8 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
     return score_tbr_lik(a, m->impl, n_tips, desc, brlen, tip_rows, shard_index, shard_count, n_moves, out_moves,
                          out_lnl, (cudaStream_t)stream);
   const int depth = depth_for(move_type);
-  // A whole SPR neighbourhood on one device (DNA x Gamma-4 walks): O(n) host records, the search
-  // walks are laid out by spr_lik_plan_kernel (PLG_LIK_NB_PLAN=host keeps the host planner)
+  // Full-radius SPR neighbourhood, whole or one shard (DNA x Gamma-4 walks): O(n) host records, the
+  // search walks are laid out by spr_lik_plan_kernel (PLG_LIK_NB_PLAN=host keeps the host planner)
   const char *plan_env = std::getenv("PLG_LIK_NB_PLAN");
   if (out_lnl && depth < 0 && n_tips >= 4 && n_tips <= (1 << WALK_MAX_LEVELS) && a.K == 4 && m->impl.R == 4 &&
       lik_nb_mode() == LIK_NB_WALK && !(plan_env && !strcmp(plan_env, "host"))) {
