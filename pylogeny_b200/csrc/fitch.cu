@@ -24,6 +24,7 @@
 #include <numeric>
 
 #include "fitch.h"
+#include "hostpool.h"
 #include "treewalk.h"
 
 namespace plg {
@@ -687,7 +688,15 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
   }
   if (device_plan && out_moves) {
     PLG_CUDA(cudaStreamSynchronize(side.s));
-    memcpy(out_moves, ws.spr_moves_host.p, (size_t)prog.spr_n_unique * sizeof(int4));
+    // pinned staging -> the caller's (pageable) table, on the host cores when it is large
+    const size_t bytes = (size_t)prog.spr_n_unique * sizeof(int4);
+    const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(HostPool::get().size(), bytes >> 20));
+    const char *src = reinterpret_cast<const char *>(ws.spr_moves_host.p);
+    char *dst = reinterpret_cast<char *>(out_moves);
+    HostPool::get().run(n_thr, [&](int ti, int nt) {
+      const size_t b0 = bytes * ti / nt, b1 = bytes * (ti + 1) / nt;
+      memcpy(dst + b0, src + b0, b1 - b0);
+    });
   }
 }
 
