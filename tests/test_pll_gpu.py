@@ -321,3 +321,28 @@ def test_batched_getLogLikelihood_wag():
     for a, b in zip(opt, want_nw):
         np.testing.assert_allclose(nbh.newick_to_desc(a, taxa)[1], nbh.newick_to_desc(b, taxa)[1], rtol=1e-6, atol=1e-9)
     pm.close(); ali.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_batched_getLogLikelihood_no_signal_data(seed):
+    """Random sequences on few sites: flat or wrongly curved likelihood surfaces on many branches,
+    where makenewz's bad-curvature guard and the z clamps do the work.  Batch == per-tree path."""
+    from pylogeny_b200 import alignment, libpllWrapper as W, pll
+    rng = np.random.default_rng(100 + seed)
+    n, S = 10, int(rng.integers(8, 60))
+    seqs = ["".join("ACGT"[i] for i in rng.integers(0, 4, S)) for _ in range(n)]
+    if seed % 2:
+        seqs[3] = seqs[2]                      # identical sequences: a zero-length optimum (z -> zmax)
+    ali = alignment.phylipFriendlyAlignment(names=["r%d" % i for i in range(n)], seqs=seqs)
+    labels = ali.getTaxa()
+    newicks = [desc_to_newick(random_desc(rng, n), labels) for _ in range(9)]
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    want = []
+    for nw in newicks:
+        h = W.new(ali.getPhylip(), nw, pm.getFileName())
+        want.append(W.getLogLikelihood(h))
+        W.destroy(h)
+    got, _ = W.getLogLikelihoodBatch(ali.getPhylip(), newicks, pm.getFileName())
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    pm.close(); ali.close()
