@@ -167,3 +167,30 @@ def test_c5_protein_tbr_neighbourhood():
     _, _, h_all = nbh.neighbour_trees(d, br, None, nbh.MOVE_TBR)
     assert set(h_spr.tolist()) <= set(h_all.tolist())
     a.close(); m.close()
+
+
+def test_likelihood_climb_scan_then_batched_smoothing():
+    """Likelihood hill-climb with the reference's per-tree semantics: a fixed-length scan of the
+    whole SPR neighbourhood ranks it, the best few are smoothed in one batch.  The path increases
+    strictly, the final lnL is what one libpllWrapper handle returns for the final topology, and the
+    climb recovers (most of) the gap to the tree the data were simulated on."""
+    from pylogeny_b200 import alignment, libpllWrapper as W, neighbourhood as nbh, pll
+    from util import simulate_dna
+    rng = np.random.default_rng(77)
+    n, S = 16, 1500
+    true = random_desc(rng, n)
+    br = rng.exponential(0.07, true.shape) + 0.01
+    seqs = simulate_dna(rng, true, br, S, np.array([1.0, 3.0, 0.7, 1.3, 4.0, 1.0]), np.array([0.3, 0.2, 0.2, 0.3]))
+    ali = alignment.phylipFriendlyAlignment(names=["s%d" % i for i in range(n)], seqs=seqs)
+    labels = ali.getTaxa()
+    start = desc_to_newick(random_desc(rng, n), labels)
+    path, final = nbh.likelihood_greedy(ali, start, top=12, max_steps=6)
+    assert len(path) >= 3 and all(b > a for a, b in zip(path, path[1:]))
+    pm = ali._pllmodel
+    h = W.new(ali.getPhylip(), final, pm.getFileName())
+    again = W.getLogLikelihood(h)                       # same topology, smoothed again from z = 0.9
+    W.destroy(h)
+    assert abs(again - path[-1]) <= 1e-9 * abs(again)
+    (truth,), _ = W.getLogLikelihoodBatch(ali.getPhylip(), [desc_to_newick(true, labels)], pm.getFileName())
+    assert path[-1] > path[0] + 0.5 * (truth - path[0])  # at least half of the way to the generating tree
+    pm.close(); ali.close()
