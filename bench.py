@@ -253,7 +253,8 @@ def run_reference(args):
         cpu_lnl_sample(seconds=1.0)
     vals, times = [], []
     for _ in range(args.steps):
-        cb, dt, _ = cpu_lnl_sample(seconds=max(2.0, 40.0 / args.steps))
+        budget = float(os.environ.get("PLG_BENCH_REF_SECONDS", "40"))  # whole run, spread over the steps
+        cb, dt, _ = cpu_lnl_sample(seconds=max(min(2.0, budget), budget / args.steps))
         vals.append(cb["value"])
         times.append(dt)
     v = float(np.mean(vals))
