@@ -57,6 +57,11 @@ int plg_profile_enable(int on);
 int plg_profile_read(int kind, double *ms, double *bytes, double *units, int64_t *launches,
                      double *requested_bytes);
 
+/* FP64 pipe peak of the current device, measured now (CUDA events, best of three): mode 0 = DFMA on
+ * the CUDA cores, 1 = DMMA m8n8k4 (FP64 tensor instructions), 2 = both interleaved.  TFLOP/s.  The
+ * roofline denominator of the likelihood walk kernels (bench.py); not in MEASURED_PEAKS.json. */
+int plg_fp64_peak(int mode, double *tflops);
+
 /* ------------------------------------------------------------------ */
 /* Parsimony (replaces fitch.cpp)                                      */
 /* ------------------------------------------------------------------ */
@@ -145,6 +150,11 @@ void plg_lik_aln_destroy(plg_lik_aln *aln);
  * sets up at libpllWrapper.c:159. */
 int plg_model_create(int n_states, const double *exch, const double *freqs, double alpha,
                      int n_cat, plg_model **out);
+/* Built-in empirical protein models by the name a partition file carries (pll.py:102-115): "WAG",
+ * "JTT" (case-insensitive).  exch[190] (upper triangle, row-major, order ARNDCQEGHILKMFPSTWYV) and
+ * freqs[20] as plg_model_create takes them; PLG_ERR_UNSUPPORTED for other names.  Provenance of the
+ * tables: csrc/protein_models.cpp. */
+int plg_protein_model(const char *name, double *exch, double *freqs);
 void plg_model_destroy(plg_model *m);
 int plg_model_gamma_rates(const plg_model *m, double *rates /*[n_cat]*/);
 /* P(t) on the host from the model's eigensystem, row-major K*K (for tests). */

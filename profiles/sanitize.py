@@ -35,7 +35,7 @@ fa2 = fitch.FitchAlignment.from_dense(st2, np.ones(700, dtype=np.int64))
 d2 = random_desc(rng, n2); br2 = rng.exponential(0.1, d2.shape)
 codes2 = rng.integers(1, 16, (n2, 700)).astype(np.uint8)
 la2 = likelihood.LikAlignment(codes2, np.ones(700))
-for env, vals in (("PLG_TREE_MODE", ("walk", "levels")), ("PLG_LIK_NB_MODE", ("walkm", "walk", "visits", "ops")),
+for env, vals in (("PLG_TREE_MODE", ("walk", "levels")), ("PLG_LIK_NB_MODE", ("walkm", "ops")),
                   ("PLG_FITCH_NB_MODE", ("walk", "ops"))):
     for v in vals:
         os.environ[env] = v

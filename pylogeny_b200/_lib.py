@@ -45,50 +45,60 @@ def check(rc):
         raise EngineError(rc, lib().plg_last_error().decode(errors="replace"))
 
 
+def _set(L, name, attr, value):
+    """Declare one entry point; a library built before the entry existed (tuning variants) still loads,
+    and calling the missing entry raises AttributeError."""
+    fn = getattr(L, name, None)
+    if fn is not None:
+        setattr(fn, attr, value)
+
+
 def _declare(L):
     i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
     strs = C.POINTER(C.c_char_p)
     vp = C.c_void_p
-    L.plg_last_error.restype = C.c_char_p
-    L.plg_last_error.argtypes = []
-    L.plg_version.restype = C.c_int
-    L.plg_launch_count.restype = C.c_int64
-    L.plg_device_count.argtypes = [C.POINTER(C.c_int)]
-    L.plg_set_device.argtypes = [C.c_int]
-    L.plg_fitch_aln_create.argtypes = [C.c_int64, strs, i64p, C.POINTER(vp)]
-    L.plg_fitch_aln_create_dense.argtypes = [C.c_int64, C.c_int, vp, vp, C.POINTER(vp)]
-    L.plg_fitch_aln_destroy.argtypes = [vp]
-    L.plg_fitch_aln_destroy.restype = None
-    L.plg_fitch_aln_info.argtypes = [vp, i64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    L.plg_fitch_cost.argtypes = [C.c_char_p, C.c_int64, strs, i64p, C.c_int, strs, i32p, i32p]
-    L.plg_fitch_score_newicks.argtypes = [vp, C.c_int64, strs, C.c_int, strs, i32p, vp, vp]
-    L.plg_fitch_score_trees.argtypes = [vp, C.c_int64, C.c_int, vp, vp, vp, vp]
+    _set(L, 'plg_last_error', 'restype', C.c_char_p)
+    _set(L, 'plg_last_error', 'argtypes', [])
+    _set(L, 'plg_version', 'restype', C.c_int)
+    _set(L, 'plg_launch_count', 'restype', C.c_int64)
+    _set(L, 'plg_device_count', 'argtypes', [C.POINTER(C.c_int)])
+    _set(L, 'plg_set_device', 'argtypes', [C.c_int])
+    _set(L, 'plg_fitch_aln_create', 'argtypes', [C.c_int64, strs, i64p, C.POINTER(vp)])
+    _set(L, 'plg_fitch_aln_create_dense', 'argtypes', [C.c_int64, C.c_int, vp, vp, C.POINTER(vp)])
+    _set(L, 'plg_fitch_aln_destroy', 'argtypes', [vp])
+    _set(L, 'plg_fitch_aln_destroy', 'restype', None)
+    _set(L, 'plg_fitch_aln_info', 'argtypes', [vp, i64p, C.POINTER(C.c_int), C.POINTER(C.c_int)])
+    _set(L, 'plg_fitch_cost', 'argtypes', [C.c_char_p, C.c_int64, strs, i64p, C.c_int, strs, i32p, i32p])
+    _set(L, 'plg_fitch_score_newicks', 'argtypes', [vp, C.c_int64, strs, C.c_int, strs, i32p, vp, vp])
+    _set(L, 'plg_fitch_score_trees', 'argtypes', [vp, C.c_int64, C.c_int, vp, vp, vp, vp])
     dp = C.POINTER(C.c_double)
-    L.plg_lik_aln_create.argtypes = [C.c_int, C.c_int, C.c_int64, vp, vp, C.POINTER(vp)]
-    L.plg_lik_aln_destroy.argtypes = [vp]
-    L.plg_lik_aln_destroy.restype = None
-    L.plg_model_create.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, C.POINTER(vp)]
-    L.plg_model_destroy.argtypes = [vp]
-    L.plg_model_destroy.restype = None
-    L.plg_model_gamma_rates.argtypes = [vp, dp]
-    L.plg_model_pmatrix.argtypes = [vp, C.c_double, dp]
-    L.plg_lik_score_trees.argtypes = [vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp, vp]
+    _set(L, 'plg_lik_aln_create', 'argtypes', [C.c_int, C.c_int, C.c_int64, vp, vp, C.POINTER(vp)])
+    _set(L, 'plg_lik_aln_destroy', 'argtypes', [vp])
+    _set(L, 'plg_lik_aln_destroy', 'restype', None)
+    _set(L, 'plg_model_create', 'argtypes', [C.c_int, dp, dp, C.c_double, C.c_int, C.POINTER(vp)])
+    _set(L, 'plg_protein_model', 'argtypes', [C.c_char_p, dp, dp])
+    _set(L, 'plg_fp64_peak', 'argtypes', [C.c_int, dp])
+    _set(L, 'plg_model_destroy', 'argtypes', [vp])
+    _set(L, 'plg_model_destroy', 'restype', None)
+    _set(L, 'plg_model_gamma_rates', 'argtypes', [vp, dp])
+    _set(L, 'plg_model_pmatrix', 'argtypes', [vp, C.c_double, dp])
+    _set(L, 'plg_lik_score_trees', 'argtypes', [vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp, vp])
     u64p = C.POINTER(C.c_uint64)
-    L.plg_neighbourhood_size.argtypes = [C.c_int, C.c_int, vp, i64p]
-    L.plg_neighbourhood_trees.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, vp]
-    L.plg_topology_hash.argtypes = [C.c_int, vp, vp, u64p]
-    L.plg_fitch_score_neighbourhood.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int64, C.c_int64, i64p, vp, vp, vp]
-    L.plg_lik_score_neighbourhood.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, i64p, vp,
-                                              vp, vp]
-    L.plg_profile_enable.argtypes = [C.c_int]
-    L.plg_profile_read.argtypes = [C.c_int, dp, dp, dp, i64p, dp]
-    L.plg_pll_new.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(vp)]
-    L.plg_pll_destroy.argtypes = [vp]
-    L.plg_pll_loglik.argtypes = [vp, dp]
-    L.plg_pll_evaluate.argtypes = [vp, dp]
-    L.plg_pll_newick.argtypes = [vp, C.c_char_p, C.POINTER(C.c_size_t)]
-    L.plg_pll_moves_compute.argtypes = [vp, C.c_int, C.c_int, i64p, C.POINTER(C.c_size_t)]
-    L.plg_pll_moves_fetch.argtypes = [vp, vp, vp, vp, C.c_size_t]
-    L.plg_pll_info.argtypes = [vp, C.POINTER(C.c_int), i64p, dp, dp]
-    L.plg_pll_loglik_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, strs, C.c_int, vp, C.POINTER(C.c_size_t)]
-    L.plg_pll_batch_newicks.argtypes = [C.c_char_p, C.c_size_t]
+    _set(L, 'plg_neighbourhood_size', 'argtypes', [C.c_int, C.c_int, vp, i64p])
+    _set(L, 'plg_neighbourhood_trees', 'argtypes', [C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, vp])
+    _set(L, 'plg_topology_hash', 'argtypes', [C.c_int, vp, vp, u64p])
+    _set(L, 'plg_fitch_score_neighbourhood', 'argtypes', [vp, C.c_int, C.c_int, vp, vp, C.c_int64, C.c_int64, i64p, vp, vp, vp])
+    _set(L, 'plg_lik_score_neighbourhood', 'argtypes',
+         [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, i64p, vp, vp, vp])
+    _set(L, 'plg_profile_enable', 'argtypes', [C.c_int])
+    _set(L, 'plg_profile_read', 'argtypes', [C.c_int, dp, dp, dp, i64p, dp])
+    _set(L, 'plg_pll_new', 'argtypes', [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(vp)])
+    _set(L, 'plg_pll_destroy', 'argtypes', [vp])
+    _set(L, 'plg_pll_loglik', 'argtypes', [vp, dp])
+    _set(L, 'plg_pll_evaluate', 'argtypes', [vp, dp])
+    _set(L, 'plg_pll_newick', 'argtypes', [vp, C.c_char_p, C.POINTER(C.c_size_t)])
+    _set(L, 'plg_pll_moves_compute', 'argtypes', [vp, C.c_int, C.c_int, i64p, C.POINTER(C.c_size_t)])
+    _set(L, 'plg_pll_moves_fetch', 'argtypes', [vp, vp, vp, vp, C.c_size_t])
+    _set(L, 'plg_pll_info', 'argtypes', [vp, C.POINTER(C.c_int), i64p, dp, dp])
+    _set(L, 'plg_pll_loglik_batch', 'argtypes', [C.c_char_p, C.c_char_p, C.c_int64, strs, C.c_int, vp, C.POINTER(C.c_size_t)])
+    _set(L, 'plg_pll_batch_newicks', 'argtypes', [C.c_char_p, C.c_size_t])

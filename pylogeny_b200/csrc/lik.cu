@@ -245,18 +245,10 @@ __global__ void reduce_partials_kernel(int n_trees, int blocks_per_eval, const d
 
 }  // namespace plg
 #include "lik_dna.cuh"
-#ifndef PLG_DNA4_WARP_PER_RATE
-#define PLG_DNA4_WARP_PER_RATE 0
-#endif
-#ifndef PLG_VISIT_TMA
-#define PLG_VISIT_TMA 0  // 1: visit4_kernel (TMA landing zone); 0: visit4b_kernel (parked shared vectors)
-#endif
 namespace plg {
-constexpr int DNA4_PATTERNS_PER_BLOCK = PLG_DNA4_WARP_PER_RATE ? R4_PATTERNS : D4_THREADS;
+constexpr int DNA4_PATTERNS_PER_BLOCK = D4_THREADS;
 }
 #include "lik_aa.cuh"
-#include "lik_visit.cuh"
-#include "lik_walk.cuh"
 #include "lik_walkm.cuh"
 #include "lik_twalk.cuh"
 namespace plg {
@@ -331,8 +323,6 @@ LikWorkspace &lik_workspace() {
 }
 
 void LikProgram::clear() {
-  visits.clear();
-  visit_level_off.clear();
   walk_visits.clear();
   walk_groups.clear();
   walk_levels = 0;
@@ -603,7 +593,7 @@ spr_lik_plan_kernel(const int4 *__restrict__ edges_g, int n_edge_int4, const int
 
 // DNA x Gamma-4 path: thread-per-pattern kernels, evaluations fused into the CLV update that
 // produces their first operand whenever the other operands are ready by then.
-static int64_t dna4_partial_stride(const LikAln &a) { return a.Ppad / (PLG_DNA4_WARP_PER_RATE ? R4_PATTERNS : D4_THREADS); }
+static int64_t dna4_partial_stride(const LikAln &a) { return a.Ppad / D4_THREADS; }
 
 static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const LikProgram &prog, cudaStream_t st,
                      int32_t *out_moves) {
@@ -667,14 +657,15 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   tm.lap("    fuse+upload");
   const int64_t bpo = a.Ppad / DNA4_PATTERNS_PER_BLOCK;
   // finest block tiling among the kernels below (search walks reduce per 32-pattern slice)
-  // PLG_LIK_NB_MODE=walk: scalar FP64 walk (lik_walk.cuh); default: the DMMA walk (lik_walkm.cuh)
-  const char *mode_env = getenv("PLG_LIK_NB_MODE");
-  const bool dmma = !(mode_env && !strcmp(mode_env, "walk"));
-  const int walk_patterns = dmma ? WM_PATTERNS : 32;
+  const int walk_patterns = WM_PATTERNS;
   const bool device_plan = prog.spr_n_visits > 0;
   const bool walks = device_plan || !prog.walk_visits.empty();
   const int64_t pstride = !walks ? dna4_partial_stride(a) : a.Ppad / walk_patterns;
   if (prog.n_trees) PLG_CUDA(cudaMemsetAsync(ws.partial.p, 0, (size_t)prog.n_trees * pstride * 8, st));
+  if (prog.n_trees && walks) {  // (mantissa, exponent) records of the walk: untouched entries read as the finished sum 0
+    ws.partial_e.alloc((size_t)prog.n_trees * pstride);
+    PLG_CUDA(cudaMemsetAsync(ws.partial_e.p, 0x80, (size_t)prog.n_trees * pstride * 4, st));
+  }
   const double Cb = (double)R * K * 8.0 + 4.0;
   auto opnd = [&](int id) { return id < 0 ? 0.0 : (id < a.n_rows ? 1.0 : Cb); };
   const LikOpF *d_ops = reinterpret_cast<const LikOpF *>(ws.fops.p);
@@ -697,15 +688,9 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
         }
       }
       prof_begin(PROF_CLV_UPDATE, st);
-#if PLG_DNA4_WARP_PER_RATE
-      clv4r_kernel<<<(unsigned)(c * bpo), R4_THREADS, 0, st>>>(d_ops + o0 + o, (int)bpo, a.n_rows, a.Ppad, a.codes.p,
-                                                              a.masks.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
-                                                              ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
-#else
       clv4_kernel<<<(unsigned)(c * bpo), D4_THREADS, 0, st>>>(d_ops + o0 + o, (int)bpo, a.n_rows, a.Ppad, a.codes.p,
                                                              a.masks.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
                                                              ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
-#endif
       count_launch();
       prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, (double)c * (double)a.P, req * (double)a.P);
     }
@@ -724,48 +709,14 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     count_launch();
     prof_end(PROF_ROOT_EVAL, st, bytes * (double)a.P, (double)c * (double)a.P);
   }
-  // search-step visits (two neighbours per step, operands staged once by the TMA)
-  if (!prog.visits.empty()) {
-    static bool attr_set[64] = {false};
-    ensure_dyn_smem(visit4_kernel, V4_SMEM_BYTES, attr_set);
-    ws.visits.alloc(prog.visits.size());
-    PLG_CUDA(cudaMemcpyAsync(ws.visits.p, prog.visits.data(), prog.visits.size() * sizeof(LikVisit),
-                             cudaMemcpyHostToDevice, st));
-    const int64_t vbpo = a.Ppad / V4_THREADS;
-    for (size_t l = 0; l + 1 < prog.visit_level_off.size(); l++) {
-      const int64_t v0 = prog.visit_level_off[l], cnt = prog.visit_level_off[l + 1] - v0;
-      if (!cnt) continue;
-      double bytes = 0, req = 0;
-      for (int64_t q = v0; q < v0 + cnt; q++) {
-        const LikVisit &v = prog.visits[q];
-        req += opnd(v.x_in) + opnd(v.tv) + opnd(v.d1) + opnd(v.d2) + (v.n1 >= 0 ? Cb : 0.0) + (v.n2 >= 0 ? Cb : 0.0) +
-               (v.tree1 >= 0 ? 8.0 : 0.0) + (v.tree2 >= 0 ? 8.0 : 0.0);
-        // per neighbour: one CLV update (result + 2 operands) and, if scored, one 3-way evaluation
-        if (v.n1 >= 0 || v.tree1 >= 0) bytes += Cb + opnd(v.x_in) + opnd(v.d2) + (v.tree1 >= 0 ? Cb + opnd(v.d1) + opnd(v.tv) + 8.0 : 0.0);
-        if (v.n2 >= 0 || v.tree2 >= 0) bytes += Cb + opnd(v.x_in) + opnd(v.d1) + (v.tree2 >= 0 ? Cb + opnd(v.d2) + opnd(v.tv) + 8.0 : 0.0);
-      }
-      prof_begin(PROF_CLV_UPDATE, st);
-#if PLG_VISIT_TMA
-      visit4_kernel<<<(unsigned)(cnt * vbpo), V4_THREADS, V4_SMEM_BYTES, st>>>(
-          ws.visits.p + v0, (int)vbpo, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
-          ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
-#else
-      visit4b_kernel<<<(unsigned)(cnt * vbpo), VB_THREADS, 0, st>>>(
-          ws.visits.p + v0, (int)vbpo, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p,
-          ws.clv.p, ws.scl.p, ws.partial.p, (int)pstride);
-#endif
-      count_launch();
-      prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, 2.0 * (double)cnt * (double)a.P, req * (double)a.P);
-    }
-  }
   tm.lap("    level launches");
   // depth-first search walks: one persistent launch, a warp per (pattern slice, pruned subtree)
   if (walks) {
     int dev = 0, n_sm = 148;
     PLG_CUDA(cudaGetDevice(&dev));
     PLG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const int n_blocks = n_sm * (dmma ? PLG_WM_MINB : PLG_WK_MINB);
-    const int64_t n_warps = (int64_t)n_blocks * (dmma ? WM_WARPS : WK_WARPS);
+    const int n_blocks = n_sm * PLG_WM_MINB;
+    const int64_t n_warps = (int64_t)n_blocks * WM_WARPS;
     const int levels = std::max(1, prog.walk_levels);
     ws.walk_visits.alloc(device_plan ? (size_t)prog.spr_n_visits : prog.walk_visits.size());
     ws.walk_groups.alloc(prog.walk_groups.size());
@@ -829,31 +780,27 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     }
     const int64_t n_items = (a.Ppad / walk_patterns) * (int64_t)prog.walk_groups.size();
     prof_begin(PROF_WALK, st);
-    if (dmma) {
+    {
       const int smem = WM_WARPS * WM_SMEM_DOUBLES_PER_WARP * 8;
       static bool wm_attr_set[64] = {false};
       ensure_dyn_smem(walk4m_kernel, smem, wm_attr_set);
       walk4m_kernel<<<n_blocks, WM_THREADS, smem, st>>>(ws.walk_groups.p, (int)prog.walk_groups.size(), ws.walk_visits.p,
                                                        n_items, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p,
                                                        ws.pmat.p, ws.clv.p, ws.scl.p, ws.walk_stack.p,
-                                                       ws.walk_stack_scl.p, levels, ws.partial.p, (int)pstride,
-                                                       ws.walk_counter.p);
-    } else {
-      static bool walk_attr_set[64] = {false};
-      ensure_dyn_smem(walk4_kernel, WK_SMEM_BYTES, walk_attr_set);
-      walk4_kernel<<<n_blocks, WK_THREADS, WK_SMEM_BYTES, st>>>(ws.walk_groups.p, (int)prog.walk_groups.size(),
-                                                               ws.walk_visits.p, n_items, a.n_rows, a.Ppad, a.codes.p,
-                                                               a.weights.p, m.d.p, ws.pmat.p, ws.tiptab.p, ws.clv.p,
-                                                               ws.scl.p, ws.walk_stack.p, ws.walk_stack_scl.p, levels,
-                                                               ws.partial.p, (int)pstride, ws.walk_counter.p);
+                                                       ws.walk_stack_scl.p, levels, ws.partial.p, ws.partial_e.p,
+                                                       (int)pstride, ws.walk_counter.p);
     }
     count_launch();
     prof_end(PROF_WALK, st, bytes * (double)a.P, units * (double)a.P, req * (double)a.P);
     tm.lap("    walk launch");
   }
   if (prog.n_trees) {
-    reduce_partials_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, (int)pstride,
-                                                                               ws.partial.p, ws.lnl.p);
+    if (walks)
+      reduce_me_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, (int)pstride, ws.partial.p,
+                                                                           ws.partial_e.p, ws.lnl.p);
+    else
+      reduce_partials_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, (int)pstride,
+                                                                                 ws.partial.p, ws.lnl.p);
     count_launch();
   }
 }
@@ -955,7 +902,7 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   const bool dna4 = (a.K == 4 && m.R == 4);
   const int64_t bpo = !dna4 ? a.Ppad / (LIK_THREADS / m.R)
                              : (prog.walk_visits.empty() && prog.spr_n_visits == 0 ? dna4_partial_stride(a)
-                                                                                    : a.Ppad / 16);  // finest walk slicing
+                                                                                    : a.Ppad / WM_PATTERNS);  // walk slicing
   ws.partial.alloc(std::max<size_t>(1, (size_t)prog.n_trees * (size_t)bpo));
   ws.lnl.alloc(std::max<size_t>(1, (size_t)prog.n_trees));
   if (!dna4 && !prog.ops.empty())

@@ -26,13 +26,7 @@ struct LikOpF {
   int pad;                           // 1: do not store dst (no reader)
 };
 
-// One search step of the SPR edge-insertion walk scoring both neighbours at the node it reaches
-// (DNA x Gamma-4 path, csrc/lik_visit.cuh).  Operand ids as in LikOp; 64 bytes.
-struct LikVisit {
-  int x_in, p_in, tv, p_v, d1, p_t1, p_h1, d2, p_t2, p_h2, n1, n2, tree1, tree2, pad0, pad1;
-};
-
-// Depth-first SPR search walks (csrc/lik_walk.cuh).  One group = one pruned subtree (both sides
+// Depth-first SPR search walks (csrc/lik_walkm.cuh).  One group = one pruned subtree (both sides
 // of the pruning point); its visits are listed in the order one warp executes them.
 //   x_in >= 0: the incoming partial is a stored operand (first step of a side); -1: it is the
 //   partial the previous visit kept in registers; <= -2: pop it from stack level (-2 - x_in).
@@ -66,7 +60,6 @@ struct LikWorkspace {
   DevBuf<double> brlen;    // [pm]
   DevBuf<LikOp> ops;
   DevBuf<char> fops;       // LikOpF[] (DNA x Gamma-4 path: updates with fused evaluations)
-  DevBuf<LikVisit> visits;
   DevBuf<LikWalkVisit> walk_visits;
   DevBuf<LikWalkGroup> walk_groups;
   DevBuf<double> walk_stack;   // [warp][level][16][32]
@@ -81,6 +74,7 @@ struct LikWorkspace {
   DevBuf<int32_t> tw_rows;
   DevBuf<LikEval> evals;
   DevBuf<double> partial;  // [eval][blocks]
+  DevBuf<int> partial_e;   // [eval][slices] exponents of the search walks' (mantissa, exponent) records
   DevBuf<double> lnl;      // [tree]
 };
 
@@ -100,8 +94,6 @@ struct LikProgram {
   std::vector<LikOp> ops;          // sorted by level
   std::vector<int64_t> level_off;  // [n_levels+1]
   std::vector<LikEval> evals;
-  std::vector<LikVisit> visits;           // sorted by level; run after every op level
-  std::vector<int64_t> visit_level_off;   // [n_visit_levels+1]
   std::vector<LikWalkVisit> walk_visits;  // depth-first search walks, run after the op levels
   std::vector<LikWalkGroup> walk_groups;  // longest first
   int walk_levels = 0;                    // stack levels a walk needs

@@ -16,9 +16,6 @@ namespace plg {
 
 // Block size / residency chosen by the sweep in profiles/tune_d4.sh (B200, 64 taxa x 10k sites):
 // 128 x {5,6,7} blocks per SM plateau at ~5.1 TB/s algorithmic; 4 blocks (128 registers) gives 4.6.
-#ifndef PLG_D4_PREFETCH
-#define PLG_D4_PREFETCH 0
-#endif
 #ifndef PLG_D4_THREADS
 #define PLG_D4_THREADS 128
 #endif
@@ -139,20 +136,6 @@ clv4_kernel(const LikOpF *__restrict__ ops, int blocks_per_op, int n_rows, int64
   const int pb = blockIdx.x - op_idx * blocks_per_op;
   const LikOpF op = ops[op_idx];
   const int64_t p = (int64_t)pb * D4_THREADS + threadIdx.x;
-#if PLG_D4_PREFETCH
-  // Later operands are fetched after dependent compute phases; start pulling their lines now.
-  {
-    auto pf = [&](int id) {
-      if (id >= n_rows && (threadIdx.x & 15) == 0) {
-        const double *src = clv + (int64_t)(id - n_rows) * 16 * Ppad + p;
-#pragma unroll
-        for (int i = 0; i < 16; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (int64_t)i * Ppad));
-      }
-    };
-    if (op.b >= 0) pf(op.b);
-    if (op.tree >= 0) { pf(op.e_b); pf(op.e_c); }
-  }
-#endif
   d4_stage(smA, op.a < n_rows, op.pa, pmat, tiptab);
   if (op.b >= 0) d4_stage(smB, op.b < n_rows, op.pb, pmat, tiptab);
   if (op.tree >= 0) {
@@ -210,133 +193,6 @@ eval4_kernel(const LikEval *__restrict__ evals, int blocks_per_eval, int n_rows,
   d4_operand<true>(sm[1], ev.b, ev.pb, n_rows, p, Ppad, codes, masks, clv, scl, v, sc);
   if (ev.c >= 0) d4_operand<true>(sm[2], ev.c, ev.pc, n_rows, p, Ppad, codes, masks, clv, scl, v, sc);
   d4_site_sum(v, sc, p, weights, model, warp_sums, partial + (int64_t)ev.tree * pstride + pb);
-}
-
-}  // namespace plg
-
-// ---------------------------------------------------------------------------------------------
-// Warp-per-category formulation of the same fused op: block = 4 warps = the 4 Gamma categories of
-// 32 patterns, a thread owns the 4 states of ONE category.  Four times as many, four times lighter
-// threads than clv4_kernel (thread = 16 entries, 80+ registers, 24 warps/SM): ncu showed that one
-// latency-bound (issue slots 40 % active, long- and short-scoreboard stalls), not HBM-bound, so
-// the lever is thread-level parallelism.  P rows come straight from L1 as warp-uniform loads (no
-// shared-memory staging, no barrier before the first global load); only the cross-category
-// maximum (rescaling) and the cross-category site sum go through shared memory.
-namespace plg {
-
-constexpr int R4_THREADS = 128;
-constexpr int R4_PATTERNS = 32;
-
-// v[k] (*)= sum_j P[r][k][j] x[j]  for this warp's category r; tips: table row slice
-template <bool MUL>
-__device__ __forceinline__ void r4_operand(int id, int pm, int r, int n_rows, int64_t p, int64_t Ppad,
-                                           const unsigned char *__restrict__ codes,
-                                           const unsigned int *__restrict__ masks, const double *__restrict__ pmat,
-                                           const double *__restrict__ tiptab, const double *__restrict__ clv,
-                                           double (&v)[4]) {
-  if (id < n_rows) {
-    const int code = codes[(int64_t)id * Ppad + p];
-    if (pm >= 0) {
-      const double *row = tiptab + (int64_t)pm * 256 + code * 16 + r * 4;
-      const double2 t01 = __ldg(reinterpret_cast<const double2 *>(row));
-      const double2 t23 = __ldg(reinterpret_cast<const double2 *>(row + 2));
-      if (MUL) { v[0] *= t01.x; v[1] *= t01.y; v[2] *= t23.x; v[3] *= t23.y; }
-      else { v[0] = t01.x; v[1] = t01.y; v[2] = t23.x; v[3] = t23.y; }
-    } else {
-      const unsigned int m = masks[code];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const double ind = (m >> k & 1) ? 1.0 : 0.0;
-        if (MUL) v[k] *= ind; else v[k] = ind;
-      }
-    }
-  } else {
-    const double *src = clv + ((int64_t)(id - n_rows) * 16 + r * 4) * Ppad + p;
-    double x[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) x[j] = __ldg(src + (int64_t)j * Ppad);
-    if (pm >= 0) {
-      const double *P = pmat + (int64_t)pm * 68 + r * 17;  // warp-uniform: broadcast from L1
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        double s = __ldg(P + k * 4) * x[0];
-        s = fma(__ldg(P + k * 4 + 1), x[1], s);
-        s = fma(__ldg(P + k * 4 + 2), x[2], s);
-        s = fma(__ldg(P + k * 4 + 3), x[3], s);
-        if (MUL) v[k] *= s; else v[k] = s;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (MUL) v[k] *= x[k]; else v[k] = x[k];
-    }
-  }
-}
-
-__global__ void __launch_bounds__(R4_THREADS)
-clv4r_kernel(const LikOpF *__restrict__ ops, int blocks_per_op, int n_rows, int64_t Ppad,
-             const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
-             const double *__restrict__ weights, const ModelDev *__restrict__ model,
-             const double *__restrict__ pmat, const double *__restrict__ tiptab, double *__restrict__ clv,
-             int *__restrict__ scl, double *__restrict__ partial, int pstride) {
-  __shared__ double xr[4][R4_PATTERNS];  // cross-category exchange: maxima, then site terms
-  const int op_idx = blockIdx.x / blocks_per_op;
-  const int pb = blockIdx.x - op_idx * blocks_per_op;
-  const LikOpF op = ops[op_idx];
-  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
-  const int64_t p = (int64_t)pb * R4_PATTERNS + lane;
-  double v[4];
-  r4_operand<false>(op.a, op.pa, r, n_rows, p, Ppad, codes, masks, pmat, tiptab, clv, v);
-  if (op.b >= 0) r4_operand<true>(op.b, op.pb, r, n_rows, p, Ppad, codes, masks, pmat, tiptab, clv, v);
-  int sc = 0;
-  if (op.a >= n_rows) sc += scl[(int64_t)(op.a - n_rows) * Ppad + p];
-  if (op.b >= n_rows) sc += scl[(int64_t)(op.b - n_rows) * Ppad + p];
-  xr[r][lane] = fmax(fmax(fabs(v[0]), fabs(v[1])), fmax(fabs(v[2]), fabs(v[3])));
-  __syncthreads();
-  const double mx = fmax(fmax(xr[0][lane], xr[1][lane]), fmax(xr[2][lane], xr[3][lane]));
-  if (mx < MINLH) {  // all 16 entries of the column below 2^-256
-#pragma unroll
-    for (int k = 0; k < 4; k++) v[k] *= TWO256;
-    sc += 1;
-  }
-  if (!op.pad) {
-    double *dst = clv + ((int64_t)(op.dst - n_rows) * 16 + r * 4) * Ppad + p;
-#pragma unroll
-    for (int k = 0; k < 4; k++) dst[(int64_t)k * Ppad] = v[k];
-    if (r == 0) scl[(int64_t)(op.dst - n_rows) * Ppad + p] = sc;
-  }
-  if (op.tree >= 0) {
-    double e[4];
-    {
-      const double *P = pmat + (int64_t)op.e_pa * 68 + r * 17;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        double s = __ldg(P + k * 4) * v[0];
-        s = fma(__ldg(P + k * 4 + 1), v[1], s);
-        s = fma(__ldg(P + k * 4 + 2), v[2], s);
-        s = fma(__ldg(P + k * 4 + 3), v[3], s);
-        e[k] = s;
-      }
-    }
-    r4_operand<true>(op.e_b, op.e_pb, r, n_rows, p, Ppad, codes, masks, pmat, tiptab, clv, e);
-    r4_operand<true>(op.e_c, op.e_pc, r, n_rows, p, Ppad, codes, masks, pmat, tiptab, clv, e);
-    if (op.e_b >= n_rows) sc += scl[(int64_t)(op.e_b - n_rows) * Ppad + p];
-    if (op.e_c >= n_rows) sc += scl[(int64_t)(op.e_c - n_rows) * Ppad + p];
-    double term = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) term = fma(model->freqs[k], e[k], term);
-    __syncthreads();  // everyone has read the maxima
-    xr[r][lane] = term;
-    __syncthreads();
-    if (r == 0) {
-      const double w = weights[p];
-      double val = 0.0;
-      if (w != 0.0) val = w * (log(((xr[0][lane] + xr[1][lane]) + (xr[2][lane] + xr[3][lane])) * 0.25) + sc * LOG_MINLH);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
-      if (lane == 0) partial[(int64_t)op.tree * pstride + pb] = val;
-    }
-  }
 }
 
 }  // namespace plg

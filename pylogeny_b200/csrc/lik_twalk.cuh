@@ -18,6 +18,42 @@ constexpr int TW_THREADS = 128;
 #define PLG_TW_MINB 4
 #endif
 
+// v (*)= P x for the four categories of one pattern: mat = P as [r][k][j] in shared memory, x in registers
+template <bool MUL>
+__device__ __forceinline__ void v4_apply_reg(const double *mat, const double (&x)[16], double (&v)[16]) {
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double2 p01 = *reinterpret_cast<const double2 *>(mat + r * 16 + k * 4);
+      const double2 p23 = *reinterpret_cast<const double2 *>(mat + r * 16 + k * 4 + 2);
+      double s = p01.x * x[r * 4];
+      s = fma(p01.y, x[r * 4 + 1], s);
+      s = fma(p23.x, x[r * 4 + 2], s);
+      s = fma(p23.y, x[r * 4 + 3], s);
+      if (MUL) v[r * 4 + k] *= s; else v[r * 4 + k] = s;
+    }
+}
+
+// weighted site log-likelihood of one pattern from its 16 joined entries e[r * 4 + k]
+__device__ __forceinline__ double v4_site(const double (&e)[16], int sc, double w, const ModelDev *__restrict__ model) {
+  double term = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) term = fma(model->freqs[k], (e[k] + e[4 + k]) + (e[8 + k] + e[12 + k]), term);
+  return w != 0.0 ? w * (log(term * 0.25) + sc * LOG_MINLH) : 0.0;
+}
+
+// per pattern: all 16 entries below 2^-256 -> multiply by 2^256 and count (libpll's scaling)
+__device__ __forceinline__ int tw_rescale(double (&n)[16]) {
+  int hi = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) hi = max(hi, __double2hiint(n[i]));
+  if (hi >= 0x2FF00000) return 0;  // high word of 2^-256 (biased exponent 1023 - 256 = 0x2FF)
+#pragma unroll
+  for (int i = 0; i < 16; i++) n[i] *= TWO256;
+  return 1;
+}
+
 // P(t r_c) of EVERY child slot of every tree straight from the descriptor's branch lengths:
 // pmat[slot][r][k][j], 64 doubles per slot.  The two slots of a root hold P(ta + tb) (evaluation
 // across the root branch, as build_full_lik_program) and nothing.
@@ -172,7 +208,7 @@ twalk4_kernel(const WalkOp *__restrict__ ops, int ni, int n_trees, unsigned long
       if (more) {
         tw_operand<false>(op.x, ca, MA, top, sct, stk, v, sc);
         tw_operand<true>(op.y, cb, MB, top, sct, stk, v, sc);
-        sc += wk_rescale(v);
+        sc += tw_rescale(v);
         if (op.z >= 0) {
           stk.store(op.z, v, sc);
         } else {

@@ -7,9 +7,9 @@
 #include "neighbourhood.h"
 #include "treewalk.h"
 
-// DNA x Gamma-4 neighbourhood planner: depth-first walks (lik_walk.cuh walk4_kernel) ship; the
-// level-by-level planners stay selectable for A/B measurements (PLG_LIK_NB_MODE=ops|visits|walk;
-// 64 taxa x 10k sites per step on B200: ops 12.4 ms, visits 10.8 ms).
+// DNA x Gamma-4 neighbourhood planner: depth-first walks (lik_walkm.cuh walk4m_kernel) ship; the
+// level-by-level planner stays selectable as the A/B reference (PLG_LIK_NB_MODE=ops; 64 taxa x 10k
+// sites per step on B200: 12.4 ms against 5.6 ms).
 
 #include <chrono>
 #include <cstdlib>
@@ -142,7 +142,6 @@ namespace plg {
 static int lik_nb_mode() {
   const char *e = std::getenv("PLG_LIK_NB_MODE");
   if (e && !strcmp(e, "ops")) return LIK_NB_OPS;
-  if (e && !strcmp(e, "visits")) return LIK_NB_VISITS;
   return LIK_NB_WALK;
 }
 // lnL of the distinct neighbours [lo, hi) of an enumerated SPR/NNI neighbourhood, in chunks that

@@ -1074,7 +1074,6 @@ void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int
 
 void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
                           LikProgram &prog, int mode, bool hoist_eval) {
-  const bool use_visits = mode == LIK_NB_VISITS;
   const UTree &t = nb.t;
   prog.clear();
   DirOrder d = dir_order(t);
@@ -1102,7 +1101,7 @@ void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int 
     tmp.push_back(o);
   }
   if (mode == LIK_NB_WALK) {
-    // Depth-first walks (lik_walk.cuh).  Search steps come in adjacent pairs (2q, 2q+1): the two
+    // Depth-first walks (lik_walkm.cuh).  Search steps come in adjacent pairs (2q, 2q+1): the two
     // insertion edges at the node a step reaches = one visit.  Visits of one pruned subtree are
     // listed in the order a warp runs them: the partial toward the child with the smaller
     // remaining search continues in registers, the other one is parked on a stack (depth <= log2 n).
@@ -1186,70 +1185,6 @@ void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int 
     }
     std::stable_sort(prog.walk_groups.begin(), prog.walk_groups.end(),
                      [](const LikWalkGroup &a, const LikWalkGroup &b) { return a.count > b.count; });
-    int max_level = 0;
-    for (auto &o : tmp) max_level = std::max(max_level, o.level);
-    prog.level_off.assign(max_level + 2, 0);
-    for (auto &o : tmp) prog.level_off[o.level + 1]++;
-    for (int l = 0; l <= max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
-    std::vector<int64_t> cur(prog.level_off.begin(), prog.level_off.end() - 1);
-    prog.ops.resize(tmp.size());
-    for (auto &o : tmp) prog.ops[cur[o.level]++] = o.op;
-    prog.n_slots = slots;
-    prog.n_trees = hi - lo;
-    return;
-  }
-  if (use_visits) {
-    // Search steps come in adjacent pairs (2q, 2q+1): the two insertion edges at the node a step
-    // reaches.  One visit scores both; a partial is stored only when a needed step continues below it.
-    std::vector<char> need = needed_moves(nb, lo, hi);
-    const size_t n_moves = nb.moves.size();
-    std::vector<char> has_child(n_moves, 0);
-    for (size_t i = 0; i < n_moves; i++)
-      if (need[i] && nb.moves[i].parent >= 0) has_child[nb.moves[i].parent] = 1;
-    std::vector<int> n_slot(n_moves, -1);
-    struct TmpV { LikVisit v; int level; };
-    std::vector<TmpV> tv;
-    tv.reserve(n_moves / 2);
-    int max_depth = 0;
-    for (size_t q = 0; q + 1 < n_moves; q += 2) {
-      if (!need[q] && !need[q + 1]) continue;
-      const Move &m1 = nb.moves[q], &m2 = nb.moves[q + 1];
-      const int x = m1.x, c1 = t.nb[x][m1.kx], c2 = t.nb[x][m2.kx];
-      int xin;
-      double lin;
-      if (m1.parent < 0) {
-        const int ko = (m1.k + 1 + (1 - m1.side)) % 3, ks = (m1.k + 1 + m1.side) % 3;
-        const int other = t.nb[m1.u][ko];
-        xin = dir_slot[3 * other + t.slot_of(other, m1.u)];
-        lin = t.len[m1.u][ko] + t.len[m1.u][ks];  // merged edge other -- x (rearrangement.py:480-490)
-      } else {
-        const Move &pm = nb.moves[m1.parent];
-        xin = n_slot[m1.parent];
-        lin = t.len[pm.x][pm.kx];
-      }
-      const int v = t.nb[m1.u][m1.k];
-      const double t1 = t.len[x][m1.kx], t2 = t.len[x][m2.kx];
-      TmpV e;
-      e.v.x_in = xin; e.v.p_in = prog.pm(lin);
-      e.v.tv = dir_slot[3 * v + t.slot_of(v, m1.u)]; e.v.p_v = prog.pm(t.len[m1.u][m1.k]);
-      e.v.d1 = dir_slot[3 * c1 + t.slot_of(c1, x)]; e.v.p_t1 = prog.pm(t1); e.v.p_h1 = prog.pm(t1 / 2.0);
-      e.v.d2 = dir_slot[3 * c2 + t.slot_of(c2, x)]; e.v.p_t2 = prog.pm(t2); e.v.p_h2 = prog.pm(t2 / 2.0);
-      e.v.n1 = e.v.n2 = -1;
-      if (need[q] && has_child[q]) { e.v.n1 = n_rows + (int)slots++; n_slot[q] = e.v.n1; }
-      if (need[q + 1] && has_child[q + 1]) { e.v.n2 = n_rows + (int)slots++; n_slot[q + 1] = e.v.n2; }
-      e.v.tree1 = (m1.unique_id >= lo && m1.unique_id < hi) ? (int)(m1.unique_id - lo) : -1;
-      e.v.tree2 = (m2.unique_id >= lo && m2.unique_id < hi) ? (int)(m2.unique_id - lo) : -1;
-      e.v.pad0 = e.v.pad1 = 0;
-      e.level = m1.depth;
-      max_depth = std::max(max_depth, m1.depth);
-      tv.push_back(e);
-    }
-    prog.visit_level_off.assign(max_depth + 2, 0);
-    for (auto &e : tv) prog.visit_level_off[e.level + 1]++;
-    for (int l = 0; l <= max_depth; l++) prog.visit_level_off[l + 1] += prog.visit_level_off[l];
-    std::vector<int64_t> vcur(prog.visit_level_off.begin(), prog.visit_level_off.end() - 1);
-    prog.visits.resize(tv.size());
-    for (auto &e : tv) prog.visits[vcur[e.level]++] = e.v;
     int max_level = 0;
     for (auto &o : tmp) max_level = std::max(max_level, o.level);
     prog.level_off.assign(max_level + 2, 0);

@@ -71,7 +71,7 @@ void desc_from_utree(const UTree &t, int32_t *desc, double *brlen);
 
 // Edge-insertion programs over moves unique[lo..hi): directional partials of the base tree, one
 // partial per search step, one join / 3-way evaluation per distinct neighbour.
-enum { LIK_NB_OPS = 0, LIK_NB_VISITS = 1, LIK_NB_WALK = 2 };
+enum { LIK_NB_OPS = 0, LIK_NB_WALK = 2 };
 
 struct FitchNbProgram {
   FitchProgram prog;
@@ -94,9 +94,7 @@ void finish_fitch_nb(const Neighbourhood &nb, const FitchNbProgram &p, const int
 // evaluation multiplies one matrix instead of three (the 20-state kernels; the DNA level kernels
 // fuse the whole evaluation into the update instead).
 // mode: LIK_NB_OPS one CLV update + one 3-way evaluation per neighbour (any state count);
-// LIK_NB_WALK depth-first search walks (LikWalkVisit, lik_walk.cuh; DNA x Gamma-4);
-// LIK_NB_VISITS: emit one LikVisit per search step (both neighbours at the node it reaches; DNA x
-// Gamma-4 kernels) instead of one CLV update + one 3-way evaluation per neighbour.
+// LIK_NB_WALK depth-first search walks (LikWalkVisit, lik_walkm.cuh; DNA x Gamma-4).
 void build_lik_nb_program(const Neighbourhood &nb, const int32_t *tip_rows, int n_rows, int64_t lo, int64_t hi,
                           LikProgram &out, int mode = LIK_NB_OPS, bool hoist_eval = false);
 

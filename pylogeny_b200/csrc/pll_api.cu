@@ -33,8 +33,7 @@ constexpr double PLL_ZMIN = 1.0e-15, PLL_ZMAX = 1.0 - 1.0e-6, PLL_DEFAULTZ = 0.9
 constexpr double SM_LOG_MINLH = -256.0 * 0.693147180559945309417232121458176568;  // log(2^-256), folded
 constexpr int SM_THREADS = 256;
 
-extern const double *const WAG_EXCH_PTR;  // protein_models.cpp
-extern const double WAG_FREQS[20];
+bool protein_model_table(const char *name, const double **exch, const double **freqs);  // protein_models.cpp
 
 // S[r*K+k][p] = (sum_i pi_i A_r[i] U[i][k]) * (sum_j Uinv[k][j] B_r[j]);  L_p(t) = (1/R) sum S exp(eval_k rate_r t)
 template <int K, int R>
@@ -370,16 +369,50 @@ static void read_phylip(const char *path, std::vector<std::string> &names, std::
     if (s.size() != m) PLG_FAIL(PLG_ERR_IO, "Alignment file could not be parsed.");
 }
 
-static std::string read_partition_model(const char *path) {
+// Partition file as pll.py:112-137 writes it: one line "<MODEL>, <name> = <from>-<to>" per partition.
+// One partition covering the whole alignment is what the engine scores (createSimpleModel,
+// pll.py:106-116 -- the only form landscape.py / scoring.py produce).  Several partitions (createModel,
+// pll.py:118-137) or a partial range would need one model per site block with joint branch lengths:
+// refused with PLG_ERR_UNSUPPORTED rather than scored under the first line's model.
+static std::string read_partition_model(const char *path, long long *range_end) {
   std::ifstream in(path);
   if (!in) PLG_FAIL(PLG_ERR_IO, "Partition file could not be read.");
-  std::string line;
-  std::getline(in, line);  // "DNA, p1 = 1-N" | "WAG, p1 = 1-N"  (pll.py:112-115)
-  std::string model = line.substr(0, line.find(','));
-  model.erase(std::remove_if(model.begin(), model.end(), [](char c) { return c == ' ' || c == '\t' || c == '\r'; }),
-              model.end());
+  std::string line, model;
+  int n_parts = 0;
+  *range_end = -1;
+  while (std::getline(in, line)) {
+    if (line.find_first_not_of(" \t\r\n") == std::string::npos) continue;
+    const size_t comma = line.find(','), eq = line.find('=');
+    if (comma == std::string::npos || eq == std::string::npos || eq < comma)
+      PLG_FAIL(PLG_ERR_IO, "Partition file could not be parsed.");
+    if (++n_parts > 1)
+      PLG_FAIL(PLG_ERR_UNSUPPORTED, "partition file with more than one partition: per-partition models are not implemented "
+               "(pll.partitionModel.createModel, pll.py:118-137); use createSimpleModel");
+    model = line.substr(0, comma);
+    model.erase(std::remove_if(model.begin(), model.end(), [](char c) { return c == ' ' || c == '\t' || c == '\r'; }),
+                model.end());
+    long long from = 0, to = 0;
+    char dash = 0;
+    std::istringstream rs(line.substr(eq + 1));
+    if (!(rs >> from >> dash >> to) || dash != '-' || from < 1 || to < from)
+      PLG_FAIL(PLG_ERR_IO, "Partition file could not be parsed.");
+    std::string rest;
+    if (rs >> rest) PLG_FAIL(PLG_ERR_UNSUPPORTED, "partition range '%s': only one contiguous range is supported", line.c_str());
+    if (from != 1) PLG_FAIL(PLG_ERR_UNSUPPORTED, "partition starts at site %lld: it must cover the whole alignment", from);
+    *range_end = to;
+  }
   if (model.empty()) PLG_FAIL(PLG_ERR_IO, "Partition file could not be parsed.");
   return model;
+}
+
+// "DNA", or a protein model the engine carries (WAG, JTT)
+static bool model_is_dna(const std::string &model_name) {
+  if (model_name == "DNA") return true;
+  const double *e, *f;
+  if (!protein_model_table(model_name.c_str(), &e, &f))
+    PLG_FAIL(PLG_ERR_UNSUPPORTED, "model '%s': the engine carries DNA (GTR), WAG and JTT (pll.py:102-115 passes the name "
+             "through); other matrices go through plg_model_create", model_name.c_str());
+  return false;
 }
 
 static uint8_t dna_code(char c) {
@@ -887,11 +920,13 @@ struct PllAlignment {
   std::shared_ptr<Model> model;
   // identity of the file it was read from
   std::string path, model_name;
+  size_t n_sites = 0;
   long long size = 0, mtime_ns = 0, ino = 0;
   int device = 0;
 };
 
-std::shared_ptr<PllAlignment> load_alignment(const char *phylip_path, bool dna) {
+std::shared_ptr<PllAlignment> load_alignment(const char *phylip_path, const std::string &model_name, bool dna,
+                                             long long range_end) {
   std::shared_ptr<PllAlignment> al(new PllAlignment());
   std::vector<std::string> seqs;
   read_phylip(phylip_path, al->names, seqs);
@@ -899,6 +934,8 @@ std::shared_ptr<PllAlignment> load_alignment(const char *phylip_path, bool dna) 
   for (size_t i = 0; i < names.size(); i++) al->row_of.emplace(names[i], (int)i);
   // encode + compress identical columns (weights = multiplicities; lnL is unchanged)
   const size_t n = names.size(), m = seqs[0].size();
+  if (range_end >= 0 && (size_t)range_end != m)
+    PLG_FAIL(PLG_ERR_UNSUPPORTED, "partition covers sites 1-%lld of %zu: it must cover the whole alignment", range_end, m);
   std::vector<uint8_t> codes(n * m);
   for (size_t r = 0; r < n; r++)
     for (size_t s = 0; s < m; s++) codes[r * m + s] = dna ? dna_code(seqs[r][s]) : aa_code(seqs[r][s]);
@@ -913,6 +950,7 @@ std::shared_ptr<PllAlignment> load_alignment(const char *phylip_path, bool dna) 
     else w[ins.first->second] += 1.0;
   }
   const size_t P = first.size();
+  al->n_sites = m;
   std::vector<uint8_t> packed(n * P);
   for (size_t r = 0; r < n; r++)
     for (size_t q = 0; q < P; q++) packed[r * P + q] = codes[r * m + first[q]];
@@ -938,7 +976,9 @@ std::shared_ptr<PllAlignment> load_alignment(const char *phylip_path, bool dna) 
     const double ones[6] = {1, 1, 1, 1, 1, 1};
     al->model.reset(new Model(4, ones, f, 1.0, 4));
   } else {
-    al->model.reset(new Model(20, WAG_EXCH_PTR, WAG_FREQS, 1.0, 4));
+    const double *exch = nullptr, *freqs = nullptr;
+    protein_model_table(model_name.c_str(), &exch, &freqs);  // (known: model_is_dna checked the name)
+    al->model.reset(new Model(20, exch, freqs, 1.0, 4));
   }
   return al;
 }
@@ -947,11 +987,12 @@ std::shared_ptr<PllAlignment> load_alignment(const char *phylip_path, bool dna) 
 // (PLG_PLL_ALN_CACHE=0 disables the cache).  Callers hold g_api_mutex.
 std::vector<std::shared_ptr<PllAlignment>> g_aln_cache;
 
-std::shared_ptr<PllAlignment> cached_alignment(const char *phylip_path, const std::string &model_name, bool dna) {
+std::shared_ptr<PllAlignment> cached_alignment(const char *phylip_path, const std::string &model_name, bool dna,
+                                               long long range_end) {
   const char *env = getenv("PLG_PLL_ALN_CACHE");
   const size_t keep = env ? (size_t)std::max(0, atoi(env)) : 4;
   struct stat sb;
-  if (keep == 0 || stat(phylip_path, &sb) != 0) return load_alignment(phylip_path, dna);  // (a missing file fails inside)
+  if (keep == 0 || stat(phylip_path, &sb) != 0) return load_alignment(phylip_path, model_name, dna, range_end);  // (a missing file fails inside)
   int dev = 0;
   cudaGetDevice(&dev);
   const long long mt = (long long)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec;
@@ -960,12 +1001,15 @@ std::shared_ptr<PllAlignment> cached_alignment(const char *phylip_path, const st
     if (c.path == phylip_path && c.model_name == model_name && c.size == (long long)sb.st_size && c.mtime_ns == mt &&
         c.ino == (long long)sb.st_ino && c.device == dev) {
       std::shared_ptr<PllAlignment> hit = g_aln_cache[i];
+      if (range_end >= 0 && range_end != (long long)hit->n_sites)
+        PLG_FAIL(PLG_ERR_UNSUPPORTED, "partition covers sites 1-%lld of %zu: it must cover the whole alignment", range_end,
+                 hit->n_sites);
       g_aln_cache.erase(g_aln_cache.begin() + i);
       g_aln_cache.insert(g_aln_cache.begin(), hit);
       return hit;
     }
   }
-  std::shared_ptr<PllAlignment> al = load_alignment(phylip_path, dna);
+  std::shared_ptr<PllAlignment> al = load_alignment(phylip_path, model_name, dna, range_end);
   al->path = phylip_path; al->model_name = model_name;
   al->size = (long long)sb.st_size; al->mtime_ns = mt; al->ino = (long long)sb.st_ino; al->device = dev;
   g_aln_cache.insert(g_aln_cache.begin(), al);
@@ -984,12 +1028,10 @@ extern "C" int plg_pll_new(const char *phylip_path, const char *newick, const ch
   // (libpllWrapper.c:138, scoring.py:41-75).  Here the parsed, pattern-compressed, device-resident
   // alignment and its model are kept per (file identity, partition model, device) and shared by
   // the handles: a hill climb pays the 45 ms of parsing once, not per neighbour.
-  const std::string model_name = read_partition_model(partition_path);
-  const bool dna = (model_name == "DNA");
-  if (!dna && model_name != "WAG")
-    PLG_FAIL(PLG_ERR_UNSUPPORTED, "protein model '%s': only WAG ships with the engine (pll.py:102 default); "
-             "use plg_model_create for other matrices", model_name.c_str());
-  std::shared_ptr<PllAlignment> al = cached_alignment(phylip_path, model_name, dna);
+  long long range_end = -1;
+  const std::string model_name = read_partition_model(partition_path, &range_end);
+  const bool dna = model_is_dna(model_name);
+  std::shared_ptr<PllAlignment> al = cached_alignment(phylip_path, model_name, dna, range_end);
   const std::vector<std::string> &names = al->names;
   std::unique_ptr<plg_pll> h(new plg_pll());
   PllProblem &pr = h->p;
@@ -1126,11 +1168,10 @@ extern "C" int plg_pll_loglik_batch(const char *phylip_path, const char *partiti
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
     PLG_FAIL(PLG_ERR_CUDA, "no CUDA device: pylogeny_b200 has no CPU fallback");
-  const std::string model_name = read_partition_model(partition_path);
-  const bool dna = (model_name == "DNA");
-  if (!dna && model_name != "WAG")
-    PLG_FAIL(PLG_ERR_UNSUPPORTED, "protein model '%s': only WAG ships with the engine", model_name.c_str());
-  std::shared_ptr<PllAlignment> al = cached_alignment(phylip_path, model_name, dna);
+  long long range_end = -1;
+  const std::string model_name = read_partition_model(partition_path, &range_end);
+  const bool dna = model_is_dna(model_name);
+  std::shared_ptr<PllAlignment> al = cached_alignment(phylip_path, model_name, dna, range_end);
   std::vector<UTree> trees(n_trees);
   std::vector<std::vector<std::string>> names(n_trees);
   std::vector<std::vector<int32_t>> rows(n_trees);

@@ -166,6 +166,10 @@ TreeBatch batch_from_desc(int64_t n_trees, int n_tips, const int32_t *desc, cons
   if (brlen) b.child_len.assign(brlen, brlen + (size_t)n_trees * ni * 2);
   for (int64_t t = 0; t <= n_trees; t++) b.node_off[t] = t * ni;
   for (int64_t x = 0; x <= n_trees * ni; x++) b.child_off[x] = 2 * x;
+  if (tip_rows)
+    for (int i = 0; i < n_tips; i++)
+      if (tip_rows[i] < 0) PLG_FAIL(PLG_ERR_ARG, "tip row %d is negative", tip_rows[i]);
+  std::vector<int64_t> used_by((size_t)n_tips + ni, -1);  // every node is a child at most (hence exactly) once
   for (int64_t t = 0; t < n_trees; t++)
     for (int i = 0; i < ni; i++)
       for (int c = 0; c < 2; c++) {
@@ -173,6 +177,10 @@ TreeBatch batch_from_desc(int64_t n_trees, int n_tips, const int32_t *desc, cons
         if (id < 0 || id >= n_tips + i)
           PLG_FAIL(PLG_ERR_ARG, "descriptor of tree %lld node %d: child id %d is not earlier in post-order",
                    (long long)t, i, id);
+        if (used_by[id] == t)
+          PLG_FAIL(PLG_ERR_ARG, "descriptor of tree %lld node %d: node %d is a child twice (not a tree)",
+                   (long long)t, i, id);
+        used_by[id] = t;
         b.child[((size_t)t * ni + i) * 2 + c] = id < n_tips ? (tip_rows ? tip_rows[id] : id) : -(id - n_tips + 1);
       }
   return b;

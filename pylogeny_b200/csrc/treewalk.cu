@@ -1,4 +1,6 @@
 // Device-side planner of tree-walk programs (see treewalk.h).
+#include <vector>
+
 #include "treewalk.h"
 
 namespace plg {
@@ -73,6 +75,10 @@ void validate_desc(int64_t n_trees, int n_tips, const int32_t *desc, const int32
                    bool rows_matter) {
   if (n_tips < 2) PLG_FAIL(PLG_ERR_ARG, "descriptor trees need at least 2 tips");
   const int ni = n_tips - 1;
+  // every tip and every non-root internal node is a child exactly once: 2 * ni slots for 2 * ni ids,
+  // so "no id twice" is the whole condition.  A DAG or a forest would make the device planner
+  // (plan_walk_kernel) write more ops than the tree's slot holds.
+  std::vector<int64_t> used_by((size_t)n_tips + ni, -1);
   for (int64_t t = 0; t < n_trees; t++) {
     const int32_t *d = desc + (size_t)t * ni * 2;
     for (int i = 0; i < ni; i++)
@@ -81,6 +87,10 @@ void validate_desc(int64_t n_trees, int n_tips, const int32_t *desc, const int32
         if (id < 0 || id >= n_tips + i)
           PLG_FAIL(PLG_ERR_ARG, "descriptor of tree %lld node %d: child id %d is not earlier in post-order",
                    (long long)t, i, id);
+        if (used_by[id] == t)
+          PLG_FAIL(PLG_ERR_ARG, "descriptor of tree %lld node %d: node %d is a child twice (not a tree)",
+                   (long long)t, i, id);
+        used_by[id] = t;
       }
   }
   if (rows_matter) {

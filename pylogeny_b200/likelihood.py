@@ -32,6 +32,15 @@ def compress_columns(codes):
     return np.ascontiguousarray(cols[first[order]].T), counts[order].astype(np.float64)
 
 
+def protein_model(name):
+    """(exch [190], freqs [20]) of a built-in empirical protein model: "WAG" or "JTT" (the names a
+    partition file carries, pll.py:102-115).  Host lookup; table provenance: csrc/protein_models.cpp."""
+    exch, freqs = np.zeros(190), np.zeros(20)
+    dp = C.POINTER(C.c_double)
+    _lib.check(_lib.lib().plg_protein_model(name.encode(), exch.ctypes.data_as(dp), freqs.ctypes.data_as(dp)))
+    return exch, freqs
+
+
 class Model(object):
     """Reversible substitution model + discrete Gamma (plg_model)."""
 

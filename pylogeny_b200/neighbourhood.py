@@ -212,12 +212,7 @@ def likelihood_greedy(ali, newick, top=16, max_steps=1000, passes=3):
     Returns (path of smoothed lnL, final Newick with optimised branch lengths)."""
     import ctypes as C_
     from . import likelihood, libpllWrapper as W, pll
-    if not hasattr(ali, '_pllmodel'):
-        m_ = pll.partitionModel(ali)
-        m_.createSimpleModel()
-        ali._pllmodel = m_
-        ali.paths['pll'] = m_.getFileName()
-    phy, part = ali.getPhylip(), ali._pllmodel.getFileName()
+    phy, part = ali.getPhylip(), pll.model_for(ali).getFileName()
     labels = ali.getTaxa()
     taxa = {l: i for i, l in enumerate(labels)}
     # the model the libpllWrapper drop-in builds for this alignment (GTR, all rates 1, empirical

@@ -9,8 +9,9 @@ _constructSet (parsimony.py:39-46) is a dictionary lookup and, when the alignmen
 exposes `as_matrix()` (pylogeny_b200.alignment does), the canonical relabelling of
 _buildVector (parsimony.py:132-145) is vectorised over all columns at once.
 
-The deprecated pure-Python Fitch (parsimony.py:147-189) is intentionally not
-provided: the only scorer is the CUDA one (scoring.getParsimony*).
+The deprecated entry points `fitch_cost(topology, profiles)` and `fitch(topology, alignment)`
+(parsimony.py:147-189, a pure-Python Fitch for binary trees) keep their names and signatures
+but score on the device like everything else (there is no CPU scorer in this package).
 """
 import numpy as np
 
@@ -153,3 +154,22 @@ class profile_set(object):
 
     def getForTaxa(self, val, tax):
         return self.profiles[val].vector[self.taxa[tax]]
+
+
+def fitch_cost(topology, profiles):
+    """parsimony.fitch_cost (parsimony.py:147-176, deprecated there): Fitch length of a topology
+    over a profile_set.  The reference walks `topology.getRoot()` in Python and reads only the first
+    two children of every node; here the topology's Newick string (`toNewick()`) goes to the CUDA
+    scorer, which equals it on binary trees (and follows fitch.cpp's k-ary rule elsewhere).  The
+    result is fitch.cpp's 32-bit total; the Python original does not wrap."""
+    from . import scoring
+    return scoring.getParsimonyFromProfiles(topology.toNewick(), profiles)
+
+
+def fitch(topology, alignment):
+    """parsimony.fitch (parsimony.py:178-189, deprecated there): profile the alignment, then
+    fitch_cost; None for an alignment without columns."""
+    profiles = profile_set(alignment)
+    if len(profiles) == 0:
+        return None
+    return fitch_cost(topology, profiles)

@@ -19,14 +19,28 @@ from . import fitch, parsimony
 
 
 def _resident(profiles):
-    """Device-resident alignment cached on the profile_set."""
+    """Device-resident alignment cached on the profile_set, keyed on its CONTENT (the reference
+    rebuilds the profile list and copies the weights on every call, scoring.py:134-137, so editing
+    either in place -- bootstrap reweighting -- must take effect here too).  The key costs O(P)
+    cheap operations per call: Python caches each string's hash inside the string object."""
+    prolist = [str(x) for x in profiles.profiles]
+    weights = [int(w) for w in profiles.weights]
+    key = (hash(tuple(prolist)), hash(tuple(weights)), len(prolist))
     cache = getattr(profiles, "_b200_cache", None)
-    key = (len(profiles.profiles), len(profiles.weights))
     if cache is None or cache[0] != key:
-        prolist = [str(x) for x in profiles.profiles]
-        cache = (key, fitch.FitchAlignment(prolist, list(profiles.weights)))
+        if cache is not None:
+            cache[1].close()
+        cache = (key, fitch.FitchAlignment(prolist, weights))
         profiles._b200_cache = cache
     return cache[1]
+
+
+def invalidate(profiles):
+    """Drop the device-resident copy of a profile_set (it is rebuilt on the next scoring call)."""
+    cache = getattr(profiles, "_b200_cache", None)
+    if cache is not None:
+        cache[1].close()
+        profiles._b200_cache = None
 
 
 def getParsimonyFromProfiles(newick, profiles):
@@ -60,14 +74,10 @@ def getLogLikelihoodBatch(trees, alignment, updateBranchLengths=True):
     from . import libpllWrapper as W, pll
     if not trees:
         return []
-    if not hasattr(alignment, '_pllmodel'):
-        m = pll.partitionModel(alignment)
-        m.createSimpleModel()
-        alignment._pllmodel = m
-        alignment.paths['pll'] = m.getFileName()
+    model = pll.model_for(alignment)
     newicks = [t.toTopology().toUnrootedNewick() for t in trees]
     try:
-        scores, optimised = W.getLogLikelihoodBatch(alignment.getPhylip(), newicks, alignment._pllmodel.getFileName())
+        scores, optimised = W.getLogLikelihoodBatch(alignment.getPhylip(), newicks, model.getFileName())
     except Exception:
         return [getLogLikelihood(t, alignment, updateBranchLengths) for t in trees]  # isolate the failing tree
     if updateBranchLengths:

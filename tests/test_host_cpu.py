@@ -136,3 +136,38 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("BASELINE configs[1]")
+
+
+def test_protein_tables():
+    """The shipped WAG and JTT tables (csrc/protein_models.cpp, typed from memory of PAML's wag.dat /
+    jones.dat): what can be checked without the published files -- shape, positivity, frequencies
+    summing to 1 within the files' rounding, landmark entries, the dominant exchanges of either
+    paper, and that the rate matrix built from them has the table's frequencies as its stationary
+    distribution (detailed balance).  See the file header for what stays unchecked."""
+    from pylogeny_b200 import likelihood
+    order = likelihood.AA_ORDER
+    idx = {c: i for i, c in enumerate(order)}
+    top_expected = {"WAG": [("I", "V"), ("F", "Y"), ("D", "E"), ("D", "N"), ("E", "Q"), ("K", "R")],
+                    "JTT": [("I", "V"), ("D", "E"), ("K", "R"), ("H", "Q"), ("H", "Y"), ("F", "Y")]}
+    landmarks = {"WAG": {("A", "R"): 0.551571, ("D", "N"): 5.429420, ("I", "V"): 7.821300, ("C", "D"): 0.0302949},
+                 "JTT": {("A", "R"): 58.0, ("D", "E"): 767.0, ("I", "V"): 961.0, ("C", "E"): 5.0}}
+    for name in ("WAG", "JTT", "wag"):
+        exch, freqs = likelihood.protein_model(name)
+        assert exch.shape == (190,) and freqs.shape == (20,) and np.all(exch > 0) and np.all(freqs > 0)
+        assert abs(freqs.sum() - 1.0) < 2e-6
+        R = np.zeros((20, 20))
+        R[np.triu_indices(20, 1)] = exch
+        R = R + R.T
+        key = name.upper()
+        for (a, b), v in landmarks[key].items():
+            assert R[idx[a], idx[b]] == v
+        ranked = sorted(((R[i, j], order[i], order[j]) for i in range(20) for j in range(i + 1, 20)), reverse=True)
+        top = {tuple(sorted((a, b))) for _, a, b in ranked[:12]}
+        for pair in top_expected[key]:
+            assert tuple(sorted(pair)) in top, (name, pair, ranked[:12])
+        Q = R * freqs[None, :]
+        np.fill_diagonal(Q, -Q.sum(1))
+        np.testing.assert_allclose(freqs @ Q, 0.0, atol=1e-12)                        # stationary
+        np.testing.assert_allclose(freqs[:, None] * Q, (freqs[:, None] * Q).T, atol=1e-15)  # reversible
+    with pytest.raises(Exception):
+        likelihood.protein_model("LG")

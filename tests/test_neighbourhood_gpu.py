@@ -109,31 +109,34 @@ def test_tbr_edge_insertion_vs_retraversal(n, P):
     fa.close(); la.close(); m.close()
 
 
-@pytest.mark.parametrize("n,P,scale", [(6, 40, 1.0), (24, 700, 1.0), (70, 300, 1.0), (40, 200, 60.0)])
-def test_lnl_planners_agree(n, P, scale, monkeypatch):
-    """The DNA x Gamma-4 neighbourhood planners (PLG_LIK_NB_MODE: per-neighbour ops, pair-fused
-    level-by-level visits, depth-first walks on the FP64 CUDA cores, and -- the default, "walkm" --
-    the same walks on the FP64 tensor pipe) give the same lnL per neighbour, also
-    in the underflow regime (long branches => 2^-256 rescaling inside the walk), for shards and for
-    radius-limited neighbourhoods; walk == oracle on a sample."""
+@pytest.mark.parametrize("n,P,scale,wmax", [(6, 40, 1.0, 4), (24, 700, 1.0, 4), (70, 300, 1.0, 4), (40, 200, 60.0, 4),
+                                            (24, 700, 1.0, 1), (70, 300, 1.0, 2), (40, 200, 60.0, 1), (9, 33, 200.0, 1)])
+def test_lnl_planners_agree(n, P, scale, wmax, monkeypatch):
+    """The DNA x Gamma-4 neighbourhood planners (PLG_LIK_NB_MODE=ops: one level-synchronous update +
+    evaluation per neighbour; default: depth-first search walks on the FP64 tensor pipe) give the
+    same lnL per neighbour, also in the underflow regime (long branches => 2^-256 rescaling inside
+    the walk), for shards and for radius-limited neighbourhoods; walk == oracle on a sample.
+    wmax = 1: unit weights, every slice takes the walk's mantissa/exponent path (no log in the
+    kernel); wmax = 2: weights 0/1 mixed with heavier ones, so both paths run in one call; wmax = 4:
+    weighted slices only."""
     from pylogeny_b200 import likelihood, neighbourhood as nbh
     rng = np.random.default_rng(11 * n + P)
     codes = (1 << rng.integers(0, 4, (n, P))).astype(np.uint8)
     codes = np.where(rng.random((n, P)) < 0.02, 15, codes).astype(np.uint8)
-    w = rng.integers(1, 4, P).astype(float)
+    w = rng.integers(1, 4, P).astype(float) if wmax == 4 else np.ones(P)
+    if wmax == 2:  # some 32-pattern slices all 0/1, others weighted
+        w[rng.random(P) < 0.1] = 0.0
+        w[P // 2:][rng.random(P - P // 2) < 0.2] = 3.0
     exch, f = rng.uniform(0.3, 3, 6), rng.dirichlet(np.ones(4) * 6)
     a = likelihood.LikAlignment(codes, w)
     m = likelihood.Model(exch, f, 0.6)
     d = random_desc(rng, n)
     br = rng.exponential(0.1 * scale, d.shape)
     res = {}
-    for mode in ("ops", "visits", "walk", "walkm"):
+    for mode in ("ops", "walkm"):
         monkeypatch.setenv("PLG_LIK_NB_MODE", mode)
         res[mode] = nbh.score_likelihood(a, m, d, br)[1]
-    np.testing.assert_allclose(res["walk"], res["ops"], rtol=1e-12)
-    np.testing.assert_allclose(res["walk"], res["visits"], rtol=1e-12)
     np.testing.assert_allclose(res["walkm"], res["ops"], rtol=1e-12)
-    monkeypatch.setenv("PLG_LIK_NB_MODE", "walkm")
     res["walk"] = res["walkm"]
     M = len(res["walk"])
     parts = [nbh.score_likelihood(a, m, d, br, shard=(i, 3))[1] for i in range(3)]

@@ -153,3 +153,43 @@ def test_lnl_oracle_scaling_long_tree():
         tot += mx + np.log(np.exp(site - mx).mean())
     assert got < -700  # really in the underflow regime
     assert abs(got - tot) <= 1e-10 * abs(tot)
+
+
+def test_closed_form_formulas_vs_expm():
+    """The textbook P(t) formulas of tests/closed_form.py are themselves transcribed correctly:
+    they equal expm(Qt) of the rate matrix they claim to solve."""
+    from scipy.linalg import expm
+    import closed_form as cf
+    import closed_form_cases as cc
+
+    def rate_matrix(exch, pi):
+        R = np.zeros((4, 4))
+        R[np.triu_indices(4, 1)] = exch
+        R = R + R.T
+        Q = R * pi[None, :]
+        np.fill_diagonal(Q, -Q.sum(1))
+        return Q / -np.sum(pi * np.diag(Q))
+
+    for t in (0.0, 0.01, 0.3, 2.0, 9.0):
+        np.testing.assert_allclose(cf.p_jc69(t), expm(rate_matrix(np.ones(6), np.full(4, 0.25)) * t), atol=1e-14)
+        np.testing.assert_allclose(cf.p_f81(cc.F81_FREQS, t), expm(rate_matrix(np.ones(6), cc.F81_FREQS) * t), atol=1e-14)
+        np.testing.assert_allclose(cf.p_hky85(cc.HKY_FREQS, 4.3, t),
+                                   expm(rate_matrix(cf.hky_exch(4.3), cc.HKY_FREQS) * t), atol=1e-14)
+    # Yang's mean rates: mean 1, increasing, and the alpha -> infinity limit is a single rate
+    for alpha in (0.2, 1.0, 3.0):
+        r = cf.gamma_mean_rates(alpha, 4)
+        assert abs(r.mean() - 1.0) < 1e-12 and np.all(np.diff(r) > 0)
+    np.testing.assert_allclose(cf.gamma_mean_rates(1e7, 4), np.ones(4), atol=2e-3)
+
+
+def test_lnl_oracle_pinned_to_closed_forms():
+    """oracle/lik_oracle.c against numbers nobody here computed: JC69 / F81 / HKY85 closed-form
+    transition probabilities, Yang-1994 mean Gamma rates from scipy, two-, three- and four-taxon
+    trees whose site likelihoods are explicit sums (star trees, the pulley principle, the
+    zero-length internal branch, saturation), every site pattern, at 1e-12 relative."""
+    import closed_form_cases as cc
+    cases = cc.cases()
+    assert len(cases) >= 70
+    for name, exch, freqs, alpha, ncat, codes, w, desc, br, want in cases:
+        got = oracle.lnl(codes, w, exch, freqs, alpha, desc, br, ncat=ncat)
+        assert abs(got - want) <= 1e-12 * abs(want), (name, got, want)

@@ -1,6 +1,8 @@
 """Tree walks (csrc/treewalk.cu, fitch_walk.cuh, lik_twalk.cuh): descriptor batches scored by the
 on-chip depth-first kernels must equal the level-synchronous programs (PLG_TREE_MODE=levels) and
 the oracle -- Fitch bit-exact, lnL within 1e-8 relative (observed ~1e-13)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -167,4 +169,31 @@ def test_walk_rejects_bad_descriptors():
         fa.score_trees(np.array([[0, 1], [3, 2]], np.int32), tip_rows=[0, 1, 9])
     with pytest.raises(Exception):
         la.score_trees(m, np.array([[0, 1], [3, 2]], np.int32), np.ones((2, 2)), tip_rows=[0, 1, -1])
-    fa.close(); la.close(); m.close()
+    # not a tree: a node used twice as a child (the device planner would emit more ops than the tree's
+    # slot holds), on the walk path and on the level path
+    st4 = random_states(rng, 4, 50, 4)
+    fa4 = fitch.FitchAlignment.from_dense(st4, np.ones(50, dtype=np.int64))
+    la4 = likelihood.LikAlignment((1 << rng.integers(0, 4, (4, 50))).astype(np.uint8), np.ones(50))
+    dag = np.array([[0, 1], [4, 4], [5, 5]], np.int32)
+    forest = np.array([[0, 1], [2, 3], [4, 4]], np.int32)
+    for mode in ("walk", "levels"):
+        os.environ["PLG_TREE_MODE"] = mode
+        try:
+            for d in (dag, forest):
+                with pytest.raises(_lib.EngineError) as e1:
+                    fa4.score_trees(d)
+                assert e1.value.code == _lib.ERR_ARG
+                with pytest.raises(_lib.EngineError) as e2:
+                    la4.score_trees(m, d, np.ones((3, 2)))
+                assert e2.value.code == _lib.ERR_ARG
+            # still fine afterwards
+            assert fa4.score_trees(np.array([[0, 1], [2, 3], [4, 5]], np.int32)).shape == (1,)
+        finally:
+            os.environ.pop("PLG_TREE_MODE")
+    with pytest.raises(_lib.EngineError):  # negative rows on the level path are not inner-node references
+        os.environ["PLG_TREE_MODE"] = "levels"
+        try:
+            fa4.score_trees(np.array([[0, 1], [2, 3], [4, 5]], np.int32), tip_rows=[0, 1, 2, -2])
+        finally:
+            os.environ.pop("PLG_TREE_MODE")
+    fa.close(); la.close(); m.close(); fa4.close(); la4.close()
