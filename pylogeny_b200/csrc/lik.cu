@@ -591,6 +591,24 @@ spr_lik_plan_kernel(const int4 *__restrict__ edges_g, int n_edge_int4, const int
   }
 }
 
+// B fragments of the DMMA search walk (lik_walkm.cuh): for every branch length t the pair
+// (P(t), P(t / 2)) -- a target branch and its half (rearrangement.py:466-470) -- interleaved the way
+// mma.m8n8k4 wants its B operand: lane 4 g + q holds (g odd ? P(t/2) : P(t))[r][g >> 1][q] for the four
+// categories r, side by side, so a lane fetches a whole fragment with ONE 32-byte load
+// (pfrag[pm][lane][r]).  Same arithmetic as pmatrix_kernel, entry by entry.
+__global__ void __launch_bounds__(128)
+pairfrag4_kernel(const ModelDev *__restrict__ model, const double *__restrict__ brlen, double *__restrict__ pfrag) {
+  const int pm = blockIdx.x, lane = threadIdx.x >> 2, r = threadIdx.x & 3;
+  const int g = lane >> 2, j = lane & 3, i = g >> 1;
+  const double t = (g & 1) ? brlen[pm] * 0.5 : brlen[pm];
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) s += model->U[i * 4 + k] * exp(model->eval[k] * t * model->rates[r]) * model->Uinv[k * 4 + j];
+  s = fmax(s, 0.0);
+  if (t == 0.0) s = (i == j) ? 1.0 : 0.0;
+  pfrag[((int64_t)pm * 32 + lane) * 4 + r] = s;
+}
+
 // DNA x Gamma-4 path: thread-per-pattern kernels, evaluations fused into the CLV update that
 // produces their first operand whenever the other operands are ready by then.
 static int64_t dna4_partial_stride(const LikAln &a) { return a.Ppad / D4_THREADS; }
@@ -726,6 +744,11 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
     PLG_CUDA(cudaMemcpyAsync(ws.walk_groups.p, prog.walk_groups.data(), prog.walk_groups.size() * sizeof(LikWalkGroup),
                              cudaMemcpyHostToDevice, st));
     PLG_CUDA(cudaMemsetAsync(ws.walk_counter.p, 0, sizeof(unsigned long long), st));
+    ws.pfrag.alloc((size_t)std::max(1, n_pm) * 128);
+    if (n_pm) {
+      pairfrag4_kernel<<<n_pm, 128, 0, st>>>(m.d.p, ws.brlen.p, ws.pfrag.p);
+      count_launch();
+    }
     // accounting: algorithmic = per neighbour one CLV update (result + 2 operands) and one 3-way
     // evaluation (3 operands + weight), as for every other planner; requested = what the walk
     // really loads and stores (far-side operands, first partial of a side, stack traffic, Tv once
@@ -786,8 +809,9 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       ensure_dyn_smem(walk4m_kernel, smem, wm_attr_set);
       walk4m_kernel<<<n_blocks, WM_THREADS, smem, st>>>(ws.walk_groups.p, (int)prog.walk_groups.size(), ws.walk_visits.p,
                                                        n_items, a.n_rows, a.Ppad, a.codes.p, a.weights.p, m.d.p,
-                                                       ws.pmat.p, ws.clv.p, ws.scl.p, ws.walk_stack.p,
-                                                       ws.walk_stack_scl.p, levels, ws.partial.p, ws.partial_e.p,
+                                                       ws.pfrag.p, ws.clv.p, ws.scl.p,
+                                                       ws.walk_stack.p, ws.walk_stack_scl.p, levels, ws.partial.p,
+                                                       ws.partial_e.p,
                                                        (int)pstride, ws.walk_counter.p);
     }
     count_launch();

@@ -56,6 +56,7 @@ struct LikWorkspace {
   DevBuf<double> clv;      // [slot][R*K][Ppad]
   DevBuf<int> scl;         // [slot][Ppad] per-pattern 2^-256 scaling counters
   DevBuf<double> pmat;     // [pm][R][K*K+1]  (padded stride: conflict-free shared-memory staging)
+  DevBuf<double> pfrag;    // [pm][32 lanes][R] (DNA x Gamma-4): (P(t), P(t/2)) as DMMA B fragments (pairfrag4_kernel)
   DevBuf<double> tiptab;   // [pm][ncodes][R*K]  sum over the code's states of P columns
   DevBuf<double> brlen;    // [pm]
   DevBuf<LikOp> ops;

@@ -2,8 +2,8 @@
 //
 // One warp carries a 32-pattern slice through a whole SPR search (all regraft positions of one
 // pruned subtree); partials never leave the SM.  The 4x4 products run as mma.sync.m8n8k4.f64: the
-// matrix is a FRAGMENT (one double per lane), the vectors are the other fragment, and one
-// instruction does 256 FMAs.  B200 measurement (plg_fp64_peak, bench.py): DMMA and DFMA share one
+// matrix is a FRAGMENT (one double per lane and category, fetched with one 32-byte load from the
+// pair table of pairfrag4_kernel), the vectors are the other fragment, and one instruction does 256 FMAs.  B200 measurement (plg_fp64_peak, bench.py): DMMA and DFMA share one
 // pipe -- so this buys no flops, it removes 7/8 of the issue slots and all of the P-row traffic
 // of a scalar formulation.
 //
@@ -39,27 +39,9 @@ constexpr int WM_THREADS = 32 * WM_WARPS;
 #ifndef PLG_WM_MINB
 #define PLG_WM_MINB 3
 #endif
-#ifndef PLG_WM_RTUNIT
-#define PLG_WM_RTUNIT 0   // 1: one copy of the search loop, the unit-weight test per evaluation
-#endif
-#ifndef PLG_WM_PREVOTE
-#define PLG_WM_PREVOTE 0  // 1: one warp vote before the per-group rescale ballots (B200: 5.17 vs 4.90 ms)
-#endif
 constexpr int WM_V = 16;          // doubles per vector per lane: [category r][group j] = v[r * 4 + j]
 constexpr int WM_PATTERNS = 32;   // patterns per warp item
-#ifndef PLG_WM_STAGE
-#define PLG_WM_STAGE 0     // 1: the far-side operands of the NEXT visit are fetched by cp.async into shared memory during this one
-#endif
-#ifndef PLG_WM_AKSMEM
-#define PLG_WM_AKSMEM 0    // 1: the partial handed from visit to visit lives in shared memory, not in 32 registers
-#endif
-#ifndef PLG_WM_DUAL
-#define PLG_WM_DUAL 0      // 1: both neighbours of a visit emitted together (one shuffle tree for the two records)
-#endif
-// staging area of one operand: 9 rows of 16 B per lane (8 rows CLV + 1 row scaling counters; a tip uses 8 B of row 0)
-constexpr int WM_STAGE_ROWS = 9;
-constexpr int WM_STAGE_DOUBLES = PLG_WM_STAGE ? 2 * WM_STAGE_ROWS * 2 * 32 : 0;  // two operands
-constexpr int WM_SMEM_DOUBLES_PER_WARP = (2 + PLG_WM_AKSMEM) * WM_V * 32 + WM_STAGE_DOUBLES;  // parked: tvv, h1 (, a); staged: D1, D2
+constexpr int WM_SMEM_DOUBLES_PER_WARP = 2 * WM_V * 32;  // parked: tvv, h1
 constexpr int WM_PLAIN = (int)0x80808080;  // exponent marker: the double is a finished sum of site terms (memset byte 0x80)
 constexpr double WM_LN2 = 0.693147180559945309417232121458176568;
 
@@ -78,11 +60,11 @@ __device__ __forceinline__ void wm_pair(const double (&x)[WM_V], const double (&
     for (int j = 0; j < 4; j++) wm_dmma(t[r * 4 + j], h[r * 4 + j], x[r * 4 + j], bf[r]);
 }
 
-// fragment of a branch pair: lane (g, q) holds (g odd ? P[pm_h] : P[pm_t])[r][g >> 1][q]
-__device__ __forceinline__ void wm_frag(const double *__restrict__ pmat, int pm_t, int pm_h, int lane, double (&bf)[4]) {
-  const double *src = pmat + (int64_t)((lane >> 2) & 1 ? pm_h : pm_t) * 68 + (lane >> 3) * 4 + (lane & 3);
-#pragma unroll
-  for (int r = 0; r < 4; r++) asm volatile("ld.global.nc.f64 %0, [%1];\n" : "=d"(bf[r]) : "l"(src + r * 17));
+// fragment of the branch pair (P(t), P(t/2)) of P-matrix id `pm`: one 32-byte load (pairfrag4_kernel)
+__device__ __forceinline__ void wm_frag(const double *__restrict__ pfrag, int pm, int lane, double (&bf)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\n"
+               : "=d"(bf[0]), "=d"(bf[1]), "=d"(bf[2]), "=d"(bf[3])
+               : "l"(pfrag + ((int64_t)pm * 32 + lane) * 4));
 }
 
 // Operand `id` as it sits at its node, in layout V (tips: indicator of the code's states; one code
@@ -120,75 +102,42 @@ __device__ __forceinline__ void wm_load_raw(int id, int n_rows, int64_t Ppad, in
   }
 }
 
-#if PLG_WM_STAGE
-// Asynchronous copy of operand `id` (as wm_load_raw reads it) into this lane's staging slots:
-// every lane fetches exactly the bytes it will consume, so no cross-lane synchronisation is needed
-// (cp.async.wait_group is per thread).  sdst = shared address of row 0 of this lane; rows are 512 B apart.
-__device__ __forceinline__ void wm_stage(int id, int n_rows, int64_t Ppad, int64_t p0, int lane,
-                                         const unsigned char *__restrict__ codes, const double *__restrict__ clv,
-                                         const int *__restrict__ scl, unsigned int sdst) {
-  const int g2 = (lane >> 2) * 2, q = lane & 3;
-  if (id < n_rows) {
-    const unsigned char *c = codes + (int64_t)id * Ppad + p0 + (g2 & ~3);  // the aligned word holding codes g2, g2+1
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sdst), "l"(c));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sdst + 4), "l"(c + 16));
-  } else {
-    const double *b = clv + (int64_t)(id - n_rows) * 16 * Ppad + p0 + g2;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const double *src = b + (int64_t)(r * 4 + q) * Ppad;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst + (2 * r) * 512), "l"(src));
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst + (2 * r + 1) * 512), "l"(src + 16));
-    }
-    const int *sp = scl + (int64_t)(id - n_rows) * Ppad + p0 + g2;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst + 8 * 512), "l"(sp));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst + 8 * 512 + 8), "l"(sp + 16));
-  }
-}
 
-// the staged operand in layout V (what wm_load_raw returns); src = this lane's row 0
-__device__ __forceinline__ void wm_unstage(int id, int n_rows, int lane, const double2 *src, double (&x)[WM_V],
-                                           int &s) {
-  const int q = lane & 3;
-  if (id < n_rows) {
-    const uint2 w = *reinterpret_cast<const uint2 *>(src);
-    const int sh = ((lane >> 2) & 1) * 16;  // (g2 & 2) * 8: which half of the aligned word
-    const unsigned int lo = (w.x >> sh) & 0xFFFFu, hi = (w.y >> sh) & 0xFFFFu;
-    unsigned int m[4] = {lo & 255u, lo >> 8, hi & 255u, hi >> 8};
+// Parked vectors (shared memory, per warp) and stack levels (global, per warp): element i = r * 4 + j
+// of this lane sits at [i][lane] (8-byte accesses; 16- and 32-byte layouts measured slower: the wide
+// register tuples cost more in spills than the instructions they save).
+__device__ __forceinline__ void wm_park_store(double *base, int lane, const double (&v)[WM_V]) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const unsigned int mask = m[j] ? m[j] : 15u;
-      const double ind = (mask >> q & 1u) ? 1.0 : 0.0;
-#pragma unroll
-      for (int r = 0; r < 4; r++) x[r * 4 + j] = ind;
-    }
-    s = 0;
-  } else {
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const double2 u = src[(2 * r) * 32], v = src[(2 * r + 1) * 32];
-      x[r * 4] = u.x; x[r * 4 + 1] = u.y; x[r * 4 + 2] = v.x; x[r * 4 + 3] = v.y;
-    }
-    const int4 c = *reinterpret_cast<const int4 *>(src + 8 * 32);
-    s = q == 0 ? c.x : (q == 1 ? c.y : (q == 2 ? c.z : c.w));
-  }
+  for (int i = 0; i < WM_V; i++) base[i * 32 + lane] = v[i];
 }
-#endif
+__device__ __forceinline__ void wm_park_load(const double *base, int lane, double (&v)[WM_V]) {
+#pragma unroll
+  for (int i = 0; i < WM_V; i++) v[i] = base[i * 32 + lane];
+}
+__device__ __forceinline__ double wm_park_at(const double *base, int lane, int i) {
+  return base[i * 32 + lane];
+}
+// stack level base `lv` = stack + level * WM_V * 32 (no lane offset)
+__device__ __forceinline__ void wm_stack_store(double *lv, int lane, const double (&v)[WM_V]) {
+#pragma unroll
+  for (int i = 0; i < WM_V; i++) lv[i * 32 + lane] = v[i];
+}
+__device__ __forceinline__ void wm_stack_load(const double *lv, int lane, double (&v)[WM_V]) {
+#pragma unroll
+  for (int i = 0; i < WM_V; i++) v[i] = lv[i * 32 + lane];
+}
 
 // per pattern: all 16 entries below 2^-256 -> multiply by 2^256 and count (libpll's scaling).
 // A pattern's entries sit in the four lanes of a quad: one vote per pattern group.  The four lanes
 // of a quad would keep identical counters for their four groups; each lane keeps only the one its
-// own site term needs (group jq = lane & 3).  One warp vote first: nothing to do unless some lane
-// holds a group whose entries are all small (the usual case by far).
+// own site term needs (group jq = lane & 3).  (A warp vote in front of the four ballots -- skip them
+// unless some lane holds an all-small group -- measured slower: 5.17 vs 4.90 ms.)
 __device__ __forceinline__ void wm_rescale(double (&n)[WM_V], int &sc, int lane) {
   int hi[4];
 #pragma unroll
   for (int j = 0; j < 4; j++)
     hi[j] = max(max(__double2hiint(n[j]), __double2hiint(n[4 + j])),
                 max(__double2hiint(n[8 + j]), __double2hiint(n[12 + j])));
-#if PLG_WM_PREVOTE
-  if (!__any_sync(0xffffffffu, min(min(hi[0], hi[1]), min(hi[2], hi[3])) < 0x2FF00000)) return;
-#endif
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     const unsigned int big = __ballot_sync(0xffffffffu, hi[j] >= 0x2FF00000);
@@ -233,10 +182,8 @@ __device__ __forceinline__ void wm_emit(double L, int scq, double w, int lane, d
     if (hi < 0x00100000) m = 0.0;      // L == 0: the product is 0 and its log -inf
     if (w == 0.0) { m = 1.0; e = 0; }  // padding pattern
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      m *= __shfl_down_sync(0xffffffffu, m, d);
-      e += __shfl_down_sync(0xffffffffu, e, d);
-    }
+    for (int d = 16; d > 0; d >>= 1) m *= __shfl_down_sync(0xffffffffu, m, d);
+    e = __reduce_add_sync(0xffffffffu, e);
     if (lane == 0) { *dst = m; *dst_e = e; }
   } else {
     double val = w != 0.0 ? w * (log(L * 0.25) + scq * LOG_MINLH) : 0.0;
@@ -246,77 +193,29 @@ __device__ __forceinline__ void wm_emit(double L, int scq, double w, int lane, d
   }
 }
 
-// mantissa / exponent of one site likelihood (see wm_emit)
-__device__ __forceinline__ void wm_split(double L, int scq, double w, double &m, int &e) {
-  int hi = __double2hiint(L);
-  e = -2 - 256 * scq;
-  if (hi < 0x00100000) {
-    L *= TWO256; L *= TWO256;
-    hi = __double2hiint(L);
-    e -= 512;
-  }
-  m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(L));
-  e += (hi >> 20) - 1023;
-  if (hi < 0x00100000) m = 0.0;
-  if (w == 0.0) { m = 1.0; e = 0; }
-}
-
-// Both neighbours of a visit in one shuffle tree (dst == nullptr: that neighbour is not scored).
-template <bool UNIT>
-__device__ __forceinline__ void wm_emit2(double La, int sa, double Lb, int sb, double w, int lane,
-                                         double *__restrict__ dst_a, int *__restrict__ dst_ea,
-                                         double *__restrict__ dst_b, int *__restrict__ dst_eb) {
-  if (UNIT) {
-    double ma, mb;
-    int ea, eb;
-    wm_split(La, sa, w, ma, ea);
-    wm_split(Lb, sb, w, mb, eb);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      ma *= __shfl_down_sync(0xffffffffu, ma, d);
-      mb *= __shfl_down_sync(0xffffffffu, mb, d);
-      ea += __shfl_down_sync(0xffffffffu, ea, d);
-      eb += __shfl_down_sync(0xffffffffu, eb, d);
-    }
-    if (lane == 0) {
-      if (dst_a) { *dst_a = ma; *dst_ea = ea; }
-      if (dst_b) { *dst_b = mb; *dst_eb = eb; }
-    }
-  } else {
-    double va = w != 0.0 ? w * (log(La * 0.25) + sa * LOG_MINLH) : 0.0;
-    double vb = w != 0.0 ? w * (log(Lb * 0.25) + sb * LOG_MINLH) : 0.0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      va += __shfl_down_sync(0xffffffffu, va, d);
-      vb += __shfl_down_sync(0xffffffffu, vb, d);
-    }
-    if (lane == 0) {
-      if (dst_a) { *dst_a = va; *dst_ea = WM_PLAIN; }
-      if (dst_b) { *dst_b = vb; *dst_eb = WM_PLAIN; }
-    }
-  }
-}
 
 // One neighbour chain of a visit in straight-line form: (a, g) = (P_t n, P_h n) category by
 // category; g is consumed at once into the per-group sums of g o h o tvv, a goes to `a_out`
-// (registers) and/or the stack -- so neither a nor g is ever live as a whole vector (the register
-// allocator spills them otherwise at 168 registers).
+// (registers) and/or the stack level `stk_lv` -- so neither a nor g is ever live as a whole vector
+// (the register allocator spills them otherwise at 168 registers).
 template <bool TO_REGS>
 __device__ __forceinline__ void wm_chain(const double (&n)[WM_V], const double (&bf)[4], const double (&h)[WM_V],
-                                         const double (*tvv)[32], int lane, double (&a_out)[WM_V], double *stk_dst,
+                                         const double *tvv, int lane, double (&a_out)[WM_V], double *stk_lv,
                                          bool push, double (&u)[4]) {
 #pragma unroll
-  for (int r = 0; r < 4; r++)
+  for (int r = 0; r < 4; r++) {
+    double a4[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int i = r * 4 + j;
-      double a, g;
-      wm_dmma(a, g, n[i], bf[r]);
-      if (TO_REGS) a_out[i] = a;
-      if (push) stk_dst[i * 32] = a;
-      const double ht = h[i] * tvv[i][lane];
+      double g;
+      wm_dmma(a4[j], g, n[i], bf[r]);
+      if (TO_REGS) a_out[i] = a4[j];
+      if (push) stk_lv[i * 32 + lane] = a4[j];
+      const double ht = h[i] * wm_park_at(tvv, lane, i);
       u[j] = r == 0 ? g * ht : fma(g, ht, u[j]);
     }
+  }
 }
 
 __device__ __forceinline__ int wm_desc_load(const LikWalkVisit *__restrict__ visits, int vi, int lane) {
@@ -325,9 +224,9 @@ __device__ __forceinline__ int wm_desc_load(const LikWalkVisit *__restrict__ vis
   return v;
 }
 
-// MODE 1: unit weights (mantissa/exponent records), 0: weighted (per-lane log), 2: decided at run time
+// MODE 1: unit weights (mantissa/exponent records), 0: weighted (per-lane log)
 template <int MODE>
-__device__ __forceinline__ void wm_search(bool unit_rt, const LikWalkGroup g, const LikWalkVisit *__restrict__ visits, int slice,
+__device__ __forceinline__ void wm_search(const LikWalkGroup g, const LikWalkVisit *__restrict__ visits, int slice,
                                           int n_rows, int64_t Ppad, const unsigned char *__restrict__ codes,
                                           double w_out, double pi_q, int out_off, const double *__restrict__ pmat,
                                           const double *__restrict__ clv, const int *__restrict__ scl,
@@ -340,62 +239,36 @@ __device__ __forceinline__ void wm_search(bool unit_rt, const LikWalkGroup g, co
   int dcur = wm_desc_load(visits, g.first, lane);
   int dnxt = g.count > 1 ? wm_desc_load(visits, g.first + 1, lane) : 0;
   double bf1[4], bf2[4];
-#if PLG_WM_STAGE
-  // staged far-side operands of the visit about to run: [operand][row][lane] 16-byte units
-  const double2 *stg = reinterpret_cast<const double2 *>(&park[2 + PLG_WM_AKSMEM][0][0]) + lane;
-  const unsigned int stg_s = (unsigned int)__cvta_generic_to_shared(stg);
-  wm_stage(__shfl_sync(0xffffffffu, dcur, 2), n_rows, Ppad, p0, lane, codes, clv, scl, stg_s);
-  wm_stage(__shfl_sync(0xffffffffu, dcur, 5), n_rows, Ppad, p0, lane, codes, clv, scl, stg_s + WM_STAGE_ROWS * 512);
-  asm volatile("cp.async.commit_group;\n" ::);
-#endif
   int st;  // scaling counters: this lane's output pattern only (wm_rescale)
   {  // the pruned subtree seen through its branch, once per search
     double x[WM_V], bv[4], t[WM_V], dump[WM_V];
     wm_load_raw(g.tv, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, st);
-    wm_frag(pmat, g.p_v, g.p_v, lane, bv);
+    wm_frag(pmat, g.p_v, lane, bv);
     wm_pair(x, bv, t, dump);
     __syncwarp();
-#pragma unroll
-    for (int i = 0; i < WM_V; i++) park[0][i][lane] = t[i];
+    wm_park_store(&park[0][0][0], lane, t);
   }
   int sk = 0;
-#if PLG_WM_AKSMEM
-  double *aks = &park[2][0][lane];  // a = P_in (incoming partial), handed from visit to visit: aks[i * 32]
-#else
   double ak[WM_V];  // a = P_in (incoming partial), handed from visit to visit
 #pragma unroll
   for (int i = 0; i < WM_V; i++) ak[i] = 0.0;
-#endif
   for (int vi = g.first; vi < v_end; vi++) {
-    const int x_in = __shfl_sync(0xffffffffu, dcur, 0), p_in = __shfl_sync(0xffffffffu, dcur, 1);
+    const int x_in = __shfl_sync(0xffffffffu, dcur, 0);
     const int d1 = __shfl_sync(0xffffffffu, dcur, 2), d2 = __shfl_sync(0xffffffffu, dcur, 5);
     const int tree1 = __shfl_sync(0xffffffffu, dcur, 8), tree2 = __shfl_sync(0xffffffffu, dcur, 9);
     const int push = __shfl_sync(0xffffffffu, dcur, 11);
     int dnn = 0;
     if (vi + 2 < v_end) dnn = wm_desc_load(visits, vi + 2, lane);
-    wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 3), __shfl_sync(0xffffffffu, dcur, 4), lane, bf1);
-    wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 6), __shfl_sync(0xffffffffu, dcur, 7), lane, bf2);
+    wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 3), lane, bf1);  // (P_t1, P_h1): the half is implied by the branch
+    wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 6), lane, bf2);
     if (x_in >= 0) {  // first step of a side: a = P_in X from a stored operand
       double x[WM_V], bi[4], dump[WM_V];
       wm_load_raw(x_in, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, sk);
-      wm_frag(pmat, p_in, p_in, lane, bi);
-#if PLG_WM_AKSMEM
-      double a0[WM_V];
-      wm_pair(x, bi, a0, dump);
-#pragma unroll
-      for (int i = 0; i < WM_V; i++) aks[i * 32] = a0[i];
-#else
+      wm_frag(pmat, __shfl_sync(0xffffffffu, dcur, 1), lane, bi);
       wm_pair(x, bi, ak, dump);
-#endif
     } else if (x_in <= -2) {
       const int lvl = -2 - x_in;
-#if PLG_WM_AKSMEM
-#pragma unroll
-      for (int i = 0; i < WM_V; i++) aks[i * 32] = stk[(lvl * WM_V + i) * 32];
-#else
-#pragma unroll
-      for (int i = 0; i < WM_V; i++) ak[i] = stk[(lvl * WM_V + i) * 32];
-#endif
+      wm_stack_load(stk + (int64_t)lvl * WM_V * 32, lane, ak);
       sk = stks[lvl * 4 * 32];
     }
     // D1 once: N2 = a o P_t1 D1 (the partial toward d2) and h1 = P_h1 D1 (far side of edge 1)
@@ -403,20 +276,12 @@ __device__ __forceinline__ void wm_search(bool unit_rt, const LikWalkGroup g, co
     int s1, sc2;
     {
       double x[WM_V], h1[WM_V];
-#if PLG_WM_STAGE
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-      wm_unstage(d1, n_rows, lane, stg, x, s1);
-#else
       wm_load_raw(d1, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, s1);
-#endif
       wm_pair(x, bf1, n2, h1);
       __syncwarp();
 #pragma unroll
-#if PLG_WM_AKSMEM
-      for (int i = 0; i < WM_V; i++) { n2[i] *= aks[i * 32]; park[1][i][lane] = h1[i]; }
-#else
-      for (int i = 0; i < WM_V; i++) { n2[i] *= ak[i]; park[1][i][lane] = h1[i]; }
-#endif
+      for (int i = 0; i < WM_V; i++) n2[i] *= ak[i];
+      wm_park_store(&park[1][0][0], lane, h1);
     }
     sc2 = sk + s1;
     wm_rescale(n2, sc2, lane);
@@ -425,78 +290,34 @@ __device__ __forceinline__ void wm_search(bool unit_rt, const LikWalkGroup g, co
     int s2, sc1;
     {
       double x[WM_V];
-#if PLG_WM_STAGE
-      wm_unstage(d2, n_rows, lane, stg + WM_STAGE_ROWS * 32, x, s2);
-      if (vi + 1 < v_end) {  // both operands are in registers: fetch the next visit's into the same slots
-        wm_stage(__shfl_sync(0xffffffffu, dnxt, 2), n_rows, Ppad, p0, lane, codes, clv, scl, stg_s);
-        wm_stage(__shfl_sync(0xffffffffu, dnxt, 5), n_rows, Ppad, p0, lane, codes, clv, scl,
-                 stg_s + WM_STAGE_ROWS * 512);
-        asm volatile("cp.async.commit_group;\n" ::);
-      }
-#else
       wm_load_raw(d2, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, s2);
-#endif
       wm_pair(x, bf2, n1, h2);
 #pragma unroll
-#if PLG_WM_AKSMEM
-      for (int i = 0; i < WM_V; i++) n1[i] *= aks[i * 32];
-#else
       for (int i = 0; i < WM_V; i++) n1[i] *= ak[i];
-#endif
     }
     sc1 = sk + s2;
     wm_rescale(n1, sc1, lane);
     // Visits come in normal form (planners): the partial toward c1 continues in registers, the
-    // one toward c2 is at most parked.  Side 2 first, so that its hand-over is on the stack (and
-    // dead) before side 1's lands directly in ak.
-#if PLG_WM_DUAL
-    double L2;
-    int q2;
-#endif
-    {  // side 2: toward c2 (at most parked) and neighbour 2 (insertion into x--c2)
-      double u[4], dummy[WM_V];
-      wm_chain<false>(n2, bf2, h2, park[0], lane, dummy, stk + (int64_t)(push >= 0 ? push : 0) * WM_V * 32, push >= 0, u);
-      if (push >= 0) stks[push * 4 * 32] = sc2;
-#if PLG_WM_DUAL
-      L2 = wm_site_L(u, pi_q, lane);
-      q2 = sc2 + s2 + st;
-#else
-      if (tree2 >= 0) {
-        const int64_t o = (int64_t)tree2 * pstride + slice;
-        const double L = wm_site_L(u, pi_q, lane);
-        if (MODE == 2 ? unit_rt : MODE == 1) wm_emit<true>(L, sc2 + s2 + st, w_out, lane, partial + o, partial_e + o);
-        else wm_emit<false>(L, sc2 + s2 + st, w_out, lane, partial + o, partial_e + o);
-      }
-#endif
-    }
-    {  // side 1: toward c1 (straight into ak) and neighbour 1 (insertion into x--c1)
-      double u[4], h1[WM_V];
-#pragma unroll
-      for (int i = 0; i < WM_V; i++) h1[i] = park[1][i][lane];
-#if PLG_WM_AKSMEM
+    // one toward c2 is at most parked.
+    double u1[4], u2[4];
+    {  // side 2 first, so that its hand-over is on the stack (and dead) before side 1's lands directly in ak
       double dummy[WM_V];
-      wm_chain<false>(n1, bf1, h1, park[0], lane, dummy, aks, true, u);  // a' straight into its shared-memory slots
-#else
-      wm_chain<true>(n1, bf1, h1, park[0], lane, ak, nullptr, false, u);
-#endif
-      sk = sc1;
-#if PLG_WM_DUAL
-      const double L1 = wm_site_L(u, pi_q, lane);
-      const int64_t o1 = (int64_t)(tree1 >= 0 ? tree1 : 0) * pstride + slice, o2 = (int64_t)(tree2 >= 0 ? tree2 : 0) * pstride + slice;
-      if (MODE == 2 ? unit_rt : MODE == 1)
-        wm_emit2<true>(L1, sc1 + s1 + st, L2, q2, w_out, lane, tree1 >= 0 ? partial + o1 : nullptr, partial_e + o1,
-                       tree2 >= 0 ? partial + o2 : nullptr, partial_e + o2);
-      else
-        wm_emit2<false>(L1, sc1 + s1 + st, L2, q2, w_out, lane, tree1 >= 0 ? partial + o1 : nullptr, partial_e + o1,
-                        tree2 >= 0 ? partial + o2 : nullptr, partial_e + o2);
-#else
-      if (tree1 >= 0) {
-        const int64_t o = (int64_t)tree1 * pstride + slice;
-        const double L = wm_site_L(u, pi_q, lane);
-        if (MODE == 2 ? unit_rt : MODE == 1) wm_emit<true>(L, sc1 + s1 + st, w_out, lane, partial + o, partial_e + o);
-        else wm_emit<false>(L, sc1 + s1 + st, w_out, lane, partial + o, partial_e + o);
-      }
-#endif
+      wm_chain<false>(n2, bf2, h2, &park[0][0][0], lane, dummy, stk + (int64_t)(push >= 0 ? push : 0) * WM_V * 32, push >= 0, u2);
+      if (push >= 0) stks[push * 4 * 32] = sc2;
+    }
+    if (tree2 >= 0) {  // neighbour 2 = insertion into x--c2
+      const int64_t o = (int64_t)tree2 * pstride + slice;
+      wm_emit<MODE == 1>(wm_site_L(u2, pi_q, lane), sc2 + s2 + st, w_out, lane, partial + o, partial_e + o);
+    }
+    {
+      double h1[WM_V];
+      wm_park_load(&park[1][0][0], lane, h1);
+      wm_chain<true>(n1, bf1, h1, &park[0][0][0], lane, ak, nullptr, false, u1);
+    }
+    sk = sc1;
+    if (tree1 >= 0) {  // neighbour 1 = insertion into x--c1
+      const int64_t o = (int64_t)tree1 * pstride + slice;
+      wm_emit<MODE == 1>(wm_site_L(u1, pi_q, lane), sc1 + s1 + st, w_out, lane, partial + o, partial_e + o);
     }
     dcur = dnxt; dnxt = dnn;
   }
@@ -513,7 +334,7 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 3;
   double(*park)[WM_V][32] = reinterpret_cast<double(*)[WM_V][32]>(wm_smem + warp * WM_SMEM_DOUBLES_PER_WARP);  // [0] tvv, [1] h1
   const int64_t gw = (int64_t)blockIdx.x * WM_WARPS + warp;
-  double *stk = stack_clv + gw * stack_levels * WM_V * 32 + lane;
+  double *stk = stack_clv + gw * stack_levels * WM_V * 32;  // level l at stk + l * WM_V * 32 (wm_stack_store)
   int *stks = stack_scl + gw * stack_levels * 4 * 32 + lane;
   const double pi_q = model->freqs[q];
   // the pattern whose site term this lane ends up with (wm_site_L): pattern(j = q, g)
@@ -527,17 +348,12 @@ walk4m_kernel(const LikWalkGroup *__restrict__ groups, int n_groups, const LikWa
     const LikWalkGroup g = groups[item - (unsigned long long)slice * n_groups];
     const double w_out = weights[(int64_t)slice * WM_PATTERNS + out_off];
     const bool unit = __all_sync(0xffffffffu, w_out == 1.0 || w_out == 0.0);
-#if PLG_WM_RTUNIT
-    wm_search<2>(unit, g, visits, slice, n_rows, Ppad, codes, w_out, pi_q, out_off, pmat, clv, scl, stk, stks, park,
-                 partial, partial_e, pstride, lane);
-#else
     if (unit)
-      wm_search<1>(true, g, visits, slice, n_rows, Ppad, codes, w_out, pi_q, out_off, pmat, clv, scl, stk, stks, park,
+      wm_search<1>(g, visits, slice, n_rows, Ppad, codes, w_out, pi_q, out_off, pmat, clv, scl, stk, stks, park,
                    partial, partial_e, pstride, lane);
     else
-      wm_search<0>(false, g, visits, slice, n_rows, Ppad, codes, w_out, pi_q, out_off, pmat, clv, scl, stk, stks, park,
+      wm_search<0>(g, visits, slice, n_rows, Ppad, codes, w_out, pi_q, out_off, pmat, clv, scl, stk, stks, park,
                    partial, partial_e, pstride, lane);
-#endif
   }
 }
 
