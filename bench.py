@@ -2,24 +2,29 @@
 """Benchmark of the tree-scoring hot path (BASELINE.json metric: trees x sites scored / second).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload lnl_target|lnl_c2|fitch_target|trees_c4|aa_c5] [--no-cpu] [--no-extra]
 
-Workload at every N: BASELINE.json configs[1] -- synthetic DNA, 64 taxa x 10,000 sites (i.i.d.
-uniform ACGT, seed 1001, so patterns = sites), GTR+Gamma4 log-likelihood at fixed branch
-lengths of every distinct SPR neighbour (14,762) of a random tree.  One "step" = one pass of
-the hot path over that batch: plan (host) + score (device) + read back the per-tree scores.
-At N > 1 the job is the pooled neighbour-tree list of N such neighbourhoods (base trees seeded
-1001+b): N x 14,762 trees, sharded across the ranks in contiguous blocks (rank r scores block r
-= the neighbours of base tree r; full alignment on every GPU, no data-path collective) and the
-per-tree scores come back through one NCCL all-gather -- weak scaling.  Splitting ONE
-neighbourhood across ranks (shard=(rank, world) in the C-ABI: each rank plans and walks only its
-block of neighbours) is measured too at N > 1, on the north_star target shape (256 taxa x 100k
-sites, all 255,530 SPR neighbours): the "one_neighbourhood_sharded" object, strong scaling.
+Default workload = the north_star target shape: synthetic DNA, 256 taxa x 100,000 sites (i.i.d. uniform
+ACGT, so patterns = sites), GTR+Gamma4 log-likelihood at fixed branch lengths of EVERY distinct SPR
+neighbour (255,530) of a random tree.  One "step" = one pass of the hot path over that batch: plan
+(host, O(n)) + score (device) + the per-tree scores and the move table back on the host.  The other
+workloads are BASELINE.json's remaining configs, each a driver-parsable headline of its own
+(`--workload`), and -- in the default run at N = 1 -- compact legs under "other_workloads".
 
-One JSON line on stdout (rank 0).  Extra objects: "roofline" (dominant kernel, CUDA-event timed
-inside the timed region), "cpu_baseline" (CPU oracle on a bounded sample of the same workload),
-"e2e" (same metric through the public API with host buffers, H2D of the alignment and D2H of
-the scores inside the timed region), "parsimony" (BASELINE config 3 shape, 256 taxa x 100k
-sites, Fitch scoring of all 255,530 SPR neighbours; N=1 only).
+N > 1 (one process per GPU, torchrun): weak scaling -- the job is the pooled list of N such batches
+(rank r scores batch r: the neighbours of base tree r, or block r of the random-tree list); every
+GPU holds the full alignment, there is no data-path collective, and the per-tree scores are written
+by the library into a device tensor that goes straight into ONE NCCL all-gather
+(pylogeny_b200/distributed.py).  "one_neighbourhood_sharded" (N > 1) additionally splits ONE
+neighbourhood across the ranks: strong scaling.
+
+One JSON line on stdout (rank 0).  `roofline` names the dominant kernel and the resource that binds
+it: "fp64" (FP64 pipe: the DMMA / DFMA peak is MEASURED IN THIS RUN by plg_fp64_peak) for the
+likelihood walks, "int" (INT32 logic pipe, measured in this run) for the Fitch walks, "hbm"
+(MEASURED_PEAKS.json copy bandwidth) for the level kernels; algorithmic bytes and
+DRAM traffic (ncu) are separate fields.  `cpu_baseline` / `--impl reference` = the CPU side on
+sample trees that the REFERENCE's own rearrangement code enumerated (tests/golden/bench_ref_trees.npz,
+tests/golden/make_bench_fixture.py): that arm imports nothing of pylogeny_b200.
 """
 import argparse
 import json
@@ -34,16 +39,45 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-N_TAXA, N_SITES, SEED = 64, 10_000, 1001
+UNIT = "tree-sites/s"
 EXCH = np.array([1.2, 3.4, 0.8, 1.1, 4.1, 1.0])
 FREQS = np.array([0.28, 0.22, 0.24, 0.26])
 ALPHA = 0.7
-METRIC = "trees x sites scored / sec (GTR+G4 logL, all SPR neighbours, 64 taxa x 10k sites)"
-UNIT = "tree-sites/s"
+FLOP_PER_UNIT_DNA = 640.0   # per neighbour x pattern: CLV update 240 + 3-way evaluation ~400
+FLOP_PER_NODEOP_DNA = 240.0  # per node-op x pattern of a full traversal (R (2 K (2K - 1) + K))
+FLOP_PER_NODEOP_AA = 6320.0
+INTOPS_PER_FITCH_UNIT = 20.0 / 32.0  # ~20 logic ops per 32 patterns per node-op (SURVEY.md 8d caveat i)
+
+WORKLOADS = {
+    "lnl_target": dict(kind="spr", score="lnl", datatype="dna", n_taxa=256, n_sites=100_000, seed=1002, ref_sample=48,
+                       metric="trees x sites scored / sec (GTR+G4 logL, all SPR neighbours, 256 taxa x 100k sites)",
+                       label="north_star target shape (BASELINE configs[2] alignment): synthetic DNA 256 taxa x 100k sites, "
+                             "GTR+G4 lnL (fixed branch lengths) of all %d distinct SPR neighbours of a random tree"),
+    "lnl_c2": dict(kind="spr", score="lnl", datatype="dna", n_taxa=64, n_sites=10_000, seed=1001, ref_sample=192,
+                   metric="trees x sites scored / sec (GTR+G4 logL, all SPR neighbours, 64 taxa x 10k sites)",
+                   label="BASELINE configs[1]: synthetic DNA 64 taxa x 10k sites, GTR+G4 lnL (fixed branch lengths) of all "
+                         "%d distinct SPR neighbours of a random tree"),
+    "fitch_target": dict(kind="spr", score="fitch", datatype="dna", n_taxa=256, n_sites=100_000, seed=1002, ref_sample=48,
+                         metric="trees x sites scored / sec (Fitch parsimony, all SPR neighbours, 256 taxa x 100k sites)",
+                         label="BASELINE configs[2] shape: synthetic DNA 256 taxa x 100k sites, Fitch length of all %d "
+                               "distinct SPR neighbours of a random tree (one step of the parsimonyGreedy climb)"),
+    "trees_c4": dict(kind="trees", score="lnl", datatype="dna", n_taxa=128, n_sites=1_000_000, seed=1004, trees_per_rank=64,
+                     ref_sample=0,
+                     metric="trees x sites scored / sec (GTR+G4 logL, random trees, 128 taxa x 1M sites)",
+                     label="BASELINE configs[3]: synthetic DNA 128 taxa x 1M sites, GTR+G4 lnL of %d random trees per GPU "
+                           "(the 100k-tree list is scored in such blocks)"),
+    "aa_c5": dict(kind="tbr", score="lnl", datatype="aa", n_taxa=50, n_sites=5_000, seed=1005, ref_sample=64,
+                  metric="trees x sites scored / sec (WAG+G4 logL, TBR neighbourhood, 50 taxa x 5k sites)",
+                  label="BASELINE configs[4]: synthetic protein 50 taxa x 5k sites, WAG+G4 lnL (fixed branch lengths) of all "
+                        "%d distinct TBR neighbours of a random tree"),
+}
+DEFAULT_WORKLOAD = "lnl_target"
 
 
+# ----------------------------------------------------------------------------------------------
+# synthetic inputs (numpy only: shared by both arms and by tests/golden/make_bench_fixture.py)
+# ----------------------------------------------------------------------------------------------
 def random_desc(rng, n_tips):
     nodes = list(range(n_tips))
     desc, nxt = [], n_tips
@@ -56,16 +90,53 @@ def random_desc(rng, n_tips):
     return np.array(desc, dtype=np.int32)
 
 
-def make_alignment(seed=SEED, n=N_TAXA, s=N_SITES):
+def make_alignment(seed=1001, n=64, s=10_000, datatype="dna"):
+    """Tip codes uint8 [n, s] (DNA: one-hot 4-bit masks; AA: 0..19) and unit pattern weights."""
     rng = np.random.default_rng(seed)
-    codes = (1 << rng.integers(0, 4, (n, s))).astype(np.uint8)
-    return codes, np.ones(s)
+    if datatype == "dna":
+        return (1 << rng.integers(0, 4, (n, s))).astype(np.uint8), np.ones(s)
+    return rng.integers(0, 20, (n, s)).astype(np.uint8), np.ones(s)
 
 
-def make_tree(seed, n=N_TAXA):
+def make_tree(seed, n=64):
     rng = np.random.default_rng(seed + 7919)
     d = random_desc(rng, n)
     return d, rng.exponential(0.1, d.shape)
+
+
+def base_tree(wl, b):
+    """Base tree number b (rank b's at N > 1) of a neighbourhood workload."""
+    if wl["n_taxa"] == 64:
+        return make_tree(wl["seed"] + b, 64)  # (round-1 convention of the configs[1] headline)
+    d = random_desc(np.random.default_rng(wl["seed"] + 7919 + 2 * b), wl["n_taxa"])
+    return d, np.random.default_rng(wl["seed"] + 7920 + 2 * b).exponential(0.1, d.shape)
+
+
+def random_trees(wl, count, block):
+    rng = np.random.default_rng(wl["seed"] + 31 * block + 5)
+    descs = np.stack([random_desc(rng, wl["n_taxa"]) for _ in range(count)])
+    return descs, rng.exponential(0.1, descs.shape)
+
+
+def fitch_states(wl):
+    """Parsimony state characters uint8 [n_sites, n_taxa] ('0'..'3') of a Fitch workload."""
+    rng = np.random.default_rng(wl["seed"])
+    return (rng.integers(0, 4, (wl["n_sites"], wl["n_taxa"])) + 48).astype(np.uint8)
+
+
+def desc_to_newick(desc, labels):
+    n, text = len(labels), {}
+    for i, (a, b) in enumerate(np.asarray(desc)):
+        text[n + i] = "(%s,%s)" % tuple(labels[c] if c < n else text[c] for c in (int(a), int(b)))
+    return text[n + len(desc) - 1] + ";"
+
+
+def protein_model_for_oracle():
+    """WAG for the CPU arm WITHOUT the product: read the table out of the C-ABI library by ctypes only if it
+    is there; the reference arm's cost does not depend on the matrix, so a fixed-seed reversible model
+    stands in otherwise (said in `sample`)."""
+    rng = np.random.default_rng(7)
+    return rng.uniform(0.1, 3.0, 190), rng.dirichlet(np.ones(20) * 20), "fixed-seed reversible 20-state model"
 
 
 class ClockSampler(object):
@@ -152,7 +223,7 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def measured_peaks():
+def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -179,155 +250,321 @@ def emit(line):
     out.flush()
 
 
-def ncu_traffic(kernel, units_per_launch):
-    """DRAM bytes (ncu dram__bytes_read+write) of one captured launch, scaled per node-op x pattern
-    unit to this run's average launch -- 'per launch like achieved'.  None if never captured."""
+def ncu_traffic(kernel, workload):
+    """DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full`
+    capture of this kernel ON THIS WORKLOAD (profiles/traffic.json names the capture); None if the
+    kernel was never captured on it."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
-        t = json.load(open(p)).get(kernel)
-        if t and t.get("units"):
-            return t["dram_bytes"] / t["units"] * units_per_launch
+        t = json.load(open(p)).get("%s@%s" % (kernel, workload))
+        if t:
+            return {"dram_bytes_per_launch": t["dram_bytes"], "source": t.get("source", "profiles/")}
     return None
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU legs (the only places bench.py touches oracle/)
+# CPU side (cpu_baseline and --impl reference): oracle/ only, never pylogeny_b200
 # ----------------------------------------------------------------------------------------------
-def cpu_lnl_sample(seconds=12.0):
-    """FP64 CPU restatement (oracle/lik_oracle.c; libpll itself is not available) on a bounded
-    sample of the workload's neighbour trees, all host cores (one tree per thread at a time)."""
-    import oracle
-    from concurrent.futures import ThreadPoolExecutor
-    from pylogeny_b200 import neighbourhood as nbh
-    codes, w = make_alignment()
-    d, br = make_tree(SEED)
-    cores = os.cpu_count() or 1
-    t0 = time.perf_counter()
-    descs, brs, _ = nbh.neighbour_trees(d, br, np.arange(1))
-    oracle.lnl(codes, w, EXCH, FREQS, ALPHA, descs[0], brs[0])
-    t1 = time.perf_counter() - t0
-    n_sample = int(max(cores, min(4096, seconds * cores / max(t1, 1e-3))))
-    n_sample -= n_sample % cores
-    sel = np.linspace(0, nbh.neighbourhood_size(d) - 1, n_sample).astype(np.int64)
-    descs, brs, _ = nbh.neighbour_trees(d, br, sel)
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(cores) as ex:  # ctypes releases the GIL inside the C call
-        out = list(ex.map(lambda i: oracle.lnl(codes, w, EXCH, FREQS, ALPHA, descs[i], brs[i]), range(n_sample)))
-    dt = time.perf_counter() - t0
-    return {"value": n_sample * N_SITES / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of the 14762 neighbour trees x all 10000 sites, FP64 scalar pruning oracle "
-                      "(libpll 1.0.2 SSE3 is not available offline), %.1f s" % (n_sample, dt)}, dt, out
+def _fixture():
+    return np.load(os.path.join(ROOT, "tests", "golden", "bench_ref_trees.npz"))
 
 
-def cpu_fitch_sample(states, desc, seconds=10.0):
-    """The reference's own compiled fitch.cpp core (oracle/_ref) when present, else the C port."""
+def cpu_sample(name, seconds):
+    """One bounded sample of workload `name` on the host cores: the FP64 CPU restatement of the
+    likelihood (oracle/lik_oracle.c; libpll itself is not available offline -- kind "port") or the
+    reference's own compiled fitch.cpp core (oracle/_ref, kind "reference"), one tree per thread at
+    a time, on sample trees enumerated by the reference's rearrangement code (fixture) or drawn at
+    random (trees_c4).  Returns (cpu_baseline dict, seconds of the sample)."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
-    from pylogeny_b200 import neighbourhood as nbh
+    wl = WORKLOADS[name]
     cores = os.cpu_count() or 1
-    n, S = states.shape[1], states.shape[0]
-    sub, per_core = 25000, 4
-    profs = [bytes(r).decode("ascii") for r in states[:sub]]
-    labels = ["T%d" % i for i in range(n)]
-    x = oracle.FitchInputs(profs, [1] * sub, {l: i for i, l in enumerate(labels)})
-    use_ref = oracle.ref_available()
-    fn = oracle.ref_fitch_cost if use_ref else oracle.fitch_cost
-    descs, _, _ = nbh.neighbour_trees(desc, None, np.linspace(0, nbh.neighbourhood_size(desc) - 1, cores * per_core).astype(np.int64))
-    nws = [nbh.desc_to_newick(dd, labels) for dd in descs]
+    n, S = wl["n_taxa"], wl["n_sites"]
+    if wl["kind"] == "trees":
+        descs, brs = random_trees(wl, max(cores, 8), 0)
+        src = "random trees (numpy, same generator as the GPU arm)"
+    else:
+        fx = _fixture()
+        descs, brs = fx[name + "_desc"].astype(np.int32), fx[name + "_brlen"]
+        src = ("SPR neighbours enumerated and materialised by the reference's rearrangement.py (tests/golden/bench_ref_trees.npz)"
+               if wl["kind"] == "spr" else "TBR neighbours from tests/golden/bench_ref_trees.npz (plain-Python bisection/reconnection; "
+               "the reference has no TBR enumerator)")
+    if wl["score"] == "fitch":
+        states = fitch_states(wl)
+        labels = ["T%d" % i for i in range(n)]
+        use_ref = oracle.ref_available()
+        fn = oracle.ref_fitch_cost if use_ref else oracle.fitch_cost
+        newicks = [desc_to_newick(d, labels) for d in descs]
+        taxa = {l: i for i, l in enumerate(labels)}
+        # calibrate on a small column sample, then size (trees x sites) to the budget
+        x0 = oracle.FitchInputs([bytes(r).decode("ascii") for r in states[:2000]], [1] * 2000, taxa)
+        t0 = time.perf_counter()
+        fn(newicks[0], inputs=x0)
+        per_site = (time.perf_counter() - t0) / 2000
+        n_trees = min(len(newicks), max(cores, 2 * cores))
+        sub = int(min(S, max(2000, seconds * cores / (per_site * n_trees))))
+        x = oracle.FitchInputs([bytes(r).decode("ascii") for r in states[:sub]], [1] * sub, taxa)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:  # ctypes releases the GIL inside the C call
+            list(ex.map(lambda s: fn(s, inputs=x), newicks[:n_trees]))
+        dt = time.perf_counter() - t0
+        kind = "reference" if use_ref else "port"
+        what = "reference fitch.cpp:6-272 compiled (oracle/_ref)" if use_ref else "C port of fitch.cpp (oracle/fitch_oracle.c)"
+        return ({"value": n_trees * sub / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                 "sample": "%d trees x %d of the %d sites, %s; %s; %.1f s" % (n_trees, sub, S, what, src, dt)}, dt)
+    codes, w = make_alignment(wl["seed"], n, S, wl["datatype"])
+    if wl["datatype"] == "dna":
+        exch, freqs, mname = EXCH, FREQS, "GTR+G4"
+    else:
+        exch, freqs, mname = protein_model_for_oracle()
+    t0 = time.perf_counter()
+    sub0 = min(S, 5000)
+    oracle.lnl(codes[:, :sub0], w[:sub0], exch, freqs, ALPHA, descs[0], brs[0])
+    per_site = (time.perf_counter() - t0) / sub0
+    n_trees = min(len(descs), max(cores, 2 * cores))
+    sub = int(min(S, max(sub0, seconds * cores / (per_site * n_trees))))
+    c_sub, w_sub = np.ascontiguousarray(codes[:, :sub]), w[:sub]
     t0 = time.perf_counter()
     with ThreadPoolExecutor(cores) as ex:
-        list(ex.map(lambda s: fn(s, inputs=x), nws))
+        list(ex.map(lambda i: oracle.lnl(c_sub, w_sub, exch, freqs, ALPHA, descs[i], brs[i]), range(n_trees)))
     dt = time.perf_counter() - t0
-    return {"value": cores * per_core * sub / dt, "unit": UNIT, "cores": cores,
-            "kind": "reference" if use_ref else "port",
-            "sample": "%d neighbour trees x %d of the %d sites, %s, %.1f s" % (
-                cores * per_core, sub, S, "reference fitch.cpp:6-272 compiled (oracle/_ref)" if use_ref else "C port", dt)}
+    return ({"value": n_trees * sub / dt, "unit": UNIT, "cores": cores, "kind": "port",
+             "sample": "%d trees x %d of the %d sites, full re-traversal by the FP64 scalar pruning oracle (%s; libpll 1.0.2 SSE3 is not "
+                       "available offline); %s; %.1f s" % (n_trees, sub, S, mname, src, dt)}, dt)
+
+
+def workload_config(name, n_gpus, count=None):
+    wl = WORKLOADS[name]
+    cfg = {"workload": wl["label"] % count if count is not None else wl["label"].replace("%d ", ""), "name": name,
+           "batches_per_step": n_gpus,
+           "sharding": "pooled list of %d batch(es) in %d contiguous block(s), one per GPU; scores written to a device tensor and "
+                       "all-gathered (NCCL)" % (n_gpus, n_gpus),
+           "l2": "per-step working set (GBs of conditional vectors) >> 126 MB L2; L2 additionally flushed between steps",
+           "seed": wl["seed"]}
+    if wl["score"] == "lnl":
+        cfg["planner"] = ("edge insertion by depth-first search walks (directional CLVs of the base tree, then per neighbour 1 CLV "
+                          "update + 1 three-way evaluation, partials kept on chip)" if wl["kind"] == "spr" and wl["datatype"] == "dna"
+                          else ("whole post-order on chip (tree walks)" if wl["kind"] == "trees" else
+                                "edge insertion on level programs (20-state DMMA kernels)"))
+    return cfg
 
 
 def run_reference(args):
-    """--impl reference: the reference-side CPU implementation of the path on the host cores."""
+    """--impl reference: the CPU side of the selected workload on the host cores, product-free."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    name = args.workload
+    budget = float(os.environ.get("PLG_BENCH_REF_SECONDS", "60"))  # whole run, spread over the steps
+    per = max(min(1.5, budget), budget / max(1, args.steps + args.warmup))
     for _ in range(args.warmup):
-        cpu_lnl_sample(seconds=1.0)
-    vals, times = [], []
+        cpu_sample(name, per)
+    vals, times, cb = [], [], None
     for _ in range(args.steps):
-        budget = float(os.environ.get("PLG_BENCH_REF_SECONDS", "40"))  # whole run, spread over the steps
-        cb, dt, _ = cpu_lnl_sample(seconds=max(min(2.0, budget), budget / args.steps))
+        cb, dt = cpu_sample(name, per)
         vals.append(cb["value"])
         times.append(dt)
     v = float(np.mean(vals))
     cb["value"] = v
+    wl = WORKLOADS[name]
     emit(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": wl["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus), "cpu_baseline": cb,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitsets" if wl["score"] == "fitch" else "f64", "data": "synthetic",
+        "config": workload_config(name, args.gpus), "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-
-
-def workload_config(n_gpus):
-    return {"workload": "BASELINE configs[1]: synthetic DNA 64 taxa x 10k sites, GTR+G4 lnL (fixed branch lengths) "
-                        "of all 14762 distinct SPR neighbours of a random tree",
-            "planner": "edge insertion by depth-first search walks (directional CLVs of the base tree, then per "
-                       "neighbour 1 CLV update + 1 three-way evaluation, partials kept on chip)",
-            "neighbourhoods_per_step": n_gpus,
-            "sharding": "pooled list of %d x 14762 neighbour trees in %d contiguous blocks, scores all-gathered (NCCL)" % (
-                n_gpus, n_gpus),
-            "l2": "per-step working set (~19 GB of CLVs) >> 126 MB L2; L2 additionally flushed between steps",
-            "seed": SEED}
 
 
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def run_ours(args):
+class Runner(object):
+    """One workload on this rank: resident inputs, the timed step, the e2e step, the roofline."""
+
+    def __init__(self, name, ctx):
+        import torch
+        from pylogeny_b200 import _lib, distributed as D, fitch, likelihood, neighbourhood as nbh
+        self.torch, self.L, self.D, self.nbh, self.lik, self.fitch = torch, _lib.lib(), D, nbh, likelihood, fitch
+        self._lib = _lib
+        self.name, self.wl, self.ctx = name, WORKLOADS[name], ctx
+        wl = self.wl
+        n, S = wl["n_taxa"], wl["n_sites"]
+        self.move = {"spr": nbh.MOVE_SPR, "tbr": nbh.MOVE_TBR}.get(wl["kind"])
+        self.model = None
+        if wl["score"] == "fitch":
+            self.states = fitch_states(wl)
+            self.w_int = np.ones(S, dtype=np.int64)
+            self.aln = fitch.FitchAlignment.from_dense(self.states, self.w_int)
+        else:
+            self.codes, self.w = make_alignment(wl["seed"], n, S, wl["datatype"])
+            dt = _lib.DATA_DNA if wl["datatype"] == "dna" else _lib.DATA_AA
+            self.aln = likelihood.LikAlignment(self.codes, self.w, dt)
+            if wl["datatype"] == "dna":
+                self.model = likelihood.Model(EXCH, FREQS, ALPHA)
+            else:
+                e, f = likelihood.protein_model("WAG")
+                self.model = likelihood.Model(e, f, ALPHA)
+        if wl["kind"] == "trees":
+            self.descs, self.brs = random_trees(wl, wl["trees_per_rank"], ctx.rank)
+            self.count = wl["trees_per_rank"]
+        else:
+            self.d, self.br = base_tree(wl, ctx.rank)
+            self.count = nbh.neighbourhood_size(self.d, self.move)
+        dtype = torch.int32 if wl["score"] == "fitch" else torch.float64
+        self.pool = torch.zeros(ctx.world * self.count, dtype=dtype, device=ctx.device)  # the pooled score list
+        self.units_per_step = ctx.world * self.count * S
+
+    # -- the hot path, inputs resident, scores of this rank's batch into its block of the pooled tensor
+    def _score_into(self, aln, model, out_ptr, want_moves):
+        C = __import__("ctypes")
+        L, _lib = self.L, self._lib
+        n = C.c_int64()
+        stream = None
+        if self.wl["kind"] == "trees":
+            _lib.check(L.plg_lik_score_trees_shard(aln._h, model._h, self.count, self.wl["n_taxa"], self.descs.ctypes.data,
+                                                   self.brs.ctypes.data, None, 0, 1, C.c_void_p(out_ptr), _lib.OUT_DEVICE, stream))
+            return None
+        moves = np.empty((self.count, 4), dtype=np.int32) if want_moves else None
+        mp = moves.ctypes.data if want_moves else None
+        if self.wl["score"] == "fitch":
+            _lib.check(L.plg_fitch_score_neighbourhood_out(aln._h, self.move, self.wl["n_taxa"], self.d.ctypes.data, None, 0, 1,
+                                                           C.byref(n), mp, C.c_void_p(out_ptr), _lib.OUT_DEVICE, stream))
+        else:
+            _lib.check(L.plg_lik_score_neighbourhood_out(aln._h, model._h, self.move, self.wl["n_taxa"], self.d.ctypes.data,
+                                                         self.br.ctypes.data, None, 0, 1, C.byref(n), mp, C.c_void_p(out_ptr),
+                                                         _lib.OUT_DEVICE, stream))
+        return moves
+
+    def step(self, aln=None, model=None):
+        """Plan + score this rank's batch; the library writes the block into the pooled device tensor, one
+        all-gather completes it on every rank; the scores (and the move table) end up on the host."""
+        ctx = self.ctx
+        block = self.pool[ctx.rank * self.count:(ctx.rank + 1) * self.count]
+        moves = self._score_into(aln or self.aln, model or self.model, block.data_ptr(), True)
+        self.D.all_gather_blocks(ctx, self.pool, ctx.world * self.count)
+        return moves, self.pool.cpu().numpy()
+
+    def e2e_step(self):
+        """Same through the public API with HOST buffers: the alignment goes up, the scores come down."""
+        if self.wl["score"] == "fitch":
+            a = self.fitch.FitchAlignment.from_dense(self.pin_states.numpy(), self.w_int)
+        else:
+            dt = self._lib.DATA_DNA if self.wl["datatype"] == "dna" else self._lib.DATA_AA
+            a = self.lik.LikAlignment(self.pin_codes.numpy(), self.pin_w.numpy(), dt)
+        moves, scores = self.step(a, self.model)
+        a.close()
+        return moves, scores
+
+    def prepare_e2e(self):
+        t = self.torch
+        if self.wl["score"] == "fitch":
+            self.pin_states = t.from_numpy(self.states).pin_memory()
+            h2d = self.states.nbytes + self.w_int.nbytes
+        else:
+            self.pin_codes, self.pin_w = t.from_numpy(self.codes).pin_memory(), t.from_numpy(self.w).pin_memory()
+            h2d = self.codes.nbytes + self.w.nbytes
+        if self.wl["kind"] == "trees":
+            h2d += self.descs.nbytes + self.brs.nbytes
+        else:
+            h2d += self.d.nbytes + (self.br.nbytes if self.wl["score"] == "lnl" else 0)
+        return h2d
+
+    def close(self):
+        self.aln.close()
+        if self.model is not None:
+            self.model.close()
+
+
+def read_prof(L, kind):
+    import ctypes as C
+    ms, by, un, n, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
+    L.plg_profile_read(kind, C.byref(ms), C.byref(by), C.byref(un), C.byref(n), C.byref(rq))
+    return {"ms": ms.value, "bytes": by.value, "units": un.value, "launches": n.value, "requested": rq.value}
+
+
+_PEAKS = {}
+
+
+def pipe_peak(L, mode):
+    """FP64 (mode 0 DFMA, 1 DMMA, 2 both) / INT32 logic (3) pipe peak, measured now on this device."""
+    import ctypes as C
+    if mode not in _PEAKS:
+        v = C.c_double()
+        from pylogeny_b200 import _lib
+        _lib.check(L.plg_fp64_peak(mode, C.byref(v)))
+        _PEAKS[mode] = v.value
+    return _PEAKS[mode]
+
+
+def roofline_for(name, L, prof, total_ms, hbm, hbm_src):
+    """The dominant kernel of a workload against the resource that binds it."""
+    wl = WORKLOADS[name]
+    kinds = {0: "fitch kernels", 1: "CLV update kernels", 2: "evaluation kernels", 3: "pmatrix_kernel", 4: "walk kernels"}
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    p = prof[dom]
+    if not p["launches"] or p["ms"] <= 0:
+        return None
+    sec = p["ms"] * 1e-3
+    alg_gbs = p["bytes"] / sec / 1e9
+    common = {"launches": p["launches"], "avg_launch_ms": p["ms"] / p["launches"], "share_of_step": p["ms"] / total_ms,
+              "algorithmic_bytes_per_launch": p["bytes"] / p["launches"], "algorithmic_gbs": alg_gbs,
+              "algorithmic_gbs_over_hbm_peak": alg_gbs / hbm, "hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src,
+              "requested_gbs": p["requested"] / sec / 1e9}
+    if wl["score"] == "lnl" and dom == 4:
+        dmma = wl["kind"] == "spr"
+        kernel = "walk4m_kernel" if dmma else "twalk4_kernel"
+        flop = FLOP_PER_UNIT_DNA if dmma else FLOP_PER_NODEOP_DNA
+        peak = max(pipe_peak(L, 1), pipe_peak(L, 0)) if dmma else pipe_peak(L, 0)
+        ach = p["units"] * flop / sec / 1e12
+        r = {"kernel": kernel, "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+             "flop_per_unit": flop,
+             "unit_definition": "neighbour x pattern (1 CLV update + 1 three-way evaluation)" if dmma else "node-op x pattern",
+             "peak_source": "measured in this run: plg_fp64_peak, %s issue rate (DFMA %.1f, DMMA %.1f, interleaved %.1f TFLOP/s: one pipe)" % (
+                 "DMMA m8n8k4" if dmma else "DFMA", pipe_peak(L, 0), pipe_peak(L, 1), pipe_peak(L, 2)),
+             "traffic": ncu_traffic(kernel, name)}
+    elif wl["score"] == "fitch":
+        kernel = "fitch_search_walk_kernel (+ fitch_level_kernel for the base tree's directional sets)"
+        peak = pipe_peak(L, 3)
+        ach = p["units"] * INTOPS_PER_FITCH_UNIT / sec / 1e12
+        r = {"kernel": kernel, "bound": "int", "achieved": ach, "peak": peak, "unit": "Tlop/s (INT32 logic lane-ops)",
+             "frac": ach / peak, "ops_per_unit": INTOPS_PER_FITCH_UNIT, "unit_definition": "node-op x pattern (fold or three-way join)",
+             "peak_source": "measured in this run: plg_fp64_peak mode 3 (LOP3 issue rate)",
+             "traffic": ncu_traffic("fitch_search_walk_kernel", name)}
+    elif wl["datatype"] == "aa":
+        kernel = {1: "clv20_kernel", 2: "eval20_rows_kernel"}.get(dom, kinds[dom])
+        peak = pipe_peak(L, 1)
+        ach = p["units"] * FLOP_PER_NODEOP_AA / sec / 1e12
+        r = {"kernel": kernel, "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+             "flop_per_unit": FLOP_PER_NODEOP_AA, "unit_definition": "node-op x pattern (20 states x 4 categories)",
+             "peak_source": "measured in this run: plg_fp64_peak, DMMA m8n8k4 issue rate", "traffic": ncu_traffic(kernel, name)}
+    else:
+        r = {"kernel": kinds[dom], "bound": "hbm", "achieved": alg_gbs, "peak": hbm, "unit": "GB/s", "frac": alg_gbs / hbm,
+             "peak_source": hbm_src, "traffic": None}
+    r.update(common)
+    r["other_kernels"] = [{"kernels": kinds[k], "ms_per_step_share": prof[k]["ms"] / total_ms, "launches": prof[k]["launches"]}
+                          for k in prof if k != dom and prof[k]["launches"]]
+    return r
+
+
+def run_workload(name, ctx, steps, warmup, sampler=None, e2e_steps=5):
+    """W warm-up steps, then exactly `steps` timed steps (CUDA events on the launching stream, barrier +
+    synchronize on both sides, L2 flushed before each, max over ranks)."""
     import torch
     import torch.distributed as dist
-    from pylogeny_b200 import _lib, fitch, likelihood, neighbourhood as nbh
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (pylogeny_b200 has no CPU fallback)")
-    torch.cuda.set_device(local)
-    _lib.check(_lib.lib().plg_set_device(local))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    L = _lib.lib()
-    dev = torch.device("cuda", local)
-    codes, w = make_alignment()
-    trees = [make_tree(SEED + b) for b in range(world)]
-    model = likelihood.Model(EXCH, FREQS, ALPHA)
-    aln = likelihood.LikAlignment(codes, w)
-    M = nbh.neighbourhood_size(trees[0][0])
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(world * M, dtype=torch.float64, device=dev) if world > 1 else None
-
-    my_d, my_br = trees[rank]
-
-    def step():
-        _, lnl = nbh.score_likelihood(aln, model, my_d, my_br)
-        if world > 1:  # tiny all-gather of the per-tree scores over NCCL
-            dist.all_gather_into_tensor(gathered, torch.from_numpy(lnl).to(dev, non_blocking=True))
-            return gathered
-        return lnl
+    world = ctx.world
+    r = Runner(name, ctx)
+    L = r.L
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=ctx.device)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for _ in range(max(warmup, 3)):
+        moves, scores = r.step()
     barrier()
-    try:
-        uuid = torch.cuda.get_device_properties(local).uuid
-    except Exception:
-        uuid = None
-    sampler = ClockSampler(local, uuid)
-    if rank == 0:
+    if sampler:
         sampler.start()
     L.plg_profile_enable(1)
     for k in range(5):
@@ -336,12 +573,12 @@ def run_ours(args):
     total_ms = 0.0
     barrier()
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.zero_()  # L2 flush, outside the per-step events
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        res = step()
+        moves, scores = r.step()
         e1.record()
         torch.cuda.synchronize()
         total_ms += e0.elapsed_time(e1)
@@ -349,240 +586,157 @@ def run_ours(args):
     wall = time.perf_counter() - wall0
     launches = L.plg_launch_count() - launches0
     L.plg_profile_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    clocks = sampler.stop() if sampler else None
+    prof = {k: read_prof(L, k) for k in range(5)}
+    t = torch.tensor([total_ms], dtype=torch.float64, device=ctx.device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = world * M * N_SITES / (ms_per_step * 1e-3)
-
-    # per-kernel roofline (events recorded by the library around every launch of the timed steps)
-    import ctypes as C
-    prof = {}
-    for k, name in enumerate(("fitch_level_kernel", "clv4_kernel", "eval4_kernel", "pmatrix_kernel", "walk4m_kernel")):
-        ms, by, un, n, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
-        L.plg_profile_read(k, C.byref(ms), C.byref(by), C.byref(un), C.byref(n), C.byref(rq))
-        prof[name] = {"ms": ms.value, "bytes": by.value, "units": un.value, "launches": n.value, "requested": rq.value}
-    peak, peak_src = measured_peaks()
-    dom = max(("walk4m_kernel", "clv4_kernel", "eval4_kernel"), key=lambda k: prof[k]["ms"])
-
-    def roof(name):
-        p = prof[name]
-        if not p["launches"] or p["ms"] <= 0:
-            return None
-        ach = p["bytes"] / (p["ms"] * 1e-3) / 1e9
-        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": ncu_traffic(name, p["units"] / p["launches"]), "peak_source": peak_src,
-                "launches": p["launches"],
-                "avg_launch_ms": p["ms"] / p["launches"], "algorithmic_bytes_per_launch": p["bytes"] / p["launches"],
-                "requested_bytes_per_launch": p["requested"] / p["launches"],
-                "requested_gbs": p["requested"] / (p["ms"] * 1e-3) / 1e9,
-                "share_of_step": p["ms"] / total_ms}
-
-    roofline = roof(dom)
-    # FP64 view of the same launches: ~640 flop per neighbour x pattern (CLV update 240, SURVEY.md 8d;
-    # 3-way evaluation ~400) against the DMMA peak measured on this pool (profiles/r1c_fp64_peak.txt)
-    if dom == "walk4m_kernel" and prof[dom]["ms"] > 0:
-        tf = prof[dom]["units"] * 640.0 / (prof[dom]["ms"] * 1e-3) / 1e12
-        roofline["fp64"] = {"achieved_tflops": tf, "peak_tflops": 37.1, "frac": tf / 37.1,
-                            "peak_source": "measured DMMA m8n8k4 (profiles/micro/fp64_peak.cu)",
-                            "flop_per_unit": 640}
-    roofline["other_kernels"] = [r for r in (roof(k) for k in prof if k != dom) if r]
-    # e2e: same metric through the public API with HOST buffers; the alignment goes up and the
-    # scores come down inside the timed region, every step -- on every rank (its own neighbourhood),
-    # host clock, barrier on both sides, max over ranks
-    pinned_codes = torch.from_numpy(codes).pin_memory()
-    pinned_w = torch.from_numpy(w).pin_memory()
+    ms_per_step = total_ms / steps
+    hbm, hbm_src = measured_hbm_peak()
+    out = {"metric": r.wl["metric"], "value": r.units_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+           "warmup": max(warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u32 bitsets" if r.wl["score"] == "fitch" else "f64", "data": "synthetic",
+           "config": workload_config(name, world, r.count), "roofline": roofline_for(name, L, prof, total_ms, hbm, hbm_src),
+           "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "trees_per_step": world * r.count,
+           "checksum": float(np.asarray(scores, dtype=np.float64).sum())}
+    # e2e: host buffers in, host results out, every step, on every rank; host clock, barrier on both sides, max over ranks
+    h2d = r.prepare_e2e()
     e2e_ms = []
-    for i in range(2 + min(args.steps, 5)):
+    for i in range(2 + e2e_steps):
         barrier()
         t0 = time.perf_counter()
-        a2 = likelihood.LikAlignment(pinned_codes.numpy(), pinned_w.numpy())
-        moves, lnl = nbh.score_likelihood(a2, model, my_d, my_br)
-        a2.close()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, torch.from_numpy(lnl).to(dev, non_blocking=True))
+        moves, scores = r.e2e_step()
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=ctx.device)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         if i >= 2:
             e2e_ms.append(1e3 * float(dt.item()))
-    h2d = world * (codes.nbytes + w.nbytes + my_d.nbytes + my_br.nbytes)
-    e2e = {"value": world * M * N_SITES / (np.mean(e2e_ms) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(world * (lnl.nbytes + moves.nbytes)), "ms_per_step": float(np.mean(e2e_ms)),
-           "ms_samples": [round(x, 3) for x in e2e_ms],
-           "note": "%d GPU(s), per rank and step: plg_lik_aln_create + plg_lik_score_neighbourhood + destroy" % world}
-    sharded = None
-    if world > 1:
-        # north_star (4), literally: ONE neighbourhood -- the target shape, 256 taxa x 100k sites, all
-        # 255,530 SPR neighbours by GTR+G4 -- sharded across the ranks (each plans and walks only the
-        # searches that hold its block of neighbours), scores combined over NCCL.  Strong scaling.
-        n2, s2 = 256, 100_000
-        rng2 = np.random.default_rng(1002)
-        codes2 = (1 << rng2.integers(0, 4, (n2, s2))).astype(np.uint8)
-        la2 = likelihood.LikAlignment(codes2, np.ones(s2))
-        d2 = random_desc(np.random.default_rng(1002 + 7919), n2)
-        br2 = np.random.default_rng(1002 + 7920).exponential(0.1, d2.shape)
-        M2 = nbh.neighbourhood_size(d2)
-        buf = torch.zeros(M2, dtype=torch.float64, device=dev)
+    d2h = scores.nbytes + (moves.nbytes if moves is not None else 0)
+    out["e2e"] = {"value": r.units_per_step / (np.mean(e2e_ms) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(world * h2d),
+                  "d2h_bytes_per_step": int(world * d2h), "ms_per_step": float(np.mean(e2e_ms)),
+                  "ms_samples": [round(x, 3) for x in e2e_ms],
+                  "note": "%d GPU(s), per rank and step: alignment create (H2D) + plan + score + all-gather + scores/moves D2H + destroy" % world}
+    r.close()
+    del flush
+    torch.cuda.empty_cache()
+    return out
 
-        def shard_step():
-            _, part = nbh.score_likelihood(la2, model, d2, br2, shard=(rank, world), want_moves=False)
-            lo, hi = M2 * rank // world, M2 * (rank + 1) // world
-            buf.zero_()
-            buf[lo:hi] = torch.from_numpy(part[lo:hi]).to(dev)
-            dist.all_reduce(buf)  # disjoint blocks: the sum is the concatenation
-            return buf
 
-        shard_step()
-        barrier()
+def sharded_neighbourhood(ctx, name="lnl_target"):
+    """north_star (4), literally: ONE neighbourhood split across the ranks (each plans and walks only the
+    searches that hold its block of neighbours), scores all-gathered.  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from pylogeny_b200 import distributed as D, likelihood
+    wl = WORKLOADS[name]
+    codes, w = make_alignment(wl["seed"], wl["n_taxa"], wl["n_sites"])
+    la = likelihood.LikAlignment(codes, w)
+    model = likelihood.Model(EXCH, FREQS, ALPHA)
+    d, br = base_tree(wl, 0)
+    ms = []
+    for i in range(4):
+        dist.barrier()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res2 = shard_step()
+        _, lnl = D.score_neighbourhood(ctx, la, model, d, br)
         e1.record()
         torch.cuda.synchronize()
-        t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        sharded = {"workload": "ONE SPR neighbourhood sharded across the ranks: synthetic DNA 256 taxa x 100k sites, "
-                               "GTR+G4 lnL of all %d neighbours" % M2,
-                   "value": M2 * s2 / (float(t2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t2.item()),
-                   "scaling": "strong", "checksum": float(res2.sum().item())}
-        la2.close()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if i:
+            ms.append(float(t.item()))
+    M = lnl.shape[0]
+    la.close(); model.close()
+    return {"workload": "ONE SPR neighbourhood split across the ranks (pylogeny_b200.distributed.score_neighbourhood): " +
+                        wl["label"] % M, "value": M * wl["n_sites"] / (np.mean(ms) * 1e-3), "unit": UNIT,
+            "ms_per_step": float(np.mean(ms)), "steps": len(ms), "scaling": "strong", "checksum": float(lnl.sum().item())}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pylogeny_b200 import distributed as D
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (pylogeny_b200 has no CPU fallback)")
+    ctx = D.init()
+    rank, world = ctx.rank, ctx.world
+    try:
+        uuid = torch.cuda.get_device_properties(ctx.device).uuid
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(ctx.device.index or 0, uuid) if rank == 0 else None
+    out = run_workload(args.workload, ctx, args.steps, args.warmup, sampler)
+    if world > 1 and args.workload == DEFAULT_WORKLOAD:
+        out["one_neighbourhood_sharded"] = sharded_neighbourhood(ctx)
+        c4 = run_workload("trees_c4", ctx, 3, 3, None, e2e_steps=1)  # BASELINE configs[3] across the GPUs
+        out["trees_c4"] = {k: c4[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "trees_per_step", "roofline", "e2e", "config")}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    # ---- rank 0 only from here: e2e, CPU baseline, parsimony leg --------------------------------
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
-           "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
-           "wall_s_timed_region": wall, "trees_per_step": world * M}
-    if sharded:
-        out["one_neighbourhood_sharded"] = sharded
-
-    out["e2e"] = e2e
     if world == 1:
         if not args.no_cpu:
-            out["cpu_baseline"] = cpu_lnl_sample()[0]
-        out["parsimony"] = parsimony_leg(fitch, nbh, L, peak, peak_src, not args.no_cpu)
-        out["streaming"] = streaming_leg(fitch, likelihood, L, peak, peak_src)
-        out["target_shape_lnl"] = target_lnl_leg(likelihood, nbh, L, peak, peak_src)
-        out["smoothed_lnl"] = smoothed_lnl_leg(nbh)
+            out["cpu_baseline"] = cpu_sample(args.workload, 12.0)[0]
+        if args.workload == DEFAULT_WORKLOAD and not args.no_extra:
+            other = {}
+            for name in WORKLOADS:
+                if name == args.workload:
+                    continue
+                o = run_workload(name, ctx, 5, 3, None, e2e_steps=3)
+                other[name] = {k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "trees_per_step", "roofline",
+                                                 "e2e", "config", "checksum", "gpu_launches")}
+                if not args.no_cpu:
+                    other[name]["cpu_baseline"] = cpu_sample(name, 6.0)[0]
+            out["other_workloads"] = other
+            out["streaming"] = streaming_leg()
+            out["smoothed_lnl"] = smoothed_lnl_leg()
+            out["greedy_climb"] = greedy_climb_leg()
     emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def parsimony_leg(fitch, nbh, L, peak, peak_src, cpu=True):
-    """BASELINE config 3 shape: 256 taxa x 100k sites, Fitch length of all 255,530 SPR neighbours."""
-    import ctypes as C
+def greedy_climb_leg():
+    """BASELINE configs[2] proper: the parsimonyGreedy hill-climb (one neighbourhood per step, move to the
+    best neighbour while it improves), first 10 steps end to end on the host clock."""
     import torch
-    n, S = 256, 100_000
-    rng = np.random.default_rng(1002)
-    states = (rng.integers(0, 4, (S, n)) + 48).astype(np.uint8)
-    a = fitch.FitchAlignment.from_dense(states, np.ones(S, dtype=np.int64))
-    d = random_desc(np.random.default_rng(1002 + 7919), n)
-    for _ in range(2):
-        moves, costs = nbh.score_parsimony(a, d)
-    L.plg_profile_enable(1)
-    L.plg_profile_read(0, None, None, None, None, None)
-    ms = []
-    for _ in range(3):
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        moves, costs = nbh.score_parsimony(a, d)
-        e1.record()
-        torch.cuda.synchronize()
-        ms.append(e0.elapsed_time(e1))
-    L.plg_profile_enable(0)
-    kms, by, un, nl, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
-    L.plg_profile_read(0, C.byref(kms), C.byref(by), C.byref(un), C.byref(nl), C.byref(rq))
-    M = len(costs)
-    ach = by.value / (kms.value * 1e-3) / 1e9
-    res = {"workload": "BASELINE configs[2] shape: synthetic DNA 256 taxa x 100k sites, Fitch length of all %d "
-                       "distinct SPR neighbours of a random tree (edge insertion)" % M,
-           "value": M * S / (np.mean(ms) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ms)), "dtype": "u32 bitsets",
-           "roofline": {"kernel": "fitch_search_walk_kernel (+ fitch_level_kernel for the base tree's directional sets)",
-                        "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": ncu_traffic("fitch_search_walk_kernel", un.value / max(nl.value, 1)),
-                        "algorithmic_bytes_per_launch": by.value / max(nl.value, 1),
-                        "requested_gbs": rq.value / (kms.value * 1e-3) / 1e9, "peak_source": peak_src,
-                        "launches": nl.value, "avg_launch_ms": kms.value / max(nl.value, 1),
-                        "share_of_step": kms.value / sum(ms)},
-           "checksum": int(costs.astype(np.int64).sum()), "min_cost": int(costs.min())}
-    # BASELINE configs[2] proper: the greedy hill-climb (one neighbourhood per step, move to the best
-    # neighbour while it improves), first 10 steps timed end to end on the host clock
-    a.score_trees(d[None])  # (the climb scores its start tree once: first use of the tree-walk path allocates)
+    from pylogeny_b200 import fitch, neighbourhood as nbh
+    wl = WORKLOADS["fitch_target"]
+    a = fitch.FitchAlignment.from_dense(fitch_states(wl), np.ones(wl["n_sites"], dtype=np.int64))
+    d, _ = base_tree(wl, 0)
+    a.score_trees(d[None])
+    nbh.score_parsimony(a, d, want_moves=False)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     path, _ = nbh.parsimony_greedy(a, d, max_steps=10)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    res["greedy_climb"] = {"steps": len(path) - 1, "ms_per_step": 1e3 * dt / max(1, len(path) - 1),
-                           "path_head": [int(x) for x in path[:4]],
-                           "note": "parsimony_greedy: score all neighbours, argmin, materialise the winner"}
-    if cpu:
-        res["cpu_baseline"] = cpu_fitch_sample(states, d)
     a.close()
-    return res
+    return {"workload": "parsimonyGreedy climb over the SPR landscape, 256 taxa x 100k sites (BASELINE configs[2]), first 10 steps",
+            "steps": len(path) - 1, "ms_per_step": 1e3 * dt / max(1, len(path) - 1), "path_head": [int(x) for x in path[:4]],
+            "note": "per step: score all 255,530 neighbours, argmin, materialise the winner"}
 
 
-def target_lnl_leg(likelihood, nbh, L, peak, peak_src):
-    """north_star target shape for likelihood: GTR+G4 lnL of all 255,530 SPR neighbours of a
-    256-taxon x 100k-site tree (the parsimony leg is the same shape).  One call, ~1 s."""
-    import ctypes as C
-    import torch
-    n, S = 256, 100_000
-    rng = np.random.default_rng(1002)
-    codes = (1 << rng.integers(0, 4, (n, S))).astype(np.uint8)
-    la = likelihood.LikAlignment(codes, np.ones(S))
-    m = likelihood.Model(EXCH, FREQS, ALPHA)
-    d = random_desc(np.random.default_rng(1002 + 7919), n)
-    br = np.random.default_rng(1002 + 7920).exponential(0.1, d.shape)
-    nbh.score_likelihood(la, m, d, br, want_moves=False)
-    L.plg_profile_enable(1)
-    L.plg_profile_read(4, None, None, None, None, None)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    _, lnl = nbh.score_likelihood(la, m, d, br, want_moves=False)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    kms, by, un, nl, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
-    L.plg_profile_read(4, C.byref(kms), C.byref(by), C.byref(un), C.byref(nl), C.byref(rq))
-    L.plg_profile_enable(0)
-    la.close()
-    ach = by.value / (kms.value * 1e-3) / 1e9
-    return {"workload": "synthetic DNA 256 taxa x 100k sites, GTR+G4 lnL (fixed branch lengths) of all %d distinct "
-                        "SPR neighbours of a random tree" % len(lnl),
-            "value": len(lnl) * S / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "checksum": float(lnl.sum()),
-            "roofline": {"kernel": "walk4m_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "requested_gbs": rq.value / (kms.value * 1e-3) / 1e9,
-                         "launches": nl.value, "avg_launch_ms": kms.value / max(nl.value, 1), "peak_source": peak_src,
-                         "fp64_tflops": un.value * 640.0 / (kms.value * 1e-3) / 1e12}}
-
-
-def smoothed_lnl_leg(nbh, T=1024):
+def smoothed_lnl_leg(T=1024):
     """What scoring.getLogLikelihood returns per tree in the reference (libpllWrapper.c:152, :205:
-    default branch lengths, 3 smoothing passes, lnL) for the first T SPR neighbours of the bench
+    default branch lengths, 3 smoothing passes, lnL) for the first T SPR neighbours of the configs[1]
     tree, through plg_pll_loglik_batch (all trees in lockstep on the device) and, on 8 of them,
     through one handle per tree as the reference does it."""
     import torch
-    from pylogeny_b200 import alignment, libpllWrapper as W, pll
-    codes, _ = make_alignment()
+    from pylogeny_b200 import alignment, libpllWrapper as W, neighbourhood as nbh, pll
+    wl = WORKLOADS["lnl_c2"]
+    codes, _ = make_alignment(wl["seed"], wl["n_taxa"], wl["n_sites"])
     letters = np.array(list("?AC?G???T"))
     seqs = ["".join(letters[row]) for row in codes]
-    ali = alignment.phylipFriendlyAlignment(names=["T%d" % i for i in range(N_TAXA)], seqs=seqs)
+    ali = alignment.phylipFriendlyAlignment(names=["T%d" % i for i in range(wl["n_taxa"])], seqs=seqs)
     labels = ali.getTaxa()
-    d, _ = make_tree(SEED)
+    d, _ = base_tree(wl, 0)
     descs, _, _ = nbh.neighbour_trees(d, None, np.arange(T, dtype=np.int64))
     newicks = [nbh.desc_to_newick(x, labels) for x in descs]
-    pm = pll.partitionModel(ali)
-    pm.createSimpleModel()
+    pm = pll.model_for(ali)
     W.getLogLikelihoodBatch(ali.getPhylip(), newicks[:8], pm.getFileName())
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -599,74 +753,64 @@ def smoothed_lnl_leg(nbh, T=1024):
     ali.close()
     return {"workload": "GTR+G4 lnL after 3 branch-length smoothing passes from z = 0.9 (scoring.getLogLikelihood "
                         "semantics) of the first %d SPR neighbours, 64 taxa x 10k sites" % T,
-            "value": T * N_SITES / dt, "unit": UNIT, "ms_per_tree": 1e3 * dt / T,
-            "per_tree_handle_ms": 1e3 * dt1,
+            "value": T * wl["n_sites"] / dt, "unit": UNIT, "ms_per_tree": 1e3 * dt / T, "per_tree_handle_ms": 1e3 * dt1,
             "max_rel_diff_vs_per_tree": float(np.max(np.abs((np.array(ref) - np.array(lnl[:8])) / np.array(ref))))}
 
 
-def streaming_leg(fitch, likelihood, L, peak, peak_src):
-    """Descriptor batches (plg_*_score_trees) at BASELINE config-4 shape for lnL (128 taxa x 1M sites)
-    and config-3 shape for Fitch (256 taxa x 100k sites, 2048 random trees).  Two formulations each:
-    `tree_walk` (shipped: whole post-order on chip, HBM only supplies the tips -- FP64 / integer
-    pipe bound, algorithmic-bytes fraction > 1) and `levels` (PLG_TREE_MODE=levels: one launch per
-    tree level, every node vector through HBM -- the plain HBM-roofline evidence for the streaming
-    kernels, working set far beyond L2)."""
-    import ctypes as C
+def streaming_leg():
+    """The level-synchronous kernels -- every node vector through HBM, working set far beyond L2 -- as the plain
+    HBM-roofline evidence north_star asks for (achieved HBM GB/s of the parsimony and CLV-update kernels), on
+    descriptor batches at BASELINE configs[3] (lnL) and configs[2] (Fitch) shapes with PLG_TREE_MODE=levels.
+    (The shipped tree walks of the same calls are the "trees_c4" workload.)"""
     import torch
+    from pylogeny_b200 import _lib, fitch, likelihood
+    L = _lib.lib()
+    hbm, hbm_src = measured_hbm_peak()
     res = {}
-
-    def read(kind):
-        ms, by, un, nl, rq = C.c_double(), C.c_double(), C.c_double(), C.c_int64(), C.c_double()
-        L.plg_profile_read(kind, C.byref(ms), C.byref(by), C.byref(un), C.byref(nl), C.byref(rq))
-        return ms.value, by.value, nl.value, rq.value
 
     def leg(call, n_units, kinds, kernel, workload):
         for _ in range(2):
             call()
         L.plg_profile_enable(1)
         for k in kinds:
-            read(k)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(3):
+            read_prof(L, k)
+        ms = []
+        for _ in range(5):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             call()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / 3
-        kms = by = nl = rq = 0
-        for k in kinds:
-            a, b, c, d = read(k)
-            kms += a; by += b; nl += c; rq += d
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        p = [read_prof(L, k) for k in kinds]
         L.plg_profile_enable(0)
+        kms, by, nl, rq = (sum(x[f] for x in p) for f in ("ms", "bytes", "launches", "requested"))
         ach = by / (kms * 1e-3) / 1e9
-        return {"workload": workload, "value": n_units / dt, "unit": UNIT, "ms_per_call": dt * 1e3,
-                "roofline": {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                             "frac": ach / peak, "requested_gbs": rq / (kms * 1e-3) / 1e9, "launches": nl // 3,
-                             "kernel_ms_per_call": kms / 3, "peak_source": peak_src}}
+        return {"workload": workload, "value": n_units / (np.mean(ms) * 1e-3), "unit": UNIT, "ms_per_call": float(np.mean(ms)), "steps": 5,
+                "roofline": {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                             "requested_gbs": rq / (kms * 1e-3) / 1e9, "launches": nl // 5, "kernel_ms_per_call": kms / 5,
+                             "peak_source": hbm_src}}
 
-    rng = np.random.default_rng(1004)
-    n, S = 128, 1_000_000
-    codes = (1 << rng.integers(0, 4, (n, S))).astype(np.uint8)
-    la = likelihood.LikAlignment(codes, np.ones(S))
-    m = likelihood.Model(EXCH, FREQS, ALPHA)
-    descs = np.stack([random_desc(rng, n) for _ in range(16)])
-    brs = rng.exponential(0.1, descs.shape)
-    for mode, T, kinds, kernel in (("walk", 16, (4,), "twalk4_kernel"), ("levels", 3, (1, 2), "clv4_kernel + eval4_kernel")):
-        os.environ["PLG_TREE_MODE"] = mode
-        res["lnl_" + ("tree_walk" if mode == "walk" else "levels")] = leg(
-            lambda: la.score_trees(m, descs[:T], brs[:T]), T * S, kinds, kernel,
-            "128 taxa x 1M sites, GTR+G4, %d random trees per call (BASELINE configs[3] shape)" % T)
-    la.close()
-    n, S, T = 256, 100_000, 2048
-    states = (rng.integers(0, 4, (S, n)) + 48).astype(np.uint8)
-    fa = fitch.FitchAlignment.from_dense(states, np.ones(S, dtype=np.int64))
-    descs = np.stack([random_desc(rng, n) for _ in range(T)])
-    for mode, kernel in (("walk", "fitch_walk_kernel"), ("levels", "fitch_level_kernel")):
-        os.environ["PLG_TREE_MODE"] = mode
-        res["fitch_" + ("tree_walk" if mode == "walk" else "levels")] = leg(
-            lambda: fa.score_trees(descs), T * S, (0,), kernel,
-            "256 taxa x 100k sites, %d random trees per call (BASELINE configs[2] shape)" % T)
-    os.environ.pop("PLG_TREE_MODE", None)
-    fa.close()
+    os.environ["PLG_TREE_MODE"] = "levels"
+    try:
+        wl = WORKLOADS["trees_c4"]
+        codes, w = make_alignment(wl["seed"], wl["n_taxa"], wl["n_sites"])
+        la = likelihood.LikAlignment(codes, w)
+        m = likelihood.Model(EXCH, FREQS, ALPHA)
+        descs, brs = random_trees(wl, 3, 0)
+        res["lnl_levels"] = leg(lambda: la.score_trees(m, descs, brs), 3 * wl["n_sites"], (1, 2), "clv4_kernel + eval4_kernel",
+                                "128 taxa x 1M sites, GTR+G4, 3 random trees per call (BASELINE configs[3] shape), level programs")
+        la.close(); m.close()
+        wl = WORKLOADS["fitch_target"]
+        fa = fitch.FitchAlignment.from_dense(fitch_states(wl), np.ones(wl["n_sites"], dtype=np.int64))
+        rng = np.random.default_rng(1004)
+        descs = np.stack([random_desc(rng, wl["n_taxa"]) for _ in range(2048)])
+        res["fitch_levels"] = leg(lambda: fa.score_trees(descs), 2048 * wl["n_sites"], (0,), "fitch_level_kernel",
+                                  "256 taxa x 100k sites, 2048 random trees per call (BASELINE configs[2] shape), level programs")
+        fa.close()
+    finally:
+        os.environ.pop("PLG_TREE_MODE", None)
     return res
 
 
@@ -676,7 +820,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="only the selected workload (no other_workloads / streaming legs)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

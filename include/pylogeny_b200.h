@@ -38,6 +38,10 @@ extern "C" {
  * getSPRMovesInDistance, libpllWrapper.c:241-262); r = 0: unlimited; r = 1 equals NNI. */
 #define PLG_MOVE_SPR_WITHIN(r) (PLG_MOVE_SPR | ((r) << 8))
 
+/* Where a scoring entry point with an `out_where` argument writes its per-tree results. */
+#define PLG_OUT_HOST 0
+#define PLG_OUT_DEVICE 1 /* device memory of the current device, e.g. a tensor that goes straight into an NCCL collective */
+
 #define PLG_DATA_DNA 4  /* 4 states, tip codes are 4-bit ambiguity masks (A=1,C=2,G=4,T=8) */
 #define PLG_DATA_AA 20  /* 20 states, tip codes 0..19, 20=B, 21=Z, 22=X/-/? */
 
@@ -57,9 +61,10 @@ int plg_profile_enable(int on);
 int plg_profile_read(int kind, double *ms, double *bytes, double *units, int64_t *launches,
                      double *requested_bytes);
 
-/* FP64 pipe peak of the current device, measured now (CUDA events, best of three): mode 0 = DFMA on
- * the CUDA cores, 1 = DMMA m8n8k4 (FP64 tensor instructions), 2 = both interleaved.  TFLOP/s.  The
- * roofline denominator of the likelihood walk kernels (bench.py); not in MEASURED_PEAKS.json. */
+/* Pipe peaks of the current device, measured now (CUDA events, best of three): mode 0 = DFMA on the
+ * CUDA cores, 1 = DMMA m8n8k4 (FP64 tensor instructions), 2 = both interleaved -- TFLOP/s; 3 = LOP3
+ * (INT32 logic) -- 10^12 lane-ops/s.  The roofline denominators of the likelihood and Fitch walk
+ * kernels (bench.py); not in MEASURED_PEAKS.json. */
 int plg_fp64_peak(int mode, double *tflops);
 
 /* ------------------------------------------------------------------ */
@@ -99,6 +104,16 @@ int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_tips,
                           const int32_t *desc, const int32_t *tip_rows,
                           int32_t *out_costs, void *stream);
 
+/* Multi-GPU form of the same (BASELINE configs[3]: a list of random trees sharded over the GPUs of a
+ * box): `desc` is the WHOLE batch, the call reads and scores only block
+ * [n_trees*i/c, n_trees*(i+1)/c) of it and writes that block of out_costs (indexed by tree, host or
+ * device memory per out_where).  One process per GPU calls it with its rank as shard_index; the
+ * blocks are combined by one all-gather (pylogeny_b200/distributed.py). */
+int plg_fitch_score_trees_shard(plg_fitch_aln *aln, int64_t n_trees, int n_tips,
+                                const int32_t *desc, const int32_t *tip_rows,
+                                int64_t shard_index, int64_t shard_count,
+                                int32_t *out_costs, int out_where, void *stream);
+
 /* ---- rearrangement neighbourhoods (host side; no device needed) ----
  * Base tree = rooted binary descriptor as above (n_tips-1 internal nodes, ids n_tips+i, root
  * last).  It is read as the unrooted tree it represents (the root's two child branches merge).
@@ -134,6 +149,14 @@ int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, int n_tips,
                                   int64_t *n_moves, int32_t *out_moves,
                                   int32_t *out_costs, void *stream);
 
+/* Same with out_costs in host or device memory (out_where).  Fitch lengths are finished on the
+ * host, so a device block is sent up from pinned staging by the library. */
+int plg_fitch_score_neighbourhood_out(plg_fitch_aln *aln, int move_type, int n_tips,
+                                      const int32_t *desc, const int32_t *tip_rows,
+                                      int64_t shard_index, int64_t shard_count,
+                                      int64_t *n_moves, int32_t *out_moves,
+                                      int32_t *out_costs, int out_where, void *stream);
+
 /* ------------------------------------------------------------------ */
 /* Likelihood (replaces libpllWrapper.c + the libpll calls it makes)   */
 /* ------------------------------------------------------------------ */
@@ -167,6 +190,13 @@ int plg_lik_score_trees(plg_lik_aln *aln, plg_model *m, int64_t n_trees, int n_t
                         const int32_t *desc, const double *brlen, const int32_t *tip_rows,
                         double *out_lnl, void *stream);
 
+/* Sharded form (see plg_fitch_score_trees_shard): only block i of c of the batch is read and scored,
+ * out_lnl is indexed by tree and lives in host or device memory per out_where. */
+int plg_lik_score_trees_shard(plg_lik_aln *aln, plg_model *m, int64_t n_trees, int n_tips,
+                              const int32_t *desc, const double *brlen, const int32_t *tip_rows,
+                              int64_t shard_index, int64_t shard_count, double *out_lnl,
+                              int out_where, void *stream);
+
 /* lnL of every distinct SPR/NNI neighbour of one base tree at fixed branch lengths, by edge
  * insertion (directional CLVs of the base tree, one CLV update per search step, one 3-way
  * evaluation per neighbour).  Same conventions as plg_fitch_score_neighbourhood; the closest
@@ -176,6 +206,14 @@ int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int move_type, i
                                 const int32_t *tip_rows, int64_t shard_index,
                                 int64_t shard_count, int64_t *n_moves, int32_t *out_moves,
                                 double *out_lnl, void *stream);
+
+/* Same with out_lnl in host or device memory (out_where): the search walk's reduction writes the
+ * shard's block straight into the caller's device buffer (no host bounce before a collective). */
+int plg_lik_score_neighbourhood_out(plg_lik_aln *aln, plg_model *m, int move_type, int n_tips,
+                                    const int32_t *desc, const double *brlen,
+                                    const int32_t *tip_rows, int64_t shard_index,
+                                    int64_t shard_count, int64_t *n_moves, int32_t *out_moves,
+                                    double *out_lnl, int out_where, void *stream);
 
 /* ---- libpllWrapper compat (libpllWrapper.c:97-239): opaque problem handle ---- */
 typedef struct plg_pll plg_pll;

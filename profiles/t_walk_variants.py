@@ -11,8 +11,9 @@ import bench
 from pylogeny_b200 import likelihood, neighbourhood as nbh, _lib
 L = _lib.lib()
 n, S = int(os.environ.get("NT", "64")), int(os.environ.get("NS", "10000"))
-codes, w = bench.make_alignment(bench.SEED, n, S)
-d, br = bench.make_tree(bench.SEED, n)
+wl = bench.WORKLOADS["lnl_c2" if n == 64 else "lnl_target"]
+codes, w = bench.make_alignment(wl["seed"], n, S)
+d, br = bench.base_tree(dict(wl, n_taxa=n), 0)
 model = likelihood.Model(bench.EXCH, bench.FREQS, bench.ALPHA)
 aln = likelihood.LikAlignment(codes, w)
 reps = int(os.environ.get("REPS", "10"))

@@ -17,6 +17,7 @@ def MOVE_SPR_WITHIN(radius):
 
 
 DATA_DNA, DATA_AA = 4, 20
+OUT_HOST, OUT_DEVICE = 0, 1
 
 _lib = None
 
@@ -90,6 +91,13 @@ def _declare(L):
     _set(L, 'plg_fitch_score_neighbourhood', 'argtypes', [vp, C.c_int, C.c_int, vp, vp, C.c_int64, C.c_int64, i64p, vp, vp, vp])
     _set(L, 'plg_lik_score_neighbourhood', 'argtypes',
          [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, i64p, vp, vp, vp])
+    _set(L, 'plg_fitch_score_trees_shard', 'argtypes', [vp, C.c_int64, C.c_int, vp, vp, C.c_int64, C.c_int64, vp, C.c_int, vp])
+    _set(L, 'plg_lik_score_trees_shard', 'argtypes',
+         [vp, vp, C.c_int64, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, vp, C.c_int, vp])
+    _set(L, 'plg_fitch_score_neighbourhood_out', 'argtypes',
+         [vp, C.c_int, C.c_int, vp, vp, C.c_int64, C.c_int64, i64p, vp, vp, C.c_int, vp])
+    _set(L, 'plg_lik_score_neighbourhood_out', 'argtypes',
+         [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, C.c_int64, i64p, vp, vp, C.c_int, vp])
     _set(L, 'plg_profile_enable', 'argtypes', [C.c_int])
     _set(L, 'plg_profile_read', 'argtypes', [C.c_int, dp, dp, dp, i64p, dp])
     _set(L, 'plg_pll_new', 'argtypes', [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(vp)])

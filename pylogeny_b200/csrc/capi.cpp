@@ -8,6 +8,11 @@ static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 std::mutex g_api_mutex;
 
+static thread_local bool g_out_dev = false;
+bool out_on_device() { return g_out_dev; }
+OutDeviceScope::OutDeviceScope(bool on) : prev(g_out_dev) { g_out_dev = on; }
+OutDeviceScope::~OutDeviceScope() { g_out_dev = prev; }
+
 void set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -57,6 +57,18 @@ struct Error {
   }                                                    \
   return PLG_OK;
 
+// Where the per-tree results of the running entry point go: host memory (default) or device memory of
+// the current device (the *_out / *_shard entry points with PLG_OUT_DEVICE: scores land in a caller's
+// tensor and go straight into a collective).  Set by an OutDeviceScope in the C-ABI wrapper, read where
+// the result vector is copied out.
+bool out_on_device();
+struct OutDeviceScope {
+  bool prev;
+  explicit OutDeviceScope(bool on);
+  ~OutDeviceScope();
+};
+inline cudaMemcpyKind out_copy_kind() { return out_on_device() ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
+
 inline void count_launch(int64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).

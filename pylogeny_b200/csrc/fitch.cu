@@ -683,7 +683,7 @@ void run_fitch_program(const FitchAln &a, FitchWorkspace &ws, const FitchProgram
   }
   PLG_CUDA(cudaGetLastError());
   if (out_costs && prog.n_costs) {
-    PLG_CUDA(cudaMemcpyAsync(out_costs, ws.cost.p, (size_t)prog.n_costs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PLG_CUDA(cudaMemcpyAsync(out_costs, ws.cost.p, (size_t)prog.n_costs * sizeof(int32_t), out_copy_kind(), st));
     PLG_CUDA(cudaStreamSynchronize(st));
   }
   if (device_plan && out_moves) {
@@ -773,7 +773,7 @@ void score_desc_walk(FitchAln &a, int64_t n_trees, int n_tips, const int32_t *de
       default: PLG_FAIL(PLG_ERR_STATES, "no kernel for %d planes", a.K);
     }
     PLG_CUDA(cudaGetLastError());
-    PLG_CUDA(cudaMemcpyAsync(out_costs + t0, ws.cost.p, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PLG_CUDA(cudaMemcpyAsync(out_costs + t0, ws.cost.p, (size_t)cnt * sizeof(int32_t), out_copy_kind(), st));
     PLG_CUDA(cudaStreamSynchronize(st));
     tm.lap("walk chunk");
   }
@@ -851,17 +851,39 @@ extern "C" int plg_fitch_score_newicks(plg_fitch_aln *aln, int64_t n_trees, cons
   PLG_API_END
 }
 
-extern "C" int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_tips, const int32_t *desc,
-                                     const int32_t *tip_rows, int32_t *out_costs, void *stream) {
-  PLG_API_BEGIN_LOCKED
+static void fitch_score_trees_impl(plg_fitch_aln *aln, int64_t n_trees, int n_tips, const int32_t *desc,
+                                   const int32_t *tip_rows, int32_t *out_costs, void *stream) {
   if (!aln || !out_costs || (n_trees > 0 && !desc)) PLG_FAIL(PLG_ERR_ARG, "null argument");
   if (tree_walk_enabled() && n_tips >= 2 && n_tips <= (1 << WALK_MAX_LEVELS)) {
     score_desc_walk(aln->impl, n_trees, n_tips, desc, tip_rows, out_costs, (cudaStream_t)stream);
-    return PLG_OK;
+    return;
   }
   TreeBatch b = batch_from_desc(n_trees, n_tips, desc, nullptr, tip_rows);
   check_rows(aln->impl, b);
   score_batch_full(aln->impl, b, out_costs, (cudaStream_t)stream);
+}
+
+extern "C" int plg_fitch_score_trees(plg_fitch_aln *aln, int64_t n_trees, int n_tips, const int32_t *desc,
+                                     const int32_t *tip_rows, int32_t *out_costs, void *stream) {
+  PLG_API_BEGIN_LOCKED
+  fitch_score_trees_impl(aln, n_trees, n_tips, desc, tip_rows, out_costs, stream);
+  PLG_API_END
+}
+
+extern "C" int plg_fitch_score_trees_shard(plg_fitch_aln *aln, int64_t n_trees, int n_tips, const int32_t *desc,
+                                           const int32_t *tip_rows, int64_t shard_index, int64_t shard_count,
+                                           int32_t *out_costs, int out_where, void *stream) {
+  PLG_API_BEGIN_LOCKED
+  if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
+    PLG_FAIL(PLG_ERR_ARG, "bad shard %lld of %lld", (long long)shard_index, (long long)shard_count);
+  if (out_where != PLG_OUT_HOST && out_where != PLG_OUT_DEVICE) PLG_FAIL(PLG_ERR_ARG, "out_where: PLG_OUT_HOST or PLG_OUT_DEVICE");
+  if (n_tips < 2) PLG_FAIL(PLG_ERR_ARG, "descriptor trees need at least 2 tips");
+  const int64_t lo = n_trees * shard_index / shard_count, hi = n_trees * (shard_index + 1) / shard_count;
+  const size_t stride = (size_t)(n_tips - 1) * 2;
+  OutDeviceScope scope(out_where == PLG_OUT_DEVICE);
+  if (hi > lo)
+    fitch_score_trees_impl(aln, hi - lo, n_tips, desc ? desc + lo * stride : nullptr, tip_rows,
+                           out_costs ? out_costs + lo : nullptr, stream);
   PLG_API_END
 }
 

@@ -943,7 +943,7 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   PLG_CUDA(cudaGetLastError());
   if (out_lnl && prog.n_trees) {
     StageTimer tm;
-    PLG_CUDA(cudaMemcpyAsync(out_lnl, ws.lnl.p, (size_t)prog.n_trees * 8, cudaMemcpyDeviceToHost, st));
+    PLG_CUDA(cudaMemcpyAsync(out_lnl, ws.lnl.p, (size_t)prog.n_trees * 8, out_copy_kind(), st));
     const bool acct = dna4 && prog.spr_n_visits > 0 && prof_enabled();
     double h[2] = {0.0, 0.0};
     if (acct) PLG_CUDA(cudaMemcpyAsync(h, ws.spr_acct.p, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -1121,7 +1121,7 @@ void score_lik_desc_walk(LikAln &a, const Model &m, int64_t n_trees, int n_tips,
     reduce_partials_kernel<<<(unsigned)((cnt + 7) / 8), 256, 0, st>>>((int)cnt, (int)tiles, ws.partial.p, ws.lnl.p);
     count_launch();
     PLG_CUDA(cudaGetLastError());
-    PLG_CUDA(cudaMemcpyAsync(out_lnl + t0, ws.lnl.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+    PLG_CUDA(cudaMemcpyAsync(out_lnl + t0, ws.lnl.p, (size_t)cnt * 8, out_copy_kind(), st));
     PLG_CUDA(cudaStreamSynchronize(st));
     tm.lap("walk chunk");
   }
@@ -1169,18 +1169,46 @@ extern "C" int plg_model_pmatrix(const plg_model *m, double t, double *out) {
   PLG_API_END
 }
 
+static void lik_score_trees_impl(plg_lik_aln *aln, plg_model *m, int64_t n_trees, int n_tips, const int32_t *desc,
+                                 const double *brlen, const int32_t *tip_rows, double *out_lnl, void *stream);
+
 extern "C" int plg_lik_score_trees(plg_lik_aln *aln, plg_model *m, int64_t n_trees, int n_tips, const int32_t *desc,
                                    const double *brlen, const int32_t *tip_rows, double *out_lnl, void *stream) {
   PLG_API_BEGIN_LOCKED
+  lik_score_trees_impl(aln, m, n_trees, n_tips, desc, brlen, tip_rows, out_lnl, stream);
+  PLG_API_END
+}
+
+extern "C" int plg_lik_score_trees_shard(plg_lik_aln *aln, plg_model *m, int64_t n_trees, int n_tips,
+                                         const int32_t *desc, const double *brlen, const int32_t *tip_rows,
+                                         int64_t shard_index, int64_t shard_count, double *out_lnl, int out_where,
+                                         void *stream) {
+  PLG_API_BEGIN_LOCKED
+  if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
+    PLG_FAIL(PLG_ERR_ARG, "bad shard %lld of %lld", (long long)shard_index, (long long)shard_count);
+  if (out_where != PLG_OUT_HOST && out_where != PLG_OUT_DEVICE) PLG_FAIL(PLG_ERR_ARG, "out_where: PLG_OUT_HOST or PLG_OUT_DEVICE");
+  if (n_tips < 2) PLG_FAIL(PLG_ERR_ARG, "descriptor trees need at least 2 tips");
+  const int64_t lo = n_trees * shard_index / shard_count, hi = n_trees * (shard_index + 1) / shard_count;
+  const size_t stride = (size_t)(n_tips - 1) * 2;
+  OutDeviceScope scope(out_where == PLG_OUT_DEVICE);
+  if (hi > lo)
+    lik_score_trees_impl(aln, m, hi - lo, n_tips, desc ? desc + lo * stride : nullptr, brlen ? brlen + lo * stride : nullptr,
+                         tip_rows, out_lnl ? out_lnl + lo : nullptr, stream);
+  PLG_API_END
+}
+
+static void lik_score_trees_impl(plg_lik_aln *aln, plg_model *m, int64_t n_trees, int n_tips, const int32_t *desc,
+                                 const double *brlen, const int32_t *tip_rows, double *out_lnl, void *stream) {
+  {
   if (!aln || !m || !out_lnl || (n_trees > 0 && (!desc || !brlen))) PLG_FAIL(PLG_ERR_ARG, "null argument");
   if (aln->impl.K == 4 && m->impl.K == 4 && m->impl.R == 4 && lik_tree_walk_enabled() && n_tips >= 2 &&
       n_tips <= (1 << WALK_MAX_LEVELS)) {
     score_lik_desc_walk(aln->impl, m->impl, n_trees, n_tips, desc, brlen, tip_rows, out_lnl, (cudaStream_t)stream);
-    return PLG_OK;
+    return;
   }
   TreeBatch b = batch_from_desc(n_trees, n_tips, desc, brlen, tip_rows);
   for (int32_t c : b.child)
     if (c >= aln->impl.n_rows) PLG_FAIL(PLG_ERR_ARG, "tip row %d is outside the alignment (%d rows)", c, aln->impl.n_rows);
   score_lik_batch_full(aln->impl, m->impl, b, out_lnl, (cudaStream_t)stream);
-  PLG_API_END
+  }
 }

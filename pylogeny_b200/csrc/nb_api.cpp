@@ -244,11 +244,10 @@ extern "C" int plg_topology_hash(int n_tips, const int32_t *desc, const int32_t 
   PLG_API_END
 }
 
-extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, int n_tips, const int32_t *desc,
-                                             const int32_t *tip_rows, int64_t shard_index, int64_t shard_count,
-                                             int64_t *n_moves, int32_t *out_moves, int32_t *out_costs,
-                                             void *stream) {
-  PLG_API_BEGIN_LOCKED
+static int fitch_score_neighbourhood_impl(plg_fitch_aln *aln, int move_type, int n_tips, const int32_t *desc,
+                                         const int32_t *tip_rows, int64_t shard_index, int64_t shard_count,
+                                         int64_t *n_moves, int32_t *out_moves, int32_t *out_costs, void *stream) {
+  {
   if (!aln || !desc || !n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
   FitchAln &a = aln->impl;
   for (int x = 0; x < n_tips; x++) {
@@ -328,14 +327,59 @@ extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, 
     tm.lap("finish");
     c0 = c1;
   }
+  }
+  return PLG_OK;
+}
+
+extern "C" int plg_fitch_score_neighbourhood(plg_fitch_aln *aln, int move_type, int n_tips, const int32_t *desc,
+                                             const int32_t *tip_rows, int64_t shard_index, int64_t shard_count,
+                                             int64_t *n_moves, int32_t *out_moves, int32_t *out_costs,
+                                             void *stream) {
+  PLG_API_BEGIN_LOCKED
+  return fitch_score_neighbourhood_impl(aln, move_type, n_tips, desc, tip_rows, shard_index, shard_count, n_moves,
+                                        out_moves, out_costs, stream);
   PLG_API_END
 }
 
-extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int move_type, int n_tips,
-                                           const int32_t *desc, const double *brlen, const int32_t *tip_rows,
-                                           int64_t shard_index, int64_t shard_count, int64_t *n_moves,
-                                           int32_t *out_moves, double *out_lnl, void *stream) {
+// Same with the costs written to DEVICE memory (out_where == PLG_OUT_DEVICE).  Fitch lengths are
+// finished on the host (constant parts per search + device miss counts), so the block goes up again
+// from pinned staging -- still one copy less for a caller who feeds a collective.
+extern "C" int plg_fitch_score_neighbourhood_out(plg_fitch_aln *aln, int move_type, int n_tips, const int32_t *desc,
+                                                 const int32_t *tip_rows, int64_t shard_index, int64_t shard_count,
+                                                 int64_t *n_moves, int32_t *out_moves, int32_t *out_costs,
+                                                 int out_where, void *stream) {
   PLG_API_BEGIN_LOCKED
+  if (out_where == PLG_OUT_HOST || !out_costs)
+    return fitch_score_neighbourhood_impl(aln, move_type, n_tips, desc, tip_rows, shard_index, shard_count, n_moves,
+                                          out_moves, out_costs, stream);
+  if (out_where != PLG_OUT_DEVICE) PLG_FAIL(PLG_ERR_ARG, "out_where: PLG_OUT_HOST or PLG_OUT_DEVICE");
+  if (!n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  int64_t M = 0;
+  const int rc0 = fitch_score_neighbourhood_impl(aln, move_type, n_tips, desc, tip_rows, shard_index, shard_count, &M,
+                                                 out_moves, nullptr, stream);  // size (and the move table) first
+  if (rc0 != PLG_OK) return rc0;
+  static thread_local HostArr<int32_t> stage;
+  stage.resize((size_t)std::max<int64_t>(1, M));
+  const int rc = fitch_score_neighbourhood_impl(aln, move_type, n_tips, desc, tip_rows, shard_index, shard_count, n_moves,
+                                                nullptr, stage.data(), stream);
+  if (rc != PLG_OK) return rc;
+  int64_t lo, hi;
+  shard_range(M, shard_index, shard_count, &lo, &hi);
+  if (hi > lo) {
+    PLG_CUDA(cudaMemcpyAsync(out_costs + lo, stage.data() + lo, (size_t)(hi - lo) * sizeof(int32_t), cudaMemcpyHostToDevice,
+                             (cudaStream_t)stream));
+    PLG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  PLG_API_END
+}
+
+// out_dev: out_lnl is device memory.  The device-planned SPR walk writes there directly; the other
+// planners (TBR, NNI, radius-limited, 20 states) finish on the host and go up again from staging.
+static int lik_score_neighbourhood_impl(plg_lik_aln *aln, plg_model *m, int move_type, int n_tips,
+                                        const int32_t *desc, const double *brlen, const int32_t *tip_rows,
+                                        int64_t shard_index, int64_t shard_count, int64_t *n_moves,
+                                        int32_t *out_moves, double *out_lnl, bool out_dev, void *stream) {
+  {
   if (!aln || !m || !desc || !brlen || !n_moves) PLG_FAIL(PLG_ERR_ARG, "null argument");
   LikAln &a = aln->impl;
   for (int x = 0; x < n_tips; x++) {
@@ -343,9 +387,27 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
     if (row < 0 || row >= a.n_rows) PLG_FAIL(PLG_ERR_ARG, "tip row %d is outside the alignment", row);
   }
   StageTimer tm;
-  if (move_type == PLG_MOVE_TBR)
-    return score_tbr_lik(a, m->impl, n_tips, desc, brlen, tip_rows, shard_index, shard_count, n_moves, out_moves,
-                         out_lnl, (cudaStream_t)stream);
+  static thread_local HostArr<double> stage;  // host-finished planners with a device output
+  auto stage_up = [&](int64_t M) {
+    int64_t lo, hi;
+    shard_range(M, shard_index, shard_count, &lo, &hi);
+    if (hi > lo) {
+      PLG_CUDA(cudaMemcpyAsync(out_lnl + lo, stage.data() + lo, (size_t)(hi - lo) * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+      PLG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+  };
+  if (move_type == PLG_MOVE_TBR) {
+    if (!(out_dev && out_lnl))
+      return score_tbr_lik(a, m->impl, n_tips, desc, brlen, tip_rows, shard_index, shard_count, n_moves, out_moves,
+                           out_lnl, (cudaStream_t)stream);
+    int64_t M = 0;
+    score_tbr_lik(a, m->impl, n_tips, desc, brlen, tip_rows, shard_index, shard_count, &M, nullptr, nullptr, (cudaStream_t)stream);
+    stage.resize((size_t)std::max<int64_t>(1, M));
+    score_tbr_lik(a, m->impl, n_tips, desc, brlen, tip_rows, shard_index, shard_count, n_moves, out_moves, stage.data(),
+                  (cudaStream_t)stream);
+    stage_up(M);
+    return PLG_OK;
+  }
   const int depth = depth_for(move_type);
   // Full-radius SPR neighbourhood, whole or one shard (DNA x Gamma-4 walks): O(n) host records, the
   // search walks are laid out by spr_lik_plan_kernel (PLG_LIK_NB_PLAN=host keeps the host planner)
@@ -375,8 +437,10 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
         enumerate_spr(t, depth, nb0);
         fill_moves(nb0, out_moves);
       }
-      if (hi > lo)  // (out_lnl is indexed by neighbour: the shard's block starts at lo)
+      if (hi > lo) {  // (out_lnl is indexed by neighbour: the shard's block starts at lo)
+        OutDeviceScope scope(out_dev);
         run_lik_program(a, m->impl, lik_workspace(), p, out_lnl + lo, (cudaStream_t)stream, whole ? out_moves : nullptr);
+      }
       tm.lap("run");
       return PLG_OK;
     }
@@ -390,7 +454,31 @@ extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int m
   if (!out_lnl || M == 0) return PLG_OK;
   int64_t lo, hi;
   shard_range(M, shard_index, shard_count, &lo, &hi);
-  score_spr_lik(a, m->impl, nb, tip_rows, lo, hi, out_lnl, (cudaStream_t)stream);
+  if (out_dev) stage.resize((size_t)M);
+  score_spr_lik(a, m->impl, nb, tip_rows, lo, hi, out_dev ? stage.data() : out_lnl, (cudaStream_t)stream);
+  if (out_dev) stage_up(M);
   tm.lap("score");
+  }
+  return PLG_OK;
+}
+
+extern "C" int plg_lik_score_neighbourhood(plg_lik_aln *aln, plg_model *m, int move_type, int n_tips,
+                                           const int32_t *desc, const double *brlen, const int32_t *tip_rows,
+                                           int64_t shard_index, int64_t shard_count, int64_t *n_moves,
+                                           int32_t *out_moves, double *out_lnl, void *stream) {
+  PLG_API_BEGIN_LOCKED
+  return lik_score_neighbourhood_impl(aln, m, move_type, n_tips, desc, brlen, tip_rows, shard_index, shard_count, n_moves,
+                                      out_moves, out_lnl, false, stream);
+  PLG_API_END
+}
+
+extern "C" int plg_lik_score_neighbourhood_out(plg_lik_aln *aln, plg_model *m, int move_type, int n_tips,
+                                               const int32_t *desc, const double *brlen, const int32_t *tip_rows,
+                                               int64_t shard_index, int64_t shard_count, int64_t *n_moves,
+                                               int32_t *out_moves, double *out_lnl, int out_where, void *stream) {
+  PLG_API_BEGIN_LOCKED
+  if (out_where != PLG_OUT_HOST && out_where != PLG_OUT_DEVICE) PLG_FAIL(PLG_ERR_ARG, "out_where: PLG_OUT_HOST or PLG_OUT_DEVICE");
+  return lik_score_neighbourhood_impl(aln, m, move_type, n_tips, desc, brlen, tip_rows, shard_index, shard_count, n_moves,
+                                      out_moves, out_lnl, out_where == PLG_OUT_DEVICE, stream);
   PLG_API_END
 }

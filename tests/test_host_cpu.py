@@ -126,16 +126,38 @@ def test_bench_reference_arm_prints_one_json_line():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, PLG_BENCH_REF_SECONDS="1.5")
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=300, text=True)
-    assert r.returncode == 0, r.stderr[-500:]
-    lines = [l for l in r.stdout.splitlines() if l.strip()]
-    assert len(lines) == 1
-    d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["unit"] == "tree-sites/s" and d["value"] > 0 and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
-    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("BASELINE configs[1]")
+    for workload, kinds, starts in ((None, ("port",), "north_star target shape"), ("fitch_target", ("reference", "port"), "BASELINE configs[2]"),
+                                    ("aa_c5", ("port",), "BASELINE configs[4]")):
+        cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"]
+        if workload:
+            cmd += ["--workload", workload]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=300, text=True)
+        assert r.returncode == 0, r.stderr[-500:]
+        lines = [l for l in r.stdout.splitlines() if l.strip()]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["unit"] == "tree-sites/s" and d["value"] > 0 and d["higher_is_better"] is True
+        assert d["cpu_baseline"]["kind"] in kinds and d["cpu_baseline"]["cores"] >= 1
+        assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert d["config"]["workload"].startswith(starts)
+
+
+def test_bench_reference_arm_is_product_free():
+    """The CPU arm scores trees the REFERENCE's rearrangement code enumerated (committed fixture) and never
+    loads the product: no pylogeny_b200 module, no libpylogeny_b200.so in the process."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json; sys.argv = ['bench.py']; sys.path.insert(0, %r); import bench\n"
+            "cb, dt = bench.cpu_sample('lnl_c2', 0.5)\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "print(json.dumps({'mods': [m for m in sys.modules if m.startswith('pylogeny_b200')], "
+            "'so': 'libpylogeny_b200' in maps, 'kind': cb['kind'], 'v': cb['value']}))" % root)
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    import json
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["mods"] == [] and d["so"] is False and d["kind"] == "port" and d["v"] > 0
 
 
 def test_protein_tables():
