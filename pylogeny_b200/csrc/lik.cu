@@ -20,6 +20,7 @@
 #include <cstring>
 
 #include "lik.h"
+#include "lik_pmatrix.cuh"
 #include "treewalk.h"
 
 namespace plg {
@@ -31,9 +32,6 @@ constexpr double MINLH = 1.0 / TWO256;
 constexpr double LOG_MINLH = -256.0 * 0.693147180559945309417232121458176568;
 constexpr int LIK_THREADS = 256;
 
-template <int K>
-struct NCodes { static constexpr int value = K == 4 ? 16 : 23; };
-
 // ----------------------------------------------------------------------------
 // device
 // ----------------------------------------------------------------------------
@@ -41,33 +39,9 @@ template <int K, int R>
 __global__ void pmatrix_kernel(const ModelDev *__restrict__ model, const double *__restrict__ brlen,
                                const unsigned int *__restrict__ masks, double *__restrict__ pmat,
                                double *__restrict__ tiptab, const int *__restrict__ idx = nullptr) {
-  constexpr int KK = K * K, KKP = KK + 1, NC = NCodes<K>::value;
-  __shared__ double ex[R * K];
-  __shared__ double Pm[R * KKP];
+  constexpr int KKP = K * K + 1, NC = NCodes<K>::value;
   const int pm = idx ? idx[blockIdx.x] : blockIdx.x;  // (idx: only the entries whose length changed)
-  const double t = brlen[pm];
-  for (int e = threadIdx.x; e < R * K; e += blockDim.x)
-    ex[e] = exp(model->eval[e % K] * t * model->rates[e / K]);
-  __syncthreads();
-  for (int e = threadIdx.x; e < R * KK; e += blockDim.x) {
-    const int r = e / KK, i = (e / K) % K, j = e % K;
-    double s = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < K; k++) s += model->U[i * K + k] * ex[r * K + k] * model->Uinv[k * K + j];
-    s = fmax(s, 0.0);  // transition probabilities: round-off can leave -1e-17 at t ~ 0
-    if (t == 0.0) s = (i == j) ? 1.0 : 0.0;  // a zero-length branch is the identity exactly
-    Pm[r * KKP + i * K + j] = s;
-    pmat[(int64_t)pm * R * KKP + r * KKP + i * K + j] = s;
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < NC * R * K; e += blockDim.x) {
-    const int code = e / (R * K), r = (e / K) % R, k = e % K;
-    const unsigned int m = masks[code];
-    double s = 0.0;
-    for (int j = 0; j < K; j++)
-      if (m >> j & 1) s += Pm[r * KKP + k * K + j];
-    tiptab[(int64_t)pm * NC * R * K + e] = s;
-  }
+  pmatrix_block<K, R>(model, brlen[pm], masks, pmat + (int64_t)pm * R * KKP, tiptab + (int64_t)pm * NC * R * K);
 }
 
 // Shared-memory staging of one operand's matrix: tip -> lookup table, inner -> P-matrix.

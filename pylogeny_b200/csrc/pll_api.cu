@@ -25,6 +25,7 @@
 
 #include "hostpool.h"
 #include "lik.h"
+#include "lik_pmatrix.cuh"
 #include "neighbourhood.h"
 
 namespace plg {
@@ -284,7 +285,11 @@ struct PllProblem {
       if (!tree.is_tip(bfs[i])) clv_update(bfs[i], tree.slot_of(bfs[i], par[bfs[i]]));
   }
 
-  double loglik(int max_passes) {
+  double loglik(int max_passes);
+
+  // the literal per-branch host loop (one device round trip per Newton step): single-category models,
+  // and the A/B reference of the lockstep path (PLG_PLL_HANDLE_MODE=host)
+  double loglik_host_loop(int max_passes) {
     if (tree.n_tips < 3) PLG_FAIL(PLG_ERR_UNSUPPORTED, "need at least 3 taxa");
     const int per_block = SM_THREADS / model->R;
     const int n_blocks = (int)(aln->Ppad / per_block);
@@ -483,20 +488,34 @@ struct OptItem {
 };
 
 template <int K, int R>
+__device__ __forceinline__ void newton_step_block(const OptItem it, int item, int64_t Ppad, const double *__restrict__ weights,
+                                                  const ModelDev *__restrict__ model, const double *__restrict__ S,
+                                                  const int *__restrict__ Ssc, double *__restrict__ brlen,
+                                                  int *__restrict__ changed, const double *__restrict__ dpart,
+                                                  int blocks_per_item);
+
+// One makenewz step of one branch per tree, ONE launch (was: sum table, Newton step, P-matrices = three):
+// every block writes its tile of the branch's sum table and its share of the derivative sums at the
+// branch's CURRENT length; the block that finishes last (ticket counter) adds the shares up in a fixed
+// order, takes the Newton step -- reading the table back only if the bad-curvature guard has to try
+// another length --, stores the new length and recomputes the branch's P-matrix and tip table.  Trees
+// that have converged (active == 0) skip the whole step.
+template <int K, int R>
 __global__ void __launch_bounds__(SM_THREADS)
-sumtable_batch_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
-                      const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
-                      const ModelDev *__restrict__ model, const double *__restrict__ clv,
-                      const int *__restrict__ scl, double *__restrict__ S, int *__restrict__ Ssc,
-                      const double *__restrict__ weights, const double *__restrict__ brlen,
-                      double *__restrict__ dpart) {
-  // Besides the table, the block's share of the derivative sums at the branch's CURRENT length:
-  // the Newton step that follows (opt_batch_kernel) normally needs nothing else, so the table is
-  // read back only when the bad-curvature guard has to try another length.
+opt_step_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
+                const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
+                const ModelDev *__restrict__ model, const double *__restrict__ clv,
+                const int *__restrict__ scl, double *__restrict__ S, int *__restrict__ Ssc,
+                const double *__restrict__ weights, double *__restrict__ brlen,
+                double *__restrict__ dpart, const int *__restrict__ active, int *__restrict__ changed,
+                unsigned int *__restrict__ tickets, double *__restrict__ pmat, double *__restrict__ tiptab,
+                int pm_stride, int tip_stride) {
   __shared__ double tab[3][R * K];
   __shared__ double red[3][SM_THREADS / 32];
+  __shared__ int s_last;
   const int item = blockIdx.x / blocks_per_item;
   const OptItem it = items[item];
+  if (!active[it.tree]) return;
   if (threadIdx.x < R * K) {
     const double z = fmin(fmax(exp(-brlen[it.branch]), PLL_ZMIN), PLL_ZMAX);
     const double lz = log(fmax(z, PLL_ZMIN));
@@ -570,18 +589,46 @@ sumtable_batch_kernel(const OptItem *__restrict__ items, int blocks_per_item, in
     for (int i = 0; i < SM_THREADS / 32; i++) t += red[threadIdx.x][i];
     dpart[((int64_t)item * 3 + threadIdx.x) * blocks_per_item + (blockIdx.x - item * blocks_per_item)] = t;
   }
+  if (!tickets) return;  // two-launch form: newton_kernel finishes the step
+  // the last block of this branch to get here finishes the step (threadfence reduction pattern)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(tickets + item, 1u);
+    s_last = ticket == (unsigned int)blocks_per_item - 1;
+    if (s_last) tickets[item] = 0;  // ready for the next step
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  newton_step_block<K, R>(it, item, Ppad, weights, model, S, Ssc, brlen, changed, dpart, blocks_per_item);
+  __syncthreads();
+  pmatrix_block<K, R>(model, brlen[it.branch], masks, pmat + (int64_t)it.branch * pm_stride, tiptab + (int64_t)it.branch * tip_stride);
 }
 
-// One makenewz step (optimise_branch with maxiter = 1) per block, on the tree's sum table.
+// Second launch of the two-launch form (large batches: one block per tree finishes its branch's step).
 template <int K, int R>
 __global__ void __launch_bounds__(SM_THREADS)
-opt_batch_kernel(const OptItem *__restrict__ items, int64_t Ppad, const double *__restrict__ weights,
-                 const ModelDev *__restrict__ model, const double *__restrict__ S, const int *__restrict__ Ssc,
-                 double *__restrict__ brlen, const int *__restrict__ active, int *__restrict__ changed,
-                 const double *__restrict__ dpart, int blocks_per_item) {
-  constexpr int RK = R * K;
+newton_kernel(const OptItem *__restrict__ items, int blocks_per_item, int64_t Ppad, const unsigned int *__restrict__ masks,
+              const ModelDev *__restrict__ model, const double *__restrict__ S, const int *__restrict__ Ssc,
+              const double *__restrict__ weights, double *__restrict__ brlen, const double *__restrict__ dpart,
+              const int *__restrict__ active, int *__restrict__ changed, double *__restrict__ pmat,
+              double *__restrict__ tiptab, int pm_stride, int tip_stride) {
   const OptItem it = items[blockIdx.x];
   if (!active[it.tree]) return;
+  newton_step_block<K, R>(it, blockIdx.x, Ppad, weights, model, S, Ssc, brlen, changed, dpart, blocks_per_item);
+  __syncthreads();
+  pmatrix_block<K, R>(model, brlen[it.branch], masks, pmat + (int64_t)it.branch * pm_stride, tiptab + (int64_t)it.branch * tip_stride);
+}
+
+// One makenewz step (optimise_branch with maxiter = 1) by one block, on the tree's sum table.
+template <int K, int R>
+__device__ __forceinline__ void newton_step_block(const OptItem it, int item, int64_t Ppad, const double *__restrict__ weights,
+                                                  const ModelDev *__restrict__ model, const double *__restrict__ S,
+                                                  const int *__restrict__ Ssc, double *__restrict__ brlen,
+                                                  int *__restrict__ changed, const double *__restrict__ dpart,
+                                                  int blocks_per_item) {
+  constexpr int RK = R * K;
   __shared__ double tab[3][RK];
   __shared__ double red[3][SM_THREADS / 32];
   __shared__ double sh_lz;
@@ -605,8 +652,8 @@ opt_batch_kernel(const OptItem *__restrict__ items, int64_t Ppad, const double *
     }
     __syncthreads();
     double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-    if (guard == 0) {  // the sums at the current length came with the table (sumtable_batch_kernel)
-      const double *dp = dpart + (int64_t)blockIdx.x * 3 * blocks_per_item;
+    if (guard == 0) {  // the sums at the current length came with the table
+      const double *dp = dpart + (int64_t)item * 3 * blocks_per_item;
       for (int b = threadIdx.x; b < blocks_per_item; b += SM_THREADS) {
         v0 += dp[b]; v1 += dp[blocks_per_item + b]; v2 += dp[2 * blocks_per_item + b];
       }
@@ -660,6 +707,7 @@ opt_batch_kernel(const OptItem *__restrict__ items, int64_t Ppad, const double *
     if (z > PLL_ZMAX) z = PLL_ZMAX;
     brlen[it.branch] = -log(z);
     if (fabs(z - z0) > PLL_DELTAZ) changed[it.tree] = 1;
+    __threadfence_block();
   }
 }
 
@@ -785,9 +833,22 @@ struct Aa20Family {
   }
 };
 
+// Device buffers of one batch.  A caller that scores one tree at a time (the per-handle drop-in path,
+// plg_pll_loglik) keeps a Scratch alive between calls so that nothing is allocated per tree.
+template <typename F>
+struct BatchScratch {
+  DevBuf<double> clv, S, pmat, tiptab, brlen, partial, lnl, dpart;
+  DevBuf<int> scl, Ssc, idx, flags;
+  DevBuf<unsigned int> tickets;
+  DevBuf<typename F::Op> d_ops;
+  DevBuf<OptItem> d_items;
+  DevBuf<LikEval> d_evals;
+};
+
 template <typename F>
 static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<UTree> &trees,
-                             const std::vector<std::vector<int32_t>> &tip_rows, int passes, double *out_lnl) {
+                             const std::vector<std::vector<int32_t>> &tip_rows, int passes, double *out_lnl,
+                             BatchScratch<F> *keep = nullptr) {
   constexpr int K = F::K, R = F::R, RK = K * R;
   using Op = typename F::Op;
   const int64_t n_trees = (int64_t)trees.size();
@@ -799,11 +860,15 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   const size_t per_tree = ((size_t)n_inner * (RK * 8 + 4) + RK * 8 + 4) * Ppad + (size_t)n_br * (F::PM_STRIDE + F::TIP_STRIDE) * 8;
   int64_t B = std::max<int64_t>(1, std::min<int64_t>(n_trees, (int64_t)(std::min<size_t>(free_b / 2, (size_t)64 << 30) / per_tree)));
   if (const char *e = getenv("PLG_PLL_BATCH_CHUNK")) B = std::max<int64_t>(1, std::min<int64_t>(B, atoll(e)));  // tests: several chunks
-  DevBuf<double> clv, S, pmat, tiptab, brlen, partial, lnl, dpart;
-  DevBuf<int> scl, Ssc, idx, flags;
-  DevBuf<Op> d_ops;
-  DevBuf<OptItem> d_items;
-  DevBuf<LikEval> d_evals;
+  BatchScratch<F> local;
+  BatchScratch<F> &sc_ = keep ? *keep : local;
+  DevBuf<double> &clv = sc_.clv, &S = sc_.S, &pmat = sc_.pmat, &tiptab = sc_.tiptab, &brlen = sc_.brlen, &partial = sc_.partial,
+                 &lnl = sc_.lnl, &dpart = sc_.dpart;
+  DevBuf<int> &scl = sc_.scl, &Ssc = sc_.Ssc, &idx = sc_.idx, &flags = sc_.flags;
+  DevBuf<unsigned int> &tickets = sc_.tickets;
+  DevBuf<Op> &d_ops = sc_.d_ops;
+  DevBuf<OptItem> &d_items = sc_.d_items;
+  DevBuf<LikEval> &d_evals = sc_.d_evals;
   clv.alloc((size_t)B * n_inner * RK * Ppad);
   scl.alloc((size_t)B * n_inner * Ppad);
   S.alloc((size_t)B * RK * Ppad);
@@ -822,6 +887,8 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   idx.alloc((size_t)B * n_br);
   const int bpi = (int)(Ppad / (SM_THREADS / R));
   dpart.alloc((size_t)B * 3 * bpi);
+  tickets.alloc((size_t)B);
+  PLG_CUDA(cudaMemsetAsync(tickets.p, 0, (size_t)B * sizeof(unsigned int), 0));
   std::vector<Op> h_ops;
   std::vector<OptItem> h_items;
   std::vector<int> h_idx, h_flags;
@@ -854,7 +921,16 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
       opt_off[s + 1] = (int64_t)h_items.size();
     }
     for (int64_t i = 0; i < cnt; i++) h_evals.push_back(plans[i].eval);
-    h_brlen.assign((size_t)cnt * n_br, -std::log(PLL_DEFAULTZ));  // useDefaultz (libpllWrapper.c:152)
+    // start from the trees' current lengths (callers load default z = 0.9: useDefaultz, libpllWrapper.c:152;
+    // a handle scored twice continues from where the first call left its branches, like the reference)
+    h_brlen.assign((size_t)cnt * n_br, 0.0);
+    for (int64_t i = 0; i < cnt; i++) {
+      const UTree &t = trees[t0 + i];
+      int b = 0;
+      for (int x = 0; x < t.n_nodes; x++)  // same numbering as plan_tree
+        for (int k = 0; k < 3; k++)
+          if (t.nb[x][k] > x) h_brlen[(size_t)i * n_br + b++] = t.len[x][k];
+    }
     h_flags.assign((size_t)2 * cnt, 0);
     for (int64_t i = 0; i < cnt; i++) h_flags[i] = 1;  // active; changed = 0
     PLG_CUDA(cudaMemcpy(d_ops.p, h_ops.data(), h_ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
@@ -865,6 +941,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
     PLG_CUDA(cudaMemcpy(flags.p, h_flags.data(), h_flags.size() * sizeof(int), cudaMemcpyHostToDevice));
     int *active = flags.p, *changed = flags.p + cnt;
     cudaStream_t st = 0;
+    const bool fused = cnt <= 4;
     F::pmatrices(aln, model, brlen.p, nullptr, cnt * n_br, pmat.p, tiptab.p, st);
     for (int j = 0; j < n_inner; j++)
       F::updates(aln, model, d_ops.p + down_off[j], down_off[j + 1] - down_off[j], pmat.p, tiptab.p, clv.p, scl.p, st);
@@ -874,13 +951,19 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
         if (nc) F::updates(aln, model, d_ops.p + pass_ops0 + clv_off[s], nc, pmat.p, tiptab.p, clv.p, scl.p, st);
         if (no) {
           const OptItem *its = d_items.p + opt_off[s];
-          sumtable_batch_kernel<K, R><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
+          // a few trees: one launch per step (the last block of a branch finishes it: launch-bound regime);
+          // many trees: two launches, no fences or tickets in the wide one
+          opt_step_kernel<K, R><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
               its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
-              aln.weights.p, brlen.p, dpart.p);
-          opt_batch_kernel<K, R><<<(unsigned)no, SM_THREADS, 0, st>>>(its, Ppad, aln.weights.p, model.d.p, S.p, Ssc.p,
-                                                                      brlen.p, active, changed, dpart.p, bpi);
-          count_launch(2);
-          F::pmatrices(aln, model, brlen.p, idx.p + opt_off[s], no, pmat.p, tiptab.p, st);
+              aln.weights.p, brlen.p, dpart.p, active, changed, fused ? tickets.p : nullptr, pmat.p, tiptab.p,
+              F::PM_STRIDE, F::TIP_STRIDE);
+          count_launch();
+          if (!fused) {
+            newton_kernel<K, R><<<(unsigned)no, SM_THREADS, 0, st>>>(its, bpi, Ppad, aln.masks.p, model.d.p, S.p, Ssc.p,
+                                                                      aln.weights.p, brlen.p, dpart.p, active, changed,
+                                                                      pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
+            count_launch();
+          }
         }
       }
       next_pass_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((int)cnt, active, changed);
@@ -902,6 +985,33 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
         }
     }
   }
+}
+
+// One handle = one tree: the same lockstep program as a batch of one (all Newton steps stay on the
+// device; the host enqueues ~5 n launches per pass and waits once), on buffers kept between calls.
+double PllProblem::loglik(int max_passes) {
+  if (tree.n_tips < 3) PLG_FAIL(PLG_ERR_UNSUPPORTED, "need at least 3 taxa");
+  const char *mode = getenv("PLG_PLL_HANDLE_MODE");
+  const bool dna4 = aln->K == 4 && model->R == 4, aa20 = aln->K == 20 && model->R == 4;
+  if ((mode && !strcmp(mode, "host")) || !(dna4 || aa20)) return loglik_host_loop(max_passes);
+  std::vector<UTree> trees(1, tree);
+  std::vector<std::vector<int32_t>> rows(1, tip_rows);
+  double out = 0.0;
+  if (dna4) {
+    static thread_local BatchScratch<Dna4Family> keep[8];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    pll_loglik_batch<Dna4Family>(*aln, *model, trees, rows, max_passes, &out, &keep[dev & 7]);
+  } else {
+    static thread_local BatchScratch<Aa20Family> keep[8];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    pll_loglik_batch<Aa20Family>(*aln, *model, trees, rows, max_passes, &out, &keep[dev & 7]);
+  }
+  tree = trees[0];
+  lnl = out;
+  smoothed = true;
+  return lnl;
 }
 
 }  // namespace plg

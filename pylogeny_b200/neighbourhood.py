@@ -197,17 +197,19 @@ def parsimony_greedy(aln, desc, tip_rows=None, move_type=MOVE_SPR, max_steps=100
     return path, d
 
 
-def likelihood_greedy(ali, newick, top=16, max_steps=1000, passes=3):
-    """Greedy hill-climb by likelihood with the reference's per-tree semantics (what
-    heuristic.likelihoodGreedy / smoothGreedy do through scoring.getLogLikelihood, heuristic.py:107-260:
-    every candidate's branch lengths are smoothed before it is scored), in two engine calls per step:
+def likelihood_greedy(ali, newick, shortlist=None, max_steps=1000, passes=3):
+    """Greedy hill-climb by likelihood over the SPR landscape with the reference's per-tree scoring
+    semantics: EVERY neighbour of the current tree is scored the way `vertex.scoreLikelihood` ->
+    `scoring.getLogLikelihood` scores it (landscape.py:1302-1314, scoring.py:41-75, as
+    heuristic.likelihoodGreedy does at heuristic.py:148-153) -- default branch lengths, `passes`
+    smoothing passes, lnL -- in ONE batched engine call per step (`libpllWrapper.getLogLikelihoodBatch`),
+    and the climb moves to the best neighbour while it beats the current tree's smoothed lnL.
 
-      1. GTR+G4 lnL of ALL SPR neighbours at the current tree's branch lengths (fixed-length
-         edge-insertion scan, `score_likelihood`) ranks the neighbourhood;
-      2. the `top` best get the reference's treatment -- default lengths, `passes` smoothing
-         passes, lnL -- in one batched call (`libpllWrapper.getLogLikelihoodBatch`).
+    shortlist=k (an APPROXIMATION, not the reference's semantics -- "lazy SPR"): the neighbourhood is
+    first ranked by GTR+G4 lnL at the current tree's branch lengths (fixed-length edge-insertion scan,
+    `score_likelihood`, ~1e3 x cheaper per neighbour) and only the k best are smoothed.  The path can
+    differ from shortlist=None when the scan's ranking and the smoothed ranking disagree beyond rank k.
 
-    The climb moves to the best smoothed neighbour while it beats the current tree's smoothed lnL.
     `ali`: alignment.phylipFriendlyAlignment (DNA); `newick`: start tree on its taxa.
     Returns (path of smoothed lnL, final Newick with optimised branch lengths)."""
     import ctypes as C_
@@ -215,29 +217,33 @@ def likelihood_greedy(ali, newick, top=16, max_steps=1000, passes=3):
     phy, part = ali.getPhylip(), pll.model_for(ali).getFileName()
     labels = ali.getTaxa()
     taxa = {l: i for i, l in enumerate(labels)}
-    # the model the libpllWrapper drop-in builds for this alignment (GTR, all rates 1, empirical
-    # frequencies, alpha = 1): read it back from a handle so both calls score under the same model
-    h = W.new(phy, newick, part)
-    K, P = C_.c_int(), C_.c_int64()
-    freqs, rates = np.zeros(4), np.zeros(4)
-    dp = C_.POINTER(C_.c_double)
-    _lib.check(_lib.lib().plg_pll_info(h.ptr, C_.byref(K), C_.byref(P), freqs.ctypes.data_as(dp), rates.ctypes.data_as(dp)))
-    W.destroy(h)
-    if K.value != 4:
-        raise ValueError("likelihood_greedy is written for DNA alignments")
-    codes, w = likelihood.compress_columns(likelihood.encode_sequences(ali.toStrList(), _lib.DATA_DNA))
-    la = likelihood.LikAlignment(codes, w)
-    model = likelihood.Model(np.ones(6), freqs, 1.0)
+    la = model = None
+    if shortlist is not None:
+        # the model the libpllWrapper drop-in builds for this alignment (GTR, all rates 1, empirical
+        # frequencies, alpha = 1): read it back from a handle so both calls score under the same model
+        h = W.new(phy, newick, part)
+        K, P = C_.c_int(), C_.c_int64()
+        freqs, rates = np.zeros(4), np.zeros(4)
+        dp = C_.POINTER(C_.c_double)
+        _lib.check(_lib.lib().plg_pll_info(h.ptr, C_.byref(K), C_.byref(P), freqs.ctypes.data_as(dp), rates.ctypes.data_as(dp)))
+        W.destroy(h)
+        if K.value != 4:
+            raise ValueError("the shortlist scan is written for DNA alignments")
+        codes, w = likelihood.compress_columns(likelihood.encode_sequences(ali.toStrList(), _lib.DATA_DNA))
+        la = likelihood.LikAlignment(codes, w)
+        model = likelihood.Model(np.ones(6), freqs, 1.0)
     try:
         (cur,), (cur_nw,) = W.getLogLikelihoodBatch(phy, [newick], part, passes)
         path = [cur]
         for _ in range(max_steps):
             d, br, rows, tips = newick_to_desc(cur_nw, taxa)
-            _, scan = score_likelihood(la, model, d, br, rows, want_moves=False)
-            if len(scan) == 0:
+            if neighbourhood_size(d) == 0:
                 break
-            best = np.argsort(-scan, kind="stable")[:top].astype(np.int64)
-            descs, _, _ = neighbour_trees(d, None, best, tip_rows=rows)
+            sel = None
+            if shortlist is not None:
+                _, scan = score_likelihood(la, model, d, br, rows, want_moves=False)
+                sel = np.argsort(-scan, kind="stable")[:shortlist].astype(np.int64)
+            descs, _, _ = neighbour_trees(d, None, sel, tip_rows=rows)
             cands = [desc_to_newick(x, tips) for x in descs]
             lnl, opt = W.getLogLikelihoodBatch(phy, cands, part, passes)
             j = int(np.argmax(lnl))
@@ -247,5 +253,6 @@ def likelihood_greedy(ali, newick, top=16, max_steps=1000, passes=3):
             path.append(cur)
         return path, cur_nw
     finally:
-        la.close()
-        model.close()
+        if la is not None:
+            la.close()
+            model.close()

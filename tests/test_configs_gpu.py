@@ -170,10 +170,10 @@ def test_c5_protein_tbr_neighbourhood():
 
 
 def test_likelihood_climb_scan_then_batched_smoothing():
-    """Likelihood hill-climb with the reference's per-tree semantics: a fixed-length scan of the
-    whole SPR neighbourhood ranks it, the best few are smoothed in one batch.  The path increases
-    strictly, the final lnL is what one libpllWrapper handle returns for the final topology, and the
-    climb recovers (most of) the gap to the tree the data were simulated on."""
+    """Likelihood hill-climb, shortlist mode (an approximation: a fixed-length scan of the whole SPR
+    neighbourhood ranks it, the best few are smoothed in one batch).  The path increases strictly, the
+    final lnL is what one libpllWrapper handle returns for the final topology, and the climb recovers
+    (most of) the gap to the tree the data were simulated on."""
     from pylogeny_b200 import alignment, libpllWrapper as W, neighbourhood as nbh, pll
     from util import simulate_dna
     rng = np.random.default_rng(77)
@@ -184,7 +184,7 @@ def test_likelihood_climb_scan_then_batched_smoothing():
     ali = alignment.phylipFriendlyAlignment(names=["s%d" % i for i in range(n)], seqs=seqs)
     labels = ali.getTaxa()
     start = desc_to_newick(random_desc(rng, n), labels)
-    path, final = nbh.likelihood_greedy(ali, start, top=12, max_steps=6)
+    path, final = nbh.likelihood_greedy(ali, start, shortlist=12, max_steps=6)
     assert len(path) >= 3 and all(b > a for a, b in zip(path, path[1:]))
     pm = ali._pllmodel
     h = W.new(ali.getPhylip(), final, pm.getFileName())
@@ -194,3 +194,45 @@ def test_likelihood_climb_scan_then_batched_smoothing():
     (truth,), _ = W.getLogLikelihoodBatch(ali.getPhylip(), [desc_to_newick(true, labels)], pm.getFileName())
     assert path[-1] > path[0] + 0.5 * (truth - path[0])  # at least half of the way to the generating tree
     pm.close(); ali.close()
+
+
+def test_likelihood_climb_reference_semantics_smooths_every_neighbour():
+    """likelihood_greedy() by default gives EVERY neighbour the reference's per-tree treatment
+    (heuristic.py:148-153 -> vertex.scoreLikelihood -> scoring.getLogLikelihood: default lengths, 3
+    smoothing passes, lnL).  One climb step on a small case equals doing exactly that through one
+    libpllWrapper handle per neighbour (the unbatched drop-in path), and picks the same winner."""
+    from pylogeny_b200 import alignment, libpllWrapper as W, neighbourhood as nbh, pll
+    from util import simulate_dna
+    rng = np.random.default_rng(78)
+    n, S = 7, 600
+    true = random_desc(rng, n)
+    br = rng.exponential(0.08, true.shape) + 0.01
+    seqs = simulate_dna(rng, true, br, S, np.array([1.0, 3.0, 0.7, 1.3, 4.0, 1.0]), np.array([0.3, 0.2, 0.2, 0.3]))
+    ali = alignment.phylipFriendlyAlignment(names=["s%d" % i for i in range(n)], seqs=seqs)
+    labels = ali.getTaxa()
+    taxa = {l: i for i, l in enumerate(labels)}
+    start = desc_to_newick(random_desc(rng, n), labels)
+    path, final = nbh.likelihood_greedy(ali, start, max_steps=1)
+    part = pll.model_for(ali).getFileName()
+    # the same step by hand, one handle per tree
+    h = W.new(ali.getPhylip(), start, part)
+    cur = W.getLogLikelihood(h)
+    cur_nw = W.getNewickString(h)
+    W.destroy(h)
+    assert abs(path[0] - cur) <= 1e-9 * abs(cur)
+    d, b, rows, tips = nbh.newick_to_desc(cur_nw, taxa)
+    descs, _, _ = nbh.neighbour_trees(d, None, None, tip_rows=rows)
+    assert len(descs) == 2 * (n - 3) * (2 * n - 7)
+    per_tree = []
+    for x in descs:
+        h = W.new(ali.getPhylip(), nbh.desc_to_newick(x, tips), part)
+        per_tree.append(W.getLogLikelihood(h))
+        W.destroy(h)
+    best = max(per_tree)
+    if best > cur:
+        assert len(path) == 2 and abs(path[1] - best) <= 1e-9 * abs(best)
+        d2, _, r2, _ = nbh.newick_to_desc(final, taxa)
+        assert nbh.topology_hash(d2, r2) == nbh.topology_hash(descs[int(np.argmax(per_tree))], rows)
+    else:
+        assert len(path) == 1
+    pll.model_for(ali).close(); ali.close()

@@ -207,10 +207,46 @@ def test_alignment_cache_is_keyed_by_file_identity(tmp_path):
     pm.close(); ali.close()
 
 
-def test_batched_getLogLikelihood_equals_per_tree_path():
+def test_handle_lockstep_equals_host_loop(monkeypatch):
+    """plg_pll_loglik on one handle runs the lockstep program as a batch of one (every Newton step on the
+    device); PLG_PLL_HANDLE_MODE=host keeps the literal loop with one device round trip per branch.  Same
+    lnL and branch lengths, also when getLogLikelihood is called again on the same handle (the reference
+    mutates the instance: the second call continues from the first call's lengths, libpllWrapper.c:205)."""
+    from pylogeny_b200 import libpllWrapper as W, neighbourhood as nbh, pll
+    ali, d = _case(n=13, S=900, seed=9)
+    labels = ali.getTaxa()
+    taxa = {l: i for i, l in enumerate(labels)}
+    nw = desc_to_newick(d, labels)
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    res = {}
+    for mode in ("host", "device"):
+        if mode == "host":
+            monkeypatch.setenv("PLG_PLL_HANDLE_MODE", "host")
+        else:
+            monkeypatch.delenv("PLG_PLL_HANDLE_MODE")
+        h = W.new(ali.getPhylip(), nw, pm.getFileName())
+        first = W.getLogLikelihood(h)
+        nw1 = W.getNewickString(h)
+        second = W.getLogLikelihood(h)
+        nw2 = W.getNewickString(h)
+        ev = W.evaluate(h)
+        W.destroy(h)
+        res[mode] = (first, second, ev, nbh.newick_to_desc(nw1, taxa)[1], nbh.newick_to_desc(nw2, taxa)[1])
+    a, b = res["host"], res["device"]
+    np.testing.assert_allclose(b[:3], a[:3], rtol=1e-9)
+    assert b[1] >= b[0] - 1e-9 * abs(b[0]) and abs(b[2] - b[1]) <= 1e-9 * abs(b[1])   # smoothing on, evaluate agrees
+    np.testing.assert_allclose(b[3], a[3], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(b[4], a[4], rtol=1e-6, atol=1e-9)
+    assert not np.allclose(b[3], b[4])                                               # the second call moved the branches on
+    pm.close(); ali.close()
+
+
+def test_batched_getLogLikelihood_equals_per_tree_path(monkeypatch):
     """plg_pll_loglik_batch (all trees smoothed in lockstep on the device) against one handle per
-    tree: same lnL and branch lengths up to the summation order of the derivative sums, and the
-    returned lnL equals the oracle's at the returned branch lengths (1e-8)."""
+    tree on the literal host loop: same lnL and branch lengths up to the summation order of the
+    derivative sums, and the returned lnL equals the oracle's at the returned branch lengths (1e-8)."""
+    monkeypatch.setenv("PLG_PLL_HANDLE_MODE", "host")
     from pylogeny_b200 import _lib, libpllWrapper as W, likelihood, neighbourhood as nbh, pll
     ali, d = _case(n=14, S=1200, seed=5)
     labels = ali.getTaxa()
@@ -256,8 +292,9 @@ def test_batched_getLogLikelihood_equals_per_tree_path():
 @pytest.mark.parametrize("n", [3, 4, 5, 9])
 def test_batched_getLogLikelihood_small_trees_and_chunks(n, monkeypatch):
     """Smallest trees (one inner node at n = 3), a trifurcating input Newick, and a batch cut into
-    several device chunks: same answers as one handle per tree."""
+    several device chunks: same answers as one handle per tree (host loop)."""
     from pylogeny_b200 import libpllWrapper as W, pll
+    monkeypatch.setenv("PLG_PLL_HANDLE_MODE", "host")
     ali, d = _case(n=max(n, 4), S=400, seed=20 + n)
     if n == 3:
         from pylogeny_b200 import alignment
@@ -288,9 +325,10 @@ def test_batched_getLogLikelihood_small_trees_and_chunks(n, monkeypatch):
     pm.close(); ali.close()
 
 
-def test_batched_getLogLikelihood_wag():
+def test_batched_getLogLikelihood_wag(monkeypatch):
     """The 20-state family of the batched smoother (clv20 / eval20 kernels, 80-entry sum tables)
-    against one handle per tree."""
+    against one handle per tree (host loop)."""
+    monkeypatch.setenv("PLG_PLL_HANDLE_MODE", "host")
     from pylogeny_b200 import alignment, libpllWrapper as W, pll
     rng = np.random.default_rng(44)
     aa = "ARNDCQEGHILKMFPSTWYV"
@@ -324,9 +362,10 @@ def test_batched_getLogLikelihood_wag():
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4])
-def test_batched_getLogLikelihood_no_signal_data(seed):
+def test_batched_getLogLikelihood_no_signal_data(seed, monkeypatch):
     """Random sequences on few sites: flat or wrongly curved likelihood surfaces on many branches,
-    where makenewz's bad-curvature guard and the z clamps do the work.  Batch == per-tree path."""
+    where makenewz's bad-curvature guard and the z clamps do the work.  Batch == per-tree host loop."""
+    monkeypatch.setenv("PLG_PLL_HANDLE_MODE", "host")
     from pylogeny_b200 import alignment, libpllWrapper as W, pll
     rng = np.random.default_rng(100 + seed)
     n, S = 10, int(rng.integers(8, 60))
