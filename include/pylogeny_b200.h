@@ -130,6 +130,15 @@ int plg_neighbourhood_size(int move_type, int n_tips, const int32_t *desc, int64
 int plg_neighbourhood_trees(int move_type, int n_tips, const int32_t *desc, const double *brlen,
                             const int32_t *tip_rows, int64_t n_sel, const int64_t *sel,
                             int32_t *out_desc, double *out_brlen, uint64_t *out_hash);
+/* Every (pruned branch, target branch) pair of an NNI / SPR neighbourhood INCLUDING the pairs that repeat
+ * a topology -- the move list the reference walks (rearrangement.py:543-594: allSPR emits 4(n-3)(n-2)
+ * moves for 2(n-3)(2n-7) topologies).  out_moves (NULL: count only): int32 [*n_all][5] = the four
+ * columns of the move table above + the index of the move's topology in the distinct list (the row of
+ * out_costs / out_lnl that scores it).  Lets host code keep the reference's per-move rules -- branch
+ * locks (rearrangement.py:228-240), enumeration order (heuristic.py:92-95 tie-breaking) -- around one
+ * engine call per neighbourhood (pylogeny_b200/explore.py). */
+int plg_neighbourhood_all_moves(int move_type, int n_tips, const int32_t *desc, int64_t *n_all,
+                                int32_t *out_moves);
 /* Canonical hash of the unrooted topology; tips are identified by tip_rows[id] (NULL: by id), so
  * the same tree written with its leaves in another order hashes the same. */
 int plg_topology_hash(int n_tips, const int32_t *desc, const int32_t *tip_rows, uint64_t *out);

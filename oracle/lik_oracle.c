@@ -153,6 +153,16 @@ void oracle_pmatrix(int K, const double *eval, const double *U, const double *Ui
   }
 }
 
+/* A model's state frequencies are a probability distribution: tables that sum to 1 only within their
+ * printed digits (PAML's wag.dat: 1 + 3e-6) are normalised before use, as the engine does
+ * (pylogeny_b200/csrc/model.cpp Model::Model).  Without it lnL shifts by P * log(sum pi). */
+static const double *oracle_unit_freqs(int K, const double *freqs, double *buf) {
+  double s = 0;
+  for (int i = 0; i < K; i++) s += freqs[i];
+  for (int i = 0; i < K; i++) buf[i] = freqs[i] / s;
+  return buf;
+}
+
 /* ---- Felsenstein pruning over a post-order descriptor ----
  * Tree: n_tips tips (ids 0..n_tips-1 = rows of `codes`), n_inner internal nodes
  * with ids n_tips+i in post-order; desc[2i],desc[2i+1] = children of internal i,
@@ -165,7 +175,8 @@ double oracle_lnl(int K, int n_tips, int64_t P, const uint8_t *codes,
                   const uint32_t *masks, const double *weights,
                   const double *exch, const double *freqs, double alpha, int ncat,
                   int n_inner, const int32_t *desc, const double *brlen) {
-  double eval[OR_MAXK], U[OR_MAXK * OR_MAXK], Uinv[OR_MAXK * OR_MAXK], rates[64];
+  double eval[OR_MAXK], U[OR_MAXK * OR_MAXK], Uinv[OR_MAXK * OR_MAXK], rates[64], unit[OR_MAXK];
+  freqs = oracle_unit_freqs(K, freqs, unit);
   oracle_eigen(K, exch, freqs, eval, U, Uinv);
   oracle_gamma_rates(alpha, ncat, rates);
   const int RK = ncat * K;
@@ -222,7 +233,8 @@ double oracle_lnl_bruteforce(int K, int n_tips, int64_t P, const uint8_t *codes,
                              const double *exch, const double *freqs, double alpha,
                              int ncat, int n_inner, const int32_t *desc,
                              const double *brlen) {
-  double eval[OR_MAXK], U[OR_MAXK * OR_MAXK], Uinv[OR_MAXK * OR_MAXK], rates[64];
+  double eval[OR_MAXK], U[OR_MAXK * OR_MAXK], Uinv[OR_MAXK * OR_MAXK], rates[64], unit[OR_MAXK];
+  freqs = oracle_unit_freqs(K, freqs, unit);
   oracle_eigen(K, exch, freqs, eval, U, Uinv);
   oracle_gamma_rates(alpha, ncat, rates);
   double *pm = (double *)malloc(sizeof(double) * (size_t)n_inner * 2 * K * K);

@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 
 using namespace plg;
 
@@ -233,6 +234,37 @@ extern "C" int plg_neighbourhood_trees(int move_type, int n_tips, const int32_t 
       desc_from_utree(r, out_desc + i * stride, out_brlen ? out_brlen + i * stride : nullptr);
     }
     if (out_hash) out_hash[i] = m.hash;
+  }
+  PLG_API_END
+}
+
+extern "C" int plg_neighbourhood_all_moves(int move_type, int n_tips, const int32_t *desc, int64_t *n_all,
+                                          int32_t *out_moves) {
+  PLG_API_BEGIN
+  if (!desc || !n_all) PLG_FAIL(PLG_ERR_ARG, "null argument");
+  static thread_local Neighbourhood nb;
+  enumerate_spr(utree_from_desc(n_tips, desc, nullptr), depth_for(move_type), nb);
+  const int64_t A = (int64_t)nb.moves.size();
+  *n_all = A;
+  if (!out_moves) return PLG_OK;
+  std::unordered_map<uint64_t, int> first;  // repeats exist at distance 1 only (enumerate_spr)
+  for (int64_t i = 0; i < A; i++)
+    if (nb.moves[i].depth == 1 && nb.moves[i].unique_id >= 0) first.emplace(nb.moves[i].hash, nb.moves[i].unique_id);
+  const UTree &t = nb.t;
+  for (int64_t i = 0; i < A; i++) {
+    const Move &m = nb.moves[i];
+    const int pe = t.rooted_child_end[3 * m.u + m.k];
+    int id = m.unique_id;
+    if (id < 0) {
+      auto it = first.find(m.hash);
+      if (it == first.end()) PLG_FAIL(PLG_ERR_ARG, "internal: repeated move %lld has no first occurrence", (long long)i);
+      id = it->second;
+    }
+    out_moves[5 * i + 0] = pe;
+    out_moves[5 * i + 1] = pe == t.nb[m.u][m.k] ? 0 : 1;
+    out_moves[5 * i + 2] = t.rooted_child_end[3 * m.x + m.kx];
+    out_moves[5 * i + 3] = m.depth;
+    out_moves[5 * i + 4] = id;
   }
   PLG_API_END
 }

@@ -500,7 +500,7 @@ __device__ __forceinline__ void newton_step_block(const OptItem it, int item, in
 // order, takes the Newton step -- reading the table back only if the bad-curvature guard has to try
 // another length --, stores the new length and recomputes the branch's P-matrix and tip table.  Trees
 // that have converged (active == 0) skip the whole step.
-template <int K, int R>
+template <int K, int R, bool FUSED>
 __global__ void __launch_bounds__(SM_THREADS)
 opt_step_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
                 const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
@@ -589,7 +589,7 @@ opt_step_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_ro
     for (int i = 0; i < SM_THREADS / 32; i++) t += red[threadIdx.x][i];
     dpart[((int64_t)item * 3 + threadIdx.x) * blocks_per_item + (blockIdx.x - item * blocks_per_item)] = t;
   }
-  if (!tickets) return;  // two-launch form: newton_kernel finishes the step
+  if constexpr (FUSED) {  // (two-launch form: newton_kernel finishes the step, and this kernel keeps its registers)
   // the last block of this branch to get here finishes the step (threadfence reduction pattern)
   __threadfence();
   __syncthreads();
@@ -604,6 +604,7 @@ opt_step_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_ro
   newton_step_block<K, R>(it, item, Ppad, weights, model, S, Ssc, brlen, changed, dpart, blocks_per_item);
   __syncthreads();
   pmatrix_block<K, R>(model, brlen[it.branch], masks, pmat + (int64_t)it.branch * pm_stride, tiptab + (int64_t)it.branch * tip_stride);
+  }
 }
 
 // Second launch of the two-launch form (large batches: one block per tree finishes its branch's step).
@@ -953,10 +954,14 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
           const OptItem *its = d_items.p + opt_off[s];
           // a few trees: one launch per step (the last block of a branch finishes it: launch-bound regime);
           // many trees: two launches, no fences or tickets in the wide one
-          opt_step_kernel<K, R><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
-              its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
-              aln.weights.p, brlen.p, dpart.p, active, changed, fused ? tickets.p : nullptr, pmat.p, tiptab.p,
-              F::PM_STRIDE, F::TIP_STRIDE);
+          if (fused)
+            opt_step_kernel<K, R, true><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
+                its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
+                aln.weights.p, brlen.p, dpart.p, active, changed, tickets.p, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
+          else
+            opt_step_kernel<K, R, false><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
+                its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
+                aln.weights.p, brlen.p, dpart.p, active, changed, nullptr, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
           count_launch();
           if (!fused) {
             newton_kernel<K, R><<<(unsigned)no, SM_THREADS, 0, st>>>(its, bpi, Ppad, aln.masks.p, model.d.p, S.p, Ssc.p,

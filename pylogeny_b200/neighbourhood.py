@@ -42,6 +42,18 @@ def topology_hash(desc, tip_rows=None):
     return h.value
 
 
+def all_moves(desc, move_type=MOVE_SPR):
+    """Every (pruned branch, target branch) pair of the NNI / SPR neighbourhood, repeats included: int32
+    [A, 5] = (child end of pruned branch, 0 subtree / 1 complement moves, child end of target branch,
+    distance, index of the move's topology among the distinct neighbours)."""
+    d = _desc(desc)
+    n = C.c_int64()
+    _lib.check(_lib.lib().plg_neighbourhood_all_moves(move_type, d.shape[0] + 1, d.ctypes.data, C.byref(n), None))
+    out = np.empty((n.value, 5), dtype=np.int32)
+    _lib.check(_lib.lib().plg_neighbourhood_all_moves(move_type, d.shape[0] + 1, d.ctypes.data, C.byref(n), out.ctypes.data))
+    return out
+
+
 def neighbour_trees(desc, brlen=None, sel=None, move_type=MOVE_SPR, tip_rows=None):
     """Materialise neighbours `sel` (default: all). Returns (descs [m, n-1, 2], brlens or None, hashes [m])."""
     d = _desc(desc)

@@ -46,10 +46,19 @@ def test_c2_full_size_lnl_spr_neighbourhood():
     moves, lnl = nbh.score_likelihood(a, m, d, br)
     M = 2 * (n - 3) * (2 * n - 7)
     assert len(lnl) == M == 14762 and np.all(np.isfinite(lnl)) and np.all(lnl < 0)
-    sel = np.linspace(0, M - 1, 40).astype(np.int64)
+    # 96 neighbours spread over the whole move list AND over every regraft distance the neighbourhood
+    # holds (moves[:, 3] = steps from the prune point: the depth of the visit inside its search walk):
+    # each against the full re-traversal of the materialised tree and against the FP64 oracle
+    dist = moves[:, 3]
+    per_depth = [np.flatnonzero(dist == k) for k in np.unique(dist)]
+    sel = np.unique(np.concatenate([np.linspace(0, M - 1, 40).astype(np.int64)] +
+                                   [ids[np.linspace(0, len(ids) - 1, min(len(ids), 3)).astype(np.int64)] for ids in per_depth]))
+    if len(sel) < 96:
+        sel = np.unique(np.concatenate([sel, rng.choice(M, 96 - len(sel), replace=False)]))
+    assert len(sel) >= 64 and set(np.unique(dist[sel]).tolist()) == set(np.unique(dist).tolist())
     descs, brs, hashes = nbh.neighbour_trees(d, br, sel)
     np.testing.assert_allclose(lnl[sel], a.score_trees(m, descs, brs), rtol=1e-11)
-    for i in (0, 13, 39):
+    for i in range(len(sel)):
         want = oracle.lnl(codes, w, exch, freqs, alpha, descs[i], brs[i])
         assert abs(lnl[sel[i]] - want) <= 1e-8 * abs(want)   # north_star tolerance
     a2 = likelihood.LikAlignment(codes, 2.0 * w)
@@ -139,15 +148,15 @@ def test_c4_shape_two_trees_full_width():
 
 
 def test_c5_protein_tbr_neighbourhood():
-    """C5: synthetic protein 50 taxa x 5k sites, WAG-like 20-state model + G4, every TBR neighbour.
-    (The exchangeability table is random: kernel parity does not depend on it, and the shipped WAG
-    numbers are flagged unverified.)  Checks: a sample against the oracle, a sample against
-    re-traversal, SPR neighbours are found again inside the TBR neighbourhood."""
+    """C5: synthetic protein 50 taxa x 5k sites, the SHIPPED WAG table (likelihood.protein_model("WAG"),
+    what a "WAG, p1 = ..." partition file selects) + G4, every TBR neighbour.  Checks: a sample against
+    the oracle (given the same table), a sample against re-traversal, SPR neighbours are found again
+    inside the TBR neighbourhood; then a sample again under JTT."""
     from pylogeny_b200 import _lib, likelihood, neighbourhood as nbh
     rng = np.random.default_rng(1005)
     n, S = 50, 5000
     codes = rng.integers(0, 20, (n, S)).astype(np.uint8)
-    exch, f = rng.uniform(0.05, 5.0, 190), rng.dirichlet(np.ones(20) * 10)
+    exch, f = likelihood.protein_model("WAG")
     a = likelihood.LikAlignment(codes, np.ones(S), _lib.DATA_AA)
     m = likelihood.Model(exch, f, 0.9)
     d = random_desc(rng, n)
@@ -155,12 +164,20 @@ def test_c5_protein_tbr_neighbourhood():
     _, lnl = nbh.score_likelihood(a, m, d, br, move_type=nbh.MOVE_TBR)
     M = len(lnl)
     assert M == nbh.neighbourhood_size(d, nbh.MOVE_TBR) and M > 2 * (n - 3) * (2 * n - 7)
-    sel = np.linspace(0, M - 1, 6).astype(np.int64)
+    sel = np.linspace(0, M - 1, 12).astype(np.int64)
     descs, brs, hashes = nbh.neighbour_trees(d, br, sel, nbh.MOVE_TBR)
     np.testing.assert_allclose(a.score_trees(m, descs, brs), lnl[sel], rtol=1e-11)
-    for j in (0, 3, 5):
+    for j in range(0, 12, 2):
         want = oracle.lnl(codes, np.ones(S), exch, f, 0.9, descs[j], brs[j])
         assert abs(lnl[sel[j]] - want) <= 1e-8 * abs(want)
+    ej, fj = likelihood.protein_model("JTT")
+    mj = likelihood.Model(ej, fj, 0.9)
+    _, lj = nbh.score_likelihood(a, mj, d, br, move_type=nbh.MOVE_TBR, want_moves=False)
+    assert len(lj) == M and not np.allclose(lj[sel], lnl[sel], rtol=1e-6)
+    for j in (1, 6, 11):
+        want = oracle.lnl(codes, np.ones(S), ej, fj, 0.9, descs[j], brs[j])
+        assert abs(lj[sel[j]] - want) <= 1e-8 * abs(want)
+    mj.close()
     # SPR neighbours are TBR neighbours (same topology; branch lengths may differ when the first
     # TBR move that reaches a topology is not the SPR one, so only identity is compared)
     _, _, h_spr = nbh.neighbour_trees(d, br, np.arange(0, 2 * (n - 3) * (2 * n - 7), 97), nbh.MOVE_SPR)

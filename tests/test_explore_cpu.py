@@ -14,7 +14,10 @@ from conftest import load_golden
 pytestmark = pytest.mark.skipif(not refshim.available(), reason="needs /root/reference (build container)")
 
 
-def test_batched_explore_matches_reference_run(monkeypatch, al_greedy, al_fitch):
+@pytest.fixture
+def ref_world(monkeypatch):
+    """The reference's landscape / tree / heuristic modules (py3 shim) over the product's scoring,
+    parsimony and alignment modules, the device call answered by the CPU oracle."""
     from pylogeny_b200 import alignment, explore, fitch, neighbourhood as nbh, parsimony, scoring
     g = load_golden("al_alignment.json")
     ali = alignment.alignment(names=g["taxa"], seqs=g["seqs"])
@@ -42,16 +45,114 @@ def test_batched_explore_matches_reference_run(monkeypatch, al_greedy, al_fitch)
     stubs = {"scoring": scoring, "parsimony": parsimony, "alignment": alignment,
              "executable": types.ModuleType("executable")}
     stubs["executable"].raxml = None
+    mods = refshim.install(stubs, want=("base", "newick", "rearrangement", "tree", "landscape", "heuristic"))
+
+    class batchedLandscape(explore.BatchedExploreMixin, mods["landscape"].landscape):
+        pass
+
+    names = g["taxa"]
+    cat = names[-1]
+    for n in reversed(names[:-1]):
+        cat = "(%s,%s)" % (n, cat)
+    w = types.SimpleNamespace(mods=mods, ali=ali, names=names, start=cat + ";", batched=batchedLandscape,
+                              plain=mods["landscape"].landscape, taxa={n: i for i, n in enumerate(names)})
+    w.make = lambda cls, newick=None: cls(ali, starting_tree=mods["tree"].tree(newick or w.start), root=True, operator="SPR")
+    w.hash_of = lambda nw: nbh.topology_hash(*[nbh.newick_to_desc(nw, w.taxa)[k] for k in (0, 2)])
     try:
-        mods = refshim.install(stubs, want=("base", "newick", "rearrangement", "tree", "landscape", "heuristic"))
+        yield w
+    finally:
+        refshim.uninstall()
 
-        class batchedLandscape(explore.BatchedExploreMixin, mods["landscape"].landscape):
-            pass
 
-        names = g["taxa"]
-        cat = names[-1]
-        for n in reversed(names[:-1]):
-            cat = "(%s,%s)" % (n, cat)
+def _first_occurrences(seq):
+    out, seen = [], set()
+    for x in seq:
+        if x not in seen:
+            seen.add(x)
+            out.append(x)
+    return out
+
+
+@pytest.mark.parametrize("move", ["SPR", "NNI"])
+def test_locks_and_reference_order(ref_world, move):
+    """landscape.locks (rearrangement.py:228-240, landscape.py:714-718) through the batched explore: for
+    every branch of the starting tree locked in turn, and for two locks at once, the mixin reaches
+    exactly the topologies the UNCHANGED reference reaches, with the same scores, in the order of
+    their first occurrence in the reference's own enumeration (reference_order is implied by locks)."""
+    w = ref_world
+    typ = getattr(w.mods["rearrangement"], "TYPE_" + move)
+    n_br = len(w.make(w.plain).getTree(0).toTopology().getBranches())
+    cases = [()] + [(k,) for k in range(n_br)] + [(2, 9), (4, 12), (3, 5, 11)]
+    sizes = set()
+    for case in cases:
+        runs = []
+        for cls in (w.plain, w.batched):
+            ls = w.make(cls)
+            ls.reference_order = True   # (read by the mixin only)
+            for k in case:
+                br = ls.getTree(ls.root).toTopology().getBranches()[k]
+                assert ls.lockBranchFoundInTree(ls.root, br) is not None
+            nb = ls.exploreTree(ls.root, typ)
+            runs.append([(w.hash_of(ls.getTree(j).getNewick()), ls.getTree(j).score[1], ls.getTree(j).origin) for j in nb])
+        ref, got = runs
+        assert len(set(h for h, _, _ in got)) == len(got)              # one node per topology
+        assert _first_occurrences(ref) == got, case                    # same topologies, scores, origin, ORDER
+        sizes.add(len(got))
+    if move == "SPR":
+        assert len(sizes) > 3                                          # the locks did restrict the neighbourhoods
+    else:
+        # the reference's NNI producer lists no move at all (rearrangement.py:609-612: every candidate
+        # destination is in the branch's own forbidden list; tests/golden n_nni_reference = 0), so in
+        # reference_order / lock mode the mixin inserts none either; without them it scores the real
+        # 2(n-3) NNI neighbours (tests/test_dropin_gpu.py)
+        assert sizes == {0}
+
+
+def test_violating_tree_steps_only_to_non_violating_neighbours(ref_world):
+    """landscape.py:743-746: a tree that does not hold a locked bipartition has no branch to lock; its
+    neighbours that violate the lock as well are skipped."""
+    w = ref_world
+    runs = []
+    for cls in (w.plain, w.batched):
+        ls = w.make(cls)
+        ls.reference_order = True
+        other = w.mods["tree"].tree("((%s,%s),(%s,%s),(%s,(%s,(%s,%s))));" % tuple(w.names[k] for k in (0, 5, 2, 7, 1, 3, 4, 6)))
+        topl = other.toTopology()
+        mine = ls.getTree(ls.root).toTopology()
+        lock = [b for b in (w.mods["tree"].bipartition(topl, br) for br in topl.getBranches())
+                if not mine.getBranchFromBipartition(b)][0]       # a split of `other` the start tree lacks
+        ls.toggleLock(lock)
+        assert ls._isViolating(ls.getTree(ls.root).toTopology())
+        nb = ls.exploreTree(ls.root)
+        runs.append([(w.hash_of(ls.getTree(j).getNewick()), ls.getTree(j).score[1]) for j in nb])
+    assert _first_occurrences(runs[0]) == runs[1] and 0 < len(runs[1]) < 90
+
+
+def test_reference_order_greedy_path_is_the_reference_path(ref_world, al_greedy):
+    """With reference_order the greedy climb breaks ties as the reference does (heuristic.py:92-95
+    sorted(...)[0] over nodes in insertion order): the same TREE at every step of the path, not only
+    the same score, and every exploration inserts the distinct topologies in the reference's order."""
+    w = ref_world
+    paths = []
+    for cls in (w.plain, w.batched):
+        ls = w.make(cls)
+        ls.reference_order = True
+        h = w.mods["heuristic"].parsimonyGreedy(ls, ls.getNode(ls.root))
+        h.explore()
+        # (heuristic.py keeps the path in a list shared between instances: take this run's tail)
+        mine = [(w.hash_of(nd["tree"].getNewick()), nd["tree"].score[1]) for nd in h.getPath()]
+        paths.append(mine[-len(al_greedy["path_scores"]):])
+        order = [w.hash_of(ls.getTree(j).getNewick()) for j in sorted(ls.graph.nodes)]
+        paths.append(_first_occurrences(order))
+    assert paths[0] == paths[2] and [s for _, s in paths[2]] == al_greedy["path_scores"]
+    assert paths[1] == paths[3]                                        # whole landscape, node order
+
+
+def test_batched_explore_matches_reference_run(ref_world, monkeypatch, al_greedy, al_fitch):
+    from pylogeny_b200 import neighbourhood as nbh, scoring
+    w = ref_world
+    mods, ali, names, cat, batchedLandscape = w.mods, w.ali, w.names, w.start[:-1], w.batched
+    if True:
         ls = batchedLandscape(ali, starting_tree=mods["tree"].tree(cat + ";"), root=True, operator="SPR")
         nbrs = ls.exploreTree(ls.root)
         scores = sorted(ls.getTree(j).score[1] for j in nbrs)
@@ -86,5 +187,3 @@ def test_batched_explore_matches_reference_run(monkeypatch, al_greedy, al_fitch)
         assert 1 < len(ls2) <= al_greedy["n_trees"]                # no string-duplicates of one topology
         hashes = [ls2._b200_hash_of(ls2.getTree(j).getNewick(), ls2.parsimony_profiles.taxa) for j in ls2.graph.nodes]
         assert len(set(hashes)) == len(hashes)
-    finally:
-        refshim.uninstall()

@@ -110,6 +110,21 @@ def test_lnl_oracle_vs_bruteforce():
         assert abs(a - b) <= 1e-11 * abs(b)
 
 
+def test_lnl_oracle_normalises_frequencies():
+    """State frequencies are a distribution: a table that sums to 1 only within its printed digits
+    (PAML's wag.dat sums to 1 + 3e-6, which would shift lnL by P * log(sum)) scores like its normalised
+    form -- the convention the engine follows too (csrc/model.cpp), pinned on the GPU by
+    tests/test_configs_gpu.py::test_c5 on the shipped WAG table."""
+    rng = np.random.default_rng(12)
+    desc, br = _rand_tree_desc(rng, 5)
+    codes = rng.integers(0, 20, (5, 9)).astype(np.uint8)
+    exch, f = rng.uniform(0.2, 3.0, 190), rng.dirichlet(np.ones(20) * 4)
+    a = oracle.lnl(codes, np.ones(9), exch, f, 0.7, desc, br)
+    for scale in (1.0 + 3.2e-6, 0.5, 7.0):
+        assert abs(oracle.lnl(codes, np.ones(9), exch, f * scale, 0.7, desc, br) - a) <= 1e-13 * abs(a)
+        assert abs(oracle.lnl(codes, np.ones(9), exch, f * scale, 0.7, desc, br, brute=True) - a) <= 1e-11 * abs(a)
+
+
 def test_lnl_oracle_scaling_long_tree():
     """Deep caterpillar with long branches forces the 2^-256 rescaling path; compare with
     a log-space computation in extended precision via per-site renormalisation."""
