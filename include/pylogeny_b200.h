@@ -67,6 +67,12 @@ int plg_profile_read(int kind, double *ms, double *bytes, double *units, int64_t
  * kernels (bench.py); not in MEASURED_PEAKS.json. */
 int plg_fp64_peak(int mode, double *tflops);
 
+/* Diagnostics of the host worker pool the planners run on (no device needed): n slices, slice fail_at
+ * (if in [0, n)) raises the planners' error.  Returns PLG_ERR_ARG in that case, PLG_OK otherwise;
+ * *ran = slices that completed (n - 1 on failure: a failing slice never takes the process or the
+ * other slices down). */
+int plg_hostpool_selftest(int n, int fail_at, int *ran);
+
 /* ------------------------------------------------------------------ */
 /* Parsimony (replaces fitch.cpp)                                      */
 /* ------------------------------------------------------------------ */

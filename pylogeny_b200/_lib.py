@@ -88,6 +88,7 @@ def _declare(L):
     _set(L, 'plg_neighbourhood_size', 'argtypes', [C.c_int, C.c_int, vp, i64p])
     _set(L, 'plg_neighbourhood_trees', 'argtypes', [C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, vp])
     _set(L, 'plg_topology_hash', 'argtypes', [C.c_int, vp, vp, u64p])
+    _set(L, 'plg_hostpool_selftest', 'argtypes', [C.c_int, C.c_int, C.POINTER(C.c_int)])
     _set(L, 'plg_neighbourhood_all_moves', 'argtypes', [C.c_int, C.c_int, vp, C.POINTER(C.c_int64), vp])
     _set(L, 'plg_fitch_score_neighbourhood', 'argtypes', [vp, C.c_int, C.c_int, vp, vp, C.c_int64, C.c_int64, i64p, vp, vp, vp])
     _set(L, 'plg_lik_score_neighbourhood', 'argtypes',

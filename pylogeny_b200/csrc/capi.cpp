@@ -55,6 +55,28 @@ extern "C" int plg_set_device(int device) {
   PLG_API_END
 }
 
+// Host worker pool check: n slices, slice `fail_at` (if in range) fails the way planner code fails.
+// The failure must come back as a status (not std::terminate), after every other slice ran, and the
+// pool must serve the next call.
+#include "hostpool.h"
+extern "C" int plg_hostpool_selftest(int n, int fail_at, int *ran) {
+  PLG_API_BEGIN
+  if (!ran || n < 1) PLG_FAIL(PLG_ERR_ARG, "bad argument");
+  std::atomic<int> count{0};
+  *ran = 0;
+  try {
+    plg::HostPool::get().run(n, [&](int i, int) {
+      if (i == fail_at) PLG_FAIL(PLG_ERR_ARG, "slice %d failed on request", i);
+      count++;
+    });
+  } catch (...) {
+    *ran = count.load();
+    throw;
+  }
+  *ran = count.load();
+  PLG_API_END
+}
+
 // ---- host stage timer ------------------------------------------------------------------------
 #include <chrono>
 namespace plg {

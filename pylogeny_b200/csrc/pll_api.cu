@@ -344,16 +344,15 @@ struct PllProblem {
 };
 
 // ---------------------------------------------------------------------------------------------
-static void read_phylip(const char *path, std::vector<std::string> &names, std::vector<std::string> &seqs) {
-  std::ifstream in(path);
-  if (!in) PLG_FAIL(PLG_ERR_IO, "Alignment file could not be parsed.");
-  size_t n = 0, m = 0;
-  in >> n >> m;
-  if (!in || n == 0 || m == 0) PLG_FAIL(PLG_ERR_IO, "Alignment file could not be parsed.");
-  std::string line;
-  std::getline(in, line);
+// PHYLIP, relaxed names.  Interleaved (n first lines "name seq...", then blocks of n continuation
+// lines) is tried first -- it is what alignment.py writes (one line per taxon is its one-block case);
+// a file that does not come out at n x m that way is read as SEQUENTIAL (each taxon's sequence runs
+// over as many lines as it needs before the next name).
+static bool read_phylip_as(std::istream &in, size_t n, size_t m, bool sequential, std::vector<std::string> &names,
+                           std::vector<std::string> &seqs) {
   names.assign(n, "");
   seqs.assign(n, "");
+  std::string line;
   size_t row = 0;
   bool header_done = false;
   while (std::getline(in, line)) {
@@ -363,6 +362,13 @@ static void read_phylip(const char *path, std::vector<std::string> &names, std::
     while (ls >> tok) toks.push_back(tok);
     if (toks.empty()) continue;
     size_t from = 0;
+    if (sequential) {
+      if (row == n) break;
+      if (names[row].empty()) { names[row] = toks[0]; from = 1; }
+      for (size_t i = from; i < toks.size(); i++) seqs[row] += toks[i];
+      if (seqs[row].size() >= m) row++;
+      continue;
+    }
     if (!header_done) { names[row] = toks[0]; from = 1; }
     for (size_t i = from; i < toks.size(); i++) seqs[row] += toks[i];
     if (++row == n) { row = 0; header_done = true; }
@@ -371,7 +377,23 @@ static void read_phylip(const char *path, std::vector<std::string> &names, std::
     if (full) break;
   }
   for (auto &s : seqs)
-    if (s.size() != m) PLG_FAIL(PLG_ERR_IO, "Alignment file could not be parsed.");
+    if (s.size() != m) return false;
+  return true;
+}
+
+static void read_phylip(const char *path, std::vector<std::string> &names, std::vector<std::string> &seqs) {
+  std::ifstream in(path);
+  if (!in) PLG_FAIL(PLG_ERR_IO, "Alignment file could not be parsed.");
+  size_t n = 0, m = 0;
+  in >> n >> m;
+  if (!in || n == 0 || m == 0) PLG_FAIL(PLG_ERR_IO, "Alignment file could not be parsed.");
+  std::string line;
+  std::getline(in, line);
+  const std::streampos body = in.tellg();
+  if (read_phylip_as(in, n, m, false, names, seqs)) return;
+  in.clear();
+  in.seekg(body);
+  if (!read_phylip_as(in, n, m, true, names, seqs)) PLG_FAIL(PLG_ERR_IO, "Alignment file could not be parsed.");
 }
 
 // Partition file as pll.py:112-137 writes it: one line "<MODEL>, <name> = <from>-<to>" per partition.

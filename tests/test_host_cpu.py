@@ -193,3 +193,16 @@ def test_protein_tables():
         np.testing.assert_allclose(freqs[:, None] * Q, (freqs[:, None] * Q).T, atol=1e-15)  # reversible
     with pytest.raises(Exception):
         likelihood.protein_model("LG")
+
+
+def test_host_pool_survives_a_failing_slice():
+    """A planner slice that fails on a pool worker (or on the caller) comes back as the call's status
+    code after all other slices ran; the pool then serves the next call (csrc/hostpool.h)."""
+    import ctypes as C
+    from pylogeny_b200 import _lib
+    L = _lib.lib()
+    ran = C.c_int()
+    for n, fail_at in ((8, 5), (8, 0), (64, 63), (3, 1)):
+        assert L.plg_hostpool_selftest(n, fail_at, C.byref(ran)) == _lib.ERR_ARG
+        assert ran.value == n - 1 and b"failed on request" in L.plg_last_error()
+        assert L.plg_hostpool_selftest(n, -1, C.byref(ran)) == 0 and ran.value == n

@@ -100,6 +100,38 @@ def test_scoring_getLogLikelihood_dropin():
     ali.close()
 
 
+def test_phylip_forms(tmp_path):
+    """The alignment reader takes the three PHYLIP forms in use -- one line per taxon (what
+    alignment.py writes), interleaved blocks, sequential with sequences wrapped over several lines --
+    and scores them identically; a truncated file is an IOError as in the reference wrapper."""
+    from pylogeny_b200 import libpllWrapper as W, pll
+    ali, d = _case(n=9, S=230, seed=17)
+    labels, seqs = ali.getTaxa(), ali.toStrList()
+    nw = desc_to_newick(d, labels)
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    h = W.new(ali.getPhylip(), nw, pm.getFileName())
+    want = W.evaluate(h)
+    W.destroy(h)
+    head = "%d %d\n" % (len(labels), len(seqs[0]))
+    inter = head + "".join("%-12s%s\n" % (l, q[:70]) for l, q in zip(labels, seqs))
+    for off in range(70, 230, 70):
+        inter += "\n" + "".join(" ".join(q[off + k:off + k + 10] for k in range(0, min(70, 230 - off), 10)) + "\n" for q in seqs)
+    seq = head + "".join("%s\n%s" % (l, "".join(q[k:k + 60] + "\n" for k in range(0, 230, 60))) for l, q in zip(labels, seqs))
+    seq2 = head + "".join("%-10s %s\n%s" % (l, q[:50], "".join(q[k:k + 60] + "\n" for k in range(50, 230, 60))) for l, q in zip(labels, seqs))
+    for name, text in (("interleaved", inter), ("sequential", seq), ("sequential2", seq2)):
+        path = tmp_path / (name + ".phy")
+        path.write_text(text)
+        h = W.new(str(path), nw, pm.getFileName())
+        assert W.evaluate(h) == want, name
+        W.destroy(h)
+    bad = tmp_path / "short.phy"
+    bad.write_text(seq[:len(seq) // 2])
+    with pytest.raises(IOError):
+        W.new(str(bad), nw, pm.getFileName())
+    pm.close(); ali.close()
+
+
 def test_wag_model_is_usable():
     """The shipped WAG table builds a valid reversible model (provenance flagged unverified)."""
     from pylogeny_b200 import _lib, alignment, libpllWrapper as W, pll
