@@ -345,7 +345,9 @@ def workload_config(name, n_gpus, count=None):
         cfg["planner"] = ("edge insertion by depth-first search walks (directional CLVs of the base tree, then per neighbour 1 CLV "
                           "update + 1 three-way evaluation, partials kept on chip)" if wl["kind"] == "spr" and wl["datatype"] == "dna"
                           else ("whole post-order on chip (tree walks)" if wl["kind"] == "trees" else
-                                "edge insertion on level programs (20-state DMMA kernels)"))
+                                "TBR by part roots: base-tree vectors pushed through their branches once (T, H), one fused candidate step per "
+                                "reconnection edge (3 chained 20x20x4 products on the FP64 tensor pipe), pair terms of a bisection as a "
+                                "per-pattern 8x8-tiled DMMA product (csrc/lik_tbr20.cuh)"))
     return cfg
 
 
@@ -531,11 +533,14 @@ def roofline_for(name, L, prof, total_ms, hbm, hbm_src):
              "peak_source": "measured in this run: plg_fp64_peak mode 3 (LOP3 issue rate)",
              "traffic": ncu_traffic("fitch_search_walk_kernel", name)}
     elif wl["datatype"] == "aa":
-        kernel = {1: "clv20_kernel", 2: "eval20_rows_kernel"}.get(dom, kinds[dom])
+        kernel = {1: "tbr20_step_kernel (+ clv20_kernel for the base tree's directional vectors)" if wl["kind"] == "tbr" else "clv20_kernel",
+                  2: "pairs20_kernel" if wl["kind"] == "tbr" else "eval20_rows_kernel"}.get(dom, kinds[dom])
         peak = pipe_peak(L, 1)
         ach = p["units"] * FLOP_PER_NODEOP_AA / sec / 1e12
         r = {"kernel": kernel, "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-             "flop_per_unit": FLOP_PER_NODEOP_AA, "unit_definition": "node-op x pattern (20 states x 4 categories)",
+             "flop_per_unit": FLOP_PER_NODEOP_AA,
+             "unit_definition": "two 20x20 matrix-vector products x 4 categories + their elementwise join, per pattern (what one CLV "
+                                "update costs: SURVEY.md 8d); the fused candidate steps are counted by the products they execute",
              "peak_source": "measured in this run: plg_fp64_peak, DMMA m8n8k4 issue rate", "traffic": ncu_traffic(kernel, name)}
     else:
         r = {"kernel": kinds[dom], "bound": "hbm", "achieved": alg_gbs, "peak": hbm, "unit": "GB/s", "frac": alg_gbs / hbm,

@@ -223,6 +223,7 @@ namespace plg {
 constexpr int DNA4_PATTERNS_PER_BLOCK = D4_THREADS;
 }
 #include "lik_aa.cuh"
+#include "lik_tbr20.cuh"
 #include "lik_walkm.cuh"
 #include "lik_twalk.cuh"
 namespace plg {
@@ -306,6 +307,12 @@ void LikProgram::clear() {
   spr_lo = spr_hi = 0;
   ops.clear();
   level_off.clear();
+  t20_ops.clear();
+  t20_level_off.clear();
+  t20_tiles.clear();
+  t20_tile_off.clear();
+  t20_pair_slots = 0;
+  t20_products = t20_bytes = t20_pair_bytes = 0;
   evals.clear();
   brlens.clear();
   pm_index.clear();
@@ -836,6 +843,38 @@ static void run_aa20(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, (double)c * (double)a.P);
     }
   }
+  if (!prog.t20_ops.empty()) {  // TBR neighbourhood: fused candidate steps, then the pair grid (lik_tbr20.cuh)
+    for (size_t l = 0; l + 1 < prog.t20_level_off.size(); l++) {
+      const int64_t o0 = prog.t20_level_off[l], cnt = prog.t20_level_off[l + 1] - o0;
+      if (!cnt) continue;
+      const double share = (double)cnt / (double)prog.t20_ops.size();  // (per-level split of the program totals)
+      static bool t20_attr_set[64] = {false};
+      ensure_dyn_smem(tbr20_step_kernel, T20_DYN_SMEM, t20_attr_set);
+      prof_begin(PROF_CLV_UPDATE, st);
+      tbr20_step_kernel<<<(unsigned)(cnt * bpo), A20_THREADS, T20_DYN_SMEM, st>>>(ws.t20_ops.p + o0, (int)cnt, a.n_rows, a.Ppad,
+                                                                      a.codes.p, a.masks.p, m.d.p, ws.pmat.p, ws.clv.p,
+                                                                      ws.scl.p, ws.pairvec.p, ws.pair_scl.p);
+      count_launch();
+      // units: node-ops of 2 products each (what FLOP_PER_NODEOP_AA counts)
+      prof_end(PROF_CLV_UPDATE, st, share * prog.t20_bytes * (double)a.P, share * 0.5 * prog.t20_products * (double)a.P);
+    }
+    const int n_edges = (int)prog.t20_tile_off.size() - 1, n_chunks = (int)(a.Ppad / P20_CHUNK);
+    const int64_t n_items = (int64_t)prog.t20_tiles.size() * n_chunks;
+    if (n_items) {
+      prof_begin(PROF_ROOT_EVAL, st);
+      pairs20_kernel<<<(unsigned)((n_items + 3) / 4), 128, 0, st>>>(ws.t20_tiles.p, ws.t20_tile_off.p, n_edges, n_chunks,
+                                                                   n_items, a.Ppad, a.weights.p, ws.pairvec.p,
+                                                                   ws.pair_scl.p, ws.partial.p);
+      count_launch();
+      prof_end(PROF_ROOT_EVAL, st, prog.t20_pair_bytes * (double)a.P, (double)prog.n_trees * (double)a.P);
+    }
+    if (prog.n_trees) {
+      reduce_partials_kernel<<<(unsigned)((prog.n_trees + 7) / 8), 256, 0, st>>>((int)prog.n_trees, n_chunks,
+                                                                                 ws.partial.p, ws.lnl.p);
+      count_launch();
+    }
+    return;
+  }
   int64_t n_ev = (int64_t)prog.evals.size();
   // evaluations without matrices whose first operand repeats (TBR pairs): one block keeps that
   // operand's tile in registers for the whole row (PLG_AA_EVAL_ROWS=0: the per-evaluation kernel)
@@ -901,8 +940,23 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   const int64_t bpo = !dna4 ? a.Ppad / (LIK_THREADS / m.R)
                              : (prog.walk_visits.empty() && prog.spr_n_visits == 0 ? dna4_partial_stride(a)
                                                                                     : a.Ppad / WM_PATTERNS);  // walk slicing
-  ws.partial.alloc(std::max<size_t>(1, (size_t)prog.n_trees * (size_t)bpo));
+  const bool t20 = !prog.t20_ops.empty();
+  ws.partial.alloc(std::max<size_t>(1, (size_t)prog.n_trees * (size_t)(t20 ? a.Ppad / P20_CHUNK : bpo)));
   ws.lnl.alloc(std::max<size_t>(1, (size_t)prog.n_trees));
+  if (t20) {
+    if (!(a.K == 20 && m.R == 4)) PLG_FAIL(PLG_ERR_ARG, "internal: TBR-20 program on a %d-state, %d-category model", a.K, m.R);
+    ws.pairvec.alloc(std::max<size_t>(1, (size_t)prog.t20_pair_slots * 80 * a.Ppad));
+    ws.pair_scl.alloc(std::max<size_t>(1, (size_t)prog.t20_pair_slots * a.Ppad));
+    ws.t20_ops.alloc(prog.t20_ops.size());
+    ws.t20_tiles.alloc(std::max<size_t>(1, prog.t20_tiles.size()));
+    ws.t20_tile_off.alloc(prog.t20_tile_off.size());
+    PLG_CUDA(cudaMemcpyAsync(ws.t20_ops.p, prog.t20_ops.data(), prog.t20_ops.size() * sizeof(Tbr20Op), cudaMemcpyHostToDevice, st));
+    if (!prog.t20_tiles.empty())
+      PLG_CUDA(cudaMemcpyAsync(ws.t20_tiles.p, prog.t20_tiles.data(), prog.t20_tiles.size() * sizeof(Tbr20Tile),
+                               cudaMemcpyHostToDevice, st));
+    PLG_CUDA(cudaMemcpyAsync(ws.t20_tile_off.p, prog.t20_tile_off.data(), prog.t20_tile_off.size() * sizeof(int),
+                             cudaMemcpyHostToDevice, st));
+  }
   if (!dna4 && !prog.ops.empty())
     PLG_CUDA(cudaMemcpyAsync(ws.ops.p, prog.ops.data(), prog.ops.size() * sizeof(LikOp), cudaMemcpyHostToDevice, st));
   if (!dna4 && !prog.evals.empty())

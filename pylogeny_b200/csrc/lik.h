@@ -52,6 +52,20 @@ struct LikSprSearch {
   int p_in, tv, pad0, pad1;              // P-matrix of the merged branch other--start; operand id of the pruned subtree
 };
 
+// 20 states x Gamma-4 TBR neighbourhoods (csrc/lik_tbr20.cuh)
+struct Tbr20Op {
+  int a, pa;   // stage 1: X = P[pa] * operand a (standard layout or tip row) ...
+  int b;       // ... o raw vector b (standard layout, already through its branch); -1: none
+  int dst;     // >= 0: X is stored in the standard layout under this operand id (children read it)
+  int p2, b2;  // p2 >= 0: stage 2: Y = (P[p2] * X) o raw b2 (b2 < 0: no join)
+  int p3;      // p3 >= 0: stage 3: Z = P[p3] * Y
+  int pdst;    // >= 0: pair-layout slot of the last stage's result; bit 30 set: times pi
+};
+struct Tbr20Tile {
+  int a[8], b[8];  // pair slots of the tile's rows (stay side) and columns (pushed side)
+  int tree[64];    // [row * 8 + col] -> tree id of the pair, -1: no such neighbour
+};
+
 struct LikWorkspace {
   DevBuf<double> clv;      // [slot][R*K][Ppad]
   DevBuf<int> scl;         // [slot][Ppad] per-pattern 2^-256 scaling counters
@@ -69,6 +83,11 @@ struct LikWorkspace {
   DevBuf<int4> spr_edges, spr_searches, spr_moves;  // device-planned SPR neighbourhoods
   DevBuf<double> spr_acct;                          // byte accounting of the planned walk (profiling)
   DevBuf<int4> eval_rows;                           // LikEvalRow[] (lik_aa.cuh eval20_rows_kernel)
+  DevBuf<double> pairvec;      // [pair slot][Ppad][80]: TBR candidates in the pair grid's layout (lik_tbr20.cuh)
+  DevBuf<int> pair_scl;        // [pair slot][Ppad]
+  DevBuf<Tbr20Op> t20_ops;
+  DevBuf<Tbr20Tile> t20_tiles;
+  DevBuf<int> t20_tile_off;
   DevBuf<int32_t> tw_desc;     // tree walks (treewalk.h): raw descriptors, planned ops, planner scratch
   DevBuf<int4> tw_ops;
   DevBuf<int> tw_scratch;
@@ -94,6 +113,13 @@ struct LikAln {
 struct LikProgram {
   std::vector<LikOp> ops;          // sorted by level
   std::vector<int64_t> level_off;  // [n_levels+1]
+  // fused TBR candidate steps (run after the op levels) and the pair grid that replaces `evals`
+  std::vector<Tbr20Op> t20_ops;           // sorted by level
+  std::vector<int64_t> t20_level_off;
+  std::vector<Tbr20Tile> t20_tiles;       // grouped by bisected branch
+  std::vector<int> t20_tile_off;          // [n_edges + 1]
+  int64_t t20_pair_slots = 0;
+  double t20_products = 0, t20_bytes = 0, t20_pair_bytes = 0;  // per pattern: 20x20x4 products, vector bytes moved
   std::vector<LikEval> evals;
   std::vector<LikWalkVisit> walk_visits;  // depth-first search walks, run after the op levels
   std::vector<LikWalkGroup> walk_groups;  // longest first

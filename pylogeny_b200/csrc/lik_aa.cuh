@@ -23,7 +23,7 @@ constexpr int A20_TILE = 64;     // patterns per block
 constexpr int A20_THREADS = 128;  // 4 warps = 4 rate categories
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
 }
@@ -97,12 +97,33 @@ __device__ __forceinline__ void a20_raw(int id, int n_rows, int r, int64_t p0, i
   }
 }
 
+// Largest high word among this lane group's entries of each of its two patterns (values are >= 0, so the
+// high words order like the doubles: integer max and 32-bit shuffles instead of FP64 compares)
+__device__ __forceinline__ void a20_colmax(const double (&c)[3][2], int g, int &m0, int &m1) {
+  m0 = max(__double2hiint(c[0][0]), __double2hiint(c[1][0]));
+  m1 = max(__double2hiint(c[0][1]), __double2hiint(c[1][1]));
+  if (g < 4) {
+    m0 = max(m0, __double2hiint(c[2][0]));
+    m1 = max(m1, __double2hiint(c[2][1]));
+  }
+#pragma unroll
+  for (int d = 4; d < 32; d <<= 1) {
+    m0 = max(m0, __shfl_xor_sync(0xffffffffu, m0, d));
+    m1 = max(m1, __shfl_xor_sync(0xffffffffu, m1, d));
+  }
+}
+constexpr int A20_HI_MINLH = 0x2FF00000;  // high word of 2^-256
+
+// The four categories of a pattern are rescaled together (all 80 entries below 2^-256: libpll's rule), so
+// the four warps exchange their column maxima per 8-pattern tile and store the tile already scaled.
+// (Round 1 stored first and repaired afterwards: on data where most patterns need a factor at the deeper
+// nodes -- 50 random protein sequences sit at 2^-300 per site -- the repair pass re-read and re-wrote
+// most of what the kernel had just written and took a third of its time, ncu profiles/r2n_*.)
 __global__ void __launch_bounds__(A20_THREADS)
 clv20_kernel(const LikOp *__restrict__ ops, int blocks_per_op, int n_rows, int64_t Ppad,
              const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
              const double *__restrict__ pmat, double *__restrict__ clv, int *__restrict__ scl) {
-  __shared__ double smax[4][A20_TILE];
-  __shared__ int srescale[A20_TILE];
+  __shared__ int smax[2][4][8];  // [tile parity][category][pattern of the tile]
   const int op_idx = blockIdx.x / blocks_per_op;
   const int pb = blockIdx.x - op_idx * blocks_per_op;
   const LikOp op = ops[op_idx];
@@ -112,9 +133,17 @@ clv20_kernel(const LikOp *__restrict__ ops, int blocks_per_op, int n_rows, int64
   a20_load_p(pmat, op.pa, r, lane, pa);
   if (op.b >= 0) a20_load_p(pmat, op.pb, r, lane, pbm);
   double *dst = clv + ((int64_t)(op.dst - n_rows) * 80 + r * 20) * Ppad;
+  const bool booker = r == 0 && g == 0;  // lane t books the counters of patterns 2t, 2t + 1 of every tile
+  const int *sa = op.a >= n_rows ? scl + (int64_t)(op.a - n_rows) * Ppad : nullptr;
+  const int *sb = op.b >= n_rows ? scl + (int64_t)(op.b - n_rows) * Ppad : nullptr;
 #pragma unroll(A20_UNROLL)
   for (int nt = 0; nt < A20_TILE / 8; nt++) {
     const int64_t p0 = pbase + nt * 8;
+    int2 ca_ = make_int2(0, 0), cb_ = ca_;
+    if (booker) {
+      if (sa) ca_ = *reinterpret_cast<const int2 *>(sa + p0 + 2 * t);
+      if (sb) cb_ = *reinterpret_cast<const int2 *>(sb + p0 + 2 * t);
+    }
     double ca[3][2], cb[3][2];
     a20_apply(pa, op.a, n_rows, r, p0, lane, Ppad, codes, masks, clv, ca);
     if (op.b >= 0) {
@@ -122,52 +151,22 @@ clv20_kernel(const LikOp *__restrict__ ops, int blocks_per_op, int n_rows, int64
 #pragma unroll
       for (int mt = 0; mt < 3; mt++) { ca[mt][0] *= cb[mt][0]; ca[mt][1] *= cb[mt][1]; }
     }
-    double m0 = 0.0, m1 = 0.0;
+    int m0, m1;
+    a20_colmax(ca, g, m0, m1);
+    int(*mx)[8] = smax[nt & 1];
+    if (g == 0) *reinterpret_cast<int2 *>(&mx[r][2 * t]) = make_int2(m0, m1);
+    __syncthreads();
+    const int r0 = max(max(mx[0][2 * t], mx[1][2 * t]), max(mx[2][2 * t], mx[3][2 * t])) < A20_HI_MINLH ? 1 : 0;
+    const int r1 = max(max(mx[0][2 * t + 1], mx[1][2 * t + 1]), max(mx[2][2 * t + 1], mx[3][2 * t + 1])) < A20_HI_MINLH ? 1 : 0;
+    const double f0 = r0 ? TWO256 : 1.0, f1 = r1 ? TWO256 : 1.0;
 #pragma unroll
     for (int mt = 0; mt < 3; mt++) {
       const int row = mt * 8 + g;
-      if (row < 20) {
-        *reinterpret_cast<double2 *>(dst + (int64_t)row * Ppad + p0 + 2 * t) = make_double2(ca[mt][0], ca[mt][1]);
-        m0 = fmax(m0, fabs(ca[mt][0]));
-        m1 = fmax(m1, fabs(ca[mt][1]));
-      }
+      if (row < 20)
+        *reinterpret_cast<double2 *>(dst + (int64_t)row * Ppad + p0 + 2 * t) = make_double2(ca[mt][0] * f0, ca[mt][1] * f1);
     }
-#pragma unroll
-    for (int d = 4; d < 32; d <<= 1) {
-      m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, d));
-      m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, d));
-    }
-    if (g == 0) { smax[r][nt * 8 + 2 * t] = m0; smax[r][nt * 8 + 2 * t + 1] = m1; }
-  }
-  __syncthreads();
-  int any = 0;
-  if (threadIdx.x < A20_TILE) {
-    const int q = threadIdx.x;
-    const double mx = fmax(fmax(smax[0][q], smax[1][q]), fmax(smax[2][q], smax[3][q]));
-    const int res = mx < MINLH ? 1 : 0;  // every one of the 80 entries below 2^-256
-    srescale[q] = res;
-    any = res;
-    int sc = res;
-    if (op.a >= n_rows) sc += scl[(int64_t)(op.a - n_rows) * Ppad + pbase + q];
-    if (op.b >= n_rows) sc += scl[(int64_t)(op.b - n_rows) * Ppad + pbase + q];
-    scl[(int64_t)(op.dst - n_rows) * Ppad + pbase + q] = sc;
-  }
-  if (__syncthreads_or(any)) {  // rare: multiply the columns just written by 2^256 (each thread its own stores)
-    for (int nt = 0; nt < A20_TILE / 8; nt++) {
-      const int q = nt * 8 + 2 * t;
-      if (!srescale[q] && !srescale[q + 1]) continue;
-#pragma unroll
-      for (int mt = 0; mt < 3; mt++) {
-        const int row = mt * 8 + g;
-        if (row < 20) {
-          double2 *ptr = reinterpret_cast<double2 *>(dst + (int64_t)row * Ppad + pbase + q);
-          double2 v = *ptr;
-          if (srescale[q]) v.x *= TWO256;
-          if (srescale[q + 1]) v.y *= TWO256;
-          *ptr = v;
-        }
-      }
-    }
+    if (booker)
+      *reinterpret_cast<int2 *>(scl + (int64_t)(op.dst - n_rows) * Ppad + p0 + 2 * t) = make_int2(ca_.x + cb_.x + r0, ca_.y + cb_.y + r1);
   }
 }
 

@@ -69,13 +69,14 @@ void fill_tbr_moves(const TbrNeighbourhood &tb, int32_t *out_moves) {
 
 // edges [e0, e1) whose pairs intersect [lo, hi), cut into chunks that fit `max_slots`
 template <typename Run>
-void for_tbr_chunks(const TbrNeighbourhood &tb, int64_t lo, int64_t hi, int64_t max_slots, Run run) {
+void for_tbr_chunks(const TbrNeighbourhood &tb, int64_t lo, int64_t hi, int64_t max_slots, bool t20, Run run) {
   const int n_edges = (int)tb.edges.size();
   int e = 0;
   while (e < n_edges && tb.edge_pair_off[e + 1] <= lo) e++;
   while (e < n_edges && tb.edge_pair_off[e] < hi) {
     int e1 = e + 1;
-    while (e1 < n_edges && tb.edge_pair_off[e1] < hi && tbr_slots_needed(tb, e, e1 + 1) <= max_slots) e1++;
+    while (e1 < n_edges && tb.edge_pair_off[e1] < hi &&
+           (t20 ? tbr20_slots_needed(tb, e, e1 + 1) : tbr_slots_needed(tb, e, e1 + 1)) <= max_slots) e1++;
     run(e, e1);
     e = e1;
   }
@@ -97,7 +98,7 @@ int score_tbr_fitch(FitchAln &a, int n_tips, const int32_t *desc, const int32_t 
   const int64_t max_slots = std::max<int64_t>(8 * n_tips, (int64_t)(budget / vec_bytes));
   FitchTbrProgram p;
   std::vector<int32_t> acc, costs;
-  for_tbr_chunks(tb, lo, hi, max_slots, [&](int e0, int e1) {
+  for_tbr_chunks(tb, lo, hi, max_slots, false, [&](int e0, int e1) {
     build_fitch_tbr_program(tb, tip_rows, a.n_cols, e0, e1, p);
     acc.resize(p.prog.n_costs);
     run_fitch_program(a, fitch_workspace(), p.prog, acc.data(), st);
@@ -127,8 +128,13 @@ int score_tbr_lik(LikAln &a, const Model &m, int n_tips, const int32_t *desc, co
   const int64_t max_slots = std::max<int64_t>(8 * n_tips, (int64_t)(budget / slot_bytes));
   LikProgram p;
   std::vector<double> lnl;
-  for_tbr_chunks(tb, lo, hi, max_slots, [&](int e0, int e1) {
-    build_lik_tbr_program(tb, tip_rows, a.n_rows, e0, e1, p);
+  // 20 states x Gamma-4: fused candidate steps + pair grid on the FP64 tensor pipe (lik_tbr20.cuh);
+  // PLG_TBR20=0 keeps the level program of plain updates and row evaluations (A/B reference)
+  const char *t20_env = std::getenv("PLG_TBR20");
+  const bool t20 = a.K == 20 && m.R == 4 && !(t20_env && !strcmp(t20_env, "0"));
+  for_tbr_chunks(tb, lo, hi, max_slots, t20, [&](int e0, int e1) {
+    if (t20) build_lik_tbr20_program(tb, tip_rows, a.n_rows, e0, e1, p);
+    else build_lik_tbr_program(tb, tip_rows, a.n_rows, e0, e1, p);
     const int64_t p0 = tb.edge_pair_off[e0], p1 = tb.edge_pair_off[e1];
     lnl.resize(p1 - p0);
     run_lik_program(a, m, lik_workspace(), p, lnl.data(), st);

@@ -1328,8 +1328,35 @@ TbrNeighbourhood enumerate_tbr(const UTree &t) {
       }
     }
   };
-  std::unordered_map<uint64_t, int> seen;
-  seen.emplace(base, -1);
+  // distinct topologies: open-addressing set of the 64-bit hashes (about n^2 / 2 candidate pairs per
+  // internal branch are tried; node-based containers made this loop the step's largest host cost)
+  size_t cap = 1024;
+  while (cap < (size_t)16 * t.n_tips * t.n_tips * (size_t)std::max(1, t.n_tips / 8)) cap <<= 1;
+  cap = std::min<size_t>(cap, (size_t)1 << 28);
+  std::vector<uint64_t> table(cap, 0);
+  size_t filled = 0;
+  auto insert = [&](uint64_t h) {  // true if new
+    if (h == 0) h = 0x9E3779B97F4A7C15ull;  // 0 marks an empty cell
+    if (2 * (filled + 1) > table.size()) {
+      std::vector<uint64_t> old(table.size() * 2, 0);
+      old.swap(table);
+      for (uint64_t x : old)
+        if (x) {
+          size_t i = (size_t)(x * 0x9E3779B97F4A7C15ull >> 20) & (table.size() - 1);
+          while (table[i]) i = (i + 1) & (table.size() - 1);
+          table[i] = x;
+        }
+    }
+    size_t i = (size_t)(h * 0x9E3779B97F4A7C15ull >> 20) & (table.size() - 1);
+    while (table[i]) {
+      if (table[i] == h) return false;
+      i = (i + 1) & (table.size() - 1);
+    }
+    table[i] = h;
+    filled++;
+    return true;
+  };
+  insert(base);
   for (int u = 0; u < t.n_nodes; u++)
     for (int k = 0; k < 3; k++) {
       const int v = t.nb[u][k];
@@ -1343,7 +1370,7 @@ TbrNeighbourhood enumerate_tbr(const UTree &t) {
       for (int64_t c1 = nb.edge_cand_off[2 * ne]; c1 < nb.edge_cand_off[2 * ne + 1]; c1++)
         for (int64_t c2 = nb.edge_cand_off[2 * ne + 1]; c2 < nb.edge_cand_off[2 * ne + 2]; c2++) {
           const uint64_t hh = base + nb.cands[c1].delta + nb.cands[c2].delta;
-          if (!seen.emplace(hh, 0).second) continue;
+          if (!insert(hh)) continue;
           nb.pairs.push_back({(int)c1, (int)c2, hh});
         }
       nb.edge_pair_off.push_back((int64_t)nb.pairs.size());
@@ -1635,6 +1662,175 @@ void build_lik_tbr_program(const TbrNeighbourhood &nb, const int32_t *tip_rows, 
   prog.ops.resize(tmp.size());
   for (auto &o : tmp) prog.ops[cur[o.level]++] = o.op;
   prog.n_slots = slots;
+  prog.n_trees = nb.edge_pair_off[e1] - p_lo;
+}
+
+int64_t tbr20_slots_needed(const TbrNeighbourhood &nb, int e0, int e1) {
+  // standard layout: D, T, H per directed edge + N per candidate; pair layout: one vector per candidate
+  return 9 * (int64_t)nb.t.n_nodes + 2 * (nb.edge_cand_off[2 * e1] - nb.edge_cand_off[2 * e0]);
+}
+
+void build_lik_tbr20_program(const TbrNeighbourhood &nb, const int32_t *tip_rows, int n_rows, int e0, int e1,
+                             LikProgram &prog) {
+  const UTree &t = nb.t;
+  prog.clear();
+  DirOrder d = dir_order(t);
+  std::vector<int> dir_slot((size_t)t.n_nodes * 3, -1);
+  for (int x = 0; x < t.n_tips; x++)
+    for (int k = 0; k < 3; k++) dir_slot[3 * x + k] = tip_rows ? tip_rows[x] : x;
+  int64_t slots = 0;
+  {  // base tree: directional vectors, level ops as in build_lik_tbr_program
+    struct Tmp { LikOp op; int level; };
+    std::vector<Tmp> tmp;
+    for (int e : d.order) {
+      const int x = e / 3, k = e % 3;
+      Tmp o;
+      o.op.dst = n_rows + (int)slots++;
+      int s = 0;
+      for (int j = 0; j < 3; j++)
+        if (j != k) {
+          const int c = t.nb[x][j];
+          const int id = dir_slot[3 * c + t.slot_of(c, x)];
+          const int pm = prog.pm(t.len[x][j]);
+          if (s == 0) { o.op.a = id; o.op.pa = pm; } else { o.op.b = id; o.op.pb = pm; }
+          s++;
+        }
+      o.level = d.level[e];
+      dir_slot[e] = o.op.dst;
+      tmp.push_back(o);
+    }
+    int max_level = 0;
+    for (auto &o : tmp) max_level = std::max(max_level, o.level);
+    prog.level_off.assign(max_level + 2, 0);
+    for (auto &o : tmp) prog.level_off[o.level + 1]++;
+    for (int l = 0; l <= max_level; l++) prog.level_off[l + 1] += prog.level_off[l];
+    std::vector<int64_t> cur(prog.level_off.begin(), prog.level_off.end() - 1);
+    prog.ops.resize(tmp.size());
+    for (auto &o : tmp) prog.ops[cur[o.level]++] = o.op;
+  }
+  struct TOp { Tbr20Op op; int level; };
+  std::vector<TOp> ops;
+  const double Cb = 4 * 20 * 8.0 + 4.0;
+  auto opnd = [&](int id) { return id < 0 ? 0.0 : (id < n_rows ? 1.0 : Cb); };
+  auto emit = [&](const Tbr20Op &o, int level) {
+    ops.push_back({o, level});
+    prog.t20_products += 1.0 + (o.p2 >= 0) + (o.p3 >= 0);
+    prog.t20_bytes += opnd(o.a) + opnd(o.b) + opnd(o.b2) + (o.dst >= 0 ? Cb : 0.0) + (o.pdst >= 0 ? Cb : 0.0);
+  };
+  // T[y -> x] = P(len) D[y -> x], H[y -> x] = P(len / 2) D[y -> x], indexed like dir_slot (3 * y + slot of x),
+  // made on first use
+  std::vector<int> t_slot((size_t)t.n_nodes * 3, -1), h_slot((size_t)t.n_nodes * 3, -1);
+  auto pushed = [&](std::vector<int> &tab, int y, int x, double len) {
+    int &s = tab[3 * y + t.slot_of(y, x)];
+    if (s < 0) {
+      s = n_rows + (int)slots++;
+      emit({dir_slot[3 * y + t.slot_of(y, x)], prog.pm(len), -1, s, -1, -1, -1, -1}, 0);
+    }
+    return s;
+  };
+  const int64_t c_lo = nb.edge_cand_off[2 * e0], c_hi = nb.edge_cand_off[2 * e1];
+  const int64_t p_lo = nb.edge_pair_off[e0];
+  // which candidates carry a pair, which side of every bisection is pushed through the reconnecting branch
+  std::vector<char> used(c_hi - c_lo, 0), has_child(c_hi - c_lo, 0);
+  for (int64_t pi = p_lo; pi < nb.edge_pair_off[e1]; pi++) {
+    used[nb.pairs[pi].c1 - c_lo] = 1;
+    used[nb.pairs[pi].c2 - c_lo] = 1;
+  }
+  for (int64_t ci = c_lo; ci < c_hi; ci++)
+    if (nb.cands[ci].parent >= 0) has_child[nb.cands[ci].parent - c_lo] = 1;
+  std::vector<int> n_slot(c_hi - c_lo, -1), pair_slot(c_hi - c_lo, -1);
+  int64_t pslots = 0;
+  for (int e = e0; e < e1; e++) {
+    const int u = nb.edges[e][0], k = nb.edges[e][1];
+    const int pmv = prog.pm(t.len[u][k]);  // the reconnecting branch keeps the removed branch's length
+    const int64_t s0 = nb.edge_cand_off[2 * e], s1 = nb.edge_cand_off[2 * e + 1], s2 = nb.edge_cand_off[2 * e + 2];
+    const bool push_second = s2 - s1 <= s1 - s0;  // the side with fewer candidates takes the extra product
+    for (int64_t ci = s0; ci < s2; ci++) {
+      const TbrCand &c = nb.cands[ci];
+      const bool push = (ci >= s1) == push_second;
+      const bool want_pair = used[ci - c_lo];
+      int pdst = -1;
+      if (want_pair) {
+        pair_slot[ci - c_lo] = (int)pslots++;
+        pdst = pair_slot[ci - c_lo] | (push ? 0 : (1 << 30));  // the stay side carries pi
+      }
+      if (c.x < 0) {  // original attachment: the part as it hangs on the cut branch
+        if (want_pair) emit({dir_slot[3 * c.u + c.k], push ? pmv : prog.pm(0.0), -1, -1, -1, -1, -1, pdst}, 0);
+        continue;
+      }
+      const int x = c.x, y = t.nb[x][c.kx];
+      int from, xin;
+      double lin;
+      if (c.parent < 0) {
+        const int ko = (c.k + 1 + (1 - c.side)) % 3, ks = (c.k + 1 + c.side) % 3;
+        const int other = t.nb[c.u][ko];
+        from = c.u;
+        xin = dir_slot[3 * other + t.slot_of(other, c.u)];
+        lin = t.len[c.u][ko] + t.len[c.u][ks];
+      } else {
+        const TbrCand &pc = nb.cands[c.parent];
+        from = pc.x;
+        xin = n_slot[c.parent - c_lo];
+        lin = t.len[pc.x][pc.kx];
+      }
+      int s = -1, ks2 = -1;
+      for (int j = 0; j < 3; j++)
+        if (t.nb[x][j] != from && t.nb[x][j] != y) { s = t.nb[x][j]; ks2 = j; }
+      if (!want_pair && !has_child[ci - c_lo]) continue;
+      Tbr20Op o;
+      o.a = xin; o.pa = prog.pm(lin);
+      o.b = pushed(t_slot, s, x, t.len[x][ks2]);
+      o.dst = has_child[ci - c_lo] ? (n_slot[ci - c_lo] = n_rows + (int)slots++) : -1;
+      o.p2 = o.b2 = o.p3 = -1;
+      o.pdst = pdst;
+      if (want_pair) {
+        const double half = t.len[x][c.kx] / 2.0;
+        o.p2 = prog.pm(half);
+        o.b2 = pushed(h_slot, y, x, half);
+        o.p3 = push ? pmv : -1;
+      }
+      emit(o, c.depth);
+    }
+    // pair grid of this bisection: rows = stay side, columns = pushed side
+    std::vector<int64_t> rows, cols;
+    for (int64_t ci = s0; ci < s2; ci++)
+      if (used[ci - c_lo]) ((ci >= s1) == push_second ? cols : rows).push_back(ci);
+    std::vector<int> pos(s2 - s0, -1);
+    for (size_t i = 0; i < rows.size(); i++) pos[rows[i] - s0] = (int)i;
+    for (size_t i = 0; i < cols.size(); i++) pos[cols[i] - s0] = (int)i;
+    const int ntr = (int)(rows.size() + 7) / 8, ntc = (int)(cols.size() + 7) / 8;
+    const size_t tile0 = prog.t20_tiles.size();
+    prog.t20_tile_off.push_back((int)tile0);
+    prog.t20_tiles.resize(tile0 + (size_t)ntr * ntc);
+    for (int tr = 0; tr < ntr; tr++)
+      for (int tc = 0; tc < ntc; tc++) {
+        Tbr20Tile &T = prog.t20_tiles[tile0 + (size_t)tr * ntc + tc];
+        for (int i = 0; i < 8; i++) {
+          const size_t ri = std::min(rows.size() - 1, (size_t)tr * 8 + i), cj = std::min(cols.size() - 1, (size_t)tc * 8 + i);
+          T.a[i] = pair_slot[rows[ri] - c_lo];
+          T.b[i] = pair_slot[cols[cj] - c_lo];
+        }
+        for (int i = 0; i < 64; i++) T.tree[i] = -1;
+      }
+    for (int64_t pi = nb.edge_pair_off[e]; pi < nb.edge_pair_off[e + 1]; pi++) {
+      const TbrPair &p = nb.pairs[pi];
+      const int64_t cr = push_second ? p.c1 : p.c2, cc = push_second ? p.c2 : p.c1;
+      const int ri = pos[cr - s0], cj = pos[cc - s0];
+      prog.t20_tiles[tile0 + (size_t)(ri / 8) * ntc + cj / 8].tree[(ri % 8) * 8 + cj % 8] = (int)(pi - p_lo);
+    }
+    prog.t20_pair_bytes += (double)ntr * ntc * 16.0 * Cb;
+  }
+  prog.t20_tile_off.push_back((int)prog.t20_tiles.size());
+  int max_level = 0;
+  for (auto &o : ops) max_level = std::max(max_level, o.level);
+  prog.t20_level_off.assign(max_level + 2, 0);
+  for (auto &o : ops) prog.t20_level_off[o.level + 1]++;
+  for (int l = 0; l <= max_level; l++) prog.t20_level_off[l + 1] += prog.t20_level_off[l];
+  std::vector<int64_t> cur(prog.t20_level_off.begin(), prog.t20_level_off.end() - 1);
+  prog.t20_ops.resize(ops.size());
+  for (auto &o : ops) prog.t20_ops[cur[o.level]++] = o.op;
+  prog.n_slots = slots;
+  prog.t20_pair_slots = pslots;
   prog.n_trees = nb.edge_pair_off[e1] - p_lo;
 }
 

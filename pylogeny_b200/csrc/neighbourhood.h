@@ -179,5 +179,9 @@ void build_lik_tbr_program(const TbrNeighbourhood &nb, const int32_t *tip_rows, 
                            LikProgram &out);
 // scratch slots a chunk of edges needs (for memory budgeting)
 int64_t tbr_slots_needed(const TbrNeighbourhood &nb, int e0, int e1);
+// 20 states x Gamma-4: fused candidate steps + pair grid (csrc/lik_tbr20.cuh); same pairs, same tree ids
+void build_lik_tbr20_program(const TbrNeighbourhood &nb, const int32_t *tip_rows, int n_rows, int e0, int e1,
+                             LikProgram &prog);
+int64_t tbr20_slots_needed(const TbrNeighbourhood &nb, int e0, int e1);
 
 }  // namespace plg

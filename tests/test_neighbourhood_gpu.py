@@ -109,6 +109,45 @@ def test_tbr_edge_insertion_vs_retraversal(n, P):
     fa.close(); la.close(); m.close()
 
 
+@pytest.mark.parametrize("n,P,scale", [(4, 30, 1.0), (5, 64, 1.0), (9, 333, 1.0), (16, 700, 1.0), (30, 150, 40.0), (60, 90, 1.0)])
+def test_tbr_20_states_fused_steps_and_pair_grid(n, P, scale, monkeypatch):
+    """20 states x Gamma-4 TBR neighbourhoods: the fused candidate steps + DMMA pair grid (lik_tbr20.cuh,
+    default) against the level program of plain updates and row evaluations (PLG_TBR20=0), against the
+    re-traversal of materialised neighbours and against the oracle -- ambiguity codes, weights (also
+    zero), the underflow regime (long branches: 2^-256 factors inside a fused step), shards."""
+    from pylogeny_b200 import _lib, likelihood, neighbourhood as nbh
+    rng = np.random.default_rng(7 * n + P)
+    codes = rng.integers(0, 20, (n, P)).astype(np.uint8)
+    codes = np.where(rng.random((n, P)) < 0.03, rng.integers(20, 23, (n, P)), codes).astype(np.uint8)
+    w = rng.integers(0, 4, P).astype(float)
+    exch, f = likelihood.protein_model("WAG") if n % 2 else (rng.uniform(0.05, 5.0, 190), rng.dirichlet(np.ones(20) * 10))
+    a = likelihood.LikAlignment(codes, w, _lib.DATA_AA)
+    m = likelihood.Model(exch, f, 0.8)
+    d = random_desc(rng, n)
+    br = rng.exponential(0.1 * scale, d.shape)
+    br[rng.random(br.shape) < 0.1] = 1e-9   # (an exact zero between two different tip states is lnL = -inf)
+    moves, lnl = nbh.score_likelihood(a, m, d, br, move_type=nbh.MOVE_TBR)
+    M = len(lnl)
+    assert M == nbh.neighbourhood_size(d, nbh.MOVE_TBR) and np.all(np.isfinite(lnl)) and np.all(lnl < 0)
+    monkeypatch.setenv("PLG_TBR20", "0")
+    moves0, lnl0 = nbh.score_likelihood(a, m, d, br, move_type=nbh.MOVE_TBR)
+    monkeypatch.delenv("PLG_TBR20")
+    assert moves.tolist() == moves0.tolist()
+    np.testing.assert_allclose(lnl, lnl0, rtol=1e-12)
+    sel = np.unique(np.linspace(0, M - 1, 24).astype(np.int64)) if M else np.zeros(0, np.int64)
+    descs, brs, _ = nbh.neighbour_trees(d, br, sel, nbh.MOVE_TBR)
+    if M:
+        np.testing.assert_allclose(lnl[sel], a.score_trees(m, descs, brs), rtol=1e-11)
+    for j in range(0, len(sel), 5):
+        want = oracle.lnl(codes, w, exch, f, 0.8, descs[j], brs[j])
+        assert abs(lnl[sel[j]] - want) <= 1e-8 * abs(want)
+    if M >= 3:
+        parts = [nbh.score_likelihood(a, m, d, br, move_type=nbh.MOVE_TBR, shard=(i, 3), want_moves=False)[1] for i in range(3)]
+        got = np.concatenate([parts[i][M * i // 3:M * (i + 1) // 3] for i in range(3)])
+        np.testing.assert_array_equal(got, lnl)
+    a.close(); m.close()
+
+
 @pytest.mark.parametrize("n,P,scale,wmax", [(6, 40, 1.0, 4), (24, 700, 1.0, 4), (70, 300, 1.0, 4), (40, 200, 60.0, 4),
                                             (24, 700, 1.0, 1), (70, 300, 1.0, 2), (40, 200, 60.0, 1), (9, 33, 200.0, 1)])
 def test_lnl_planners_agree(n, P, scale, wmax, monkeypatch):
