@@ -149,12 +149,9 @@ __device__ __forceinline__ void wm_rescale(double (&n)[WM_V], int &sc, int lane)
   }
 }
 
-// Site likelihoods from the per-group sums u[j] = sum_r e[r][j] (this lane's state q, not yet
-// weighted by pi): transpose-reduce over the quad, lane q ends with L of pattern (j = q, g).
-__device__ __forceinline__ double wm_site_L(const double (&u)[4], double pi_q, int lane) {
-  double v[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) v[j] = pi_q * u[j];
+// Site likelihoods from the per-group sums v[j] = sum_r e[r][j] (this lane's state q; pi_q is already
+// inside: wm_search folds it into the pruned subtree's vector once per search): transpose-reduce over the quad, lane q ends with L of pattern (j = q, g).
+__device__ __forceinline__ double wm_site_L(const double (&v)[4], int lane) {
   const bool hi = lane & 2, odd = lane & 1;
   double k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
   k0 += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 2);
@@ -245,6 +242,8 @@ __device__ __forceinline__ void wm_search(const LikWalkGroup g, const LikWalkVis
     wm_load_raw(g.tv, n_rows, Ppad, p0, lane, out_off, codes, clv, scl, x, st);
     wm_frag(pmat, g.p_v, lane, bv);
     wm_pair(x, bv, t, dump);
+#pragma unroll
+    for (int i = 0; i < WM_V; i++) t[i] *= pi_q;  // every site term of the search carries pi_q (x) this vector
     __syncwarp();
     wm_park_store(&park[0][0][0], lane, t);
   }
@@ -307,7 +306,7 @@ __device__ __forceinline__ void wm_search(const LikWalkGroup g, const LikWalkVis
     }
     if (tree2 >= 0) {  // neighbour 2 = insertion into x--c2
       const int64_t o = (int64_t)tree2 * pstride + slice;
-      wm_emit<MODE == 1>(wm_site_L(u2, pi_q, lane), sc2 + s2 + st, w_out, lane, partial + o, partial_e + o);
+      wm_emit<MODE == 1>(wm_site_L(u2, lane), sc2 + s2 + st, w_out, lane, partial + o, partial_e + o);
     }
     {
       double h1[WM_V];
@@ -317,7 +316,7 @@ __device__ __forceinline__ void wm_search(const LikWalkGroup g, const LikWalkVis
     sk = sc1;
     if (tree1 >= 0) {  // neighbour 1 = insertion into x--c1
       const int64_t o = (int64_t)tree1 * pstride + slice;
-      wm_emit<MODE == 1>(wm_site_L(u1, pi_q, lane), sc1 + s1 + st, w_out, lane, partial + o, partial_e + o);
+      wm_emit<MODE == 1>(wm_site_L(u1, lane), sc1 + s1 + st, w_out, lane, partial + o, partial_e + o);
     }
     dcur = dnxt; dnxt = dnn;
   }

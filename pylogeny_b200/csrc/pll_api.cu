@@ -1014,13 +1014,107 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   }
 }
 
-// One handle = one tree: the same lockstep program as a batch of one (all Newton steps stay on the
-// device; the host enqueues ~5 n launches per pass and waits once), on buffers kept between calls.
+}  // namespace plg
+#include "pll_smooth1.cuh"
+namespace plg {
+
+// DNA x Gamma-4, one tree: the whole smoothing program in one cooperative launch (pll_smooth1.cuh).
+// Returns false when the grid cannot be co-resident (very long alignments): the caller takes the
+// lockstep program instead.
+static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const std::vector<int32_t> &tip_rows,
+                    int max_passes, double *out_lnl) {
+  struct Scratch {
+    DevBuf<double> clv, pmat, tiptab, brlen, dpart, out;
+    DevBuf<int> scl;
+    DevBuf<S1Act> acts;
+    int max_blocks = -1;
+  };
+  static thread_local Scratch keep[8];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  Scratch &sc = keep[dev & 7];
+  if (sc.max_blocks < 0) {
+    int per_sm = 0, sms = 0, coop = 0;
+    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smooth1_kernel, S1_THREADS, 0));
+    PLG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PLG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    sc.max_blocks = coop ? per_sm * sms : 0;
+  }
+  const int64_t Ppad = aln.Ppad;
+  const int n_blocks = (int)(Ppad / S1_THREADS);
+  if (n_blocks > sc.max_blocks) return false;
+  const int n = tree.n_tips, n_inner = n - 2, n_br = 2 * n - 3;
+  TreePlan plan = plan_tree(tree, tip_rows, aln.n_rows, 0, 0, 0);
+  std::vector<S1Act> acts;
+  acts.reserve(plan.down.size() + plan.acts.size() + 1);
+  for (const LikOp &o : plan.down) acts.push_back({0, o.dst, o.a, o.b, o.pa, o.pb, -1, 0});
+  for (const TreePlan::Act &a : plan.acts) {
+    if (a.is_opt) acts.push_back({1, -1, a.it.a_id, a.it.b_id, -1, -1, a.it.branch, 0});
+    else acts.push_back({0, a.op.dst, a.op.a, a.op.b, a.op.pa, a.op.pb, -1, 0});
+  }
+  acts.push_back({1, -1, plan.eval.a, plan.eval.b, -1, -1, plan.eval.pb, 0});  // lnL across the branch at tip 0
+  std::vector<double> h_brlen(n_br, 0.0);
+  {
+    int b = 0;
+    for (int x = 0; x < tree.n_nodes; x++)  // same numbering as plan_tree
+      for (int k = 0; k < 3; k++)
+        if (tree.nb[x][k] > x) h_brlen[b++] = tree.len[x][k];
+  }
+  sc.clv.alloc((size_t)n_inner * 16 * Ppad);
+  sc.scl.alloc((size_t)n_inner * Ppad);
+  sc.pmat.alloc((size_t)n_br * 68);
+  sc.tiptab.alloc((size_t)n_br * 256);
+  sc.brlen.alloc(n_br);
+  sc.dpart.alloc((size_t)2 * 3 * n_blocks);
+  sc.out.alloc(1);
+  sc.acts.alloc(acts.size());
+  cudaStream_t st = 0;
+  PLG_CUDA(cudaMemcpyAsync(sc.acts.p, acts.data(), acts.size() * sizeof(S1Act), cudaMemcpyHostToDevice, st));
+  PLG_CUDA(cudaMemcpyAsync(sc.brlen.p, h_brlen.data(), (size_t)n_br * 8, cudaMemcpyHostToDevice, st));
+  dna4_pmatrices(aln, model, sc.brlen.p, nullptr, n_br, sc.pmat.p, sc.tiptab.p, st);
+  const S1Act *d_acts = sc.acts.p;
+  int n_down = (int)plan.down.size(), n_pass = (int)plan.acts.size(), passes = max_passes, n_rows = aln.n_rows;
+  int64_t ppad = Ppad;
+  const unsigned char *codes = aln.codes.p;
+  const unsigned int *masks = aln.masks.p;
+  const double *weights = aln.weights.p;
+  const ModelDev *md = model.d.p;
+  double *pm = sc.pmat.p, *tt = sc.tiptab.p, *clv = sc.clv.p, *bl = sc.brlen.p, *dp = sc.dpart.p, *out = sc.out.p;
+  int *scl = sc.scl.p;
+  void *args[] = {&d_acts, &n_down, &n_pass, &passes, &n_rows, &ppad, &codes, &masks, &weights, &md,
+                  &pm, &tt, &clv, &scl, &bl, &dp, &out};
+  PLG_CUDA(cudaLaunchCooperativeKernel((const void *)smooth1_kernel, dim3(n_blocks), dim3(S1_THREADS), args, 0, st));
+  count_launch();
+  double h_out = 0.0;
+  PLG_CUDA(cudaMemcpyAsync(&h_out, sc.out.p, 8, cudaMemcpyDeviceToHost, st));
+  PLG_CUDA(cudaMemcpyAsync(h_brlen.data(), sc.brlen.p, (size_t)n_br * 8, cudaMemcpyDeviceToHost, st));
+  PLG_CUDA(cudaStreamSynchronize(st));
+  *out_lnl = h_out;
+  int b = 0;
+  for (int x = 0; x < tree.n_nodes; x++)
+    for (int k = 0; k < 3; k++) {
+      const int y = tree.nb[x][k];
+      if (y > x) { const double len = h_brlen[b++]; tree.len[x][k] = len; tree.len[y][tree.slot_of(y, x)] = len; }
+    }
+  return true;
+}
+
+// One handle = one tree.  DNA x Gamma-4: the whole smoothing in ONE cooperative launch (smooth1 above;
+// PLG_PLL_HANDLE_MODE=batch keeps the lockstep program as a batch of one -- ~5 n launches per pass --,
+// =host the literal per-branch loop with a device round trip per Newton step: the A/B references).
 double PllProblem::loglik(int max_passes) {
   if (tree.n_tips < 3) PLG_FAIL(PLG_ERR_UNSUPPORTED, "need at least 3 taxa");
   const char *mode = getenv("PLG_PLL_HANDLE_MODE");
   const bool dna4 = aln->K == 4 && model->R == 4, aa20 = aln->K == 20 && model->R == 4;
   if ((mode && !strcmp(mode, "host")) || !(dna4 || aa20)) return loglik_host_loop(max_passes);
+  if (dna4 && max_passes > 0 && !(mode && !strcmp(mode, "batch"))) {
+    double out = 0.0;
+    if (smooth1(*aln, *model, tree, tip_rows, max_passes, &out)) {
+      lnl = out;
+      smoothed = true;
+      return lnl;
+    }
+  }
   std::vector<UTree> trees(1, tree);
   std::vector<std::vector<int32_t>> rows(1, tip_rows);
   double out = 0.0;

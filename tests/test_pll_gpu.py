@@ -240,8 +240,9 @@ def test_alignment_cache_is_keyed_by_file_identity(tmp_path):
 
 
 def test_handle_lockstep_equals_host_loop(monkeypatch):
-    """plg_pll_loglik on one handle runs the lockstep program as a batch of one (every Newton step on the
-    device); PLG_PLL_HANDLE_MODE=host keeps the literal loop with one device round trip per branch.  Same
+    """plg_pll_loglik on one handle runs the whole smoothing program in one cooperative launch (DNA x
+    Gamma-4, pll_smooth1.cuh); PLG_PLL_HANDLE_MODE=batch runs the lockstep program as a batch of one,
+    =host keeps the literal loop with one device round trip per branch.  Same
     lnL and branch lengths, also when getLogLikelihood is called again on the same handle (the reference
     mutates the instance: the second call continues from the first call's lengths, libpllWrapper.c:205)."""
     from pylogeny_b200 import libpllWrapper as W, neighbourhood as nbh, pll
@@ -252,9 +253,9 @@ def test_handle_lockstep_equals_host_loop(monkeypatch):
     pm = pll.partitionModel(ali)
     pm.createSimpleModel()
     res = {}
-    for mode in ("host", "device"):
-        if mode == "host":
-            monkeypatch.setenv("PLG_PLL_HANDLE_MODE", "host")
+    for mode in ("host", "batch", "device"):
+        if mode != "device":
+            monkeypatch.setenv("PLG_PLL_HANDLE_MODE", mode)
         else:
             monkeypatch.delenv("PLG_PLL_HANDLE_MODE")
         h = W.new(ali.getPhylip(), nw, pm.getFileName())
@@ -265,12 +266,14 @@ def test_handle_lockstep_equals_host_loop(monkeypatch):
         ev = W.evaluate(h)
         W.destroy(h)
         res[mode] = (first, second, ev, nbh.newick_to_desc(nw1, taxa)[1], nbh.newick_to_desc(nw2, taxa)[1])
-    a, b = res["host"], res["device"]
-    np.testing.assert_allclose(b[:3], a[:3], rtol=1e-9)
-    assert b[1] >= b[0] - 1e-9 * abs(b[0]) and abs(b[2] - b[1]) <= 1e-9 * abs(b[1])   # smoothing on, evaluate agrees
-    np.testing.assert_allclose(b[3], a[3], rtol=1e-6, atol=1e-9)
-    np.testing.assert_allclose(b[4], a[4], rtol=1e-6, atol=1e-9)
-    assert not np.allclose(b[3], b[4])                                               # the second call moved the branches on
+    a = res["host"]
+    for mode in ("batch", "device"):   # the lockstep program as a batch of one; the single cooperative launch
+        b = res[mode]
+        np.testing.assert_allclose(b[:3], a[:3], rtol=1e-9)
+        assert b[1] >= b[0] - 1e-9 * abs(b[0]) and abs(b[2] - b[1]) <= 1e-9 * abs(b[1])   # smoothing on, evaluate agrees
+        np.testing.assert_allclose(b[3], a[3], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(b[4], a[4], rtol=1e-6, atol=1e-9)
+        assert not np.allclose(b[3], b[4])                                               # the second call moved the branches on
     pm.close(); ali.close()
 
 
@@ -318,6 +321,56 @@ def test_batched_getLogLikelihood_equals_per_tree_path(monkeypatch):
     W.destroy(h)
     with pytest.raises(IOError):
         W.getLogLikelihoodBatch(ali.getPhylip(), ["(a,b,c);"], pm.getFileName())
+    pm.close(); ali.close()
+
+
+@pytest.mark.parametrize("n,S,signal", [(3, 200, True), (4, 64, True), (5, 300, True), (9, 1500, True), (33, 2500, True),
+                                        (10, 12, False), (10, 40, False), (7, 25, False), (12, 55, False)])
+def test_single_launch_smoother_equals_host_loop(n, S, signal, monkeypatch):
+    """The per-handle getLogLikelihood of a DNA tree -- ONE cooperative launch that walks the whole
+    smoothing program with a grid barrier per Newton evaluation (pll_smooth1.cuh) -- against the literal
+    per-branch host loop: smallest trees, alignments of a few patterns (one block), several blocks, and
+    random sequences on few sites, where the bad-curvature guard retries and the z clamps do the work.
+    lnL, branch lengths, and the oracle at the returned lengths."""
+    from pylogeny_b200 import _lib, alignment, libpllWrapper as W, likelihood, neighbourhood as nbh, pll
+    rng = np.random.default_rng(1000 * n + S)
+    if signal:
+        ali, d = _case(n=max(n, 4), S=S, seed=n + S)
+        if n == 3:
+            seqs = ali.toStrList()[:3]
+            ali.close()
+            ali = alignment.phylipFriendlyAlignment(names=["tax%d" % i for i in range(3)], seqs=seqs)
+            d = np.array([[0, 1], [3, 2]], dtype=np.int32)
+    else:
+        seqs = ["".join(rng.choice(list("ACGT"), S)) for _ in range(n)]
+        ali = alignment.phylipFriendlyAlignment(names=["tax%d" % i for i in range(n)], seqs=seqs)
+        d = random_desc(rng, n)
+    labels = ali.getTaxa()
+    taxa = {l: i for i, l in enumerate(labels)}
+    nw = desc_to_newick(d, labels)
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    res = {}
+    for mode in ("host", "device"):
+        if mode == "host":
+            monkeypatch.setenv("PLG_PLL_HANDLE_MODE", "host")
+        else:
+            monkeypatch.delenv("PLG_PLL_HANDLE_MODE")
+        h = W.new(ali.getPhylip(), nw, pm.getFileName())
+        lnl = W.getLogLikelihood(h)
+        res[mode] = (lnl, W.getNewickString(h), W.evaluate(h))
+        if mode == "device":
+            K, P = C.c_int(), C.c_int64()
+            freqs, rates = np.zeros(4), np.zeros(4)
+            dp = C.POINTER(C.c_double)
+            _lib.check(_lib.lib().plg_pll_info(h.ptr, C.byref(K), C.byref(P), freqs.ctypes.data_as(dp), rates.ctypes.data_as(dp)))
+        W.destroy(h)
+    (l0, nw0, e0), (l1, nw1, e1) = res["host"], res["device"]
+    assert abs(l1 - l0) <= 1e-9 * abs(l0) and abs(e1 - l1) <= 1e-9 * abs(l1)
+    np.testing.assert_allclose(nbh.newick_to_desc(nw1, taxa)[1], nbh.newick_to_desc(nw0, taxa)[1], rtol=1e-6, atol=1e-9)
+    codes = likelihood.encode_sequences(ali.toStrList(), _lib.DATA_DNA)
+    want = _oracle_at(nw1, taxa, codes, np.ones(ali.getSize()), np.ones(6), freqs, 1.0)
+    assert abs(l1 - want) <= 1e-8 * abs(want)
     pm.close(); ali.close()
 
 
