@@ -509,12 +509,26 @@ struct OptItem {
   int a_id, b_id, tree, branch;  // operand ids of the branch's two ends; tree of the chunk; global branch index
 };
 
+// K = 4: the sum table is NOT stored -- the Newton step normally needs only the derivative sums that came
+// with it, and the rare bad-curvature retry recomputes a pattern's 16 table entries from the two operand
+// columns (2 x 16 loads instead of 16, but 13 % less traffic per tree on the common path).  K = 20 keeps the
+// stored table (80 entries per pattern do not fit in registers beside the operands).
+struct OptOperands {
+  int n_rows;
+  const unsigned char *codes;
+  const unsigned int *masks;
+  const double *clv;
+  const int *scl;
+};
+template <int K>
+__host__ __device__ constexpr bool store_sumtable() { return K != 4; }
+
 template <int K, int R>
 __device__ __forceinline__ void newton_step_block(const OptItem it, int item, int64_t Ppad, const double *__restrict__ weights,
                                                   const ModelDev *__restrict__ model, const double *__restrict__ S,
                                                   const int *__restrict__ Ssc, double *__restrict__ brlen,
                                                   int *__restrict__ changed, const double *__restrict__ dpart,
-                                                  int blocks_per_item);
+                                                  int blocks_per_item, const OptOperands ops);
 
 // One makenewz step of one branch per tree, ONE launch (was: sum table, Newton step, P-matrices = three):
 // every block writes its tile of the branch's sum table and its share of the derivative sums at the
@@ -576,12 +590,12 @@ opt_step_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_ro
       rr = fma(model->Uinv[k * K + i], B[i], rr);
     }
     const double sv = l * rr;
-    So[((int64_t)r * K + k) * Ppad + p] = sv;
+    if (store_sumtable<K>()) So[((int64_t)r * K + k) * Ppad + p] = sv;
     l0 = fma(sv, tab[0][r * K + k], l0);
     l1 = fma(sv, tab[1][r * K + k], l1);
     l2 = fma(sv, tab[2][r * K + k], l2);
   }
-  if (r == 0) Ssc[(int64_t)it.tree * Ppad + p] = sc;
+  if (store_sumtable<K>() && r == 0) Ssc[(int64_t)it.tree * Ppad + p] = sc;
 #pragma unroll
   for (int d = 1; d < R; d <<= 1) {
     l0 += __shfl_xor_sync(0xffffffffu, l0, d);
@@ -623,9 +637,104 @@ opt_step_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_ro
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  newton_step_block<K, R>(it, item, Ppad, weights, model, S, Ssc, brlen, changed, dpart, blocks_per_item);
+  newton_step_block<K, R>(it, item, Ppad, weights, model, S, Ssc, brlen, changed, dpart, blocks_per_item,
+                          OptOperands{n_rows, codes, masks, clv, scl});
   __syncthreads();
   pmatrix_block<K, R>(model, brlen[it.branch], masks, pmat + (int64_t)it.branch * pm_stride, tiptab + (int64_t)it.branch * tip_stride);
+  }
+}
+
+// DNA x Gamma-4, two-launch form: thread = pattern (128 per block), as the conditional-vector kernels.  The
+// generic kernel above gives a thread one (pattern, category): 8 loads of 64-byte runs per operand and a
+// block prologue (branch length -> exp -> log -> exp) in front of them; the launch list of a 256-tree
+// batch had it at 1.6 TB/s against 4.6 for clv4_kernel (profiles/launches_r2w.csv).  Here every thread
+// issues its 32 column loads first, the first 16 threads make the table meanwhile, and no sum table is
+// stored.
+#ifndef PLG_OPT4_MINB
+#define PLG_OPT4_MINB 5
+#endif
+constexpr int OPT4_THREADS = 128;
+__global__ void __launch_bounds__(OPT4_THREADS, PLG_OPT4_MINB)
+opt_step4_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
+                 const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
+                 const ModelDev *__restrict__ model, const double *__restrict__ clv, const int *__restrict__ scl,
+                 const double *__restrict__ weights, const double *__restrict__ brlen, double *__restrict__ dpart,
+                 const int *__restrict__ active) {
+  __shared__ double tab[3][16];
+  __shared__ double mU[16], mUinv[16], mpi[4];
+  __shared__ double red[3][OPT4_THREADS / 32];
+  const int item = blockIdx.x / blocks_per_item;
+  const OptItem it = items[item];
+  if (!active[it.tree]) return;
+  const int64_t p = (int64_t)(blockIdx.x - item * blocks_per_item) * OPT4_THREADS + threadIdx.x;
+  // operands category by category (8 column entries live at a time instead of 32)
+  const bool tipA = it.a_id < n_rows, tipB = it.b_id < n_rows;
+  const unsigned int mA = tipA ? masks[codes[(int64_t)it.a_id * Ppad + p]] : 0u;
+  const unsigned int mB = tipB ? masks[codes[(int64_t)it.b_id * Ppad + p]] : 0u;
+  const double *srcA = clv + (int64_t)(tipA ? 0 : it.a_id - n_rows) * 16 * Ppad + p;
+  const double *srcB = clv + (int64_t)(tipB ? 0 : it.b_id - n_rows) * 16 * Ppad + p;
+  int sc = 0;
+  if (!tipA) sc += __ldg(scl + (int64_t)(it.a_id - n_rows) * Ppad + p);
+  if (!tipB) sc += __ldg(scl + (int64_t)(it.b_id - n_rows) * Ppad + p);
+  const double w = weights[p];
+  if (threadIdx.x < 16) {
+    const double z = fmin(fmax(exp(-brlen[it.branch]), PLL_ZMIN), PLL_ZMAX);
+    const double lz = log(fmax(z, PLL_ZMIN));
+    const double g = -model->eval[threadIdx.x & 3] * model->rates[threadIdx.x >> 2];
+    const double e = exp(g * lz);
+    tab[0][threadIdx.x] = e; tab[1][threadIdx.x] = g * e; tab[2][threadIdx.x] = g * g * e;
+    mU[threadIdx.x] = model->U[threadIdx.x];
+    mUinv[threadIdx.x] = model->Uinv[threadIdx.x];
+    if (threadIdx.x < 4) mpi[threadIdx.x] = model->freqs[threadIdx.x];
+  }
+  __syncthreads();
+  double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      a[i] = tipA ? ((mA >> i & 1) ? 1.0 : 0.0) : __ldg(srcA + (int64_t)(r * 4 + i) * Ppad);
+      b[i] = tipB ? ((mB >> i & 1) ? 1.0 : 0.0) : __ldg(srcB + (int64_t)(r * 4 + i) * Ppad);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] *= mpi[i];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      double l = 0.0, rr = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        l = fma(a[i], mU[i * 4 + k], l);
+        rr = fma(mUinv[k * 4 + i], b[i], rr);
+      }
+      const double sv = l * rr;
+      l0 = fma(sv, tab[0][r * 4 + k], l0);
+      l1 = fma(sv, tab[1][r * 4 + k], l1);
+      l2 = fma(sv, tab[2][r * 4 + k], l2);
+    }
+  }
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  if (w != 0.0) {
+    const double inv = 1.0 / l0, q1 = l1 * inv;
+    v0 = w * (log(l0 * 0.25) + sc * SM_LOG_MINLH);
+    v1 = w * q1;
+    v2 = w * (l2 * inv - q1 * q1);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v0 += __shfl_down_sync(0xffffffffu, v0, d);
+    v1 += __shfl_down_sync(0xffffffffu, v1, d);
+    v2 += __shfl_down_sync(0xffffffffu, v2, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = v0; red[1][threadIdx.x >> 5] = v1; red[2][threadIdx.x >> 5] = v2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < OPT4_THREADS / 32; i++) t += red[threadIdx.x][i];
+    dpart[((int64_t)item * 3 + threadIdx.x) * blocks_per_item + (blockIdx.x - item * blocks_per_item)] = t;
   }
 }
 
@@ -636,10 +745,10 @@ newton_kernel(const OptItem *__restrict__ items, int blocks_per_item, int64_t Pp
               const ModelDev *__restrict__ model, const double *__restrict__ S, const int *__restrict__ Ssc,
               const double *__restrict__ weights, double *__restrict__ brlen, const double *__restrict__ dpart,
               const int *__restrict__ active, int *__restrict__ changed, double *__restrict__ pmat,
-              double *__restrict__ tiptab, int pm_stride, int tip_stride) {
+              double *__restrict__ tiptab, int pm_stride, int tip_stride, const OptOperands ops) {
   const OptItem it = items[blockIdx.x];
   if (!active[it.tree]) return;
-  newton_step_block<K, R>(it, blockIdx.x, Ppad, weights, model, S, Ssc, brlen, changed, dpart, blocks_per_item);
+  newton_step_block<K, R>(it, blockIdx.x, Ppad, weights, model, S, Ssc, brlen, changed, dpart, blocks_per_item, ops);
   __syncthreads();
   pmatrix_block<K, R>(model, brlen[it.branch], masks, pmat + (int64_t)it.branch * pm_stride, tiptab + (int64_t)it.branch * tip_stride);
 }
@@ -650,7 +759,7 @@ __device__ __forceinline__ void newton_step_block(const OptItem it, int item, in
                                                   const ModelDev *__restrict__ model, const double *__restrict__ S,
                                                   const int *__restrict__ Ssc, double *__restrict__ brlen,
                                                   int *__restrict__ changed, const double *__restrict__ dpart,
-                                                  int blocks_per_item) {
+                                                  int blocks_per_item, const OptOperands ops) {
   constexpr int RK = R * K;
   __shared__ double tab[3][RK];
   __shared__ double red[3][SM_THREADS / 32];
@@ -685,15 +794,50 @@ __device__ __forceinline__ void newton_step_block(const OptItem it, int item, in
       const double w = weights[p];
       if (w == 0.0) continue;
       double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+      int scp = 0;
+      if constexpr (store_sumtable<K>()) {
 #pragma unroll
-      for (int e = 0; e < RK; e++) {
-        const double sv = Sb[(int64_t)e * Ppad + p];
-        l0 = fma(sv, tab[0][e], l0);
-        l1 = fma(sv, tab[1][e], l1);
-        l2 = fma(sv, tab[2][e], l2);
+        for (int e = 0; e < RK; e++) {
+          const double sv = Sb[(int64_t)e * Ppad + p];
+          l0 = fma(sv, tab[0][e], l0);
+          l1 = fma(sv, tab[1][e], l1);
+          l2 = fma(sv, tab[2][e], l2);
+        }
+        scp = sc[p];
+      } else {  // the pattern's table entries again, from the two operand columns (as opt_step_kernel makes them)
+        double A[RK], B[RK];
+        auto fetch = [&](int id, double(&x)[RK]) {
+          if (id < ops.n_rows) {
+            const unsigned int m = ops.masks[ops.codes[(int64_t)id * Ppad + p]];
+#pragma unroll
+            for (int e = 0; e < RK; e++) x[e] = (m >> (e % K) & 1) ? 1.0 : 0.0;
+          } else {
+            const double *src = ops.clv + (int64_t)(id - ops.n_rows) * RK * Ppad + p;
+#pragma unroll
+            for (int e = 0; e < RK; e++) x[e] = src[(int64_t)e * Ppad];
+            scp += ops.scl[(int64_t)(id - ops.n_rows) * Ppad + p];
+          }
+        };
+        fetch(it.a_id, A);
+        fetch(it.b_id, B);
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            double l = 0.0, rr = 0.0;
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+              l = fma(A[r * K + i] * model->freqs[i], model->U[i * K + k], l);
+              rr = fma(model->Uinv[k * K + i], B[r * K + i], rr);
+            }
+            const double sv = l * rr;
+            l0 = fma(sv, tab[0][r * K + k], l0);
+            l1 = fma(sv, tab[1][r * K + k], l1);
+            l2 = fma(sv, tab[2][r * K + k], l2);
+          }
       }
       const double inv = 1.0 / l0, q1 = l1 * inv;
-      v0 += w * (log(l0 * (1.0 / R)) + sc[p] * SM_LOG_MINLH);
+      v0 += w * (log(l0 * (1.0 / R)) + scp * SM_LOG_MINLH);
       v1 += w * q1;
       v2 += w * (l2 * inv - q1 * q1);
     }
@@ -894,8 +1038,8 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   DevBuf<LikEval> &d_evals = sc_.d_evals;
   clv.alloc((size_t)B * n_inner * RK * Ppad);
   scl.alloc((size_t)B * n_inner * Ppad);
-  S.alloc((size_t)B * RK * Ppad);
-  Ssc.alloc((size_t)B * Ppad);
+  S.alloc(store_sumtable<K>() ? (size_t)B * RK * Ppad : 1);
+  Ssc.alloc(store_sumtable<K>() ? (size_t)B * Ppad : 1);
   pmat.alloc((size_t)B * n_br * F::PM_STRIDE);
   tiptab.alloc((size_t)B * n_br * F::TIP_STRIDE);
   brlen.alloc((size_t)B * n_br);
@@ -909,6 +1053,8 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   d_items.alloc((size_t)B * n_br);
   idx.alloc((size_t)B * n_br);
   const int bpi = (int)(Ppad / (SM_THREADS / R));
+  // blocks per branch of the launch that leaves the derivative-sum shares (DNA, large batches: opt_step4_kernel)
+  const int bpi2 = (K == 4 && R == 4) ? (int)(Ppad / OPT4_THREADS) : bpi;
   dpart.alloc((size_t)B * 3 * bpi);
   tickets.alloc((size_t)B);
   PLG_CUDA(cudaMemsetAsync(tickets.p, 0, (size_t)B * sizeof(unsigned int), 0));
@@ -980,15 +1126,20 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
             opt_step_kernel<K, R, true><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
                 its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
                 aln.weights.p, brlen.p, dpart.p, active, changed, tickets.p, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
+          else if constexpr (K == 4 && R == 4)
+            opt_step4_kernel<<<(unsigned)(no * bpi2), OPT4_THREADS, 0, st>>>(
+                its, bpi2, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, aln.weights.p, brlen.p,
+                dpart.p, active);
           else
             opt_step_kernel<K, R, false><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
                 its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
                 aln.weights.p, brlen.p, dpart.p, active, changed, nullptr, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
           count_launch();
           if (!fused) {
-            newton_kernel<K, R><<<(unsigned)no, SM_THREADS, 0, st>>>(its, bpi, Ppad, aln.masks.p, model.d.p, S.p, Ssc.p,
+            newton_kernel<K, R><<<(unsigned)no, SM_THREADS, 0, st>>>(its, bpi2, Ppad, aln.masks.p, model.d.p, S.p, Ssc.p,
                                                                       aln.weights.p, brlen.p, dpart.p, active, changed,
-                                                                      pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
+                                                                      pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE,
+                                                                      OptOperands{aln.n_rows, aln.codes.p, aln.masks.p, clv.p, scl.p});
             count_launch();
           }
         }
