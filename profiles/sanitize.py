@@ -53,3 +53,32 @@ for env, vals in (("PLG_FITCH_NB_PLAN", ("device", "host")), ("PLG_LIK_NB_PLAN",
               nbh.score_likelihood(pa, pm, d, br, move_type=nbh.MOVE_TBR)[1].sum())
     os.environ.pop(env)
 print("sanitize pass 3 done")
+# round 2: 20-state TBR (fused candidate steps + pair grid; PLG_TBR20=0 = the level program), a deeper
+# protein tree with long branches (scaling factors inside the fused steps), the batched smoother (stored
+# table for 20 states, none for DNA), the single-launch smoother and the lockstep batch of one
+for v in ("1", "0"):
+    os.environ["PLG_TBR20"] = v
+    print("PLG_TBR20", v, nbh.score_likelihood(pa, pm, d, br, move_type=nbh.MOVE_TBR)[1].sum())
+os.environ.pop("PLG_TBR20")
+n3 = 26
+aa3 = rng.integers(0, 20, (n3, 150)).astype(np.uint8)
+pa3 = likelihood.LikAlignment(aa3, rng.integers(0, 3, 150).astype(float), _lib.DATA_AA)
+d3 = random_desc(rng, n3); br3 = rng.exponential(3.0, d3.shape)
+print("aa tbr deep", nbh.score_likelihood(pa3, pm, d3, br3, move_type=nbh.MOVE_TBR)[1].sum())
+from util import desc_to_newick
+from pylogeny_b200 import alignment, libpllWrapper as W, pll
+for letters, nt in (("ACGT", 11), ("ARNDCQEGHILKMFPSTWYV", 7)):
+    seqs = ["".join(rng.choice(list(letters), 300)) for _ in range(nt)]
+    ali = alignment.phylipFriendlyAlignment(names=["t%d" % i for i in range(nt)], seqs=seqs)
+    pmod = pll.partitionModel(ali); pmod.createSimpleModel()
+    nws = [desc_to_newick(random_desc(rng, nt), ali.getTaxa()) for _ in range(6)]
+    print("batch smoother", letters[:4], W.getLogLikelihoodBatch(ali.getPhylip(), nws, pmod.getFileName())[0][:2])
+    for mode in ("", "batch", "host"):
+        if mode:
+            os.environ["PLG_PLL_HANDLE_MODE"] = mode
+        h = W.new(ali.getPhylip(), nws[0], pmod.getFileName())
+        print("handle", mode or "single launch", W.getLogLikelihood(h))
+        W.destroy(h)
+        os.environ.pop("PLG_PLL_HANDLE_MODE", None)
+    pmod.close(); ali.close()
+print("sanitize pass 4 done")
