@@ -697,7 +697,7 @@ def run_ours(args):
                     other[name]["cpu_baseline"] = cpu_sample(name, 6.0)[0]
             out["other_workloads"] = other
             out["streaming"] = streaming_leg()
-            out["smoothed_lnl"] = smoothed_lnl_leg()
+            out["smoothed_lnl"] = smoothed_lnl_leg(full=True)
             out["greedy_climb"] = greedy_climb_leg()
     emit(json.dumps(out))
     if world > 1:
@@ -725,7 +725,7 @@ def greedy_climb_leg():
             "note": "per step: score all 255,530 neighbours, argmin, materialise the winner"}
 
 
-def smoothed_lnl_leg(T=1024):
+def smoothed_lnl_leg(T=1024, full=False):
     """What scoring.getLogLikelihood returns per tree in the reference (libpllWrapper.c:152, :205:
     default branch lengths, 3 smoothing passes, lnL) for the first T SPR neighbours of the configs[1]
     tree, through plg_pll_loglik_batch (all trees in lockstep on the device) and, on 8 of them,
@@ -754,12 +754,39 @@ def smoothed_lnl_leg(T=1024):
         ref.append(W.getLogLikelihood(h))
         W.destroy(h)
     dt1 = (time.perf_counter() - t0) / 8
+    out = {"workload": "GTR+G4 lnL after 3 branch-length smoothing passes from z = 0.9 (scoring.getLogLikelihood "
+                       "semantics) of the first %d SPR neighbours, 64 taxa x 10k sites" % T,
+           "value": T * wl["n_sites"] / dt, "unit": UNIT, "ms_per_tree": 1e3 * dt / T, "per_tree_handle_ms": 1e3 * dt1,
+           "max_rel_diff_vs_per_tree": float(np.max(np.abs((np.array(ref) - np.array(lnl[:8])) / np.array(ref))))}
+    if full:
+        # the WHOLE neighbourhood with the reference's per-tree semantics (what one step of heuristic.likelihoodGreedy
+        # evaluates, heuristic.py:148-153), in one batched call; bytes = every conditional vector an action reads or
+        # writes, once (C + 4 = 132 B per inner vector and pattern, 1 B per tip): per pass 3(n-2) re-orientations
+        # (result + two operands) and 2n-3 Newton steps (the two end vectors), three passes, plus the down pass
+        n = wl["n_taxa"]
+        all_desc, _, _ = nbh.neighbour_trees(d, None, None)
+        all_nw = [nbh.desc_to_newick(x, labels) for x in all_desc]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        full_lnl, _ = W.getLogLikelihoodBatch(ali.getPhylip(), all_nw, pm.getFileName())
+        dtf = time.perf_counter() - t0
+        C4 = 132.0
+        per_pass = 3 * (n - 2) * C4 + (4 * n - 12) * C4 + 2 * n + (3 * n - 6) * C4 + n
+        down = (n - 2) * C4 + (n - 3) * C4 + (n - 1)
+        bytes_per_tree = (3 * per_pass + down) * wl["n_sites"]
+        hbm, hbm_src = measured_hbm_peak()
+        gbs = len(all_nw) * bytes_per_tree / dtf / 1e9
+        out["full_neighbourhood"] = {
+            "workload": "the same for ALL %d SPR neighbours in one call (one likelihoodGreedy step)" % len(all_nw),
+            "seconds": dtf, "ms_per_tree": 1e3 * dtf / len(all_nw), "value": len(all_nw) * wl["n_sites"] / dtf, "unit": UNIT,
+            "best_lnl": float(np.max(full_lnl)),
+            "roofline": {"kernels": "clv4_kernel + opt_step4_kernel + newton_kernel (lockstep program, host clock over the whole call "
+                                    "incl. planning and uploads)", "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                         "frac": gbs / hbm, "peak_source": hbm_src, "bytes_per_tree": bytes_per_tree,
+                         "assumes": "all three passes run on every tree (they do from z = 0.9 on random data)"}}
     pm.close()
     ali.close()
-    return {"workload": "GTR+G4 lnL after 3 branch-length smoothing passes from z = 0.9 (scoring.getLogLikelihood "
-                        "semantics) of the first %d SPR neighbours, 64 taxa x 10k sites" % T,
-            "value": T * wl["n_sites"] / dt, "unit": UNIT, "ms_per_tree": 1e3 * dt / T, "per_tree_handle_ms": 1e3 * dt1,
-            "max_rel_diff_vs_per_tree": float(np.max(np.abs((np.array(ref) - np.array(lnl[:8])) / np.array(ref))))}
+    return out
 
 
 def streaming_leg():

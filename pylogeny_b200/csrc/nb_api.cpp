@@ -113,19 +113,25 @@ int score_tbr_fitch(FitchAln &a, int n_tips, const int32_t *desc, const int32_t 
 int score_tbr_lik(LikAln &a, const Model &m, int n_tips, const int32_t *desc, const double *brlen,
                   const int32_t *tip_rows, int64_t shard_index, int64_t shard_count, int64_t *n_moves,
                   int32_t *out_moves, double *out_lnl, cudaStream_t st) {
+  StageTimer tm;
   TbrNeighbourhood tb = enumerate_tbr(utree_from_desc(n_tips, desc, brlen));
+  tm.lap("tbr enumerate");
   const int64_t M = (int64_t)tb.pairs.size();
   *n_moves = M;
   fill_tbr_moves(tb, out_moves);
   if (!out_lnl || M == 0) return PLG_OK;
   int64_t lo, hi;
   shard_range(M, shard_index, shard_count, &lo, &hi);
-  size_t free_b = 0, total_b = 0;
-  PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t slot_bytes = ((size_t)m.R * a.K * 8 + 4) * a.Ppad;
-  const size_t held = lik_workspace().clv.n * 8 + lik_workspace().scl.n * 4;
-  const size_t budget = std::min<size_t>((free_b + held) / 2, (size_t)80 << 30);
+  LikWorkspace &wsp = lik_workspace();
+  const size_t held = wsp.clv.n * 8 + wsp.scl.n * 4 + wsp.pairvec.n * 8 + wsp.pair_scl.n * 4;
+  // (cudaMemGetInfo is a driver call of 0.1 - 2 ms: skipped once the pools hold what the whole neighbourhood needs)
+  const size_t need_all = (size_t)(3 * (int64_t)tb.t.n_nodes + 3 * (int64_t)tb.cands.size() + 9 * (int64_t)tb.t.n_nodes) * slot_bytes;
+  size_t free_b = 0, total_b = 0;
+  if (need_all > held) PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = need_all <= held ? need_all : std::min<size_t>((free_b + held) / 2, (size_t)80 << 30);
   const int64_t max_slots = std::max<int64_t>(8 * n_tips, (int64_t)(budget / slot_bytes));
+  tm.lap("tbr moves+mem");
   LikProgram p;
   std::vector<double> lnl;
   // 20 states x Gamma-4: fused candidate steps + pair grid on the FP64 tensor pipe (lik_tbr20.cuh);
@@ -135,9 +141,11 @@ int score_tbr_lik(LikAln &a, const Model &m, int n_tips, const int32_t *desc, co
   for_tbr_chunks(tb, lo, hi, max_slots, t20, [&](int e0, int e1) {
     if (t20) build_lik_tbr20_program(tb, tip_rows, a.n_rows, e0, e1, p);
     else build_lik_tbr_program(tb, tip_rows, a.n_rows, e0, e1, p);
+    tm.lap("tbr build");
     const int64_t p0 = tb.edge_pair_off[e0], p1 = tb.edge_pair_off[e1];
     lnl.resize(p1 - p0);
     run_lik_program(a, m, lik_workspace(), p, lnl.data(), st);
+    tm.lap("tbr run");
     for (int64_t i = std::max(p0, lo); i < std::min(p1, hi); i++) out_lnl[i] = lnl[i - p0];
   });
   return PLG_OK;

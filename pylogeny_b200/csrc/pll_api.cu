@@ -651,9 +651,13 @@ opt_step_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_ro
 // issues its 32 column loads first, the first 16 threads make the table meanwhile, and no sum table is
 // stored.
 #ifndef PLG_OPT4_MINB
-#define PLG_OPT4_MINB 5
+#define PLG_OPT4_MINB 4
 #endif
 constexpr int OPT4_THREADS = 128;
+#ifndef PLG_OPT4_TILES
+#define PLG_OPT4_TILES 2
+#endif
+constexpr int OPT4_TILES = PLG_OPT4_TILES;  // (Ppad is a multiple of 256)
 __global__ void __launch_bounds__(OPT4_THREADS, PLG_OPT4_MINB)
 opt_step4_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
                  const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
@@ -666,17 +670,6 @@ opt_step4_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_r
   const int item = blockIdx.x / blocks_per_item;
   const OptItem it = items[item];
   if (!active[it.tree]) return;
-  const int64_t p = (int64_t)(blockIdx.x - item * blocks_per_item) * OPT4_THREADS + threadIdx.x;
-  // operands category by category (8 column entries live at a time instead of 32)
-  const bool tipA = it.a_id < n_rows, tipB = it.b_id < n_rows;
-  const unsigned int mA = tipA ? masks[codes[(int64_t)it.a_id * Ppad + p]] : 0u;
-  const unsigned int mB = tipB ? masks[codes[(int64_t)it.b_id * Ppad + p]] : 0u;
-  const double *srcA = clv + (int64_t)(tipA ? 0 : it.a_id - n_rows) * 16 * Ppad + p;
-  const double *srcB = clv + (int64_t)(tipB ? 0 : it.b_id - n_rows) * 16 * Ppad + p;
-  int sc = 0;
-  if (!tipA) sc += __ldg(scl + (int64_t)(it.a_id - n_rows) * Ppad + p);
-  if (!tipB) sc += __ldg(scl + (int64_t)(it.b_id - n_rows) * Ppad + p);
-  const double w = weights[p];
   if (threadIdx.x < 16) {
     const double z = fmin(fmax(exp(-brlen[it.branch]), PLL_ZMIN), PLL_ZMAX);
     const double lz = log(fmax(z, PLL_ZMIN));
@@ -687,38 +680,51 @@ opt_step4_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_r
     mUinv[threadIdx.x] = model->Uinv[threadIdx.x];
     if (threadIdx.x < 4) mpi[threadIdx.x] = model->freqs[threadIdx.x];
   }
-  __syncthreads();
-  double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    double a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      a[i] = tipA ? ((mA >> i & 1) ? 1.0 : 0.0) : __ldg(srcA + (int64_t)(r * 4 + i) * Ppad);
-      b[i] = tipB ? ((mB >> i & 1) ? 1.0 : 0.0) : __ldg(srcB + (int64_t)(r * 4 + i) * Ppad);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) a[i] *= mpi[i];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      double l = 0.0, rr = 0.0;
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        l = fma(a[i], mU[i * 4 + k], l);
-        rr = fma(mUinv[k * 4 + i], b[i], rr);
-      }
-      const double sv = l * rr;
-      l0 = fma(sv, tab[0][r * 4 + k], l0);
-      l1 = fma(sv, tab[1][r * 4 + k], l1);
-      l2 = fma(sv, tab[2][r * 4 + k], l2);
-    }
-  }
+  const bool tipA = it.a_id < n_rows, tipB = it.b_id < n_rows;
   double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-  if (w != 0.0) {
-    const double inv = 1.0 / l0, q1 = l1 * inv;
-    v0 = w * (log(l0 * 0.25) + sc * SM_LOG_MINLH);
-    v1 = w * q1;
-    v2 = w * (l2 * inv - q1 * q1);
+  // OPT4_TILES tiles of 128 patterns per block: the prologue above (item, branch length, exp / log / exp) is
+  // a chain of dependent global loads and transcendental calls as long as a tile's own loads
+#pragma unroll 1
+  for (int tl = 0; tl < OPT4_TILES; tl++) {
+    const int64_t p = ((int64_t)(blockIdx.x - item * blocks_per_item) * OPT4_TILES + tl) * OPT4_THREADS + threadIdx.x;
+    const unsigned int mA = tipA ? masks[codes[(int64_t)it.a_id * Ppad + p]] : 0u;
+    const unsigned int mB = tipB ? masks[codes[(int64_t)it.b_id * Ppad + p]] : 0u;
+    const double *srcA = clv + (int64_t)(tipA ? 0 : it.a_id - n_rows) * 16 * Ppad + p;
+    const double *srcB = clv + (int64_t)(tipB ? 0 : it.b_id - n_rows) * 16 * Ppad + p;
+    int sc = 0;
+    if (!tipA) sc += __ldg(scl + (int64_t)(it.a_id - n_rows) * Ppad + p);
+    if (!tipB) sc += __ldg(scl + (int64_t)(it.b_id - n_rows) * Ppad + p);
+    const double w = weights[p];
+    double a[16], b[16];  // operand columns: category by category below, all loads issued up front
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      a[e] = tipA ? ((mA >> (e & 3) & 1) ? 1.0 : 0.0) : __ldg(srcA + (int64_t)e * Ppad);
+      b[e] = tipB ? ((mB >> (e & 3) & 1) ? 1.0 : 0.0) : __ldg(srcB + (int64_t)e * Ppad);
+    }
+    if (tl == 0) __syncthreads();  // the table
+    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        double l = 0.0, rr = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          l = fma(a[r * 4 + i] * mpi[i], mU[i * 4 + k], l);
+          rr = fma(mUinv[k * 4 + i], b[r * 4 + i], rr);
+        }
+        const double sv = l * rr;
+        l0 = fma(sv, tab[0][r * 4 + k], l0);
+        l1 = fma(sv, tab[1][r * 4 + k], l1);
+        l2 = fma(sv, tab[2][r * 4 + k], l2);
+      }
+    }
+    if (w != 0.0) {
+      const double inv = 1.0 / l0, q1 = l1 * inv;
+      v0 += w * (log(l0 * 0.25) + sc * SM_LOG_MINLH);
+      v1 += w * q1;
+      v2 += w * (l2 * inv - q1 * q1);
+    }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -1054,7 +1060,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   idx.alloc((size_t)B * n_br);
   const int bpi = (int)(Ppad / (SM_THREADS / R));
   // blocks per branch of the launch that leaves the derivative-sum shares (DNA, large batches: opt_step4_kernel)
-  const int bpi2 = (K == 4 && R == 4) ? (int)(Ppad / OPT4_THREADS) : bpi;
+  const int bpi2 = (K == 4 && R == 4) ? (int)(Ppad / (OPT4_THREADS * OPT4_TILES)) : bpi;
   dpart.alloc((size_t)B * 3 * bpi);
   tickets.alloc((size_t)B);
   PLG_CUDA(cudaMemsetAsync(tickets.p, 0, (size_t)B * sizeof(unsigned int), 0));
