@@ -131,7 +131,8 @@ __device__ __forceinline__ void wm_stack_load(const double *lv, int lane, double
 // A pattern's entries sit in the four lanes of a quad: one vote per pattern group.  The four lanes
 // of a quad would keep identical counters for their four groups; each lane keeps only the one its
 // own site term needs (group jq = lane & 3).  (A warp vote in front of the four ballots -- skip them
-// unless some lane holds an all-small group -- measured slower: 5.17 vs 4.90 ms.)
+// unless some lane holds an all-small group -- measured slower: 5.17 vs 4.90 ms; testing the ballot's
+// own result for a zero nibble costs no vote.)
 __device__ __forceinline__ void wm_rescale(double (&n)[WM_V], int &sc, int lane) {
   int hi[4];
 #pragma unroll
@@ -141,10 +142,15 @@ __device__ __forceinline__ void wm_rescale(double (&n)[WM_V], int &sc, int lane)
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     const unsigned int big = __ballot_sync(0xffffffffu, hi[j] >= 0x2FF00000);
-    if (((big >> (lane & 28)) & 15u) == 0u) {
+    // `big` is the same in every lane: a quad needs the factor iff its nibble is 0.  The common case -- no
+    // nibble is 0 -- is a UNIFORM branch around the multiplies (predicated off they still took an issue
+    // slot each: 9 % of the walk's instructions in profiles/r2q_walk4m_ncu.txt)
+    if ((big - 0x11111111u) & ~big & 0x88888888u) {
+      if (((big >> (lane & 28)) & 15u) == 0u) {
 #pragma unroll
-      for (int r = 0; r < 4; r++) n[r * 4 + j] *= TWO256;
-      sc += (j == (lane & 3)) ? 1 : 0;
+        for (int r = 0; r < 4; r++) n[r * 4 + j] *= TWO256;
+        sc += (j == (lane & 3)) ? 1 : 0;
+      }
     }
   }
 }
