@@ -648,8 +648,10 @@ opt_step_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_ro
 // generic kernel above gives a thread one (pattern, category): 8 loads of 64-byte runs per operand and a
 // block prologue (branch length -> exp -> log -> exp) in front of them; the launch list of a 256-tree
 // batch had it at 1.6 TB/s against 4.6 for clv4_kernel (profiles/launches_r2w.csv).  Here every thread
-// issues its 32 column loads first, the first 16 threads make the table meanwhile, and no sum table is
-// stored.
+// issues its column loads first, the first 16 threads make the table meanwhile, and no sum table is
+// stored.  The eigensystem arrives BY VALUE (kernel parameters live in the constant bank, so U, U^-1 and pi
+// are immediate operands of the FMAs: the first version read them from shared memory and executed ~900
+// instructions per pattern tile for ~280 of arithmetic, issue-bound at 2.9 TB/s -- profiles/r3e_*).
 #ifndef PLG_OPT4_MINB
 #define PLG_OPT4_MINB 4
 #endif
@@ -658,14 +660,17 @@ constexpr int OPT4_THREADS = 128;
 #define PLG_OPT4_TILES 2
 #endif
 constexpr int OPT4_TILES = PLG_OPT4_TILES;  // (Ppad is a multiple of 256)
+struct Eigen4 {
+  double piU[16];   // pi_i U[i][k]
+  double Uinv[16];  // [k][i]
+  double g[16];     // -eval[k] * rate[r], [r][k]
+};
 __global__ void __launch_bounds__(OPT4_THREADS, PLG_OPT4_MINB)
 opt_step4_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
-                 const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
-                 const ModelDev *__restrict__ model, const double *__restrict__ clv, const int *__restrict__ scl,
-                 const double *__restrict__ weights, const double *__restrict__ brlen, double *__restrict__ dpart,
-                 const int *__restrict__ active) {
+                 const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks, const Eigen4 eg,
+                 const double *__restrict__ clv, const int *__restrict__ scl, const double *__restrict__ weights,
+                 const double *__restrict__ brlen, double *__restrict__ dpart, const int *__restrict__ active) {
   __shared__ double tab[3][16];
-  __shared__ double mU[16], mUinv[16], mpi[4];
   __shared__ double red[3][OPT4_THREADS / 32];
   const int item = blockIdx.x / blocks_per_item;
   const OptItem it = items[item];
@@ -673,45 +678,51 @@ opt_step4_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_r
   if (threadIdx.x < 16) {
     const double z = fmin(fmax(exp(-brlen[it.branch]), PLL_ZMIN), PLL_ZMAX);
     const double lz = log(fmax(z, PLL_ZMIN));
-    const double g = -model->eval[threadIdx.x & 3] * model->rates[threadIdx.x >> 2];
+    const double g = eg.g[threadIdx.x];
     const double e = exp(g * lz);
     tab[0][threadIdx.x] = e; tab[1][threadIdx.x] = g * e; tab[2][threadIdx.x] = g * g * e;
-    mU[threadIdx.x] = model->U[threadIdx.x];
-    mUinv[threadIdx.x] = model->Uinv[threadIdx.x];
-    if (threadIdx.x < 4) mpi[threadIdx.x] = model->freqs[threadIdx.x];
   }
-  const bool tipA = it.a_id < n_rows, tipB = it.b_id < n_rows;
+  const bool tipA = it.a_id < n_rows, tipB = it.b_id < n_rows;  // (block-uniform)
   double v0 = 0.0, v1 = 0.0, v2 = 0.0;
   // OPT4_TILES tiles of 128 patterns per block: the prologue above (item, branch length, exp / log / exp) is
   // a chain of dependent global loads and transcendental calls as long as a tile's own loads
 #pragma unroll 1
   for (int tl = 0; tl < OPT4_TILES; tl++) {
     const int64_t p = ((int64_t)(blockIdx.x - item * blocks_per_item) * OPT4_TILES + tl) * OPT4_THREADS + threadIdx.x;
-    const unsigned int mA = tipA ? masks[codes[(int64_t)it.a_id * Ppad + p]] : 0u;
-    const unsigned int mB = tipB ? masks[codes[(int64_t)it.b_id * Ppad + p]] : 0u;
-    const double *srcA = clv + (int64_t)(tipA ? 0 : it.a_id - n_rows) * 16 * Ppad + p;
-    const double *srcB = clv + (int64_t)(tipB ? 0 : it.b_id - n_rows) * 16 * Ppad + p;
+    double a[16], b[16];
     int sc = 0;
-    if (!tipA) sc += __ldg(scl + (int64_t)(it.a_id - n_rows) * Ppad + p);
-    if (!tipB) sc += __ldg(scl + (int64_t)(it.b_id - n_rows) * Ppad + p);
-    const double w = weights[p];
-    double a[16], b[16];  // operand columns: category by category below, all loads issued up front
+    if (tipA) {
+      const unsigned int m = masks[codes[(int64_t)it.a_id * Ppad + p]];
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
-      a[e] = tipA ? ((mA >> (e & 3) & 1) ? 1.0 : 0.0) : __ldg(srcA + (int64_t)e * Ppad);
-      b[e] = tipB ? ((mB >> (e & 3) & 1) ? 1.0 : 0.0) : __ldg(srcB + (int64_t)e * Ppad);
+      for (int e = 0; e < 16; e++) a[e] = (m >> (e & 3) & 1) ? 1.0 : 0.0;
+    } else {
+      const double *src = clv + (int64_t)(it.a_id - n_rows) * 16 * Ppad + p;
+#pragma unroll
+      for (int e = 0; e < 16; e++) a[e] = __ldg(src + (int64_t)e * Ppad);
+      sc += __ldg(scl + (int64_t)(it.a_id - n_rows) * Ppad + p);
     }
+    if (tipB) {
+      const unsigned int m = masks[codes[(int64_t)it.b_id * Ppad + p]];
+#pragma unroll
+      for (int e = 0; e < 16; e++) b[e] = (m >> (e & 3) & 1) ? 1.0 : 0.0;
+    } else {
+      const double *src = clv + (int64_t)(it.b_id - n_rows) * 16 * Ppad + p;
+#pragma unroll
+      for (int e = 0; e < 16; e++) b[e] = __ldg(src + (int64_t)e * Ppad);
+      sc += __ldg(scl + (int64_t)(it.b_id - n_rows) * Ppad + p);
+    }
+    const double w = weights[p];
     if (tl == 0) __syncthreads();  // the table
     double l0 = 0.0, l1 = 0.0, l2 = 0.0;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        double l = 0.0, rr = 0.0;
+        double l = a[r * 4] * eg.piU[k], rr = eg.Uinv[k * 4] * b[r * 4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          l = fma(a[r * 4 + i] * mpi[i], mU[i * 4 + k], l);
-          rr = fma(mUinv[k * 4 + i], b[r * 4 + i], rr);
+        for (int i = 1; i < 4; i++) {
+          l = fma(a[r * 4 + i], eg.piU[i * 4 + k], l);
+          rr = fma(eg.Uinv[k * 4 + i], b[r * 4 + i], rr);
         }
         const double sv = l * rr;
         l0 = fma(sv, tab[0][r * 4 + k], l0);
@@ -1061,6 +1072,13 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   const int bpi = (int)(Ppad / (SM_THREADS / R));
   // blocks per branch of the launch that leaves the derivative-sum shares (DNA, large batches: opt_step4_kernel)
   const int bpi2 = (K == 4 && R == 4) ? (int)(Ppad / (OPT4_THREADS * OPT4_TILES)) : bpi;
+  Eigen4 eigen4;
+  if (K == 4 && R == 4)
+    for (int e = 0; e < 16; e++) {
+      eigen4.piU[e] = model.h.freqs[e >> 2] * model.h.U[e];  // [i][k]: pi_i U[i][k]
+      eigen4.Uinv[e] = model.h.Uinv[e];
+      eigen4.g[e] = -model.h.eval[e & 3] * model.h.rates[e >> 2];
+    }
   dpart.alloc((size_t)B * 3 * bpi);
   tickets.alloc((size_t)B);
   PLG_CUDA(cudaMemsetAsync(tickets.p, 0, (size_t)B * sizeof(unsigned int), 0));
@@ -1069,6 +1087,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   std::vector<int> h_idx, h_flags;
   std::vector<LikEval> h_evals;
   std::vector<double> h_brlen, h_lnl;
+  StageTimer tm;
   for (int64_t t0 = 0; t0 < n_trees; t0 += B) {
     const int64_t cnt = std::min(B, n_trees - t0);
     std::vector<TreePlan> plans(cnt);
@@ -1108,6 +1127,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
     }
     h_flags.assign((size_t)2 * cnt, 0);
     for (int64_t i = 0; i < cnt; i++) h_flags[i] = 1;  // active; changed = 0
+    tm.lap("  smooth plan");
     PLG_CUDA(cudaMemcpy(d_ops.p, h_ops.data(), h_ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(d_items.p, h_items.data(), h_items.size() * sizeof(OptItem), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(idx.p, h_idx.data(), h_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -1117,6 +1137,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
     int *active = flags.p, *changed = flags.p + cnt;
     cudaStream_t st = 0;
     const bool fused = cnt <= 4;
+    tm.lap("  smooth upload");
     F::pmatrices(aln, model, brlen.p, nullptr, cnt * n_br, pmat.p, tiptab.p, st);
     for (int j = 0; j < n_inner; j++)
       F::updates(aln, model, d_ops.p + down_off[j], down_off[j + 1] - down_off[j], pmat.p, tiptab.p, clv.p, scl.p, st);
@@ -1134,7 +1155,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
                 aln.weights.p, brlen.p, dpart.p, active, changed, tickets.p, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
           else if constexpr (K == 4 && R == 4)
             opt_step4_kernel<<<(unsigned)(no * bpi2), OPT4_THREADS, 0, st>>>(
-                its, bpi2, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, aln.weights.p, brlen.p,
+                its, bpi2, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, eigen4, clv.p, scl.p, aln.weights.p, brlen.p,
                 dpart.p, active);
           else
             opt_step_kernel<K, R, false><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
@@ -1155,9 +1176,11 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
     }
     F::evals(aln, model, d_evals.p, cnt, pmat.p, tiptab.p, clv.p, scl.p, partial.p, lnl.p, st);
     PLG_CUDA(cudaGetLastError());
+    tm.lap("  smooth enqueue");
     h_lnl.resize(cnt);
     PLG_CUDA(cudaMemcpy(h_lnl.data(), lnl.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
     PLG_CUDA(cudaMemcpy(h_brlen.data(), brlen.p, (size_t)cnt * n_br * 8, cudaMemcpyDeviceToHost));
+    tm.lap("  smooth wait+D2H");
     for (int64_t i = 0; i < cnt; i++) {
       out_lnl[t0 + i] = h_lnl[i];
       UTree &t = trees[t0 + i];
