@@ -1199,8 +1199,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
 namespace plg {
 
 // DNA x Gamma-4, one tree: the whole smoothing program in one cooperative launch (pll_smooth1.cuh).
-// Returns false when the grid cannot be co-resident (very long alignments): the caller takes the
-// lockstep program instead.
+// Returns false when the device cannot launch cooperatively: the caller takes the lockstep program instead.
 static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const std::vector<int32_t> &tip_rows,
                     int max_passes, double *out_lnl) {
   struct Scratch {
@@ -1221,8 +1220,10 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
     sc.max_blocks = coop ? per_sm * sms : 0;
   }
   const int64_t Ppad = aln.Ppad;
-  const int n_blocks = (int)(Ppad / S1_THREADS);
-  if (n_blocks > sc.max_blocks) return false;
+  if (sc.max_blocks < 1) return false;
+  // co-resident grid; a block takes every gridDim.x-th tile of 128 patterns
+  int n_blocks = (int)std::min<int64_t>(Ppad / S1_THREADS, sc.max_blocks);
+  if (const char *e = getenv("PLG_S1_MAX_BLOCKS")) n_blocks = std::max(1, std::min(n_blocks, atoi(e)));  // tests: several tiles per block
   const int n = tree.n_tips, n_inner = n - 2, n_br = 2 * n - 3;
   TreePlan plan = plan_tree(tree, tip_rows, aln.n_rows, 0, 0, 0);
   std::vector<S1Act> acts;

@@ -14,6 +14,10 @@
 // moved branch's P-matrix is recomputed by every block into its own shared memory for immediate use;
 // block 0 also publishes it for the later steps (one barrier later at the earliest).
 //
+// A block covers tiles blockIdx.x, blockIdx.x + gridDim.x, ... of 128 patterns, so any alignment length
+// runs on a co-resident grid (a curvature-guard retry recomputes the sum-table columns instead of keeping
+// them in registers across the barrier).
+//
 // Loads of data written inside the kernel (vectors, counters, matrices) are ld.global.cg: the
 // read-only (.nc) path the other kernels use is not coherent with stores of the same launch.
 #pragma once
@@ -113,8 +117,7 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
   __shared__ double tab[3][16];
   __shared__ double red[3][S1_THREADS / 32];
   __shared__ double tot[3];
-  const int64_t p = (int64_t)blockIdx.x * S1_THREADS + threadIdx.x;
-  const double w = weights[p];
+  const int n_tiles = (int)(Ppad / S1_THREADS);
   if (threadIdx.x < 16) {
     mU[threadIdx.x] = model->U[threadIdx.x];          // [i][k]  (LIK_MAX_STATES-strided rows are not used: K = 4 packs them)
     mUinv[threadIdx.x] = model->Uinv[threadIdx.x];    // [k][j]
@@ -128,45 +131,76 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
     s1_stage(smA, op.a < n_rows, op.pa, cur_branch, cur_pm, cur_tt, pmat, tiptab);
     s1_stage(smB, op.b < n_rows, op.pb, cur_branch, cur_pm, cur_tt, pmat, tiptab);
     __syncthreads();
-    double v[16];
-    int sc = 0;
-    s1_operand<false>(smA, op.a, n_rows, p, Ppad, codes, clv, scl, v, sc);
-    s1_operand<true>(smB, op.b, n_rows, p, Ppad, codes, clv, scl, v, sc);
-    int hi = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t p = (int64_t)tile * S1_THREADS + threadIdx.x;
+      double v[16];
+      int sc = 0;
+      s1_operand<false>(smA, op.a, n_rows, p, Ppad, codes, clv, scl, v, sc);
+      s1_operand<true>(smB, op.b, n_rows, p, Ppad, codes, clv, scl, v, sc);
+      int hi = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) hi = max(hi, __double2hiint(v[i]));
-    if (hi < 0x2FF00000) {  // every entry below 2^-256 (values are >= 0): rescale the column, count it
+      for (int i = 0; i < 16; i++) hi = max(hi, __double2hiint(v[i]));
+      if (hi < 0x2FF00000) {  // every entry below 2^-256 (values are >= 0): rescale the column, count it
 #pragma unroll
-      for (int i = 0; i < 16; i++) v[i] *= 1.15792089237316195423570985008687907853269984665640564039457584007913129639936e77;
-      sc += 1;
+        for (int i = 0; i < 16; i++) v[i] *= 1.15792089237316195423570985008687907853269984665640564039457584007913129639936e77;
+        sc += 1;
+      }
+      double *dst = clv + (int64_t)(op.dst - n_rows) * 16 * Ppad + p;
+#pragma unroll
+      for (int i = 0; i < 16; i++) dst[(int64_t)i * Ppad] = v[i];
+      scl[(int64_t)(op.dst - n_rows) * Ppad + p] = sc;
     }
-    double *dst = clv + (int64_t)(op.dst - n_rows) * 16 * Ppad + p;
-#pragma unroll
-    for (int i = 0; i < 16; i++) dst[(int64_t)i * Ppad] = v[i];
-    scl[(int64_t)(op.dst - n_rows) * Ppad + p] = sc;
     __syncthreads();  // smA / smB are restaged by the next step
   };
 
-  // sums (lnL, d1, d2) of the sum-table columns sv at log z = lz, identical in every thread of the grid
-  auto sums = [&](const double (&sv)[16], int sc, double lz, double &s0, double &s1, double &s2) {
+  // sum-table column of pattern p for the branch between operands a and b
+  auto column = [&](int a_id, int b_id, int64_t p, double (&sv)[16], int &sc) {
+    double A[16], B[16];
+    sc = 0;
+    s1_raw(a_id, n_rows, p, Ppad, codes, masks, clv, scl, A, sc);
+    s1_raw(b_id, n_rows, p, Ppad, codes, masks, clv, scl, B, sc);
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        double l = 0.0, rr = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          l = fma(A[r * 4 + i] * mpi[i], mU[i * 4 + k], l);
+          rr = fma(mUinv[k * 4 + i], B[r * 4 + i], rr);
+        }
+        sv[r * 4 + k] = l * rr;
+      }
+  };
+
+  // sums (lnL, d1, d2) over all patterns for the branch between a and b at log z = lz, identical in every
+  // thread of the grid
+  auto sums = [&](int a_id, int b_id, double lz, double &s0, double &s1, double &s2) {
     if (threadIdx.x < 16) {
       const double g = mg[threadIdx.x], e = exp(g * lz);
       tab[0][threadIdx.x] = e; tab[1][threadIdx.x] = g * e; tab[2][threadIdx.x] = g * g * e;
     }
     __syncthreads();
-    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-#pragma unroll
-    for (int e = 0; e < 16; e++) {
-      l0 = fma(sv[e], tab[0][e], l0);
-      l1 = fma(sv[e], tab[1][e], l1);
-      l2 = fma(sv[e], tab[2][e], l2);
-    }
     double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-    if (w != 0.0) {
-      const double inv = 1.0 / l0, q1 = l1 * inv;
-      v0 = w * (log(l0 * 0.25) + sc * SM_LOG_MINLH);
-      v1 = w * q1;
-      v2 = w * (l2 * inv - q1 * q1);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t p = (int64_t)tile * S1_THREADS + threadIdx.x;
+      const double w = weights[p];
+      double sv[16];
+      int sc;
+      column(a_id, b_id, p, sv, sc);
+      double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        l0 = fma(sv[e], tab[0][e], l0);
+        l1 = fma(sv[e], tab[1][e], l1);
+        l2 = fma(sv[e], tab[2][e], l2);
+      }
+      if (w != 0.0) {
+        const double inv = 1.0 / l0, q1 = l1 * inv;
+        v0 += w * (log(l0 * 0.25) + sc * SM_LOG_MINLH);
+        v1 += w * q1;
+        v2 += w * (l2 * inv - q1 * q1);
+      }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -203,26 +237,6 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
     __syncthreads();  // tab / red / tot are reused by the next evaluation
   };
 
-  // sum-table column of this thread's pattern for the branch between operands a and b (registers)
-  auto column = [&](int a_id, int b_id, double (&sv)[16], int &sc) {
-    double A[16], B[16];
-    sc = 0;
-    s1_raw(a_id, n_rows, p, Ppad, codes, masks, clv, scl, A, sc);
-    s1_raw(b_id, n_rows, p, Ppad, codes, masks, clv, scl, B, sc);
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        double l = 0.0, rr = 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          l = fma(A[r * 4 + i] * mpi[i], mU[i * 4 + k], l);
-          rr = fma(mUinv[k * 4 + i], B[r * 4 + i], rr);
-        }
-        sv[r * 4 + k] = l * rr;
-      }
-  };
-
   for (int i = 0; i < n_down; i++) update(acts[i]);
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   for (int pass = 0; pass < max_passes; pass++) {
@@ -231,13 +245,10 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
       const S1Act op = acts[n_down + i];
       if (op.kind == 0) { update(op); continue; }
       // one makenewz step (libpll: optimise the branch with maxiter = 1), as newton_step_block
-      double sv[16];
-      int sc;
-      column(op.a, op.b, sv, sc);
       const double z0 = exp(-__ldcg(brlen + op.branch));
       double z = fmin(fmax(z0, PLL_ZMIN), PLL_ZMAX), zprev = z;
       for (int guard = 0; guard < 64; guard++) {  // "bad curvature: shorten the branch"
-        sums(sv, sc, log(fmax(z, PLL_ZMIN)), s0, s1, s2);
+        sums(op.a, op.b, log(fmax(z, PLL_ZMIN)), s0, s1, s2);
         if (s2 >= 0.0 && z < PLL_ZMAX) zprev = z = 0.37 * z + 0.63;
         else break;
       }
@@ -268,12 +279,9 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
   }
   {  // lnL at the final lengths
     const S1Act op = acts[n_down + n_pass];
-    double sv[16];
-    int sc;
-    column(op.a, op.b, sv, sc);
     grid.sync();  // (block 0's last brlen store)
     const double z = fmin(fmax(exp(-__ldcg(brlen + op.branch)), PLL_ZMIN), PLL_ZMAX);
-    sums(sv, sc, log(fmax(z, PLL_ZMIN)), s0, s1, s2);
+    sums(op.a, op.b, log(fmax(z, PLL_ZMIN)), s0, s1, s2);
     if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = s0;
   }
 }

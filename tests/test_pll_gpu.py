@@ -324,14 +324,19 @@ def test_batched_getLogLikelihood_equals_per_tree_path(monkeypatch):
     pm.close(); ali.close()
 
 
-@pytest.mark.parametrize("n,S,signal", [(3, 200, True), (4, 64, True), (5, 300, True), (9, 1500, True), (33, 2500, True),
-                                        (10, 12, False), (10, 40, False), (7, 25, False), (12, 55, False)])
-def test_single_launch_smoother_equals_host_loop(n, S, signal, monkeypatch):
+@pytest.mark.parametrize("n,S,signal,max_blocks", [(3, 200, True, 0), (4, 64, True, 0), (5, 300, True, 0), (9, 1500, True, 0),
+                                                   (33, 2500, True, 0), (10, 12, False, 0), (10, 40, False, 0), (7, 25, False, 0),
+                                                   (12, 55, False, 0), (9, 1500, True, 1), (33, 2500, True, 3), (14, 3000, False, 2)])
+def test_single_launch_smoother_equals_host_loop(n, S, signal, max_blocks, monkeypatch):
     """The per-handle getLogLikelihood of a DNA tree -- ONE cooperative launch that walks the whole
     smoothing program with a grid barrier per Newton evaluation (pll_smooth1.cuh) -- against the literal
     per-branch host loop: smallest trees, alignments of a few patterns (one block), several blocks, and
-    random sequences on few sites, where the bad-curvature guard retries and the z clamps do the work.
-    lnL, branch lengths, and the oracle at the returned lengths."""
+    random sequences on few sites, where the bad-curvature guard retries and the z clamps do the work;
+    max_blocks caps the grid (PLG_S1_MAX_BLOCKS) so that a block walks several 128-pattern tiles, as on
+    alignments too long for one co-resident tile per block.  lnL, branch lengths, and the oracle at the
+    returned lengths."""
+    if max_blocks:
+        monkeypatch.setenv("PLG_S1_MAX_BLOCKS", str(max_blocks))
     from pylogeny_b200 import _lib, alignment, libpllWrapper as W, likelihood, neighbourhood as nbh, pll
     rng = np.random.default_rng(1000 * n + S)
     if signal:
