@@ -130,7 +130,8 @@ int score_tbr_lik(LikAln &a, const Model &m, int n_tips, const int32_t *desc, co
   size_t free_b = 0, total_b = 0;
   if (need_all > held) PLG_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t budget = need_all <= held ? need_all : std::min<size_t>((free_b + held) / 2, (size_t)80 << 30);
-  const int64_t max_slots = std::max<int64_t>(8 * n_tips, (int64_t)(budget / slot_bytes));
+  int64_t max_slots = std::max<int64_t>(8 * n_tips, (int64_t)(budget / slot_bytes));
+  if (const char *e = std::getenv("PLG_TBR_MAX_SLOTS")) max_slots = std::max<int64_t>(1, atoll(e));  // tests: several chunks of bisections
   tm.lap("tbr moves+mem");
   LikProgram p;
   std::vector<double> lnl;

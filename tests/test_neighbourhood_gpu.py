@@ -145,6 +145,14 @@ def test_tbr_20_states_fused_steps_and_pair_grid(n, P, scale, monkeypatch):
         parts = [nbh.score_likelihood(a, m, d, br, move_type=nbh.MOVE_TBR, shard=(i, 3), want_moves=False)[1] for i in range(3)]
         got = np.concatenate([parts[i][M * i // 3:M * (i + 1) // 3] for i in range(3)])
         np.testing.assert_array_equal(got, lnl)
+        # the neighbourhood cut into chunks of bisections that fit a (tiny) memory budget: same numbers
+        for mode in ("1", "0"):
+            monkeypatch.setenv("PLG_TBR20", mode)
+            monkeypatch.setenv("PLG_TBR_MAX_SLOTS", str(12 * n))
+            _, chunked = nbh.score_likelihood(a, m, d, br, move_type=nbh.MOVE_TBR, want_moves=False)
+            monkeypatch.delenv("PLG_TBR_MAX_SLOTS")
+            np.testing.assert_array_equal(chunked, lnl if mode == "1" else lnl0)
+        monkeypatch.delenv("PLG_TBR20")
     a.close(); m.close()
 
 
