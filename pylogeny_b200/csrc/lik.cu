@@ -1006,6 +1006,126 @@ void dna4_updates(const LikAln &a, const Model &m, const LikOpF *d_ops, int64_t 
   prof_end(PROF_CLV_UPDATE, st, (double)n * 3.0 * 132.0 * (double)a.P, (double)n * (double)a.P);
 }
 
+// Fused re-orientation + sum-table pass (lik.h ClvOptOp).  Block = 128 threads x 2 tiles of 128 patterns: the
+// tile / block mapping, the arithmetic and the order of the sums are those of opt_step4_kernel (pll_api.cu),
+// so the derivative-sum shares are bit-identical to the unfused pair of launches.
+constexpr double PLLF_ZMIN = 1.0e-15, PLLF_ZMAX = 1.0 - 1.0e-6;
+__global__ void __launch_bounds__(D4_THREADS, 4)
+clvopt4_kernel(const ClvOptOp *__restrict__ ops, int blocks_per_op, int n_rows, int64_t Ppad,
+               const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
+               const double *__restrict__ weights, const Eigen4 eg, const double *__restrict__ pmat,
+               const double *__restrict__ tiptab, double *__restrict__ clv, int *__restrict__ scl,
+               const double *__restrict__ brlen, const int *__restrict__ active, double *__restrict__ dpart) {
+  static_assert(D4_THREADS == 128, "tile mapping of opt_step4_kernel");
+  __shared__ __align__(16) double smA[256];
+  __shared__ __align__(16) double smB[256];
+  __shared__ double tab[3][16];
+  __shared__ double red[3][D4_THREADS / 32];
+  const int op_idx = blockIdx.x / blocks_per_op;
+  const int blk = blockIdx.x - op_idx * blocks_per_op;
+  const ClvOptOp op = ops[op_idx];
+  const bool act = active[op.tree] != 0;
+  d4_stage(smA, op.a < n_rows, op.pa, pmat, tiptab);
+  d4_stage(smB, op.b < n_rows, op.pb, pmat, tiptab);
+  if (act && threadIdx.x < 16) {
+    const double z = fmin(fmax(exp(-brlen[op.branch]), PLLF_ZMIN), PLLF_ZMAX);
+    const double lz = log(fmax(z, PLLF_ZMIN));
+    const double g = eg.g[threadIdx.x];
+    const double e = exp(g * lz);
+    tab[0][threadIdx.x] = e; tab[1][threadIdx.x] = g * e; tab[2][threadIdx.x] = g * g * e;
+  }
+  __syncthreads();
+  const bool tipO = op.other < n_rows;
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+#pragma unroll 1
+  for (int tl = 0; tl < 2; tl++) {
+    const int64_t p = ((int64_t)blk * 2 + tl) * D4_THREADS + threadIdx.x;
+    double v[16];
+    int sc = 0;
+    d4_operand<false>(smA, op.a, op.pa, n_rows, p, Ppad, codes, masks, clv, scl, v, sc);
+    d4_operand<true>(smB, op.b, op.pb, n_rows, p, Ppad, codes, masks, clv, scl, v, sc);
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) mx = fmax(mx, fabs(v[i]));
+    if (mx < MINLH) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) v[i] *= TWO256;
+      sc += 1;
+    }
+    double *dst = clv + (int64_t)(op.dst - n_rows) * 16 * Ppad + p;
+#pragma unroll
+    for (int i = 0; i < 16; i++) dst[(int64_t)i * Ppad] = v[i];
+    scl[(int64_t)(op.dst - n_rows) * Ppad + p] = sc;
+    if (!act) continue;
+    double a[16];
+    if (tipO) {
+      const unsigned int m = masks[codes[(int64_t)op.other * Ppad + p]];
+#pragma unroll
+      for (int e = 0; e < 16; e++) a[e] = (m >> (e & 3) & 1) ? 1.0 : 0.0;
+    } else {
+      const double *src = clv + (int64_t)(op.other - n_rows) * 16 * Ppad + p;
+#pragma unroll
+      for (int e = 0; e < 16; e++) a[e] = __ldg(src + (int64_t)e * Ppad);
+      sc += __ldg(scl + (int64_t)(op.other - n_rows) * Ppad + p);
+    }
+    const double w = weights[p];
+    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        double l = a[r * 4] * eg.piU[k], rr = eg.Uinv[k * 4] * v[r * 4];
+#pragma unroll
+        for (int i = 1; i < 4; i++) {
+          l = fma(a[r * 4 + i], eg.piU[i * 4 + k], l);
+          rr = fma(eg.Uinv[k * 4 + i], v[r * 4 + i], rr);
+        }
+        const double sv = l * rr;
+        l0 = fma(sv, tab[0][r * 4 + k], l0);
+        l1 = fma(sv, tab[1][r * 4 + k], l1);
+        l2 = fma(sv, tab[2][r * 4 + k], l2);
+      }
+    }
+    if (w != 0.0) {
+      const double inv = 1.0 / l0, q1 = l1 * inv;
+      v0 += w * (log(l0 * 0.25) + sc * LOG_MINLH);
+      v1 += w * q1;
+      v2 += w * (l2 * inv - q1 * q1);
+    }
+  }
+  if (!act) return;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v0 += __shfl_down_sync(0xffffffffu, v0, d);
+    v1 += __shfl_down_sync(0xffffffffu, v1, d);
+    v2 += __shfl_down_sync(0xffffffffu, v2, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = v0; red[1][threadIdx.x >> 5] = v1; red[2][threadIdx.x >> 5] = v2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < D4_THREADS / 32; i++) t += red[threadIdx.x][i];
+    dpart[((int64_t)op.dslot * 3 + threadIdx.x) * blocks_per_op + blk] = t;
+  }
+}
+
+void dna4_updates_opt(const LikAln &a, const Model &m, const ClvOptOp *d_ops, int64_t n, const double *d_pmat,
+                      const double *d_tiptab, double *d_clv, int *d_scl, const Eigen4 &eg, const double *d_brlen,
+                      const int *d_active, double *d_dpart, cudaStream_t st) {
+  if (n <= 0) return;
+  (void)m;
+  const int64_t bpo = a.Ppad / (2 * D4_THREADS);
+  prof_begin(PROF_CLV_UPDATE, st);
+  clvopt4_kernel<<<(unsigned)(n * bpo), D4_THREADS, 0, st>>>(d_ops, (int)bpo, a.n_rows, a.Ppad, a.codes.p, a.masks.p,
+                                                            a.weights.p, eg, d_pmat, d_tiptab, d_clv, d_scl, d_brlen,
+                                                            d_active, d_dpart);
+  count_launch();
+  prof_end(PROF_CLV_UPDATE, st, (double)n * 4.0 * 132.0 * (double)a.P, (double)n * (double)a.P);
+}
+
 void dna4_evals(const LikAln &a, const Model &m, const LikEval *d_evals, int64_t n, const double *d_pmat,
                 const double *d_tiptab, const double *d_clv, const int *d_scl, double *d_partial, double *d_lnl,
                 cudaStream_t st) {

@@ -154,6 +154,23 @@ void dna4_updates(const LikAln &a, const Model &m, const LikOpF *d_ops, int64_t 
 void dna4_evals(const LikAln &a, const Model &m, const LikEval *d_evals, int64_t n, const double *d_pmat,
                 const double *d_tiptab, const double *d_clv, const int *d_scl, double *d_partial, double *d_lnl,
                 cudaStream_t st);
+// Batched branch-length smoothing, DNA x Gamma-4 (pll_api.cu): a re-orientation whose result is an end of the
+// branch the NEXT action optimises is fused with that action's sum-table pass -- the new vector goes
+// from the registers straight into the derivative sums (one 132-byte read per pattern less).
+struct Eigen4 {
+  double piU[16];   // pi_i U[i][k]
+  double Uinv[16];  // [k][i]
+  double g[16];     // -eval[k] * rate[r], [r][k]
+};
+struct ClvOptOp {
+  int dst, a, b, pa, pb;       // the update, as LikOp
+  int other, branch, tree;     // the branch's other end (operand id), its index, the tree's flag index
+  int dslot, pad0, pad1, pad2; // slot of the derivative-sum shares (index in the next step's item list)
+};
+// n fused ops; dpart[(dslot * 3 + j) * blocks_per_op + block], blocks_per_op = Ppad / 256
+void dna4_updates_opt(const LikAln &a, const Model &m, const ClvOptOp *d_ops, int64_t n, const double *d_pmat,
+                      const double *d_tiptab, double *d_clv, int *d_scl, const Eigen4 &eg, const double *d_brlen,
+                      const int *d_active, double *d_dpart, cudaStream_t st);
 // the same for 20 states x Gamma-4 (lik_aa.cuh); P-matrix stride 4 * 401, tip table 23 * 80 per entry,
 // partial: >= n * Ppad / 64 doubles
 void aa20_pmatrices(const LikAln &a, const Model &m, const double *d_brlen, const int *d_idx, int64_t n,

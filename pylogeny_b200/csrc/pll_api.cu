@@ -660,11 +660,7 @@ constexpr int OPT4_THREADS = 128;
 #define PLG_OPT4_TILES 2
 #endif
 constexpr int OPT4_TILES = PLG_OPT4_TILES;  // (Ppad is a multiple of 256)
-struct Eigen4 {
-  double piU[16];   // pi_i U[i][k]
-  double Uinv[16];  // [k][i]
-  double g[16];     // -eval[k] * rate[r], [r][k]
-};
+// (Eigen4: lik.h)
 __global__ void __launch_bounds__(OPT4_THREADS, PLG_OPT4_MINB)
 opt_step4_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_rows, int64_t Ppad,
                  const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks, const Eigen4 eg,
@@ -1027,6 +1023,7 @@ struct BatchScratch {
   DevBuf<typename F::Op> d_ops;
   DevBuf<OptItem> d_items;
   DevBuf<LikEval> d_evals;
+  DevBuf<ClvOptOp> d_fops;
 };
 
 template <typename F>
@@ -1053,6 +1050,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   DevBuf<Op> &d_ops = sc_.d_ops;
   DevBuf<OptItem> &d_items = sc_.d_items;
   DevBuf<LikEval> &d_evals = sc_.d_evals;
+  DevBuf<ClvOptOp> &d_fops = sc_.d_fops;
   clv.alloc((size_t)B * n_inner * RK * Ppad);
   scl.alloc((size_t)B * n_inner * Ppad);
   S.alloc(store_sumtable<K>() ? (size_t)B * RK * Ppad : 1);
@@ -1079,7 +1077,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
       eigen4.Uinv[e] = model.h.Uinv[e];
       eigen4.g[e] = -model.h.eval[e & 3] * model.h.rates[e >> 2];
     }
-  dpart.alloc((size_t)B * 3 * bpi);
+  dpart.alloc((size_t)2 * B * 3 * bpi);  // two halves, alternating by step (a fused re-orientation writes the NEXT step's)
   tickets.alloc((size_t)B);
   PLG_CUDA(cudaMemsetAsync(tickets.p, 0, (size_t)B * sizeof(unsigned int), 0));
   std::vector<Op> h_ops;
@@ -1105,14 +1103,36 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
       down_off[j + 1] = (int64_t)h_ops.size();
     }
     const int64_t pass_ops0 = (int64_t)h_ops.size();
+    // DNA, wide batches: a re-orientation whose result is the b end of the branch the tree's NEXT action
+    // optimises runs fused with that action's sum-table pass (lik.h ClvOptOp); such items come first in
+    // their step's list and skip the sum-table launch
+    const bool can_fuse = K == 4 && R == 4 && cnt > 4 && !getenv("PLG_PLL_NO_FUSE");
+    auto fuses = [&](int64_t i, int s) {
+      if (!can_fuse || s < 0 || s + 1 >= n_steps) return false;
+      const TreePlan::Act &a = plans[i].acts[s], &nx = plans[i].acts[s + 1];
+      return !a.is_opt && nx.is_opt && nx.it.b_id == a.op.dst;
+    };
+    std::vector<ClvOptOp> h_fops;
+    std::vector<int64_t> fop_off(n_steps + 1, 0), n_pre(n_steps, 0);
     for (int s = 0; s < n_steps; s++) {
+      for (int64_t i = 0; i < cnt; i++)  // items whose sums the previous step's fused launch leaves
+        if (plans[i].acts[s].is_opt && fuses(i, s - 1)) { h_items.push_back(plans[i].acts[s].it); h_idx.push_back(plans[i].acts[s].it.branch); }
+      n_pre[s] = (int64_t)h_items.size() - opt_off[s];
+      int64_t slot = 0;
       for (int64_t i = 0; i < cnt; i++) {
         const TreePlan::Act &a = plans[i].acts[s];
-        if (a.is_opt) { h_items.push_back(a.it); h_idx.push_back(a.it.branch); }
-        else h_ops.push_back(F::make(a.op));
+        if (a.is_opt) {
+          if (!fuses(i, s - 1)) { h_items.push_back(a.it); h_idx.push_back(a.it.branch); }
+        } else if (fuses(i, s)) {
+          const OptItem &it = plans[i].acts[s + 1].it;
+          h_fops.push_back({a.op.dst, a.op.a, a.op.b, a.op.pa, a.op.pb, it.a_id, it.branch, it.tree, (int)slot++, 0, 0, 0});
+        } else {
+          h_ops.push_back(F::make(a.op));
+        }
       }
       clv_off[s + 1] = (int64_t)h_ops.size() - pass_ops0;
       opt_off[s + 1] = (int64_t)h_items.size();
+      fop_off[s + 1] = (int64_t)h_fops.size();
     }
     for (int64_t i = 0; i < cnt; i++) h_evals.push_back(plans[i].eval);
     // start from the trees' current lengths (callers load default z = 0.9: useDefaultz, libpllWrapper.c:152;
@@ -1130,6 +1150,8 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
     tm.lap("  smooth plan");
     PLG_CUDA(cudaMemcpy(d_ops.p, h_ops.data(), h_ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(d_items.p, h_items.data(), h_items.size() * sizeof(OptItem), cudaMemcpyHostToDevice));
+    d_fops.alloc(std::max<size_t>(1, h_fops.size()));
+    if (!h_fops.empty()) PLG_CUDA(cudaMemcpy(d_fops.p, h_fops.data(), h_fops.size() * sizeof(ClvOptOp), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(idx.p, h_idx.data(), h_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(d_evals.p, h_evals.data(), h_evals.size() * sizeof(LikEval), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(brlen.p, h_brlen.data(), h_brlen.size() * 8, cudaMemcpyHostToDevice));
@@ -1143,28 +1165,34 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
       F::updates(aln, model, d_ops.p + down_off[j], down_off[j + 1] - down_off[j], pmat.p, tiptab.p, clv.p, scl.p, st);
     for (int pass = 0; pass < passes; pass++) {
       for (int s = 0; s < n_steps; s++) {
-        const int64_t nc = clv_off[s + 1] - clv_off[s], no = opt_off[s + 1] - opt_off[s];
+        const int64_t nc = clv_off[s + 1] - clv_off[s], no = opt_off[s + 1] - opt_off[s], nf = fop_off[s + 1] - fop_off[s];
+        double *dp_cur = dpart.p + (size_t)(s & 1) * B * 3 * bpi, *dp_next = dpart.p + (size_t)((s + 1) & 1) * B * 3 * bpi;
         if (nc) F::updates(aln, model, d_ops.p + pass_ops0 + clv_off[s], nc, pmat.p, tiptab.p, clv.p, scl.p, st);
+        if constexpr (K == 4 && R == 4)
+          if (nf) dna4_updates_opt(aln, model, d_fops.p + fop_off[s], nf, pmat.p, tiptab.p, clv.p, scl.p, eigen4, brlen.p, active, dp_next, st);
         if (no) {
           const OptItem *its = d_items.p + opt_off[s];
+          const int64_t npre = n_pre[s];  // their derivative-sum shares are already in dp_cur
           // a few trees: one launch per step (the last block of a branch finishes it: launch-bound regime);
           // many trees: two launches, no fences or tickets in the wide one
           if (fused)
             opt_step_kernel<K, R, true><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
                 its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
-                aln.weights.p, brlen.p, dpart.p, active, changed, tickets.p, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
-          else if constexpr (K == 4 && R == 4)
-            opt_step4_kernel<<<(unsigned)(no * bpi2), OPT4_THREADS, 0, st>>>(
-                its, bpi2, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, eigen4, clv.p, scl.p, aln.weights.p, brlen.p,
-                dpart.p, active);
+                aln.weights.p, brlen.p, dp_cur, active, changed, tickets.p, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
+          else if constexpr (K == 4 && R == 4) {
+            if (no > npre)
+              opt_step4_kernel<<<(unsigned)((no - npre) * bpi2), OPT4_THREADS, 0, st>>>(
+                  its + npre, bpi2, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, eigen4, clv.p, scl.p, aln.weights.p, brlen.p,
+                  dp_cur + (size_t)npre * 3 * bpi2, active);
+          }
           else
             opt_step_kernel<K, R, false><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
                 its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
-                aln.weights.p, brlen.p, dpart.p, active, changed, nullptr, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
+                aln.weights.p, brlen.p, dp_cur, active, changed, nullptr, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
           count_launch();
           if (!fused) {
             newton_kernel<K, R><<<(unsigned)no, SM_THREADS, 0, st>>>(its, bpi2, Ppad, aln.masks.p, model.d.p, S.p, Ssc.p,
-                                                                      aln.weights.p, brlen.p, dpart.p, active, changed,
+                                                                      aln.weights.p, brlen.p, dp_cur, active, changed,
                                                                       pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE,
                                                                       OptOperands{aln.n_rows, aln.codes.p, aln.masks.p, clv.p, scl.p});
             count_launch();

@@ -324,6 +324,24 @@ def test_batched_getLogLikelihood_equals_per_tree_path(monkeypatch):
     pm.close(); ali.close()
 
 
+def test_batched_smoother_fused_reorientation_is_bit_identical(monkeypatch):
+    """DNA batches of more than four trees run a re-orientation fused with the sum-table pass of the Newton
+    step that follows it on the same vector (lik.h ClvOptOp); PLG_PLL_NO_FUSE=1 keeps the two launches.
+    Same tile mapping, same arithmetic, same order of the sums: identical lnL and Newick strings."""
+    from pylogeny_b200 import libpllWrapper as W, pll
+    ali, d = _case(n=17, S=2100, seed=31)
+    labels = ali.getTaxa()
+    rng = np.random.default_rng(5)
+    newicks = [desc_to_newick(random_desc(rng, 17), labels) for _ in range(11)]
+    pm = pll.partitionModel(ali)
+    pm.createSimpleModel()
+    got = W.getLogLikelihoodBatch(ali.getPhylip(), newicks, pm.getFileName())
+    monkeypatch.setenv("PLG_PLL_NO_FUSE", "1")
+    want = W.getLogLikelihoodBatch(ali.getPhylip(), newicks, pm.getFileName())
+    assert list(got[0]) == list(want[0]) and list(got[1]) == list(want[1])
+    pm.close(); ali.close()
+
+
 @pytest.mark.parametrize("n,S,signal,max_blocks", [(3, 200, True, 0), (4, 64, True, 0), (5, 300, True, 0), (9, 1500, True, 0),
                                                    (33, 2500, True, 0), (10, 12, False, 0), (10, 40, False, 0), (7, 25, False, 0),
                                                    (12, 55, False, 0), (9, 1500, True, 1), (33, 2500, True, 3), (14, 3000, False, 2)])
