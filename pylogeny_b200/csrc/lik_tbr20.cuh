@@ -94,15 +94,50 @@ __device__ __forceinline__ void t20_cp16(double *smem_dst, const double *gsrc) {
 
 // This warp's (category r) rows of the op's stored operands for the 8 patterns at p0 -> one stage.
 // 20 rows x 64 bytes per operand = 80 16-byte pieces over 32 lanes; nothing passes through registers,
-// so T20_STAGES - 1 tiles are in flight per warp while one is being multiplied.
-__device__ __forceinline__ void t20_stage_issue(double *stage, const Tbr20Op &op, int n_rows, int r, int64_t p0,
-                                                int lane, int64_t Ppad, const double *__restrict__ clv) {
-  const int ids[3] = {op.a, op.b, op.b2};
+// so T20_STAGES - 1 tiles are in flight per warp while one is being multiplied.  The per-lane piece
+// offsets (global: row * Ppad + part, shared: row * 64 + part * 16 bytes) are computed ONCE per block:
+// in the first version this loop's address arithmetic was a third of the kernel's instructions
+// (profiles/r2o_tbr20_step_ncu.txt, source page).
+// A fragments of P[pm][r] like a20_load_p, but as loads the compiler may not hoist out of the tile loop
+__device__ __forceinline__ void t20_load_p_again(const double *__restrict__ pmat, int pm, int r, int lane, double (&a)[3][5]) {
+  const double *P = pmat + ((int64_t)pm * 4 + r) * 401;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 3; mt++) {
+    const int row = mt * 8 + g;
+#pragma unroll
+    for (int ks = 0; ks < 5; ks++) {
+      a[mt][ks] = 0.0;
+      if (row < 20) asm volatile("ld.global.nc.f64 %0, [%1];\n" : "=d"(a[mt][ks]) : "l"(P + row * 20 + ks * 4 + t));
+    }
+  }
+}
+
+struct T20Pieces {
+  int g[3];       // element offsets from (operand base + p0)
+  unsigned s[3];  // byte offsets inside an operand's 20 x 8 stage block
+  int n;          // pieces this lane copies (3 for lanes < 16, else 2)
+};
+__device__ __forceinline__ T20Pieces t20_pieces(int lane, int64_t Ppad) {
+  T20Pieces pc;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int i = lane + 32 * k;
+    pc.g[k] = (int)((i >> 2) * Ppad + (i & 3) * 2);
+    pc.s[k] = (unsigned)((i >> 2) * 64 + (i & 3) * 16);
+  }
+  pc.n = lane < 16 ? 3 : 2;
+  return pc;
+}
+__device__ __forceinline__ void t20_stage_issue(unsigned stage_s, const double *const (&base)[3], const T20Pieces &pc, int64_t p0) {
 #pragma unroll
   for (int o = 0; o < 3; o++) {
-    if (ids[o] < n_rows) continue;  // absent (-1) or a tip row (read from the codes)
-    const double *src = clv + ((int64_t)(ids[o] - n_rows) * 80 + r * 20) * Ppad + p0;
-    for (int i = lane; i < 80; i += 32) t20_cp16(stage + (o * 20 + (i >> 2)) * 8 + (i & 3) * 2, src + (int64_t)(i >> 2) * Ppad + (i & 3) * 2);
+    if (!base[o]) continue;  // absent operand, or a tip row (read from the codes)
+    const double *src = base[o] + p0;
+    const unsigned dst = stage_s + o * (20 * 64);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + pc.s[0]), "l"(src + pc.g[0]));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + pc.s[1]), "l"(src + pc.g[1]));
+    if (pc.n == 3) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + pc.s[2]), "l"(src + pc.g[2]));
   }
   asm volatile("cp.async.commit_group;\n" ::);
 }
@@ -124,13 +159,20 @@ tbr20_step_kernel(const Tbr20Op *__restrict__ ops, int n_ops, int n_rows, int64_
   const int64_t pbase = (int64_t)pb * A20_TILE;
   const int pslot = op.pdst >= 0 ? (op.pdst & ~T20_TIMES_PI) : -1;
   double *stages = t20_smem + r * T20_STAGES * T20_STAGE_DOUBLES;
+  const unsigned stages_s = (unsigned)__cvta_generic_to_shared(stages);
+  const T20Pieces pc = t20_pieces(lane, Ppad);
+  const double *obase[3];  // this warp's category rows of the stored operands (null: absent or a tip)
+  {
+    const int ids[3] = {op.a, op.b, op.b2};
+#pragma unroll
+    for (int o = 0; o < 3; o++) obase[o] = ids[o] >= n_rows ? clv + ((int64_t)(ids[o] - n_rows) * 80 + r * 20) * Ppad : nullptr;
+  }
 #pragma unroll
   for (int s = 0; s < T20_STAGES - 1; s++)
-    t20_stage_issue(stages + s * T20_STAGE_DOUBLES, op, n_rows, r, pbase + s * 8, lane, Ppad, clv);
-  double pa[3][5], p2[3][5], p3[3][5];
+    t20_stage_issue(stages_s + s * (T20_STAGE_DOUBLES * 8), obase, pc, pbase + s * 8);
+  double pa[3][5], p2[3][5];  // (the third matrix, pushed candidates only, is fetched per tile: L1 hits, 30 registers less)
   a20_load_p(pmat, op.pa, r, lane, pa);
   if (op.p2 >= 0) a20_load_p(pmat, op.p2, r, lane, p2);
-  if (op.p3 >= 0) a20_load_p(pmat, op.p3, r, lane, p3);
   double fr[3];
 #pragma unroll
   for (int mt = 0; mt < 3; mt++)
@@ -148,8 +190,8 @@ tbr20_step_kernel(const Tbr20Op *__restrict__ ops, int n_ops, int n_rows, int64_
     // tile nt + STAGES - 1 goes into the stage tile nt - 1 was read from (every lane is past it: syncwarp)
     __syncwarp();
     if (nt + T20_STAGES - 1 < A20_TILE / 8)
-      t20_stage_issue(stages + ((nt + T20_STAGES - 1) % T20_STAGES) * T20_STAGE_DOUBLES, op, n_rows, r,
-                      pbase + (nt + T20_STAGES - 1) * 8, lane, Ppad, clv);
+      t20_stage_issue(stages_s + ((nt + T20_STAGES - 1) % T20_STAGES) * (T20_STAGE_DOUBLES * 8), obase, pc,
+                      pbase + (nt + T20_STAGES - 1) * 8);
     else
       asm volatile("cp.async.commit_group;\n" ::);  // (keeps the group count uniform)
     int2 ca = make_int2(0, 0), cb = ca, cb2 = ca;
@@ -194,7 +236,11 @@ tbr20_step_kernel(const Tbr20Op *__restrict__ ops, int n_ops, int n_rows, int64_
             c[mt][0] *= v.x; c[mt][1] *= v.y;
           }
       }
-      if (op.p3 >= 0) t20_chain(tr[r], p3, c, lane);
+      if (op.p3 >= 0) {
+        double p3[3][5];
+        t20_load_p_again(pmat, op.p3, r, lane, p3);
+        t20_chain(tr[r], p3, c, lane);
+      }
       t20_colmax(c, g, mo0, mo1);
     }
     // the four categories of a pattern are scaled together: exchange the column maxima, then store.
