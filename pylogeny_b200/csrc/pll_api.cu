@@ -1233,6 +1233,7 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
   struct Scratch {
     DevBuf<double> clv, pmat, tiptab, brlen, dpart, out;
     DevBuf<int> scl;
+    DevBuf<unsigned int> bar;
     DevBuf<S1Act> acts;
     int max_blocks = -1;
   };
@@ -1242,7 +1243,8 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
   Scratch &sc = keep[dev & 7];
   if (sc.max_blocks < 0) {
     int per_sm = 0, sms = 0, coop = 0;
-    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smooth1_kernel, S1_THREADS, 0));
+    PLG_CUDA(cudaFuncSetAttribute(smooth1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10));
+    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smooth1_kernel, S1_THREADS, 64 << 10));
     PLG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     PLG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     sc.max_blocks = coop ? per_sm * sms : 0;
@@ -1276,10 +1278,12 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
   sc.brlen.alloc(n_br);
   sc.dpart.alloc((size_t)2 * 3 * n_blocks);
   sc.out.alloc(1);
+  sc.bar.alloc(1);
   sc.acts.alloc(acts.size());
   cudaStream_t st = 0;
   PLG_CUDA(cudaMemcpyAsync(sc.acts.p, acts.data(), acts.size() * sizeof(S1Act), cudaMemcpyHostToDevice, st));
   PLG_CUDA(cudaMemcpyAsync(sc.brlen.p, h_brlen.data(), (size_t)n_br * 8, cudaMemcpyHostToDevice, st));
+  PLG_CUDA(cudaMemsetAsync(sc.bar.p, 0, sizeof(unsigned int), st));
   dna4_pmatrices(aln, model, sc.brlen.p, nullptr, n_br, sc.pmat.p, sc.tiptab.p, st);
   const S1Act *d_acts = sc.acts.p;
   int n_down = (int)plan.down.size(), n_pass = (int)plan.acts.size(), passes = max_passes, n_rows = aln.n_rows;
@@ -1290,9 +1294,13 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
   const ModelDev *md = model.d.p;
   double *pm = sc.pmat.p, *tt = sc.tiptab.p, *clv = sc.clv.p, *bl = sc.brlen.p, *dp = sc.dpart.p, *out = sc.out.p;
   int *scl = sc.scl.p;
+  unsigned int *bar = sc.bar.p;
+  const size_t acts_bytes = acts.size() * sizeof(S1Act);
+  int acts_smem = acts_bytes <= (size_t)64 << 10 ? 1 : 0;
   void *args[] = {&d_acts, &n_down, &n_pass, &passes, &n_rows, &ppad, &codes, &masks, &weights, &md,
-                  &pm, &tt, &clv, &scl, &bl, &dp, &out};
-  PLG_CUDA(cudaLaunchCooperativeKernel((const void *)smooth1_kernel, dim3(n_blocks), dim3(S1_THREADS), args, 0, st));
+                  &pm, &tt, &clv, &scl, &bl, &dp, &out, &bar, &acts_smem};
+  PLG_CUDA(cudaLaunchCooperativeKernel((const void *)smooth1_kernel, dim3(n_blocks), dim3(S1_THREADS), args,
+                                       acts_smem ? acts_bytes : 0, st));
   count_launch();
   double h_out = 0.0;
   PLG_CUDA(cudaMemcpyAsync(&h_out, sc.out.p, 8, cudaMemcpyDeviceToHost, st));

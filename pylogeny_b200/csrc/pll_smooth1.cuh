@@ -10,7 +10,7 @@
 // grid -- thread = pattern, block = 128 patterns -- runs the whole program; vector updates need no
 // synchronisation at all, a Newton step is: per-thread sum-table column in REGISTERS, block partials,
 // one grid barrier, every block adds the partials in the same fixed order and takes the same step
-// (the curvature guard re-evaluates from the registers and costs one more barrier per retry).  The
+// (the curvature guard re-evaluates and costs one more barrier per retry).  The
 // moved branch's P-matrix is recomputed by every block into its own shared memory for immediate use;
 // block 0 also publishes it for the later steps (one barrier later at the earliest).
 //
@@ -21,11 +21,13 @@
 // Loads of data written inside the kernel (vectors, counters, matrices) are ld.global.cg: the
 // read-only (.nc) path the other kernels use is not coherent with stores of the same launch.
 #pragma once
-#include <cooperative_groups.h>
 
 namespace plg {
 
-constexpr int S1_THREADS = 128;
+#ifndef PLG_S1_THREADS
+#define PLG_S1_THREADS 128
+#endif
+constexpr int S1_THREADS = PLG_S1_THREADS;
 
 struct S1Act {
   int kind;              // 0: vector update (dst = a x b through pa, pb); 1: Newton step on `branch` between a and b
@@ -83,6 +85,39 @@ __device__ __forceinline__ void s1_operand(const double *sm, int id, int n_rows,
   }
 }
 
+// v (*)= P x for a column that is already in registers (the previous action's result, see `fwd` below)
+template <bool MUL>
+__device__ __forceinline__ void s1_apply_regs(const double *sm, const double (&x)[16], double (&v)[16]) {
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      double s = sm[r * 16 + k * 4] * x[r * 4];
+      s = fma(sm[r * 16 + k * 4 + 1], x[r * 4 + 1], s);
+      s = fma(sm[r * 16 + k * 4 + 2], x[r * 4 + 2], s);
+      s = fma(sm[r * 16 + k * 4 + 3], x[r * 4 + 3], s);
+      if (MUL) v[r * 4 + k] *= s; else v[r * 4 + k] = s;
+    }
+}
+
+// Grid barrier: one monotonic counter, generation g waits for g * gridDim.x arrivals.  Hand-rolled instead of
+// cooperative_groups' grid.sync() because the launch runs ~380 of them back to back on a dependent chain
+// (the launch is still cooperative: co-residency is what makes spinning safe).
+__device__ __forceinline__ void s1_grid_barrier(unsigned int *counter, unsigned int &generation) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    generation++;
+    const unsigned int target = generation * gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
 // operand as it sits at its node (tips: indicator of the code's states)
 __device__ __forceinline__ void s1_raw(int id, int n_rows, int64_t p, int64_t Ppad, const unsigned char *__restrict__ codes,
                                        const unsigned int *__restrict__ masks, const double *clv, const int *scl,
@@ -107,9 +142,7 @@ __global__ void __launch_bounds__(S1_THREADS)
 smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_passes, int n_rows, int64_t Ppad,
                const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
                const double *__restrict__ weights, const ModelDev *__restrict__ model, double *pmat, double *tiptab,
-               double *clv, int *scl, double *brlen, double *dpart, double *out) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+               double *clv, int *scl, double *brlen, double *dpart, double *out, unsigned int *bar, int acts_smem) {
   __shared__ __align__(16) double smA[256];
   __shared__ __align__(16) double smB[256];
   __shared__ double cur_pm[68], cur_tt[256];
@@ -118,6 +151,17 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
   __shared__ double red[3][S1_THREADS / 32];
   __shared__ double tot[3];
   const int n_tiles = (int)(Ppad / S1_THREADS);
+  // the action list in shared memory when it fits (acts_smem != 0): every action starts with its record, and a
+  // global load there is one more round trip on the dependent chain of ~1,300 actions
+  extern __shared__ __align__(16) unsigned char s1_dyn[];
+  const S1Act *alist = acts;
+  if (acts_smem) {
+    const int n_all = n_down + n_pass + 1;
+    int4 *d = reinterpret_cast<int4 *>(s1_dyn);
+    const int4 *g = reinterpret_cast<const int4 *>(acts);
+    for (int e = threadIdx.x; e < n_all * 2; e += S1_THREADS) d[e] = g[e];
+    alist = reinterpret_cast<const S1Act *>(s1_dyn);
+  }
   if (threadIdx.x < 16) {
     mU[threadIdx.x] = model->U[threadIdx.x];          // [i][k]  (LIK_MAX_STATES-strided rows are not used: K = 4 packs them)
     mUinv[threadIdx.x] = model->Uinv[threadIdx.x];    // [k][j]
@@ -126,6 +170,15 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
   }
   __syncthreads();
   int cur_branch = -1, parity = 0;
+  unsigned int generation = 0;
+  // Forwarding: with one tile per block a thread owns ONE pattern for the whole launch, and most actions
+  // read the vector the previous action wrote (the re-orientation chain along the depth-first path, the
+  // Newton step on the branch just re-oriented toward): that column stays in registers.
+  const bool fwd = n_tiles <= (int)gridDim.x;
+  int last_dst = -1, last_sc = 0;
+  double last_v[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) last_v[i] = 0.0;
 
   auto update = [&](const S1Act &op) {
     s1_stage(smA, op.a < n_rows, op.pa, cur_branch, cur_pm, cur_tt, pmat, tiptab);
@@ -135,8 +188,10 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
       const int64_t p = (int64_t)tile * S1_THREADS + threadIdx.x;
       double v[16];
       int sc = 0;
-      s1_operand<false>(smA, op.a, n_rows, p, Ppad, codes, clv, scl, v, sc);
-      s1_operand<true>(smB, op.b, n_rows, p, Ppad, codes, clv, scl, v, sc);
+      if (fwd && op.a == last_dst) { s1_apply_regs<false>(smA, last_v, v); sc += last_sc; }
+      else s1_operand<false>(smA, op.a, n_rows, p, Ppad, codes, clv, scl, v, sc);
+      if (fwd && op.b == last_dst) { s1_apply_regs<true>(smB, last_v, v); sc += last_sc; }
+      else s1_operand<true>(smB, op.b, n_rows, p, Ppad, codes, clv, scl, v, sc);
       int hi = 0;
 #pragma unroll
       for (int i = 0; i < 16; i++) hi = max(hi, __double2hiint(v[i]));
@@ -149,7 +204,13 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
 #pragma unroll
       for (int i = 0; i < 16; i++) dst[(int64_t)i * Ppad] = v[i];
       scl[(int64_t)(op.dst - n_rows) * Ppad + p] = sc;
+      if (fwd) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) last_v[i] = v[i];
+        last_sc = sc;
+      }
     }
+    last_dst = op.dst;
     __syncthreads();  // smA / smB are restaged by the next step
   };
 
@@ -157,8 +218,20 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
   auto column = [&](int a_id, int b_id, int64_t p, double (&sv)[16], int &sc) {
     double A[16], B[16];
     sc = 0;
-    s1_raw(a_id, n_rows, p, Ppad, codes, masks, clv, scl, A, sc);
-    s1_raw(b_id, n_rows, p, Ppad, codes, masks, clv, scl, B, sc);
+    if (fwd && a_id == last_dst) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) A[i] = last_v[i];
+      sc += last_sc;
+    } else {
+      s1_raw(a_id, n_rows, p, Ppad, codes, masks, clv, scl, A, sc);
+    }
+    if (fwd && b_id == last_dst) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) B[i] = last_v[i];
+      sc += last_sc;
+    } else {
+      s1_raw(b_id, n_rows, p, Ppad, codes, masks, clv, scl, B, sc);
+    }
 #pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -217,7 +290,7 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
       for (int i = 0; i < S1_THREADS / 32; i++) s += red[threadIdx.x][i];
       dp[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
     }
-    grid.sync();
+    s1_grid_barrier(bar, generation);
     if (threadIdx.x < 32) {  // one warp adds the blocks' shares: strided, then a fixed shuffle tree
       double a0 = 0.0, a1 = 0.0, a2 = 0.0;
       for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) {
@@ -237,12 +310,12 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
     __syncthreads();  // tab / red / tot are reused by the next evaluation
   };
 
-  for (int i = 0; i < n_down; i++) update(acts[i]);
+  for (int i = 0; i < n_down; i++) update(alist[i]);
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   for (int pass = 0; pass < max_passes; pass++) {
     bool changed = false;
     for (int i = 0; i < n_pass; i++) {
-      const S1Act op = acts[n_down + i];
+      const S1Act op = alist[n_down + i];
       if (op.kind == 0) { update(op); continue; }
       // one makenewz step (libpll: optimise the branch with maxiter = 1), as newton_step_block
       const double z0 = exp(-__ldcg(brlen + op.branch));
@@ -278,8 +351,8 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
     if (!changed) break;
   }
   {  // lnL at the final lengths
-    const S1Act op = acts[n_down + n_pass];
-    grid.sync();  // (block 0's last brlen store)
+    const S1Act op = alist[n_down + n_pass];
+    s1_grid_barrier(bar, generation);  // (block 0's last brlen store)
     const double z = fmin(fmax(exp(-__ldcg(brlen + op.branch)), PLL_ZMIN), PLL_ZMAX);
     sums(op.a, op.b, log(fmax(z, PLL_ZMIN)), s0, s1, s2);
     if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = s0;
