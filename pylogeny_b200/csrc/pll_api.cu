@@ -751,6 +751,70 @@ opt_step4_kernel(const OptItem *__restrict__ items, int blocks_per_item, int n_r
   }
 }
 
+// 20 states x Gamma-4, two-launch form.  The sum table of a branch IS a conditional-vector update with two
+// special matrices: sv[r][k] = (sum_i pi_i U[i][k] a[r][i]) * (sum_i Uinv[k][i] b[r][i]) = ((M1 a) o (M2 b))[r][k]
+// with M1 = (diag(pi) U)^T and M2 = U^-1 for every category -- so it runs on the FP64 tensor pipe through
+// clv20_kernel into a conditional-vector slot (one per tree), scaling counters included.  This kernel then
+// folds the table with the branch's exp / g exp / g^2 exp entries: thread = pattern, 80 coalesced loads.
+// (The generic (pattern, category)-per-thread kernel read U and U^-1 from memory once per FMA: 254.6 ms of
+// a 128-tree batch's 483 ms, profiles/launches_r3l.csv.)
+constexpr int DSUM20_THREADS = 128;
+__global__ void __launch_bounds__(DSUM20_THREADS)
+dsum20_kernel(const OptItem *__restrict__ items, int blocks_per_item, int64_t Ppad, const ModelDev *__restrict__ model,
+              const double *__restrict__ S, const int *__restrict__ Ssc, const double *__restrict__ weights,
+              const double *__restrict__ brlen, double *__restrict__ dpart, const int *__restrict__ active) {
+  __shared__ double tab[3][80];
+  __shared__ double red[3][DSUM20_THREADS / 32];
+  const int item = blockIdx.x / blocks_per_item;
+  const OptItem it = items[item];
+  if (!active[it.tree]) return;
+  if (threadIdx.x < 80) {
+    const double z = fmin(fmax(exp(-brlen[it.branch]), PLL_ZMIN), PLL_ZMAX);
+    const double lz = log(fmax(z, PLL_ZMIN));
+    const double g = -model->eval[threadIdx.x % 20] * model->rates[threadIdx.x / 20];
+    const double e = exp(g * lz);
+    tab[0][threadIdx.x] = e; tab[1][threadIdx.x] = g * e; tab[2][threadIdx.x] = g * g * e;
+  }
+  const int64_t p = (int64_t)(blockIdx.x - item * blocks_per_item) * DSUM20_THREADS + threadIdx.x;
+  const double *Sb = S + (int64_t)it.tree * 80 * Ppad + p;
+  double sv[80];
+#pragma unroll
+  for (int e = 0; e < 80; e++) sv[e] = __ldg(Sb + (int64_t)e * Ppad);
+  const int sc = __ldg(Ssc + (int64_t)it.tree * Ppad + p);
+  const double w = weights[p];
+  __syncthreads();
+  double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+  for (int e = 0; e < 80; e++) {
+    l0 = fma(sv[e], tab[0][e], l0);
+    l1 = fma(sv[e], tab[1][e], l1);
+    l2 = fma(sv[e], tab[2][e], l2);
+  }
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  if (w != 0.0) {
+    const double inv = 1.0 / l0, q1 = l1 * inv;
+    v0 = w * (log(l0 * 0.25) + sc * SM_LOG_MINLH);
+    v1 = w * q1;
+    v2 = w * (l2 * inv - q1 * q1);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v0 += __shfl_down_sync(0xffffffffu, v0, d);
+    v1 += __shfl_down_sync(0xffffffffu, v1, d);
+    v2 += __shfl_down_sync(0xffffffffu, v2, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = v0; red[1][threadIdx.x >> 5] = v1; red[2][threadIdx.x >> 5] = v2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < DSUM20_THREADS / 32; i++) t += red[threadIdx.x][i];
+    dpart[((int64_t)item * 3 + threadIdx.x) * blocks_per_item + (blockIdx.x - item * blocks_per_item)] = t;
+  }
+}
+
 // Second launch of the two-launch form (large batches: one block per tree finishes its branch's step).
 template <int K, int R>
 __global__ void __launch_bounds__(SM_THREADS)
@@ -1024,6 +1088,7 @@ struct BatchScratch {
   DevBuf<OptItem> d_items;
   DevBuf<LikEval> d_evals;
   DevBuf<ClvOptOp> d_fops;
+  DevBuf<LikOp> d_sops;  // 20 states: the Newton steps' sum tables as conditional-vector updates
 };
 
 template <typename F>
@@ -1051,11 +1116,28 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   DevBuf<OptItem> &d_items = sc_.d_items;
   DevBuf<LikEval> &d_evals = sc_.d_evals;
   DevBuf<ClvOptOp> &d_fops = sc_.d_fops;
-  clv.alloc((size_t)B * n_inner * RK * Ppad);
-  scl.alloc((size_t)B * n_inner * Ppad);
-  S.alloc(store_sumtable<K>() ? (size_t)B * RK * Ppad : 1);
-  Ssc.alloc(store_sumtable<K>() ? (size_t)B * Ppad : 1);
-  pmat.alloc((size_t)B * n_br * F::PM_STRIDE);
+  DevBuf<LikOp> &d_sops = sc_.d_sops;
+  // K = 20: the sum tables are conditional-vector slots B * n_inner + tree of the same buffers (clv20_kernel
+  // writes them), and two more P-matrix entries hold M1 = (diag(pi) U)^T, M2 = U^-1 (dsum20_kernel above)
+  constexpr bool S_IN_CLV = K == 20 && R == 4;
+  clv.alloc((size_t)B * (n_inner + (S_IN_CLV ? 1 : 0)) * RK * Ppad);
+  scl.alloc((size_t)B * (n_inner + (S_IN_CLV ? 1 : 0)) * Ppad);
+  S.alloc(store_sumtable<K>() && !S_IN_CLV ? (size_t)B * RK * Ppad : 1);
+  Ssc.alloc(store_sumtable<K>() && !S_IN_CLV ? (size_t)B * Ppad : 1);
+  double *const Sp = S_IN_CLV ? clv.p + (size_t)B * n_inner * RK * Ppad : S.p;
+  int *const Sscp = S_IN_CLV ? scl.p + (size_t)B * n_inner * Ppad : Ssc.p;
+  pmat.alloc(((size_t)B * n_br + 2) * F::PM_STRIDE);
+  const int PM_M1 = (int)(B * n_br), PM_M2 = PM_M1 + 1;
+  if (S_IN_CLV) {
+    std::vector<double> hm((size_t)2 * F::PM_STRIDE, 0.0);
+    for (int r = 0; r < R; r++)
+      for (int k = 0; k < K; k++)
+        for (int i = 0; i < K; i++) {
+          hm[(size_t)r * (K * K + 1) + k * K + i] = model.h.freqs[i] * model.h.U[i * K + k];
+          hm[(size_t)F::PM_STRIDE + (size_t)r * (K * K + 1) + k * K + i] = model.h.Uinv[k * K + i];
+        }
+    PLG_CUDA(cudaMemcpy(pmat.p + (size_t)PM_M1 * F::PM_STRIDE, hm.data(), hm.size() * 8, cudaMemcpyHostToDevice));
+  }
   tiptab.alloc((size_t)B * n_br * F::TIP_STRIDE);
   brlen.alloc((size_t)B * n_br);
   const int64_t ebpo = Ppad / F::EVAL_TILE;
@@ -1069,7 +1151,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
   idx.alloc((size_t)B * n_br);
   const int bpi = (int)(Ppad / (SM_THREADS / R));
   // blocks per branch of the launch that leaves the derivative-sum shares (DNA, large batches: opt_step4_kernel)
-  const int bpi2 = (K == 4 && R == 4) ? (int)(Ppad / (OPT4_THREADS * OPT4_TILES)) : bpi;
+  const int bpi2 = (K == 4 && R == 4) ? (int)(Ppad / (OPT4_THREADS * OPT4_TILES)) : (S_IN_CLV ? (int)(Ppad / DSUM20_THREADS) : bpi);
   Eigen4 eigen4;
   if (K == 4 && R == 4)
     for (int e = 0; e < 16; e++) {
@@ -1134,6 +1216,12 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
       opt_off[s + 1] = (int64_t)h_items.size();
       fop_off[s + 1] = (int64_t)h_fops.size();
     }
+    std::vector<LikOp> h_sops;
+    if (S_IN_CLV && cnt > 4) {  // (item order: dsum20_kernel and newton_kernel index the tables by tree)
+      h_sops.reserve(h_items.size());
+      for (const OptItem &it : h_items)
+        h_sops.push_back({(int)(aln.n_rows + B * n_inner + it.tree), it.a_id, it.b_id, PM_M1, PM_M2});
+    }
     for (int64_t i = 0; i < cnt; i++) h_evals.push_back(plans[i].eval);
     // start from the trees' current lengths (callers load default z = 0.9: useDefaultz, libpllWrapper.c:152;
     // a handle scored twice continues from where the first call left its branches, like the reference)
@@ -1150,6 +1238,8 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
     tm.lap("  smooth plan");
     PLG_CUDA(cudaMemcpy(d_ops.p, h_ops.data(), h_ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(d_items.p, h_items.data(), h_items.size() * sizeof(OptItem), cudaMemcpyHostToDevice));
+    d_sops.alloc(std::max<size_t>(1, h_sops.size()));
+    if (!h_sops.empty()) PLG_CUDA(cudaMemcpy(d_sops.p, h_sops.data(), h_sops.size() * sizeof(LikOp), cudaMemcpyHostToDevice));
     d_fops.alloc(std::max<size_t>(1, h_fops.size()));
     if (!h_fops.empty()) PLG_CUDA(cudaMemcpy(d_fops.p, h_fops.data(), h_fops.size() * sizeof(ClvOptOp), cudaMemcpyHostToDevice));
     PLG_CUDA(cudaMemcpy(idx.p, h_idx.data(), h_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -1177,7 +1267,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
           // many trees: two launches, no fences or tickets in the wide one
           if (fused)
             opt_step_kernel<K, R, true><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
-                its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
+                its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, Sp, Sscp,
                 aln.weights.p, brlen.p, dp_cur, active, changed, tickets.p, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
           else if constexpr (K == 4 && R == 4) {
             if (no > npre)
@@ -1185,13 +1275,17 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
                   its + npre, bpi2, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, eigen4, clv.p, scl.p, aln.weights.p, brlen.p,
                   dp_cur + (size_t)npre * 3 * bpi2, active);
           }
-          else
+          else if constexpr (S_IN_CLV) {
+            aa20_updates(aln, model, d_sops.p + opt_off[s], no, pmat.p, clv.p, scl.p, st);
+            dsum20_kernel<<<(unsigned)(no * bpi2), DSUM20_THREADS, 0, st>>>(its, bpi2, Ppad, model.d.p, Sp, Sscp, aln.weights.p,
+                                                                          brlen.p, dp_cur, active);
+          } else
             opt_step_kernel<K, R, false><<<(unsigned)(no * bpi), SM_THREADS, 0, st>>>(
-                its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, S.p, Ssc.p,
+                its, bpi, aln.n_rows, Ppad, aln.codes.p, aln.masks.p, model.d.p, clv.p, scl.p, Sp, Sscp,
                 aln.weights.p, brlen.p, dp_cur, active, changed, nullptr, pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE);
           count_launch();
           if (!fused) {
-            newton_kernel<K, R><<<(unsigned)no, SM_THREADS, 0, st>>>(its, bpi2, Ppad, aln.masks.p, model.d.p, S.p, Ssc.p,
+            newton_kernel<K, R><<<(unsigned)no, SM_THREADS, 0, st>>>(its, bpi2, Ppad, aln.masks.p, model.d.p, Sp, Sscp,
                                                                       aln.weights.p, brlen.p, dp_cur, active, changed,
                                                                       pmat.p, tiptab.p, F::PM_STRIDE, F::TIP_STRIDE,
                                                                       OptOperands{aln.n_rows, aln.codes.p, aln.masks.p, clv.p, scl.p});
