@@ -945,6 +945,7 @@ void run_lik_program(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   ws.lnl.alloc(std::max<size_t>(1, (size_t)prog.n_trees));
   if (t20) {
     if (!(a.K == 20 && m.R == 4)) PLG_FAIL(PLG_ERR_ARG, "internal: TBR-20 program on a %d-state, %d-category model", a.K, m.R);
+    if (a.Ppad * 20 > (int64_t)0x7fffffff) PLG_FAIL(PLG_ERR_UNSUPPORTED, "TBR-20 kernels index a vector's rows with 32 bits: %lld patterns are too many", (long long)a.P);
     ws.pairvec.alloc(std::max<size_t>(1, (size_t)prog.t20_pair_slots * 80 * a.Ppad));
     ws.pair_scl.alloc(std::max<size_t>(1, (size_t)prog.t20_pair_slots * a.Ppad));
     ws.t20_ops.alloc(prog.t20_ops.size());
