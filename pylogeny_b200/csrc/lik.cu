@@ -810,6 +810,24 @@ static void run_dna4(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
   }
 }
 
+// n independent 20-state updates: the staged kernel (lik_tbr20.cuh clv20s_kernel), or with PLG_A20_STAGED=0 /
+// row offsets beyond 32 bits the unstaged clv20_kernel (A/B reference)
+static void launch_clv20(const LikAln &a, const LikOp *d_ops, int64_t n, const double *d_pmat, double *d_clv, int *d_scl,
+                         cudaStream_t st) {
+  const int64_t bpo = a.Ppad / A20_TILE;
+  const char *e = getenv("PLG_A20_STAGED");
+  const bool staged = !(e && !strcmp(e, "0"));
+  if (staged && a.Ppad * 20 <= (int64_t)0x7fffffff) {
+    static bool attr_set[64] = {false};
+    ensure_dyn_smem(clv20s_kernel, T20_DYN_SMEM, attr_set);
+    clv20s_kernel<<<(unsigned)(n * bpo), A20_THREADS, T20_DYN_SMEM, st>>>(d_ops, (int)n, a.n_rows, a.Ppad, a.codes.p,
+                                                                         a.masks.p, d_pmat, d_clv, d_scl);
+  } else {
+    clv20_kernel<<<(unsigned)(n * bpo), A20_THREADS, 0, st>>>(d_ops, (int)bpo, a.n_rows, a.Ppad, a.codes.p, a.masks.p,
+                                                             d_pmat, d_clv, d_scl);
+  }
+}
+
 // 20 states x Gamma-4 path: DMMA kernels (lik_aa.cuh).  Tips enter the tensor-core product as
 // indicator columns, so only the P-matrices are needed (the tip tables are still produced by
 // pmatrix_kernel for the generic path).
@@ -837,8 +855,7 @@ static void run_aa20(const LikAln &a, const Model &m, LikWorkspace &ws, const Li
       double bytes = 0;
       for (int64_t q = o0 + o; q < o0 + o + c; q++) bytes += Cb + opnd(prog.ops[q].a) + opnd(prog.ops[q].b);
       prof_begin(PROF_CLV_UPDATE, st);
-      clv20_kernel<<<(unsigned)(c * bpo), A20_THREADS, 0, st>>>(ws.ops.p + o0 + o, (int)bpo, a.n_rows, a.Ppad,
-                                                               a.codes.p, a.masks.p, ws.pmat.p, ws.clv.p, ws.scl.p);
+      launch_clv20(a, ws.ops.p + o0 + o, c, ws.pmat.p, ws.clv.p, ws.scl.p, st);
       count_launch();
       prof_end(PROF_CLV_UPDATE, st, bytes * (double)a.P, (double)c * (double)a.P);
     }
@@ -1155,10 +1172,8 @@ void aa20_pmatrices(const LikAln &a, const Model &m, const double *d_brlen, cons
 void aa20_updates(const LikAln &a, const Model &m, const LikOp *d_ops, int64_t n, const double *d_pmat,
                   double *d_clv, int *d_scl, cudaStream_t st) {
   if (n <= 0) return;
-  const int64_t bpo = a.Ppad / A20_TILE;
   prof_begin(PROF_CLV_UPDATE, st);
-  clv20_kernel<<<(unsigned)(n * bpo), A20_THREADS, 0, st>>>(d_ops, (int)bpo, a.n_rows, a.Ppad, a.codes.p, a.masks.p,
-                                                           d_pmat, d_clv, d_scl);
+  launch_clv20(a, d_ops, n, d_pmat, d_clv, d_scl, st);
   count_launch();
   prof_end(PROF_CLV_UPDATE, st, (double)n * 3.0 * 644.0 * (double)a.P, (double)n * (double)a.P);
 }

@@ -287,6 +287,95 @@ tbr20_step_kernel(const Tbr20Op *__restrict__ ops, int n_ops, int n_rows, int64_
   }
 }
 
+// The plain 20-state update dst = (P_a a) o (P_b b) (LikOp) on the same staged pipeline: the operands' rows
+// arrive by cp.async into the warp-private ring while the previous tiles are multiplied, blocks are ordered
+// pattern-tile-major.  Replaces clv20_kernel (lik_aa.cuh: operand loads in front of every product) behind
+// aa20_updates; both are kept bit-compatible (same products, same scaling rule).
+__global__ void __launch_bounds__(A20_THREADS, PLG_T20_MINB)
+clv20s_kernel(const LikOp *__restrict__ ops, int n_ops, int n_rows, int64_t Ppad, const unsigned char *__restrict__ codes,
+              const unsigned int *__restrict__ masks, const double *__restrict__ pmat, double *__restrict__ clv,
+              int *__restrict__ scl) {
+  extern __shared__ __align__(16) double t20_smem[];
+  __shared__ int smx[2][4][8];  // [tile parity][category][pattern of the tile]: column maxima
+  const int pb = blockIdx.x / n_ops;
+  const LikOp op = ops[blockIdx.x - pb * n_ops];
+  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int64_t pbase = (int64_t)pb * A20_TILE;
+  double *stages = t20_smem + r * T20_STAGES * T20_STAGE_DOUBLES;
+  const unsigned stages_s = (unsigned)__cvta_generic_to_shared(stages);
+  const T20Pieces pc = t20_pieces(lane, Ppad);
+  const double *obase[3];
+  obase[0] = op.a >= n_rows ? clv + ((int64_t)(op.a - n_rows) * 80 + r * 20) * Ppad : nullptr;
+  obase[1] = op.b >= n_rows ? clv + ((int64_t)(op.b - n_rows) * 80 + r * 20) * Ppad : nullptr;
+  obase[2] = nullptr;
+#pragma unroll
+  for (int s = 0; s < T20_STAGES - 1; s++)
+    t20_stage_issue(stages_s + s * (T20_STAGE_DOUBLES * 8), obase, pc, pbase + s * 8);
+  double pa[3][5], pbm[3][5];
+  a20_load_p(pmat, op.pa, r, lane, pa);
+  if (op.b >= 0) a20_load_p(pmat, op.pb, r, lane, pbm);
+  double *dst = clv + ((int64_t)(op.dst - n_rows) * 80 + r * 20) * Ppad;
+  const bool booker = r == 0 && g == 0;
+  const int *sa = op.a >= n_rows ? scl + (int64_t)(op.a - n_rows) * Ppad : nullptr;
+  const int *sb = op.b >= n_rows ? scl + (int64_t)(op.b - n_rows) * Ppad : nullptr;
+#pragma unroll(T20_UNROLL)
+  for (int nt = 0; nt < A20_TILE / 8; nt++) {
+    const int64_t p0 = pbase + nt * 8;
+    __syncwarp();
+    if (nt + T20_STAGES - 1 < A20_TILE / 8)
+      t20_stage_issue(stages_s + ((nt + T20_STAGES - 1) % T20_STAGES) * (T20_STAGE_DOUBLES * 8), obase, pc,
+                      pbase + (nt + T20_STAGES - 1) * 8);
+    else
+      asm volatile("cp.async.commit_group;\n" ::);
+    int2 ca = make_int2(0, 0), cb = ca;
+    if (booker) {
+      if (sa) ca = *reinterpret_cast<const int2 *>(sa + p0 + 2 * t);
+      if (sb) cb = *reinterpret_cast<const int2 *>(sb + p0 + 2 * t);
+    }
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(T20_STAGES - 1));
+    __syncwarp();
+    const double(*sg)[20][8] = reinterpret_cast<const double(*)[20][8]>(stages + (nt % T20_STAGES) * T20_STAGE_DOUBLES);
+    double x[3][2], bf[5];
+    if (op.a < n_rows) {
+      const unsigned int m = masks[codes[(int64_t)op.a * Ppad + p0 + g]];
+#pragma unroll
+      for (int ks = 0; ks < 5; ks++) bf[ks] = (m >> (ks * 4 + t) & 1) ? 1.0 : 0.0;
+    } else {
+#pragma unroll
+      for (int ks = 0; ks < 5; ks++) bf[ks] = sg[0][ks * 4 + t][g];
+    }
+    t20_mma(pa, bf, x);
+    if (op.b >= 0) {
+      double y[3][2];
+      if (op.b < n_rows) {
+        const unsigned int m = masks[codes[(int64_t)op.b * Ppad + p0 + g]];
+#pragma unroll
+        for (int ks = 0; ks < 5; ks++) bf[ks] = (m >> (ks * 4 + t) & 1) ? 1.0 : 0.0;
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < 5; ks++) bf[ks] = sg[1][ks * 4 + t][g];
+      }
+      t20_mma(pbm, bf, y);
+#pragma unroll
+      for (int mt = 0; mt < 3; mt++) { x[mt][0] *= y[mt][0]; x[mt][1] *= y[mt][1]; }
+    }
+    int m0, m1;
+    t20_colmax(x, g, m0, m1);
+    int(*mx)[8] = smx[nt & 1];
+    if (g == 0) *reinterpret_cast<int2 *>(&mx[r][2 * t]) = make_int2(m0, m1);
+    __syncthreads();
+    const int r0 = max(max(mx[0][2 * t], mx[1][2 * t]), max(mx[2][2 * t], mx[3][2 * t])) < T20_HI_MINLH ? 1 : 0;
+    const int r1 = max(max(mx[0][2 * t + 1], mx[1][2 * t + 1]), max(mx[2][2 * t + 1], mx[3][2 * t + 1])) < T20_HI_MINLH ? 1 : 0;
+    const double f0 = r0 ? TWO256 : 1.0, f1 = r1 ? TWO256 : 1.0;
+#pragma unroll
+    for (int mt = 0; mt < 3; mt++)
+      if (mt * 8 + g < 20)
+        *reinterpret_cast<double2 *>(dst + (int64_t)(mt * 8 + g) * Ppad + p0 + 2 * t) = make_double2(x[mt][0] * f0, x[mt][1] * f1);
+    if (booker)
+      *reinterpret_cast<int2 *>(scl + (int64_t)(op.dst - n_rows) * Ppad + p0 + 2 * t) = make_int2(ca.x + cb.x + r0, ca.y + cb.y + r1);
+  }
+}
+
 // Pair grid (see the header): warp item = (tile, chunk of 32 patterns).  Items of one bisection are
 // adjacent -- chunk-major, tiles inside -- so the vectors of a bisection's candidates are re-read
 // from L2 (and, within a block, from L1) by the tiles that share them.

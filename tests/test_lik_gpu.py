@@ -70,6 +70,31 @@ def test_protein_gamma_vs_oracle():
     a.close(); m.close()
 
 
+@pytest.mark.parametrize("n,P,scale", [(12, 400, 1.0), (70, 130, 30.0), (5, 64, 1.0)])
+def test_protein_staged_update_is_bit_identical(n, P, scale, monkeypatch):
+    """The 20-state update behind every protein level program runs with its operands staged by cp.async
+    (clv20s_kernel, pattern-tile-major blocks); PLG_A20_STAGED=0 keeps clv20_kernel.  Same products, same
+    scaling rule -- identical lnL, also where 2^-256 factors are taken (long branches, 70 taxa) -- and the
+    oracle on one tree."""
+    from pylogeny_b200 import _lib, likelihood
+    rng = np.random.default_rng(3 * n + P)
+    codes = rng.integers(0, 20, (n, P)).astype(np.uint8)
+    codes = np.where(rng.random((n, P)) < 0.03, rng.integers(20, 23, (n, P)), codes).astype(np.uint8)
+    w = rng.integers(0, 4, P).astype(float)
+    exch, f = likelihood.protein_model("JTT")
+    a = likelihood.LikAlignment(codes, w, _lib.DATA_AA)
+    m = likelihood.Model(exch, f, 0.7)
+    descs = np.stack([random_desc(rng, n) for _ in range(5)])
+    brs = rng.exponential(0.1 * scale, descs.shape)
+    got = a.score_trees(m, descs, brs)
+    monkeypatch.setenv("PLG_A20_STAGED", "0")
+    ref = a.score_trees(m, descs, brs)
+    assert got.tolist() == ref.tolist()
+    want = oracle.lnl(codes, w, exch, f, 0.7, descs[0], brs[0])
+    assert abs(got[0] - want) <= RTOL * abs(want)
+    a.close(); m.close()
+
+
 def test_scaling_counters_deep_tree():
     """600-taxon caterpillar with long branches: per-site CLVs underflow 2^-256 several times."""
     from pylogeny_b200 import likelihood
