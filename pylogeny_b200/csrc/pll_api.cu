@@ -1217,7 +1217,7 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
       fop_off[s + 1] = (int64_t)h_fops.size();
     }
     std::vector<LikOp> h_sops;
-    if (S_IN_CLV && cnt > 4) {  // (item order: dsum20_kernel and newton_kernel index the tables by tree)
+    if (S_IN_CLV) {  // (item order: dsum20_kernel and newton_kernel index the tables by tree)
       h_sops.reserve(h_items.size());
       for (const OptItem &it : h_items)
         h_sops.push_back({(int)(aln.n_rows + B * n_inner + it.tree), it.a_id, it.b_id, PM_M1, PM_M2});
@@ -1248,7 +1248,9 @@ static void pll_loglik_batch(const LikAln &aln, const Model &model, std::vector<
     PLG_CUDA(cudaMemcpy(flags.p, h_flags.data(), h_flags.size() * sizeof(int), cudaMemcpyHostToDevice));
     int *active = flags.p, *changed = flags.p + cnt;
     cudaStream_t st = 0;
-    const bool fused = cnt <= 4;
+    // (20 states: the tensor-pipe sum table + dsum20_kernel + newton_kernel beat the generic fused kernel even for
+    // one tree: 36 us per Newton step against ~23)
+    const bool fused = cnt <= 4 && !S_IN_CLV;
     tm.lap("  smooth upload");
     F::pmatrices(aln, model, brlen.p, nullptr, cnt * n_br, pmat.p, tiptab.p, st);
     for (int j = 0; j < n_inner; j++)
