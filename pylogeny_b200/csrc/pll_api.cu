@@ -1327,39 +1327,26 @@ namespace plg {
 static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const std::vector<int32_t> &tip_rows,
                     int max_passes, double *out_lnl) {
   struct Scratch {
-    DevBuf<double> clv, pmat, tiptab, priv, brlen, out;
+    DevBuf<double> clv, pmat, tiptab, brlen, out;
     DevBuf<int> scl;
     DevBuf<unsigned long long> ll;
     DevBuf<S1Act> acts;
-    int max_blocks[2] = {-1, -1};  // co-resident blocks of smooth1_kernel<false>, <true>
+    int sms = -1, coop = 0;
   };
   static thread_local Scratch keep[8];
   int dev = 0;
   cudaGetDevice(&dev);
   Scratch &sc = keep[dev & 7];
-  constexpr size_t S1_DYN_MAX = (size_t)64 << 10;
-  if (sc.max_blocks[0] < 0) {
-    int per_sm[2] = {0, 0}, sms = 0, coop = 0;
+  constexpr size_t S1_DYN_MAX = (size_t)176 << 10;
+  if (sc.sms < 0) {
     PLG_CUDA(cudaFuncSetAttribute(smooth1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_DYN_MAX));
     PLG_CUDA(cudaFuncSetAttribute(smooth1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_DYN_MAX));
-    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], smooth1_kernel<false>, S1_THREADS, S1_DYN_MAX));
-    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], smooth1_kernel<true>, S1_THREADS, S1_DYN_MAX));
-    PLG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    PLG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    sc.max_blocks[0] = coop ? per_sm[0] * sms : 0;
-    sc.max_blocks[1] = coop ? per_sm[1] * sms : 0;
+    PLG_CUDA(cudaDeviceGetAttribute(&sc.sms, cudaDevAttrMultiProcessorCount, dev));
+    PLG_CUDA(cudaDeviceGetAttribute(&sc.coop, cudaDevAttrCooperativeLaunch, dev));
   }
   const int64_t Ppad = aln.Ppad;
-  if (sc.max_blocks[0] < 1) return false;
+  if (!sc.coop) return false;
   const int n = tree.n_tips, n_inner = n - 2, n_br = 2 * n - 3;
-  // shared memory of a block: its branch lengths and moved flags, and the action list when that still fits
-  const size_t own_bytes = (((size_t)n_br * 8 + 15) & ~(size_t)15) + (((size_t)n_br + 15) & ~(size_t)15);
-  if (own_bytes > S1_DYN_MAX) return false;
-  // co-resident grid; a block takes every gridDim.x-th tile of 128 patterns
-  const int64_t n_tiles = Ppad / S1_THREADS;
-  int n_blocks = (int)std::min<int64_t>(n_tiles, n_tiles <= sc.max_blocks[1] ? sc.max_blocks[1] : sc.max_blocks[0]);
-  if (const char *e = getenv("PLG_S1_MAX_BLOCKS")) n_blocks = std::max(1, std::min(n_blocks, atoi(e)));  // tests: several tiles per block
-  const bool one = n_blocks == n_tiles;  // a thread keeps one pattern for the whole launch
   TreePlan plan = plan_tree(tree, tip_rows, aln.n_rows, 0, 0, 0);
   std::vector<S1Act> acts;
   acts.reserve(plan.down.size() + plan.acts.size() + 1);
@@ -1369,6 +1356,22 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
     else acts.push_back({0, a.op.dst, a.op.a, a.op.b, a.op.pa, a.op.pb, -1, 0});
   }
   acts.push_back({1, -1, plan.eval.a, plan.eval.b, -1, -1, plan.eval.pb, 0});  // lnL across the branch at tip 0
+  // shared memory of a block: every branch's P-matrix and length (trees too large for that -- more than 174 taxa -- take
+  // the lockstep program), and the action list when it still fits
+  const size_t own_bytes = (size_t)n_br * 64 * 8 + (size_t)((n_br + 1) & ~1) * 8, acts_bytes = acts.size() * sizeof(S1Act);
+  if (own_bytes > S1_DYN_MAX) return false;
+  int acts_smem = own_bytes + acts_bytes <= S1_DYN_MAX ? 1 : 0;
+  const size_t dyn_bytes = own_bytes + (acts_smem ? acts_bytes : 0);
+  // co-resident grid; a block takes every gridDim.x-th tile of S1_TILE patterns.  One tile per block when that
+  // many blocks are co-resident (a thread then keeps one pattern for the whole launch).
+  const int64_t n_tiles = Ppad / S1_TILE;
+  int per_sm[2] = {0, 0};
+  PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], smooth1_kernel<true>, S1_THREADS, dyn_bytes));
+  PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], smooth1_kernel<false>, S1_THREADS, dyn_bytes));
+  if (per_sm[0] < 1) return false;
+  int n_blocks = (int)std::min<int64_t>(n_tiles, n_tiles <= (int64_t)per_sm[1] * sc.sms ? per_sm[1] * sc.sms : per_sm[0] * sc.sms);
+  if (const char *e = getenv("PLG_S1_MAX_BLOCKS")) n_blocks = std::max(1, std::min(n_blocks, atoi(e)));  // tests: several tiles per block
+  const bool one = n_blocks == n_tiles;
   std::vector<double> h_brlen(n_br, 0.0);
   {
     int b = 0;
@@ -1380,13 +1383,12 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
   sc.scl.alloc((size_t)n_inner * Ppad);
   sc.pmat.alloc((size_t)n_br * 68);
   sc.tiptab.alloc((size_t)n_br * 256);
-  sc.priv.alloc((size_t)n_blocks * n_br * S1_PRIV);  // every block's own copy of the matrices it moves
   sc.brlen.alloc(n_br);
   sc.ll.alloc((size_t)2 * 6 * n_blocks * n_blocks);  // inboxes: [parity][destination][source]
   sc.out.alloc(1);
   sc.acts.alloc(acts.size());
   cudaStream_t st = 0;
-  PLG_CUDA(cudaMemcpyAsync(sc.acts.p, acts.data(), acts.size() * sizeof(S1Act), cudaMemcpyHostToDevice, st));
+  PLG_CUDA(cudaMemcpyAsync(sc.acts.p, acts.data(), acts_bytes, cudaMemcpyHostToDevice, st));
   PLG_CUDA(cudaMemcpyAsync(sc.brlen.p, h_brlen.data(), (size_t)n_br * 8, cudaMemcpyHostToDevice, st));
   PLG_CUDA(cudaMemsetAsync(sc.ll.p, 0, (size_t)2 * 6 * n_blocks * n_blocks * 8, st));  // generation 0 = nothing sent yet
   dna4_pmatrices(aln, model, sc.brlen.p, nullptr, n_br, sc.pmat.p, sc.tiptab.p, st);
@@ -1397,17 +1399,14 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
   const unsigned int *masks = aln.masks.p;
   const double *weights = aln.weights.p;
   const ModelDev *md = model.d.p;
-  const double *pm = sc.pmat.p, *tt = sc.tiptab.p;
-  double *priv = sc.priv.p, *clv = sc.clv.p, *bl = sc.brlen.p, *out = sc.out.p;
+  const double *pm = sc.pmat.p;
+  double *clv = sc.clv.p, *bl = sc.brlen.p, *out = sc.out.p;
   int *scl = sc.scl.p;
   unsigned long long *ll = sc.ll.p;
-  const size_t acts_bytes = acts.size() * sizeof(S1Act);
-  int acts_smem = own_bytes + acts_bytes <= S1_DYN_MAX ? 1 : 0;
   void *args[] = {&d_acts, &n_down, &n_pass, &passes, &n_rows, &nbr, &ppad, &codes, &masks, &weights, &md,
-                  &pm, &tt, &priv, &clv, &scl, &bl, &ll, &out, &acts_smem};
+                  &pm, &clv, &scl, &bl, &ll, &out, &acts_smem};
   PLG_CUDA(cudaLaunchCooperativeKernel(one ? (const void *)smooth1_kernel<true> : (const void *)smooth1_kernel<false>,
-                                       dim3(n_blocks), dim3(S1_THREADS), args,
-                                       own_bytes + (acts_smem ? acts_bytes : 0), st));
+                                       dim3(n_blocks), dim3(S1_THREADS), args, dyn_bytes, st));
   count_launch();
   double h_out = 0.0;
   PLG_CUDA(cudaMemcpyAsync(&h_out, sc.out.p, 8, cudaMemcpyDeviceToHost, st));
