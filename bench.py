@@ -143,7 +143,8 @@ class ClockSampler(object):
     """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML thread
     (pynvml) when available: an `nvidia-smi -lms` child process perturbed the timed steps by up to
     a millisecond per sample (it takes the driver lock for tens of fields); the NVML calls used here
-    are two cheap queries per sample.  Falls back to nvidia-smi."""
+    are two cheap queries per sample, every 50 ms (every 10 ms they doubled the step time of the launch-rich
+    aa_c5 workload -- 70 ms against 35.7 -- while leaving the long steps alone).  Falls back to nvidia-smi."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -177,7 +178,7 @@ class ClockSampler(object):
                         self.mask |= int(reasons(h))
                     except Exception:
                         pass
-                    time.sleep(0.01)
+                    time.sleep(float(os.environ.get("PLG_BENCH_SAMPLE_S", "0.05")))
 
             self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()

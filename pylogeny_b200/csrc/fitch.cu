@@ -281,14 +281,24 @@ FitchAln::FitchAln(int64_t n_prof, int n_cols_, const uint8_t *states, const int
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
     PLG_FAIL(PLG_ERR_CUDA, "no CUDA device: pylogeny_b200 has no CPU fallback");
   // distinct symbols per pattern -> number of planes
+  // (a 256-bit set per pattern, patterns split over the host cores: at 100k x 256 the scalar loop with a
+  // 256-byte `seen` table was most of what creating the handle cost)
   int kmax = 1;
-  for (int64_t p = 0; p < P; p++) {
-    bool seen[256] = {false};
-    int k = 0;
-    const uint8_t *colp = states + p * n_cols;
-    for (int r = 0; r < n_cols; r++)
-      if (!seen[colp[r]]) { seen[colp[r]] = true; k++; }
-    kmax = std::max(kmax, k);
+  {
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(HostPool::get().size(), P * n_cols >> 20));
+    std::vector<int> part(n_thr, 1);
+    HostPool::get().run(n_thr, [&](int ti, int nt) {
+      int best = 1;
+      for (int64_t p = P * ti / nt; p < P * (ti + 1) / nt; p++) {
+        uint64_t m[4] = {0, 0, 0, 0};
+        const uint8_t *colp = states + p * n_cols;
+        for (int r = 0; r < n_cols; r++) m[colp[r] >> 6] |= 1ull << (colp[r] & 63);
+        best = std::max(best, __builtin_popcountll(m[0]) + __builtin_popcountll(m[1]) + __builtin_popcountll(m[2]) +
+                                  __builtin_popcountll(m[3]));
+      }
+      part[ti] = best;
+    });
+    for (int k : part) kmax = std::max(kmax, k);
   }
   K_real = kmax;
   K = pick_template_planes(kmax);
@@ -302,7 +312,9 @@ FitchAln::FitchAln(int64_t n_prof, int n_cols_, const uint8_t *states, const int
   std::iota(order.begin(), order.end(), 0);
   std::vector<uint32_t> w32(P);
   for (int64_t p = 0; p < P; p++) w32[p] = (uint32_t)(uint64_t)weights[p];
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return w32[a] > w32[b]; });
+  bool sorted = true;  // (equal weights -- distinct patterns of a long alignment -- are in order already)
+  for (int64_t p = 1; p < P && sorted; p++) sorted = w32[p] <= w32[p - 1];
+  if (!sorted) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return w32[a] > w32[b]; });
   // bit-sliced weights + per-128-chunk plane count
   std::vector<uint8_t> nb(W4, 0xFF);
   int B = 0;

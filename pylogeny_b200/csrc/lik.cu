@@ -231,6 +231,18 @@ namespace plg {
 // ----------------------------------------------------------------------------
 // host: alignment
 // ----------------------------------------------------------------------------
+// largest tip code of the uploaded alignment (range check of LikAln's constructor)
+__global__ void max_code_kernel(const uint4 *__restrict__ codes, int64_t n16, unsigned int *__restrict__ out) {
+  unsigned int m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(codes + i);
+    m = __vmaxu4(m, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+  }
+  m = max(max(m & 255u, (m >> 8) & 255u), max((m >> 16) & 255u, m >> 24));
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 LikAln::LikAln(int datatype, int n_rows_, int64_t P_, const uint8_t *h_codes, const double *h_w) {
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
@@ -253,27 +265,31 @@ LikAln::LikAln(int datatype, int n_rows_, int64_t P_, const uint8_t *h_codes, co
   const int64_t tile = LIK_THREADS;  // multiple of LIK_THREADS / R for every supported R
   Ppad = std::max<int64_t>(tile, (P + tile - 1) / tile * tile);
   const uint8_t any = (uint8_t)(K == 4 ? 15 : 22);
-  std::vector<uint8_t> padded((size_t)n_rows * Ppad);
-  for (int r = 0; r < n_rows; r++) {
-    const uint8_t *src = h_codes + (size_t)r * P;
-    uint8_t *dst = padded.data() + (size_t)r * Ppad;
-    uint8_t mx = 0;
-    for (int64_t p = 0; p < P; p++) mx = std::max(mx, src[p]);  // vectorised range check
-    if (mx >= n_codes)
-      for (int64_t p = 0; p < P; p++)
-        if (src[p] >= n_codes)
-          PLG_FAIL(PLG_ERR_ARG, "tip code %d at row %d pattern %lld is out of range", src[p], r, (long long)p);
-    memcpy(dst, src, (size_t)P);
-    memset(dst + P, any, (size_t)(Ppad - P));
-  }
-  std::vector<double> w(Ppad, 0.0);
-  for (int64_t p = 0; p < P; p++) w[p] = h_w[p];
-  codes.alloc(padded.size());
-  weights.alloc(w.size());
+  // Rows go up straight from the caller's buffer (a pitched copy: DMA at full rate when it is pinned; a padded
+  // host copy of a 128 x 1M alignment cost more than scoring 64 trees on it), padding and the range check
+  // happen on the device.
+  codes.alloc((size_t)n_rows * Ppad);
+  weights.alloc((size_t)Ppad);
   masks.alloc(h_masks.size());
-  PLG_CUDA(cudaMemcpy(codes.p, padded.data(), padded.size(), cudaMemcpyHostToDevice));
-  PLG_CUDA(cudaMemcpy(weights.p, w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+  if (P > 0) PLG_CUDA(cudaMemcpy2D(codes.p, (size_t)Ppad, h_codes, (size_t)P, (size_t)P, (size_t)n_rows, cudaMemcpyHostToDevice));
+  if (Ppad > P) PLG_CUDA(cudaMemset2D(codes.p + P, (size_t)Ppad, any, (size_t)(Ppad - P), (size_t)n_rows));
+  PLG_CUDA(cudaMemset(weights.p, 0, (size_t)Ppad * 8));
+  if (P > 0) PLG_CUDA(cudaMemcpy(weights.p, h_w, (size_t)P * 8, cudaMemcpyHostToDevice));
   PLG_CUDA(cudaMemcpy(masks.p, h_masks.data(), h_masks.size() * 4, cudaMemcpyHostToDevice));
+  DevBuf<unsigned int> d_max;
+  d_max.alloc(1);
+  PLG_CUDA(cudaMemset(d_max.p, 0, sizeof(unsigned int)));
+  const int64_t n16 = (int64_t)n_rows * Ppad / 16;  // (Ppad is a multiple of 256)
+  max_code_kernel<<<(unsigned)std::min<int64_t>((n16 + 255) / 256, 148 * 8), 256>>>(reinterpret_cast<const uint4 *>(codes.p), n16, d_max.p);
+  count_launch();
+  PLG_CUDA(cudaGetLastError());
+  unsigned int mx = 0;
+  PLG_CUDA(cudaMemcpy(&mx, d_max.p, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  if (mx >= (unsigned int)n_codes)  // (the error path alone walks the host copy, to name the place)
+    for (int r = 0; r < n_rows; r++)
+      for (int64_t p = 0; p < P; p++)
+        if (h_codes[(size_t)r * P + p] >= n_codes)
+          PLG_FAIL(PLG_ERR_ARG, "tip code %d at row %d pattern %lld is out of range", h_codes[(size_t)r * P + p], r, (long long)p);
 }
 
 // ----------------------------------------------------------------------------
