@@ -273,33 +273,53 @@ static int pick_template_planes(int K) {
   return -1;
 }
 
+// Largest number of distinct symbols in a pattern (= the number of planes): one warp per pattern, a 256-bit
+// set per lane, OR-reduced over the warp.  (On the host this was half of what creating a handle cost at
+// 256 x 100k, even on all cores.)
+__global__ void fitch_kmax_kernel(const unsigned char *__restrict__ states, int64_t P, int n_cols, int *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int best = 0;
+  for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < P; p += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    unsigned int m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned char *colp = states + p * n_cols;
+    for (int r = lane; r < n_cols; r += 32) {
+      const unsigned int c = colp[r], bit = 1u << (c & 31), q = c >> 5;
+#pragma unroll
+      for (int i = 0; i < 8; i++) m[i] |= q == (unsigned int)i ? bit : 0u;
+    }
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) k += __popc(__reduce_or_sync(0xffffffffu, m[i]));
+    best = max(best, k);
+  }
+  if (lane == 0 && best) atomicMax(out, best);
+}
+
 FitchAln::FitchAln(int64_t n_prof, int n_cols_, const uint8_t *states, const int64_t *weights) {
+  StageTimer tm;
   P = n_prof;
   n_cols = n_cols_;
   if (P < 0 || n_cols <= 0) PLG_FAIL(PLG_ERR_ARG, "alignment needs n_prof >= 0 and n_cols > 0");
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
     PLG_FAIL(PLG_ERR_CUDA, "no CUDA device: pylogeny_b200 has no CPU fallback");
-  // distinct symbols per pattern -> number of planes
-  // (a 256-bit set per pattern, patterns split over the host cores: at 100k x 256 the scalar loop with a
-  // 256-byte `seen` table was most of what creating the handle cost)
+  // distinct symbols per pattern -> number of planes: the symbols go up first (the pack kernel needs them
+  // anyway) and are counted on the device
+  DevBuf<unsigned char> d_states;
+  d_states.alloc(std::max<size_t>(1, (size_t)P * n_cols));
   int kmax = 1;
-  {
-    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(HostPool::get().size(), P * n_cols >> 20));
-    std::vector<int> part(n_thr, 1);
-    HostPool::get().run(n_thr, [&](int ti, int nt) {
-      int best = 1;
-      for (int64_t p = P * ti / nt; p < P * (ti + 1) / nt; p++) {
-        uint64_t m[4] = {0, 0, 0, 0};
-        const uint8_t *colp = states + p * n_cols;
-        for (int r = 0; r < n_cols; r++) m[colp[r] >> 6] |= 1ull << (colp[r] & 63);
-        best = std::max(best, __builtin_popcountll(m[0]) + __builtin_popcountll(m[1]) + __builtin_popcountll(m[2]) +
-                                  __builtin_popcountll(m[3]));
-      }
-      part[ti] = best;
-    });
-    for (int k : part) kmax = std::max(kmax, k);
+  if (P) {
+    PLG_CUDA(cudaMemcpy(d_states.p, states, (size_t)P * n_cols, cudaMemcpyHostToDevice));
+    DevBuf<int> d_k;
+    d_k.alloc(1);
+    PLG_CUDA(cudaMemset(d_k.p, 0, sizeof(int)));
+    fitch_kmax_kernel<<<(unsigned)std::min<int64_t>((P + 7) / 8, 148 * 16), 256>>>(d_states.p, P, n_cols, d_k.p);
+    count_launch();
+    PLG_CUDA(cudaGetLastError());
+    PLG_CUDA(cudaMemcpy(&kmax, d_k.p, sizeof(int), cudaMemcpyDeviceToHost));
+    kmax = std::max(kmax, 1);
   }
+  tm.lap("aln states");
   K_real = kmax;
   K = pick_template_planes(kmax);
   if (K < 0)
@@ -340,25 +360,23 @@ FitchAln::FitchAln(int64_t n_prof, int n_cols_, const uint8_t *states, const int
     for (int b = 0; b < B; b++)
       if (w >> b & 1) wb[(size_t)b * words32 + (p >> 5)] |= 1u << (p & 31);
   }
+  tm.lap("aln weights");
   tips.alloc((size_t)n_cols * K * words32);
   wbits.alloc(wb.size());
   chunk_nb.alloc(W4);
   PLG_CUDA(cudaMemcpy(wbits.p, wb.data(), wb.size() * 4, cudaMemcpyHostToDevice));
   PLG_CUDA(cudaMemcpy(chunk_nb.p, nb.data(), W4, cudaMemcpyHostToDevice));
   // pack on the device
-  DevBuf<unsigned char> d_states;
   DevBuf<int> d_order;
-  d_states.alloc(std::max<size_t>(1, (size_t)P * n_cols));
   d_order.alloc(std::max<size_t>(1, P));
-  if (P) {
-    PLG_CUDA(cudaMemcpy(d_states.p, states, (size_t)P * n_cols, cudaMemcpyHostToDevice));
-    PLG_CUDA(cudaMemcpy(d_order.p, order.data(), (size_t)P * sizeof(int), cudaMemcpyHostToDevice));
-  }
+  if (P) PLG_CUDA(cudaMemcpy(d_order.p, order.data(), (size_t)P * sizeof(int), cudaMemcpyHostToDevice));
+  tm.lap("aln upload");
   dim3 grid((unsigned)((words32 + 127) / 128), (unsigned)n_cols);
   fitch_pack_kernel<<<grid, 128>>>(d_states.p, d_order.p, P, n_cols, K, words32, tips.p);
   count_launch();
   PLG_CUDA(cudaGetLastError());
   PLG_CUDA(cudaDeviceSynchronize());
+  tm.lap("aln pack");
 }
 
 // ----------------------------------------------------------------------------
