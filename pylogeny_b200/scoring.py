@@ -69,7 +69,8 @@ def getParsimonyForTopology(topo, alignment):
 
 def getLogLikelihoodBatch(trees, alignment, updateBranchLengths=True):
     """getLogLikelihood for a list of trees on one alignment in a single engine call (all trees are
-    smoothed in lockstep on the device; ~1 ms instead of ~20 ms per 64-taxon tree).  Returns a list
+    smoothed in lockstep on the device: ~0.6 ms per 64-taxon x 10k-site tree against ~2.2 ms through one
+    handle per tree).  Returns a list
     of floats (None where the reference path would have returned None for that tree)."""
     from . import libpllWrapper as W, pll
     if not trees:
