@@ -1327,7 +1327,7 @@ namespace plg {
 static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const std::vector<int32_t> &tip_rows,
                     int max_passes, double *out_lnl) {
   struct Scratch {
-    DevBuf<double> clv, pmat, tiptab, brlen, out;
+    DevBuf<double> clv, pmat, tiptab, brlen, out, spill;
     DevBuf<int> scl;
     DevBuf<unsigned long long> ll;
     DevBuf<S1Act> acts;
@@ -1339,8 +1339,10 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
   Scratch &sc = keep[dev & 7];
   constexpr size_t S1_DYN_MAX = (size_t)176 << 10;
   if (sc.sms < 0) {
-    PLG_CUDA(cudaFuncSetAttribute(smooth1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_DYN_MAX));
-    PLG_CUDA(cudaFuncSetAttribute(smooth1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_DYN_MAX));
+    PLG_CUDA(cudaFuncSetAttribute(smooth1_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_DYN_MAX));
+    PLG_CUDA(cudaFuncSetAttribute(smooth1_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_DYN_MAX));
+    PLG_CUDA(cudaFuncSetAttribute(smooth1_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_DYN_MAX));
+    PLG_CUDA(cudaFuncSetAttribute(smooth1_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_DYN_MAX));
     PLG_CUDA(cudaDeviceGetAttribute(&sc.sms, cudaDevAttrMultiProcessorCount, dev));
     PLG_CUDA(cudaDeviceGetAttribute(&sc.coop, cudaDevAttrCooperativeLaunch, dev));
   }
@@ -1356,18 +1358,28 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
     else acts.push_back({0, a.op.dst, a.op.a, a.op.b, a.op.pa, a.op.pb, -1, 0});
   }
   acts.push_back({1, -1, plan.eval.a, plan.eval.b, -1, -1, plan.eval.pb, 0});  // lnL across the branch at tip 0
-  // shared memory of a block: every branch's P-matrix and length (trees too large for that -- more than 174 taxa -- take
-  // the lockstep program), and the action list when it still fits
-  const size_t own_bytes = (size_t)n_br * 64 * 8 + (size_t)((n_br + 1) & ~1) * 8, acts_bytes = acts.size() * sizeof(S1Act);
-  if (own_bytes > S1_DYN_MAX) return false;
+  // shared memory of a block: every branch's length and P-matrix -- as many matrices as fit (all of them up to 174
+  // taxa; the others go to the block's own global region) -- and the action list when it still fits
+  const size_t len_bytes = (size_t)((n_br + 1) & ~1) * 8, acts_bytes = acts.size() * sizeof(S1Act);
+  if (len_bytes + 64 * 8 > S1_DYN_MAX) return false;
+  const int n_sm_br = (int)std::min<size_t>((size_t)n_br, (S1_DYN_MAX - len_bytes) / (64 * 8));
+  const bool fit = n_sm_br == n_br;
+  const size_t own_bytes = (size_t)n_sm_br * 64 * 8 + len_bytes;
   int acts_smem = own_bytes + acts_bytes <= S1_DYN_MAX ? 1 : 0;
   const size_t dyn_bytes = own_bytes + (acts_smem ? acts_bytes : 0);
   // co-resident grid; a block takes every gridDim.x-th tile of S1_TILE patterns.  One tile per block when that
   // many blocks are co-resident (a thread then keeps one pattern for the whole launch).
+  const void *kern[2][2] = {{(const void *)smooth1_kernel<false, false>, (const void *)smooth1_kernel<false, true>},
+                            {(const void *)smooth1_kernel<true, false>, (const void *)smooth1_kernel<true, true>}};
   const int64_t n_tiles = Ppad / S1_TILE;
   int per_sm[2] = {0, 0};
-  PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], smooth1_kernel<true>, S1_THREADS, dyn_bytes));
-  PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], smooth1_kernel<false>, S1_THREADS, dyn_bytes));
+  if (fit) {
+    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], smooth1_kernel<true, true>, S1_THREADS, dyn_bytes));
+    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], smooth1_kernel<false, true>, S1_THREADS, dyn_bytes));
+  } else {
+    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], smooth1_kernel<true, false>, S1_THREADS, dyn_bytes));
+    PLG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], smooth1_kernel<false, false>, S1_THREADS, dyn_bytes));
+  }
   if (per_sm[0] < 1) return false;
   int n_blocks = (int)std::min<int64_t>(n_tiles, n_tiles <= (int64_t)per_sm[1] * sc.sms ? per_sm[1] * sc.sms : per_sm[0] * sc.sms);
   if (const char *e = getenv("PLG_S1_MAX_BLOCKS")) n_blocks = std::max(1, std::min(n_blocks, atoi(e)));  // tests: several tiles per block
@@ -1385,6 +1397,7 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
   sc.tiptab.alloc((size_t)n_br * 256);
   sc.brlen.alloc(n_br);
   sc.ll.alloc((size_t)2 * 6 * n_blocks * n_blocks);  // inboxes: [parity][destination][source]
+  sc.spill.alloc(std::max<size_t>(1, (size_t)n_blocks * (n_br - n_sm_br) * 64));
   sc.out.alloc(1);
   sc.acts.alloc(acts.size());
   cudaStream_t st = 0;
@@ -1393,7 +1406,8 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
   PLG_CUDA(cudaMemsetAsync(sc.ll.p, 0, (size_t)2 * 6 * n_blocks * n_blocks * 8, st));  // generation 0 = nothing sent yet
   dna4_pmatrices(aln, model, sc.brlen.p, nullptr, n_br, sc.pmat.p, sc.tiptab.p, st);
   const S1Act *d_acts = sc.acts.p;
-  int n_down = (int)plan.down.size(), n_pass = (int)plan.acts.size(), passes = max_passes, n_rows = aln.n_rows, nbr = n_br;
+  int n_down = (int)plan.down.size(), n_pass = (int)plan.acts.size(), passes = max_passes, n_rows = aln.n_rows, nbr = n_br, nsm = n_sm_br;
+  double *spill = sc.spill.p;
   int64_t ppad = Ppad;
   const unsigned char *codes = aln.codes.p;
   const unsigned int *masks = aln.masks.p;
@@ -1403,10 +1417,9 @@ static bool smooth1(const LikAln &aln, const Model &model, UTree &tree, const st
   double *clv = sc.clv.p, *bl = sc.brlen.p, *out = sc.out.p;
   int *scl = sc.scl.p;
   unsigned long long *ll = sc.ll.p;
-  void *args[] = {&d_acts, &n_down, &n_pass, &passes, &n_rows, &nbr, &ppad, &codes, &masks, &weights, &md,
+  void *args[] = {&d_acts, &n_down, &n_pass, &passes, &n_rows, &nbr, &nsm, &spill, &ppad, &codes, &masks, &weights, &md,
                   &pm, &clv, &scl, &bl, &ll, &out, &acts_smem};
-  PLG_CUDA(cudaLaunchCooperativeKernel(one ? (const void *)smooth1_kernel<true> : (const void *)smooth1_kernel<false>,
-                                       dim3(n_blocks), dim3(S1_THREADS), args, dyn_bytes, st));
+  PLG_CUDA(cudaLaunchCooperativeKernel(kern[one ? 1 : 0][fit ? 1 : 0], dim3(n_blocks), dim3(S1_THREADS), args, dyn_bytes, st));
   count_launch();
   double h_out = 0.0;
   PLG_CUDA(cudaMemcpyAsync(&h_out, sc.out.p, 8, cudaMemcpyDeviceToHost, st));

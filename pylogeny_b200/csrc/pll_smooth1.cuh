@@ -15,7 +15,8 @@
 //    and its own copy of ALL the tree's P-matrices in shared memory (64 doubles per branch; a tip
 //    operand is the matrix applied to the indicator vector of its code, the same additions as a tip
 //    lookup table): nothing is published, no matrix is staged, and a vector update needs no block
-//    barrier at all;
+//    barrier at all (trees of more than 174 taxa: the matrices that do not fit live in the block's own
+//    global region, instantiation FIT = false);
 //  * the sums travel as flagged words (the LL protocol of collective libraries): a block stores each
 //    half of its three partial sums as one 8-byte word (generation << 32 | half) into every block's
 //    inbox, every block polls its own inbox until all words carry the current generation and adds
@@ -220,11 +221,12 @@ __device__ __forceinline__ void s1_exchange(unsigned long long *ll, unsigned int
 // the evaluation step (kind 1: its sums at the branch's final length give the lnL).
 // pmat: the matrices of the initial lengths (rows of 17, as pmatrix_kernel writes them); ll: 2 x gridDim.x^2 x 6
 // words, zero at launch; brlen: initial lengths in, final lengths out; out[0] = lnL.
-// Dynamic shared memory: n_br x 64 doubles (matrices), n_br doubles (lengths), then the action list when
-// acts_smem != 0.
-template <bool ONE>
+// Dynamic shared memory: n_br (FIT) or n_sm_br x 64 doubles (matrices), n_br doubles (lengths), then the action list
+// when acts_smem != 0; spill_all: gridDim.x x (n_br - n_sm_br) x 64 doubles when not FIT.
+template <bool ONE, bool FIT>
 __global__ void __launch_bounds__(S1_THREADS)
-smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_passes, int n_rows, int n_br, int64_t Ppad,
+smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_passes, int n_rows, int n_br, int n_sm_br,
+               double *spill_all, int64_t Ppad,
                const unsigned char *__restrict__ codes, const unsigned int *__restrict__ masks,
                const double *__restrict__ weights, const ModelDev *__restrict__ model, const double *__restrict__ pmat,
                double *clv, int *scl, double *brlen, unsigned long long *ll, double *out, int acts_smem) {
@@ -239,8 +241,15 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
   const int n_tiles = (int)(Ppad / S1_TILE);
   const int pat = threadIdx.x / S1_SPLIT, half = threadIdx.x % S1_SPLIT;  // a pattern's threads are neighbouring lanes
   extern __shared__ __align__(16) unsigned char s1_dyn[];
+  // FIT: every branch's matrix is in shared memory.  Otherwise (trees of more than ~174 taxa) the first n_sm_br are,
+  // and the rest live in this block's own global region (L2): slower steps on those branches, still one launch.
   double *pm = reinterpret_cast<double *>(s1_dyn);  // [branch][r][k][j]
-  double *bl = pm + (size_t)n_br * 64;
+  double *bl = pm + (size_t)(FIT ? n_br : n_sm_br) * 64;
+  double *spill = FIT ? nullptr : spill_all + (size_t)blockIdx.x * (n_br - n_sm_br) * 64;
+  auto mat = [&](int b) -> double * {
+    if (FIT) return pm + b * 64;
+    return b < n_sm_br ? pm + b * 64 : spill + (size_t)(b - n_sm_br) * 64;
+  };
   const S1Act *alist = acts;
   if (acts_smem) {
     const int n_all = n_down + n_pass + 1;
@@ -250,7 +259,7 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
     alist = reinterpret_cast<const S1Act *>(d);
   }
   for (int e = threadIdx.x; e < n_br; e += S1_THREADS) bl[e] = brlen[e];
-  for (int e = threadIdx.x; e < n_br * 64; e += S1_THREADS) pm[e] = pmat[(e >> 6) * 68 + ((e >> 4) & 3) * 17 + (e & 15)];
+  for (int e = threadIdx.x; e < n_br * 64; e += S1_THREADS) mat(e >> 6)[e & 63] = pmat[(e >> 6) * 68 + ((e >> 4) & 3) * 17 + (e & 15)];
   if (threadIdx.x < 16) {
     mU[threadIdx.x] = model->U[threadIdx.x];          // [i][k]  (LIK_MAX_STATES-strided rows are not used: K = 4 packs them)
     mUinv[threadIdx.x] = model->Uinv[threadIdx.x];    // [k][j]
@@ -304,7 +313,7 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
   // vector update: dst = (P_pa a) o (P_pb b).  Everything it touches is the thread's own or read-only shared
   // memory: no block barrier.
   auto update = [&](const S1Act &op, const S1Pre &o, const double *px, const int *psc) {
-    const double *ma = pm + op.pa * 64 + half * (S1_R * 16), *mb = pm + op.pb * 64 + half * (S1_R * 16);
+    const double *ma = mat(op.pa) + half * (S1_R * 16), *mb = mat(op.pb) + half * (S1_R * 16);
     for (int tile = blockIdx.x; tile < (one ? (int)blockIdx.x + 1 : n_tiles); tile += gridDim.x) {
       const int64_t p = (int64_t)tile * S1_TILE + pat;
       double x[S1_E], v[S1_E];
@@ -445,7 +454,7 @@ smooth1_kernel(const S1Act *__restrict__ acts, int n_down, int n_pass, int max_p
       for (int k = 0; k < 4; k++) s += mU[i * 4 + k] * ex[r * 4 + k] * mUinv[k * 4 + j];
       s = fmax(s, 0.0);  // transition probabilities: round-off can leave -1e-17 at t ~ 0
       if (t_new == 0.0) s = (i == j) ? 1.0 : 0.0;  // a zero-length branch is the identity exactly
-      pm[op.branch * 64 + threadIdx.x] = s;
+      mat(op.branch)[threadIdx.x] = s;
     }
     if (threadIdx.x == 0) bl[op.branch] = t_new;
     __syncthreads();

@@ -345,7 +345,8 @@ def test_batched_smoother_fused_reorientation_is_bit_identical(monkeypatch):
 @pytest.mark.parametrize("n,S,signal,max_blocks", [(3, 200, True, 0), (4, 64, True, 0), (5, 300, True, 0), (9, 1500, True, 0),
                                                    (33, 2500, True, 0), (10, 12, False, 0), (10, 40, False, 0), (7, 25, False, 0),
                                                    (12, 55, False, 0), (9, 1500, True, 1), (33, 2500, True, 3), (14, 3000, False, 2),
-                                                   (150, 60, True, 0), (180, 60, True, 0)])
+                                                   (150, 60, True, 0), (180, 60, True, 0), (300, 200, True, 0),
+                                                   (200, 300, True, 1)])
 def test_single_launch_smoother_equals_host_loop(n, S, signal, max_blocks, monkeypatch):
     """The per-handle getLogLikelihood of a DNA tree -- ONE cooperative launch that walks the whole
     smoothing program with a grid barrier per Newton evaluation (pll_smooth1.cuh) -- against the literal
@@ -353,8 +354,8 @@ def test_single_launch_smoother_equals_host_loop(n, S, signal, max_blocks, monke
     random sequences on few sites, where the bad-curvature guard retries and the z clamps do the work;
     max_blocks caps the grid (PLG_S1_MAX_BLOCKS) so that a block walks several 128-pattern tiles, as on
     alignments too long for one co-resident tile per block; 150 taxa: the action list no longer fits
-    shared memory beside the matrices; 180 taxa: the matrices do not fit either and the handle takes the lockstep
-    program.  lnL, branch lengths, and the oracle at the
+    shared memory beside the matrices; 180 and more: the matrices do not all fit either, and the rest live in the
+    blocks' own global regions.  lnL, branch lengths, and the oracle at the
     returned lengths."""
     if max_blocks:
         monkeypatch.setenv("PLG_S1_MAX_BLOCKS", str(max_blocks))
